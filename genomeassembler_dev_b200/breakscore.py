@@ -1,0 +1,334 @@
+"""Host-side mirror of the upstream scorer interface over the C-ABI (include/breakscore.h).
+
+Upstream exports ``calc_breakscore(path, sequencing_reads, true_solution, kmer, bp_kmer,
+bp_prob)`` from ``lib/BreakageScorer.cpp:185-191`` to R through Rcpp and returns a named list
+(``:343-353``).  :func:`calc_breakscore` below has the same argument names, order and meaning
+and returns a dict with the same member names (plus the KS statistics the R driver computes
+from that list, ``lib/DeNovoAssembler.R:416-424``).  Everything is computed by
+``libbreakscore.so`` (CUDA, sm_100a); this module only flattens strings into the flat-buffer
+layout of the C-ABI.  There is no CPU path: if the library is missing or no B200 is visible
+the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_PKG, "libbreakscore.so")
+
+# flags (include/breakscore.h)
+WANT_PROB_DIST = 0x001
+WANT_KS = 0x002
+WANT_HIST = 0x004
+WANT_POS = 0x008
+WANT_STARTPOS = 0x010
+PLACE_SCAN = 0x100
+DEVICE_CHARS = 0x200
+DEVICE_RESULT = 0x400
+DEFAULT_FLAGS = WANT_PROB_DIST | WANT_KS | WANT_STARTPOS
+
+STAGES = ("h2d", "pack", "place", "score", "truth_spectrum", "prob_dist_ks", "ks_path_freq",
+          "startpos", "d2h")
+
+ABI_SYMBOLS = (
+    "bs_abi_version", "bs_ctx_create", "bs_ctx_destroy", "bs_last_error", "bs_ctx_set_stream",
+    "bs_ctx_synchronize", "bs_ctx_launch_count", "bs_ctx_enable_timing", "bs_ctx_last_timings",
+    "bs_ctx_last_place_ms", "bs_set_table", "bs_set_truth_table", "bs_score_batch", "bs_score",
+    "bs_host_alloc", "bs_host_free",
+)
+
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class BreakscoreError(RuntimeError):
+    """A non-zero status of the C-ABI (upstream analogue: Rcpp::stop)."""
+
+    def __init__(self, code, text):
+        super().__init__(f"breakscore error {code}: {text}")
+        self.code = code
+
+
+class _Batch(C.Structure):
+    _fields_ = [
+        ("n_segments", C.c_int64), ("n_reads", C.c_int64), ("n_contigs", C.c_int64),
+        ("read_chars", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_int32),
+        ("contig_chars", C.c_void_p), ("contig_off", C.c_void_p),
+        ("truth_chars", C.c_void_p), ("truth_off", C.c_void_p),
+        ("seg_read_start", C.c_void_p), ("seg_contig_start", C.c_void_p),
+    ]
+
+
+class _Result(C.Structure):
+    _fields_ = [
+        ("sequence_len", C.c_void_p), ("bp_score", C.c_void_p),
+        ("bp_score_norm_by_break_freqs", C.c_void_p), ("bp_score_norm_by_len", C.c_void_p),
+        ("kmer_breaks", C.c_void_p), ("path_prob_dist_startpos", C.c_void_p),
+        ("lev_dist_vs_true", C.c_void_p), ("ks_stat_prob_dist", C.c_void_p),
+        ("ks_stat_path_freq", C.c_void_p), ("path_prob_dist", C.c_void_p),
+        ("path_prob_dist_off", C.c_void_p), ("hist", C.c_void_p), ("pos", C.c_void_p),
+        ("pos_off", C.c_void_p),
+    ]
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """dlopen the C-ABI library and declare the prototypes of include/breakscore.h."""
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.bs_abi_version.restype = C.c_int
+    lib.bs_ctx_create.restype = C.c_int
+    lib.bs_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.bs_ctx_destroy.restype = None
+    lib.bs_ctx_destroy.argtypes = [C.c_void_p]
+    lib.bs_last_error.restype = C.c_char_p
+    lib.bs_last_error.argtypes = [C.c_void_p]
+    lib.bs_ctx_set_stream.restype = C.c_int
+    lib.bs_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bs_ctx_synchronize.restype = C.c_int
+    lib.bs_ctx_synchronize.argtypes = [C.c_void_p]
+    lib.bs_ctx_launch_count.restype = C.c_int64
+    lib.bs_ctx_launch_count.argtypes = [C.c_void_p]
+    lib.bs_ctx_enable_timing.restype = C.c_int
+    lib.bs_ctx_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.bs_ctx_last_timings.restype = C.c_int
+    lib.bs_ctx_last_timings.argtypes = [C.c_void_p, _f64p, C.c_int]
+    lib.bs_ctx_last_place_ms.restype = C.c_double
+    lib.bs_ctx_last_place_ms.argtypes = [C.c_void_p]
+    lib.bs_set_table.restype = C.c_int
+    lib.bs_set_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.bs_set_truth_table.restype = C.c_int
+    lib.bs_set_truth_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.bs_score_batch.restype = C.c_int
+    lib.bs_score_batch.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_int, C.c_uint32, C.POINTER(_Result)]
+    lib.bs_score.restype = C.c_int
+    lib.bs_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                             C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.POINTER(_Result)]
+    lib.bs_host_alloc.restype = C.c_void_p
+    lib.bs_host_alloc.argtypes = [C.c_int64]
+    lib.bs_host_free.restype = None
+    lib.bs_host_free.argtypes = [C.c_void_p]
+    if lib.bs_abi_version() != 1:
+        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 1")
+    return lib
+
+
+def flatten(strings):
+    """list of str / bytes -> (uint8 chars, int64 offsets[n+1])  (string i = chars[off[i]:off[i+1]])"""
+    bs = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        np.cumsum(np.fromiter((len(b) for b in bs), dtype=np.int64, count=len(bs)), out=off[1:])
+    chars = np.frombuffer(b"".join(bs), dtype=np.uint8) if off[-1] else np.zeros(1, np.uint8)
+    return chars, off
+
+
+def prob_dist_offsets(contig_off, kmer):
+    """where each contig's rolling-window vector goes: max(L_c - kmer + 1, 0) values each"""
+    lens = np.maximum(np.diff(np.asarray(contig_off, dtype=np.int64)) - kmer + 1, 0)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    return off
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class BreakageScorer:
+    """A device context with a resident probability table (bs_ctx of include/breakscore.h)."""
+
+    def __init__(self, device: int = 0, lib_path: str | None = None):
+        self._lib = load_library(lib_path)
+        self._ctx = C.c_void_p()
+        rc = self._lib.bs_ctx_create(device, C.byref(self._ctx))
+        if rc != 0:
+            text = self._lib.bs_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise BreakscoreError(rc, text)
+        self.device = device
+        self.n_table = 0
+        self._table_key = None
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.bs_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BreakscoreError(rc, self._lib.bs_last_error(self._ctx).decode())
+
+    # -- context controls ----------------------------------------------------------------
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._lib.bs_ctx_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.bs_ctx_synchronize(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bs_ctx_launch_count(self._ctx))
+
+    def enable_timing(self, on: bool = True):
+        self._check(self._lib.bs_ctx_enable_timing(self._ctx, 1 if on else 0))
+
+    def last_timings(self) -> dict:
+        ms = np.zeros(len(STAGES), np.float64)
+        n = self._lib.bs_ctx_last_timings(self._ctx, ms.ctypes.data_as(_f64p), len(STAGES))
+        return {STAGES[i]: float(ms[i]) for i in range(n)}
+
+    # -- table ---------------------------------------------------------------------------
+    def set_table(self, bp_kmer, bp_prob, truth_prob=None):
+        """bp_kmer / bp_prob of the upstream call (lib/BreakageScorer.cpp:194-197); truth_prob is
+        the table behind the truth-side distribution of the KS statistics (the R driver keeps the
+        real probabilities there in its "random" pass, lib/DeNovoAssembler.R:326-333)."""
+        prob = np.ascontiguousarray(bp_prob, dtype=np.float64)
+        if isinstance(bp_kmer, tuple) and len(bp_kmer) == 2 and isinstance(bp_kmer[0], np.ndarray):
+            chars, off = bp_kmer
+        else:
+            chars, off = flatten(bp_kmer)
+        if len(off) - 1 != len(prob):
+            raise ValueError(f"bp_kmer has {len(off) - 1} rows, bp_prob {len(prob)}")
+        self._check(self._lib.bs_set_table(self._ctx, _ptr(chars), _ptr(off), _ptr(prob), len(prob)))
+        self.n_table = len(prob)
+        if truth_prob is not None:
+            t = np.ascontiguousarray(truth_prob, dtype=np.float64)
+            self._check(self._lib.bs_set_truth_table(self._ctx, _ptr(t), len(t)))
+        else:
+            self._check(self._lib.bs_set_truth_table(self._ctx, None, 0))
+
+    # -- scoring -------------------------------------------------------------------------
+    def score_batch(self, read_chars, read_off, read_len, contig_chars, contig_off, truth_chars,
+                    truth_off, seg_read_start, seg_contig_start, kmer=8, flags=DEFAULT_FLAGS):
+        """Many independent segments in one call (one upstream calc_breakscore call each).
+        Host numpy buffers in, dict of numpy arrays out (flat path_prob_dist + offsets)."""
+        contig_off = np.ascontiguousarray(contig_off, dtype=np.int64)
+        truth_off = np.ascontiguousarray(truth_off, dtype=np.int64)
+        srs = np.ascontiguousarray(seg_read_start, dtype=np.int64)
+        scs = np.ascontiguousarray(seg_contig_start, dtype=np.int64)
+        read_chars = np.ascontiguousarray(read_chars, dtype=np.uint8)
+        contig_chars = np.ascontiguousarray(contig_chars, dtype=np.uint8)
+        truth_chars = np.ascontiguousarray(truth_chars, dtype=np.uint8)
+        if read_off is not None:
+            read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        S, N, Cn = len(truth_off) - 1, int(srs[-1]), int(scs[-1])
+        b = _Batch(S, N, Cn, read_chars.ctypes.data, None if read_off is None else read_off.ctypes.data,
+                   int(read_len or 0), contig_chars.ctypes.data, contig_off.ctypes.data,
+                   truth_chars.ctypes.data, truth_off.ctypes.data, srs.ctypes.data, scs.ctypes.data)
+        out = {
+            "sequence_len": np.zeros(Cn, np.int32),
+            "bp_score": np.zeros(Cn, np.float64),
+            "bp_score_norm_by_break_freqs": np.zeros(Cn, np.float64),
+            "bp_score_norm_by_len": np.zeros(Cn, np.float64),
+            "kmer_breaks": np.zeros(Cn, np.int32),
+            "lev_dist_vs_true": np.zeros(Cn, np.int32),
+            "path_prob_dist_startpos": np.zeros(Cn, np.int32),
+        }
+        r = _Result()
+        for k, v in out.items():
+            setattr(r, k, v.ctypes.data)
+        keep = [read_chars, contig_chars, truth_chars, read_off, contig_off, truth_off, srs, scs]
+        if flags & WANT_KS:
+            out["ks_stat_prob_dist"] = np.zeros(Cn, np.float64)
+            out["ks_stat_path_freq"] = np.zeros(Cn, np.float64)
+            r.ks_stat_prob_dist = out["ks_stat_prob_dist"].ctypes.data
+            r.ks_stat_path_freq = out["ks_stat_path_freq"].ctypes.data
+        if flags & WANT_PROB_DIST:
+            pd_off = prob_dist_offsets(contig_off, kmer)
+            out["path_prob_dist_flat"] = np.zeros(max(int(pd_off[-1]), 1), np.float64)
+            out["path_prob_dist_off"] = pd_off
+            r.path_prob_dist = out["path_prob_dist_flat"].ctypes.data
+            r.path_prob_dist_off = pd_off.ctypes.data
+        if flags & WANT_HIST:
+            out["hist"] = np.zeros((Cn, self.n_table + 1), np.int32)
+            r.hist = out["hist"].ctypes.data
+        if flags & WANT_POS:
+            nr_of_contig = np.repeat(np.diff(srs), np.diff(scs))
+            pos_off = np.zeros(Cn + 1, np.int64)
+            np.cumsum(nr_of_contig, out=pos_off[1:])
+            out["pos_flat"] = np.zeros(max(int(pos_off[-1]), 1), np.int32)
+            out["pos_off"] = pos_off
+            r.pos = out["pos_flat"].ctypes.data
+            r.pos_off = pos_off.ctypes.data
+        self._check(self._lib.bs_score_batch(self._ctx, C.byref(b), int(kmer), int(flags), C.byref(r)))
+        del keep
+        return out
+
+    def score_batch_raw(self, batch: _Batch, result: _Result, kmer: int, flags: int):
+        """Thin call for callers that manage their own (possibly device) buffers: bench.py."""
+        self._check(self._lib.bs_score_batch(self._ctx, C.byref(batch), int(kmer), int(flags), C.byref(result)))
+
+    def score(self, path, sequencing_reads, true_solution, kmer=8, flags=DEFAULT_FLAGS):
+        """One segment; returns the upstream list (lib/BreakageScorer.cpp:343-353) as a dict."""
+        ct, ct_off = flatten(path)
+        if isinstance(sequencing_reads, np.ndarray) and sequencing_reads.ndim == 2:
+            rd = np.ascontiguousarray(sequencing_reads, dtype=np.uint8).reshape(-1)
+            rd_off, rlen, nr = None, sequencing_reads.shape[1], sequencing_reads.shape[0]
+        else:
+            rd, rd_off = flatten(sequencing_reads)
+            rlen, nr = 0, len(sequencing_reads)
+        tr, tr_off = flatten([true_solution])
+        res = self.score_batch(rd, rd_off, rlen, ct, ct_off, tr, tr_off, [0, nr], [0, len(path)],
+                               kmer=kmer, flags=flags)
+        res["sequence"] = list(path)
+        if flags & WANT_PROB_DIST:
+            flat, off = res.pop("path_prob_dist_flat"), res.pop("path_prob_dist_off")
+            res["path_prob_dist"] = [flat[off[i]:off[i + 1]] for i in range(len(path))]
+        if flags & WANT_POS:
+            flat = res.pop("pos_flat")
+            res.pop("pos_off")
+            res["pos"] = flat[:len(path) * nr].reshape(len(path), nr)
+        return res
+
+
+_default = {}
+
+
+def default_scorer(device: int = 0, lib_path: str | None = None) -> BreakageScorer:
+    """Process-lifetime context per device (the Rcpp glue keeps the same kind of singleton)."""
+    key = (device, lib_path or DEFAULT_LIB)
+    if key not in _default:
+        _default[key] = BreakageScorer(device, lib_path)
+    return _default[key]
+
+
+def calc_breakscore(path, sequencing_reads, true_solution, kmer, bp_kmer, bp_prob, *,
+                    truth_prob=None, flags=DEFAULT_FLAGS, device=0, lib_path=None):
+    """Drop-in for the upstream export (lib/BreakageScorer.cpp:185-191), same argument list.
+
+    Returns a dict with the upstream list members ``sequence, sequence_len, bp_score,
+    bp_score_norm_by_break_freqs, bp_score_norm_by_len, kmer_breaks, lev_dist_vs_true,
+    path_prob_dist_startpos, path_prob_dist`` and, with WANT_KS, ``ks_stat_prob_dist`` /
+    ``ks_stat_path_freq`` (the statistic of lib/DeNovoAssembler.R:416-424 for the two variants
+    of the per-contig vector).  ``lev_dist_vs_true`` is not computed (edlib, off the path): 0.
+    """
+    sc = default_scorer(device, lib_path)
+    prob = np.ascontiguousarray(bp_prob, dtype=np.float64)
+    tprob = None if truth_prob is None else np.ascontiguousarray(truth_prob, dtype=np.float64)
+    names = ",".join(k if isinstance(k, str) else bytes(k).decode("ascii") for k in bp_kmer)
+    key = (names, prob.tobytes(), None if tprob is None else tprob.tobytes())
+    if sc._table_key != key:
+        sc.set_table(bp_kmer, prob, tprob)
+        sc._table_key = key
+    return sc.score(path, sequencing_reads, true_solution, kmer=kmer, flags=flags)

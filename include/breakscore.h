@@ -1,0 +1,152 @@
+/*
+ * breakscore.h -- C-ABI of the B200-native breakage scorer.
+ *
+ * Drop-in boundary for ONE path of SahakyanLab/GenomeAssembler_dev: the Rcpp-exported
+ *     Rcpp::List calc_breakscore(path, sequencing_reads, true_solution, kmer, bp_kmer, bp_prob)
+ * of upstream lib/BreakageScorer.cpp:185-191 (called from lib/DeNovoAssembler.R:348-355).
+ * The entry points below are what an Rcpp / ctypes / cgo binding for that path binds; every
+ * argument is a plain pointer or size, strings travel as flat buffers + offsets
+ * (string i of a set = chars[off[i] .. off[i+1])).  The library links cudart only: no torch,
+ * no Python, no R.  There is NO CPU fallback: without a usable sm_100 GPU, bs_ctx_create fails.
+ *
+ * Upstream item replaced                              | entry point
+ * ----------------------------------------------------+-----------------------------------------
+ * bp_matrix build, lib/BreakageScorer.cpp:194-197     | bs_set_table
+ * kmer_from_seq table, lib/GenerateReads.R:243-259    | bs_set_truth_table (KS y-side)
+ * calc_breakscore body, lib/BreakageScorer.cpp:200-353| bs_score (one segment) / bs_score_batch
+ * ks.test statistic, lib/DeNovoAssembler.R:416-424    | BS_WANT_KS outputs of the same calls
+ * Rcpp::stop / R error                                | int status + bs_last_error
+ */
+#ifndef BREAKSCORE_H
+#define BREAKSCORE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BS_ABI_VERSION 1
+
+/* the library is built with -fvisibility=hidden: only these entry points are exported */
+#if defined(__GNUC__)
+#define BS_API __attribute__((visibility("default")))
+#else
+#define BS_API
+#endif
+
+typedef struct bs_ctx bs_ctx;
+
+/* status codes (0 = ok).  Nothing throws across this boundary. */
+enum {
+    BS_OK = 0,
+    BS_ERR_INVALID = 1,   /* bad argument (NULL pointer, negative size, offsets not monotone ...) */
+    BS_ERR_CUDA = 2,      /* a CUDA runtime call failed; bs_last_error has the text */
+    BS_ERR_TABLE = 3,     /* table key outside the supported domain (ACGT, length 1..8) */
+    BS_ERR_ALLOC = 4,     /* host or device allocation failed */
+    BS_ERR_NO_DEVICE = 5, /* no usable GPU: there is no CPU fallback */
+    BS_ERR_STATE = 6      /* e.g. scoring before bs_set_table */
+};
+
+/* flags of bs_score / bs_score_batch */
+#define BS_WANT_PROB_DIST 0x001u /* fill path_prob_dist (lib/BreakageScorer.cpp:200-215,352) */
+#define BS_WANT_KS        0x002u /* fill ks_stat_prob_dist and ks_stat_path_freq */
+#define BS_WANT_HIST      0x004u /* fill hist: dense per-contig break-k-mer counts (parity/debug) */
+#define BS_WANT_POS       0x008u /* fill pos: leftmost match of every read in every contig (parity/debug) */
+#define BS_WANT_STARTPOS  0x010u /* fill path_prob_dist_startpos (lib/BreakageScorer.cpp:273-274) */
+#define BS_PLACE_SCAN     0x100u /* placement by exhaustive scan instead of the seed index (same results) */
+#define BS_DEVICE_CHARS   0x200u /* read_chars / contig_chars / truth_chars are DEVICE pointers */
+#define BS_DEVICE_RESULT  0x400u /* every non-NULL pointer in bs_result is a DEVICE pointer */
+#define BS_DEFAULT_FLAGS (BS_WANT_PROB_DIST | BS_WANT_KS | BS_WANT_STARTPOS)
+
+/*
+ * Input of a scoring call: n_segments independent experiments (upstream: one calc_breakscore
+ * call each).  Segment s owns reads [seg_read_start[s], seg_read_start[s+1]) and contigs
+ * [seg_contig_start[s], seg_contig_start[s+1]) and the truth string s.
+ * All offset / start arrays are HOST memory (metadata).  The three char buffers are host
+ * memory unless BS_DEVICE_CHARS is set.
+ * Reads: if read_off == NULL every read has read_len bytes and read_chars is dense
+ * (read i at i*read_len); otherwise read_off[n_reads+1] gives arbitrary lengths.
+ */
+typedef struct {
+    int64_t n_segments;
+    int64_t n_reads;
+    int64_t n_contigs;
+    const char *read_chars;
+    const int64_t *read_off; /* may be NULL (uniform length) */
+    int32_t read_len;        /* used when read_off == NULL */
+    const char *contig_chars;
+    const int64_t *contig_off;       /* [n_contigs+1] */
+    const char *truth_chars;
+    const int64_t *truth_off;        /* [n_segments+1] */
+    const int64_t *seg_read_start;   /* [n_segments+1] */
+    const int64_t *seg_contig_start; /* [n_segments+1] */
+} bs_batch;
+
+/*
+ * Output of a scoring call; arrays are caller-allocated, any pointer may be NULL, all are in
+ * input contig order (upstream keeps input order: lib/BreakageScorer.cpp:308-315).
+ * Names follow the upstream R list (lib/BreakageScorer.cpp:343-353).
+ */
+typedef struct {
+    int32_t *sequence_len;                  /* [C] */
+    double *bp_score;                       /* [C] sum prob*count               (:286-287) */
+    double *bp_score_norm_by_break_freqs;   /* [C] sum prob*(count/total)       (:290-292) */
+    double *bp_score_norm_by_len;           /* [C] bp_score / sequence_len      (:302-303) */
+    int32_t *kmer_breaks;                   /* [C] total_breaks                 (:298)     */
+    int32_t *path_prob_dist_startpos;       /* [C] truth.find(contig) if any read hit else 0 */
+    int32_t *lev_dist_vs_true;              /* [C] NOT computed by this library (edlib, off the path): filled with 0 */
+    double *ks_stat_prob_dist;              /* [C] KS(path_prob_dist, truth window probabilities) */
+    double *ks_stat_path_freq;              /* [C] KS(count/total over table rows, same y); NaN if no breaks */
+    double *path_prob_dist;                 /* flat; contig c at path_prob_dist_off[c], max(L_c-kmer+1,0) values */
+    const int64_t *path_prob_dist_off;      /* HOST [C+1], required with BS_WANT_PROB_DIST */
+    int32_t *hist;                          /* [C][T+1], row-major; bin T = key not in table */
+    int32_t *pos;                           /* contig c: n_reads(segment of c) entries at pos_off[c]; -1 = no match */
+    const int64_t *pos_off;                 /* HOST [C+1], required with BS_WANT_POS */
+} bs_result;
+
+/* context: owns the device, a stream, the resident tables and grow-only work buffers */
+BS_API int bs_ctx_create(int device, bs_ctx **out);
+BS_API void bs_ctx_destroy(bs_ctx *ctx);
+/* last error text of ctx (or of the last failed bs_ctx_create when ctx == NULL) */
+BS_API const char *bs_last_error(const bs_ctx *ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL = the context's own stream */
+BS_API int bs_ctx_set_stream(bs_ctx *ctx, void *cuda_stream);
+/* block until everything queued by this context has finished */
+BS_API int bs_ctx_synchronize(bs_ctx *ctx);
+/* number of kernel launches issued by this context so far */
+BS_API int64_t bs_ctx_launch_count(const bs_ctx *ctx);
+/* per-stage CUDA-event timing (off by default).  bs_ctx_last_timings blocks on the stream and
+ * writes up to n stage times (ms, -1 = stage did not run) of the last scoring call, in the order
+ * h2d, pack, place, score, truth_spectrum, prob_dist_ks, ks_path_freq, startpos, d2h; returns
+ * how many it wrote. */
+#define BS_N_STAGES 9
+BS_API int bs_ctx_enable_timing(bs_ctx *ctx, int on);
+BS_API int bs_ctx_last_timings(bs_ctx *ctx, double *ms, int n);
+/* device-event time (ms) of the placement kernel of the last scoring call, -1 if none */
+BS_API double bs_ctx_last_place_ms(bs_ctx *ctx);
+
+/* scoring table: n (k-mer, probability) pairs.  Keys: ACGT strings of length 1..8; a repeated
+ * key overrides the earlier row (map assignment, lib/BreakageScorer.cpp:195-197). */
+BS_API int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, const double *prob, int64_t n);
+/* probabilities used for the truth-side distribution of the KS statistics (same keys/rows as the
+ * scoring table).  prob == NULL: follow the scoring table. */
+BS_API int bs_set_truth_table(bs_ctx *ctx, const double *prob, int64_t n);
+
+BS_API int bs_score_batch(bs_ctx *ctx, const bs_batch *batch, int kmer, uint32_t flags, bs_result *result);
+
+/* one segment, the upstream argument list flattened */
+BS_API int bs_score(bs_ctx *ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
+             const char *read_chars, const int64_t *read_off, int64_t n_reads,
+             const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *result);
+
+/* pinned host memory for staging buffers (cudaHostAlloc / cudaFreeHost) */
+BS_API void *bs_host_alloc(int64_t bytes);
+BS_API void bs_host_free(void *p);
+
+BS_API int bs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BREAKSCORE_H */
