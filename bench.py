@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Benchmark of the breakage-scoring hot path (BASELINE.json metric: reads scored/s and
+read x contig Gbp compared/s; % of HBM peak).
+
+A "step" is one pass of the hot path over one batch: the cfg-2 study of BASELINE.json
+(`--segments` synthetic 50 kb segments, 150 bp reads at 30x, velvet-style contig sets) scored by ONE
+bs_score_batch call per rank with the upstream default outputs (scores, kmer_breaks, startpos,
+path_prob_dist, KS statistics).  Ranks own disjoint studies (weak scaling: segments are independent
+units, no data-path collective; per-contig score records are gathered to rank 0 over NCCL).
+
+  value     whole-job Gbp/s, inputs already resident in HBM (device pointers through the C-ABI)
+  e2e       the same metric through the C-ABI with HOST buffers: H2D of the ASCII inputs and D2H of
+            every result array inside the timed region
+  roofline  placement kernel: algorithmic bytes ((8*W_r+4) B per (unique read, contig)
+            pair) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the UNMODIFIED upstream calc_breakscore (oracle/_ref, edit distance
+            stubbed: off the scored path) on the box's host cores, one process per core over
+            disjoint segments of the same workload (bounded sample)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from genomeassembler_dev_b200 import synth, tables  # noqa: E402
+
+METRIC = "read_x_contig_Gbp_compared_per_s"
+UNIT = "Gbp/s"
+SEED = 1234
+LENGTH, READ_LEN, COVERAGE = 50_000, 150, 30.0
+
+
+def workload_name(n_segments):
+    return (f"cfg2: {n_segments} synthetic 50 kb segments per GPU, 150 bp reads 30x, velvet-style contig sets "
+            f"(5-60 contigs/segment, 10% mutated), kmer=8, real breakage table")
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm (test/bench infrastructure: oracle/_ref = unmodified upstream code)
+# ------------------------------------------------------------------------------------------
+
+def _ref_task(args):
+    seeds, use_ref = args
+    from oracle import loader as O
+    kmers = tables.all_kmer_strings()
+    prob = tables.normalised(tables.load_raw())
+    p8 = tables.sub_table(prob, 8)
+    segs = []
+    for s in seeds:
+        rng = np.random.default_rng(s)
+        nct = int(rng.integers(5, 61))
+        segs.append(synth.make_segment(s, LENGTH, READ_LEN, COVERAGE, nct, p8))
+    reads = [sg.read_list for sg in segs]
+    t0 = time.perf_counter()
+    pair = 0.0
+    nreads = 0
+    for sg, rl in zip(segs, reads):
+        if use_ref:
+            O.ref_calc_breakscore(sg.contigs, rl, sg.truth, 8, kmers, prob, edit_distance=False)
+        else:
+            O.oracle_calc_breakscore(sg.contigs, rl, sg.truth, 8, kmers, prob, want_ks=False)
+        pair += len(rl) * float(sum(len(c) for c in sg.contigs))
+        nreads += len(rl)
+    return time.perf_counter() - t0, pair, nreads
+
+
+def run_cpu_reference(n_segments_sample, cores, seed0=SEED):
+    """one process per core, disjoint segments; returns (Gbp/s, reads/s, seconds, kind)"""
+    import multiprocessing as mp
+    from oracle import loader as O
+    O.build()
+    use_ref = O.have_ref()
+    seeds = [seed0 + i for i in range(n_segments_sample)]
+    chunks = [seeds[i::cores] for i in range(cores) if seeds[i::cores]]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(chunks)) as pool:
+        res = pool.map(_ref_task, [(c, use_ref) for c in chunks])
+    wall_all = time.perf_counter() - t0
+    t = max(r[0] for r in res)  # scoring time of the slowest process (generation excluded)
+    pair = sum(r[1] for r in res)
+    nreads = sum(r[2] for r in res)
+    return pair / 1e9 / t, nreads / t, t, ("reference" if use_ref else "port"), wall_all
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8)
+    for _ in range(args.warmup):
+        run_cpu_reference(min(per_step, cores), cores)
+    tot_pair, tot_reads, tot_t = 0.0, 0.0, 0.0
+    kind = "reference"
+    for k in range(args.steps):
+        gbps, rps, t, kind, _ = run_cpu_reference(per_step, cores, seed0=SEED + k * per_step)
+        tot_pair += gbps * t
+        tot_reads += rps * t
+        tot_t += t
+    value = tot_pair / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 compare / int32 count / f64 sums",
+        "data": "synthetic", "reads_scored_per_s": tot_reads / tot_t,
+        "config": {"workload": workload_name(args.segments), "sample_per_step": f"{per_step} segments of that workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{per_step} segments per step, one process per core, unmodified upstream "
+                                   f"calc_breakscore (edlib stubbed)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mhz.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+# ------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(batch, unique_reads_per_seg, flags, T, B):
+    """B_alg = sum_seg U*C*(8*W_r+4) + sum_c [8*ceil(L_c/32) + 8*(L_c-7)*[pd] + 48] + 8T"""
+    W = (batch.read_len + 31) // 32
+    ncs = np.diff(batch.seg_contig_start).astype(np.float64)
+    pair_bytes = float((unique_reads_per_seg * ncs).sum()) * (8 * W + 4)
+    lens = np.diff(batch.contig_off).astype(np.float64)
+    per_contig = float((8 * np.ceil(lens / 32)).sum()) + 48.0 * len(lens)
+    if flags & B.WANT_PROB_DIST:
+        per_contig += float((8 * np.maximum(lens - 7, 0)).sum())
+    return pair_bytes, per_contig + 8.0 * T
+
+
+def unique_reads_per_segment(batch):
+    out = np.zeros(batch.n_segments, dtype=np.float64)
+    rl = batch.read_len
+    for s in range(batch.n_segments):
+        r0, r1 = int(batch.seg_read_start[s]), int(batch.seg_read_start[s + 1])
+        rows = batch.read_chars[r0 * rl:r1 * rl].reshape(-1, rl)
+        out[s] = len(np.unique(np.ascontiguousarray(rows).view(np.dtype((np.void, rl)))))
+    return out
+
+
+def b200_main(args):
+    import torch
+    import torch.distributed as dist
+
+    from genomeassembler_dev_b200 import breakscore as B
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        # before CUDA is initialised (fork); bounded sample: one segment per host core
+        cores = os.cpu_count() or 1
+        n_sample = max(cores, 8)
+        gbps, rps, t, kind, _ = run_cpu_reference(n_sample, cores)
+        cpu_base = {"value": gbps, "unit": UNIT, "cores": cores, "kind": kind, "reads_scored_per_s": rps,
+                    "seconds": t,
+                    "sample": f"{n_sample} segments of the workload, one process per core, unmodified upstream "
+                              f"calc_breakscore (edlib stubbed: off the scored path)"}
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; there is no CPU fallback for the scorer")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    # ---- inputs: this rank's study ----
+    batch = synth.make_batch(args.segments, seed=SEED + rank * args.segments, length=LENGTH, read_len=READ_LEN,
+                             coverage=COVERAGE)
+    kmers = tables.all_kmer_strings()
+    prob = tables.normalised(tables.load_raw())
+    sc = B.BreakageScorer(local)
+    sc.set_table(kmers, prob)
+    stream = torch.cuda.current_stream()
+    sc.set_stream(stream.cuda_stream)
+    flags = B.DEFAULT_FLAGS
+    Cn, N, S = batch.n_contigs, batch.n_reads, batch.n_segments
+    pd_off = B.prob_dist_offsets(batch.contig_off, 8)
+    pair_bases = batch.pair_bases()
+
+    # device-resident inputs and outputs
+    d_reads = torch.from_numpy(batch.read_chars).to(dev)
+    d_ctgs = torch.from_numpy(batch.contig_chars).to(dev)
+    d_truth = torch.from_numpy(batch.truth_chars).to(dev)
+    d_i32 = torch.zeros(4, Cn, dtype=torch.int32, device=dev)
+    d_f64 = torch.zeros(5, Cn, dtype=torch.float64, device=dev)
+    d_pd = torch.zeros(max(int(pd_off[-1]), 1), dtype=torch.float64, device=dev)
+
+    def make_batch_struct(rc, cc, tc):
+        return B._Batch(S, N, Cn, rc, None, batch.read_len, cc, batch.contig_off.ctypes.data, tc,
+                        batch.truth_off.ctypes.data, batch.seg_read_start.ctypes.data, batch.seg_contig_start.ctypes.data)
+
+    def make_result_struct(i32_ptrs, f64_ptrs, pd_ptr):
+        r = B._Result()
+        r.sequence_len, r.kmer_breaks, r.path_prob_dist_startpos, r.lev_dist_vs_true = i32_ptrs
+        (r.bp_score, r.bp_score_norm_by_break_freqs, r.bp_score_norm_by_len, r.ks_stat_prob_dist,
+         r.ks_stat_path_freq) = f64_ptrs
+        r.path_prob_dist = pd_ptr
+        r.path_prob_dist_off = pd_off.ctypes.data
+        return r
+
+    db = make_batch_struct(d_reads.data_ptr(), d_ctgs.data_ptr(), d_truth.data_ptr())
+    dr = make_result_struct([d_i32[i].data_ptr() for i in range(4)], [d_f64[i].data_ptr() for i in range(5)], d_pd.data_ptr())
+    dflags = flags | B.DEVICE_CHARS | B.DEVICE_RESULT
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def gather_records():
+        # the path's one exchange: fixed-width per-contig records to rank 0 (NCCL gather over NVLink)
+        if world > 1:
+            out = [torch.empty_like(d_f64) for _ in range(world)] if rank == 0 else None
+            dist.gather(d_f64, out, dst=0)
+
+    def step_device():
+        sc.score_batch_raw(db, dr, 8, dflags)
+        gather_records()
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    sc.enable_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = sc.launch_count
+    stage_ms = {k: 0.0 for k in B.STAGES}
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+        for k, v in sc.last_timings().items():  # CUDA events on the launching stream, per stage
+            if v > 0:
+                stage_ms[k] += v
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = sc.launch_count - launches0
+    clocks = sampler.stop()
+    sc.enable_timing(False)
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    totals = torch.tensor([pair_bases, float(N)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM)
+    ms_total = float(t_ms.item())
+    all_pair, all_reads = float(totals[0].item()), float(totals[1].item())
+    ms_per_step = ms_total / args.steps
+    value = all_pair / 1e9 / (ms_per_step / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI (pinned), H2D + D2H inside the timed region ----
+    def pinned_copy(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+
+    h_reads, h_ctgs, h_truth = pinned_copy(batch.read_chars), pinned_copy(batch.contig_chars), pinned_copy(batch.truth_chars)
+    h_i32 = torch.zeros(4, Cn, dtype=torch.int32).pin_memory()
+    h_f64 = torch.zeros(5, Cn, dtype=torch.float64).pin_memory()
+    h_pd = torch.zeros(max(int(pd_off[-1]), 1), dtype=torch.float64).pin_memory()
+    hb = make_batch_struct(h_reads.data_ptr(), h_ctgs.data_ptr(), h_truth.data_ptr())
+    hr = make_result_struct([h_i32[i].data_ptr() for i in range(4)], [h_f64[i].data_ptr() for i in range(5)], h_pd.data_ptr())
+    h2d = int(h_reads.numel() + h_ctgs.numel() + h_truth.numel())
+    d2h = int(h_i32[:3].numel() * 4 + h_f64.numel() * 8 + h_pd.numel() * 8)
+
+    def step_host():
+        sc.score_batch_raw(hb, hr, 8, flags)  # returns with every result on the host
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e.item())
+    e2e_value = all_pair / 1e9 / (e2e_s / args.steps)
+    # device-resident and host paths must agree bit for bit
+    same = bool(torch.equal(d_f64.cpu().nan_to_num(nan=-1.0), h_f64.nan_to_num(nan=-1.0)) and
+                torch.equal(d_i32[:3].cpu(), h_i32[:3]))
+
+    # ---- roofline of the placement kernel ----
+    peak, peak_src = measured_peak()
+    uniq = unique_reads_per_segment(batch)
+    pair_bytes, other_bytes = algorithmic_bytes(batch, uniq, flags, len(prob), B)
+    place_ms = stage_ms["place"] / args.steps
+    achieved = pair_bytes / (place_ms / 1e3) / 1e9 if place_ms > 0 else None
+    roofline = {
+        "kernel": "k_place", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": pair_bytes, "ms_per_launch": place_ms,
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+        "note": "algorithmic bytes = (8*W_r+4) B x unique (read, contig) pairs of the all-pairs formulation "
+                "(SURVEY.md 8d); the seed-index placement kernel keeps reads in L2 and touches far fewer DRAM bytes",
+    }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 compare / int32 count / f64 sums", "data": "synthetic",
+            "reads_scored_per_s": all_reads / (ms_per_step / 1e3),
+            "config": {"workload": workload_name(args.segments), "segments_per_gpu": args.segments,
+                       "reads_per_gpu": N, "contigs_per_gpu": Cn, "outputs": "scores+kmer_breaks+startpos+path_prob_dist+KS",
+                       "l2": "inputs per step (%.0f MB ASCII) exceed the 126 MB L2; no flush" % (h2d / 1e6),
+                       "parallelism": f"segments sharded over {world} GPU(s), NCCL gather of score records"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "matches_device_resident_run": same},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        }
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    sc.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--segments", type=int, default=1000, help="segments per GPU (cfg-2 study size: 1000)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        return reference_main(args)
+    return b200_main(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

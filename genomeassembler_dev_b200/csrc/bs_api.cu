@@ -79,7 +79,7 @@ struct bs_ctx {
     bool meta_pending = false;
     DevBuf d_meta, d_read_chars, d_read_off, d_ctg_chars, d_tr_chars;
     DevBuf d_rwords, d_rflags, d_cwords, d_cmask, d_twords, d_tmask;
-    DevBuf d_w, d_total, d_ycnt, d_scratch, d_ovf, d_status;
+    DevBuf d_w, d_total, d_ycnt, d_scratch, d_ovf, d_status, d_rank_scratch;
     DevBuf d_out_i32, d_out_f64, d_pd, d_hist, d_pos;
 
     // timing
@@ -286,7 +286,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
                       &ctx->ks.lt_idx, &ctx->ks.yv, &ctx->d_meta, &ctx->d_read_chars, &ctx->d_read_off,
                       &ctx->d_ctg_chars, &ctx->d_tr_chars, &ctx->d_rwords, &ctx->d_rflags, &ctx->d_cwords,
                       &ctx->d_cmask, &ctx->d_twords, &ctx->d_tmask, &ctx->d_w, &ctx->d_total, &ctx->d_ycnt,
-                      &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status, &ctx->d_out_i32, &ctx->d_out_f64,
+                      &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status, &ctx->d_rank_scratch, &ctx->d_out_i32, &ctx->d_out_f64,
                       &ctx->d_pd, &ctx->d_hist, &ctx->d_pos};
     for (DevBuf *b : bufs) release(*b);
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
@@ -724,11 +724,19 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
         pa.R_x = ks_a ? k.R_x : 0; pa.R_y = ks_a ? k.R_y : 0; pa.rank_zero = ks_a ? k.rank_zero : 0;
         pa.kmer = kmer; pa.n_contigs = C;
         pa.prob_dist = o_pd; pa.pd_off = d_pd_off; pa.ks = ks_a ? o_ksa : nullptr;
-        const size_t smem = bs::probdist_smem_bytes(pa.R_x, kKsThreads, ks_a);
-        if (smem > ctx->smem_optin) return fail(ctx, BS_ERR_INVALID, "KS rank histogram needs %zu bytes of shared memory", smem);
+        // rank histogram: shared memory when it fits (real table: 32 897 ranks = 129 KB), else a
+        // per-block global scratch that stays in L2 (all-distinct tables: 65 537 ranks)
+        bool in_smem = ks_a && bs::probdist_smem_bytes(pa.R_x, kKsThreads, true) + 1024 <= ctx->smem_optin;
+        const size_t smem = bs::probdist_smem_bytes(pa.R_x, kKsThreads, in_smem);
         BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int per_sm = ks_a ? std::max<int>(1, (int)(ctx->smem_optin / (smem + 1024))) : 2;
-        BS_LAUNCH(bs::k_prob_dist_ks, (unsigned)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm), kKsThreads, smem, st, pa);
+        const int per_sm = in_smem ? std::max<int>(1, (int)(ctx->smem_optin / (smem + 1024))) : 2;
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm);
+        pa.rank_scratch = nullptr;
+        if (ks_a && !in_smem) {
+            if ((rc = ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * pa.R_x * 4))) return rc;
+            pa.rank_scratch = (int32_t *)ctx->d_rank_scratch.p;
+        }
+        BS_LAUNCH(bs::k_prob_dist_ks, (unsigned)nblk, kKsThreads, smem, st, pa);
         ctx->launches++;
     }
     if (want_ks && o_ksb) {

@@ -452,10 +452,11 @@ struct ProbDistArgs {
     double *prob_dist;       // optional
     const int64_t *pd_off;
     double *ks;              // optional [C]
+    int32_t *rank_scratch;   // [gridDim][R_x] global rank histogram when R_x does not fit shared memory, else NULL
 };
 
-BS_HD size_t probdist_smem_bytes(int R_x, int nthr, bool want_ks) {
-    return (want_ks ? (size_t)R_x * 4 : 0) + (size_t)nthr * 8 + 16;
+BS_HD size_t probdist_smem_bytes(int R_x, int nthr, bool hist_in_smem) {
+    return (hist_in_smem ? (size_t)R_x * 4 : 0) + (size_t)nthr * 8 + 16;
 }
 
 __global__ void k_prob_dist_ks(ProbDistArgs a) {
@@ -463,7 +464,7 @@ __global__ void k_prob_dist_ks(ProbDistArgs a) {
     unsigned char *sm = bs_dyn_smem();
     double *s_red = (double *)sm;
     int64_t *s_scan = (int64_t *)sm;  // same storage, used at different times
-    int32_t *s_hist = (int32_t *)(sm + (size_t)nthr * 8);
+    int32_t *s_hist = a.rank_scratch ? a.rank_scratch + (int64_t)blockIdx.x * a.R_x : (int32_t *)(sm + (size_t)nthr * 8);
     const bool want_ks = a.ks != nullptr;
     const int doff = (a.kmer >= 1 && a.kmer <= MAXK) ? dense_offset(a.kmer) : 0;
     for (int64_t c = blockIdx.x; c < a.n_contigs; c += gridDim.x) {

@@ -1,0 +1,65 @@
+"""The DEVICE ALGORITHM (the same kernel sources, compiled against tests/emul/cuda_emul.h) checked
+against the oracle and the reference vectors on machines without a GPU.  This is not the product
+path -- the GPU tests (test_gpu_parity.py) run the nvcc build through the same C-ABI."""
+import numpy as np
+import pytest
+
+import parity_cases as P
+from conftest import load_ref_vectors
+from genomeassembler_dev_b200 import breakscore as B
+from genomeassembler_dev_b200 import tables
+
+CASES = [c for c in load_ref_vectors() if c["table"] in ("real", "rowid")]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_reference_vectors(case, emul_scorer, kmers, table_set):
+    P.check_reference_vector(emul_scorer, case, kmers, table_set)
+
+
+@pytest.mark.parametrize("params", P.SMALL, ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL])
+@pytest.mark.parametrize("scan", [False, True], ids=["seed_index", "scan"])
+def test_small_segments_vs_oracle(params, scan, emul_scorer, oracle, kmers, prob):
+    seg = P.make(*params)
+    P.check_segment(emul_scorer, oracle, kmers, prob, seg, flags=P.FULL | (B.PLACE_SCAN if scan else 0))
+
+
+@pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
+def test_edge_inputs(name, contigs, reads, truth, kmer, emul_scorer, oracle, kmers, prob):
+    from genomeassembler_dev_b200.synth import Segment
+    seg = Segment(truth, None, contigs)
+    P.check_segment(emul_scorer, oracle, kmers, prob, seg, kmer=kmer, reads=reads)
+
+
+def test_random_pass_keeps_real_truth_table(emul_scorer, oracle, kmers, prob):
+    """lib/DeNovoAssembler.R:326-333: uniform scoring table, real probabilities on the truth side"""
+    seg = P.make(41, 2500, 50, 10, 5, 0)
+    P.check_segment(emul_scorer, oracle, kmers, tables.uniform(len(prob)), seg, truth_prob=prob)
+
+
+def test_batch_equals_single_calls(emul_scorer, kmers, prob):
+    from genomeassembler_dev_b200 import synth
+    emul_scorer.set_table(kmers, prob)
+    b = synth.make_batch(3, seed=50, length=2000, read_len=40, coverage=8, contigs_lo=2, contigs_hi=5)
+    res = emul_scorer.score_batch(b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars,
+                                  b.truth_off, b.seg_read_start, b.seg_contig_start, flags=B.DEFAULT_FLAGS | B.WANT_HIST)
+    for s in range(b.n_segments):
+        seg = b.segment(s)
+        one = emul_scorer.score(seg.contigs, seg.reads, seg.truth, flags=B.DEFAULT_FLAGS | B.WANT_HIST)
+        c0, c1 = int(b.seg_contig_start[s]), int(b.seg_contig_start[s + 1])
+        for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos", "bp_score", "bp_score_norm_by_break_freqs",
+                  "ks_stat_prob_dist", "ks_stat_path_freq", "hist"):
+            assert np.array_equal(res[k][c0:c1], one[k], equal_nan=True), k
+
+
+def test_argument_errors(emul_scorer, kmers, prob):
+    with pytest.raises(B.BreakscoreError):
+        emul_scorer.set_table(["ACGX"], [0.5])
+    with pytest.raises(B.BreakscoreError):
+        emul_scorer.set_table(["ACGTACGTA"], [0.5])
+    emul_scorer.set_table(kmers, prob)
+    with pytest.raises(B.BreakscoreError):
+        emul_scorer.score([b"ACGT"], [b"AC"], b"ACGT", kmer=0)
+    with pytest.raises(B.BreakscoreError):
+        emul_scorer.score_batch(np.zeros(4, np.uint8), None, 2, np.zeros(4, np.uint8), [0, 4, 2], np.zeros(4, np.uint8),
+                                [0, 4], [0, 2], [0, 2])

@@ -1,0 +1,138 @@
+"""Parity tests proper: the nvcc-built CUDA library, called through its C-ABI on a B200, against
+the oracle (same seeded inputs), the reference vectors, and size-independent properties at
+BASELINE.json's full sizes.  Bit-exact for positions / histograms / integer outputs /
+path_prob_dist; fp64 scores and KS within 1e-9 relative (conftest.RTOL)."""
+import numpy as np
+import pytest
+
+import parity_cases as P
+from conftest import load_ref_vectors
+from genomeassembler_dev_b200 import breakscore as B
+from genomeassembler_dev_b200 import synth, tables
+
+pytestmark = pytest.mark.gpu
+CASES = load_ref_vectors()
+
+
+def test_product_library_is_loaded(gpu_scorer, product_lib):
+    assert gpu_scorer._lib._name == product_lib
+    maps = open("/proc/self/maps").read()
+    assert "libbreakscore.so" in maps and "libbreakscore_emul" not in maps.replace("tests/emul", "")
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_reference_vectors(case, gpu_scorer, kmers, table_set):
+    P.check_reference_vector(gpu_scorer, case, kmers, table_set)
+
+
+@pytest.mark.parametrize("params", P.SMALL + P.MEDIUM, ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL + P.MEDIUM])
+@pytest.mark.parametrize("scan", [False, True], ids=["seed_index", "scan"])
+def test_segments_vs_oracle(params, scan, gpu_scorer, oracle, kmers, prob):
+    seg = P.make(*params)
+    before = gpu_scorer.launch_count
+    P.check_segment(gpu_scorer, oracle, kmers, prob, seg, flags=P.FULL | (B.PLACE_SCAN if scan else 0))
+    assert gpu_scorer.launch_count > before
+
+
+@pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
+def test_edge_inputs(name, contigs, reads, truth, kmer, gpu_scorer, oracle, kmers, prob):
+    seg = synth.Segment(truth, None, contigs)
+    P.check_segment(gpu_scorer, oracle, kmers, prob, seg, kmer=kmer, reads=reads)
+
+
+def test_random_pass_keeps_real_truth_table(gpu_scorer, oracle, kmers, prob):
+    seg = P.make(41, 20000, 50, 20, 9, 1)
+    P.check_segment(gpu_scorer, oracle, kmers, tables.uniform(len(prob)), seg, truth_prob=prob)
+
+
+def test_long_contig_spans_many_tiles(gpu_scorer, oracle, kmers, prob):
+    """contigs longer than one shared-memory tile (scaffolds, cfg-4 shape): leftmost rule across tiles"""
+    seg = synth.make_scaffold_set(61, length=30000, read_len=100, coverage=20, n_base=8, n_scaffolds=6, lo=20000, hi=30000)
+    P.check_segment(gpu_scorer, oracle, kmers, prob, seg)
+
+
+def test_batch_equals_oracle_per_segment(gpu_scorer, oracle, kmers, prob):
+    gpu_scorer.set_table(kmers, prob)
+    b = synth.make_batch(6, seed=70, length=20000, read_len=150, coverage=20, contigs_lo=3, contigs_hi=12, n_gap_scaffolds=1)
+    res = gpu_scorer.score_batch(b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars,
+                                 b.truth_off, b.seg_read_start, b.seg_contig_start, flags=B.DEFAULT_FLAGS | B.WANT_HIST)
+    for s in range(b.n_segments):
+        seg = b.segment(s)
+        want = oracle.oracle_calc_breakscore(seg.contigs, seg.read_list, seg.truth, 8, kmers, prob, want_hist=True)
+        c0, c1 = int(b.seg_contig_start[s]), int(b.seg_contig_start[s + 1])
+        for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos", "hist"):
+            assert np.array_equal(res[k][c0:c1], want[k]), k
+        for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len", "ks_stat_prob_dist", "ks_stat_path_freq"):
+            np.testing.assert_allclose(res[k][c0:c1], want[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+        off = res["path_prob_dist_off"]
+        for c in range(c0, c1):
+            assert np.array_equal(res["path_prob_dist_flat"][off[c]:off[c + 1]], want["path_prob_dist"][c - c0])
+
+
+# ---- full BASELINE.json sizes: size-independent properties ---------------------------------
+
+@pytest.fixture(scope="module")
+def cfg1():
+    return synth.make_segment(1234, length=50000, read_len=100, coverage=30, n_contigs=16, mut_frac=0.2, n_gap_scaffolds=1)
+
+
+def test_cfg1_full_size_vs_oracle(cfg1, gpu_scorer, oracle, kmers, prob):
+    P.check_segment(gpu_scorer, oracle, kmers, prob, cfg1)
+
+
+def test_cfg1_properties(cfg1, gpu_scorer, kmers, prob):
+    gpu_scorer.set_table(kmers, prob)
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST
+    base = gpu_scorer.score(cfg1.contigs, cfg1.reads, cfg1.truth, flags=flags)
+    # histogram mass == kmer_breaks; at most three non-octamer rows
+    assert np.array_equal(base["hist"].sum(axis=1), base["kmer_breaks"])
+    assert (base["hist"][:, :16 + 256 + 4096] > 0).sum(axis=1).max() <= 3
+    # read order and contig order are irrelevant; results are bit-identical (fixed reduction order)
+    rng = np.random.default_rng(0)
+    rp, cp = rng.permutation(len(cfg1.reads)), rng.permutation(len(cfg1.contigs))
+    perm = gpu_scorer.score([cfg1.contigs[i] for i in cp], cfg1.reads[rp], cfg1.truth, flags=flags)
+    for k in ("kmer_breaks", "bp_score", "bp_score_norm_by_break_freqs", "ks_stat_prob_dist", "ks_stat_path_freq", "hist",
+              "path_prob_dist_startpos"):
+        assert np.array_equal(perm[k], base[k][cp], equal_nan=True), k
+    # duplicates are weights: scoring every read twice doubles counts and bp_score, keeps the normalised score
+    dbl = gpu_scorer.score(cfg1.contigs, np.concatenate([cfg1.reads, cfg1.reads]), cfg1.truth, flags=flags)
+    assert np.array_equal(dbl["hist"], 2 * base["hist"])
+    np.testing.assert_allclose(dbl["bp_score"], 2 * base["bp_score"], rtol=1e-12)
+    np.testing.assert_allclose(dbl["bp_score_norm_by_break_freqs"], base["bp_score_norm_by_break_freqs"], rtol=1e-12)
+    # scan placement and seed-index placement agree
+    scan = gpu_scorer.score(cfg1.contigs, cfg1.reads, cfg1.truth, flags=flags | B.PLACE_SCAN)
+    for k in ("kmer_breaks", "bp_score", "hist"):
+        assert np.array_equal(scan[k], base[k]), k
+
+
+def test_cfg2_shape_batch_properties(gpu_scorer, oracle, kmers, prob):
+    """cfg-2 shape (150 bp, 30x, 50 kb segments) at 24 segments: one batched call == per-segment calls,
+    integer-table checksum of the histogram == bp_score, and a sampled segment equals the oracle."""
+    b = synth.make_batch(24, seed=1234, length=50000, read_len=150, coverage=30)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+            b.seg_read_start, b.seg_contig_start)
+    T = len(prob)
+    rowid = np.arange(1, T + 1, dtype=np.float64)
+    gpu_scorer.set_table(kmers, rowid)
+    chk = gpu_scorer.score_batch(*args, flags=B.WANT_HIST)
+    assert np.array_equal(chk["bp_score"], (chk["hist"][:, :T].astype(np.float64) * rowid).sum(axis=1))
+    gpu_scorer.set_table(kmers, prob)
+    res = gpu_scorer.score_batch(*args, flags=B.DEFAULT_FLAGS)
+    assert np.array_equal(res["kmer_breaks"], chk["kmer_breaks"])
+    for s in (0, 11, 23):
+        seg = b.segment(s)
+        want = oracle.oracle_calc_breakscore(seg.contigs, seg.read_list, seg.truth, 8, kmers, prob)
+        c0, c1 = int(b.seg_contig_start[s]), int(b.seg_contig_start[s + 1])
+        assert np.array_equal(res["kmer_breaks"][c0:c1], want["kmer_breaks"])
+        assert np.array_equal(res["path_prob_dist_startpos"][c0:c1], want["path_prob_dist_startpos"])
+        np.testing.assert_allclose(res["bp_score"][c0:c1], want["bp_score"], rtol=1e-9)
+        np.testing.assert_allclose(res["ks_stat_prob_dist"][c0:c1], want["ks_stat_prob_dist"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(res["ks_stat_path_freq"][c0:c1], want["ks_stat_path_freq"], rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+def test_argument_errors(gpu_scorer, kmers, prob):
+    with pytest.raises(B.BreakscoreError):
+        gpu_scorer.set_table(["ACGX"], [0.5])
+    gpu_scorer.set_table(kmers, prob)
+    with pytest.raises(B.BreakscoreError):
+        gpu_scorer.score([b"ACGT"], [b"AC"], b"ACGT", kmer=0)
