@@ -179,12 +179,16 @@ class ClockSampler:
                 return
             time.sleep(self.period)
 
+    def mark(self):
+        self.first = len(self.mhz)
+
     def stop(self):
         self._stop.set()
         if self.thread:
             self.thread.join(timeout=2)
-        out = {"sm_mhz": float(np.median(self.mhz)) if self.mhz else None, "sm_max_mhz": self.max_mhz,
-               "reasons": sorted(self.reasons), "samples": len(self.mhz), "source": "NVML, sampled during the timed region"}
+        mhz = self.mhz[getattr(self, "first", 0):]
+        out = {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(mhz), "source": "NVML, sampled during the timed region"}
         if self.err:
             out["error"] = self.err
         return out
@@ -303,12 +307,13 @@ def b200_main(args):
         sc.score_batch_raw(db, dr, 8, dflags)
         gather_records()
 
+    sampler = ClockSampler(local)
+    sampler.start()  # NVML takes a while to answer the first query: start before the warm-up
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
     sc.enable_timing(True)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()   # keep only samples taken from here on (the timed region)
     launches0 = sc.launch_count
     stage_ms = {k: 0.0 for k in B.STAGES}
     barrier()

@@ -26,6 +26,7 @@ WANT_HIST = 0x004
 WANT_POS = 0x008
 WANT_STARTPOS = 0x010
 PLACE_SCAN = 0x100
+PLACE_TILE = 0x800
 DEVICE_CHARS = 0x200
 DEVICE_RESULT = 0x400
 DEFAULT_FLAGS = WANT_PROB_DIST | WANT_KS | WANT_STARTPOS

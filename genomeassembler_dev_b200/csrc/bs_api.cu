@@ -1,6 +1,11 @@
 // C-ABI of the breakage scorer (include/breakscore.h): context, resident tables, work buffers
-// and the per-call orchestration of the kernels in bs_kernels.cuh.  Host C++ only talks to
-// the CUDA runtime; nothing here depends on torch, Python or R.
+// and the orchestration of the kernels in bs_kernels.cuh.  Host C++ only talks to the CUDA
+// runtime; nothing here depends on torch, Python or R.
+//
+// A scoring call is cut into CHUNKS of whole segments (independent experiments).  Chunks run
+// through a three-stream pipeline -- H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1
+// overlap -- over two workspaces, so an end-to-end call from host buffers is bound by the PCIe
+// copy of the ASCII reads, not by the sum of copy and compute.
 #ifdef BS_CPU_EMUL
 #include "cuda_emul.h"  // tests/emul: CPU emulation used by the CPU-only test-suite, never shipped
 #endif
@@ -10,8 +15,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -26,15 +33,19 @@ constexpr int kPlaceThreads = 64;
 constexpr int kScoreThreads = 64;
 constexpr int kKsThreads = 64;
 constexpr int kPackThreads = 64;
+constexpr int kPlaceIxThreads = 64;
 #else
 constexpr int kPlaceThreads = 256;
 constexpr int kScoreThreads = 256;
 constexpr int kKsThreads = 1024;
 constexpr int kPackThreads = 256;
+constexpr int kPlaceIxThreads = 256;
 #endif
-constexpr int kMaxTile = 8192;        // contig positions per shared-memory tile
-constexpr int64_t kMaxChunk = 32768;  // reads per placement work item (bitmask of 4 KB)
+constexpr int kMaxTile = 8192;        // contig positions per shared-memory tile (tile placement modes)
+constexpr int64_t kMaxChunk = 32768;  // reads per placement work item (tile placement modes)
 constexpr int64_t kMinChunk = 2048;
+constexpr int kHitCap = 8192;         // reads placed per contig kept in shared memory (k_place_index)
+constexpr int kWorkspaces = 2;
 
 enum Stage { ST_H2D, ST_PACK, ST_PLACE, ST_SCORE, ST_SPECTRUM, ST_PROBDIST, ST_PATHFREQ, ST_STARTPOS, ST_D2H, ST_COUNT };
 
@@ -50,16 +61,44 @@ struct KsCache {
     DevBuf rank_x, rank_y, le_idx, lt_idx, yv;
 };
 
+// device + pinned staging memory of one in-flight chunk
+struct Workspace {
+    void *h_meta = nullptr;
+    size_t h_meta_cap = 0;
+    DevBuf meta, read_chars, read_off, ctg_chars, tr_chars;
+    DevBuf rwords, rflags, cwords, cmask, twords, tmask;
+    DevBuf w, total, ycnt, head, next, odd_head;
+    DevBuf out_i32, out_f64, pd, hist, pos;
+    cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
+    bool in_flight = false;
+};
+
+struct TimedSpan {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+// a run of whole segments processed together
+struct Chunk {
+    int64_t s0, s1;  // segments
+    int64_t r0, r1;  // reads
+    int64_t c0, c1;  // contigs
+};
+
 }  // namespace
 
 struct bs_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;   // compute stream unless the caller sets one
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // H2D
+    cudaStream_t out_stream = nullptr;   // D2H
     char err[512] = "";
     int64_t launches = 0;
+    int64_t chunk_bytes_host = (int64_t)96 << 20;    // ASCII bytes per chunk when inputs come from the host
+    int64_t chunk_bytes_dev = (int64_t)1024 << 20;   // ... when they are already on the device
 
     // table
     bool has_table = false;
@@ -72,21 +111,16 @@ struct bs_ctx {
     DevBuf d_tab_prob, d_tab_row;
     KsCache ks;
 
-    // staging + work buffers (grow-only)
-    void *h_meta = nullptr;
-    size_t h_meta_cap = 0;
-    cudaEvent_t meta_done = nullptr;
-    bool meta_pending = false;
-    DevBuf d_meta, d_read_chars, d_read_off, d_ctg_chars, d_tr_chars;
-    DevBuf d_rwords, d_rflags, d_cwords, d_cmask, d_twords, d_tmask;
-    DevBuf d_w, d_total, d_ycnt, d_scratch, d_ovf, d_status, d_rank_scratch;
-    DevBuf d_out_i32, d_out_f64, d_pd, d_hist, d_pos;
+    Workspace ws[kWorkspaces];
+    // scratch shared by all chunks (kernels of different chunks never overlap: one compute stream)
+    DevBuf d_best, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters;
+    size_t best_elems = 0;
+    bool best_dirty = true;
 
     // timing
     bool timing = false;
-    cudaEvent_t ev[ST_COUNT][2] = {};
-    bool ev_used[ST_COUNT] = {};
-    double last_ms[ST_COUNT] = {};
+    std::vector<TimedSpan> spans;
+    size_t spans_used = 0;
 };
 
 namespace {
@@ -105,6 +139,11 @@ int fail(bs_ctx *ctx, int code, const char *fmt, ...) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(ctx, BS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
                         __FILE__, __LINE__);                                                       \
+    } while (0)
+#define BS_TRY(expr)                 \
+    do {                             \
+        int rc_ = (expr);            \
+        if (rc_ != BS_OK) return rc_; \
     } while (0)
 
 int ensure(bs_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -126,7 +165,7 @@ void release(DevBuf &b) {
     b.cap = 0;
 }
 
-// host-side assembly of the small per-call metadata arrays into one pinned block, one H2D
+// host-side assembly of the small per-chunk metadata arrays into one pinned block, one H2D
 struct MetaBuilder {
     std::vector<unsigned char> bytes;
     template <class T>
@@ -140,12 +179,21 @@ struct MetaBuilder {
 
 struct StageTimer {
     bs_ctx *ctx;
-    Stage st;
-    StageTimer(bs_ctx *c, Stage s) : ctx(c), st(s) {
-        if (ctx->timing) { cudaEventRecord(ctx->ev[st][0], ctx->stream); }
+    cudaStream_t st;
+    TimedSpan *span = nullptr;
+    StageTimer(bs_ctx *c, Stage s, cudaStream_t stream) : ctx(c), st(stream) {
+        if (!ctx->timing) return;
+        if (ctx->spans_used == ctx->spans.size()) {
+            TimedSpan t{(int)s, nullptr, nullptr};
+            if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+            ctx->spans.push_back(t);
+        }
+        span = &ctx->spans[ctx->spans_used++];
+        span->stage = (int)s;
+        cudaEventRecord(span->a, st);
     }
     ~StageTimer() {
-        if (ctx->timing) { cudaEventRecord(ctx->ev[st][1], ctx->stream); ctx->ev_used[st] = true; }
+        if (span) cudaEventRecord(span->b, st);
     }
 };
 
@@ -156,10 +204,16 @@ int grid_for(int64_t work_items, int threads, int cap) {
     return (int)g;
 }
 
+int sync_all(bs_ctx *ctx) {
+    BS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    BS_CUDA(cudaStreamSynchronize(ctx->stream));
+    BS_CUDA(cudaStreamSynchronize(ctx->out_stream));
+    return BS_OK;
+}
+
 int upload_table(bs_ctx *ctx) {
-    int rc;
-    if ((rc = ensure(ctx, ctx->d_tab_prob, bs::DENSE_SIZE * sizeof(double)))) return rc;
-    if ((rc = ensure(ctx, ctx->d_tab_row, bs::DENSE_SIZE * sizeof(int32_t)))) return rc;
+    BS_TRY(ensure(ctx, ctx->d_tab_prob, bs::DENSE_SIZE * sizeof(double)));
+    BS_TRY(ensure(ctx, ctx->d_tab_row, bs::DENSE_SIZE * sizeof(int32_t)));
     BS_CUDA(cudaMemcpyAsync(ctx->d_tab_prob.p, ctx->prob_dense.data(), bs::DENSE_SIZE * sizeof(double),
                             cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaMemcpyAsync(ctx->d_tab_row.p, ctx->row_dense.data(), bs::DENSE_SIZE * sizeof(int32_t),
@@ -202,12 +256,11 @@ int prepare_ks(bs_ctx *ctx, int kmer) {
         lt[i] = (int32_t)(std::lower_bound(yv.begin(), yv.end(), xv[i]) - yv.begin()) - 1;
     }
     if (yv.empty()) yv.push_back(0.0);  // keep the device array non-empty; R_y stays 0
-    int rc;
-    if ((rc = ensure(ctx, k.rank_x, rank_x.size() * 4))) return rc;
-    if ((rc = ensure(ctx, k.rank_y, rank_y.size() * 4))) return rc;
-    if ((rc = ensure(ctx, k.le_idx, le.size() * 4))) return rc;
-    if ((rc = ensure(ctx, k.lt_idx, lt.size() * 4))) return rc;
-    if ((rc = ensure(ctx, k.yv, yv.size() * 8))) return rc;
+    BS_TRY(ensure(ctx, k.rank_x, rank_x.size() * 4));
+    BS_TRY(ensure(ctx, k.rank_y, rank_y.size() * 4));
+    BS_TRY(ensure(ctx, k.le_idx, le.size() * 4));
+    BS_TRY(ensure(ctx, k.lt_idx, lt.size() * 4));
+    BS_TRY(ensure(ctx, k.yv, yv.size() * 8));
     BS_CUDA(cudaMemcpyAsync(k.rank_x.p, rank_x.data(), rank_x.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaMemcpyAsync(k.rank_y.p, rank_y.data(), rank_y.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaMemcpyAsync(k.le_idx.p, le.data(), le.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -217,8 +270,7 @@ int prepare_ks(bs_ctx *ctx, int kmer) {
     k.kmer = kmer;
     k.table_version = ctx->table_version;
     k.R_x = (int)xv.size();
-    // number of distinct truth-side values actually present
-    int ry = 0;
+    int ry = 0;  // number of distinct truth-side values actually present
     for (int c = 0; c < ncode; c++) ry = std::max(ry, rank_y[c] + 1);
     k.R_y = ry;
     k.rank_zero = rank_zero;
@@ -230,6 +282,478 @@ int check_offsets(bs_ctx *ctx, const char *what, const int64_t *off, int64_t n) 
     if (off[0] < 0) return fail(ctx, BS_ERR_INVALID, "%s offsets start below 0", what);
     for (int64_t i = 0; i < n; i++)
         if (off[i + 1] < off[i]) return fail(ctx, BS_ERR_INVALID, "%s offsets are not monotone at %lld", what, (long long)i);
+    return BS_OK;
+}
+
+// everything of a call that does not change from chunk to chunk
+struct CallEnv {
+    const bs_batch *b;
+    bs_result *res;
+    int kmer;
+    uint32_t flags;
+    bool dev_chars, dev_res, want_ks, want_pd, want_pos, want_hist, want_sp;
+    const char *read_chars;  // base of read 0 (shifted when offsets turned out to be uniform)
+    const int64_t *roff;     // read offsets or NULL (every read has rlen bytes, dense)
+    int32_t rlen;
+    int64_t T;
+};
+
+int64_t read_byte_begin(const CallEnv &e, int64_t n) { return e.roff ? e.roff[n] : n * (int64_t)e.rlen; }
+
+// ---- one chunk: metadata, H2D, kernels, D2H --------------------------------------------------
+int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
+    const bs_batch *b = e.b;
+    bs_result *res = e.res;
+    const int64_t S = ch.s1 - ch.s0, N = ch.r1 - ch.r0, C = ch.c1 - ch.c0;
+    const int64_t T = e.T;
+    const int kmer = e.kmer;
+    cudaStream_t st = ctx->stream;
+
+    // the workspace's previous chunk must have left it (its results are on their way or home)
+    if (ws.in_flight) {
+        BS_CUDA(cudaEventSynchronize(ws.ev_d2h));
+        ws.in_flight = false;
+    }
+
+    // ---------------- chunk-local metadata ----------------
+    const int64_t ctg_b0 = b->contig_off[ch.c0], ctg_bytes = b->contig_off[ch.c1] - ctg_b0;
+    const int64_t tr_b0 = b->truth_off[ch.s0], tr_bytes = b->truth_off[ch.s1] - tr_b0;
+    const int64_t rd_b0 = read_byte_begin(e, ch.r0), read_bytes = read_byte_begin(e, ch.r1) - rd_b0;
+
+    std::vector<int64_t> ctg_off(C + 1), ctg_woff(C + 1), tr_off(S + 1), tr_woff(S + 1), seg_rs(S + 1), tab_off(std::max<int64_t>(S, 1));
+    std::vector<int32_t> ctg_seg(std::max<int64_t>(C, 1)), seed_len(std::max<int64_t>(S, 1)), tab_mask(std::max<int64_t>(S, 1));
+    int64_t max_ctg = 0, max_tr = 0;
+    ctg_woff[0] = 0;
+    for (int64_t c = 0; c <= C; c++) ctg_off[c] = b->contig_off[ch.c0 + c] - ctg_b0;
+    for (int64_t c = 0; c < C; c++) {
+        const int64_t L = ctg_off[c + 1] - ctg_off[c];
+        max_ctg = std::max(max_ctg, L);
+        ctg_woff[c + 1] = ctg_woff[c] + (L + 31) / 32 + 2;
+    }
+    tr_woff[0] = 0;
+    int64_t max_seg_reads = 0, head_total = 0;
+    int64_t max_read = 0;
+    for (int64_t s = 0; s <= S; s++) {
+        tr_off[s] = b->truth_off[ch.s0 + s] - tr_b0;
+        seg_rs[s] = b->seg_read_start[ch.s0 + s] - ch.r0;
+    }
+    for (int64_t s = 0; s < S; s++) {
+        const int64_t L = tr_off[s + 1] - tr_off[s];
+        max_tr = std::max(max_tr, L);
+        tr_woff[s + 1] = tr_woff[s] + (L + 31) / 32 + 2;
+        for (int64_t c = b->seg_contig_start[ch.s0 + s]; c < b->seg_contig_start[ch.s0 + s + 1]; c++) ctg_seg[c - ch.c0] = (int32_t)s;
+        const int64_t ns = seg_rs[s + 1] - seg_rs[s];
+        max_seg_reads = std::max(max_seg_reads, ns);
+        int64_t mn = 32;
+        if (e.roff) {
+            for (int64_t n = ch.r0 + seg_rs[s]; n < ch.r0 + seg_rs[s + 1]; n++) {
+                const int64_t l = e.roff[n + 1] - e.roff[n];
+                max_read = std::max(max_read, l);
+                if (l > 0 && l < mn) mn = l;
+            }
+        } else {
+            max_read = e.rlen;
+            mn = std::min<int64_t>(32, std::max<int64_t>(1, e.rlen));
+        }
+        seed_len[s] = (int32_t)mn;
+        int64_t hs = 64;
+        while (hs < 2 * ns) hs <<= 1;
+        tab_off[s] = head_total;
+        tab_mask[s] = (int32_t)(hs - 1);
+        head_total += hs;
+    }
+    if (max_read > 0x3fffffff) return fail(ctx, BS_ERR_INVALID, "read longer than 2^30");
+    const int W = (int)std::max<int64_t>(1, (max_read + 31) / 32);
+    const bool tile_mode = (e.flags & (BS_PLACE_SCAN | BS_PLACE_TILE)) != 0;
+
+    // placement order of the index kernel: longest contigs first
+    std::vector<int32_t> order;
+    std::vector<bs::PlaceItem> items;
+    int tile_len = 0, hash_size = 0, found_words = 0;
+    size_t place_smem = 0;
+    if (!tile_mode) {
+        order.resize((size_t)C);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+            return ctg_off[x + 1] - ctg_off[x] > ctg_off[y + 1] - ctg_off[y];
+        });
+    } else {
+        // tile placement: one work item per (contig, read chunk)
+        tile_len = (int)std::min<int64_t>(kMaxTile, std::max<int64_t>(32, (max_ctg + 31) / 32 * 32));
+        hash_size = 64;
+        while (hash_size < tile_len) hash_size <<= 1;
+        items.reserve((size_t)C);
+        const int64_t target_items = (int64_t)ctx->sm_count * 8;
+        int64_t max_chunk = 1;
+        for (int64_t c = 0; c < C; c++) {
+            const int32_t s = ctg_seg[c];
+            const int64_t r0 = seg_rs[s], r1 = seg_rs[s + 1];
+            const int64_t nr = r1 - r0;
+            int64_t nchunks = 1;
+            if (C < target_items) nchunks = std::min((target_items + C - 1) / C, std::max<int64_t>(1, nr / kMinChunk));
+            nchunks = std::max(nchunks, (nr + kMaxChunk - 1) / kMaxChunk);
+            nchunks = std::max<int64_t>(nchunks, 1);
+            const int64_t per = (nr + nchunks - 1) / nchunks;
+            for (int64_t k = 0; k < nchunks; k++) {
+                bs::PlaceItem it;
+                it.contig = (int32_t)c;
+                it.seg = s;
+                it.read_begin = r0 + k * per;
+                it.read_end = std::min(r1, it.read_begin + per);
+                if (k > 0 && it.read_begin >= it.read_end) break;
+                max_chunk = std::max(max_chunk, it.read_end - it.read_begin);
+                items.push_back(it);
+            }
+        }
+        found_words = (int)((max_chunk + 31) / 32);
+        place_smem = bs::place_smem_bytes(tile_len, hash_size, W, found_words);
+        if (place_smem > ctx->smem_optin) return fail(ctx, BS_ERR_INVALID, "placement tile needs %zu bytes of shared memory", place_smem);
+    }
+
+    std::vector<int64_t> pd_off, pos_off;
+    if (e.want_pd) {
+        pd_off.resize(C + 1);
+        for (int64_t c = 0; c <= C; c++) pd_off[c] = res->path_prob_dist_off[ch.c0 + c] - res->path_prob_dist_off[ch.c0];
+    }
+    if (e.want_pos) {
+        pos_off.resize(C + 1);
+        for (int64_t c = 0; c <= C; c++) pos_off[c] = res->pos_off[ch.c0 + c] - res->pos_off[ch.c0];
+    }
+    std::vector<int64_t> roff_local;
+    if (e.roff) {
+        roff_local.resize(N + 1);
+        for (int64_t n = 0; n <= N; n++) roff_local[n] = e.roff[ch.r0 + n] - rd_b0;
+    }
+
+    MetaBuilder mb;
+    const size_t o_ctg_off = mb.add(ctg_off.data(), (size_t)C + 1);
+    const size_t o_ctg_woff = mb.add(ctg_woff.data(), (size_t)C + 1);
+    const size_t o_ctg_seg = mb.add(ctg_seg.data(), (size_t)C);
+    const size_t o_tr_off = mb.add(tr_off.data(), (size_t)S + 1);
+    const size_t o_tr_woff = mb.add(tr_woff.data(), (size_t)S + 1);
+    const size_t o_seg_rs = mb.add(seg_rs.data(), (size_t)S + 1);
+    const size_t o_seed = mb.add(seed_len.data(), (size_t)S);
+    const size_t o_tab_off = mb.add(tab_off.data(), (size_t)S);
+    const size_t o_tab_mask = mb.add(tab_mask.data(), (size_t)S);
+    const size_t o_order = mb.add(order.data(), order.size());
+    const size_t o_items = mb.add(items.data(), items.size());
+    const size_t o_pd_off = e.want_pd ? mb.add(pd_off.data(), (size_t)C + 1) : 0;
+    const size_t o_pos_off = e.want_pos ? mb.add(pos_off.data(), (size_t)C + 1) : 0;
+    const size_t o_roff = e.roff ? mb.add(roff_local.data(), (size_t)N + 1) : 0;
+
+    if (mb.bytes.size() > ws.h_meta_cap) {
+        if (ws.h_meta) cudaFreeHost(ws.h_meta);
+        ws.h_meta = nullptr;
+        ws.h_meta_cap = 0;
+        const size_t want = mb.bytes.size() * 2 + 4096;
+        if (cudaHostAlloc(&ws.h_meta, want, cudaHostAllocDefault) != cudaSuccess)
+            return fail(ctx, BS_ERR_ALLOC, "cudaHostAlloc(%zu) failed", want);
+        ws.h_meta_cap = want;
+    }
+    std::memcpy(ws.h_meta, mb.bytes.data(), mb.bytes.size());
+
+    // ---------------- device buffers ----------------
+    const int64_t w_elems = ctg_bytes + C;
+    const int64_t pd_elems = e.want_pd ? pd_off[C] : 0;
+    const int64_t pos_elems = e.want_pos ? pos_off[C] : 0;
+    BS_TRY(ensure(ctx, ws.meta, mb.bytes.size()));
+    if (!e.dev_chars) {
+        BS_TRY(ensure(ctx, ws.read_chars, (size_t)read_bytes + 32));
+        BS_TRY(ensure(ctx, ws.ctg_chars, (size_t)ctg_bytes + 32));
+        BS_TRY(ensure(ctx, ws.tr_chars, (size_t)tr_bytes + 32));
+    }
+    BS_TRY(ensure(ctx, ws.rwords, (size_t)std::max<int64_t>(N, 1) * W * 8));
+    BS_TRY(ensure(ctx, ws.rflags, (size_t)std::max<int64_t>(N, 1) + 8));
+    BS_TRY(ensure(ctx, ws.cwords, (size_t)ctg_woff[C] * 8 + 8));
+    BS_TRY(ensure(ctx, ws.cmask, (size_t)ctg_woff[C] * 4 + 8));
+    BS_TRY(ensure(ctx, ws.twords, (size_t)tr_woff[S] * 8 + 8));
+    BS_TRY(ensure(ctx, ws.tmask, (size_t)tr_woff[S] * 4 + 8));
+    BS_TRY(ensure(ctx, ws.w, (size_t)w_elems * 4));
+    BS_TRY(ensure(ctx, ws.total, (size_t)C * 4));
+    if (!tile_mode) {
+        BS_TRY(ensure(ctx, ws.head, (size_t)std::max<int64_t>(head_total, 1) * 4));
+        BS_TRY(ensure(ctx, ws.next, (size_t)std::max<int64_t>(N, 1) * 4));
+        BS_TRY(ensure(ctx, ws.odd_head, (size_t)std::max<int64_t>(S, 1) * 4));
+    }
+    if (!e.dev_res) {
+        BS_TRY(ensure(ctx, ws.out_i32, (size_t)3 * C * 4));
+        BS_TRY(ensure(ctx, ws.out_f64, (size_t)5 * C * 8));
+        if (e.want_pd) BS_TRY(ensure(ctx, ws.pd, (size_t)std::max<int64_t>(pd_elems, 1) * 8));
+        if (e.want_hist) BS_TRY(ensure(ctx, ws.hist, (size_t)C * (T + 1) * 4));
+        if (e.want_pos) BS_TRY(ensure(ctx, ws.pos, (size_t)std::max<int64_t>(pos_elems, 1) * 4));
+    }
+
+    unsigned char *dm = (unsigned char *)ws.meta.p;
+    const int64_t *d_ctg_off = (const int64_t *)(dm + o_ctg_off);
+    const int64_t *d_ctg_woff = (const int64_t *)(dm + o_ctg_woff);
+    const int32_t *d_ctg_seg = (const int32_t *)(dm + o_ctg_seg);
+    const int64_t *d_tr_off = (const int64_t *)(dm + o_tr_off);
+    const int64_t *d_tr_woff = (const int64_t *)(dm + o_tr_woff);
+    const int64_t *d_seg_rs = (const int64_t *)(dm + o_seg_rs);
+    const int32_t *d_seed = (const int32_t *)(dm + o_seed);
+    const int64_t *d_tab_off = (const int64_t *)(dm + o_tab_off);
+    const int32_t *d_tab_mask = (const int32_t *)(dm + o_tab_mask);
+    const int32_t *d_order = (const int32_t *)(dm + o_order);
+    const bs::PlaceItem *d_items = (const bs::PlaceItem *)(dm + o_items);
+    const int64_t *d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
+    const int64_t *d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
+    const int64_t *d_roff = e.roff ? (const int64_t *)(dm + o_roff) : nullptr;
+
+    // ---------------- H2D (copy stream) ----------------
+    const uint8_t *d_rchars, *d_cchars, *d_tchars;
+    {
+        StageTimer tm(ctx, ST_H2D, ctx->copy_stream);
+        cudaStream_t cs = ctx->copy_stream;
+        BS_CUDA(cudaMemcpyAsync(ws.meta.p, ws.h_meta, mb.bytes.size(), cudaMemcpyHostToDevice, cs));
+        if (e.dev_chars) {
+            d_rchars = (const uint8_t *)e.read_chars + rd_b0;
+            d_cchars = (const uint8_t *)b->contig_chars + ctg_b0;
+            d_tchars = (const uint8_t *)b->truth_chars + tr_b0;
+        } else {
+            if (read_bytes) BS_CUDA(cudaMemcpyAsync(ws.read_chars.p, e.read_chars + rd_b0, (size_t)read_bytes, cudaMemcpyHostToDevice, cs));
+            if (ctg_bytes) BS_CUDA(cudaMemcpyAsync(ws.ctg_chars.p, b->contig_chars + ctg_b0, (size_t)ctg_bytes, cudaMemcpyHostToDevice, cs));
+            if (tr_bytes) BS_CUDA(cudaMemcpyAsync(ws.tr_chars.p, b->truth_chars + tr_b0, (size_t)tr_bytes, cudaMemcpyHostToDevice, cs));
+            d_rchars = (const uint8_t *)ws.read_chars.p;
+            d_cchars = (const uint8_t *)ws.ctg_chars.p;
+            d_tchars = (const uint8_t *)ws.tr_chars.p;
+        }
+    }
+    BS_CUDA(cudaEventRecord(ws.ev_h2d, ctx->copy_stream));
+    BS_CUDA(cudaStreamWaitEvent(st, ws.ev_h2d, 0));
+
+    // result destinations on the device
+    int32_t *o_len, *o_breaks, *o_startpos, *o_hist = nullptr, *o_pos = nullptr;
+    double *o_score, *o_norm, *o_bylen, *o_ksa, *o_ksb, *o_pd = nullptr;
+    const bool ks_a = e.want_ks && res->ks_stat_prob_dist, ks_b = e.want_ks && res->ks_stat_path_freq;
+    if (e.dev_res) {
+        o_len = res->sequence_len ? res->sequence_len + ch.c0 : nullptr;
+        o_breaks = res->kmer_breaks ? res->kmer_breaks + ch.c0 : nullptr;
+        o_startpos = e.want_sp ? res->path_prob_dist_startpos + ch.c0 : nullptr;
+        o_score = res->bp_score ? res->bp_score + ch.c0 : nullptr;
+        o_norm = res->bp_score_norm_by_break_freqs ? res->bp_score_norm_by_break_freqs + ch.c0 : nullptr;
+        o_bylen = res->bp_score_norm_by_len ? res->bp_score_norm_by_len + ch.c0 : nullptr;
+        o_ksa = ks_a ? res->ks_stat_prob_dist + ch.c0 : nullptr;
+        o_ksb = ks_b ? res->ks_stat_path_freq + ch.c0 : nullptr;
+        if (e.want_pd) o_pd = res->path_prob_dist + res->path_prob_dist_off[ch.c0];
+        if (e.want_hist) o_hist = res->hist + ch.c0 * (T + 1);
+        if (e.want_pos) o_pos = res->pos + res->pos_off[ch.c0];
+    } else {
+        int32_t *i32 = (int32_t *)ws.out_i32.p;
+        double *f64 = (double *)ws.out_f64.p;
+        o_len = i32; o_breaks = i32 + C; o_startpos = e.want_sp ? i32 + 2 * C : nullptr;
+        o_score = f64; o_norm = f64 + C; o_bylen = f64 + 2 * C;
+        o_ksa = ks_a ? f64 + 3 * C : nullptr;
+        o_ksb = ks_b ? f64 + 4 * C : nullptr;
+        if (e.want_pd) o_pd = (double *)ws.pd.p;
+        if (e.want_hist) o_hist = (int32_t *)ws.hist.p;
+        if (e.want_pos) o_pos = (int32_t *)ws.pos.p;
+    }
+
+    BS_CUDA(cudaMemsetAsync(ws.w.p, 0, (size_t)w_elems * 4, st));
+    BS_CUDA(cudaMemsetAsync(ws.total.p, 0, (size_t)C * 4, st));
+    if (o_hist) BS_CUDA(cudaMemsetAsync(o_hist, 0, (size_t)C * (T + 1) * 4, st));
+    if (o_pos && pos_elems > 0) BS_CUDA(cudaMemsetAsync(o_pos, 0xff, (size_t)pos_elems * 4, st));
+
+    // ---------------- kernels (compute stream) ----------------
+    const int grid_cap = ctx->sm_count * 32;
+    bs::SeqSet cs{d_cchars, d_ctg_off, d_ctg_woff, (uint64_t *)ws.cwords.p, (uint32_t *)ws.cmask.p, C, ctg_woff[C]};
+    bs::SeqSet ts{d_tchars, d_tr_off, d_tr_woff, (uint64_t *)ws.twords.p, (uint32_t *)ws.tmask.p, S, tr_woff[S]};
+    bs::ReadSet rs{d_rchars, d_roff, e.rlen, W, N, (uint64_t *)ws.rwords.p, (uint8_t *)ws.rflags.p};
+    bs::ReadIndex ix;
+    std::memset(&ix, 0, sizeof(ix));
+    if (!tile_mode) {
+        ix.head = (uint32_t *)ws.head.p; ix.next = (uint32_t *)ws.next.p; ix.odd_head = (uint32_t *)ws.odd_head.p;
+        ix.tab_off = d_tab_off; ix.tab_mask = d_tab_mask; ix.seed_len = d_seed; ix.seg_read_start = d_seg_rs; ix.n_seg = (int32_t)S;
+    }
+    {
+        StageTimer tm(ctx, ST_PACK, st);
+        BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
+        ctx->launches++;
+        if (e.want_ks || e.want_sp) {
+            BS_LAUNCH(bs::k_pack_seqs, grid_for(ts.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, ts);
+            ctx->launches++;
+        }
+        if (N > 0) {
+            if (!tile_mode) {
+                BS_CUDA(cudaMemsetAsync(ws.head.p, 0, (size_t)head_total * 4, st));
+                BS_CUDA(cudaMemsetAsync(ws.odd_head.p, 0, (size_t)S * 4, st));
+            }
+            if (!e.roff && e.rlen >= 1) {
+                BS_CUDA(cudaMemsetAsync(ws.rflags.p, 0, (size_t)N + 8, st));
+                const int64_t tiles = (N * W + bs::PACK_THREADS - 1) / bs::PACK_THREADS;
+                BS_LAUNCH(bs::k_pack_reads_uniform, (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 16), bs::PACK_THREADS, 0, st, rs, ix);
+            } else {
+                BS_LAUNCH(bs::k_pack_reads, grid_for(N, kPackThreads, grid_cap), kPackThreads, 0, st, rs, ix);
+            }
+            ctx->launches++;
+        }
+    }
+    {
+        StageTimer tm(ctx, ST_PLACE, st);
+        if (N > 0 && C > 0 && !tile_mode) {
+            // per-block scratch row of leftmost positions, all POS_INF between launches
+            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * 4);
+            const int64_t stride = (max_seg_reads + 31) / 32 * 32;
+            const int64_t budget = (int64_t)8 << 30;
+            nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * 4, 1)));
+            const size_t need = (size_t)nblk * (size_t)stride;
+            if (need > ctx->best_elems || ctx->best_dirty) {
+                const size_t elems = std::max(need, ctx->best_elems);
+                BS_TRY(ensure(ctx, ctx->d_best, elems * 4));
+                ctx->best_elems = elems;
+                BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
+            }
+            ctx->best_dirty = true;  // cleared when the call ends without an error
+            BS_TRY(ensure(ctx, ctx->d_counters, 64));
+            BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
+            bs::PlaceIxArgs pa;
+            pa.order = d_order; pa.n_items = (int32_t)C; pa.work_counter = (int32_t *)ctx->d_counters.p;
+            pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
+            pa.ctg_chars = d_cchars; pa.ctg_seg = d_ctg_seg;
+            pa.reads = rs; pa.ix = ix;
+            pa.best = (uint32_t *)ctx->d_best.p; pa.best_stride = stride;
+            pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
+            pa.pos = o_pos; pa.pos_off = d_pos_off;
+            pa.hit_cap = kHitCap;
+            BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, (size_t)kHitCap * 4, st, pa);
+            ctx->launches++;
+        } else if (N > 0 && !items.empty()) {
+            bs::PlaceArgs pa;
+            pa.items = d_items;
+            pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff;
+            pa.ctg_words = cs.words; pa.ctg_mask = cs.mask; pa.ctg_chars = d_cchars;
+            pa.reads = rs;
+            pa.seg_seed_len = d_seed; pa.seg_read_start = d_seg_rs;
+            pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
+            pa.pos = o_pos; pa.pos_off = d_pos_off;
+            pa.tile_len = tile_len; pa.hash_size = hash_size; pa.found_words = found_words;
+            pa.scan_mode = (e.flags & BS_PLACE_SCAN) ? 1 : 0;
+            BS_CUDA(cudaFuncSetAttribute(bs::k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem));
+            BS_LAUNCH(bs::k_place, (unsigned)items.size(), kPlaceThreads, place_smem, st, pa);
+            ctx->launches++;
+        }
+    }
+    {
+        StageTimer tm(ctx, ST_SCORE, st);
+        bs::ScoreArgs sa;
+        sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask;
+        sa.w = (const int32_t *)ws.w.p; sa.total = (const int32_t *)ws.total.p;
+        sa.tab_prob = (const double *)ctx->d_tab_prob.p; sa.tab_row = (const int32_t *)ctx->d_tab_row.p;
+        sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
+        sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
+        sa.kmer_breaks = o_breaks; sa.hist = o_hist;
+        BS_LAUNCH(bs::k_break_score, (unsigned)std::min<int64_t>(C, grid_cap), kScoreThreads, kScoreThreads * 8 + 16, st, sa);
+        ctx->launches++;
+    }
+    if (e.want_ks) {
+        const KsCache &k = ctx->ks;
+        const int R_y = std::max(k.R_y, 1);
+        BS_TRY(ensure(ctx, ws.ycnt, (size_t)S * R_y * 4));
+        StageTimer tm(ctx, ST_SPECTRUM, st);
+        BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, st));
+        if (k.R_y > 0) {
+            bs::SpectrumArgs sp;
+            sp.tr_off = d_tr_off; sp.tr_woff = d_tr_woff; sp.tr_words = ts.words; sp.tr_mask = ts.mask;
+            sp.rank_y = (const int32_t *)k.rank_y.p; sp.ycnt = (int32_t *)ws.ycnt.p;
+            sp.R_y = R_y; sp.kmer = kmer;
+            sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(64, (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
+            BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, st, sp);
+            ctx->launches++;
+            BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, st, (int32_t *)ws.ycnt.p, R_y);
+            ctx->launches++;
+        }
+    }
+    if (e.want_pd || ks_a) {
+        StageTimer tm(ctx, ST_PROBDIST, st);
+        const KsCache &k = ctx->ks;
+        bs::ProbDistArgs pa;
+        pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
+        pa.ctg_seg = d_ctg_seg;
+        pa.tab_prob = (const double *)ctx->d_tab_prob.p; pa.tab_row = (const int32_t *)ctx->d_tab_row.p;
+        pa.rank_x = ks_a ? (const int32_t *)k.rank_x.p : nullptr;
+        pa.le_idx = ks_a ? (const int32_t *)k.le_idx.p : nullptr;
+        pa.lt_idx = ks_a ? (const int32_t *)k.lt_idx.p : nullptr;
+        pa.ycum = ks_a ? (const int32_t *)ws.ycnt.p : nullptr;
+        pa.R_x = ks_a ? k.R_x : 0; pa.R_y = ks_a ? k.R_y : 0; pa.rank_zero = ks_a ? k.rank_zero : 0;
+        pa.kmer = kmer; pa.n_contigs = C;
+        pa.prob_dist = o_pd; pa.pd_off = d_pd_off; pa.ks = ks_a ? o_ksa : nullptr;
+        // rank histogram: shared memory when it fits (real table: 32 897 ranks = 129 KB), else a
+        // per-block global scratch that stays in L2 (all-distinct tables: 65 537 ranks)
+        const bool in_smem = ks_a && bs::probdist_smem_bytes(pa.R_x, kKsThreads, true) + 1024 <= ctx->smem_optin;
+        const size_t smem = bs::probdist_smem_bytes(pa.R_x, kKsThreads, in_smem);
+        BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = in_smem ? std::max<int>(1, (int)(ctx->smem_optin / (smem + 1024))) : 2;
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm);
+        pa.rank_scratch = nullptr;
+        if (ks_a && !in_smem) {
+            BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * pa.R_x * 4));
+            pa.rank_scratch = (int32_t *)ctx->d_rank_scratch.p;
+        }
+        BS_LAUNCH(bs::k_prob_dist_ks, (unsigned)nblk, kKsThreads, smem, st, pa);
+        ctx->launches++;
+    }
+    if (ks_b) {
+        StageTimer tm(ctx, ST_PATHFREQ, st);
+        const KsCache &k = ctx->ks;
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * 4);
+        const size_t scratch_bytes = (size_t)nblk * (T + 1) * 4;
+        if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
+            BS_TRY(ensure(ctx, ctx->d_scratch, scratch_bytes));
+            BS_CUDA(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, st));
+        }
+        BS_TRY(ensure(ctx, ctx->d_ovf, (size_t)nblk * bs::OVF_CAP * 4));
+        bs::PathFreqArgs fa;
+        fa.ctg_off = d_ctg_off; fa.ctg_woff = d_ctg_woff; fa.ctg_words = cs.words; fa.ctg_mask = cs.mask;
+        fa.ctg_seg = d_ctg_seg; fa.w = (const int32_t *)ws.w.p; fa.total = (const int32_t *)ws.total.p;
+        fa.tab_row = (const int32_t *)ctx->d_tab_row.p; fa.yv = (const double *)k.yv.p; fa.ycum = (const int32_t *)ws.ycnt.p;
+        fa.scratch = (int32_t *)ctx->d_scratch.p; fa.ovf_cnt = (int32_t *)ctx->d_ovf.p; fa.status = (int32_t *)ctx->d_status.p;
+        fa.R_y = k.R_y; fa.kmer = kmer; fa.T = (int32_t)T; fa.n_contigs = C; fa.ks = o_ksb;
+        BS_LAUNCH(bs::k_ks_path_freq, (unsigned)nblk, kScoreThreads, kScoreThreads * 8 + bs::CC_DENSE * 4 + 16, st, fa);
+        ctx->launches++;
+    }
+    if (e.want_sp) {
+        StageTimer tm(ctx, ST_STARTPOS, st);
+        bs::StartposArgs sa;
+        sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_chars = d_cchars;
+        sa.ctg_seg = d_ctg_seg; sa.tr_off = d_tr_off; sa.tr_woff = d_tr_woff; sa.tr_words = ts.words; sa.tr_mask = ts.mask;
+        sa.tr_chars = d_tchars; sa.total = (const int32_t *)ws.total.p; sa.n_contigs = C; sa.startpos = o_startpos;
+        BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kScoreThreads, 0, st, sa);
+        ctx->launches++;
+    }
+    BS_CUDA(cudaGetLastError());
+    BS_CUDA(cudaEventRecord(ws.ev_compute, st));
+
+    // ---------------- results ----------------
+    if (e.dev_res) {
+        if (res->lev_dist_vs_true) BS_CUDA(cudaMemsetAsync(res->lev_dist_vs_true + ch.c0, 0, (size_t)C * 4, st));
+        if (!e.want_sp && res->path_prob_dist_startpos) BS_CUDA(cudaMemsetAsync(res->path_prob_dist_startpos + ch.c0, 0, (size_t)C * 4, st));
+        BS_CUDA(cudaEventRecord(ws.ev_d2h, st));
+        ws.in_flight = true;
+        return BS_OK;
+    }
+    {
+        cudaStream_t os = ctx->out_stream;
+        BS_CUDA(cudaStreamWaitEvent(os, ws.ev_compute, 0));
+        StageTimer tm(ctx, ST_D2H, os);
+        auto d2h = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+            if (!dst || !src || !bytes) return cudaSuccess;
+            return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, os);
+        };
+        auto at = [](auto *p, int64_t off) -> void * { return p ? (void *)(p + off) : nullptr; };
+        BS_CUDA(d2h(at(res->sequence_len, ch.c0), o_len, (size_t)C * 4));
+        BS_CUDA(d2h(at(res->kmer_breaks, ch.c0), o_breaks, (size_t)C * 4));
+        BS_CUDA(d2h(at(res->path_prob_dist_startpos, ch.c0), o_startpos, (size_t)C * 4));
+        BS_CUDA(d2h(at(res->bp_score, ch.c0), o_score, (size_t)C * 8));
+        BS_CUDA(d2h(at(res->bp_score_norm_by_break_freqs, ch.c0), o_norm, (size_t)C * 8));
+        BS_CUDA(d2h(at(res->bp_score_norm_by_len, ch.c0), o_bylen, (size_t)C * 8));
+        BS_CUDA(d2h(at(res->ks_stat_prob_dist, ch.c0), o_ksa, (size_t)C * 8));
+        BS_CUDA(d2h(at(res->ks_stat_path_freq, ch.c0), o_ksb, (size_t)C * 8));
+        if (e.want_pd) BS_CUDA(d2h(at(res->path_prob_dist, res->path_prob_dist_off[ch.c0]), o_pd, (size_t)pd_elems * 8));
+        if (e.want_hist) BS_CUDA(d2h(at(res->hist, ch.c0 * (T + 1)), o_hist, (size_t)C * (T + 1) * 4));
+        if (e.want_pos) BS_CUDA(d2h(at(res->pos, res->pos_off[ch.c0]), o_pos, (size_t)pos_elems * 4));
+    }
+    BS_CUDA(cudaEventRecord(ws.ev_d2h, ctx->out_stream));
+    ws.in_flight = true;
     return BS_OK;
 }
 
@@ -265,15 +789,23 @@ int bs_ctx_create(int device, bs_ctx **out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->meta_done)) != cudaSuccess) {
-        fail(nullptr, BS_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
-        delete ctx;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < kWorkspaces; i++)
+        ok = cudaEventCreateWithFlags(&ctx->ws[i].ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ws[i].ev_compute, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ws[i].ev_d2h, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        fail(nullptr, BS_ERR_CUDA, "stream/event creation failed");
+        bs_ctx_destroy(ctx);
         return BS_ERR_CUDA;
     }
-    for (int s = 0; s < ST_COUNT; s++)
-        for (int j = 0; j < 2; j++) cudaEventCreate(&ctx->ev[s][j]);
     ctx->stream = ctx->own_stream;
+    if (const char *env = std::getenv("BS_CHUNK_KB")) {  // tuning / tests: ASCII bytes per pipeline chunk
+        const long kb = std::atol(env);
+        if (kb > 0) ctx->chunk_bytes_host = ctx->chunk_bytes_dev = (int64_t)kb << 10;
+    }
     *out = ctx;
     return BS_OK;
 }
@@ -281,27 +813,35 @@ int bs_ctx_create(int device, bs_ctx **out) {
 void bs_ctx_destroy(bs_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->d_tab_prob, &ctx->d_tab_row, &ctx->ks.rank_x, &ctx->ks.rank_y, &ctx->ks.le_idx,
-                      &ctx->ks.lt_idx, &ctx->ks.yv, &ctx->d_meta, &ctx->d_read_chars, &ctx->d_read_off,
-                      &ctx->d_ctg_chars, &ctx->d_tr_chars, &ctx->d_rwords, &ctx->d_rflags, &ctx->d_cwords,
-                      &ctx->d_cmask, &ctx->d_twords, &ctx->d_tmask, &ctx->d_w, &ctx->d_total, &ctx->d_ycnt,
-                      &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status, &ctx->d_rank_scratch, &ctx->d_out_i32, &ctx->d_out_f64,
-                      &ctx->d_pd, &ctx->d_hist, &ctx->d_pos};
+                      &ctx->ks.lt_idx, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
+                      &ctx->d_rank_scratch, &ctx->d_counters};
     for (DevBuf *b : bufs) release(*b);
-    if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
-    for (int s = 0; s < ST_COUNT; s++)
-        for (int j = 0; j < 2; j++)
-            if (ctx->ev[s][j]) cudaEventDestroy(ctx->ev[s][j]);
-    if (ctx->meta_done) cudaEventDestroy(ctx->meta_done);
+    for (Workspace &w : ctx->ws) {
+        DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
+                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.head, &w.next, &w.odd_head,
+                        &w.out_i32, &w.out_f64, &w.pd, &w.hist, &w.pos};
+        for (DevBuf *b : wb) release(*b);
+        if (w.h_meta) cudaFreeHost(w.h_meta);
+        if (w.ev_h2d) cudaEventDestroy(w.ev_h2d);
+        if (w.ev_compute) cudaEventDestroy(w.ev_compute);
+        if (w.ev_d2h) cudaEventDestroy(w.ev_d2h);
+    }
+    for (TimedSpan &t : ctx->spans) {
+        if (t.a) cudaEventDestroy(t.a);
+        if (t.b) cudaEventDestroy(t.b);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     delete ctx;
 }
 
 int bs_ctx_set_stream(bs_ctx *ctx, void *cuda_stream) {
     if (!ctx) return BS_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    BS_CUDA(cudaStreamSynchronize(ctx->stream));
+    BS_TRY(sync_all(ctx));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return BS_OK;
 }
@@ -309,8 +849,7 @@ int bs_ctx_set_stream(bs_ctx *ctx, void *cuda_stream) {
 int bs_ctx_synchronize(bs_ctx *ctx) {
     if (!ctx) return BS_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    BS_CUDA(cudaStreamSynchronize(ctx->stream));
-    return BS_OK;
+    return sync_all(ctx);
 }
 
 int64_t bs_ctx_launch_count(const bs_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -321,20 +860,22 @@ int bs_ctx_enable_timing(bs_ctx *ctx, int on) {
     return BS_OK;
 }
 
-// per-stage device time (ms) of the last scoring call; order: h2d, pack, place, score, spectrum,
-// prob_dist_ks, ks_path_freq, startpos, d2h.  Returns the number of stages written.
+// per-stage device time (ms) of the last scoring call, summed over its chunks; order: h2d, pack,
+// place, score, spectrum, prob_dist_ks, ks_path_freq, startpos, d2h.  Returns the number written.
 int bs_ctx_last_timings(bs_ctx *ctx, double *ms, int n) {
     if (!ctx || !ms) return 0;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    int k = 0;
-    for (; k < n && k < ST_COUNT; k++) {
-        float t = -1.f;
-        if (ctx->timing && ctx->ev_used[k]) {
-            if (cudaEventElapsedTime(&t, ctx->ev[k][0], ctx->ev[k][1]) != cudaSuccess) t = -1.f;
-        }
-        ms[k] = t;
+    sync_all(ctx);
+    double acc[ST_COUNT];
+    bool used[ST_COUNT] = {};
+    for (int i = 0; i < ST_COUNT; i++) acc[i] = 0.0;
+    for (size_t i = 0; i < ctx->spans_used; i++) {
+        float t = 0.f;
+        const TimedSpan &sp = ctx->spans[i];
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { acc[sp.stage] += t; used[sp.stage] = true; }
     }
+    int k = 0;
+    for (; k < n && k < ST_COUNT; k++) ms[k] = (ctx->timing && used[k]) ? acc[k] : -1.0;
     return k;
 }
 
@@ -378,6 +919,7 @@ int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, c
         pd[di] = prob[i];
         rd[di] = (int32_t)i;  // a repeated key overrides the earlier row
     }
+    BS_TRY(sync_all(ctx));
     ctx->prob_dense.swap(pd);
     ctx->row_dense.swap(rd);
     if (!ctx->has_truth_table || (int64_t)ctx->T != n) {
@@ -421,385 +963,99 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     if (kmer < 1) return fail(ctx, BS_ERR_INVALID, "kmer must be >= 1 (got %d)", kmer);
     const int64_t S = b->n_segments, N = b->n_reads, C = b->n_contigs;
     if (S < 0 || N < 0 || C < 0) return fail(ctx, BS_ERR_INVALID, "negative counts");
-    if (C > 0x7fffffff || S > 0x7fffffff) return fail(ctx, BS_ERR_INVALID, "too many contigs/segments for one call");
-    int rc;
-    if ((rc = check_offsets(ctx, "contig", b->contig_off, C))) return rc;
-    if ((rc = check_offsets(ctx, "truth", b->truth_off, S))) return rc;
-    if ((rc = check_offsets(ctx, "segment read-start", b->seg_read_start, S))) return rc;
-    if ((rc = check_offsets(ctx, "segment contig-start", b->seg_contig_start, S))) return rc;
+    if (C > 0x7fffffff || S > 0x7fffffff || N > 0xfffffff0ll) return fail(ctx, BS_ERR_INVALID, "too many contigs/segments/reads for one call");
+    BS_TRY(check_offsets(ctx, "contig", b->contig_off, C));
+    BS_TRY(check_offsets(ctx, "truth", b->truth_off, S));
+    BS_TRY(check_offsets(ctx, "segment read-start", b->seg_read_start, S));
+    BS_TRY(check_offsets(ctx, "segment contig-start", b->seg_contig_start, S));
     if (b->seg_read_start[0] != 0 || b->seg_read_start[S] != N || b->seg_contig_start[0] != 0 || b->seg_contig_start[S] != C)
         return fail(ctx, BS_ERR_INVALID, "segment start arrays do not cover all reads/contigs");
-    if (b->read_off) { if ((rc = check_offsets(ctx, "read", b->read_off, N))) return rc; }
+    if (b->read_off) BS_TRY(check_offsets(ctx, "read", b->read_off, N));
     else if (b->read_len < 0) return fail(ctx, BS_ERR_INVALID, "read_len < 0");
     if ((flags & BS_WANT_PROB_DIST) && (!res->path_prob_dist || !res->path_prob_dist_off))
         return fail(ctx, BS_ERR_INVALID, "BS_WANT_PROB_DIST needs path_prob_dist and path_prob_dist_off");
     if ((flags & BS_WANT_POS) && (!res->pos || !res->pos_off)) return fail(ctx, BS_ERR_INVALID, "BS_WANT_POS needs pos and pos_off");
     if ((flags & BS_WANT_HIST) && !res->hist) return fail(ctx, BS_ERR_INVALID, "BS_WANT_HIST needs hist");
+    for (int64_t c = 0; c < C; c++)
+        if (b->contig_off[c + 1] - b->contig_off[c] > 0x7f000000ll) return fail(ctx, BS_ERR_INVALID, "contig %lld longer than 2^31", (long long)c);
+    for (int64_t s = 0; s < S; s++)
+        if (b->truth_off[s + 1] - b->truth_off[s] > 0x7f000000ll) return fail(ctx, BS_ERR_INVALID, "truth %lld longer than 2^31", (long long)s);
     if (C == 0) return BS_OK;
+    const int64_t read_total = b->read_off ? b->read_off[N] : N * (int64_t)b->read_len;
+    if (N > 0 && !b->read_chars && read_total > 0) return fail(ctx, BS_ERR_INVALID, "read_chars is NULL");
+    if (b->contig_off[C] > 0 && !b->contig_chars) return fail(ctx, BS_ERR_INVALID, "contig_chars is NULL");
+    if (b->truth_off[S] > 0 && !b->truth_chars) return fail(ctx, BS_ERR_INVALID, "truth_chars is NULL");
     cudaSetDevice(ctx->device);
-    cudaStream_t st = ctx->stream;
-    for (int i = 0; i < ST_COUNT; i++) ctx->ev_used[i] = false;
-    const bool dev_chars = (flags & BS_DEVICE_CHARS) != 0;
-    const bool dev_res = (flags & BS_DEVICE_RESULT) != 0;
-    const bool want_ks = (flags & BS_WANT_KS) && (res->ks_stat_prob_dist || res->ks_stat_path_freq);
-    const bool want_pd = (flags & BS_WANT_PROB_DIST) != 0;
-    const bool want_pos = (flags & BS_WANT_POS) != 0;
-    const bool want_hist = (flags & BS_WANT_HIST) != 0;
-    const bool want_sp = (flags & BS_WANT_STARTPOS) && res->path_prob_dist_startpos;
-    const int64_t T = ctx->T;
+    ctx->spans_used = 0;
 
-    // ---------------- host metadata ----------------
-    const int64_t read_bytes = b->read_off ? b->read_off[N] : N * (int64_t)b->read_len;
-    const int64_t ctg_bytes = b->contig_off[C];
-    const int64_t tr_bytes = b->truth_off[S];
-    if (N > 0 && !b->read_chars && read_bytes > 0) return fail(ctx, BS_ERR_INVALID, "read_chars is NULL");
-    if (ctg_bytes > 0 && !b->contig_chars) return fail(ctx, BS_ERR_INVALID, "contig_chars is NULL");
-    if (tr_bytes > 0 && !b->truth_chars) return fail(ctx, BS_ERR_INVALID, "truth_chars is NULL");
+    CallEnv e;
+    e.b = b; e.res = res; e.kmer = kmer; e.flags = flags; e.T = ctx->T;
+    e.dev_chars = (flags & BS_DEVICE_CHARS) != 0;
+    e.dev_res = (flags & BS_DEVICE_RESULT) != 0;
+    e.want_ks = (flags & BS_WANT_KS) && (res->ks_stat_prob_dist || res->ks_stat_path_freq);
+    e.want_pd = (flags & BS_WANT_PROB_DIST) != 0;
+    e.want_pos = (flags & BS_WANT_POS) != 0;
+    e.want_hist = (flags & BS_WANT_HIST) != 0;
+    e.want_sp = (flags & BS_WANT_STARTPOS) && res->path_prob_dist_startpos;
+    e.read_chars = b->read_chars;
+    e.roff = b->read_off;
+    e.rlen = b->read_len;
+    // reads given with offsets but all of one length (dense by construction): the fast uniform path
+    if (e.roff && N > 0) {
+        const int64_t l0 = e.roff[1] - e.roff[0];
+        bool uni = l0 >= 1 && l0 <= 0x3fffffff;
+        for (int64_t n = 1; uni && n < N; n++) uni = (e.roff[n + 1] - e.roff[n]) == l0;
+        if (uni) {
+            e.read_chars = b->read_chars + e.roff[0];
+            e.roff = nullptr;
+            e.rlen = (int32_t)l0;
+        }
+    }
+    if (e.want_ks) BS_TRY(prepare_ks(ctx, kmer));
+    if (e.want_ks && res->ks_stat_path_freq) {
+        BS_TRY(ensure(ctx, ctx->d_status, 16));
+        BS_CUDA(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
+    }
 
-    std::vector<int64_t> ctg_woff(C + 1), tr_woff(S + 1);
-    std::vector<int32_t> ctg_seg(C), seed_len(std::max<int64_t>(S, 1));
-    int64_t max_ctg = 0;
-    ctg_woff[0] = 0;
-    for (int64_t c = 0; c < C; c++) {
-        const int64_t L = b->contig_off[c + 1] - b->contig_off[c];
-        if (L > 0x7ffffff0) return fail(ctx, BS_ERR_INVALID, "contig %lld longer than 2^31", (long long)c);
-        max_ctg = std::max(max_ctg, L);
-        ctg_woff[c + 1] = ctg_woff[c] + (L + 31) / 32 + 2;
-    }
-    tr_woff[0] = 0;
-    for (int64_t s = 0; s < S; s++) {
-        const int64_t L = b->truth_off[s + 1] - b->truth_off[s];
-        if (L > 0x7ffffff0) return fail(ctx, BS_ERR_INVALID, "truth %lld longer than 2^31", (long long)s);
-        tr_woff[s + 1] = tr_woff[s] + (L + 31) / 32 + 2;
-        for (int64_t c = b->seg_contig_start[s]; c < b->seg_contig_start[s + 1]; c++) ctg_seg[c] = (int32_t)s;
-    }
-    int64_t max_read = 0;
-    if (b->read_off) {
+    // ---------------- chunks of whole segments ----------------
+    const int64_t target = e.dev_chars ? ctx->chunk_bytes_dev : ctx->chunk_bytes_host;
+    std::vector<Chunk> chunks;
+    {
+        int64_t s0 = 0, bytes = 0;
         for (int64_t s = 0; s < S; s++) {
-            int64_t mn = 32;
-            for (int64_t n = b->seg_read_start[s]; n < b->seg_read_start[s + 1]; n++) {
-                const int64_t l = b->read_off[n + 1] - b->read_off[n];
-                max_read = std::max(max_read, l);
-                if (l > 0 && l < mn) mn = l;
+            const int64_t rb = read_byte_begin(e, b->seg_read_start[s + 1]) - read_byte_begin(e, b->seg_read_start[s]);
+            const int64_t cb = b->contig_off[b->seg_contig_start[s + 1]] - b->contig_off[b->seg_contig_start[s]];
+            const int64_t tb = b->truth_off[s + 1] - b->truth_off[s];
+            const int64_t seg_bytes = rb + cb + tb;
+            if (s > s0 && bytes + seg_bytes > target) {
+                chunks.push_back({s0, s, b->seg_read_start[s0], b->seg_read_start[s], b->seg_contig_start[s0], b->seg_contig_start[s]});
+                s0 = s;
+                bytes = 0;
             }
-            seed_len[s] = (int32_t)mn;
+            bytes += seg_bytes;
         }
-    } else {
-        max_read = b->read_len;
-        for (int64_t s = 0; s < S; s++) seed_len[s] = (int32_t)std::min<int64_t>(32, std::max<int64_t>(1, b->read_len));
+        chunks.push_back({s0, S, b->seg_read_start[s0], b->seg_read_start[S], b->seg_contig_start[s0], b->seg_contig_start[S]});
     }
-    if (max_read > 0x3fffffff) return fail(ctx, BS_ERR_INVALID, "read longer than 2^30");
-    const int W = (int)std::max<int64_t>(1, (max_read + 31) / 32);
-
-    // placement work items: one per (contig, read chunk)
-    int tile_len = (int)std::min<int64_t>(kMaxTile, std::max<int64_t>(32, (max_ctg + 31) / 32 * 32));
-    int hash_size = 64;
-    while (hash_size < tile_len) hash_size <<= 1;
-    std::vector<bs::PlaceItem> items;
-    items.reserve((size_t)C);
-    const int64_t target_items = (int64_t)ctx->sm_count * 8;
-    int64_t max_chunk = 1;
-    for (int64_t c = 0; c < C; c++) {
-        const int32_t s = ctg_seg[c];
-        const int64_t r0 = b->seg_read_start[s], r1 = b->seg_read_start[s + 1];
-        const int64_t nr = r1 - r0;
-        int64_t nchunks = 1;
-        if (C < target_items) nchunks = std::min((target_items + C - 1) / C, std::max<int64_t>(1, nr / kMinChunk));
-        nchunks = std::max(nchunks, (nr + kMaxChunk - 1) / kMaxChunk);
-        nchunks = std::max<int64_t>(nchunks, 1);
-        const int64_t per = (nr + nchunks - 1) / nchunks;
-        for (int64_t k = 0; k < nchunks; k++) {
-            bs::PlaceItem it;
-            it.contig = (int32_t)c;
-            it.seg = s;
-            it.read_begin = r0 + k * per;
-            it.read_end = std::min(r1, it.read_begin + per);
-            if (k > 0 && it.read_begin >= it.read_end) break;
-            max_chunk = std::max(max_chunk, it.read_end - it.read_begin);
-            items.push_back(it);
-        }
+    int k = 0;
+    for (const Chunk &ch : chunks) {
+        if (ch.c1 == ch.c0) continue;  // segments without contigs produce nothing
+        BS_TRY(run_chunk(ctx, ctx->ws[k % kWorkspaces], e, ch));
+        k++;
     }
-    const int found_words = (int)((max_chunk + 31) / 32);
-    const size_t place_smem = bs::place_smem_bytes(tile_len, hash_size, W, found_words);
-    if (place_smem > ctx->smem_optin) return fail(ctx, BS_ERR_INVALID, "placement tile needs %zu bytes of shared memory", place_smem);
-
-    std::vector<int64_t> w_dummy;
-    MetaBuilder mb;
-    const size_t o_ctg_off = mb.add(b->contig_off, (size_t)C + 1);
-    const size_t o_ctg_woff = mb.add(ctg_woff.data(), (size_t)C + 1);
-    const size_t o_ctg_seg = mb.add(ctg_seg.data(), (size_t)C);
-    const size_t o_tr_off = mb.add(b->truth_off, (size_t)S + 1);
-    const size_t o_tr_woff = mb.add(tr_woff.data(), (size_t)S + 1);
-    const size_t o_seg_rs = mb.add(b->seg_read_start, (size_t)S + 1);
-    const size_t o_seed = mb.add(seed_len.data(), (size_t)S);
-    const size_t o_items = mb.add(items.data(), items.size());
-    const size_t o_pd_off = want_pd ? mb.add(res->path_prob_dist_off, (size_t)C + 1) : 0;
-    const size_t o_pos_off = want_pos ? mb.add(res->pos_off, (size_t)C + 1) : 0;
-
-    // previous call's metadata copy must have left the staging block
-    if (ctx->meta_pending) { BS_CUDA(cudaEventSynchronize(ctx->meta_done)); ctx->meta_pending = false; }
-    if (mb.bytes.size() > ctx->h_meta_cap) {
-        if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
-        ctx->h_meta = nullptr;
-        ctx->h_meta_cap = 0;
-        const size_t want = mb.bytes.size() * 2 + 4096;
-        if (cudaHostAlloc(&ctx->h_meta, want, cudaHostAllocDefault) != cudaSuccess)
-            return fail(ctx, BS_ERR_ALLOC, "cudaHostAlloc(%zu) failed", want);
-        ctx->h_meta_cap = want;
-    }
-    std::memcpy(ctx->h_meta, mb.bytes.data(), mb.bytes.size());
-
-    // ---------------- device buffers ----------------
-    const int64_t n_out_i32 = 3 * C, n_out_f64 = 5 * C;
-    const int64_t w_elems = ctg_bytes + C;
-    const int ks_R_y_max = 65537;
-    (void)ks_R_y_max;
-    if ((rc = ensure(ctx, ctx->d_meta, mb.bytes.size()))) return rc;
-    if (!dev_chars) {
-        if ((rc = ensure(ctx, ctx->d_read_chars, (size_t)read_bytes + 16))) return rc;
-        if ((rc = ensure(ctx, ctx->d_ctg_chars, (size_t)ctg_bytes + 16))) return rc;
-        if ((rc = ensure(ctx, ctx->d_tr_chars, (size_t)tr_bytes + 16))) return rc;
-    }
-    if (b->read_off) { if ((rc = ensure(ctx, ctx->d_read_off, (size_t)(N + 1) * 8))) return rc; }
-    if ((rc = ensure(ctx, ctx->d_rwords, (size_t)std::max<int64_t>(N, 1) * W * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->d_rflags, (size_t)std::max<int64_t>(N, 1)))) return rc;
-    if ((rc = ensure(ctx, ctx->d_cwords, (size_t)ctg_woff[C] * 8))) return rc;
-    if ((rc = ensure(ctx, ctx->d_cmask, (size_t)ctg_woff[C] * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->d_twords, (size_t)tr_woff[S] * 8 + 8))) return rc;
-    if ((rc = ensure(ctx, ctx->d_tmask, (size_t)tr_woff[S] * 4 + 8))) return rc;
-    if ((rc = ensure(ctx, ctx->d_w, (size_t)w_elems * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->d_total, (size_t)C * 4))) return rc;
-    if (!dev_res) {
-        if ((rc = ensure(ctx, ctx->d_out_i32, (size_t)n_out_i32 * 4))) return rc;
-        if ((rc = ensure(ctx, ctx->d_out_f64, (size_t)n_out_f64 * 8))) return rc;
-        if (want_pd) { if ((rc = ensure(ctx, ctx->d_pd, (size_t)std::max<int64_t>(res->path_prob_dist_off[C], 1) * 8))) return rc; }
-        if (want_hist) { if ((rc = ensure(ctx, ctx->d_hist, (size_t)C * (T + 1) * 4))) return rc; }
-        if (want_pos) { if ((rc = ensure(ctx, ctx->d_pos, (size_t)std::max<int64_t>(res->pos_off[C], 1) * 4))) return rc; }
-    }
-    if (want_ks && (rc = prepare_ks(ctx, kmer))) return rc;
-
-    unsigned char *dm = (unsigned char *)ctx->d_meta.p;
-    const int64_t *d_ctg_off = (const int64_t *)(dm + o_ctg_off);
-    const int64_t *d_ctg_woff = (const int64_t *)(dm + o_ctg_woff);
-    const int32_t *d_ctg_seg = (const int32_t *)(dm + o_ctg_seg);
-    const int64_t *d_tr_off = (const int64_t *)(dm + o_tr_off);
-    const int64_t *d_tr_woff = (const int64_t *)(dm + o_tr_woff);
-    const int64_t *d_seg_rs = (const int64_t *)(dm + o_seg_rs);
-    const int32_t *d_seed = (const int32_t *)(dm + o_seed);
-    const bs::PlaceItem *d_items = (const bs::PlaceItem *)(dm + o_items);
-    const int64_t *d_pd_off = want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
-    const int64_t *d_pos_off = want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
-
-    const uint8_t *d_rchars, *d_cchars, *d_tchars;
-    {
-        StageTimer tm(ctx, ST_H2D);
-        BS_CUDA(cudaMemcpyAsync(ctx->d_meta.p, ctx->h_meta, mb.bytes.size(), cudaMemcpyHostToDevice, st));
-        BS_CUDA(cudaEventRecord(ctx->meta_done, st));
-        ctx->meta_pending = true;
-        if (dev_chars) {
-            d_rchars = (const uint8_t *)b->read_chars;
-            d_cchars = (const uint8_t *)b->contig_chars;
-            d_tchars = (const uint8_t *)b->truth_chars;
-        } else {
-            if (read_bytes) BS_CUDA(cudaMemcpyAsync(ctx->d_read_chars.p, b->read_chars, (size_t)read_bytes, cudaMemcpyHostToDevice, st));
-            if (ctg_bytes) BS_CUDA(cudaMemcpyAsync(ctx->d_ctg_chars.p, b->contig_chars, (size_t)ctg_bytes, cudaMemcpyHostToDevice, st));
-            if (tr_bytes) BS_CUDA(cudaMemcpyAsync(ctx->d_tr_chars.p, b->truth_chars, (size_t)tr_bytes, cudaMemcpyHostToDevice, st));
-            d_rchars = (const uint8_t *)ctx->d_read_chars.p;
-            d_cchars = (const uint8_t *)ctx->d_ctg_chars.p;
-            d_tchars = (const uint8_t *)ctx->d_tr_chars.p;
-        }
-        if (b->read_off) BS_CUDA(cudaMemcpyAsync(ctx->d_read_off.p, b->read_off, (size_t)(N + 1) * 8, cudaMemcpyHostToDevice, st));
-    }
-
-    // result destinations on the device
-    int32_t *o_len, *o_breaks, *o_startpos, *o_hist = nullptr, *o_pos = nullptr;
-    double *o_score, *o_norm, *o_bylen, *o_ksa, *o_ksb, *o_pd = nullptr;
-    if (dev_res) {
-        o_len = res->sequence_len; o_breaks = res->kmer_breaks; o_startpos = want_sp ? res->path_prob_dist_startpos : nullptr;
-        o_score = res->bp_score; o_norm = res->bp_score_norm_by_break_freqs; o_bylen = res->bp_score_norm_by_len;
-        o_ksa = want_ks ? res->ks_stat_prob_dist : nullptr; o_ksb = want_ks ? res->ks_stat_path_freq : nullptr;
-        if (want_pd) o_pd = res->path_prob_dist;
-        if (want_hist) o_hist = res->hist;
-        if (want_pos) o_pos = res->pos;
-    } else {
-        int32_t *i32 = (int32_t *)ctx->d_out_i32.p;
-        double *f64 = (double *)ctx->d_out_f64.p;
-        o_len = i32; o_breaks = i32 + C; o_startpos = want_sp ? i32 + 2 * C : nullptr;
-        o_score = f64; o_norm = f64 + C; o_bylen = f64 + 2 * C;
-        o_ksa = (want_ks && res->ks_stat_prob_dist) ? f64 + 3 * C : nullptr;
-        o_ksb = (want_ks && res->ks_stat_path_freq) ? f64 + 4 * C : nullptr;
-        if (want_pd) o_pd = (double *)ctx->d_pd.p;
-        if (want_hist) o_hist = (int32_t *)ctx->d_hist.p;
-        if (want_pos) o_pos = (int32_t *)ctx->d_pos.p;
-    }
-
-    BS_CUDA(cudaMemsetAsync(ctx->d_w.p, 0, (size_t)w_elems * 4, st));
-    BS_CUDA(cudaMemsetAsync(ctx->d_total.p, 0, (size_t)C * 4, st));
-    if (o_hist) BS_CUDA(cudaMemsetAsync(o_hist, 0, (size_t)C * (T + 1) * 4, st));
-    if (o_pos && res->pos_off[C] > 0) BS_CUDA(cudaMemsetAsync(o_pos, 0xff, (size_t)res->pos_off[C] * 4, st));
-
-    // ---------------- kernels ----------------
-    const int grid_cap = ctx->sm_count * 32;
-    bs::SeqSet cs{d_cchars, d_ctg_off, d_ctg_woff, (uint64_t *)ctx->d_cwords.p, (uint32_t *)ctx->d_cmask.p, C, ctg_woff[C]};
-    bs::SeqSet ts{d_tchars, d_tr_off, d_tr_woff, (uint64_t *)ctx->d_twords.p, (uint32_t *)ctx->d_tmask.p, S, tr_woff[S]};
-    bs::ReadSet rs{d_rchars, b->read_off ? (const int64_t *)ctx->d_read_off.p : nullptr, b->read_len, W, N,
-                   (uint64_t *)ctx->d_rwords.p, (uint8_t *)ctx->d_rflags.p};
-    {
-        StageTimer tm(ctx, ST_PACK);
-        BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
-        ctx->launches++;
-        if (want_ks || want_sp) {
-            BS_LAUNCH(bs::k_pack_seqs, grid_for(ts.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, ts);
-            ctx->launches++;
-        }
-        if (N > 0) {
-            BS_LAUNCH(bs::k_pack_reads, grid_for(N, kPackThreads, grid_cap), kPackThreads, 0, st, rs);
-            ctx->launches++;
-        }
-    }
-    {
-        StageTimer tm(ctx, ST_PLACE);
-        if (N > 0 && !items.empty()) {
-            bs::PlaceArgs pa;
-            pa.items = d_items;
-            pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff;
-            pa.ctg_words = cs.words; pa.ctg_mask = cs.mask; pa.ctg_chars = d_cchars;
-            pa.reads = rs;
-            pa.seg_seed_len = d_seed; pa.seg_read_start = d_seg_rs;
-            pa.w = (int32_t *)ctx->d_w.p; pa.total = (int32_t *)ctx->d_total.p;
-            pa.pos = o_pos; pa.pos_off = d_pos_off;
-            pa.tile_len = tile_len; pa.hash_size = hash_size; pa.found_words = found_words;
-            pa.scan_mode = (flags & BS_PLACE_SCAN) ? 1 : 0;
-            BS_CUDA(cudaFuncSetAttribute(bs::k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem));
-            BS_LAUNCH(bs::k_place, (unsigned)items.size(), kPlaceThreads, place_smem, st, pa);
-            ctx->launches++;
-        }
-    }
-    {
-        StageTimer tm(ctx, ST_SCORE);
-        bs::ScoreArgs sa;
-        sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask;
-        sa.w = (const int32_t *)ctx->d_w.p; sa.total = (const int32_t *)ctx->d_total.p;
-        sa.tab_prob = (const double *)ctx->d_tab_prob.p; sa.tab_row = (const int32_t *)ctx->d_tab_row.p;
-        sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
-        sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
-        sa.kmer_breaks = o_breaks; sa.hist = o_hist;
-        BS_LAUNCH(bs::k_break_score, (unsigned)std::min<int64_t>(C, grid_cap), kScoreThreads, kScoreThreads * 8 + 16, st, sa);
-        ctx->launches++;
-    }
-    if (want_ks) {
-        const KsCache &k = ctx->ks;
-        const int R_y = std::max(k.R_y, 1);
-        if ((rc = ensure(ctx, ctx->d_ycnt, (size_t)S * R_y * 4))) return rc;
-        {
-            StageTimer tm(ctx, ST_SPECTRUM);
-            BS_CUDA(cudaMemsetAsync(ctx->d_ycnt.p, 0, (size_t)S * R_y * 4, st));
-            if (k.R_y > 0) {
-                bs::SpectrumArgs sp;
-                sp.tr_off = d_tr_off; sp.tr_woff = d_tr_woff; sp.tr_words = ts.words; sp.tr_mask = ts.mask;
-                sp.rank_y = (const int32_t *)k.rank_y.p; sp.ycnt = (int32_t *)ctx->d_ycnt.p;
-                sp.R_y = R_y; sp.kmer = kmer;
-                int64_t max_tr = 0;
-                for (int64_t s = 0; s < S; s++) max_tr = std::max(max_tr, b->truth_off[s + 1] - b->truth_off[s]);
-                sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(64, (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
-                BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, st, sp);
-                ctx->launches++;
-                BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, st, (int32_t *)ctx->d_ycnt.p, R_y);
-                ctx->launches++;
-            }
-        }
-    }
-    if (want_pd || (want_ks && o_ksa)) {
-        StageTimer tm(ctx, ST_PROBDIST);
-        const KsCache &k = ctx->ks;
-        bs::ProbDistArgs pa;
-        pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
-        pa.ctg_seg = d_ctg_seg;
-        pa.tab_prob = (const double *)ctx->d_tab_prob.p; pa.tab_row = (const int32_t *)ctx->d_tab_row.p;
-        const bool ks_a = want_ks && o_ksa;
-        pa.rank_x = ks_a ? (const int32_t *)k.rank_x.p : nullptr;
-        pa.le_idx = ks_a ? (const int32_t *)k.le_idx.p : nullptr;
-        pa.lt_idx = ks_a ? (const int32_t *)k.lt_idx.p : nullptr;
-        pa.ycum = ks_a ? (const int32_t *)ctx->d_ycnt.p : nullptr;
-        pa.R_x = ks_a ? k.R_x : 0; pa.R_y = ks_a ? k.R_y : 0; pa.rank_zero = ks_a ? k.rank_zero : 0;
-        pa.kmer = kmer; pa.n_contigs = C;
-        pa.prob_dist = o_pd; pa.pd_off = d_pd_off; pa.ks = ks_a ? o_ksa : nullptr;
-        // rank histogram: shared memory when it fits (real table: 32 897 ranks = 129 KB), else a
-        // per-block global scratch that stays in L2 (all-distinct tables: 65 537 ranks)
-        bool in_smem = ks_a && bs::probdist_smem_bytes(pa.R_x, kKsThreads, true) + 1024 <= ctx->smem_optin;
-        const size_t smem = bs::probdist_smem_bytes(pa.R_x, kKsThreads, in_smem);
-        BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int per_sm = in_smem ? std::max<int>(1, (int)(ctx->smem_optin / (smem + 1024))) : 2;
-        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm);
-        pa.rank_scratch = nullptr;
-        if (ks_a && !in_smem) {
-            if ((rc = ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * pa.R_x * 4))) return rc;
-            pa.rank_scratch = (int32_t *)ctx->d_rank_scratch.p;
-        }
-        BS_LAUNCH(bs::k_prob_dist_ks, (unsigned)nblk, kKsThreads, smem, st, pa);
-        ctx->launches++;
-    }
-    if (want_ks && o_ksb) {
-        StageTimer tm(ctx, ST_PATHFREQ);
-        const KsCache &k = ctx->ks;
-        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * 4);
-        const size_t scratch_bytes = (size_t)nblk * (T + 1) * 4;
-        if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
-            if ((rc = ensure(ctx, ctx->d_scratch, scratch_bytes))) return rc;
-            BS_CUDA(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, st));
-        }
-        if ((rc = ensure(ctx, ctx->d_ovf, (size_t)nblk * bs::OVF_CAP * 4))) return rc;
-        if ((rc = ensure(ctx, ctx->d_status, 16))) return rc;
-        BS_CUDA(cudaMemsetAsync(ctx->d_status.p, 0, 16, st));
-        bs::PathFreqArgs fa;
-        fa.ctg_off = d_ctg_off; fa.ctg_woff = d_ctg_woff; fa.ctg_words = cs.words; fa.ctg_mask = cs.mask;
-        fa.ctg_seg = d_ctg_seg; fa.w = (const int32_t *)ctx->d_w.p; fa.total = (const int32_t *)ctx->d_total.p;
-        fa.tab_row = (const int32_t *)ctx->d_tab_row.p; fa.yv = (const double *)k.yv.p; fa.ycum = (const int32_t *)ctx->d_ycnt.p;
-        fa.scratch = (int32_t *)ctx->d_scratch.p; fa.ovf_cnt = (int32_t *)ctx->d_ovf.p; fa.status = (int32_t *)ctx->d_status.p;
-        fa.R_y = k.R_y; fa.kmer = kmer; fa.T = (int32_t)T; fa.n_contigs = C; fa.ks = o_ksb;
-        BS_LAUNCH(bs::k_ks_path_freq, (unsigned)nblk, kScoreThreads, kScoreThreads * 8 + bs::CC_DENSE * 4 + 16, st, fa);
-        ctx->launches++;
-    }
-    if (want_sp) {
-        StageTimer tm(ctx, ST_STARTPOS);
-        bs::StartposArgs sa;
-        sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_chars = d_cchars;
-        sa.ctg_seg = d_ctg_seg; sa.tr_off = d_tr_off; sa.tr_woff = d_tr_woff; sa.tr_words = ts.words; sa.tr_mask = ts.mask;
-        sa.tr_chars = d_tchars; sa.total = (const int32_t *)ctx->d_total.p; sa.n_contigs = C; sa.startpos = o_startpos;
-        BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kScoreThreads, 0, st, sa);
-        ctx->launches++;
-    }
-    BS_CUDA(cudaGetLastError());
-
-    // ---------------- results ----------------
-    if (dev_res) {
-        if (res->lev_dist_vs_true) BS_CUDA(cudaMemsetAsync(res->lev_dist_vs_true, 0, (size_t)C * 4, st));
-        return BS_OK;  // asynchronous: the caller orders later work on the same stream
-    }
-    {
-        StageTimer tm(ctx, ST_D2H);
-        auto d2h = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
-            if (!dst || !src || !bytes) return cudaSuccess;
-            return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
-        };
-        BS_CUDA(d2h(res->sequence_len, o_len, (size_t)C * 4));
-        BS_CUDA(d2h(res->kmer_breaks, o_breaks, (size_t)C * 4));
-        BS_CUDA(d2h(res->path_prob_dist_startpos, o_startpos, (size_t)C * 4));
-        BS_CUDA(d2h(res->bp_score, o_score, (size_t)C * 8));
-        BS_CUDA(d2h(res->bp_score_norm_by_break_freqs, o_norm, (size_t)C * 8));
-        BS_CUDA(d2h(res->bp_score_norm_by_len, o_bylen, (size_t)C * 8));
-        BS_CUDA(d2h(res->ks_stat_prob_dist, o_ksa, (size_t)C * 8));
-        BS_CUDA(d2h(res->ks_stat_path_freq, o_ksb, (size_t)C * 8));
-        if (want_pd) BS_CUDA(d2h(res->path_prob_dist, o_pd, (size_t)res->path_prob_dist_off[C] * 8));
-        if (want_hist) BS_CUDA(d2h(res->hist, o_hist, (size_t)C * (T + 1) * 4));
-        if (want_pos) BS_CUDA(d2h(res->pos, o_pos, (size_t)res->pos_off[C] * 4));
+    if (e.dev_res) {
+        // asynchronous: the caller orders later work on the compute stream.  Workspaces are reused
+        // in stream order by the next call, so nothing has to be awaited here.
+        for (Workspace &w : ctx->ws) w.in_flight = false;
+        ctx->best_dirty = false;
+        return BS_OK;
     }
     int32_t status = 0;
-    if (want_ks && o_ksb) BS_CUDA(cudaMemcpyAsync(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, st));
-    BS_CUDA(cudaStreamSynchronize(st));
-    ctx->meta_pending = false;
+    if (e.want_ks && res->ks_stat_path_freq) BS_CUDA(cudaMemcpyAsync(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BS_TRY(sync_all(ctx));
+    for (Workspace &w : ctx->ws) w.in_flight = false;
+    ctx->best_dirty = false;
     if (res->lev_dist_vs_true) std::memset(res->lev_dist_vs_true, 0, (size_t)C * 4);
-    if (want_sp == false && res->path_prob_dist_startpos) std::memset(res->path_prob_dist_startpos, 0, (size_t)C * 4);
+    if (!e.want_sp && res->path_prob_dist_startpos) std::memset(res->path_prob_dist_startpos, 0, (size_t)C * 4);
     if (status) return fail(ctx, BS_ERR_INVALID, "ks_stat_path_freq: more than %d table rows with a count >= %d in one contig", bs::OVF_CAP, bs::CC_DENSE);
     return BS_OK;
 }

@@ -37,7 +37,8 @@ struct SeqSet {
     int64_t total_words;
 };
 
-// reads packed SoA: word j of read i at words[j * n + i]
+// reads packed AoS: word j of read i at words[i * W + j] (a placement candidate is verified from
+// one or two 32-byte sectors)
 struct ReadSet {
     const uint8_t *chars;
     const int64_t *off;  // NULL => uniform_len, dense
@@ -85,13 +86,53 @@ __global__ void k_pack_seqs(SeqSet s) {
     }
 }
 
-// one thread per read: all W words + the "has non-ACGT byte" flag
-__global__ void k_pack_reads(ReadSet r) {
+// ---- read index ------------------------------------------------------------------------------
+// Per segment, a chained hash table over the reads' seeds (their first seed_len bases, seed_len =
+// min(32, shortest read of the segment)): head[tab_off[s] + (hash(seed) & tab_mask[s])] -> read id
+// + 1, next[read] -> next read id + 1 of the same bucket (0 ends the chain).  Reads whose seed
+// cannot be packed (a byte outside ACGT in it, or an empty read) hang on odd_head[s] instead and
+// are placed by byte comparison.  Built by the packing kernels, consumed by k_place_index.
+struct ReadIndex {
+    uint32_t *head;
+    uint32_t *next;           // [N]
+    uint32_t *odd_head;       // [S]
+    const int64_t *tab_off;   // [S]
+    const int32_t *tab_mask;  // [S] table size - 1 (size is a power of two)
+    const int32_t *seed_len;  // [S]
+    const int64_t *seg_read_start;  // [S+1]
+    int32_t n_seg;
+};
+
+// segment owning read n: largest s with seg_read_start[s] <= n (empty segments are skipped)
+__device__ __forceinline__ int segment_of_read(const ReadIndex &ix, int64_t n) {
+    int lo = 0, hi = ix.n_seg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ix.seg_read_start[mid] <= n) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void index_insert(const ReadIndex &ix, int64_t n, uint64_t word0, int len, bool seed_bad) {
+    const int s = segment_of_read(ix, n);
+    const int S = ix.seed_len[s];
+    if (len == 0 || seed_bad) {
+        ix.next[n] = atomicExch(&ix.odd_head[s], (uint32_t)n + 1u);
+    } else {
+        const uint32_t h = seed_hash(word0 & keep_bases(S)) & (uint32_t)ix.tab_mask[s];
+        ix.next[n] = atomicExch(&ix.head[ix.tab_off[s] + h], (uint32_t)n + 1u);
+    }
+}
+
+// general packing (reads of arbitrary lengths): one thread per read, all W words, the
+// "has a byte outside ACGT" flag and the index insertion
+__global__ void k_pack_reads(ReadSet r, ReadIndex ix) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += stride) {
         const int64_t c0 = read_begin(r, i);
         const int32_t len = read_length(r, i);
-        uint32_t any_bad = 0;
+        uint32_t any_bad = 0, seed_bad = 0;
+        uint64_t w0 = 0;
         for (int j = 0; j < r.W; j++) {
             uint64_t w = 0;
             for (int b = 0; b < 32; b++) {
@@ -103,9 +144,103 @@ __global__ void k_pack_reads(ReadSet r) {
                 }
                 w = (w << 2) | code;
             }
-            r.words[(int64_t)j * r.n + i] = w;
+            r.words[i * r.W + j] = w;
+            if (j == 0) { w0 = w; seed_bad = any_bad; }
         }
         r.flags[i] = (uint8_t)any_bad;
+        if (ix.head) index_insert(ix, i, w0, len, seed_bad != 0);
+    }
+}
+
+// ---- fast packing for reads of one common length (the simulated-read case) -------------------
+// 16 ASCII bytes -> 32 bits of 2-bit codes, four bytes at a time inside a 32-bit register:
+//   code  = ((c >> 1) ^ (c >> 2)) & 3 per byte, gathered into one byte by a multiply;
+//   valid = the byte equals "ACGT"[code] (a byte-permute looks the expected letter up).
+__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t &diff) {
+    const uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+    uint32_t u = (t | (t >> 4)) & 0x00ff00ffu;
+    u = u | (u >> 8);  // code of byte i in nibble i
+    diff |= x ^ __byte_perm(0x54474341u, 0u, u & 0xffffu);
+    return t * 0x40100401u;  // top byte = c0 c1 c2 c3 (first base in the most significant bits)
+}
+__device__ __forceinline__ uint32_t pack16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t &diff) {
+    const uint32_t g0 = pack4(x0, diff), g1 = pack4(x1, diff), g2 = pack4(x2, diff), g3 = pack4(x3, diff);
+    const uint32_t hi = __byte_perm(g0, g1, 0x3700u);  // byte3 = g0.3, byte2 = g1.3
+    const uint32_t lo = __byte_perm(g2, g3, 0x0037u);  // byte1 = g2.3, byte0 = g3.3
+    return __byte_perm(hi, lo, 0x3254u);
+}
+
+constexpr int PACK_THREADS = 256;            // one output word per thread and tile
+constexpr int PACK_CELLS = PACK_THREADS * 2 + 4;  // 16-byte cells a tile of 256 words can touch
+
+// One tile = PACK_THREADS consecutive output words (AoS order: read-major).  Their source bytes
+// are one contiguous span of the dense read buffer: staged by coalesced 16-byte loads, converted
+// once per 16-byte cell into shared memory, then each thread cuts its 32 bases out of two or
+// three cells with funnel shifts.  A cell holding any byte outside ACGT flags every read that
+// overlaps it (conservative: flagged reads are verified by byte comparison, still exact).
+__global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, ReadIndex ix) {
+    __shared__ uint32_t s_code[PACK_CELLS];
+    __shared__ uint32_t s_bad[PACK_CELLS];
+    const int tid = threadIdx.x;
+    const int64_t n_words = r.n * r.W;
+    const int64_t total_bytes = r.n * (int64_t)r.uniform_len;
+    const uintptr_t base = (uintptr_t)r.chars;
+    const int L = r.uniform_len;
+    for (int64_t k0 = (int64_t)blockIdx.x * PACK_THREADS; k0 < n_words; k0 += (int64_t)gridDim.x * PACK_THREADS) {
+        int64_t klast = k0 + PACK_THREADS - 1;
+        if (klast >= n_words) klast = n_words - 1;
+        const int64_t lo = (k0 / r.W) * L + (k0 % r.W) * 32;       // first source byte of the tile
+        int64_t hi = (klast / r.W) * L + (klast % r.W) * 32 + 32;  // one past the last
+        if (hi > total_bytes) hi = total_bytes;
+        const int64_t lo16 = lo - (int64_t)((base + (uintptr_t)lo) & 15);  // 16-byte aligned address, may be < 0
+        const int n_cells = (int)((hi - lo16 + 15) >> 4);
+        __syncthreads();
+        for (int ci = tid; ci < n_cells; ci += PACK_THREADS) {
+            const int64_t cb = lo16 + 16 * (int64_t)ci;
+            uint32_t x0, x1, x2, x3;
+            if (cb >= 0 && cb + 16 <= total_bytes) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(r.chars + cb);
+                x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+            } else {  // partly outside the buffer: bytes that do not exist read as 'A'
+                uint32_t xs[4];
+                for (int q = 0; q < 4; q++) {
+                    uint32_t x = 0;
+                    for (int b = 3; b >= 0; b--) {
+                        const int64_t pb = cb + 4 * q + b;
+                        x = (x << 8) | ((pb >= 0 && pb < total_bytes) ? (uint32_t)r.chars[pb] : (uint32_t)'A');
+                    }
+                    xs[q] = x;
+                }
+                x0 = xs[0]; x1 = xs[1]; x2 = xs[2]; x3 = xs[3];
+            }
+            uint32_t diff = 0;
+            s_code[ci] = pack16(x0, x1, x2, x3, diff);
+            s_bad[ci] = diff;
+        }
+        __syncthreads();
+        const int64_t k = k0 + tid;
+        if (k < n_words) {
+            const int64_t n = k / r.W;
+            const int j = (int)(k % r.W);
+            const int64_t a = n * L + 32 * j - lo16;  // byte offset inside the staged span
+            const int ci = (int)(a >> 4);
+            const uint32_t sh = 2u * (uint32_t)(a & 15);
+            const int rem = L - 32 * j;  // bases of this word that belong to the read (may exceed 32)
+            // cells past the staged span are only touched by bases beyond the read: clamp the index
+            const int c1 = ci + 1 < n_cells ? ci + 1 : n_cells - 1, c2 = ci + 2 < n_cells ? ci + 2 : n_cells - 1;
+            const uint32_t w0 = s_code[ci], w1 = s_code[c1], w2 = s_code[c2];
+            const uint32_t o_hi = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
+            const uint32_t o_lo = sh ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;
+            const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(rem);
+            r.words[k] = word;
+            // cells overlapping this word's own bytes [a, a + min(rem, 32))
+            const int last_cell = (int)((a + (rem < 32 ? rem : 32) - 1) >> 4);
+            uint32_t bad = s_bad[ci];
+            if (last_cell >= ci + 1) bad |= s_bad[c1];
+            if (last_cell >= ci + 2) bad |= s_bad[c2];
+            if (bad) atomicOr(reinterpret_cast<unsigned *>(r.flags) + (n >> 2), 1u << (8 * (int)(n & 3)));
+            if (j == 0 && ix.head) index_insert(ix, n, word, L, bad != 0);
+        }
     }
 }
 
@@ -157,7 +292,7 @@ __device__ __forceinline__ bool match_packed(const uint64_t *s_seq, const uint32
     const int nw = (len + 31) >> 5;
     for (int j = 0; j < nw; j++) {
         const int rem = len - 32 * j;
-        const uint64_t rw = (j == 0) ? r0 : __ldg(&rd.words[(int64_t)j * rd.n + n]);
+        const uint64_t rw = (j == 0) ? r0 : __ldg(&rd.words[n * rd.W + j]);
         const uint64_t cw = window64(s_seq[idx + j], s_seq[idx + j + 1], o);
         if ((cw ^ rw) & keep_bases(rem)) return false;
         if (window32(s_mask[idx + j], s_mask[idx + j + 1], o) & keep_bits(rem)) return false;
@@ -242,7 +377,7 @@ __global__ void k_place(PlaceArgs a) {
                         if (i == len) { best = p; break; }
                     }
                 } else {
-                    const uint64_t r0 = __ldg(&a.reads.words[n]);
+                    const uint64_t r0 = __ldg(&a.reads.words[n * a.reads.W]);
                     if (a.scan_mode) {
                         for (int pr = 0; pr < Lt; pr++) {
                             if (t0 + pr + len > L) break;
@@ -272,6 +407,166 @@ __global__ void k_place(PlaceArgs a) {
         }
     }
     if ((tid & 31) == 0 && placed) atomicAdd(&a.total[c], placed);
+}
+
+// ------------------------------------------------------------------------------------------
+// placement through the read index (default).  The contig streams past the segment's read
+// index: every contig position looks its seed up, candidates are verified on the packed words
+// (XOR of whole words under the validity mask), and the LEFTMOST position per (read, contig)
+// wins through an atomicMin on a per-block scratch row -- std::string::find semantics of
+// upstream lib/BreakageScorer.cpp:241.  Work per contig is O(L_c + hits) instead of O(U * L_c).
+// ------------------------------------------------------------------------------------------
+
+constexpr uint32_t POS_INF = 0x7f7f7f7fu;  // memset-able "no position yet"
+
+struct PlaceIxArgs {
+    const int32_t *order;  // [n_items] contig ids, longest first
+    int32_t n_items;
+    int32_t *work_counter;  // zero on entry
+    const int64_t *ctg_off;
+    const int64_t *ctg_woff;
+    const uint64_t *ctg_words;
+    const uint32_t *ctg_mask;
+    const uint8_t *ctg_chars;
+    const int32_t *ctg_seg;
+    ReadSet reads;
+    ReadIndex ix;
+    uint32_t *best;       // [gridDim][best_stride], all POS_INF on entry and on exit
+    int64_t best_stride;  // >= reads of the largest segment
+    int32_t *w;           // position weights: contig c, position p at ctg_off[c] + c + p
+    int32_t *total;       // [C] reads placed (kmer_breaks)
+    int32_t *pos;         // optional
+    const int64_t *pos_off;
+    int32_t hit_cap;      // shared-memory list of reads placed in the current contig
+};
+
+// leftmost byte-exact occurrence of read n in contig text, or -1 (reads that cannot be packed)
+__device__ __forceinline__ int64_t find_bytes(const uint8_t *cc, int64_t L, const uint8_t *rc, int len) {
+    if (len == 0) return 0;  // std::string::find("") == 0
+    for (int64_t p = 0; p + len <= L; p++) {
+        int i = 0;
+        while (i < len && cc[p + i] == rc[i]) i++;
+        if (i == len) return p;
+    }
+    return -1;
+}
+
+// does read n (length len, packed words rw) equal the contig at position p?
+__device__ __forceinline__ bool verify_at(const PlaceIxArgs &a, const uint64_t *gw, const uint32_t *gm, const uint8_t *cc,
+                                          int64_t p, int64_t n, int len, uint64_t w0) {
+    if (a.reads.flags[n] & 1) {  // bytes outside ACGT somewhere in (or next to) the read: compare the text
+        const uint8_t *rc = a.reads.chars + read_begin(a.reads, n);
+        for (int i = 0; i < len; i++)
+            if (cc[p + i] != rc[i]) return false;
+        return true;
+    }
+    const int64_t idx = p >> 5;
+    const uint32_t o = (uint32_t)(p & 31);
+    const int nw = (len + 31) >> 5;
+    const uint64_t *rw = a.reads.words + n * a.reads.W;
+    uint64_t c_lo = __ldg(&gw[idx]);
+    uint32_t m_lo = __ldg(&gm[idx]);
+    for (int j = 0; j < nw; j++) {
+        const int rem = len - 32 * j;
+        const uint64_t c_hi = __ldg(&gw[idx + j + 1]);
+        const uint32_t m_hi = __ldg(&gm[idx + j + 1]);
+        const uint64_t r = (j == 0) ? w0 : __ldg(&rw[j]);
+        if ((window64(c_lo, c_hi, o) ^ r) & keep_bases(rem)) return false;
+        if (window32(m_lo, m_hi, o) & keep_bits(rem)) return false;
+        c_lo = c_hi;
+        m_lo = m_hi;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_place_index(PlaceIxArgs a) {
+    uint32_t *s_hits = (uint32_t *)bs_dyn_smem();
+    __shared__ int s_item, s_nhit, s_placed;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    uint32_t *best = a.best + (int64_t)blockIdx.x * a.best_stride;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; }
+        __syncthreads();
+        const int item = s_item;
+        if (item >= a.n_items) break;
+        const int c = a.order[item];
+        const int s = a.ctg_seg[c];
+        const int64_t coff = a.ctg_off[c];
+        const int64_t L = a.ctg_off[c + 1] - coff;
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
+        const uint8_t *cc = a.ctg_chars + coff;
+        const int64_t r0 = a.ix.seg_read_start[s];
+        const int64_t n_seg_reads = a.ix.seg_read_start[s + 1] - r0;
+        const int S = a.ix.seed_len[s];
+        const uint32_t *head = a.ix.head + a.ix.tab_off[s];
+        const uint32_t hmask = (uint32_t)a.ix.tab_mask[s];
+        const uint64_t keepS = keep_bases(S);
+        const uint32_t keepSm = keep_bits(S);
+
+        // ---- every contig position against the index ----
+        if (n_seg_reads > 0) {
+            for (int64_t p = tid; p + S <= L; p += nthr) {
+                const int64_t idx = p >> 5;
+                const uint32_t o = (uint32_t)(p & 31);
+                if (window32(__ldg(&gm[idx]), __ldg(&gm[idx + 1]), o) & keepSm) continue;  // seed window holds a non-ACGT base
+                const uint64_t seed = window64(__ldg(&gw[idx]), __ldg(&gw[idx + 1]), o) & keepS;
+                uint32_t q = head[seed_hash(seed) & hmask];
+                while (q != 0) {
+                    const int64_t n = (int64_t)q - 1;
+                    q = a.ix.next[n];
+                    const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
+                    if ((w0 ^ seed) & keepS) continue;
+                    const int len = read_length(a.reads, n);
+                    if (p + len > L) continue;
+                    if (!verify_at(a, gw, gm, cc, p, n, len, w0)) continue;
+                    const uint32_t old = atomicMin(&best[n - r0], (uint32_t)p);
+                    if (old == POS_INF) {
+                        const int slot = atomicAdd(&s_nhit, 1);
+                        if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
+                    }
+                }
+            }
+            // ---- reads outside the index: text comparison, one read per thread ----
+            int i = 0;
+            for (uint32_t q = a.ix.odd_head[s]; q != 0; i++) {
+                const int64_t n = (int64_t)q - 1;
+                q = a.ix.next[n];
+                if (i % nthr != tid) continue;
+                const int64_t p = find_bytes(cc, L, a.reads.chars + read_begin(a.reads, n), read_length(a.reads, n));
+                if (p < 0) continue;
+                best[n - r0] = (uint32_t)p;  // each such read is visited by exactly one thread
+                const int slot = atomicAdd(&s_nhit, 1);
+                if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        // ---- leftmost positions -> position weights ----
+        const int nh = s_nhit;
+        int placed = 0;
+        if (nh <= a.hit_cap) {
+            for (int h = tid; h < nh; h += nthr) {
+                const uint32_t nl = s_hits[h];
+                const uint32_t p = atomicExch(&best[nl], POS_INF);
+                atomicAdd(&a.w[coff + c + p], 1);
+                if (a.pos) a.pos[a.pos_off[c] + nl] = (int32_t)p;
+                placed++;
+            }
+        } else {  // more distinct reads than the list holds: sweep the whole scratch row
+            for (int64_t nl = tid; nl < n_seg_reads; nl += nthr) {
+                const uint32_t p = atomicExch(&best[nl], POS_INF);
+                if (p == POS_INF) continue;
+                atomicAdd(&a.w[coff + c + p], 1);
+                if (a.pos) a.pos[a.pos_off[c] + nl] = (int32_t)p;
+                placed++;
+            }
+        }
+        if (placed) atomicAdd(&s_placed, placed);
+        __syncthreads();
+        if (tid == 0) a.total[c] = s_placed;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

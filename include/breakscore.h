@@ -54,7 +54,8 @@ enum {
 #define BS_WANT_HIST      0x004u /* fill hist: dense per-contig break-k-mer counts (parity/debug) */
 #define BS_WANT_POS       0x008u /* fill pos: leftmost match of every read in every contig (parity/debug) */
 #define BS_WANT_STARTPOS  0x010u /* fill path_prob_dist_startpos (lib/BreakageScorer.cpp:273-274) */
-#define BS_PLACE_SCAN     0x100u /* placement by exhaustive scan instead of the seed index (same results) */
+#define BS_PLACE_SCAN     0x100u /* placement by exhaustive all-pairs scan of the contig tile in shared memory (same results) */
+#define BS_PLACE_TILE     0x800u /* placement by a seed index over the contig tile, reads streamed past it (same results) */
 #define BS_DEVICE_CHARS   0x200u /* read_chars / contig_chars / truth_chars are DEVICE pointers */
 #define BS_DEVICE_RESULT  0x400u /* every non-NULL pointer in bs_result is a DEVICE pointer */
 #define BS_DEFAULT_FLAGS (BS_WANT_PROB_DIST | BS_WANT_KS | BS_WANT_STARTPOS)

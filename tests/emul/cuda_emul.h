@@ -204,6 +204,20 @@ inline T __shfl_up_sync(unsigned, T v, unsigned d) {
     unsigned l = bs_emul::t_lane;
     return bs_emul_shfl(v, l >= d ? l - d : l);
 }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned sel = (s >> (4 * i)) & 0xf;
+        unsigned byte = (unsigned)((v >> (8 * (sel & 7))) & 0xff);
+        if (sel & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+struct uint4 {
+    unsigned x, y, z, w;
+};
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
@@ -213,7 +227,7 @@ typedef void *cudaStream_t;
 typedef struct bs_emul_event { double t; } *cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaEventDisableTiming = 2 };
 struct cudaDeviceProp {
     char name[256];
     int major, minor, multiProcessorCount;
@@ -241,6 +255,8 @@ inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new bs_emul_event{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

@@ -18,17 +18,18 @@ def test_reference_vectors(case, emul_scorer, kmers, table_set):
 
 
 @pytest.mark.parametrize("params", P.SMALL, ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL])
-@pytest.mark.parametrize("scan", [False, True], ids=["seed_index", "scan"])
-def test_small_segments_vs_oracle(params, scan, emul_scorer, oracle, kmers, prob):
+@pytest.mark.parametrize("mode", [0, B.PLACE_TILE, B.PLACE_SCAN], ids=["read_index", "tile_index", "scan"])
+def test_small_segments_vs_oracle(params, mode, emul_scorer, oracle, kmers, prob):
     seg = P.make(*params)
-    P.check_segment(emul_scorer, oracle, kmers, prob, seg, flags=P.FULL | (B.PLACE_SCAN if scan else 0))
+    P.check_segment(emul_scorer, oracle, kmers, prob, seg, flags=P.FULL | mode)
 
 
+@pytest.mark.parametrize("mode", [0, B.PLACE_TILE, B.PLACE_SCAN], ids=["read_index", "tile_index", "scan"])
 @pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
-def test_edge_inputs(name, contigs, reads, truth, kmer, emul_scorer, oracle, kmers, prob):
+def test_edge_inputs(name, contigs, reads, truth, kmer, mode, emul_scorer, oracle, kmers, prob):
     from genomeassembler_dev_b200.synth import Segment
     seg = Segment(truth, None, contigs)
-    P.check_segment(emul_scorer, oracle, kmers, prob, seg, kmer=kmer, reads=reads)
+    P.check_segment(emul_scorer, oracle, kmers, prob, seg, kmer=kmer, reads=reads, flags=P.FULL | mode)
 
 
 def test_random_pass_keeps_real_truth_table(emul_scorer, oracle, kmers, prob):
@@ -63,3 +64,20 @@ def test_argument_errors(emul_scorer, kmers, prob):
     with pytest.raises(B.BreakscoreError):
         emul_scorer.score_batch(np.zeros(4, np.uint8), None, 2, np.zeros(4, np.uint8), [0, 4, 2], np.zeros(4, np.uint8),
                                 [0, 4], [0, 2], [0, 2])
+
+
+def test_chunked_pipeline_equals_one_chunk(emul_lib, emul_scorer, kmers, prob, monkeypatch):
+    """many small pipeline chunks (two workspaces reused) == one chunk, bit for bit"""
+    from genomeassembler_dev_b200 import synth
+    b = synth.make_batch(7, seed=90, length=1500, read_len=30, coverage=6, contigs_lo=1, contigs_hi=4)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+            b.seg_read_start, b.seg_contig_start)
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS
+    emul_scorer.set_table(kmers, prob)
+    one = emul_scorer.score_batch(*args, flags=flags)
+    monkeypatch.setenv("BS_CHUNK_KB", "12")
+    with B.BreakageScorer(0, emul_lib) as sc:
+        sc.set_table(kmers, prob)
+        many = sc.score_batch(*args, flags=flags)
+    for k in one:
+        assert np.array_equal(one[k], many[k], equal_nan=True), k

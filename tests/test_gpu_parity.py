@@ -26,18 +26,19 @@ def test_reference_vectors(case, gpu_scorer, kmers, table_set):
 
 
 @pytest.mark.parametrize("params", P.SMALL + P.MEDIUM, ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL + P.MEDIUM])
-@pytest.mark.parametrize("scan", [False, True], ids=["seed_index", "scan"])
-def test_segments_vs_oracle(params, scan, gpu_scorer, oracle, kmers, prob):
+@pytest.mark.parametrize("mode", [0, B.PLACE_TILE, B.PLACE_SCAN], ids=["read_index", "tile_index", "scan"])
+def test_segments_vs_oracle(params, mode, gpu_scorer, oracle, kmers, prob):
     seg = P.make(*params)
     before = gpu_scorer.launch_count
-    P.check_segment(gpu_scorer, oracle, kmers, prob, seg, flags=P.FULL | (B.PLACE_SCAN if scan else 0))
+    P.check_segment(gpu_scorer, oracle, kmers, prob, seg, flags=P.FULL | mode)
     assert gpu_scorer.launch_count > before
 
 
+@pytest.mark.parametrize("mode", [0, B.PLACE_TILE, B.PLACE_SCAN], ids=["read_index", "tile_index", "scan"])
 @pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
-def test_edge_inputs(name, contigs, reads, truth, kmer, gpu_scorer, oracle, kmers, prob):
+def test_edge_inputs(name, contigs, reads, truth, kmer, mode, gpu_scorer, oracle, kmers, prob):
     seg = synth.Segment(truth, None, contigs)
-    P.check_segment(gpu_scorer, oracle, kmers, prob, seg, kmer=kmer, reads=reads)
+    P.check_segment(gpu_scorer, oracle, kmers, prob, seg, kmer=kmer, reads=reads, flags=P.FULL | mode)
 
 
 def test_random_pass_keeps_real_truth_table(gpu_scorer, oracle, kmers, prob):
@@ -99,10 +100,11 @@ def test_cfg1_properties(cfg1, gpu_scorer, kmers, prob):
     assert np.array_equal(dbl["hist"], 2 * base["hist"])
     np.testing.assert_allclose(dbl["bp_score"], 2 * base["bp_score"], rtol=1e-12)
     np.testing.assert_allclose(dbl["bp_score_norm_by_break_freqs"], base["bp_score_norm_by_break_freqs"], rtol=1e-12)
-    # scan placement and seed-index placement agree
-    scan = gpu_scorer.score(cfg1.contigs, cfg1.reads, cfg1.truth, flags=flags | B.PLACE_SCAN)
-    for k in ("kmer_breaks", "bp_score", "hist"):
-        assert np.array_equal(scan[k], base[k]), k
+    # the three placement kernels agree bit for bit
+    for mode in (B.PLACE_SCAN, B.PLACE_TILE):
+        other = gpu_scorer.score(cfg1.contigs, cfg1.reads, cfg1.truth, flags=flags | mode)
+        for k in ("kmer_breaks", "bp_score", "hist"):
+            assert np.array_equal(other[k], base[k]), k
 
 
 def test_cfg2_shape_batch_properties(gpu_scorer, oracle, kmers, prob):
@@ -136,3 +138,21 @@ def test_argument_errors(gpu_scorer, kmers, prob):
     gpu_scorer.set_table(kmers, prob)
     with pytest.raises(B.BreakscoreError):
         gpu_scorer.score([b"ACGT"], [b"AC"], b"ACGT", kmer=0)
+
+
+def test_chunked_pipeline_equals_one_chunk(product_lib, gpu_scorer, kmers, prob, monkeypatch):
+    """the H2D / compute / D2H pipeline over many chunks == one chunk, bit for bit"""
+    b = synth.make_batch(40, seed=90, length=20000, read_len=100, coverage=20, contigs_lo=2, contigs_hi=10)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+            b.seg_read_start, b.seg_contig_start)
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST
+    gpu_scorer.set_table(kmers, prob)
+    one = gpu_scorer.score_batch(*args, flags=flags)
+    monkeypatch.setenv("BS_CHUNK_KB", "1500")
+    with B.BreakageScorer(0, product_lib) as sc:
+        sc.set_table(kmers, prob)
+        many = sc.score_batch(*args, flags=flags)
+        again = sc.score_batch(*args, flags=flags)
+    for k in one:
+        assert np.array_equal(one[k], many[k], equal_nan=True), k
+        assert np.array_equal(one[k], again[k], equal_nan=True), k
