@@ -1,0 +1,101 @@
+"""Partitioning of a scoring job over the GPUs of one box (one process per GPU).
+
+Segments and contigs are independent units of the path (upstream resets all per-contig state at
+``lib/BreakageScorer.cpp:279-297``), so a rank scores its share with no data-path collective and the
+fixed-width per-contig records are gathered afterwards.
+
+* many segments (cfg-2 study): contiguous runs of whole segments balanced by read x contig work;
+* one segment, many contigs (cfg-4 scaffold sets, cfg-5): contigs dealt out longest-first (LPT) with
+  the segment's reads replicated to every rank.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_segments(seg_read_start, seg_contig_start, contig_off, world: int):
+    """Split segments [0, S) into `world` contiguous runs of about equal sum(N_s * L_s) work.
+    Returns a list of (s0, s1) per rank (possibly empty runs when S < world)."""
+    srs = np.asarray(seg_read_start, dtype=np.int64)
+    scs = np.asarray(seg_contig_start, dtype=np.int64)
+    coff = np.asarray(contig_off, dtype=np.int64)
+    S = len(srs) - 1
+    n_s = np.diff(srs).astype(np.float64)
+    l_s = (coff[scs[1:]] - coff[scs[:-1]]).astype(np.float64)
+    work = n_s * l_s + 1.0
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(cum, cum[-1] * r / world, side="left")))
+    bounds.append(S)
+    bounds = np.maximum.accumulate(np.minimum(bounds, S))
+    return [(int(bounds[r]), int(bounds[r + 1])) for r in range(world)]
+
+
+def shard_contigs_lpt(contig_lens, world: int):
+    """Longest-processing-time-first assignment of contigs to ranks.  Returns a list of index arrays
+    (ascending inside a rank, so a rank's results stay in input order)."""
+    lens = np.asarray(contig_lens, dtype=np.int64)
+    order = np.argsort(-lens, kind="stable")
+    load = np.zeros(world, dtype=np.int64)
+    owner = np.zeros(len(lens), dtype=np.int64)
+    for i in order:
+        r = int(np.argmin(load))
+        owner[i] = r
+        load[r] += int(lens[i]) + 1
+    return [np.nonzero(owner == r)[0] for r in range(world)]
+
+
+def slice_batch(batch, s0: int, s1: int):
+    """The sub-batch of segments [s0, s1) of a synth.Batch-like object (uniform read length), as the
+    argument tuple of BreakageScorer.score_batch."""
+    r0, r1 = int(batch.seg_read_start[s0]), int(batch.seg_read_start[s1])
+    c0, c1 = int(batch.seg_contig_start[s0]), int(batch.seg_contig_start[s1])
+    rl = batch.read_len
+    return (batch.read_chars[r0 * rl:r1 * rl], None, rl,
+            batch.contig_chars[batch.contig_off[c0]:batch.contig_off[c1]], batch.contig_off[c0:c1 + 1] - batch.contig_off[c0],
+            batch.truth_chars[batch.truth_off[s0]:batch.truth_off[s1]], batch.truth_off[s0:s1 + 1] - batch.truth_off[s0],
+            batch.seg_read_start[s0:s1 + 1] - r0, batch.seg_contig_start[s0:s1 + 1] - c0)
+
+
+RECORD_F64 = ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len", "ks_stat_prob_dist", "ks_stat_path_freq")
+RECORD_I32 = ("sequence_len", "kmer_breaks", "path_prob_dist_startpos")
+
+
+def pack_records(res: dict, n: int) -> np.ndarray:
+    """Fixed-width per-contig record block [n, 8] float64 (ints are exact in float64) for the gather."""
+    out = np.full((n, len(RECORD_F64) + len(RECORD_I32)), np.nan, dtype=np.float64)
+    for j, k in enumerate(RECORD_F64):
+        if k in res:
+            out[:, j] = res[k]
+    for j, k in enumerate(RECORD_I32):
+        out[:, len(RECORD_F64) + j] = res[k]
+    return out
+
+
+def unpack_records(rec: np.ndarray) -> dict:
+    out = {k: rec[:, j].copy() for j, k in enumerate(RECORD_F64)}
+    for j, k in enumerate(RECORD_I32):
+        out[k] = rec[:, len(RECORD_F64) + j].astype(np.int32)
+    return out
+
+
+def gather_records(rec: np.ndarray, counts, group=None, dst: int = 0):
+    """torch.distributed gather of per-rank record blocks (variable row counts) to rank `dst`.
+    Works with NCCL (CUDA tensors) and gloo (CPU tensors, used by the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    width = rec.shape[1]
+    pad = int(max(counts))
+    mine = torch.full((pad, width), float("nan"), dtype=torch.float64, device=dev)
+    if rec.shape[0]:
+        mine[:rec.shape[0]] = torch.from_numpy(rec).to(dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    if rank != dst:
+        return None
+    return np.concatenate([out[r][:int(counts[r])].cpu().numpy() for r in range(world)], axis=0)

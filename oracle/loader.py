@@ -136,11 +136,12 @@ def oracle_ks_statistic(x, y) -> float:
 
 
 def ref_calc_breakscore(path, sequencing_reads, true_solution, kmer, bp_kmer, bp_prob,
-                        edit_distance=False, want_prob_dist=True):
+                        edit_distance=False, want_prob_dist=True, lib_path=None):
     """The unmodified upstream calc_breakscore.  ``edit_distance=False`` uses the build whose
     edlib stand-in returns 0 (edit distance is off the scored path and dominates run time)."""
-    lib = _load(os.path.join("_ref", "libref_breakscore.so" if edit_distance
-                             else "libref_breakscore_noedit.so"))
+    # lib_path: another build of the same driver (tests/test_rcpp_glue.py wraps the Rcpp glue with it)
+    lib = C.CDLL(lib_path) if lib_path else _load(os.path.join("_ref", "libref_breakscore.so" if edit_distance
+                                                               else "libref_breakscore_noedit.so"))
     fn = lib.ref_calc_breakscore
     fn.restype = C.c_int
     ct, ct_off = flatten(path)

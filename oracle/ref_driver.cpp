@@ -78,6 +78,7 @@ int ref_calc_breakscore(const char *contig_chars, const int64_t *contig_off, int
     }
 }
 
+#ifndef BS_DRIVER_NO_ASSEMBLE
 // Upstream assemble_contigs (lib/BreakageScorer.cpp:79-174): returns the number of scaffolds
 // and, if out_chars != NULL, writes them '\n'-separated (out_cap bytes available).
 int64_t ref_assemble_contigs(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
@@ -102,5 +103,6 @@ int64_t ref_assemble_contigs(const char *contig_chars, const int64_t *contig_off
         return -1;
     }
 }
+#endif
 
 }  // extern "C"

@@ -1,0 +1,164 @@
+// [[Rcpp::plugins("cpp17")]]
+// Drop-in replacement for the scorer half of upstream lib/BreakageScorer.cpp: the same
+// Rcpp-exported entry point, argument list and returned list (upstream :185-191, :343-353), with
+// the body replaced by one call into libbreakscore.so (include/breakscore.h).  The other export of
+// the upstream file, assemble_contigs (:79-174, host C++), is not part of the accelerated path: keep
+// upstream's definition next to this one.
+//
+// Build from R:
+//   Sys.setenv(PKG_CXXFLAGS = "-I<repo>/include", PKG_LIBS = "-L<repo>/genomeassembler_dev_b200 -lbreakscore -Wl,-rpath,<repo>/genomeassembler_dev_b200")
+//   Rcpp::sourceCpp("BreakageScorer.cpp")
+// No CPU fallback: without a B200 the call stops with the library's error text.
+#include <Rcpp.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "breakscore.h"
+
+namespace {
+
+// process-lifetime device context: table, work buffers and pinned staging survive across calls
+struct Session {
+    bs_ctx *ctx = nullptr;
+    std::vector<std::string> table_kmer;
+    std::vector<double> table_prob;
+    std::vector<double> truth_prob;  // optional: table behind the KS truth side (set_breakscore_truth_prob)
+    bool truth_dirty = false;
+    char *pinned = nullptr;
+    int64_t pinned_cap = 0;
+    ~Session() {
+        if (pinned) bs_host_free(pinned);
+        if (ctx) bs_ctx_destroy(ctx);
+    }
+};
+
+Session &session() {
+    static Session s;
+    if (!s.ctx) {
+        const char *dev = std::getenv("BREAKSCORE_DEVICE");
+        if (bs_ctx_create(dev ? std::atoi(dev) : 0, &s.ctx) != BS_OK) Rcpp::stop(bs_last_error(nullptr));
+    }
+    return s;
+}
+
+void check(Session &s, int rc) {
+    if (rc != BS_OK) Rcpp::stop(bs_last_error(s.ctx));
+}
+
+// strings -> one flat buffer (written at dst) + offsets
+int64_t flat_size(const std::vector<std::string> &v) {
+    int64_t n = 0;
+    for (const auto &x : v) n += (int64_t)x.size();
+    return n;
+}
+char *flatten(const std::vector<std::string> &v, char *dst, std::vector<int64_t> &off) {
+    off.resize(v.size() + 1);
+    int64_t o = 0;
+    for (size_t i = 0; i < v.size(); i++) {
+        off[i] = o;
+        std::memcpy(dst + o, v[i].data(), v[i].size());
+        o += (int64_t)v[i].size();
+    }
+    off[v.size()] = o;
+    return dst + o;
+}
+
+}  // namespace
+
+// Optional: probabilities used for the truth-side distribution of the KS columns.  The upstream
+// driver keeps the REAL table there even in its "random" pass (lib/DeNovoAssembler.R:326-333);
+// call this once with df_prob$all$prob to reproduce that.  An empty vector resets to "same as bp_prob".
+// [[Rcpp::export]]
+void set_breakscore_truth_prob(const std::vector<double> &prob) {
+    Session &s = session();
+    s.truth_prob = prob;
+    s.truth_dirty = true;
+}
+
+// [[Rcpp::export]]
+Rcpp::List calc_breakscore(
+    const std::vector<std::string> &path,
+    const std::vector<std::string> &sequencing_reads,
+    const std::string &true_solution,
+    const int &kmer,
+    const std::vector<std::string> &bp_kmer,
+    const std::vector<double> &bp_prob) {
+    Session &s = session();
+    if (bp_kmer.size() != bp_prob.size()) Rcpp::stop("bp_kmer and bp_prob differ in length");
+
+    // table: uploaded only when it changed (the driver passes the same one for every call of a pass)
+    if (bp_prob != s.table_prob || bp_kmer != s.table_kmer) {
+        std::vector<char> chars((size_t)flat_size(bp_kmer) + 1);
+        std::vector<int64_t> off;
+        flatten(bp_kmer, chars.data(), off);
+        check(s, bs_set_table(s.ctx, chars.data(), off.data(), bp_prob.data(), (int64_t)bp_prob.size()));
+        s.table_kmer = bp_kmer;
+        s.table_prob = bp_prob;
+        s.truth_dirty = true;
+    }
+    if (s.truth_dirty) {
+        if (s.truth_prob.size() == bp_prob.size()) check(s, bs_set_truth_table(s.ctx, s.truth_prob.data(), (int64_t)s.truth_prob.size()));
+        else check(s, bs_set_truth_table(s.ctx, nullptr, 0));
+        s.truth_dirty = false;
+    }
+
+    // inputs: flattened straight into pinned memory (the copy Rcpp's conversion forces anyway)
+    const int64_t need = flat_size(path) + flat_size(sequencing_reads) + (int64_t)true_solution.size() + 64;
+    if (need > s.pinned_cap) {
+        if (s.pinned) bs_host_free(s.pinned);
+        s.pinned = (char *)bs_host_alloc(need + need / 4);
+        s.pinned_cap = s.pinned ? need + need / 4 : 0;
+        if (!s.pinned) Rcpp::stop("pinned host allocation failed");
+    }
+    std::vector<int64_t> ctg_off, read_off;
+    char *ctg_chars = s.pinned;
+    char *read_chars = flatten(path, ctg_chars, ctg_off);
+    char *truth_chars = flatten(sequencing_reads, read_chars, read_off);
+    std::memcpy(truth_chars, true_solution.data(), true_solution.size());
+
+    const int64_t C = (int64_t)path.size();
+    std::vector<int> sequence_len(C), kmer_breaks(C), lev_dist(C), startpos(C);
+    std::vector<double> bp_score(C), norm_freq(C), norm_len(C), ks_a(C), ks_b(C);
+    std::vector<int64_t> pd_off(C + 1, 0);
+    for (int64_t c = 0; c < C; c++) {
+        const int64_t n = (int64_t)path[c].size() - kmer + 1;
+        pd_off[c + 1] = pd_off[c] + (n > 0 ? n : 0);
+    }
+    std::vector<double> pd_flat((size_t)pd_off[C] + 1);
+
+    bs_result r;
+    std::memset(&r, 0, sizeof(r));
+    r.sequence_len = sequence_len.data();
+    r.bp_score = bp_score.data();
+    r.bp_score_norm_by_break_freqs = norm_freq.data();
+    r.bp_score_norm_by_len = norm_len.data();
+    r.kmer_breaks = kmer_breaks.data();
+    r.path_prob_dist_startpos = startpos.data();
+    r.lev_dist_vs_true = lev_dist.data();
+    r.ks_stat_prob_dist = ks_a.data();
+    r.ks_stat_path_freq = ks_b.data();
+    r.path_prob_dist = pd_flat.data();
+    r.path_prob_dist_off = pd_off.data();
+    check(s, bs_score(s.ctx, ctg_chars, ctg_off.data(), C, read_chars, read_off.data(), (int64_t)sequencing_reads.size(),
+                      truth_chars, (int64_t)true_solution.size(), kmer, BS_DEFAULT_FLAGS, &r));
+
+    std::vector<std::vector<double>> path_prob_dist((size_t)C);
+    for (int64_t c = 0; c < C; c++) path_prob_dist[c].assign(pd_flat.begin() + pd_off[c], pd_flat.begin() + pd_off[c + 1]);
+
+    // the upstream list (lib/BreakageScorer.cpp:343-353), input order, plus the KS statistics of
+    // lib/DeNovoAssembler.R:416-424 computed on the device
+    return Rcpp::List::create(
+        Rcpp::Named("sequence") = path,
+        Rcpp::Named("sequence_len") = sequence_len,
+        Rcpp::Named("bp_score") = bp_score,
+        Rcpp::Named("bp_score_norm_by_break_freqs") = norm_freq,
+        Rcpp::Named("bp_score_norm_by_len") = norm_len,
+        Rcpp::Named("kmer_breaks") = kmer_breaks,
+        Rcpp::Named("lev_dist_vs_true") = lev_dist,
+        Rcpp::Named("path_prob_dist_startpos") = startpos,
+        Rcpp::Named("path_prob_dist") = Rcpp::wrap(path_prob_dist),
+        Rcpp::Named("ks_stat_prob_dist") = ks_a,
+        Rcpp::Named("ks_stat_path_freq") = ks_b);
+}

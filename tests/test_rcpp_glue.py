@@ -1,0 +1,41 @@
+"""The Rcpp front-end (rcpp/BreakageScorer.cpp) cannot be built against real Rcpp here (no R in
+the image), so it is compiled against the oracle's stand-in Rcpp.h and driven through the same
+C wrapper as the verbatim reference build (oracle/ref_driver.cpp).  CPU: it compiles and links
+against libbreakscore.so.  GPU: its calc_breakscore returns the reference's list members on the
+reference vectors."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_matches_reference
+
+
+@pytest.fixture(scope="module")
+def glue_lib(product_lib, tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("glue") / "libglue_breakscore.so")
+    pkg = os.path.dirname(product_lib)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w",
+                    "-I", os.path.join(ROOT, "oracle", "shim", "inc"), "-I", os.path.join(ROOT, "include"),
+                    "-DBS_DRIVER_NO_ASSEMBLE", f'-DBS_REFERENCE_SRC="{os.path.join(ROOT, "rcpp", "BreakageScorer.cpp")}"',
+                    os.path.join(ROOT, "oracle", "ref_driver.cpp"), "-o", out,
+                    "-L", pkg, "-lbreakscore", f"-Wl,-rpath,{pkg}"], check=True)
+    return out
+
+
+def test_glue_compiles_and_links(glue_lib):
+    syms = subprocess.run(["nm", "-D", "--defined-only", glue_lib], capture_output=True, text=True, check=True).stdout
+    assert "ref_calc_breakscore" in syms  # the driver's wrapper around the glue's calc_breakscore
+    assert "libbreakscore.so" in subprocess.run(["ldd", glue_lib], capture_output=True, text=True).stdout
+
+
+@pytest.mark.gpu
+def test_glue_returns_the_reference_list(glue_lib, oracle, kmers, table_set, ref_vectors):
+    for case in ref_vectors:
+        if case["table"] not in ("real", "rowid"):
+            continue
+        got = oracle.ref_calc_breakscore(case["path"], case["reads"], case["truth"], case["kmer"], kmers,
+                                         table_set[case["table"]], lib_path=glue_lib)
+        assert_matches_reference(got, case["expected"])
+        assert np.all(got["lev_dist_vs_true"] == 0)
