@@ -37,7 +37,7 @@ constexpr int kPlaceIxThreads = 64;
 #else
 constexpr int kPlaceThreads = 256;
 constexpr int kScoreThreads = 256;
-constexpr int kKsThreads = 1024;
+constexpr int kKsThreads = 512;
 constexpr int kPackThreads = 256;
 constexpr int kPlaceIxThreads = 256;
 #endif
@@ -58,7 +58,9 @@ struct KsCache {
     int kmer = -1;
     uint64_t table_version = 0;
     int R_x = 0, R_y = 0, rank_zero = 0;
-    DevBuf rank_x, rank_y, le_idx, lt_idx, yv;
+    DevBuf win, rank_y, lelt, yv;
+    double y_max = 0.0;
+    int zero_le = -1, zero_lt = -1;  // truth cumulative-count indices of the last y value <= 0 / < 0
 };
 
 // device + pinned staging memory of one in-flight chunk
@@ -67,7 +69,7 @@ struct Workspace {
     size_t h_meta_cap = 0;
     DevBuf meta, read_chars, read_off, ctg_chars, tr_chars;
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
-    DevBuf w, total, ycnt, head, next, odd_head;
+    DevBuf w, total, ycnt, head, next, odd_head, spbest;
     DevBuf out_i32, out_f64, pd, hist, pos;
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
@@ -250,21 +252,29 @@ int prepare_ks(bs_ctx *ctx, int kmer) {
             rank_y[c] = (int32_t)(std::lower_bound(yv.begin(), yv.end(), ctx->tprob_dense[doff + c]) - yv.begin());
         }
     }
-    std::vector<int32_t> le(xv.size()), lt(xv.size());
+    std::vector<bs::LeLt> lelt(xv.size());
     for (size_t i = 0; i < xv.size(); i++) {
-        le[i] = (int32_t)(std::upper_bound(yv.begin(), yv.end(), xv[i]) - yv.begin()) - 1;
-        lt[i] = (int32_t)(std::lower_bound(yv.begin(), yv.end(), xv[i]) - yv.begin()) - 1;
+        lelt[i].le = (int32_t)(std::upper_bound(yv.begin(), yv.end(), xv[i]) - yv.begin()) - 1;
+        lelt[i].lt = (int32_t)(std::lower_bound(yv.begin(), yv.end(), xv[i]) - yv.begin()) - 1;
     }
+    std::vector<bs::WinEntry> win((size_t)ncode);
+    for (int c = 0; c < ncode; c++) {
+        const bool in_table = in_range && ctx->row_dense[doff + c] >= 0;
+        win[c].prob = in_table ? ctx->prob_dense[doff + c] : 0.0;
+        win[c].rank = rank_x[c];
+        win[c].pad = 0;
+    }
+    k.y_max = yv.empty() ? 0.0 : yv.back();
+    k.zero_le = (int)(std::upper_bound(yv.begin(), yv.end(), 0.0) - yv.begin()) - 1;
+    k.zero_lt = (int)(std::lower_bound(yv.begin(), yv.end(), 0.0) - yv.begin()) - 1;
     if (yv.empty()) yv.push_back(0.0);  // keep the device array non-empty; R_y stays 0
-    BS_TRY(ensure(ctx, k.rank_x, rank_x.size() * 4));
+    BS_TRY(ensure(ctx, k.win, win.size() * sizeof(bs::WinEntry)));
     BS_TRY(ensure(ctx, k.rank_y, rank_y.size() * 4));
-    BS_TRY(ensure(ctx, k.le_idx, le.size() * 4));
-    BS_TRY(ensure(ctx, k.lt_idx, lt.size() * 4));
+    BS_TRY(ensure(ctx, k.lelt, lelt.size() * sizeof(bs::LeLt)));
     BS_TRY(ensure(ctx, k.yv, yv.size() * 8));
-    BS_CUDA(cudaMemcpyAsync(k.rank_x.p, rank_x.data(), rank_x.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    BS_CUDA(cudaMemcpyAsync(k.win.p, win.data(), win.size() * sizeof(bs::WinEntry), cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaMemcpyAsync(k.rank_y.p, rank_y.data(), rank_y.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    BS_CUDA(cudaMemcpyAsync(k.le_idx.p, le.data(), le.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    BS_CUDA(cudaMemcpyAsync(k.lt_idx.p, lt.data(), lt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    BS_CUDA(cudaMemcpyAsync(k.lelt.p, lelt.data(), lelt.size() * sizeof(bs::LeLt), cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaMemcpyAsync(k.yv.p, yv.data(), yv.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaStreamSynchronize(ctx->stream));
     k.kmer = kmer;
@@ -320,7 +330,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     const int64_t tr_b0 = b->truth_off[ch.s0], tr_bytes = b->truth_off[ch.s1] - tr_b0;
     const int64_t rd_b0 = read_byte_begin(e, ch.r0), read_bytes = read_byte_begin(e, ch.r1) - rd_b0;
 
-    std::vector<int64_t> ctg_off(C + 1), ctg_woff(C + 1), tr_off(S + 1), tr_woff(S + 1), seg_rs(S + 1), tab_off(std::max<int64_t>(S, 1));
+    std::vector<int64_t> ctg_off(C + 1), ctg_woff(C + 1), tr_off(S + 1), tr_woff(S + 1), seg_rs(S + 1), seg_cs(S + 1), tab_off(std::max<int64_t>(S, 1));
     std::vector<int32_t> ctg_seg(std::max<int64_t>(C, 1)), seed_len(std::max<int64_t>(S, 1)), tab_mask(std::max<int64_t>(S, 1));
     int64_t max_ctg = 0, max_tr = 0;
     ctg_woff[0] = 0;
@@ -336,6 +346,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     for (int64_t s = 0; s <= S; s++) {
         tr_off[s] = b->truth_off[ch.s0 + s] - tr_b0;
         seg_rs[s] = b->seg_read_start[ch.s0 + s] - ch.r0;
+        seg_cs[s] = b->seg_contig_start[ch.s0 + s] - ch.c0;
     }
     for (int64_t s = 0; s < S; s++) {
         const int64_t L = tr_off[s + 1] - tr_off[s];
@@ -371,13 +382,12 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     std::vector<bs::PlaceItem> items;
     int tile_len = 0, hash_size = 0, found_words = 0;
     size_t place_smem = 0;
-    if (!tile_mode) {
-        order.resize((size_t)C);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-            return ctg_off[x + 1] - ctg_off[x] > ctg_off[y + 1] - ctg_off[y];
-        });
-    } else {
+    order.resize((size_t)C);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return ctg_off[x + 1] - ctg_off[x] > ctg_off[y + 1] - ctg_off[y];
+    });
+    if (tile_mode) {
         // tile placement: one work item per (contig, read chunk)
         tile_len = (int)std::min<int64_t>(kMaxTile, std::max<int64_t>(32, (max_ctg + 31) / 32 * 32));
         hash_size = 64;
@@ -432,6 +442,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     const size_t o_tr_off = mb.add(tr_off.data(), (size_t)S + 1);
     const size_t o_tr_woff = mb.add(tr_woff.data(), (size_t)S + 1);
     const size_t o_seg_rs = mb.add(seg_rs.data(), (size_t)S + 1);
+    const size_t o_seg_cs = mb.add(seg_cs.data(), (size_t)S + 1);
     const size_t o_seed = mb.add(seed_len.data(), (size_t)S);
     const size_t o_tab_off = mb.add(tab_off.data(), (size_t)S);
     const size_t o_tab_mask = mb.add(tab_mask.data(), (size_t)S);
@@ -490,10 +501,12 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     const int64_t *d_tr_off = (const int64_t *)(dm + o_tr_off);
     const int64_t *d_tr_woff = (const int64_t *)(dm + o_tr_woff);
     const int64_t *d_seg_rs = (const int64_t *)(dm + o_seg_rs);
+    const int64_t *d_seg_cs = (const int64_t *)(dm + o_seg_cs);
     const int32_t *d_seed = (const int32_t *)(dm + o_seed);
     const int64_t *d_tab_off = (const int64_t *)(dm + o_tab_off);
     const int32_t *d_tab_mask = (const int32_t *)(dm + o_tab_mask);
     const int32_t *d_order = (const int32_t *)(dm + o_order);
+    const int32_t *d_order2 = d_order;
     const bs::PlaceItem *d_items = (const bs::PlaceItem *)(dm + o_items);
     const int64_t *d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
     const int64_t *d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
@@ -551,6 +564,8 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
 
     BS_CUDA(cudaMemsetAsync(ws.w.p, 0, (size_t)w_elems * 4, st));
     BS_CUDA(cudaMemsetAsync(ws.total.p, 0, (size_t)C * 4, st));
+    BS_TRY(ensure(ctx, ctx->d_counters, 64));
+    BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));  // work counters of the persistent kernels
     if (o_hist) BS_CUDA(cudaMemsetAsync(o_hist, 0, (size_t)C * (T + 1) * 4, st));
     if (o_pos && pos_elems > 0) BS_CUDA(cudaMemsetAsync(o_pos, 0xff, (size_t)pos_elems * 4, st));
 
@@ -604,8 +619,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
                 BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
             }
             ctx->best_dirty = true;  // cleared when the call ends without an error
-            BS_TRY(ensure(ctx, ctx->d_counters, 64));
-            BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));
             bs::PlaceIxArgs pa;
             pa.order = d_order; pa.n_items = (int32_t)C; pa.work_counter = (int32_t *)ctx->d_counters.p;
             pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
@@ -633,18 +646,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             ctx->launches++;
         }
     }
-    {
-        StageTimer tm(ctx, ST_SCORE, st);
-        bs::ScoreArgs sa;
-        sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask;
-        sa.w = (const int32_t *)ws.w.p; sa.total = (const int32_t *)ws.total.p;
-        sa.tab_prob = (const double *)ctx->d_tab_prob.p; sa.tab_row = (const int32_t *)ctx->d_tab_row.p;
-        sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
-        sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
-        sa.kmer_breaks = o_breaks; sa.hist = o_hist;
-        BS_LAUNCH(bs::k_break_score, (unsigned)std::min<int64_t>(C, grid_cap), kScoreThreads, kScoreThreads * 8 + 16, st, sa);
-        ctx->launches++;
-    }
     if (e.want_ks) {
         const KsCache &k = ctx->ks;
         const int R_y = std::max(k.R_y, 1);
@@ -663,60 +664,87 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             ctx->launches++;
         }
     }
+    {
+        // scores (+ histogram, + KS of the normalised break histogram); after the truth spectrum
+        StageTimer tm(ctx, ST_SCORE, st);
+        const KsCache &k = ctx->ks;
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * 4);
+        bs::ScoreArgs sa;
+        std::memset(&sa, 0, sizeof(sa));
+        sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + 2;
+        sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_seg = d_ctg_seg;
+        sa.w = (const int32_t *)ws.w.p; sa.total = (const int32_t *)ws.total.p;
+        sa.tab_prob = (const double *)ctx->d_tab_prob.p; sa.tab_row = (const int32_t *)ctx->d_tab_row.p;
+        sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
+        sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
+        sa.kmer_breaks = o_breaks; sa.hist = o_hist;
+        if (ks_b) {
+            const size_t scratch_bytes = (size_t)nblk * (T + 1) * 4;
+            if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
+                BS_TRY(ensure(ctx, ctx->d_scratch, scratch_bytes));
+                BS_CUDA(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, st));
+            }
+            BS_TRY(ensure(ctx, ctx->d_ovf, (size_t)nblk * bs::OVF_CAP * 4));
+            sa.ks_b = o_ksb; sa.yv = (const double *)k.yv.p; sa.ycum = (const int32_t *)ws.ycnt.p; sa.R_y = k.R_y;
+            sa.zero_le = k.zero_le; sa.zero_lt = k.zero_lt; sa.y_max = k.y_max;
+            sa.scratch = (int32_t *)ctx->d_scratch.p; sa.ovf_cnt = (int32_t *)ctx->d_ovf.p; sa.status = (int32_t *)ctx->d_status.p;
+        }
+        BS_LAUNCH(bs::k_break_score, (unsigned)nblk, kScoreThreads, 0, st, sa);
+        ctx->launches++;
+    }
     if (e.want_pd || ks_a) {
         StageTimer tm(ctx, ST_PROBDIST, st);
         const KsCache &k = ctx->ks;
         bs::ProbDistArgs pa;
+        pa.order = d_order2; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
         pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
         pa.ctg_seg = d_ctg_seg;
-        pa.tab_prob = (const double *)ctx->d_tab_prob.p; pa.tab_row = (const int32_t *)ctx->d_tab_row.p;
-        pa.rank_x = ks_a ? (const int32_t *)k.rank_x.p : nullptr;
-        pa.le_idx = ks_a ? (const int32_t *)k.le_idx.p : nullptr;
-        pa.lt_idx = ks_a ? (const int32_t *)k.lt_idx.p : nullptr;
+        pa.win = (kmer >= 1 && kmer <= bs::MAXK) ? (const bs::WinEntry *)k.win.p : nullptr;
+        pa.lelt = (const bs::LeLt *)k.lelt.p;
         pa.ycum = ks_a ? (const int32_t *)ws.ycnt.p : nullptr;
-        pa.R_x = ks_a ? k.R_x : 0; pa.R_y = ks_a ? k.R_y : 0; pa.rank_zero = ks_a ? k.rank_zero : 0;
+        pa.R_x = k.R_x; pa.R_y = k.R_y; pa.rank_zero = k.rank_zero;
         pa.kmer = kmer; pa.n_contigs = C;
         pa.prob_dist = o_pd; pa.pd_off = d_pd_off; pa.ks = ks_a ? o_ksa : nullptr;
-        // rank histogram: shared memory when it fits (real table: 32 897 ranks = 129 KB), else a
-        // per-block global scratch that stays in L2 (all-distinct tables: 65 537 ranks)
-        const bool in_smem = ks_a && bs::probdist_smem_bytes(pa.R_x, kKsThreads, true) + 1024 <= ctx->smem_optin;
-        const size_t smem = bs::probdist_smem_bytes(pa.R_x, kKsThreads, in_smem);
-        BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int per_sm = in_smem ? std::max<int>(1, (int)(ctx->smem_optin / (smem + 1024))) : 2;
+        // rank histogram in shared memory: 16-bit counters (two per word) when no contig has 65 536
+        // windows -- real table: 32 897 ranks = 66 KB, three blocks per SM -- else 32-bit counters,
+        // else (all-distinct tables with long contigs) a per-block global scratch that stays in L2
+        const bool packed = max_ctg - kmer + 1 < 65536;
+        pa.hist_words = ks_a ? (packed ? (k.R_x + 1) / 2 : k.R_x) : 0;
+        const size_t hist_bytes = (size_t)pa.hist_words * 4;
+        const bool in_smem = hist_bytes + 2048 <= ctx->smem_optin;
+        const size_t smem = in_smem ? hist_bytes : 0;
+        const int per_sm = std::max<int>(1, std::min<int>(2048 / kKsThreads, (int)((ctx->smem_optin + 1024) / (smem + 1024))));
         const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm);
         pa.rank_scratch = nullptr;
         if (ks_a && !in_smem) {
-            BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * pa.R_x * 4));
-            pa.rank_scratch = (int32_t *)ctx->d_rank_scratch.p;
+            BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * hist_bytes));
+            pa.rank_scratch = (uint32_t *)ctx->d_rank_scratch.p;
         }
-        BS_LAUNCH(bs::k_prob_dist_ks, (unsigned)nblk, kKsThreads, smem, st, pa);
-        ctx->launches++;
-    }
-    if (ks_b) {
-        StageTimer tm(ctx, ST_PATHFREQ, st);
-        const KsCache &k = ctx->ks;
-        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * 4);
-        const size_t scratch_bytes = (size_t)nblk * (T + 1) * 4;
-        if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
-            BS_TRY(ensure(ctx, ctx->d_scratch, scratch_bytes));
-            BS_CUDA(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, st));
+        if (packed) {
+            BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BS_LAUNCH(bs::k_prob_dist_ks<true>, (unsigned)nblk, kKsThreads, smem, st, pa);
+        } else {
+            BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BS_LAUNCH(bs::k_prob_dist_ks<false>, (unsigned)nblk, kKsThreads, smem, st, pa);
         }
-        BS_TRY(ensure(ctx, ctx->d_ovf, (size_t)nblk * bs::OVF_CAP * 4));
-        bs::PathFreqArgs fa;
-        fa.ctg_off = d_ctg_off; fa.ctg_woff = d_ctg_woff; fa.ctg_words = cs.words; fa.ctg_mask = cs.mask;
-        fa.ctg_seg = d_ctg_seg; fa.w = (const int32_t *)ws.w.p; fa.total = (const int32_t *)ws.total.p;
-        fa.tab_row = (const int32_t *)ctx->d_tab_row.p; fa.yv = (const double *)k.yv.p; fa.ycum = (const int32_t *)ws.ycnt.p;
-        fa.scratch = (int32_t *)ctx->d_scratch.p; fa.ovf_cnt = (int32_t *)ctx->d_ovf.p; fa.status = (int32_t *)ctx->d_status.p;
-        fa.R_y = k.R_y; fa.kmer = kmer; fa.T = (int32_t)T; fa.n_contigs = C; fa.ks = o_ksb;
-        BS_LAUNCH(bs::k_ks_path_freq, (unsigned)nblk, kScoreThreads, kScoreThreads * 8 + bs::CC_DENSE * 4 + 16, st, fa);
         ctx->launches++;
     }
     if (e.want_sp) {
         StageTimer tm(ctx, ST_STARTPOS, st);
+        BS_TRY(ensure(ctx, ws.spbest, (size_t)C * 4));
+        BS_CUDA(cudaMemsetAsync(ws.spbest.p, 0x7f, (size_t)C * 4, st));
         bs::StartposArgs sa;
         sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_chars = d_cchars;
-        sa.ctg_seg = d_ctg_seg; sa.tr_off = d_tr_off; sa.tr_woff = d_tr_woff; sa.tr_words = ts.words; sa.tr_mask = ts.mask;
-        sa.tr_chars = d_tchars; sa.total = (const int32_t *)ws.total.p; sa.n_contigs = C; sa.startpos = o_startpos;
+        sa.ctg_seg = d_ctg_seg; sa.seg_contig_start = d_seg_cs;
+        sa.tr_off = d_tr_off; sa.tr_woff = d_tr_woff; sa.tr_words = ts.words; sa.tr_mask = ts.mask;
+        sa.tr_chars = d_tchars; sa.total = (const int32_t *)ws.total.p; sa.n_contigs = C; sa.n_seg = (int32_t)S;
+        sa.best = (uint32_t *)ws.spbest.p; sa.startpos = o_startpos;
+        // enough blocks to fill the machine even for a single segment; at least 2048 positions each
+        int64_t splits = ((int64_t)ctx->sm_count * 4 + S - 1) / std::max<int64_t>(S, 1);
+        splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 2047) / 2048));
+        sa.splits = (int32_t)splits;
+        BS_LAUNCH(bs::k_startpos_index, (unsigned)(S * splits), kScoreThreads, 0, st, sa);
+        ctx->launches++;
         BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kScoreThreads, 0, st, sa);
         ctx->launches++;
     }
@@ -814,13 +842,12 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->d_tab_prob, &ctx->d_tab_row, &ctx->ks.rank_x, &ctx->ks.rank_y, &ctx->ks.le_idx,
-                      &ctx->ks.lt_idx, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
+    DevBuf *bufs[] = {&ctx->d_tab_prob, &ctx->d_tab_row, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
                       &ctx->d_rank_scratch, &ctx->d_counters};
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
-                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.head, &w.next, &w.odd_head,
+                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.head, &w.next, &w.odd_head, &w.spbest,
                         &w.out_i32, &w.out_f64, &w.pd, &w.hist, &w.pos};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);
@@ -1011,7 +1038,7 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
             e.rlen = (int32_t)l0;
         }
     }
-    if (e.want_ks) BS_TRY(prepare_ks(ctx, kmer));
+    if (e.want_ks || e.want_pd) BS_TRY(prepare_ks(ctx, kmer));
     if (e.want_ks && res->ks_stat_path_freq) {
         BS_TRY(ensure(ctx, ctx->d_status, 16));
         BS_CUDA(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));

@@ -613,14 +613,23 @@ __device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *s_sc
 }
 
 // ------------------------------------------------------------------------------------------
-// break k-mers -> probability-weighted sums (upstream lib/BreakageScorer.cpp:244-303)
+// break k-mers -> probability-weighted sums (upstream lib/BreakageScorer.cpp:244-303), the
+// optional dense histogram, and the KS statistic of the normalised break histogram (variant
+// lib/DeNovoAssembler.cpp:395-420: x = count_row / total for every table row, y = truth
+// distribution) -- one pass family over the position weights of a contig
 // ------------------------------------------------------------------------------------------
 
+constexpr int CC_DENSE = 4096;  // counts below this are tallied in a dense shared-memory array
+constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
+
 struct ScoreArgs {
+    const int32_t *order;   // [C] contig ids, longest first
+    int32_t *work_counter;  // zero on entry
     const int64_t *ctg_off;
     const int64_t *ctg_woff;
     const uint64_t *ctg_words;
     const uint32_t *ctg_mask;
+    const int32_t *ctg_seg;
     const int32_t *w;
     const int32_t *total;
     const double *tab_prob;  // [DENSE_SIZE] probability of a dense k-mer index (0.0 if absent)
@@ -634,23 +643,73 @@ struct ScoreArgs {
     double *norm_by_len;
     int32_t *kmer_breaks;
     int32_t *hist;  // optional [C][T+1]
+    // KS of the normalised break histogram (all NULL / 0 when not wanted)
+    double *ks_b;          // [C]
+    const double *yv;      // [R_y] sorted distinct truth-table values
+    const int32_t *ycum;   // [S][R_y] inclusive cumulative counts of the truth distribution
+    int32_t R_y;
+    int32_t zero_le, zero_lt;  // indices into ycum of the last y value <= 0.0 / < 0.0 (-1: none)
+    double y_max;          // largest truth-table value
+    int32_t *scratch;      // [gridDim][T+1], all zero on entry and on exit
+    int32_t *ovf_cnt;      // [gridDim][OVF_CAP] counts >= CC_DENSE (unsorted)
+    int32_t *status;       // set to 1 if a block ran out of overflow space
 };
 
-// one block per contig; sums in position order with a fixed tree (bit-reproducible, the same
-// for every GPU count)
-__global__ void k_break_score(ScoreArgs a) {
-    double *s_red = (double *)bs_dyn_smem();
+// number of y values <= v (le) and < v (lt), from the cumulative counts
+__device__ __forceinline__ void y_counts_at(const double *yv, const int32_t *ycum, int R_y, double y_max, double v,
+                                            double *le, double *lt) {
+    if (R_y <= 0) { *le = 0.0; *lt = 0.0; return; }
+    if (v > y_max) { *le = *lt = (double)ycum[R_y - 1]; return; }  // the usual case: count/total >> any table value
+    int lo = 0, hi = R_y;  // first index with yv > v
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (yv[mid] <= v) lo = mid + 1; else hi = mid; }
+    const int ule = lo;  // #distinct <= v
+    lo = 0; hi = R_y;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (yv[mid] < v) lo = mid + 1; else hi = mid; }
+    const int ult = lo;  // #distinct < v
+    *le = ule > 0 ? (double)ycum[ule - 1] : 0.0;
+    *lt = ult > 0 ? (double)ycum[ult - 1] : 0.0;
+}
+
+// sum over the block in a fixed order (lane tree, then warps in order): bit-reproducible, the
+// same for every GPU count; valid on thread 0
+__device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL_MASK, v, m);
+    __syncthreads();
+    if (lane == 0) s_w[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) for (int i = 0; i < nwarp; i++) t += s_w[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
+    __shared__ double s_w[32];
+    __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
+    __shared__ int s_item, s_novf, s_maxc, s_nz;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int64_t c = blockIdx.x; c < a.n_contigs; c += gridDim.x) {
+    const bool want_ks = a.ks_b != nullptr;
+    int32_t *scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
+    int32_t *ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    if (want_ks) for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; }
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
         const int64_t coff = a.ctg_off[c];
         const int64_t L = a.ctg_off[c + 1] - coff;
         const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
         const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
         const int32_t *w = a.w + coff + c;
         const int32_t total = a.total[c];
+        const int64_t np = L > 0 ? L : 1;
         double s1 = 0.0, s2 = 0.0;
+        // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS)
         if (total != 0) {
-            const int64_t np = L > 0 ? L : 1;
             for (int64_t p = tid; p < np; p += nthr) {
                 const int32_t wv = w[p];
                 if (wv == 0) continue;
@@ -661,18 +720,102 @@ __global__ void k_break_score(ScoreArgs a) {
                     const double pr = a.tab_prob[di];
                     s1 += pr * (double)wv;
                     s2 += pr * ((double)wv / (double)total);
+                    if (want_ks) atomicAdd(&scratch[row], wv);
                 }
                 if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv);
             }
         }
-        s1 = block_sum(s1, s_red);
-        s2 = block_sum(s2, s_red);
+        s1 = block_sum_fixed(s1, s_w);
+        s2 = block_sum_fixed(s2, s_w);
         if (tid == 0) {
             if (a.sequence_len) a.sequence_len[c] = (int32_t)L;
             if (a.bp_score) a.bp_score[c] = s1;
             if (a.norm_by_break_freqs) a.norm_by_break_freqs[c] = s2;
             if (a.norm_by_len) a.norm_by_len[c] = s1 / (double)(int32_t)L;
             if (a.kmer_breaks) a.kmer_breaks[c] = total;
+        }
+        if (!want_ks) continue;
+        if (total == 0) {  // 0/0 for every row: R drops the NaNs and ks.test stops on empty x
+            if (tid == 0) a.ks_b[c] = qnan;
+            continue;
+        }
+        __threadfence_block();
+        __syncthreads();
+        // pass 2: whoever swaps a row's count out first owns it; tally rows per count value
+        for (int64_t p = tid; p < np; p += nthr) {
+            const int32_t wv = w[p];
+            if (wv == 0) continue;
+            const BreakWindow bw = break_window(p, a.kmer, L);
+            const int di = dense_index_at(gw, gm, bw.start, bw.len);
+            const int32_t row = di >= 0 ? a.tab_row[di] : -1;
+            if (row < 0) continue;
+            const int32_t cnt = atomicExch(&scratch[row], 0);
+            if (cnt == 0) continue;
+            atomicAdd(&s_nz, 1);
+            if (cnt < CC_DENSE) { atomicAdd(&s_cc[cnt], 1); atomicMax(&s_maxc, cnt); }
+            else {
+                const int slot = atomicAdd(&s_novf, 1);
+                if (slot < OVF_CAP) ovf[slot] = cnt; else *a.status = 1;
+            }
+        }
+        __syncthreads();
+        // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them
+        if (tid == 0) {
+            const int32_t *ycum = a.ycum + (int64_t)a.ctg_seg[c] * a.R_y;
+            const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
+            const int novf = s_novf < OVF_CAP ? s_novf : OVF_CAP;
+            double d = 0.0;
+            if (n_y > 0 && a.T > 0) {
+                const double inx = (double)a.T, iny = (double)n_y;
+                int64_t run = (int64_t)a.T - s_nz;  // rows never broken: x value 0
+                if (run > 0) {
+                    const double le = a.zero_le >= 0 ? (double)ycum[a.zero_le] : 0.0;
+                    const double lt = a.zero_lt >= 0 ? (double)ycum[a.zero_lt] : 0.0;
+                    double d1 = lt / iny, d2 = (double)run / inx - le / iny;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    d = d1 > d2 ? d1 : d2;
+                }
+                for (int j = 1; j <= s_maxc; j++) {
+                    const int32_t cnt = s_cc[j];
+                    if (cnt == 0) continue;
+                    s_cc[j] = 0;
+                    double le, lt;
+                    y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)j / (double)total, &le, &lt);
+                    double d1 = (double)run / inx - lt / iny;
+                    run += cnt;
+                    double d2 = (double)run / inx - le / iny;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    if (d1 > d) d = d1;
+                    if (d2 > d) d = d2;
+                }
+                // counts >= CC_DENSE: few; walked in ascending order
+                int32_t last = CC_DENSE - 1;
+                for (int done = 0; done < novf;) {
+                    int32_t cur = 0x7fffffff;
+                    int mult = 0;
+                    for (int i = 0; i < novf; i++) {
+                        const int32_t v = ovf[i];
+                        if (v > last && v < cur) { cur = v; mult = 1; }
+                        else if (v == cur) mult++;
+                    }
+                    double le, lt;
+                    y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)cur / (double)total, &le, &lt);
+                    double d1 = (double)run / inx - lt / iny;
+                    run += mult;
+                    double d2 = (double)run / inx - le / iny;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    if (d1 > d) d = d1;
+                    if (d2 > d) d = d2;
+                    last = cur;
+                    done += mult;
+                }
+            } else {
+                for (int j = 1; j <= s_maxc; j++) s_cc[j] = 0;
+            }
+            a.ks_b[c] = (n_y > 0 && a.T > 0) ? d : qnan;
         }
     }
 }
@@ -728,17 +871,28 @@ __global__ void k_row_cumsum(int32_t *m, int32_t R) {
 // (upstream lib/BreakageScorer.cpp:200-215 and lib/DeNovoAssembler.R:416-424)
 // ------------------------------------------------------------------------------------------
 
+// one entry per k-mer code of the window length: what a window contributes to path_prob_dist
+// (0.0 when the k-mer is not a table row) and the rank of that value among the distinct x values
+struct alignas(16) WinEntry {
+    double prob;
+    int32_t rank;
+    int32_t pad;
+};
+// per x-value rank: index into the truth cumulative counts of the last y value <= / < that x value
+struct LeLt {
+    int32_t le, lt;
+};
+
 struct ProbDistArgs {
+    const int32_t *order;     // [C] contig ids, longest first
+    int32_t *work_counter;    // zero on entry
     const int64_t *ctg_off;
     const int64_t *ctg_woff;
     const uint64_t *ctg_words;
     const uint32_t *ctg_mask;
     const int32_t *ctg_seg;  // [C] segment of a contig
-    const double *tab_prob;
-    const int32_t *tab_row;
-    const int32_t *rank_x;   // [4^kmer] rank of a window's scoring-table value among xv (0.0 included)
-    const int32_t *le_idx;   // [R_x] index into the y cumulative counts of the last y value <= xv[k], -1 none
-    const int32_t *lt_idx;   // [R_x] ... of the last y value < xv[k], -1 none
+    const WinEntry *win;     // [4^kmer], NULL when kmer is outside 1..8 (every window is "not in the table")
+    const LeLt *lelt;        // [R_x]
     const int32_t *ycum;     // [S][R_y] inclusive cumulative counts of the truth distribution
     int32_t R_x, R_y;
     int32_t rank_zero;       // rank of the value 0.0 (windows not in the table)
@@ -747,65 +901,107 @@ struct ProbDistArgs {
     double *prob_dist;       // optional
     const int64_t *pd_off;
     double *ks;              // optional [C]
-    int32_t *rank_scratch;   // [gridDim][R_x] global rank histogram when R_x does not fit shared memory, else NULL
+    uint32_t *rank_scratch;  // [gridDim][hist_words] global rank histogram when it does not fit shared memory, else NULL
+    int32_t hist_words;      // 32-bit words of one rank histogram (packed: two 16-bit counters per word)
 };
 
-BS_HD size_t probdist_smem_bytes(int R_x, int nthr, bool hist_in_smem) {
-    return (hist_in_smem ? (size_t)R_x * 4 : 0) + (size_t)nthr * 8 + 16;
+// PACKED: two 16-bit counters per word (every contig of the launch has < 65536 windows)
+template <bool PACKED>
+__device__ __forceinline__ uint32_t hist_get(const uint32_t *h, int r) {
+    return PACKED ? (h[r >> 1] >> (16 * (r & 1))) & 0xffffu : h[r];
 }
 
-__global__ void k_prob_dist_ks(ProbDistArgs a) {
+template <bool PACKED>
+__global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     const int tid = threadIdx.x, nthr = blockDim.x;
-    unsigned char *sm = bs_dyn_smem();
-    double *s_red = (double *)sm;
-    int64_t *s_scan = (int64_t *)sm;  // same storage, used at different times
-    int32_t *s_hist = a.rank_scratch ? a.rank_scratch + (int64_t)blockIdx.x * a.R_x : (int32_t *)(sm + (size_t)nthr * 8);
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    __shared__ int64_t s_wsum[32];
+    __shared__ double s_wmax[32];
+    __shared__ int s_item;
+    uint32_t *s_hist = a.rank_scratch ? a.rank_scratch + (int64_t)blockIdx.x * a.hist_words : (uint32_t *)bs_dyn_smem();
     const bool want_ks = a.ks != nullptr;
-    const int doff = (a.kmer >= 1 && a.kmer <= MAXK) ? dense_offset(a.kmer) : 0;
-    for (int64_t c = blockIdx.x; c < a.n_contigs; c += gridDim.x) {
+    const int kshift = 64 - 2 * a.kmer;
+    const uint32_t kbits = keep_bits(a.kmer);
+    if (want_ks) {
+        for (int i = tid; i < a.hist_words; i += nthr) s_hist[i] = 0;
+    }
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
         const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
         const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
         const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
         int64_t nwin = L - a.kmer + 1;
         if (nwin < 0) nwin = 0;
-        if (want_ks) {
-            __syncthreads();
-            for (int i = tid; i < a.R_x; i += nthr) s_hist[i] = 0;
-            __syncthreads();
-        }
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
-        for (int64_t p = tid; p < nwin; p += nthr) {
-            const int di = dense_index_at(gw, gm, p, a.kmer);
-            double val = 0.0;
-            int32_t rk = a.rank_zero;
-            if (di >= 0 && a.tab_row[di] >= 0) {
-                val = a.tab_prob[di];
-                if (want_ks) rk = a.rank_x[di - doff];
+        // ---- windows: table value out, rank histogram in ----
+        for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {
+            double val[4];
+            int32_t rk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t p = p0 + (int64_t)u * nthr + tid;
+                val[u] = 0.0;
+                rk[u] = a.rank_zero;
+                if (p < nwin && a.win) {
+                    const int64_t wi = p >> 5;
+                    const uint32_t o = (uint32_t)(p & 31);
+                    if (!(window32(__ldg(&gm[wi]), __ldg(&gm[wi + 1]), o) & kbits)) {
+                        const uint64_t code = window64(__ldg(&gw[wi]), __ldg(&gw[wi + 1]), o) >> kshift;
+                        const WinEntry e = a.win[code];  // one 16-byte gather
+                        val[u] = e.prob;
+                        rk[u] = e.rank;
+                    }
+                }
             }
-            if (pd) pd[p] = val;
-            if (want_ks) atomicAdd(&s_hist[rk], 1);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t p = p0 + (int64_t)u * nthr + tid;
+                if (p < nwin) {
+                    if (pd) pd[p] = val[u];
+                    if (want_ks) {
+                        if (PACKED) atomicAdd(&s_hist[rk[u] >> 1], 1u << (16 * (rk[u] & 1)));
+                        else atomicAdd(&s_hist[rk[u]], 1u);
+                    }
+                }
+            }
         }
         if (!want_ks) continue;
         __syncthreads();
-        // D = sup |F_x - F_y| over the pooled distinct values, evaluated at every x value that
-        // is present: just below it (F_x of the previous step vs #{y < v}) and at it.
+        // ---- D = sup |F_x - F_y| over the pooled distinct values, evaluated at every x value that
+        // is present: just below it (F_x of the previous step vs #{y < v}) and at it ----
         const int64_t seg = a.ctg_seg[c];
         const int32_t *ycum = a.ycum + seg * a.R_y;
         const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
-        const int per = (a.R_x + nthr - 1) / nthr;
-        const int lo = tid * per, hi = (lo + per < a.R_x) ? lo + per : a.R_x;
+        int per = (a.R_x + nthr - 1) / nthr;
+        per += per & 1;  // even: a thread owns whole packed words
+        const int lo = tid * per < a.R_x ? tid * per : a.R_x;
+        const int hi = lo + per < a.R_x ? lo + per : a.R_x;
         int64_t sum = 0;
-        for (int i = lo; i < hi; i++) sum += s_hist[i];
-        int64_t run = block_exclusive_scan(sum, s_scan, nullptr);
+        for (int i = lo; i < hi; i++) sum += hist_get<PACKED>(s_hist, i);
+        // exclusive prefix of the per-thread sums: warp scan, then the warp totals
+        int64_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t o = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int64_t run = incl - sum;
+        for (int w = 0; w < warp; w++) run += s_wsum[w];
         double d = 0.0;
         if (nwin > 0 && n_y > 0) {
             const double inx = (double)nwin, iny = (double)n_y;
             for (int i = lo; i < hi; i++) {
-                const int32_t cnt = s_hist[i];
+                const uint32_t cnt = hist_get<PACKED>(s_hist, i);
                 if (cnt == 0) continue;
-                const int32_t li = a.lt_idx[i], ei = a.le_idx[i];
-                const double lt = li >= 0 ? (double)ycum[li] : 0.0;
-                const double le = ei >= 0 ? (double)ycum[ei] : 0.0;
+                const LeLt q = a.lelt[i];
+                const double lt = q.lt >= 0 ? (double)ycum[q.lt] : 0.0;
+                const double le = q.le >= 0 ? (double)ycum[q.le] : 0.0;
                 double d1 = (double)run / inx - lt / iny;
                 run += cnt;
                 double d2 = (double)run / inx - le / iny;
@@ -815,179 +1011,32 @@ __global__ void k_prob_dist_ks(ProbDistArgs a) {
                 if (d2 > d) d = d2;
             }
         }
-        d = block_max(d, s_red);
-        if (tid == 0) a.ks[c] = (nwin > 0 && n_y > 0) ? d : __longlong_as_double(0x7ff8000000000000ll);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// KS statistic of the normalised break histogram (variant lib/DeNovoAssembler.cpp:395-420):
-// x = count_row / total for every table row, y = truth distribution
-// ------------------------------------------------------------------------------------------
-
-struct PathFreqArgs {
-    const int64_t *ctg_off;
-    const int64_t *ctg_woff;
-    const uint64_t *ctg_words;
-    const uint32_t *ctg_mask;
-    const int32_t *ctg_seg;
-    const int32_t *w;
-    const int32_t *total;
-    const int32_t *tab_row;
-    const double *yv;      // [R_y] sorted distinct truth-table values
-    const int32_t *ycum;   // [S][R_y]
-    int32_t *scratch;      // [gridDim][T+1], all zero on entry and on exit
-    int32_t *ovf_cnt;      // [gridDim][OVF_CAP] counts >= CC_DENSE (unsorted), and
-    int32_t *status;       // set to 1 if a block ran out of overflow space
-    int32_t R_y;
-    int32_t kmer;
-    int32_t T;
-    int64_t n_contigs;
-    double *ks;            // [C]
-};
-constexpr int CC_DENSE = 4096;  // counts below this are tallied in a dense shared-memory array
-constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
-
-// number of y values <= v (le) and < v (lt), from the cumulative counts
-__device__ __forceinline__ void y_counts_at(const double *yv, const int32_t *ycum, int R_y, double v,
-                                            double *le, double *lt) {
-    // first index with yv > v
-    int lo = 0, hi = R_y;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (yv[mid] <= v) lo = mid + 1; else hi = mid; }
-    const int ule = lo;  // #distinct <= v
-    lo = 0; hi = R_y;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (yv[mid] < v) lo = mid + 1; else hi = mid; }
-    const int ult = lo;  // #distinct < v
-    *le = ule > 0 ? (double)ycum[ule - 1] : 0.0;
-    *lt = ult > 0 ? (double)ycum[ult - 1] : 0.0;
-}
-
-__global__ void k_ks_path_freq(PathFreqArgs a) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    unsigned char *sm = bs_dyn_smem();
-    double *s_red = (double *)sm;
-    int64_t *s_scan = (int64_t *)sm;
-    int32_t *s_cc = (int32_t *)(sm + (size_t)nthr * 8);  // [CC_DENSE] rows having count j
-    __shared__ int s_novf;
-    int32_t *scratch = a.scratch + (int64_t)blockIdx.x * (a.T + 1);
-    int32_t *ovf = a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP;
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    for (int64_t c = blockIdx.x; c < a.n_contigs; c += gridDim.x) {
-        const int64_t coff = a.ctg_off[c];
-        const int64_t L = a.ctg_off[c + 1] - coff;
-        const int32_t total = a.total[c];
-        if (total == 0) {  // 0/0 for every row: R drops the NaNs and ks.test stops on empty x
-            if (tid == 0) a.ks[c] = qnan;
-            continue;
+        // leave the histogram zeroed for the next contig
+        if (PACKED) { for (int i = lo >> 1; i < (hi + 1) >> 1; i++) s_hist[i] = 0; }
+        else { for (int i = lo; i < hi; i++) s_hist[i] = 0; }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const double o = __shfl_xor_sync(FULL_MASK, d, m);
+            if (o > d) d = o;
         }
-        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
-        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
-        const int32_t *w = a.w + coff + c;
-        const int64_t np = L > 0 ? L : 1;
+        if (lane == 0) s_wmax[warp] = d;
         __syncthreads();
-        for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
-        if (tid == 0) s_novf = 0;
-        __syncthreads();
-        // pass 1: per-row counts in the block's scratch histogram
-        for (int64_t p = tid; p < np; p += nthr) {
-            const int32_t wv = w[p];
-            if (wv == 0) continue;
-            const BreakWindow bw = break_window(p, a.kmer, L);
-            const int di = dense_index_at(gw, gm, bw.start, bw.len);
-            const int32_t row = di >= 0 ? a.tab_row[di] : -1;
-            if (row >= 0) atomicAdd(&scratch[row], wv);
+        if (tid == 0) {
+            for (int w = 1; w < nwarp; w++) if (s_wmax[w] > d) d = s_wmax[w];
+            a.ks[c] = (nwin > 0 && n_y > 0) ? d : __longlong_as_double(0x7ff8000000000000ll);
         }
-        __syncthreads();
-        // pass 2: whoever swaps a row's count out first owns it; tally rows per count value
-        for (int64_t p = tid; p < np; p += nthr) {
-            const int32_t wv = w[p];
-            if (wv == 0) continue;
-            const BreakWindow bw = break_window(p, a.kmer, L);
-            const int di = dense_index_at(gw, gm, bw.start, bw.len);
-            const int32_t row = di >= 0 ? a.tab_row[di] : -1;
-            if (row < 0) continue;
-            const int32_t cnt = atomicExch(&scratch[row], 0);
-            if (cnt == 0) continue;
-            if (cnt < CC_DENSE) atomicAdd(&s_cc[cnt], 1);
-            else {
-                const int slot = atomicAdd(&s_novf, 1);
-                if (slot < OVF_CAP) ovf[slot] = cnt; else *a.status = 1;
-            }
-        }
-        __syncthreads();
-        // rows with a non-zero count, to get the number of zero rows
-        const int per = CC_DENSE / nthr > 0 ? (CC_DENSE + nthr - 1) / nthr : 1;
-        const int lo = tid * per, hi = (lo + per < CC_DENSE) ? lo + per : CC_DENSE;
-        int64_t sum = 0;
-        for (int j = (lo > 0 ? lo : 1); j < hi; j++) sum += s_cc[j];
-        int64_t nz_dense = 0;
-        int64_t run = block_exclusive_scan(sum, s_scan, &nz_dense);
-        const int novf = s_novf < OVF_CAP ? s_novf : OVF_CAP;
-        const int64_t n_zero = (int64_t)a.T - nz_dense - novf;
-        const int32_t *ycum = a.ycum + (int64_t)a.ctg_seg[c] * a.R_y;
-        const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
-        double d = 0.0;
-        if (n_y > 0 && a.T > 0) {
-            const double inx = (double)a.T, iny = (double)n_y;
-            // x value 0 (rows never broken)
-            if (tid == 0 && n_zero > 0) {
-                double le, lt;
-                y_counts_at(a.yv, ycum, a.R_y, 0.0, &le, &lt);
-                double d1 = lt / iny, d2 = (double)n_zero / inx - le / iny;
-                if (d1 < 0) d1 = -d1;
-                if (d2 < 0) d2 = -d2;
-                d = d1 > d2 ? d1 : d2;
-            }
-            run += n_zero;
-            for (int j = (lo > 0 ? lo : 1); j < hi; j++) {
-                const int32_t cnt = s_cc[j];
-                if (cnt == 0) continue;
-                const double v = (double)j / (double)total;
-                double le, lt;
-                y_counts_at(a.yv, ycum, a.R_y, v, &le, &lt);
-                double d1 = (double)run / inx - lt / iny;
-                run += cnt;
-                double d2 = (double)run / inx - le / iny;
-                if (d1 < 0) d1 = -d1;
-                if (d2 < 0) d2 = -d2;
-                if (d1 > d) d = d1;
-                if (d2 > d) d = d2;
-            }
-            // counts >= CC_DENSE: few; thread 0 walks them in ascending order
-            if (tid == 0 && novf > 0) {
-                int64_t below = n_zero + nz_dense;
-                int32_t last = CC_DENSE - 1;
-                for (int done = 0; done < novf;) {
-                    int32_t cur = 0x7fffffff;
-                    int mult = 0;
-                    for (int i = 0; i < novf; i++) {
-                        const int32_t v = ovf[i];
-                        if (v > last && v < cur) { cur = v; mult = 1; }
-                        else if (v == cur) mult++;
-                    }
-                    const double v = (double)cur / (double)total;
-                    double le, lt;
-                    y_counts_at(a.yv, ycum, a.R_y, v, &le, &lt);
-                    double d1 = (double)below / inx - lt / iny;
-                    below += mult;
-                    double d2 = (double)below / inx - le / iny;
-                    if (d1 < 0) d1 = -d1;
-                    if (d2 < 0) d2 = -d2;
-                    if (d1 > d) d = d1;
-                    if (d2 > d) d = d2;
-                    last = cur;
-                    done += mult;
-                }
-            }
-        }
-        d = block_max(d, s_red);
-        if (tid == 0) a.ks[c] = (n_y > 0 && a.T > 0) ? d : qnan;
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // contig-in-truth offset (upstream lib/BreakageScorer.cpp:273-274): leftmost exact occurrence
-// of the whole contig in its segment's truth, assigned only if at least one read was placed
+// of the whole contig in its segment's truth, assigned only if at least one read was placed.
+//
+// k_startpos_index: the truth streams past a small shared-memory table of the segment's contig
+// SEEDS (first 32 bases); a seed hit is verified by the whole warp on packed words; the leftmost
+// verified position wins through atomicMin.  O(L_truth + sum L_c) per segment instead of
+// O(C * L_truth).  Contigs without a packable seed (shorter than 32, or a non-ACGT byte in it)
+// are left to k_startpos, which also turns the atomicMin scratch into the final values.
 // ------------------------------------------------------------------------------------------
 
 struct StartposArgs {
@@ -997,6 +1046,7 @@ struct StartposArgs {
     const uint32_t *ctg_mask;
     const uint8_t *ctg_chars;
     const int32_t *ctg_seg;
+    const int64_t *seg_contig_start;  // [S+1]
     const int64_t *tr_off;
     const int64_t *tr_woff;
     const uint64_t *tr_words;
@@ -1004,9 +1054,124 @@ struct StartposArgs {
     const uint8_t *tr_chars;
     const int32_t *total;
     int64_t n_contigs;
+    int32_t n_seg;
+    int32_t splits;       // blocks per segment (each scans a slice of the truth)
+    uint32_t *best;       // [C] leftmost verified position, POS_INF on entry (k_startpos_index writes, k_startpos reads)
     int32_t *startpos;
 };
 
+constexpr int SP_SLOTS = 2048;  // seed table slots per pass
+constexpr int SP_GROUP = 1024;  // contigs per pass
+
+// a contig the seed index can look for: 32 valid leading bases, fits in the truth, had a read placed
+__device__ __forceinline__ bool startpos_indexable(const StartposArgs &a, int64_t c, int64_t LT) {
+    const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+    return L >= 32 && L <= LT && a.total[c] != 0 && a.ctg_mask[a.ctg_woff[c]] == 0;
+}
+
+__global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
+    __shared__ uint64_t s_key[SP_SLOTS];
+    __shared__ int32_t s_head[SP_SLOTS];  // local contig index + 1 of the first contig with that seed
+    __shared__ int32_t s_next[SP_GROUP];  // next contig with the same seed
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const int seg = blockIdx.x / a.splits, part = blockIdx.x % a.splits;
+    const int64_t LT = a.tr_off[seg + 1] - a.tr_off[seg];
+    const uint64_t *tw = a.tr_words + a.tr_woff[seg];
+    const uint32_t *tm = a.tr_mask + a.tr_woff[seg];
+    const uint8_t *tc = a.tr_chars + a.tr_off[seg];
+    const int64_t nq = LT - 31;  // positions that can hold a 32-base seed
+    if (nq <= 0) return;
+    int64_t span = (nq + a.splits - 1) / a.splits;
+    span = (span + 31) / 32 * 32;
+    const int64_t q_begin = (int64_t)part * span;
+    const int64_t q_end = q_begin + span < nq ? q_begin + span : nq;
+    if (q_begin >= q_end) return;
+    const int64_t c0 = a.seg_contig_start[seg], c1 = a.seg_contig_start[seg + 1];
+    for (int64_t g0 = c0; g0 < c1; g0 += SP_GROUP) {
+        const int gn = (int)(c1 - g0 < SP_GROUP ? c1 - g0 : SP_GROUP);
+        __syncthreads();
+        for (int i = tid; i < SP_SLOTS; i += nthr) s_head[i] = 0;
+        __syncthreads();
+        if (tid == 0) {  // serial build: a few dozen contigs per segment in the usual case
+            for (int i = 0; i < gn; i++) {
+                const int64_t c = g0 + i;
+                if (!startpos_indexable(a, c, LT)) continue;
+                const uint64_t key = a.ctg_words[a.ctg_woff[c]];
+                uint32_t h = seed_hash(key) & (SP_SLOTS - 1);
+                while (s_head[h] != 0 && s_key[h] != key) h = (h + 1) & (SP_SLOTS - 1);
+                s_next[i] = s_head[h];  // chain: newest first
+                s_key[h] = key;
+                s_head[h] = i + 1;
+            }
+        }
+        __syncthreads();
+        for (int64_t qb = q_begin; qb < q_end; qb += nthr) {
+            const int64_t q = qb + tid;
+            int cand = 0;
+            if (q < q_end) {
+                const int64_t idx = q >> 5;
+                const uint32_t o = (uint32_t)(q & 31);
+                if (window32(__ldg(&tm[idx]), __ldg(&tm[idx + 1]), o) == 0) {
+                    const uint64_t seed = window64(__ldg(&tw[idx]), __ldg(&tw[idx + 1]), o);
+                    uint32_t h = seed_hash(seed) & (SP_SLOTS - 1);
+                    while (s_head[h] != 0) {
+                        if (s_key[h] == seed) { cand = s_head[h]; break; }
+                        h = (h + 1) & (SP_SLOTS - 1);
+                    }
+                }
+            }
+            // seed hits of the warp, one after the other, each verified by all 32 lanes
+            unsigned hits = __ballot_sync(FULL_MASK, cand != 0);
+            while (hits) {
+                const int src = __ffs((int)hits) - 1;
+                hits &= hits - 1;
+                const int64_t qc = __shfl_sync(FULL_MASK, q, src);
+                int ci = __shfl_sync(FULL_MASK, cand, src);
+                for (; ci != 0; ci = s_next[ci - 1]) {
+                    const int64_t c = g0 + ci - 1;
+                    const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+                    if (qc + L > LT) continue;
+                    // a position further left may already be known; one lane reads so that the whole
+                    // warp takes the same branch (the value can change under us)
+                    uint32_t known = 0;
+                    if (lane == 0) known = *(volatile uint32_t *)&a.best[c];
+                    known = __shfl_sync(FULL_MASK, known, 0);
+                    if ((uint32_t)qc >= known) continue;
+                    const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
+                    const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
+                    const int64_t idx = qc >> 5;
+                    const uint32_t o = (uint32_t)(qc & 31);
+                    const int64_t nw = (L + 31) >> 5;
+                    bool ok = true, any_invalid = false;
+                    for (int64_t j0 = 0; ok && j0 < nw; j0 += 32) {
+                        const int64_t j = j0 + lane;
+                        bool okl = true;
+                        if (j < nw) {
+                            const int rem = (L - 32 * j) < 32 ? (int)(L - 32 * j) : 32;
+                            const uint32_t mj = cm[j];
+                            // byte equality == equal 2-bit codes AND equal validity AND equal raw bytes where invalid
+                            okl = ((window64(tw[idx + j], tw[idx + j + 1], o) ^ cw[j]) & keep_bases(rem)) == 0 &&
+                                  ((window32(tm[idx + j], tm[idx + j + 1], o) ^ mj) & keep_bits(rem)) == 0;
+                            any_invalid |= (mj & keep_bits(rem)) != 0;
+                        }
+                        ok = __ballot_sync(FULL_MASK, !okl) == 0;
+                    }
+                    if (ok && __ballot_sync(FULL_MASK, any_invalid) != 0) {
+                        const uint8_t *cc = a.ctg_chars + a.ctg_off[c];
+                        for (int64_t i0 = 0; ok && i0 < L; i0 += 32) {
+                            const int64_t i = i0 + lane;
+                            const bool okl = i < L ? tc[qc + i] == cc[i] : true;
+                            ok = __ballot_sync(FULL_MASK, !okl) == 0;
+                        }
+                    }
+                    if (ok && lane == 0) atomicMin(&a.best[c], (uint32_t)qc);
+                }
+            }
+        }
+    }
+}
+
+// final values, and the scan for the contigs the index cannot take
 __global__ void k_startpos(StartposArgs a) {
     __shared__ int s_best;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -1017,6 +1182,10 @@ __global__ void k_startpos(StartposArgs a) {
         if (a.total[c] == 0 || L == 0 || L > LT) {
             // no read placed: upstream never assigns (stays 0); "" is found at 0; too long: npos
             if (tid == 0) a.startpos[c] = (a.total[c] != 0 && L > LT) ? -1 : 0;
+            continue;
+        }
+        if (a.best && startpos_indexable(a, c, LT)) {
+            if (tid == 0) { const uint32_t b = a.best[c]; a.startpos[c] = b == POS_INF ? -1 : (int32_t)b; }
             continue;
         }
         const uint64_t *cw = a.ctg_words + a.ctg_woff[c];

@@ -69,5 +69,10 @@ def edge_inputs():
         ("contig_longer_than_truth", [c + c], [c[4:14]], c, 8),
         ("truth_shorter_than_kmer", [c], [c[4:14]], b"ACG", 8),
         ("all_same_base", [b"A" * 200], [b"A" * 20, b"A" * 33, b"A" * 64, b"AAAC"], b"A" * 300, 8),
+        ("n_contig_in_n_truth", [rep[40:90] + b"NNNN" + rep[3:40], rep[50:90] + b"NNNN" + rep[3:10] + b"T"],
+         [rep[45:70], rep[60:80]], rep[:90] + b"NNNN" + rep[3:60], 8),
+        ("seed_repeats_before_match", [b"A" * 40 + b"G", b"A" * 33 + b"C"], [b"A" * 20, b"AAAC"],
+         b"A" * 40 + b"C" + b"A" * 40 + b"G" + b"A" * 50, 8),
+        ("contig_equals_truth", [rep[:200]], [rep[5:30]], rep[:200], 8),
         ("exact_word_boundaries", [rep[:64], rep[:96], rep[:32]], [rep[:32], rep[32:64], rep[:64], rep[31:64], rep[1:33]], rep, 8),
     ]
