@@ -110,7 +110,7 @@ struct bs_ctx {
     std::vector<double> tprob_dense;   // [DENSE_SIZE] truth-side values (follows prob_dense unless set)
     std::vector<int32_t> row_dense;    // [DENSE_SIZE]
     bool has_truth_table = false;
-    DevBuf d_tab_prob, d_tab_row;
+    DevBuf d_tab;  // bs::TabEntry[DENSE_SIZE]
     KsCache ks;
 
     Workspace ws[kWorkspaces];
@@ -206,6 +206,14 @@ int grid_for(int64_t work_items, int threads, int cap) {
     return (int)g;
 }
 
+// resident blocks per SM of a persistent kernel (grid = SMs x this): what the hardware can hold
+template <class K>
+int blocks_per_sm(K kernel, int threads, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
 int sync_all(bs_ctx *ctx) {
     BS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     BS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -214,12 +222,14 @@ int sync_all(bs_ctx *ctx) {
 }
 
 int upload_table(bs_ctx *ctx) {
-    BS_TRY(ensure(ctx, ctx->d_tab_prob, bs::DENSE_SIZE * sizeof(double)));
-    BS_TRY(ensure(ctx, ctx->d_tab_row, bs::DENSE_SIZE * sizeof(int32_t)));
-    BS_CUDA(cudaMemcpyAsync(ctx->d_tab_prob.p, ctx->prob_dense.data(), bs::DENSE_SIZE * sizeof(double),
-                            cudaMemcpyHostToDevice, ctx->stream));
-    BS_CUDA(cudaMemcpyAsync(ctx->d_tab_row.p, ctx->row_dense.data(), bs::DENSE_SIZE * sizeof(int32_t),
-                            cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<bs::TabEntry> tab(bs::DENSE_SIZE);
+    for (int i = 0; i < bs::DENSE_SIZE; i++) {
+        tab[i].prob = ctx->prob_dense[i];
+        tab[i].row = ctx->row_dense[i];
+        tab[i].pad = 0;
+    }
+    BS_TRY(ensure(ctx, ctx->d_tab, tab.size() * sizeof(bs::TabEntry)));
+    BS_CUDA(cudaMemcpyAsync(ctx->d_tab.p, tab.data(), tab.size() * sizeof(bs::TabEntry), cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaStreamSynchronize(ctx->stream));
     return BS_OK;
 }
@@ -382,11 +392,17 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     std::vector<bs::PlaceItem> items;
     int tile_len = 0, hash_size = 0, found_words = 0;
     size_t place_smem = 0;
+    // work order of the persistent kernels: the long contigs first, longest first (they set the
+    // tail), then the rest in input order so that the blocks running at one time share few
+    // segments (read index and reads of those segments stay in L2)
     order.resize((size_t)C);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-        return ctg_off[x + 1] - ctg_off[x] > ctg_off[y + 1] - ctg_off[y];
-    });
+    {
+        const int64_t long_len = 8192;
+        auto len_of = [&](int32_t x) { return ctg_off[x + 1] - ctg_off[x]; };
+        auto mid = std::stable_partition(order.begin(), order.end(), [&](int32_t x) { return len_of(x) > long_len; });
+        std::stable_sort(order.begin(), mid, [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
+    }
     if (tile_mode) {
         // tile placement: one work item per (contig, read chunk)
         tile_len = (int)std::min<int64_t>(kMaxTile, std::max<int64_t>(32, (max_ctg + 31) / 32 * 32));
@@ -607,7 +623,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         StageTimer tm(ctx, ST_PLACE, st);
         if (N > 0 && C > 0 && !tile_mode) {
             // per-block scratch row of leftmost positions, all POS_INF between launches
-            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * 4);
+            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_place_index, kPlaceIxThreads, (size_t)kHitCap * 4));
             const int64_t stride = (max_seg_reads + 31) / 32 * 32;
             const int64_t budget = (int64_t)8 << 30;
             nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * 4, 1)));
@@ -651,30 +667,38 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         const int R_y = std::max(k.R_y, 1);
         BS_TRY(ensure(ctx, ws.ycnt, (size_t)S * R_y * 4));
         StageTimer tm(ctx, ST_SPECTRUM, st);
-        BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, st));
-        if (k.R_y > 0) {
-            bs::SpectrumArgs sp;
-            sp.tr_off = d_tr_off; sp.tr_woff = d_tr_woff; sp.tr_words = ts.words; sp.tr_mask = ts.mask;
-            sp.rank_y = (const int32_t *)k.rank_y.p; sp.ycnt = (int32_t *)ws.ycnt.p;
-            sp.R_y = R_y; sp.kmer = kmer;
-            sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(64, (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
-            BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, st, sp);
+        const size_t sp_smem = (size_t)((k.R_y + 1) / 2) * 4;
+        bs::SpectrumArgs sp;
+        sp.tr_off = d_tr_off; sp.tr_woff = d_tr_woff; sp.tr_words = ts.words; sp.tr_mask = ts.mask;
+        sp.rank_y = (const int32_t *)k.rank_y.p; sp.ycnt = (int32_t *)ws.ycnt.p;
+        sp.R_y = R_y; sp.kmer = kmer; sp.blocks_per_seg = 1;
+        if (k.R_y > 0 && kmer <= bs::MAXK && max_tr - kmer + 1 < 65536 && sp_smem + 1024 <= ctx->smem_optin) {
+            // one block per segment, histogram and prefix sum in shared memory
+            BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+            BS_LAUNCH(bs::k_truth_spectrum_smem, (unsigned)S, kKsThreads, sp_smem, st, sp);
             ctx->launches++;
-            BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, st, (int32_t *)ws.ycnt.p, R_y);
-            ctx->launches++;
+        } else {
+            BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, st));
+            if (k.R_y > 0) {
+                sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(64, (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
+                BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, st, sp);
+                ctx->launches++;
+                BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, st, (int32_t *)ws.ycnt.p, R_y);
+                ctx->launches++;
+            }
         }
     }
     {
         // scores (+ histogram, + KS of the normalised break histogram); after the truth spectrum
         StageTimer tm(ctx, ST_SCORE, st);
         const KsCache &k = ctx->ks;
-        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * 4);
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kScoreThreads, 0));
         bs::ScoreArgs sa;
         std::memset(&sa, 0, sizeof(sa));
         sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + 2;
         sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_seg = d_ctg_seg;
         sa.w = (const int32_t *)ws.w.p; sa.total = (const int32_t *)ws.total.p;
-        sa.tab_prob = (const double *)ctx->d_tab_prob.p; sa.tab_row = (const int32_t *)ctx->d_tab_row.p;
+        sa.tab = (const bs::TabEntry *)ctx->d_tab.p;
         sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
         sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
         sa.kmer_breaks = o_breaks; sa.hist = o_hist;
@@ -709,8 +733,9 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         // windows -- real table: 32 897 ranks = 66 KB, three blocks per SM -- else 32-bit counters,
         // else (all-distinct tables with long contigs) a per-block global scratch that stays in L2
         const bool packed = max_ctg - kmer + 1 < 65536;
-        pa.hist_words = ks_a ? (packed ? (k.R_x + 1) / 2 : k.R_x) : 0;
-        const size_t hist_bytes = (size_t)pa.hist_words * 4;
+        pa.hist_words = ks_a ? bs::hist_phys_words(k.R_x, packed) : 0;
+        pa.n_ranges = ks_a ? (k.R_x + 63) / 64 : 0;
+        const size_t hist_bytes = (size_t)(pa.hist_words + pa.n_ranges) * 4;
         const bool in_smem = hist_bytes + 2048 <= ctx->smem_optin;
         const size_t smem = in_smem ? hist_bytes : 0;
         const int per_sm = std::max<int>(1, std::min<int>(2048 / kKsThreads, (int)((ctx->smem_optin + 1024) / (smem + 1024))));
@@ -842,7 +867,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->d_tab_prob, &ctx->d_tab_row, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
+    DevBuf *bufs[] = {&ctx->d_tab, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
                       &ctx->d_rank_scratch, &ctx->d_counters};
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {

@@ -113,8 +113,7 @@ __device__ __forceinline__ int segment_of_read(const ReadIndex &ix, int64_t n) {
     return lo;
 }
 
-__device__ __forceinline__ void index_insert(const ReadIndex &ix, int64_t n, uint64_t word0, int len, bool seed_bad) {
-    const int s = segment_of_read(ix, n);
+__device__ __forceinline__ void index_insert(const ReadIndex &ix, int s, int64_t n, uint64_t word0, int len, bool seed_bad) {
     const int S = ix.seed_len[s];
     if (len == 0 || seed_bad) {
         ix.next[n] = atomicExch(&ix.odd_head[s], (uint32_t)n + 1u);
@@ -148,7 +147,7 @@ __global__ void k_pack_reads(ReadSet r, ReadIndex ix) {
             if (j == 0) { w0 = w; seed_bad = any_bad; }
         }
         r.flags[i] = (uint8_t)any_bad;
-        if (ix.head) index_insert(ix, i, w0, len, seed_bad != 0);
+        if (ix.head) index_insert(ix, segment_of_read(ix, i), i, w0, len, seed_bad != 0);
     }
 }
 
@@ -181,20 +180,31 @@ constexpr int PACK_CELLS = PACK_THREADS * 2 + 4;  // 16-byte cells a tile of 256
 __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, ReadIndex ix) {
     __shared__ uint32_t s_code[PACK_CELLS];
     __shared__ uint32_t s_bad[PACK_CELLS];
+    __shared__ int64_t s_n0;  // read and word-in-read of the tile's first output word, its segment
+    __shared__ int s_j0, s_seg0;
     const int tid = threadIdx.x;
     const int64_t n_words = r.n * r.W;
     const int64_t total_bytes = r.n * (int64_t)r.uniform_len;
     const uintptr_t base = (uintptr_t)r.chars;
     const int L = r.uniform_len;
     for (int64_t k0 = (int64_t)blockIdx.x * PACK_THREADS; k0 < n_words; k0 += (int64_t)gridDim.x * PACK_THREADS) {
-        int64_t klast = k0 + PACK_THREADS - 1;
-        if (klast >= n_words) klast = n_words - 1;
-        const int64_t lo = (k0 / r.W) * L + (k0 % r.W) * 32;       // first source byte of the tile
-        int64_t hi = (klast / r.W) * L + (klast % r.W) * 32 + 32;  // one past the last
+        __syncthreads();
+        if (tid == 0) {  // the only 64-bit divisions of the tile
+            s_n0 = k0 / r.W;
+            s_j0 = (int)(k0 - s_n0 * r.W);
+            s_seg0 = ix.head ? segment_of_read(ix, s_n0) : 0;
+        }
+        __syncthreads();
+        const int64_t n0 = s_n0;
+        const int j0 = s_j0;
+        const int ntile = (int)(n_words - k0 < PACK_THREADS ? n_words - k0 : PACK_THREADS);
+        const uint32_t xl = (uint32_t)(j0 + ntile - 1);
+        const uint32_t dnl = xl / (uint32_t)r.W;
+        const int64_t lo = n0 * L + (int64_t)j0 * 32;  // first source byte of the tile
+        int64_t hi = (n0 + dnl) * L + (int64_t)(xl - dnl * (uint32_t)r.W) * 32 + 32;  // one past the last
         if (hi > total_bytes) hi = total_bytes;
         const int64_t lo16 = lo - (int64_t)((base + (uintptr_t)lo) & 15);  // 16-byte aligned address, may be < 0
         const int n_cells = (int)((hi - lo16 + 15) >> 4);
-        __syncthreads();
         for (int ci = tid; ci < n_cells; ci += PACK_THREADS) {
             const int64_t cb = lo16 + 16 * (int64_t)ci;
             uint32_t x0, x1, x2, x3;
@@ -220,8 +230,10 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
         __syncthreads();
         const int64_t k = k0 + tid;
         if (k < n_words) {
-            const int64_t n = k / r.W;
-            const int j = (int)(k % r.W);
+            const uint32_t x = (uint32_t)(j0 + tid);
+            const uint32_t dn = x / (uint32_t)r.W;
+            const int64_t n = n0 + dn;
+            const int j = (int)(x - dn * (uint32_t)r.W);
             const int64_t a = n * L + 32 * j - lo16;  // byte offset inside the staged span
             const int ci = (int)(a >> 4);
             const uint32_t sh = 2u * (uint32_t)(a & 15);
@@ -239,7 +251,11 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
             if (last_cell >= ci + 1) bad |= s_bad[c1];
             if (last_cell >= ci + 2) bad |= s_bad[c2];
             if (bad) atomicOr(reinterpret_cast<unsigned *>(r.flags) + (n >> 2), 1u << (8 * (int)(n & 3)));
-            if (j == 0 && ix.head) index_insert(ix, n, word, L, bad != 0);
+            if (j == 0 && ix.head) {
+                int sg = s_seg0;  // reads of a tile rarely span more than one segment
+                while (sg + 1 < ix.n_seg && n >= ix.seg_read_start[sg + 1]) sg++;
+                index_insert(ix, sg, n, word, L, bad != 0);
+            }
         }
     }
 }
@@ -505,26 +521,44 @@ __global__ void __launch_bounds__(256) k_place_index(PlaceIxArgs a) {
         const uint64_t keepS = keep_bases(S);
         const uint32_t keepSm = keep_bits(S);
 
-        // ---- every contig position against the index ----
+        // ---- every contig position against the index; four positions per thread in flight so that
+        // the dependent L2 round trips (bucket head -> read word -> verification) overlap ----
         if (n_seg_reads > 0) {
-            for (int64_t p = tid; p + S <= L; p += nthr) {
-                const int64_t idx = p >> 5;
-                const uint32_t o = (uint32_t)(p & 31);
-                if (window32(__ldg(&gm[idx]), __ldg(&gm[idx + 1]), o) & keepSm) continue;  // seed window holds a non-ACGT base
-                const uint64_t seed = window64(__ldg(&gw[idx]), __ldg(&gw[idx + 1]), o) & keepS;
-                uint32_t q = head[seed_hash(seed) & hmask];
-                while (q != 0) {
-                    const int64_t n = (int64_t)q - 1;
-                    q = a.ix.next[n];
-                    const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
-                    if ((w0 ^ seed) & keepS) continue;
-                    const int len = read_length(a.reads, n);
-                    if (p + len > L) continue;
-                    if (!verify_at(a, gw, gm, cc, p, n, len, w0)) continue;
-                    const uint32_t old = atomicMin(&best[n - r0], (uint32_t)p);
-                    if (old == POS_INF) {
-                        const int slot = atomicAdd(&s_nhit, 1);
-                        if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
+            for (int64_t p0 = 0; p0 + S <= L; p0 += 4 * (int64_t)nthr) {
+                uint32_t q4[4];
+                uint64_t seed4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t p = p0 + (int64_t)u * nthr + tid;
+                    q4[u] = 0;
+                    seed4[u] = 0;
+                    if (p + S <= L) {
+                        const int64_t idx = p >> 5;
+                        const uint32_t o = (uint32_t)(p & 31);
+                        if (!(window32(__ldg(&gm[idx]), __ldg(&gm[idx + 1]), o) & keepSm)) {  // else: a non-ACGT base in the seed window
+                            seed4[u] = window64(__ldg(&gw[idx]), __ldg(&gw[idx + 1]), o) & keepS;
+                            q4[u] = head[seed_hash(seed4[u]) & hmask];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t p = p0 + (int64_t)u * nthr + tid;
+                    uint32_t q = q4[u];
+                    const uint64_t seed = seed4[u];
+                    while (q != 0) {
+                        const int64_t n = (int64_t)q - 1;
+                        q = a.ix.next[n];
+                        const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
+                        if ((w0 ^ seed) & keepS) continue;
+                        const int len = read_length(a.reads, n);
+                        if (p + len > L) continue;
+                        if (!verify_at(a, gw, gm, cc, p, n, len, w0)) continue;
+                        const uint32_t old = atomicMin(&best[n - r0], (uint32_t)p);
+                        if (old == POS_INF) {
+                            const int slot = atomicAdd(&s_nhit, 1);
+                            if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
+                        }
                     }
                 }
             }
@@ -619,6 +653,13 @@ __device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *s_sc
 // distribution) -- one pass family over the position weights of a contig
 // ------------------------------------------------------------------------------------------
 
+// scoring table over the dense k-mer index space (all lengths 1..8), one 16-byte gather per break
+struct alignas(16) TabEntry {
+    double prob;
+    int32_t row;
+    int32_t pad;
+};
+
 constexpr int CC_DENSE = 4096;  // counts below this are tallied in a dense shared-memory array
 constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
 
@@ -632,8 +673,7 @@ struct ScoreArgs {
     const int32_t *ctg_seg;
     const int32_t *w;
     const int32_t *total;
-    const double *tab_prob;  // [DENSE_SIZE] probability of a dense k-mer index (0.0 if absent)
-    const int32_t *tab_row;  // [DENSE_SIZE] table row of a dense k-mer index (-1 if absent)
+    const TabEntry *tab;     // [DENSE_SIZE] probability and table row of a dense k-mer index (row -1 if absent)
     int32_t kmer;
     int32_t T;
     int64_t n_contigs;
@@ -708,21 +748,38 @@ __global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
         const int32_t total = a.total[c];
         const int64_t np = L > 0 ? L : 1;
         double s1 = 0.0, s2 = 0.0;
-        // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS)
+        // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS); four
+        // positions per thread in flight so that the table gathers overlap
         if (total != 0) {
-            for (int64_t p = tid; p < np; p += nthr) {
-                const int32_t wv = w[p];
-                if (wv == 0) continue;
-                const BreakWindow bw = break_window(p, a.kmer, L);
-                const int di = dense_index_at(gw, gm, bw.start, bw.len);
-                const int32_t row = di >= 0 ? a.tab_row[di] : -1;
-                if (row >= 0) {
-                    const double pr = a.tab_prob[di];
-                    s1 += pr * (double)wv;
-                    s2 += pr * ((double)wv / (double)total);
-                    if (want_ks) atomicAdd(&scratch[row], wv);
+            for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
+                int32_t wv[4];
+                TabEntry te[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t p = p0 + (int64_t)u * nthr + tid;
+                    wv[u] = p < np ? w[p] : 0;
                 }
-                if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    te[u].prob = 0.0;
+                    te[u].row = -1;
+                    if (wv[u] != 0) {
+                        const BreakWindow bw = break_window(p0 + (int64_t)u * nthr + tid, a.kmer, L);
+                        const int di = dense_index_at(gw, gm, bw.start, bw.len);
+                        if (di >= 0) te[u] = a.tab[di];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (wv[u] == 0) continue;
+                    const int32_t row = te[u].row;
+                    if (row >= 0) {
+                        s1 += te[u].prob * (double)wv[u];
+                        s2 += te[u].prob * ((double)wv[u] / (double)total);
+                        if (want_ks) atomicAdd(&scratch[row], wv[u]);
+                    }
+                    if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv[u]);
+                }
             }
         }
         s1 = block_sum_fixed(s1, s_w);
@@ -742,20 +799,33 @@ __global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
         __threadfence_block();
         __syncthreads();
         // pass 2: whoever swaps a row's count out first owns it; tally rows per count value
-        for (int64_t p = tid; p < np; p += nthr) {
-            const int32_t wv = w[p];
-            if (wv == 0) continue;
-            const BreakWindow bw = break_window(p, a.kmer, L);
-            const int di = dense_index_at(gw, gm, bw.start, bw.len);
-            const int32_t row = di >= 0 ? a.tab_row[di] : -1;
-            if (row < 0) continue;
-            const int32_t cnt = atomicExch(&scratch[row], 0);
-            if (cnt == 0) continue;
-            atomicAdd(&s_nz, 1);
-            if (cnt < CC_DENSE) { atomicAdd(&s_cc[cnt], 1); atomicMax(&s_maxc, cnt); }
-            else {
-                const int slot = atomicAdd(&s_novf, 1);
-                if (slot < OVF_CAP) ovf[slot] = cnt; else *a.status = 1;
+        for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
+            int32_t wv[4], row[4], cnt[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t p = p0 + (int64_t)u * nthr + tid;
+                wv[u] = p < np ? w[p] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                row[u] = -1;
+                if (wv[u] != 0) {
+                    const BreakWindow bw = break_window(p0 + (int64_t)u * nthr + tid, a.kmer, L);
+                    const int di = dense_index_at(gw, gm, bw.start, bw.len);
+                    if (di >= 0) row[u] = a.tab[di].row;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) cnt[u] = row[u] >= 0 ? atomicExch(&scratch[row[u]], 0) : 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (cnt[u] == 0) continue;
+                atomicAdd(&s_nz, 1);
+                if (cnt[u] < CC_DENSE) { atomicAdd(&s_cc[cnt[u]], 1); atomicMax(&s_maxc, cnt[u]); }
+                else {
+                    const int slot = atomicAdd(&s_novf, 1);
+                    if (slot < OVF_CAP) ovf[slot] = cnt[u]; else *a.status = 1;
+                }
             }
         }
         __syncthreads();
@@ -853,6 +923,59 @@ __global__ void k_truth_spectrum(SpectrumArgs a) {
     }
 }
 
+// The same for truths of fewer than 65 536 windows, one block per segment: counts in shared
+// memory (two 16-bit counters per word), cumulated in place, written out once, coalesced.
+__global__ void __launch_bounds__(512, 3) k_truth_spectrum_smem(SpectrumArgs a) {
+    uint32_t *s_h = (uint32_t *)bs_dyn_smem();
+    __shared__ uint32_t s_wsum[32];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t s = blockIdx.x;
+    const int64_t L = a.tr_off[s + 1] - a.tr_off[s];
+    const uint64_t *gw = a.tr_words + a.tr_woff[s];
+    const uint32_t *gm = a.tr_mask + a.tr_woff[s];
+    const int64_t nwin = L - a.kmer + 1;
+    const int kshift = 64 - 2 * a.kmer;
+    const uint32_t kbits = keep_bits(a.kmer);
+    const int nword = (a.R_y + 1) >> 1;
+    for (int i = tid; i < nword; i += nthr) s_h[i] = 0;
+    __syncthreads();
+    for (int64_t p = tid; p < nwin; p += nthr) {
+        const int64_t wi = p >> 5;
+        const uint32_t o = (uint32_t)(p & 31);
+        if (window32(__ldg(&gm[wi]), __ldg(&gm[wi + 1]), o) & kbits) continue;
+        const uint64_t code = window64(__ldg(&gw[wi]), __ldg(&gw[wi + 1]), o) >> kshift;
+        const int32_t rk = __ldg(&a.rank_y[code]);
+        if (rk >= 0) atomicAdd(&s_h[rk >> 1], 1u << (16 * (rk & 1)));
+    }
+    __syncthreads();
+    // inclusive prefix over ranks: every thread owns an even number of consecutive ranks
+    int per = (a.R_y + nthr - 1) / nthr;
+    per += per & 1;
+    const int lo = tid * per < a.R_y ? tid * per : a.R_y;
+    const int hi = lo + per < a.R_y ? lo + per : a.R_y;
+    uint32_t sum = 0;
+    for (int i = lo >> 1; i < (hi + 1) >> 1; i++) { const uint32_t w = s_h[i]; sum += (w & 0xffffu) + (w >> 16); }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+    for (int w = 0; w < warp; w++) run += s_wsum[w];
+    for (int i = lo >> 1; i < (hi + 1) >> 1; i++) {
+        const uint32_t w = s_h[i];
+        const uint32_t c0 = run + (w & 0xffffu), c1 = c0 + (w >> 16);
+        s_h[i] = c0 | (c1 << 16);  // totals stay below 65 536
+        run = c1;
+    }
+    __syncthreads();
+    int32_t *out = a.ycnt + s * a.R_y;
+    for (int i = tid; i < a.R_y; i += nthr) out[i] = (int32_t)((s_h[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+}
+
 // in-place inclusive prefix sum of every row of a [rows][R] int32 matrix; one block per row
 __global__ void k_row_cumsum(int32_t *m, int32_t R) {
     int64_t *s_scan = (int64_t *)bs_dyn_smem();
@@ -901,14 +1024,23 @@ struct ProbDistArgs {
     double *prob_dist;       // optional
     const int64_t *pd_off;
     double *ks;              // optional [C]
-    uint32_t *rank_scratch;  // [gridDim][hist_words] global rank histogram when it does not fit shared memory, else NULL
-    int32_t hist_words;      // 32-bit words of one rank histogram (packed: two 16-bit counters per word)
+    uint32_t *rank_scratch;  // [gridDim][hist_words + n_ranges] global rank histogram when it does not fit shared memory, else NULL
+    int32_t hist_words;      // 32-bit words of one rank histogram (hist_phys_words)
+    int32_t n_ranges;        // ceil(R_x / 64)
 };
 
-// PACKED: two 16-bit counters per word (every contig of the launch has < 65536 windows)
+// Rank histogram layout.  Ranks are grouped into RANGES of 64 (one thread sweeps one range);
+// PACKED: two 16-bit counters per 32-bit word (every contig of the launch has < 65536 windows).
+// One pad word after every 32 keeps a warp's simultaneous sweeps on different banks.
+constexpr int KS_RANGE_SHIFT = 6;
 template <bool PACKED>
-__device__ __forceinline__ uint32_t hist_get(const uint32_t *h, int r) {
-    return PACKED ? (h[r >> 1] >> (16 * (r & 1))) & 0xffffu : h[r];
+__device__ __forceinline__ int hist_word(int r) {
+    const int w = PACKED ? r >> 1 : r;
+    return w + (w >> 5);
+}
+BS_HD int hist_phys_words(int R_x, bool packed) {
+    const int w = packed ? (R_x + 1) / 2 : R_x;
+    return w + (w >> 5) + 2;
 }
 
 template <bool PACKED>
@@ -918,12 +1050,14 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     __shared__ int64_t s_wsum[32];
     __shared__ double s_wmax[32];
     __shared__ int s_item;
-    uint32_t *s_hist = a.rank_scratch ? a.rank_scratch + (int64_t)blockIdx.x * a.hist_words : (uint32_t *)bs_dyn_smem();
+    // dynamic shared memory (or the global scratch row): histogram words, then one count per range
+    uint32_t *s_hist = a.rank_scratch ? a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges) : (uint32_t *)bs_dyn_smem();
+    uint32_t *s_rc = s_hist + a.hist_words;
     const bool want_ks = a.ks != nullptr;
     const int kshift = 64 - 2 * a.kmer;
     const uint32_t kbits = keep_bits(a.kmer);
     if (want_ks) {
-        for (int i = tid; i < a.hist_words; i += nthr) s_hist[i] = 0;
+        for (int i = tid; i < a.hist_words + a.n_ranges; i += nthr) s_hist[i] = 0;
     }
     for (;;) {
         __syncthreads();
@@ -963,8 +1097,9 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                 if (p < nwin) {
                     if (pd) pd[p] = val[u];
                     if (want_ks) {
-                        if (PACKED) atomicAdd(&s_hist[rk[u] >> 1], 1u << (16 * (rk[u] & 1)));
-                        else atomicAdd(&s_hist[rk[u]], 1u);
+                        if (PACKED) atomicAdd(&s_hist[hist_word<true>(rk[u])], 1u << (16 * (rk[u] & 1)));
+                        else atomicAdd(&s_hist[hist_word<false>(rk[u])], 1u);
+                        atomicAdd(&s_rc[rk[u] >> KS_RANGE_SHIFT], 1u);
                     }
                 }
             }
@@ -976,44 +1111,61 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         const int64_t seg = a.ctg_seg[c];
         const int32_t *ycum = a.ycum + seg * a.R_y;
         const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
-        int per = (a.R_x + nthr - 1) / nthr;
-        per += per & 1;  // even: a thread owns whole packed words
-        const int lo = tid * per < a.R_x ? tid * per : a.R_x;
-        const int hi = lo + per < a.R_x ? lo + per : a.R_x;
-        int64_t sum = 0;
-        for (int i = lo; i < hi; i++) sum += hist_get<PACKED>(s_hist, i);
-        // exclusive prefix of the per-thread sums: warp scan, then the warp totals
-        int64_t incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int64_t o = __shfl_up_sync(FULL_MASK, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        int64_t run = incl - sum;
-        for (int w = 0; w < warp; w++) run += s_wsum[w];
+        const bool defined = nwin > 0 && n_y > 0;
+        const double inx = (double)nwin, iny = (double)n_y;
         double d = 0.0;
-        if (nwin > 0 && n_y > 0) {
-            const double inx = (double)nwin, iny = (double)n_y;
-            for (int i = lo; i < hi; i++) {
-                const uint32_t cnt = hist_get<PACKED>(s_hist, i);
-                if (cnt == 0) continue;
-                const LeLt q = a.lelt[i];
-                const double lt = q.lt >= 0 ? (double)ycum[q.lt] : 0.0;
-                const double le = q.le >= 0 ? (double)ycum[q.le] : 0.0;
-                double d1 = (double)run / inx - lt / iny;
-                run += cnt;
-                double d2 = (double)run / inx - le / iny;
-                if (d1 < 0) d1 = -d1;
-                if (d2 < 0) d2 = -d2;
-                if (d1 > d) d = d1;
-                if (d2 > d) d = d2;
+        int64_t carry = 0;  // windows in the ranges of earlier rounds (same value on every thread)
+        for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {  // one range of 64 ranks per thread and round
+            const int r = r0 + tid;
+            const int64_t cnt_r = r < a.n_ranges ? s_rc[r] : 0;
+            if (cnt_r) s_rc[r] = 0;
+            // exclusive prefix of the range counts over the block (+ what earlier rounds held)
+            int64_t incl = cnt_r;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int64_t o = __shfl_up_sync(FULL_MASK, incl, dd);
+                if (lane >= dd) incl += o;
             }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int64_t run = carry + incl - cnt_r;
+            for (int w = 0; w < nwarp; w++) {
+                if (w < warp) run += s_wsum[w];
+                carry += s_wsum[w];
+            }
+            if (cnt_r) {
+                const int rank0 = r << KS_RANGE_SHIFT;
+                const int n_logical = PACKED ? (a.R_x + 1) >> 1 : a.R_x;  // the last range is partial
+                const int first = PACKED ? rank0 >> 1 : rank0;
+                const int nword = n_logical - first < (PACKED ? 32 : 64) ? n_logical - first : (PACKED ? 32 : 64);
+                const int w0 = hist_word<PACKED>(rank0);  // the range's words are contiguous (pad only at k = 32)
+#pragma unroll 4
+                for (int k = 0; k < nword; k++) {
+                    const uint32_t word = s_hist[w0 + k + (PACKED ? 0 : (k >> 5))];
+                    if (word == 0) continue;
+                    s_hist[w0 + k + (PACKED ? 0 : (k >> 5))] = 0;  // leave the histogram zeroed for the next contig
+                    const int nsub = PACKED ? 2 : 1;
+                    for (int h = 0; h < nsub; h++) {
+                        const uint32_t cnt = PACKED ? (word >> (16 * h)) & 0xffffu : word;
+                        if (cnt == 0) continue;
+                        const int i = rank0 + (PACKED ? 2 * k + h : k);
+                        if (defined) {
+                            const LeLt q = a.lelt[i];
+                            const double lt = q.lt >= 0 ? (double)ycum[q.lt] : 0.0;
+                            const double le = q.le >= 0 ? (double)ycum[q.le] : 0.0;
+                            double d1 = (double)run / inx - lt / iny;
+                            run += cnt;
+                            double d2 = (double)run / inx - le / iny;
+                            if (d1 < 0) d1 = -d1;
+                            if (d2 < 0) d2 = -d2;
+                            if (d1 > d) d = d1;
+                            if (d2 > d) d = d2;
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // s_wsum is rewritten by the next round
         }
-        // leave the histogram zeroed for the next contig
-        if (PACKED) { for (int i = lo >> 1; i < (hi + 1) >> 1; i++) s_hist[i] = 0; }
-        else { for (int i = lo; i < hi; i++) s_hist[i] = 0; }
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
             const double o = __shfl_xor_sync(FULL_MASK, d, m);
@@ -1023,7 +1175,7 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         __syncthreads();
         if (tid == 0) {
             for (int w = 1; w < nwarp; w++) if (s_wmax[w] > d) d = s_wmax[w];
-            a.ks[c] = (nwin > 0 && n_y > 0) ? d : __longlong_as_double(0x7ff8000000000000ll);
+            a.ks[c] = defined ? d : __longlong_as_double(0x7ff8000000000000ll);
         }
     }
 }
