@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     __shared__ int64_t s_wsum[32];
-    __shared__ double s_wmax[32];
+    __shared__ int64_t s_wmax[32];
     __shared__ int s_item;
     // dynamic shared memory (or the global scratch row): histogram words, then one count per range
     uint32_t *s_hist = a.rank_scratch ? a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges) : (uint32_t *)bs_dyn_smem();
@@ -1112,8 +1112,9 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         const int32_t *ycum = a.ycum + seg * a.R_y;
         const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
         const bool defined = nwin > 0 && n_y > 0;
-        const double inx = (double)nwin, iny = (double)n_y;
-        double d = 0.0;
+        // |F_x - F_y| = |run * n_y - ycount * nwin| / (nwin * n_y): the numerator is maximised in exact
+        // 64-bit integers (both factors are below 2^31), one division at the end
+        int64_t best = 0;
         int64_t carry = 0;  // windows in the ranges of earlier rounds (same value on every thread)
         for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {  // one range of 64 ranks per thread and round
             const int r = r0 + tid;
@@ -1151,15 +1152,15 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                         const int i = rank0 + (PACKED ? 2 * k + h : k);
                         if (defined) {
                             const LeLt q = a.lelt[i];
-                            const double lt = q.lt >= 0 ? (double)ycum[q.lt] : 0.0;
-                            const double le = q.le >= 0 ? (double)ycum[q.le] : 0.0;
-                            double d1 = (double)run / inx - lt / iny;
+                            const int64_t lt = q.lt >= 0 ? ycum[q.lt] : 0;
+                            const int64_t le = q.le >= 0 ? ycum[q.le] : 0;
+                            int64_t d1 = run * n_y - lt * nwin;
                             run += cnt;
-                            double d2 = (double)run / inx - le / iny;
+                            int64_t d2 = run * n_y - le * nwin;
                             if (d1 < 0) d1 = -d1;
                             if (d2 < 0) d2 = -d2;
-                            if (d1 > d) d = d1;
-                            if (d2 > d) d = d2;
+                            if (d1 > best) best = d1;
+                            if (d2 > best) best = d2;
                         }
                     }
                 }
@@ -1168,14 +1169,14 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         }
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
-            const double o = __shfl_xor_sync(FULL_MASK, d, m);
-            if (o > d) d = o;
+            const int64_t o = __shfl_xor_sync(FULL_MASK, best, m);
+            if (o > best) best = o;
         }
-        if (lane == 0) s_wmax[warp] = d;
+        if (lane == 0) s_wmax[warp] = best;
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < nwarp; w++) if (s_wmax[w] > d) d = s_wmax[w];
-            a.ks[c] = defined ? d : __longlong_as_double(0x7ff8000000000000ll);
+            for (int w = 1; w < nwarp; w++) if (s_wmax[w] > best) best = s_wmax[w];
+            a.ks[c] = defined ? (double)best / ((double)nwin * (double)n_y) : __longlong_as_double(0x7ff8000000000000ll);
         }
     }
 }
