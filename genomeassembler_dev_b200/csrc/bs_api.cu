@@ -31,12 +31,14 @@ char g_create_error[512] = "";
 #ifdef BS_CPU_EMUL
 constexpr int kPlaceThreads = 64;
 constexpr int kScoreThreads = 64;
+constexpr int kStartposThreads = 64;
 constexpr int kKsThreads = 64;
 constexpr int kPackThreads = 64;
 constexpr int kPlaceIxThreads = 64;
 #else
 constexpr int kPlaceThreads = 256;
-constexpr int kScoreThreads = 256;
+constexpr int kScoreThreads = 128;
+constexpr int kStartposThreads = 256;
 constexpr int kKsThreads = 512;
 constexpr int kPackThreads = 256;
 constexpr int kPlaceIxThreads = 256;
@@ -44,7 +46,7 @@ constexpr int kPlaceIxThreads = 256;
 constexpr int kMaxTile = 8192;        // contig positions per shared-memory tile (tile placement modes)
 constexpr int64_t kMaxChunk = 32768;  // reads per placement work item (tile placement modes)
 constexpr int64_t kMinChunk = 2048;
-constexpr int kHitCap = 8192;         // reads placed per contig kept in shared memory (k_place_index)
+constexpr int kHitCap = 4096;         // reads placed per contig kept in shared memory (k_place_index)
 constexpr int kWorkspaces = 2;
 
 enum Stage { ST_H2D, ST_PACK, ST_PLACE, ST_SCORE, ST_SPECTRUM, ST_PROBDIST, ST_PATHFREQ, ST_STARTPOS, ST_D2H, ST_COUNT };
@@ -612,7 +614,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             if (!e.roff && e.rlen >= 1) {
                 BS_CUDA(cudaMemsetAsync(ws.rflags.p, 0, (size_t)N + 8, st));
                 const int64_t tiles = (N * W + bs::PACK_THREADS - 1) / bs::PACK_THREADS;
-                BS_LAUNCH(bs::k_pack_reads_uniform, (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 16), bs::PACK_THREADS, 0, st, rs, ix);
+                BS_LAUNCH(bs::k_pack_reads_uniform, (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 8), bs::PACK_THREADS, 0, st, rs, ix);
             } else {
                 BS_LAUNCH(bs::k_pack_reads, grid_for(N, kPackThreads, grid_cap), kPackThreads, 0, st, rs, ix);
             }
@@ -623,7 +625,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         StageTimer tm(ctx, ST_PLACE, st);
         if (N > 0 && C > 0 && !tile_mode) {
             // per-block scratch row of leftmost positions, all POS_INF between launches
-            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_place_index, kPlaceIxThreads, (size_t)kHitCap * 4));
+            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap)));
             const int64_t stride = (max_seg_reads + 31) / 32 * 32;
             const int64_t budget = (int64_t)8 << 30;
             nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * 4, 1)));
@@ -644,7 +646,8 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
             pa.pos = o_pos; pa.pos_off = d_pos_off;
             pa.hit_cap = kHitCap;
-            BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, (size_t)kHitCap * 4, st, pa);
+            BS_CUDA(cudaFuncSetAttribute(bs::k_place_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::place_index_smem_bytes(kHitCap)));
+            BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap), st, pa);
             ctx->launches++;
         } else if (N > 0 && !items.empty()) {
             bs::PlaceArgs pa;
@@ -745,13 +748,15 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * hist_bytes));
             pa.rank_scratch = (uint32_t *)ctx->d_rank_scratch.p;
         }
-        if (packed) {
-            BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            BS_LAUNCH(bs::k_prob_dist_ks<true>, (unsigned)nblk, kKsThreads, smem, st, pa);
-        } else {
-            BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            BS_LAUNCH(bs::k_prob_dist_ks<false>, (unsigned)nblk, kKsThreads, smem, st, pa);
-        }
+        auto launch = [&](auto kern) -> int {
+            BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BS_LAUNCH(kern, (unsigned)nblk, kKsThreads, smem, st, pa);
+            return BS_OK;
+        };
+        if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true>));
+        else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false>));
+        else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true>));
+        else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
         ctx->launches++;
     }
     if (e.want_sp) {
@@ -768,9 +773,9 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         int64_t splits = ((int64_t)ctx->sm_count * 4 + S - 1) / std::max<int64_t>(S, 1);
         splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 2047) / 2048));
         sa.splits = (int32_t)splits;
-        BS_LAUNCH(bs::k_startpos_index, (unsigned)(S * splits), kScoreThreads, 0, st, sa);
+        BS_LAUNCH(bs::k_startpos_index, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
         ctx->launches++;
-        BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kScoreThreads, 0, st, sa);
+        BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kStartposThreads, 0, st, sa);
         ctx->launches++;
     }
     BS_CUDA(cudaGetLastError());

@@ -169,43 +169,45 @@ __device__ __forceinline__ uint32_t pack16(uint32_t x0, uint32_t x1, uint32_t x2
     return __byte_perm(hi, lo, 0x3254u);
 }
 
-constexpr int PACK_THREADS = 256;            // one output word per thread and tile
-constexpr int PACK_CELLS = PACK_THREADS * 2 + 4;  // 16-byte cells a tile of 256 words can touch
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_WARP_CELLS = 68;  // 16-byte cells a warp tile (32 words = at most 1024 bytes + alignment) can touch
 
-// One tile = PACK_THREADS consecutive output words (AoS order: read-major).  Their source bytes
-// are one contiguous span of the dense read buffer: staged by coalesced 16-byte loads, converted
-// once per 16-byte cell into shared memory, then each thread cuts its 32 bases out of two or
-// three cells with funnel shifts.  A cell holding any byte outside ACGT flags every read that
-// overlaps it (conservative: flagged reads are verified by byte comparison, still exact).
+// One WARP tile = 32 consecutive output words (AoS order: read-major).  Their source bytes are
+// one contiguous span of the dense read buffer: staged by coalesced 16-byte loads, converted
+// once per 16-byte cell into the warp's slice of shared memory, then each lane cuts its 32 bases
+// out of two or three cells with funnel shifts.  Warps never wait for one another (__syncwarp
+// only).  A cell holding any byte outside ACGT flags every read that overlaps it (conservative:
+// flagged reads are verified by byte comparison, still exact).
 __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, ReadIndex ix) {
-    __shared__ uint32_t s_code[PACK_CELLS];
-    __shared__ uint32_t s_bad[PACK_CELLS];
-    __shared__ int64_t s_n0;  // read and word-in-read of the tile's first output word, its segment
-    __shared__ int s_j0, s_seg0;
-    const int tid = threadIdx.x;
+    __shared__ uint32_t s_code_all[PACK_THREADS / 32][PACK_WARP_CELLS];
+    __shared__ uint32_t s_bad_all[PACK_THREADS / 32][PACK_WARP_CELLS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *s_code = s_code_all[warp], *s_bad = s_bad_all[warp];
     const int64_t n_words = r.n * r.W;
     const int64_t total_bytes = r.n * (int64_t)r.uniform_len;
     const uintptr_t base = (uintptr_t)r.chars;
     const int L = r.uniform_len;
-    for (int64_t k0 = (int64_t)blockIdx.x * PACK_THREADS; k0 < n_words; k0 += (int64_t)gridDim.x * PACK_THREADS) {
-        __syncthreads();
-        if (tid == 0) {  // the only 64-bit divisions of the tile
-            s_n0 = k0 / r.W;
-            s_j0 = (int)(k0 - s_n0 * r.W);
-            s_seg0 = ix.head ? segment_of_read(ix, s_n0) : 0;
-        }
-        __syncthreads();
-        const int64_t n0 = s_n0;
-        const int j0 = s_j0;
-        const int ntile = (int)(n_words - k0 < PACK_THREADS ? n_words - k0 : PACK_THREADS);
-        const uint32_t xl = (uint32_t)(j0 + ntile - 1);
-        const uint32_t dnl = xl / (uint32_t)r.W;
+    const uint32_t W = (uint32_t)r.W;
+    const int64_t warps_total = (int64_t)gridDim.x * (PACK_THREADS / 32);
+    int64_t k0 = ((int64_t)blockIdx.x * (PACK_THREADS / 32) + warp) * 32;
+    if (k0 >= n_words) return;
+    // (read, word-in-read) of the tile's first word: one 64-bit division, then 32-bit increments
+    int64_t n0 = k0 / W;
+    uint32_t j0 = (uint32_t)(k0 - n0 * W);
+    const uint32_t adv = (uint32_t)(warps_total * 32 % W);
+    const int64_t adv_n = warps_total * 32 / W;
+    int seg = ix.head ? segment_of_read(ix, n0) : 0;
+    for (; k0 < n_words; k0 += warps_total * 32) {
+        const int ntile = (int)(n_words - k0 < 32 ? n_words - k0 : 32);
+        const uint32_t xl = j0 + (uint32_t)ntile - 1;
+        const uint32_t dnl = xl / W;
         const int64_t lo = n0 * L + (int64_t)j0 * 32;  // first source byte of the tile
-        int64_t hi = (n0 + dnl) * L + (int64_t)(xl - dnl * (uint32_t)r.W) * 32 + 32;  // one past the last
+        int64_t hi = (n0 + dnl) * L + (int64_t)(xl - dnl * W) * 32 + 32;  // one past the last
         if (hi > total_bytes) hi = total_bytes;
         const int64_t lo16 = lo - (int64_t)((base + (uintptr_t)lo) & 15);  // 16-byte aligned address, may be < 0
         const int n_cells = (int)((hi - lo16 + 15) >> 4);
-        for (int ci = tid; ci < n_cells; ci += PACK_THREADS) {
+        __syncwarp();
+        for (int ci = lane; ci < n_cells; ci += 32) {
             const int64_t cb = lo16 + 16 * (int64_t)ci;
             uint32_t x0, x1, x2, x3;
             if (cb >= 0 && cb + 16 <= total_bytes) {
@@ -227,13 +229,12 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
             s_code[ci] = pack16(x0, x1, x2, x3, diff);
             s_bad[ci] = diff;
         }
-        __syncthreads();
-        const int64_t k = k0 + tid;
-        if (k < n_words) {
-            const uint32_t x = (uint32_t)(j0 + tid);
-            const uint32_t dn = x / (uint32_t)r.W;
+        __syncwarp();
+        if (lane < ntile) {
+            const uint32_t x = j0 + (uint32_t)lane;
+            const uint32_t dn = x / W;
             const int64_t n = n0 + dn;
-            const int j = (int)(x - dn * (uint32_t)r.W);
+            const int j = (int)(x - dn * W);
             const int64_t a = n * L + 32 * j - lo16;  // byte offset inside the staged span
             const int ci = (int)(a >> 4);
             const uint32_t sh = 2u * (uint32_t)(a & 15);
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
             const uint32_t o_hi = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
             const uint32_t o_lo = sh ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;
             const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(rem);
-            r.words[k] = word;
+            r.words[k0 + lane] = word;
             // cells overlapping this word's own bytes [a, a + min(rem, 32))
             const int last_cell = (int)((a + (rem < 32 ? rem : 32) - 1) >> 4);
             uint32_t bad = s_bad[ci];
@@ -252,11 +253,16 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
             if (last_cell >= ci + 2) bad |= s_bad[c2];
             if (bad) atomicOr(reinterpret_cast<unsigned *>(r.flags) + (n >> 2), 1u << (8 * (int)(n & 3)));
             if (j == 0 && ix.head) {
-                int sg = s_seg0;  // reads of a tile rarely span more than one segment
+                int sg = seg;  // reads of a tile rarely span more than one segment
                 while (sg + 1 < ix.n_seg && n >= ix.seg_read_start[sg + 1]) sg++;
                 index_insert(ix, sg, n, word, L, bad != 0);
             }
         }
+        // next tile of this warp
+        n0 += adv_n;
+        j0 += adv;
+        if (j0 >= W) { j0 -= W; n0++; }
+        if (ix.head) while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
     }
 }
 
@@ -495,14 +501,19 @@ __device__ __forceinline__ bool verify_at(const PlaceIxArgs &a, const uint64_t *
     return true;
 }
 
-__global__ void __launch_bounds__(256) k_place_index(PlaceIxArgs a) {
+constexpr int PLACE_CAND_CAP = 2048;  // seed hits of one block iteration awaiting verification
+
+BS_HD size_t place_index_smem_bytes(int hit_cap) { return (size_t)hit_cap * 4 + (size_t)PLACE_CAND_CAP * 8; }
+
+__global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
     uint32_t *s_hits = (uint32_t *)bs_dyn_smem();
-    __shared__ int s_item, s_nhit, s_placed;
+    uint2 *s_cand = (uint2 *)(s_hits + a.hit_cap);  // (read id, contig position) with an equal seed
+    __shared__ int s_item, s_nhit, s_placed, s_ncand[2];
     const int tid = threadIdx.x, nthr = blockDim.x;
     uint32_t *best = a.best + (int64_t)blockIdx.x * a.best_stride;
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; }
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; s_ncand[0] = 0; s_ncand[1] = 0; }
         __syncthreads();
         const int item = s_item;
         if (item >= a.n_items) break;
@@ -521,10 +532,24 @@ __global__ void __launch_bounds__(256) k_place_index(PlaceIxArgs a) {
         const uint64_t keepS = keep_bases(S);
         const uint32_t keepSm = keep_bits(S);
 
-        // ---- every contig position against the index; four positions per thread in flight so that
-        // the dependent L2 round trips (bucket head -> read word -> verification) overlap ----
+        // a read with an equal seed at position p: verify the rest, keep the leftmost position
+        auto verify_and_record = [&](int64_t n, int64_t p) {
+            const int len = read_length(a.reads, n);
+            const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
+            if (!verify_at(a, gw, gm, cc, p, n, len, w0)) return;
+            const uint32_t old = atomicMin(&best[n - r0], (uint32_t)p);
+            if (old == POS_INF) {  // first time this read is seen in this contig
+                const int slot = atomicAdd(&s_nhit, 1);
+                if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
+            }
+        };
+
         if (n_seg_reads > 0) {
-            for (int64_t p0 = 0; p0 + S <= L; p0 += 4 * (int64_t)nthr) {
+            // ---- every contig position against the index.  Phase 1 (sparse, cheap): four positions
+            // per thread in flight, bucket head -> chain -> seed word; equal seeds are queued.
+            // Phase 2 (dense): one queued candidate per thread is verified on the packed words. ----
+            int it = 0;
+            for (int64_t p0 = 0; p0 + S <= L; p0 += 4 * (int64_t)nthr, it ^= 1) {
                 uint32_t q4[4];
                 uint64_t seed4[4];
 #pragma unroll
@@ -545,22 +570,25 @@ __global__ void __launch_bounds__(256) k_place_index(PlaceIxArgs a) {
                 for (int u = 0; u < 4; u++) {
                     const int64_t p = p0 + (int64_t)u * nthr + tid;
                     uint32_t q = q4[u];
-                    const uint64_t seed = seed4[u];
                     while (q != 0) {
                         const int64_t n = (int64_t)q - 1;
                         q = a.ix.next[n];
                         const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
-                        if ((w0 ^ seed) & keepS) continue;
-                        const int len = read_length(a.reads, n);
-                        if (p + len > L) continue;
-                        if (!verify_at(a, gw, gm, cc, p, n, len, w0)) continue;
-                        const uint32_t old = atomicMin(&best[n - r0], (uint32_t)p);
-                        if (old == POS_INF) {
-                            const int slot = atomicAdd(&s_nhit, 1);
-                            if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
-                        }
+                        if ((w0 ^ seed4[u]) & keepS) continue;
+                        if (p + read_length(a.reads, n) > L) continue;
+                        const int slot = atomicAdd(&s_ncand[it], 1);
+                        if (slot < PLACE_CAND_CAP) s_cand[slot] = make_uint2((uint32_t)n, (uint32_t)p);
+                        else verify_and_record(n, p);  // queue full (long chains): verify in place
                     }
                 }
+                __syncthreads();
+                const int nc = s_ncand[it] < PLACE_CAND_CAP ? s_ncand[it] : PLACE_CAND_CAP;
+                if (tid == 0) s_ncand[it ^ 1] = 0;
+                for (int i = tid; i < nc; i += nthr) {
+                    const uint2 cd = s_cand[i];
+                    verify_and_record((int64_t)cd.x, (int64_t)cd.y);
+                }
+                __syncthreads();
             }
             // ---- reads outside the index: text comparison, one read per thread ----
             int i = 0;
@@ -724,7 +752,7 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
     return t;
 }
 
-__global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
+__global__ void __launch_bounds__(128) k_break_score(ScoreArgs a) {
     __shared__ double s_w[32];
     __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
     __shared__ int s_item, s_novf, s_maxc, s_nz;
@@ -939,13 +967,22 @@ __global__ void __launch_bounds__(512, 3) k_truth_spectrum_smem(SpectrumArgs a) 
     const int nword = (a.R_y + 1) >> 1;
     for (int i = tid; i < nword; i += nthr) s_h[i] = 0;
     __syncthreads();
-    for (int64_t p = tid; p < nwin; p += nthr) {
-        const int64_t wi = p >> 5;
-        const uint32_t o = (uint32_t)(p & 31);
-        if (window32(__ldg(&gm[wi]), __ldg(&gm[wi + 1]), o) & kbits) continue;
-        const uint64_t code = window64(__ldg(&gw[wi]), __ldg(&gw[wi + 1]), o) >> kshift;
-        const int32_t rk = __ldg(&a.rank_y[code]);
-        if (rk >= 0) atomicAdd(&s_h[rk >> 1], 1u << (16 * (rk & 1)));
+    for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {  // four rank gathers per thread in flight
+        int32_t rk[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t p = p0 + (int64_t)u * nthr + tid;
+            rk[u] = -1;
+            if (p < nwin) {
+                const int64_t wi = p >> 5;
+                const uint32_t o = (uint32_t)(p & 31);
+                if (!(window32(__ldg(&gm[wi]), __ldg(&gm[wi + 1]), o) & kbits))
+                    rk[u] = __ldg(&a.rank_y[window64(__ldg(&gw[wi]), __ldg(&gw[wi + 1]), o) >> kshift]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (rk[u] >= 0) atomicAdd(&s_h[rk[u] >> 1], 1u << (16 * (rk[u] & 1)));
     }
     __syncthreads();
     // inclusive prefix over ranks: every thread owns an even number of consecutive ranks
@@ -1043,7 +1080,7 @@ BS_HD int hist_phys_words(int R_x, bool packed) {
     return w + (w >> 5) + 2;
 }
 
-template <bool PACKED>
+template <bool PACKED, bool IN_SMEM>
 __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -1051,7 +1088,7 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     __shared__ int64_t s_wmax[32];
     __shared__ int s_item;
     // dynamic shared memory (or the global scratch row): histogram words, then one count per range
-    uint32_t *s_hist = a.rank_scratch ? a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges) : (uint32_t *)bs_dyn_smem();
+    uint32_t *s_hist = IN_SMEM ? (uint32_t *)bs_dyn_smem() : a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges);
     uint32_t *s_rc = s_hist + a.hist_words;
     const bool want_ks = a.ks != nullptr;
     const int kshift = 64 - 2 * a.kmer;
@@ -1140,28 +1177,62 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                 const int first = PACKED ? rank0 >> 1 : rank0;
                 const int nword = n_logical - first < (PACKED ? 32 : 64) ? n_logical - first : (PACKED ? 32 : 64);
                 const int w0 = hist_word<PACKED>(rank0);  // the range's words are contiguous (pad only at k = 32)
-#pragma unroll 4
-                for (int k = 0; k < nword; k++) {
-                    const uint32_t word = s_hist[w0 + k + (PACKED ? 0 : (k >> 5))];
-                    if (word == 0) continue;
-                    s_hist[w0 + k + (PACKED ? 0 : (k >> 5))] = 0;  // leave the histogram zeroed for the next contig
-                    const int nsub = PACKED ? 2 : 1;
-                    for (int h = 0; h < nsub; h++) {
-                        const uint32_t cnt = PACKED ? (word >> (16 * h)) & 0xffffu : word;
-                        if (cnt == 0) continue;
-                        const int i = rank0 + (PACKED ? 2 * k + h : k);
-                        if (defined) {
-                            const LeLt q = a.lelt[i];
-                            const int64_t lt = q.lt >= 0 ? ycum[q.lt] : 0;
-                            const int64_t le = q.le >= 0 ? ycum[q.le] : 0;
-                            int64_t d1 = run * n_y - lt * nwin;
-                            run += cnt;
-                            int64_t d2 = run * n_y - le * nwin;
-                            if (d1 < 0) d1 = -d1;
-                            if (d2 < 0) d2 = -d2;
-                            if (d1 > best) best = d1;
-                            if (d2 > best) best = d2;
+                // one present x value: the statistic just below it and at it
+                auto eval = [&](int i, uint32_t cnt, LeLt q) {
+                    const int64_t lt = q.lt >= 0 ? ycum[q.lt] : 0;
+                    const int64_t le = q.le >= 0 ? ycum[q.le] : 0;
+                    int64_t d1 = run * n_y - lt * nwin;
+                    run += cnt;
+                    int64_t d2 = run * n_y - le * nwin;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    if (d1 > best) best = d1;
+                    if (d2 > best) best = d2;
+                };
+                if (PACKED) {
+                    // Few of the 64 ranks are present.  First compact them into the words already
+                    // consumed (entry = offset << 24 | count), then evaluate the short list: lanes
+                    // of a warp then loop over ~3 entries each instead of diverging over 64 ranks,
+                    // and two entries' dependent gathers (lelt -> ycum) are in flight at a time.
+                    int nent = 0;
+                    auto flush = [&]() {
+                        for (int j = 0; j < nent; j += 2) {
+                            const uint32_t e0 = s_hist[w0 + j];
+                            const uint32_t e1 = j + 1 < nent ? s_hist[w0 + j + 1] : 0u;
+                            s_hist[w0 + j] = 0;
+                            if (j + 1 < nent) s_hist[w0 + j + 1] = 0;
+                            const int i0 = rank0 + (int)(e0 >> 24), i1 = rank0 + (int)(e1 >> 24);
+                            LeLt q0 = a.lelt[i0], q1;
+                            q1.le = q1.lt = -1;
+                            if (e1) q1 = a.lelt[i1];
+                            if (defined) {
+                                eval(i0, e0 & 0xffffffu, q0);
+                                if (e1) eval(i1, e1 & 0xffffffu, q1);
+                            }
                         }
+                        nent = 0;
+                    };
+                    for (int k = 0; k < nword; k++) {
+                        const uint32_t word = s_hist[w0 + k];
+                        if (word == 0) continue;
+                        s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const uint32_t cnt = (word >> (16 * h)) & 0xffffu;
+                            if (cnt == 0) continue;
+                            if (nent > k) flush();  // no consumed word left to hold the entry (dense range): rare
+                            s_hist[w0 + nent] = ((uint32_t)(2 * k + h) << 24) | cnt;
+                            nent++;
+                        }
+                    }
+                    flush();
+                } else {
+                    for (int k = 0; k < nword; k++) {
+                        const int wi = w0 + k + (k >> 5);
+                        const uint32_t cnt = s_hist[wi];
+                        if (cnt == 0) continue;
+                        s_hist[wi] = 0;
+                        if (defined) eval(rank0 + k, cnt, a.lelt[rank0 + k]);
                     }
                 }
             }

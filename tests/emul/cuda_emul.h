@@ -218,6 +218,10 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 struct uint4 {
     unsigned x, y, z, w;
 };
+struct uint2 {
+    unsigned x, y;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
