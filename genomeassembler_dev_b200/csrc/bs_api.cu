@@ -37,7 +37,7 @@ constexpr int kPackThreads = 64;
 constexpr int kPlaceIxThreads = 64;
 #else
 constexpr int kPlaceThreads = 256;
-constexpr int kScoreThreads = 128;
+constexpr int kScoreThreads = 256;
 constexpr int kStartposThreads = 256;
 constexpr int kKsThreads = 512;
 constexpr int kPackThreads = 256;
@@ -737,7 +737,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         // else (all-distinct tables with long contigs) a per-block global scratch that stays in L2
         const bool packed = max_ctg - kmer + 1 < 65536;
         pa.hist_words = ks_a ? bs::hist_phys_words(k.R_x, packed) : 0;
-        pa.n_ranges = ks_a ? (k.R_x + 63) / 64 : 0;
+        pa.n_ranges = ks_a ? bs::hist_ranges(k.R_x, packed) : 0;
         const size_t hist_bytes = (size_t)(pa.hist_words + pa.n_ranges) * 4;
         const bool in_smem = hist_bytes + 2048 <= ctx->smem_optin;
         const size_t smem = in_smem ? hist_bytes : 0;

@@ -550,25 +550,28 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
             // Phase 2 (dense): one queued candidate per thread is verified on the packed words. ----
             int it = 0;
             for (int64_t p0 = 0; p0 + S <= L; p0 += 4 * (int64_t)nthr, it ^= 1) {
+                // a thread takes four CONSECUTIVE positions (never straddling a word boundary)
+                const int64_t pb = p0 + 4 * (int64_t)tid;
                 uint32_t q4[4];
                 uint64_t seed4[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int64_t p = p0 + (int64_t)u * nthr + tid;
-                    q4[u] = 0;
-                    seed4[u] = 0;
-                    if (p + S <= L) {
-                        const int64_t idx = p >> 5;
-                        const uint32_t o = (uint32_t)(p & 31);
-                        if (!(window32(__ldg(&gm[idx]), __ldg(&gm[idx + 1]), o) & keepSm)) {  // else: a non-ACGT base in the seed window
-                            seed4[u] = window64(__ldg(&gw[idx]), __ldg(&gw[idx + 1]), o) & keepS;
+                for (int u = 0; u < 4; u++) { q4[u] = 0; seed4[u] = 0; }
+                if (pb + S <= L) {
+                    const int64_t idx = pb >> 5;
+                    const uint32_t o = (uint32_t)(pb & 31);
+                    const uint64_t cw0 = __ldg(&gw[idx]), cw1 = __ldg(&gw[idx + 1]);
+                    const uint32_t cm0 = __ldg(&gm[idx]), cm1 = __ldg(&gm[idx + 1]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (pb + u + S <= L && !(window32(cm0, cm1, o + u) & keepSm)) {  // else: a non-ACGT base in the seed window
+                            seed4[u] = window64(cw0, cw1, o + u) & keepS;
                             q4[u] = head[seed_hash(seed4[u]) & hmask];
                         }
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int64_t p = p0 + (int64_t)u * nthr + tid;
+                    const int64_t p = pb + u;
                     uint32_t q = q4[u];
                     while (q != 0) {
                         const int64_t n = (int64_t)q - 1;
@@ -752,7 +755,7 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
     return t;
 }
 
-__global__ void __launch_bounds__(128) k_break_score(ScoreArgs a) {
+__global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
     __shared__ double s_w[32];
     __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
     __shared__ int s_item, s_novf, s_maxc, s_nz;
@@ -967,18 +970,20 @@ __global__ void __launch_bounds__(512, 3) k_truth_spectrum_smem(SpectrumArgs a) 
     const int nword = (a.R_y + 1) >> 1;
     for (int i = tid; i < nword; i += nthr) s_h[i] = 0;
     __syncthreads();
-    for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {  // four rank gathers per thread in flight
+    // a thread takes four CONSECUTIVE windows (never straddling a 32-base word boundary): the truth
+    // words are loaded once per four windows and the four rank gathers are in flight together
+    for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {
+        const int64_t pb = p0 + 4 * (int64_t)tid;
+        if (pb >= nwin) continue;
+        const int64_t wi = pb >> 5;
+        const uint32_t o = (uint32_t)(pb & 31);
+        const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
+        const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
         int32_t rk[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int64_t p = p0 + (int64_t)u * nthr + tid;
             rk[u] = -1;
-            if (p < nwin) {
-                const int64_t wi = p >> 5;
-                const uint32_t o = (uint32_t)(p & 31);
-                if (!(window32(__ldg(&gm[wi]), __ldg(&gm[wi + 1]), o) & kbits))
-                    rk[u] = __ldg(&a.rank_y[window64(__ldg(&gw[wi]), __ldg(&gw[wi + 1]), o) >> kshift]);
-            }
+            if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) rk[u] = __ldg(&a.rank_y[window64(w0, w1, o + u) >> kshift]);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
@@ -1063,22 +1068,22 @@ struct ProbDistArgs {
     double *ks;              // optional [C]
     uint32_t *rank_scratch;  // [gridDim][hist_words + n_ranges] global rank histogram when it does not fit shared memory, else NULL
     int32_t hist_words;      // 32-bit words of one rank histogram (hist_phys_words)
-    int32_t n_ranges;        // ceil(R_x / 64)
+    int32_t n_ranges;        // hist_ranges: ranges of 32 histogram words
 };
 
-// Rank histogram layout.  Ranks are grouped into RANGES of 64 (one thread sweeps one range);
-// PACKED: two 16-bit counters per 32-bit word (every contig of the launch has < 65536 windows).
-// One pad word after every 32 keeps a warp's simultaneous sweeps on different banks.
-constexpr int KS_RANGE_SHIFT = 6;
+// Rank histogram layout.  PACKED: two 16-bit counters per 32-bit word (every contig of the launch
+// has < 65536 windows), else one counter per word.  Words are grouped into RANGES of 32 (one
+// thread sweeps one range) with one pad word after every range, which keeps a warp's
+// simultaneous sweeps on different banks.  A bitmap word per range marks the non-empty words, so
+// a sweep touches only those: its cost follows the contig's windows, not the number of ranks.
 template <bool PACKED>
-__device__ __forceinline__ int hist_word(int r) {
-    const int w = PACKED ? r >> 1 : r;
-    return w + (w >> 5);
-}
+__device__ __forceinline__ int hist_logical_word(int r) { return PACKED ? r >> 1 : r; }
+BS_HD int hist_logical_words(int R_x, bool packed) { return packed ? (R_x + 1) / 2 : R_x; }
 BS_HD int hist_phys_words(int R_x, bool packed) {
-    const int w = packed ? (R_x + 1) / 2 : R_x;
+    const int w = hist_logical_words(R_x, packed);
     return w + (w >> 5) + 2;
 }
+BS_HD int hist_ranges(int R_x, bool packed) { return (hist_logical_words(R_x, packed) + 31) / 32; }
 
 template <bool PACKED, bool IN_SMEM>
 __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
@@ -1087,9 +1092,9 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     __shared__ int64_t s_wsum[32];
     __shared__ int64_t s_wmax[32];
     __shared__ int s_item;
-    // dynamic shared memory (or the global scratch row): histogram words, then one count per range
+    // dynamic shared memory (or the global scratch row): histogram words, then the range bitmaps
     uint32_t *s_hist = IN_SMEM ? (uint32_t *)bs_dyn_smem() : a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges);
-    uint32_t *s_rc = s_hist + a.hist_words;
+    uint32_t *s_bm = s_hist + a.hist_words;
     const bool want_ks = a.ks != nullptr;
     const int kshift = 64 - 2 * a.kmer;
     const uint32_t kbits = keep_bits(a.kmer);
@@ -1108,21 +1113,24 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         int64_t nwin = L - a.kmer + 1;
         if (nwin < 0) nwin = 0;
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
-        // ---- windows: table value out, rank histogram in ----
+        // ---- windows: table value out, rank histogram in.  A thread takes four CONSECUTIVE
+        // positions (they never straddle a 32-base word boundary), so the contig words are
+        // loaded once per four windows; the four table gathers are in flight together ----
         for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {
+            const int64_t pb = p0 + 4 * (int64_t)tid;
             double val[4];
             int32_t rk[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int64_t p = p0 + (int64_t)u * nthr + tid;
-                val[u] = 0.0;
-                rk[u] = a.rank_zero;
-                if (p < nwin && a.win) {
-                    const int64_t wi = p >> 5;
-                    const uint32_t o = (uint32_t)(p & 31);
-                    if (!(window32(__ldg(&gm[wi]), __ldg(&gm[wi + 1]), o) & kbits)) {
-                        const uint64_t code = window64(__ldg(&gw[wi]), __ldg(&gw[wi + 1]), o) >> kshift;
-                        const WinEntry e = a.win[code];  // one 16-byte gather
+            for (int u = 0; u < 4; u++) { val[u] = 0.0; rk[u] = a.rank_zero; }
+            if (pb < nwin && a.win) {
+                const int64_t wi = pb >> 5;
+                const uint32_t o = (uint32_t)(pb & 31);  // multiple of 4: o + 3 <= 31
+                const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
+                const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) {
+                        const WinEntry e = a.win[window64(w0, w1, o + u) >> kshift];  // one 16-byte gather
                         val[u] = e.prob;
                         rk[u] = e.rank;
                     }
@@ -1130,13 +1138,12 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int64_t p = p0 + (int64_t)u * nthr + tid;
-                if (p < nwin) {
-                    if (pd) pd[p] = val[u];
+                if (pb + u < nwin) {
+                    if (pd) pd[pb + u] = val[u];
                     if (want_ks) {
-                        if (PACKED) atomicAdd(&s_hist[hist_word<true>(rk[u])], 1u << (16 * (rk[u] & 1)));
-                        else atomicAdd(&s_hist[hist_word<false>(rk[u])], 1u);
-                        atomicAdd(&s_rc[rk[u] >> KS_RANGE_SHIFT], 1u);
+                        const int lw = hist_logical_word<PACKED>(rk[u]);
+                        atomicAdd(&s_hist[lw + (lw >> 5)], PACKED ? 1u << (16 * (rk[u] & 1)) : 1u);
+                        atomicOr(&s_bm[lw >> 5], 1u << (lw & 31));
                     }
                 }
             }
@@ -1153,10 +1160,16 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         // 64-bit integers (both factors are below 2^31), one division at the end
         int64_t best = 0;
         int64_t carry = 0;  // windows in the ranges of earlier rounds (same value on every thread)
-        for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {  // one range of 64 ranks per thread and round
+        for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {  // one range of 32 words per thread and round
             const int r = r0 + tid;
-            const int64_t cnt_r = r < a.n_ranges ? s_rc[r] : 0;
-            if (cnt_r) s_rc[r] = 0;
+            const uint32_t m = r < a.n_ranges ? s_bm[r] : 0u;
+            if (m) s_bm[r] = 0;
+            const int w0 = 33 * r;  // physical index of the range's first word
+            int64_t cnt_r = 0;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const uint32_t w = s_hist[w0 + __ffs((int)mm) - 1];
+                cnt_r += PACKED ? (w & 0xffffu) + (w >> 16) : w;
+            }
             // exclusive prefix of the range counts over the block (+ what earlier rounds held)
             int64_t incl = cnt_r;
 #pragma unroll
@@ -1171,14 +1184,16 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                 if (w < warp) run += s_wsum[w];
                 carry += s_wsum[w];
             }
-            if (cnt_r) {
-                const int rank0 = r << KS_RANGE_SHIFT;
-                const int n_logical = PACKED ? (a.R_x + 1) >> 1 : a.R_x;  // the last range is partial
-                const int first = PACKED ? rank0 >> 1 : rank0;
-                const int nword = n_logical - first < (PACKED ? 32 : 64) ? n_logical - first : (PACKED ? 32 : 64);
-                const int w0 = hist_word<PACKED>(rank0);  // the range's words are contiguous (pad only at k = 32)
-                // one present x value: the statistic just below it and at it
-                auto eval = [&](int i, uint32_t cnt, LeLt q) {
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const int k = __ffs((int)mm) - 1;
+                const uint32_t w = s_hist[w0 + k];
+                s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
+#pragma unroll
+                for (int h = 0; h < (PACKED ? 2 : 1); h++) {
+                    const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
+                    if (cnt == 0 || !defined) continue;
+                    const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
+                    const LeLt q = a.lelt[i];
                     const int64_t lt = q.lt >= 0 ? ycum[q.lt] : 0;
                     const int64_t le = q.le >= 0 ? ycum[q.le] : 0;
                     int64_t d1 = run * n_y - lt * nwin;
@@ -1188,52 +1203,6 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                     if (d2 < 0) d2 = -d2;
                     if (d1 > best) best = d1;
                     if (d2 > best) best = d2;
-                };
-                if (PACKED) {
-                    // Few of the 64 ranks are present.  First compact them into the words already
-                    // consumed (entry = offset << 24 | count), then evaluate the short list: lanes
-                    // of a warp then loop over ~3 entries each instead of diverging over 64 ranks,
-                    // and two entries' dependent gathers (lelt -> ycum) are in flight at a time.
-                    int nent = 0;
-                    auto flush = [&]() {
-                        for (int j = 0; j < nent; j += 2) {
-                            const uint32_t e0 = s_hist[w0 + j];
-                            const uint32_t e1 = j + 1 < nent ? s_hist[w0 + j + 1] : 0u;
-                            s_hist[w0 + j] = 0;
-                            if (j + 1 < nent) s_hist[w0 + j + 1] = 0;
-                            const int i0 = rank0 + (int)(e0 >> 24), i1 = rank0 + (int)(e1 >> 24);
-                            LeLt q0 = a.lelt[i0], q1;
-                            q1.le = q1.lt = -1;
-                            if (e1) q1 = a.lelt[i1];
-                            if (defined) {
-                                eval(i0, e0 & 0xffffffu, q0);
-                                if (e1) eval(i1, e1 & 0xffffffu, q1);
-                            }
-                        }
-                        nent = 0;
-                    };
-                    for (int k = 0; k < nword; k++) {
-                        const uint32_t word = s_hist[w0 + k];
-                        if (word == 0) continue;
-                        s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const uint32_t cnt = (word >> (16 * h)) & 0xffffu;
-                            if (cnt == 0) continue;
-                            if (nent > k) flush();  // no consumed word left to hold the entry (dense range): rare
-                            s_hist[w0 + nent] = ((uint32_t)(2 * k + h) << 24) | cnt;
-                            nent++;
-                        }
-                    }
-                    flush();
-                } else {
-                    for (int k = 0; k < nword; k++) {
-                        const int wi = w0 + k + (k >> 5);
-                        const uint32_t cnt = s_hist[wi];
-                        if (cnt == 0) continue;
-                        s_hist[wi] = 0;
-                        if (defined) eval(rank0 + k, cnt, a.lelt[rank0 + k]);
-                    }
                 }
             }
             __syncthreads();  // s_wsum is rewritten by the next round
