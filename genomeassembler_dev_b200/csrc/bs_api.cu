@@ -102,7 +102,7 @@ struct bs_ctx {
     char err[512] = "";
     int64_t launches = 0;
     int64_t chunk_bytes_host = (int64_t)96 << 20;    // ASCII bytes per chunk when inputs come from the host
-    int64_t chunk_bytes_dev = (int64_t)1024 << 20;   // ... when they are already on the device
+    int64_t chunk_bytes_dev = (int64_t)4096 << 20;   // ... when they are already on the device
 
     // table
     bool has_table = false;

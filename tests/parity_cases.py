@@ -24,6 +24,13 @@ MEDIUM = [
     (35, 50000, 300, 30, 8, 0),
     (36, 20000, 64, 30, 12, 1),    # read length a multiple of 32
     (37, 20000, 65, 30, 12, 1),
+    # cfg-3: read-length sweep 50-300 bp; candidate sets get shorter and more numerous with larger k
+    (38, 50000, 50, 30, 120, 0),
+    (39, 50000, 75, 30, 80, 1),
+    (40, 50000, 200, 30, 40, 0),
+    (41, 50000, 250, 30, 25, 1),
+    (42, 50000, 14, 40, 60, 0),    # script 00 grid, second row
+    (43, 50000, 25, 40, 40, 0),
 ]
 
 

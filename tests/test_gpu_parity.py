@@ -156,3 +156,68 @@ def test_chunked_pipeline_equals_one_chunk(product_lib, gpu_scorer, kmers, prob,
     for k in one:
         assert np.array_equal(one[k], many[k], equal_nan=True), k
         assert np.array_equal(one[k], again[k], equal_nan=True), k
+
+
+# ---- cfg-4 / cfg-5 shapes ---------------------------------------------------------------------
+
+def test_cfg4_scaffold_set(gpu_scorer, oracle, kmers, prob):
+    """cfg-4 shape: thousands of 10-50 kb scaffolds (permuted concatenations of the same base contigs)
+    of ONE segment.  A sample of scaffolds against the oracle; all of them through size-independent
+    properties: histogram checksum under the integer table, equal scaffolds score equally, and
+    contig-sharding over 1/2/4/8 ranks (reads replicated) changes nothing, bit for bit."""
+    from genomeassembler_dev_b200 import sharding
+    seg = synth.make_scaffold_set(404, length=50000, read_len=150, coverage=30, n_base=16, n_scaffolds=1500)
+    sample = list(range(0, 1500, 75))
+    sub = synth.Segment(seg.truth, seg.reads, [seg.contigs[i] for i in sample])
+    P.check_segment(gpu_scorer, oracle, kmers, prob, sub, flags=B.DEFAULT_FLAGS | B.WANT_HIST)
+    T = len(prob)
+    rowid = np.arange(1, T + 1, dtype=np.float64)
+    gpu_scorer.set_table(kmers, rowid)
+    chk = gpu_scorer.score(seg.contigs, seg.reads, seg.truth, flags=B.WANT_HIST)
+    assert np.array_equal(chk["bp_score"], (chk["hist"][:, :T].astype(np.float64) * rowid).sum(axis=1))
+    assert np.array_equal(chk["hist"].sum(axis=1), chk["kmer_breaks"])
+    gpu_scorer.set_table(kmers, prob)
+    flags = B.WANT_KS | B.WANT_STARTPOS
+    whole = gpu_scorer.score(seg.contigs, seg.reads, seg.truth, flags=flags)
+    assert np.array_equal(whole["kmer_breaks"], chk["kmer_breaks"])
+    first = {}
+    for i, c in enumerate(seg.contigs):
+        j = first.setdefault(c, i)
+        if j != i:
+            for k in ("bp_score", "kmer_breaks", "ks_stat_prob_dist", "ks_stat_path_freq", "path_prob_dist_startpos"):
+                assert whole[k][i] == whole[k][j] or (np.isnan(whole[k][i]) and np.isnan(whole[k][j])), k
+    lens = [len(c) for c in seg.contigs]
+    for world in (2, 4, 8):
+        parts = sharding.shard_contigs_lpt(lens, world)
+        for part in parts:
+            res = gpu_scorer.score([seg.contigs[i] for i in part], seg.reads, seg.truth, flags=flags)
+            for k in ("bp_score", "bp_score_norm_by_break_freqs", "kmer_breaks", "ks_stat_prob_dist", "ks_stat_path_freq",
+                      "path_prob_dist_startpos"):
+                assert np.array_equal(res[k], whole[k][part], equal_nan=True), (world, k)
+
+
+def test_cfg5_shape_scaled(gpu_scorer, oracle, kmers, prob):
+    """cfg-5 shape scaled to test size: one 1 Mb truth, 1e5 uniform-start 150 bp reads, 1000 contigs of
+    about 1 kb.  A sample of contigs against the oracle (contigs are independent), the rest through the
+    histogram checksum."""
+    rng = np.random.default_rng(505)
+    L, N, Cn, r = 1_000_000, 100_000, 1000, 150
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, L))
+    starts = rng.integers(0, L - r, size=N)
+    reads = truth[starts[:, None] + np.arange(r)[None, :]]
+    cstart = np.sort(rng.integers(0, L - 3000, size=Cn))
+    clen = rng.integers(200, 2000, size=Cn)
+    contigs = [truth[a:a + b].tobytes() for a, b in zip(cstart, clen)]
+    seg = synth.Segment(truth.tobytes(), reads, contigs)
+    sample = list(range(0, Cn, 50))
+    sub = synth.Segment(seg.truth, seg.reads, [contigs[i] for i in sample])
+    got, want = P.check_segment(gpu_scorer, oracle, kmers, prob, sub, flags=B.DEFAULT_FLAGS | B.WANT_HIST)
+    assert np.array_equal(got["path_prob_dist_startpos"], cstart[sample].astype(np.int32) * (got["kmer_breaks"] > 0))
+    T = len(prob)
+    rowid = np.arange(1, T + 1, dtype=np.float64)
+    gpu_scorer.set_table(kmers, rowid)
+    chk = gpu_scorer.score(contigs, reads, seg.truth, flags=B.WANT_HIST | B.WANT_STARTPOS)
+    assert np.array_equal(chk["bp_score"], (chk["hist"][:, :T].astype(np.float64) * rowid).sum(axis=1))
+    # a read starting inside a contig and ending inside it is placed there exactly once
+    expect = np.array([np.count_nonzero((starts >= a) & (starts + r <= a + b)) for a, b in zip(cstart, clen)])
+    assert np.all(chk["kmer_breaks"] >= expect)
