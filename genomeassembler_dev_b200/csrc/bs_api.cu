@@ -71,7 +71,7 @@ struct Workspace {
     size_t h_meta_cap = 0;
     DevBuf meta, read_chars, read_off, ctg_chars, tr_chars;
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
-    DevBuf w, total, ycnt, head, next, odd_head, spbest;
+    DevBuf w, total, ycnt, yx, head, next, odd_head, spbest;
     DevBuf out_i32, out_f64, pd, hist, pos;
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
@@ -501,7 +501,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     BS_TRY(ensure(ctx, ws.total, (size_t)C * 4));
     if (!tile_mode) {
         BS_TRY(ensure(ctx, ws.head, (size_t)std::max<int64_t>(head_total, 1) * 4));
-        BS_TRY(ensure(ctx, ws.next, (size_t)std::max<int64_t>(N, 1) * 4));
+        BS_TRY(ensure(ctx, ws.next, (size_t)std::max<int64_t>(N, 1) * 8));
         BS_TRY(ensure(ctx, ws.odd_head, (size_t)std::max<int64_t>(S, 1) * 4));
     }
     if (!e.dev_res) {
@@ -595,7 +595,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     bs::ReadIndex ix;
     std::memset(&ix, 0, sizeof(ix));
     if (!tile_mode) {
-        ix.head = (uint32_t *)ws.head.p; ix.next = (uint32_t *)ws.next.p; ix.odd_head = (uint32_t *)ws.odd_head.p;
+        ix.head = (uint32_t *)ws.head.p; ix.next = (uint2 *)ws.next.p; ix.odd_head = (uint32_t *)ws.odd_head.p;
         ix.tab_off = d_tab_off; ix.tab_mask = d_tab_mask; ix.seed_len = d_seed; ix.seg_read_start = d_seg_rs; ix.n_seg = (int32_t)S;
     }
     {
@@ -669,12 +669,14 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         const KsCache &k = ctx->ks;
         const int R_y = std::max(k.R_y, 1);
         BS_TRY(ensure(ctx, ws.ycnt, (size_t)S * R_y * 4));
+        if (ks_a) BS_TRY(ensure(ctx, ws.yx, (size_t)S * k.R_x * sizeof(bs::LeLt)));
         StageTimer tm(ctx, ST_SPECTRUM, st);
         const size_t sp_smem = (size_t)((k.R_y + 1) / 2) * 4;
         bs::SpectrumArgs sp;
         sp.tr_off = d_tr_off; sp.tr_woff = d_tr_woff; sp.tr_words = ts.words; sp.tr_mask = ts.mask;
         sp.rank_y = (const int32_t *)k.rank_y.p; sp.ycnt = (int32_t *)ws.ycnt.p;
         sp.R_y = R_y; sp.kmer = kmer; sp.blocks_per_seg = 1;
+        sp.lelt = ks_a ? (const bs::LeLt *)k.lelt.p : nullptr; sp.yx = ks_a ? (bs::LeLt *)ws.yx.p : nullptr; sp.R_x = k.R_x;
         if (k.R_y > 0 && kmer <= bs::MAXK && max_tr - kmer + 1 < 65536 && sp_smem + 1024 <= ctx->smem_optin) {
             // one block per segment, histogram and prefix sum in shared memory
             BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
@@ -687,6 +689,10 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
                 BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, st, sp);
                 ctx->launches++;
                 BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, st, (int32_t *)ws.ycnt.p, R_y);
+                ctx->launches++;
+            }
+            if (ks_a) {
+                BS_LAUNCH(bs::k_yx_gather, grid_for(S * (int64_t)k.R_x, kScoreThreads, grid_cap), kScoreThreads, 0, st, sp, S);
                 ctx->launches++;
             }
         }
@@ -727,7 +733,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
         pa.ctg_seg = d_ctg_seg;
         pa.win = (kmer >= 1 && kmer <= bs::MAXK) ? (const bs::WinEntry *)k.win.p : nullptr;
-        pa.lelt = (const bs::LeLt *)k.lelt.p;
+        pa.yx = ks_a ? (const bs::LeLt *)ws.yx.p : nullptr;
         pa.ycum = ks_a ? (const int32_t *)ws.ycnt.p : nullptr;
         pa.R_x = k.R_x; pa.R_y = k.R_y; pa.rank_zero = k.rank_zero;
         pa.kmer = kmer; pa.n_contigs = C;
@@ -877,7 +883,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
-                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.head, &w.next, &w.odd_head, &w.spbest,
+                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.head, &w.next, &w.odd_head, &w.spbest,
                         &w.out_i32, &w.out_f64, &w.pd, &w.hist, &w.pos};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);

@@ -48,6 +48,16 @@ BS_HD uint32_t seed_hash(uint64_t s) {
     return x;
 }
 
+// second, independent 32-bit mix of a seed: stored with a read in its index chain
+BS_HD uint32_t seed_tag(uint64_t s) {
+    uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+    uint32_t x = lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
+    x ^= x >> 16;
+    x *= 0x165667B1u;
+    x ^= x >> 15;
+    return x;
+}
+
 // ---- the break-k-mer rule --------------------------------------------------------------
 // A read placed at `pos` of a contig of length L breaks the k-mer
 //   contig.substr(start, e),  start = max(0, pos - kmer/2),  e = 8, except when start == 0:

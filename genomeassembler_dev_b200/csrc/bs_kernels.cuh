@@ -94,7 +94,7 @@ __global__ void k_pack_seqs(SeqSet s) {
 // are placed by byte comparison.  Built by the packing kernels, consumed by k_place_index.
 struct ReadIndex {
     uint32_t *head;
-    uint32_t *next;           // [N]
+    uint2 *next;              // [N] x = next read id + 1 of the bucket (0 ends the chain), y = seed tag
     uint32_t *odd_head;       // [S]
     const int64_t *tab_off;   // [S]
     const int32_t *tab_mask;  // [S] table size - 1 (size is a power of two)
@@ -116,10 +116,11 @@ __device__ __forceinline__ int segment_of_read(const ReadIndex &ix, int64_t n) {
 __device__ __forceinline__ void index_insert(const ReadIndex &ix, int s, int64_t n, uint64_t word0, int len, bool seed_bad) {
     const int S = ix.seed_len[s];
     if (len == 0 || seed_bad) {
-        ix.next[n] = atomicExch(&ix.odd_head[s], (uint32_t)n + 1u);
+        ix.next[n] = make_uint2(atomicExch(&ix.odd_head[s], (uint32_t)n + 1u), 0u);
     } else {
-        const uint32_t h = seed_hash(word0 & keep_bases(S)) & (uint32_t)ix.tab_mask[s];
-        ix.next[n] = atomicExch(&ix.head[ix.tab_off[s] + h], (uint32_t)n + 1u);
+        const uint64_t seed = word0 & keep_bases(S);
+        const uint32_t h = seed_hash(seed) & (uint32_t)ix.tab_mask[s];
+        ix.next[n] = make_uint2(atomicExch(&ix.head[ix.tab_off[s] + h], (uint32_t)n + 1u), seed_tag(seed));
     }
 }
 
@@ -535,6 +536,7 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
         // a read with an equal seed at position p: verify the rest, keep the leftmost position
         auto verify_and_record = [&](int64_t n, int64_t p) {
             const int len = read_length(a.reads, n);
+            if (p + len > L) return;
             const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
             if (!verify_at(a, gw, gm, cc, p, n, len, w0)) return;
             const uint32_t old = atomicMin(&best[n - r0], (uint32_t)p);
@@ -573,12 +575,12 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
                 for (int u = 0; u < 4; u++) {
                     const int64_t p = pb + u;
                     uint32_t q = q4[u];
-                    while (q != 0) {
-                        const int64_t n = (int64_t)q - 1;
-                        q = a.ix.next[n];
-                        const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
-                        if ((w0 ^ seed4[u]) & keepS) continue;
-                        if (p + read_length(a.reads, n) > L) continue;
+                    const uint32_t tag = seed_tag(seed4[u]);
+                    while (q != 0) {  // the chain entry carries a 32-bit tag of the read's seed: the packed
+                        const int64_t n = (int64_t)q - 1;  // reads themselves are only touched in phase 2
+                        const uint2 e = a.ix.next[n];
+                        q = e.x;
+                        if (e.y != tag) continue;
                         const int slot = atomicAdd(&s_ncand[it], 1);
                         if (slot < PLACE_CAND_CAP) s_cand[slot] = make_uint2((uint32_t)n, (uint32_t)p);
                         else verify_and_record(n, p);  // queue full (long chains): verify in place
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
             int i = 0;
             for (uint32_t q = a.ix.odd_head[s]; q != 0; i++) {
                 const int64_t n = (int64_t)q - 1;
-                q = a.ix.next[n];
+                q = a.ix.next[n].x;
                 if (i % nthr != tid) continue;
                 const int64_t p = find_bytes(cc, L, a.reads.chars + read_begin(a.reads, n), read_length(a.reads, n));
                 if (p < 0) continue;
@@ -926,6 +928,12 @@ __global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
 // lib/GenerateReads.R:243-259): per segment, counts of truth windows per distinct table value
 // ------------------------------------------------------------------------------------------
 
+// per x-value rank: index into the truth cumulative counts of the last y value <= / < that x value
+// (table level), or the cumulative counts themselves (segment level, yx below)
+struct LeLt {
+    int32_t le, lt;
+};
+
 struct SpectrumArgs {
     const int64_t *tr_off;
     const int64_t *tr_woff;
@@ -933,6 +941,9 @@ struct SpectrumArgs {
     const uint32_t *tr_mask;
     const int32_t *rank_y;  // [4^kmer] rank of the window's truth-table value, -1 = not in table (NA)
     int32_t *ycnt;          // [S][R_y]
+    const LeLt *lelt;       // [R_x] table-level indices (NULL: no yx output)
+    LeLt *yx;               // [S][R_x] #{truth windows <= x value}, #{truth windows < x value} per x-value rank
+    int32_t R_x;
     int32_t R_y;
     int32_t kmer;
     int32_t blocks_per_seg;
@@ -1016,6 +1027,31 @@ __global__ void __launch_bounds__(512, 3) k_truth_spectrum_smem(SpectrumArgs a) 
     __syncthreads();
     int32_t *out = a.ycnt + s * a.R_y;
     for (int i = tid; i < a.R_y; i += nthr) out[i] = (int32_t)((s_h[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+    if (a.lelt) {  // the same counts looked up per x-value rank: the KS sweep then needs one gather, not two
+        LeLt *yx = a.yx + s * a.R_x;
+        for (int i = tid; i < a.R_x; i += nthr) {
+            const LeLt q = a.lelt[i];
+            LeLt o;
+            o.le = q.le >= 0 ? (int32_t)((s_h[q.le >> 1] >> (16 * (q.le & 1))) & 0xffffu) : 0;
+            o.lt = q.lt >= 0 ? (int32_t)((s_h[q.lt >> 1] >> (16 * (q.lt & 1))) & 0xffffu) : 0;
+            yx[i] = o;
+        }
+    }
+}
+
+// yx from the cumulative counts in global memory (after k_truth_spectrum + k_row_cumsum)
+__global__ void k_yx_gather(SpectrumArgs a, int64_t n_seg) {
+    const int64_t total = n_seg * a.R_x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = t / a.R_x;
+        const int i = (int)(t - s * a.R_x);
+        const LeLt q = a.lelt[i];
+        const int32_t *ycum = a.ycnt + s * a.R_y;
+        LeLt o;
+        o.le = q.le >= 0 ? ycum[q.le] : 0;
+        o.lt = q.lt >= 0 ? ycum[q.lt] : 0;
+        a.yx[t] = o;
+    }
 }
 
 // in-place inclusive prefix sum of every row of a [rows][R] int32 matrix; one block per row
@@ -1043,10 +1079,6 @@ struct alignas(16) WinEntry {
     int32_t rank;
     int32_t pad;
 };
-// per x-value rank: index into the truth cumulative counts of the last y value <= / < that x value
-struct LeLt {
-    int32_t le, lt;
-};
 
 struct ProbDistArgs {
     const int32_t *order;     // [C] contig ids, longest first
@@ -1057,7 +1089,7 @@ struct ProbDistArgs {
     const uint32_t *ctg_mask;
     const int32_t *ctg_seg;  // [C] segment of a contig
     const WinEntry *win;     // [4^kmer], NULL when kmer is outside 1..8 (every window is "not in the table")
-    const LeLt *lelt;        // [R_x]
+    const LeLt *yx;          // [S][R_x] truth windows <= / < every x value
     const int32_t *ycum;     // [S][R_y] inclusive cumulative counts of the truth distribution
     int32_t R_x, R_y;
     int32_t rank_zero;       // rank of the value 0.0 (windows not in the table)
@@ -1154,6 +1186,7 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         // is present: just below it (F_x of the previous step vs #{y < v}) and at it ----
         const int64_t seg = a.ctg_seg[c];
         const int32_t *ycum = a.ycum + seg * a.R_y;
+        const LeLt *yx = a.yx + seg * a.R_x;
         const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
         const bool defined = nwin > 0 && n_y > 0;
         // |F_x - F_y| = |run * n_y - ycount * nwin| / (nwin * n_y): the numerator is maximised in exact
@@ -1193,9 +1226,8 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                     const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
                     if (cnt == 0 || !defined) continue;
                     const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
-                    const LeLt q = a.lelt[i];
-                    const int64_t lt = q.lt >= 0 ? ycum[q.lt] : 0;
-                    const int64_t le = q.le >= 0 ? ycum[q.le] : 0;
+                    const LeLt q = yx[i];  // one 8-byte gather
+                    const int64_t lt = q.lt, le = q.le;
                     int64_t d1 = run * n_y - lt * nwin;
                     run += cnt;
                     int64_t d2 = run * n_y - le * nwin;
