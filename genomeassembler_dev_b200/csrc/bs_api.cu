@@ -614,7 +614,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             if (!e.roff && e.rlen >= 1) {
                 BS_CUDA(cudaMemsetAsync(ws.rflags.p, 0, (size_t)N + 8, st));
                 const int64_t tiles = (N * W + bs::PACK_THREADS - 1) / bs::PACK_THREADS;
-                BS_LAUNCH(bs::k_pack_reads_uniform, (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 8), bs::PACK_THREADS, 0, st, rs, ix);
+                BS_LAUNCH(bs::k_pack_reads_uniform, (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_pack_reads_uniform, bs::PACK_THREADS, 0)), bs::PACK_THREADS, 0, st, rs, ix);
             } else {
                 BS_LAUNCH(bs::k_pack_reads, grid_for(N, kPackThreads, grid_cap), kPackThreads, 0, st, rs, ix);
             }

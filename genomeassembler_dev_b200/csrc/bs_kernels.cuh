@@ -171,7 +171,7 @@ __device__ __forceinline__ uint32_t pack16(uint32_t x0, uint32_t x1, uint32_t x2
 }
 
 constexpr int PACK_THREADS = 256;
-constexpr int PACK_WARP_CELLS = 68;  // 16-byte cells a warp tile (32 words = at most 1024 bytes + alignment) can touch
+constexpr int PACK_WARP_CELLS = 66;  // 16-byte cells a warp tile (32 words = at most 1024 bytes + alignment) can touch
 
 // One WARP tile = 32 consecutive output words (AoS order: read-major).  Their source bytes are
 // one contiguous span of the dense read buffer: staged by coalesced 16-byte loads, converted
@@ -189,31 +189,42 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
     const uintptr_t base = (uintptr_t)r.chars;
     const int L = r.uniform_len;
     const uint32_t W = (uint32_t)r.W;
+    // every warp owns a contiguous run of tiles: consecutive tiles read adjacent bytes and stay in
+    // the same segment, and the next tile's loads can be issued before the current one is finished
     const int64_t warps_total = (int64_t)gridDim.x * (PACK_THREADS / 32);
-    int64_t k0 = ((int64_t)blockIdx.x * (PACK_THREADS / 32) + warp) * 32;
-    if (k0 >= n_words) return;
+    const int64_t tiles_total = (n_words + 31) / 32;
+    const int64_t per_warp = (tiles_total + warps_total - 1) / warps_total;
+    const int64_t wid = (int64_t)blockIdx.x * (PACK_THREADS / 32) + warp;
+    int64_t k0 = wid * per_warp * 32;
+    int64_t k_end = k0 + per_warp * 32;
+    if (k_end > n_words) k_end = n_words;
+    if (k0 >= k_end) return;
     // (read, word-in-read) of the tile's first word: one 64-bit division, then 32-bit increments
     int64_t n0 = k0 / W;
     uint32_t j0 = (uint32_t)(k0 - n0 * W);
-    const uint32_t adv = (uint32_t)(warps_total * 32 % W);
-    const int64_t adv_n = warps_total * 32 / W;
+    const uint32_t adv = 32u % W, adv_n = 32u / W;
     int seg = ix.head ? segment_of_read(ix, n0) : 0;
-    for (; k0 < n_words; k0 += warps_total * 32) {
-        const int ntile = (int)(n_words - k0 < 32 ? n_words - k0 : 32);
-        const uint32_t xl = j0 + (uint32_t)ntile - 1;
+
+    // geometry of a tile and the (up to three) 16-byte cells this lane stages for it
+    struct Tile { int64_t lo16; int n_cells; int ntile; };
+    auto tile_of = [&](int64_t k, int64_t n, uint32_t j) {
+        Tile t;
+        t.ntile = (int)(k_end - k < 32 ? k_end - k : 32);
+        const uint32_t xl = j + (uint32_t)t.ntile - 1;
         const uint32_t dnl = xl / W;
-        const int64_t lo = n0 * L + (int64_t)j0 * 32;  // first source byte of the tile
-        int64_t hi = (n0 + dnl) * L + (int64_t)(xl - dnl * W) * 32 + 32;  // one past the last
+        const int64_t lo = n * L + (int64_t)j * 32;                          // first source byte of the tile
+        int64_t hi = (n + dnl) * L + (int64_t)(xl - dnl * W) * 32 + 32;      // one past the last
         if (hi > total_bytes) hi = total_bytes;
-        const int64_t lo16 = lo - (int64_t)((base + (uintptr_t)lo) & 15);  // 16-byte aligned address, may be < 0
-        const int n_cells = (int)((hi - lo16 + 15) >> 4);
-        __syncwarp();
-        for (int ci = lane; ci < n_cells; ci += 32) {
-            const int64_t cb = lo16 + 16 * (int64_t)ci;
-            uint32_t x0, x1, x2, x3;
+        t.lo16 = lo - (int64_t)((base + (uintptr_t)lo) & 15);               // 16-byte aligned address, may be < 0
+        t.n_cells = (int)((hi - t.lo16 + 15) >> 4);
+        return t;
+    };
+    auto load_cell = [&](const Tile &t, int ci) {
+        uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+        if (ci < t.n_cells) {
+            const int64_t cb = t.lo16 + 16 * (int64_t)ci;
             if (cb >= 0 && cb + 16 <= total_bytes) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(r.chars + cb);
-                x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+                v = *reinterpret_cast<const uint4 *>(r.chars + cb);
             } else {  // partly outside the buffer: bytes that do not exist read as 'A'
                 uint32_t xs[4];
                 for (int q = 0; q < 4; q++) {
@@ -224,34 +235,67 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
                     }
                     xs[q] = x;
                 }
-                x0 = xs[0]; x1 = xs[1]; x2 = xs[2]; x3 = xs[3];
+                v = make_uint4(xs[0], xs[1], xs[2], xs[3]);
             }
+        }
+        return v;
+    };
+
+    Tile t = tile_of(k0, n0, j0);
+    uint4 c0 = load_cell(t, lane), c1 = load_cell(t, lane + 32), c2 = load_cell(t, lane + 64);
+    for (;;) {
+        // ---- convert this tile's cells into the warp's shared-memory slice ----
+        __syncwarp();
+        {
             uint32_t diff = 0;
-            s_code[ci] = pack16(x0, x1, x2, x3, diff);
-            s_bad[ci] = diff;
+            s_code[lane] = pack16(c0.x, c0.y, c0.z, c0.w, diff);
+            s_bad[lane] = diff;
+            diff = 0;
+            s_code[lane + 32] = pack16(c1.x, c1.y, c1.z, c1.w, diff);
+            s_bad[lane + 32] = diff;
+            if (lane + 64 < PACK_WARP_CELLS) {
+                diff = 0;
+                s_code[lane + 64] = pack16(c2.x, c2.y, c2.z, c2.w, diff);
+                s_bad[lane + 64] = diff;
+            }
         }
         __syncwarp();
-        if (lane < ntile) {
-            const uint32_t x = j0 + (uint32_t)lane;
+        // ---- issue the next tile's loads before cutting this tile's words ----
+        const Tile cur = t;
+        const int64_t k_cur = k0, n_cur = n0;
+        const uint32_t j_cur = j0;
+        k0 += 32;
+        n0 += adv_n;
+        j0 += adv;
+        if (j0 >= W) { j0 -= W; n0++; }
+        const bool more = k0 < k_end;
+        if (more) {
+            t = tile_of(k0, n0, j0);
+            c0 = load_cell(t, lane);
+            c1 = load_cell(t, lane + 32);
+            c2 = load_cell(t, lane + 64);
+        }
+        if (lane < cur.ntile) {
+            const uint32_t x = j_cur + (uint32_t)lane;
             const uint32_t dn = x / W;
-            const int64_t n = n0 + dn;
+            const int64_t n = n_cur + dn;
             const int j = (int)(x - dn * W);
-            const int64_t a = n * L + 32 * j - lo16;  // byte offset inside the staged span
-            const int ci = (int)(a >> 4);
+            const int a = (int)(n * L + 32 * j - cur.lo16);  // byte offset inside the staged span (< 1100)
+            const int ci = a >> 4;
             const uint32_t sh = 2u * (uint32_t)(a & 15);
             const int rem = L - 32 * j;  // bases of this word that belong to the read (may exceed 32)
             // cells past the staged span are only touched by bases beyond the read: clamp the index
-            const int c1 = ci + 1 < n_cells ? ci + 1 : n_cells - 1, c2 = ci + 2 < n_cells ? ci + 2 : n_cells - 1;
-            const uint32_t w0 = s_code[ci], w1 = s_code[c1], w2 = s_code[c2];
+            const int i1 = ci + 1 < cur.n_cells ? ci + 1 : cur.n_cells - 1, i2 = ci + 2 < cur.n_cells ? ci + 2 : cur.n_cells - 1;
+            const uint32_t w0 = s_code[ci], w1 = s_code[i1], w2 = s_code[i2];
             const uint32_t o_hi = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
             const uint32_t o_lo = sh ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;
             const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(rem);
-            r.words[k0 + lane] = word;
+            r.words[k_cur + lane] = word;
             // cells overlapping this word's own bytes [a, a + min(rem, 32))
-            const int last_cell = (int)((a + (rem < 32 ? rem : 32) - 1) >> 4);
+            const int last_cell = (a + (rem < 32 ? rem : 32) - 1) >> 4;
             uint32_t bad = s_bad[ci];
-            if (last_cell >= ci + 1) bad |= s_bad[c1];
-            if (last_cell >= ci + 2) bad |= s_bad[c2];
+            if (last_cell >= ci + 1) bad |= s_bad[i1];
+            if (last_cell >= ci + 2) bad |= s_bad[i2];
             if (bad) atomicOr(reinterpret_cast<unsigned *>(r.flags) + (n >> 2), 1u << (8 * (int)(n & 3)));
             if (j == 0 && ix.head) {
                 int sg = seg;  // reads of a tile rarely span more than one segment
@@ -259,10 +303,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, 
                 index_insert(ix, sg, n, word, L, bad != 0);
             }
         }
-        // next tile of this warp
-        n0 += adv_n;
-        j0 += adv;
-        if (j0 >= W) { j0 -= W; n0++; }
+        if (!more) break;
         if (ix.head) while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
     }
 }

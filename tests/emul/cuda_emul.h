@@ -218,6 +218,7 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 struct uint4 {
     unsigned x, y, z, w;
 };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct uint2 {
     unsigned x, y;
 };
