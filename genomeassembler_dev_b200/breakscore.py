@@ -38,7 +38,8 @@ ABI_SYMBOLS = (
     "bs_abi_version", "bs_ctx_create", "bs_ctx_destroy", "bs_last_error", "bs_ctx_set_stream",
     "bs_ctx_synchronize", "bs_ctx_launch_count", "bs_ctx_enable_timing", "bs_ctx_last_timings",
     "bs_ctx_last_place_ms", "bs_set_table", "bs_set_truth_table", "bs_score_batch", "bs_score",
-    "bs_host_alloc", "bs_host_free",
+    "bs_host_alloc", "bs_host_free", "bs_assemble_contigs", "bs_assemble_last_error", "bs_string_list_size",
+    "bs_string_list_bytes", "bs_string_list_copy", "bs_string_list_free",
 )
 
 _i64p = C.POINTER(C.c_int64)
@@ -116,6 +117,18 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_host_alloc.argtypes = [C.c_int64]
     lib.bs_host_free.restype = None
     lib.bs_host_free.argtypes = [C.c_void_p]
+    lib.bs_assemble_contigs.restype = C.c_int
+    lib.bs_assemble_contigs.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(C.c_void_p)]
+    lib.bs_assemble_last_error.restype = C.c_char_p
+    lib.bs_string_list_size.restype = C.c_int64
+    lib.bs_string_list_size.argtypes = [C.c_void_p]
+    lib.bs_string_list_bytes.restype = C.c_int64
+    lib.bs_string_list_bytes.argtypes = [C.c_void_p]
+    lib.bs_string_list_copy.restype = None
+    lib.bs_string_list_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bs_string_list_free.restype = None
+    lib.bs_string_list_free.argtypes = [C.c_void_p]
     if lib.bs_abi_version() != 1:
         raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 1")
     return lib
@@ -333,3 +346,25 @@ def calc_breakscore(path, sequencing_reads, true_solution, kmer, bp_kmer, bp_pro
         sc.set_table(bp_kmer, prob, tprob)
         sc._table_key = key
     return sc.score(path, sequencing_reads, true_solution, kmer=kmer, flags=flags)
+
+
+def assemble_contigs(velvet_contigs, dbg_kmer, seed, *, n_shuffles=20000, n_threads=0, lib_path=None):
+    """Drop-in for the upstream export ``assemble_contigs(velvet_contigs, dbg_kmer, seed)``
+    (lib/BreakageScorer.cpp:79-83): the scaffold explosion that produces the candidate set scored by
+    :func:`calc_breakscore`.  Host code in the same library (all cores); returns a list of bytes,
+    longest first, in upstream's order."""
+    lib = load_library(lib_path)
+    chars, off = flatten(velvet_contigs)
+    h = C.c_void_p()
+    rc = lib.bs_assemble_contigs(_ptr(chars), _ptr(off), len(velvet_contigs), int(dbg_kmer), int(seed), int(n_shuffles),
+                                 int(n_threads), C.byref(h))
+    if rc != 0:
+        raise BreakscoreError(rc, lib.bs_assemble_last_error().decode())
+    try:
+        n = lib.bs_string_list_size(h)
+        out_chars = np.zeros(max(int(lib.bs_string_list_bytes(h)), 1), np.uint8)
+        out_off = np.zeros(n + 1, np.int64)
+        lib.bs_string_list_copy(h, _ptr(out_chars), _ptr(out_off))
+    finally:
+        lib.bs_string_list_free(h)
+    return [out_chars[out_off[i]:out_off[i + 1]].tobytes() for i in range(n)]

@@ -16,6 +16,7 @@
  * calc_breakscore body, lib/BreakageScorer.cpp:200-353| bs_score (one segment) / bs_score_batch
  * ks.test statistic, lib/DeNovoAssembler.R:416-424    | BS_WANT_KS outputs of the same calls
  * Rcpp::stop / R error                                | int status + bs_last_error
+ * assemble_contigs, lib/BreakageScorer.cpp:79-174     | bs_assemble_contigs (host; candidate generator)
  */
 #ifndef BREAKSCORE_H
 #define BREAKSCORE_H
@@ -140,6 +141,22 @@ BS_API int bs_score_batch(bs_ctx *ctx, const bs_batch *batch, int kmer, uint32_t
 BS_API int bs_score(bs_ctx *ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
              const char *read_chars, const int64_t *read_off, int64_t n_reads,
              const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *result);
+
+/*
+ * Scaffold explosion on the host (upstream assemble_contigs, lib/BreakageScorer.cpp:79-174): the
+ * generator of the candidate set that bs_score then scores.  n_shuffles: upstream uses 20000;
+ * n_threads <= 0: all host cores.  The result is an opaque list of strings (longest first, upstream
+ * order), read with bs_string_list_size / _bytes / _copy (chars may be NULL to get offsets only;
+ * off has size+1 entries) and released with bs_string_list_free.  Needs no GPU.
+ */
+typedef struct bs_string_list bs_string_list;
+BS_API int bs_assemble_contigs(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer,
+                               int seed, int n_shuffles, int n_threads, bs_string_list **out);
+BS_API const char *bs_assemble_last_error(void);
+BS_API int64_t bs_string_list_size(const bs_string_list *l);
+BS_API int64_t bs_string_list_bytes(const bs_string_list *l);
+BS_API void bs_string_list_copy(const bs_string_list *l, char *chars, int64_t *off);
+BS_API void bs_string_list_free(bs_string_list *l);
 
 /* pinned host memory for staging buffers (cudaHostAlloc / cudaFreeHost) */
 BS_API void *bs_host_alloc(int64_t bytes);

@@ -175,3 +175,22 @@ def ref_calc_breakscore(path, sequencing_reads, true_solution, kmer, bp_kmer, bp
     if want_prob_dist:
         out["path_prob_dist"] = [pd[pd_off[i]:pd_off[i + 1]].copy() for i in range(nc)]
     return out
+
+
+def ref_assemble_contigs(velvet_contigs, dbg_kmer, seed):
+    """The unmodified upstream assemble_contigs (lib/BreakageScorer.cpp:79-174, 20 000 shuffles)."""
+    lib = _load(os.path.join("_ref", "libref_breakscore_noedit.so"))
+    fn = lib.ref_assemble_contigs
+    fn.restype = C.c_int64
+    ct, ct_off = flatten(velvet_contigs)
+    need = C.c_int64(0)
+    n = fn(_p(ct, C.c_char_p), _p(ct_off, _c_i64p), C.c_int64(len(velvet_contigs)), C.c_int(dbg_kmer), C.c_int(seed),
+           None, C.c_int64(0), C.byref(need))
+    if n < 0:
+        raise RuntimeError("reference assemble_contigs threw")
+    buf = C.create_string_buffer(max(need.value, 1))
+    n = fn(_p(ct, C.c_char_p), _p(ct_off, _c_i64p), C.c_int64(len(velvet_contigs)), C.c_int(dbg_kmer), C.c_int(seed),
+           buf, C.c_int64(need.value), C.byref(need))
+    items = buf.raw[:need.value].split(b"\n")[:-1] if need.value else []
+    assert len(items) == n
+    return items

@@ -1,9 +1,9 @@
 // [[Rcpp::plugins("cpp17")]]
 // Drop-in replacement for the scorer half of upstream lib/BreakageScorer.cpp: the same
 // Rcpp-exported entry point, argument list and returned list (upstream :185-191, :343-353), with
-// the body replaced by one call into libbreakscore.so (include/breakscore.h).  The other export of
-// the upstream file, assemble_contigs (:79-174, host C++), is not part of the accelerated path: keep
-// upstream's definition next to this one.
+// the bodies replaced by calls into libbreakscore.so (include/breakscore.h).  Both exports of the
+// upstream file are here: assemble_contigs (:79-174, the scaffold explosion, native host code in the
+// library) and calc_breakscore (the scorer, CUDA).
 //
 // Build from R:
 //   Sys.setenv(PKG_CXXFLAGS = "-I<repo>/include", PKG_LIBS = "-L<repo>/genomeassembler_dev_b200 -lbreakscore -Wl,-rpath,<repo>/genomeassembler_dev_b200")
@@ -66,6 +66,30 @@ char *flatten(const std::vector<std::string> &v, char *dst, std::vector<int64_t>
 }
 
 }  // namespace
+
+// Same name, arguments and result as upstream lib/BreakageScorer.cpp:79-83: every scaffold reachable by
+// greedy suffix/prefix merging over 20 000 seeded shuffles of the contig list, duplicates removed,
+// longest first (identical strings in identical order; multi-threaded host code, no GPU needed).
+// [[Rcpp::export]]
+std::vector<std::string> assemble_contigs(
+    const std::vector<std::string> &velvet_contigs,
+    const int &dbg_kmer,
+    const int &seed) {
+    std::vector<char> chars((size_t)flat_size(velvet_contigs) + 1);
+    std::vector<int64_t> off;
+    flatten(velvet_contigs, chars.data(), off);
+    bs_string_list *list = nullptr;
+    if (bs_assemble_contigs(chars.data(), off.data(), (int64_t)velvet_contigs.size(), dbg_kmer, seed, 20000, 0, &list) != BS_OK)
+        Rcpp::stop(bs_assemble_last_error());
+    const int64_t n = bs_string_list_size(list);
+    std::vector<char> out_chars((size_t)bs_string_list_bytes(list) + 1);
+    std::vector<int64_t> out_off((size_t)n + 1);
+    bs_string_list_copy(list, out_chars.data(), out_off.data());
+    bs_string_list_free(list);
+    std::vector<std::string> res((size_t)n);
+    for (int64_t i = 0; i < n; i++) res[(size_t)i].assign(out_chars.data() + out_off[i], (size_t)(out_off[i + 1] - out_off[i]));
+    return res;
+}
 
 // Optional: probabilities used for the truth-side distribution of the KS columns.  The upstream
 // driver keeps the REAL table there even in its "random" pass (lib/DeNovoAssembler.R:326-333);
