@@ -75,7 +75,7 @@ def emul_lib():
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++20", "-DBS_CPU_EMUL", "-fPIC", "-shared", "-pthread",
                         "-I", os.path.join(ROOT, "tests", "emul"), "-I", csrc, "-x", "c++",
-                        os.path.join(csrc, "bs_api.cu"), "-o", out], check=True)
+                        os.path.join(csrc, "bs_api.cu"), os.path.join(csrc, "bs_assemble.cpp"), "-o", out], check=True)
     return out
 
 
