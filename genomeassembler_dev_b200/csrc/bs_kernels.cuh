@@ -1336,9 +1336,10 @@ __device__ __forceinline__ bool startpos_indexable(const StartposArgs &a, int64_
 }
 
 __global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
-    __shared__ uint64_t s_key[SP_SLOTS];
-    __shared__ int32_t s_head[SP_SLOTS];  // local contig index + 1 of the first contig with that seed
+    __shared__ unsigned long long s_key[SP_SLOTS + 1];  // slot SP_SLOTS is reserved for the all-ones seed (= the empty marker)
+    __shared__ int32_t s_head[SP_SLOTS + 1];  // local contig index + 1 of the first contig with that seed
     __shared__ int32_t s_next[SP_GROUP];  // next contig with the same seed
+    const unsigned long long EMPTY = ~0ull;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const int seg = blockIdx.x / a.splits, part = blockIdx.x % a.splits;
     const int64_t LT = a.tr_off[seg + 1] - a.tr_off[seg];
@@ -1356,19 +1357,24 @@ __global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
     for (int64_t g0 = c0; g0 < c1; g0 += SP_GROUP) {
         const int gn = (int)(c1 - g0 < SP_GROUP ? c1 - g0 : SP_GROUP);
         __syncthreads();
-        for (int i = tid; i < SP_SLOTS; i += nthr) s_head[i] = 0;
+        for (int i = tid; i <= SP_SLOTS; i += nthr) { s_head[i] = 0; s_key[i] = EMPTY; }
         __syncthreads();
-        if (tid == 0) {  // serial build: a few dozen contigs per segment in the usual case
-            for (int i = 0; i < gn; i++) {
-                const int64_t c = g0 + i;
-                if (!startpos_indexable(a, c, LT)) continue;
-                const uint64_t key = a.ctg_words[a.ctg_woff[c]];
-                uint32_t h = seed_hash(key) & (SP_SLOTS - 1);
-                while (s_head[h] != 0 && s_key[h] != key) h = (h + 1) & (SP_SLOTS - 1);
-                s_next[i] = s_head[h];  // chain: newest first
-                s_key[h] = key;
-                s_head[h] = i + 1;
+        // parallel build: claim the seed's slot by compare-and-swap (linear probing), then push the
+        // contig on the slot's chain
+        for (int i = tid; i < gn; i += nthr) {
+            const int64_t c = g0 + i;
+            if (!startpos_indexable(a, c, LT)) continue;
+            const unsigned long long key = a.ctg_words[a.ctg_woff[c]];
+            uint32_t h = SP_SLOTS;
+            if (key != EMPTY) {
+                h = seed_hash(key) & (SP_SLOTS - 1);
+                for (;;) {
+                    const unsigned long long prev = atomicCAS(&s_key[h], EMPTY, key);
+                    if (prev == EMPTY || prev == key) break;
+                    h = (h + 1) & (SP_SLOTS - 1);
+                }
             }
+            s_next[i] = atomicExch(&s_head[h], i + 1);
         }
         __syncthreads();
         for (int64_t qb = q_begin; qb < q_end; qb += nthr) {
@@ -1378,11 +1384,16 @@ __global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
                 const int64_t idx = q >> 5;
                 const uint32_t o = (uint32_t)(q & 31);
                 if (window32(__ldg(&tm[idx]), __ldg(&tm[idx + 1]), o) == 0) {
-                    const uint64_t seed = window64(__ldg(&tw[idx]), __ldg(&tw[idx + 1]), o);
-                    uint32_t h = seed_hash(seed) & (SP_SLOTS - 1);
-                    while (s_head[h] != 0) {
-                        if (s_key[h] == seed) { cand = s_head[h]; break; }
-                        h = (h + 1) & (SP_SLOTS - 1);
+                    const unsigned long long seed = window64(__ldg(&tw[idx]), __ldg(&tw[idx + 1]), o);
+                    if (seed == EMPTY) cand = s_head[SP_SLOTS];
+                    else {
+                        uint32_t h = seed_hash(seed) & (SP_SLOTS - 1);
+                        for (;;) {
+                            const unsigned long long k = s_key[h];
+                            if (k == EMPTY) break;
+                            if (k == seed) { cand = s_head[h]; break; }
+                            h = (h + 1) & (SP_SLOTS - 1);
+                        }
                     }
                 }
             }

@@ -80,6 +80,8 @@ def edge_inputs():
          [rep[45:70], rep[60:80]], rep[:90] + b"NNNN" + rep[3:60], 8),
         ("seed_repeats_before_match", [b"A" * 40 + b"G", b"A" * 33 + b"C"], [b"A" * 20, b"AAAC"],
          b"A" * 40 + b"C" + b"A" * 40 + b"G" + b"A" * 50, 8),
+        ("all_T_seed", [b"T" * 40 + b"ACG", b"T" * 36, b"A" * 33 + b"T"], [b"T" * 20, b"TTACG", b"AAAT"],
+         b"G" + b"T" * 40 + b"ACG" + b"A" * 40 + b"T", 8),
         ("contig_equals_truth", [rep[:200]], [rep[5:30]], rep[:200], 8),
         ("exact_word_boundaries", [rep[:64], rep[:96], rep[:32]], [rep[:32], rep[32:64], rep[:64], rep[31:64], rep[1:33]], rep, 8),
     ]

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Stage timings of the scorer on the other BASELINE.json shapes (not the bench line): cfg-1 single
+segment, cfg-3 read-length sweep, cfg-4 scaffold set, cfg-5 scaled.  Prints one JSON line per shape."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from genomeassembler_dev_b200 import breakscore as B, synth, tables  # noqa: E402
+
+
+def run(sc, name, seg, reps=3, flags=B.DEFAULT_FLAGS):
+    ct, ct_off = B.flatten(seg.contigs)
+    rd = np.ascontiguousarray(seg.reads).reshape(-1)
+    tr, tr_off = B.flatten([seg.truth])
+    args = (rd, None, seg.reads.shape[1], ct, ct_off, tr, tr_off, [0, seg.reads.shape[0]], [0, len(seg.contigs)])
+    sc.score_batch(*args, flags=flags)
+    sc.enable_timing(True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = sc.score_batch(*args, flags=flags)
+    wall = (time.perf_counter() - t0) / reps
+    st = {k: round(v, 3) for k, v in sc.last_timings().items() if v >= 0}
+    sc.enable_timing(False)
+    pair = seg.reads.shape[0] * float(sum(len(c) for c in seg.contigs))
+    print(json.dumps({"shape": name, "reads": int(seg.reads.shape[0]), "contigs": len(seg.contigs),
+                      "contig_bases": int(sum(len(c) for c in seg.contigs)), "wall_ms": round(wall * 1e3, 2),
+                      "pair_Gbp_per_s_wall": round(pair / 1e9 / wall, 1), "stage_ms": st,
+                      "placed": int(res["kmer_breaks"].sum())}), flush=True)
+
+
+def main():
+    kmers, prob = tables.all_kmer_strings(), tables.normalised(tables.load_raw())
+    sc = B.BreakageScorer(0)
+    sc.set_table(kmers, prob)
+    run(sc, "cfg1: 50 kb, r=100 30x, 16 contigs", synth.make_segment(1234, 50000, 100, 30, 16))
+    for r in (50, 300):
+        run(sc, f"cfg3: 50 kb, r={r} 30x, 40 contigs", synth.make_segment(1300 + r, 50000, r, 30, 40))
+    run(sc, "cfg3: 50 kb, r=12 40x, 60 contigs (script 00 grid)", synth.make_segment(1312, 50000, 12, 40, 60))
+    run(sc, "cfg4: 10000 scaffolds of 10-50 kb, one segment", synth.make_scaffold_set(1400, n_scaffolds=10000), reps=2,
+        flags=B.WANT_KS | B.WANT_STARTPOS)
+    rng = np.random.default_rng(1500)
+    L, N, Cn, r = 10_000_000, 2_000_000, 10_000, 150
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, L))
+    starts = rng.integers(0, L - r, size=N)
+    reads = truth[starts[:, None] + np.arange(r)[None, :]]
+    cstart = np.sort(rng.integers(0, L - 3000, size=Cn))
+    clen = rng.integers(200, 2000, size=Cn)
+    seg = synth.Segment(truth.tobytes(), reads, [truth[a:a + b].tobytes() for a, b in zip(cstart, clen)])
+    run(sc, "cfg5 scaled 1/10: 10 Mb truth, 2e6 reads, 1e4 contigs of ~1 kb", seg, reps=2)
+
+
+if __name__ == "__main__":
+    main()
