@@ -25,6 +25,7 @@ WANT_KS = 0x002
 WANT_HIST = 0x004
 WANT_POS = 0x008
 WANT_STARTPOS = 0x010
+WANT_LEV = 0x020
 PLACE_SCAN = 0x100
 PLACE_TILE = 0x800
 DEVICE_CHARS = 0x200
@@ -32,7 +33,7 @@ DEVICE_RESULT = 0x400
 DEFAULT_FLAGS = WANT_PROB_DIST | WANT_KS | WANT_STARTPOS
 
 STAGES = ("h2d", "pack", "place", "score", "truth_spectrum", "prob_dist_ks", "ks_path_freq",
-          "startpos", "d2h")
+          "startpos", "d2h", "lev")
 
 ABI_SYMBOLS = (
     "bs_abi_version", "bs_ctx_create", "bs_ctx_destroy", "bs_last_error", "bs_ctx_set_stream",
@@ -335,7 +336,8 @@ def calc_breakscore(path, sequencing_reads, true_solution, kmer, bp_kmer, bp_pro
     bp_score_norm_by_break_freqs, bp_score_norm_by_len, kmer_breaks, lev_dist_vs_true,
     path_prob_dist_startpos, path_prob_dist`` and, with WANT_KS, ``ks_stat_prob_dist`` /
     ``ks_stat_path_freq`` (the statistic of lib/DeNovoAssembler.R:416-424 for the two variants
-    of the per-contig vector).  ``lev_dist_vs_true`` is not computed (edlib, off the path): 0.
+    of the per-contig vector).  ``lev_dist_vs_true`` is computed with WANT_LEV (infix edit distance, the
+    semantics of upstream's edlib call), else 0.
     """
     sc = default_scorer(device, lib_path)
     prob = np.ascontiguousarray(bp_prob, dtype=np.float64)

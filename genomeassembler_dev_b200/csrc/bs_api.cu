@@ -32,6 +32,7 @@ char g_create_error[512] = "";
 constexpr int kPlaceThreads = 64;
 constexpr int kScoreThreads = 64;
 constexpr int kStartposThreads = 64;
+constexpr int kLevThreads = 64;
 constexpr int kKsThreads = 64;
 constexpr int kPackThreads = 64;
 constexpr int kPlaceIxThreads = 64;
@@ -39,6 +40,7 @@ constexpr int kPlaceIxThreads = 64;
 constexpr int kPlaceThreads = 256;
 constexpr int kScoreThreads = 256;
 constexpr int kStartposThreads = 256;
+constexpr int kLevThreads = 128;
 constexpr int kKsThreads = 512;
 constexpr int kPackThreads = 256;
 constexpr int kPlaceIxThreads = 256;
@@ -49,7 +51,7 @@ constexpr int64_t kMinChunk = 2048;
 constexpr int kHitCap = 4096;         // reads placed per contig kept in shared memory (k_place_index)
 constexpr int kWorkspaces = 2;
 
-enum Stage { ST_H2D, ST_PACK, ST_PLACE, ST_SCORE, ST_SPECTRUM, ST_PROBDIST, ST_PATHFREQ, ST_STARTPOS, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D, ST_PACK, ST_PLACE, ST_SCORE, ST_SPECTRUM, ST_PROBDIST, ST_PATHFREQ, ST_STARTPOS, ST_D2H, ST_LEV, ST_COUNT };
 
 struct DevBuf {
     void *p = nullptr;
@@ -71,7 +73,7 @@ struct Workspace {
     size_t h_meta_cap = 0;
     DevBuf meta, read_chars, read_off, ctg_chars, tr_chars;
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
-    DevBuf w, total, ycnt, yx, head, next, odd_head, spbest;
+    DevBuf w, total, ycnt, yx, head, next, odd_head, spbest, exact;
     DevBuf out_i32, out_f64, pd, hist, pos;
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
@@ -117,7 +119,7 @@ struct bs_ctx {
 
     Workspace ws[kWorkspaces];
     // scratch shared by all chunks (kernels of different chunks never overlap: one compute stream)
-    DevBuf d_best, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters;
+    DevBuf d_best, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
     size_t best_elems = 0;
     bool best_dirty = true;
 
@@ -313,7 +315,7 @@ struct CallEnv {
     bs_result *res;
     int kmer;
     uint32_t flags;
-    bool dev_chars, dev_res, want_ks, want_pd, want_pos, want_hist, want_sp;
+    bool dev_chars, dev_res, want_ks, want_pd, want_pos, want_hist, want_sp, want_lev;
     const char *read_chars;  // base of read 0 (shifted when offsets turned out to be uniform)
     const int64_t *roff;     // read offsets or NULL (every read has rlen bytes, dense)
     int32_t rlen;
@@ -505,7 +507,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         BS_TRY(ensure(ctx, ws.odd_head, (size_t)std::max<int64_t>(S, 1) * 4));
     }
     if (!e.dev_res) {
-        BS_TRY(ensure(ctx, ws.out_i32, (size_t)3 * C * 4));
+        BS_TRY(ensure(ctx, ws.out_i32, (size_t)4 * C * 4));
         BS_TRY(ensure(ctx, ws.out_f64, (size_t)5 * C * 8));
         if (e.want_pd) BS_TRY(ensure(ctx, ws.pd, (size_t)std::max<int64_t>(pd_elems, 1) * 8));
         if (e.want_hist) BS_TRY(ensure(ctx, ws.hist, (size_t)C * (T + 1) * 4));
@@ -553,13 +555,14 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     BS_CUDA(cudaStreamWaitEvent(st, ws.ev_h2d, 0));
 
     // result destinations on the device
-    int32_t *o_len, *o_breaks, *o_startpos, *o_hist = nullptr, *o_pos = nullptr;
+    int32_t *o_len, *o_breaks, *o_startpos, *o_lev, *o_hist = nullptr, *o_pos = nullptr;
     double *o_score, *o_norm, *o_bylen, *o_ksa, *o_ksb, *o_pd = nullptr;
     const bool ks_a = e.want_ks && res->ks_stat_prob_dist, ks_b = e.want_ks && res->ks_stat_path_freq;
     if (e.dev_res) {
         o_len = res->sequence_len ? res->sequence_len + ch.c0 : nullptr;
         o_breaks = res->kmer_breaks ? res->kmer_breaks + ch.c0 : nullptr;
         o_startpos = e.want_sp ? res->path_prob_dist_startpos + ch.c0 : nullptr;
+        o_lev = e.want_lev ? res->lev_dist_vs_true + ch.c0 : nullptr;
         o_score = res->bp_score ? res->bp_score + ch.c0 : nullptr;
         o_norm = res->bp_score_norm_by_break_freqs ? res->bp_score_norm_by_break_freqs + ch.c0 : nullptr;
         o_bylen = res->bp_score_norm_by_len ? res->bp_score_norm_by_len + ch.c0 : nullptr;
@@ -572,6 +575,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         int32_t *i32 = (int32_t *)ws.out_i32.p;
         double *f64 = (double *)ws.out_f64.p;
         o_len = i32; o_breaks = i32 + C; o_startpos = e.want_sp ? i32 + 2 * C : nullptr;
+        o_lev = e.want_lev ? i32 + 3 * C : nullptr;
         o_score = f64; o_norm = f64 + C; o_bylen = f64 + 2 * C;
         o_ksa = ks_a ? f64 + 3 * C : nullptr;
         o_ksb = ks_b ? f64 + 4 * C : nullptr;
@@ -602,7 +606,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         StageTimer tm(ctx, ST_PACK, st);
         BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
         ctx->launches++;
-        if (e.want_ks || e.want_sp) {
+        if (e.want_ks || e.want_sp || e.want_lev) {
             BS_LAUNCH(bs::k_pack_seqs, grid_for(ts.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, ts);
             ctx->launches++;
         }
@@ -765,16 +769,18 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
         ctx->launches++;
     }
-    if (e.want_sp) {
+    if (e.want_sp || e.want_lev) {
         StageTimer tm(ctx, ST_STARTPOS, st);
         BS_TRY(ensure(ctx, ws.spbest, (size_t)C * 4));
         BS_CUDA(cudaMemsetAsync(ws.spbest.p, 0x7f, (size_t)C * 4, st));
+        if (e.want_lev) BS_TRY(ensure(ctx, ws.exact, (size_t)C * 4));
         bs::StartposArgs sa;
         sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_chars = d_cchars;
         sa.ctg_seg = d_ctg_seg; sa.seg_contig_start = d_seg_cs;
         sa.tr_off = d_tr_off; sa.tr_woff = d_tr_woff; sa.tr_words = ts.words; sa.tr_mask = ts.mask;
         sa.tr_chars = d_tchars; sa.total = (const int32_t *)ws.total.p; sa.n_contigs = C; sa.n_seg = (int32_t)S;
         sa.best = (uint32_t *)ws.spbest.p; sa.startpos = o_startpos;
+        sa.exact = e.want_lev ? (int32_t *)ws.exact.p : nullptr; sa.search_all = e.want_lev ? 1 : 0;
         // enough blocks to fill the machine even for a single segment; at least 2048 positions each
         int64_t splits = ((int64_t)ctx->sm_count * 4 + S - 1) / std::max<int64_t>(S, 1);
         splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 2047) / 2048));
@@ -784,12 +790,34 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kStartposThreads, 0, st, sa);
         ctx->launches++;
     }
+    if (e.want_lev) {
+        // infix edit distance contig vs truth: one warp per contig, longest first
+        StageTimer tm(ctx, ST_LEV, st);
+        const int warps_per_block = kLevThreads / 32;
+        int nblk = (int)std::min<int64_t>((C + warps_per_block - 1) / warps_per_block,
+                                          (int64_t)ctx->sm_count * blocks_per_sm(bs::k_lev_infix, kLevThreads, 0));
+        bs::LevArgs la;
+        la.order = d_order; la.work_counter = (int32_t *)ctx->d_counters.p + 3;
+        la.ctg_off = d_ctg_off; la.ctg_woff = d_ctg_woff; la.ctg_words = cs.words; la.ctg_mask = cs.mask; la.ctg_chars = d_cchars;
+        la.ctg_seg = d_ctg_seg; la.tr_off = d_tr_off; la.tr_woff = d_tr_woff; la.tr_words = ts.words; la.tr_mask = ts.mask;
+        la.tr_chars = d_tchars; la.exact = (const int32_t *)ws.exact.p; la.n_contigs = C; la.lev = o_lev;
+        la.hbuf = nullptr; la.hbuf_stride = 0;
+        if (max_ctg > 32 * 64) {  // chunk-boundary deltas of contigs longer than one warp of blocks
+            const int64_t stride = (max_tr + 63) / 64 * 64;
+            const int64_t budget = (int64_t)4 << 30;
+            nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * warps_per_block, 1)));
+            BS_TRY(ensure(ctx, ctx->d_hbuf, (size_t)nblk * warps_per_block * stride));
+            la.hbuf = (int8_t *)ctx->d_hbuf.p; la.hbuf_stride = stride;
+        }
+        BS_LAUNCH(bs::k_lev_infix, (unsigned)nblk, kLevThreads, 0, st, la);
+        ctx->launches++;
+    }
     BS_CUDA(cudaGetLastError());
     BS_CUDA(cudaEventRecord(ws.ev_compute, st));
 
     // ---------------- results ----------------
     if (e.dev_res) {
-        if (res->lev_dist_vs_true) BS_CUDA(cudaMemsetAsync(res->lev_dist_vs_true + ch.c0, 0, (size_t)C * 4, st));
+        if (res->lev_dist_vs_true && !e.want_lev) BS_CUDA(cudaMemsetAsync(res->lev_dist_vs_true + ch.c0, 0, (size_t)C * 4, st));
         if (!e.want_sp && res->path_prob_dist_startpos) BS_CUDA(cudaMemsetAsync(res->path_prob_dist_startpos + ch.c0, 0, (size_t)C * 4, st));
         BS_CUDA(cudaEventRecord(ws.ev_d2h, st));
         ws.in_flight = true;
@@ -807,6 +835,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         BS_CUDA(d2h(at(res->sequence_len, ch.c0), o_len, (size_t)C * 4));
         BS_CUDA(d2h(at(res->kmer_breaks, ch.c0), o_breaks, (size_t)C * 4));
         BS_CUDA(d2h(at(res->path_prob_dist_startpos, ch.c0), o_startpos, (size_t)C * 4));
+        BS_CUDA(d2h(at(res->lev_dist_vs_true, ch.c0), o_lev, (size_t)C * 4));
         BS_CUDA(d2h(at(res->bp_score, ch.c0), o_score, (size_t)C * 8));
         BS_CUDA(d2h(at(res->bp_score_norm_by_break_freqs, ch.c0), o_norm, (size_t)C * 8));
         BS_CUDA(d2h(at(res->bp_score_norm_by_len, ch.c0), o_bylen, (size_t)C * 8));
@@ -879,11 +908,11 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->d_tab, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
-                      &ctx->d_rank_scratch, &ctx->d_counters};
+                      &ctx->d_rank_scratch, &ctx->d_counters, &ctx->d_hbuf};
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
-                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.head, &w.next, &w.odd_head, &w.spbest,
+                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact,
                         &w.out_i32, &w.out_f64, &w.pd, &w.hist, &w.pos};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);
@@ -1060,6 +1089,7 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     e.want_pos = (flags & BS_WANT_POS) != 0;
     e.want_hist = (flags & BS_WANT_HIST) != 0;
     e.want_sp = (flags & BS_WANT_STARTPOS) && res->path_prob_dist_startpos;
+    e.want_lev = (flags & BS_WANT_LEV) && res->lev_dist_vs_true;
     e.read_chars = b->read_chars;
     e.roff = b->read_off;
     e.rlen = b->read_len;
@@ -1117,7 +1147,7 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     BS_TRY(sync_all(ctx));
     for (Workspace &w : ctx->ws) w.in_flight = false;
     ctx->best_dirty = false;
-    if (res->lev_dist_vs_true) std::memset(res->lev_dist_vs_true, 0, (size_t)C * 4);
+    if (res->lev_dist_vs_true && !e.want_lev) std::memset(res->lev_dist_vs_true, 0, (size_t)C * 4);
     if (!e.want_sp && res->path_prob_dist_startpos) std::memset(res->path_prob_dist_startpos, 0, (size_t)C * 4);
     if (status) return fail(ctx, BS_ERR_INVALID, "ks_stat_path_freq: more than %d table rows with a count >= %d in one contig", bs::OVF_CAP, bs::CC_DENSE);
     return BS_OK;

@@ -55,6 +55,7 @@ enum {
 #define BS_WANT_HIST      0x004u /* fill hist: dense per-contig break-k-mer counts (parity/debug) */
 #define BS_WANT_POS       0x008u /* fill pos: leftmost match of every read in every contig (parity/debug) */
 #define BS_WANT_STARTPOS  0x010u /* fill path_prob_dist_startpos (lib/BreakageScorer.cpp:273-274) */
+#define BS_WANT_LEV       0x020u /* fill lev_dist_vs_true: infix edit distance contig vs truth (lib/BreakageScorer.cpp:41-55,339) */
 #define BS_PLACE_SCAN     0x100u /* placement by exhaustive all-pairs scan of the contig tile in shared memory (same results) */
 #define BS_PLACE_TILE     0x800u /* placement by a seed index over the contig tile, reads streamed past it (same results) */
 #define BS_DEVICE_CHARS   0x200u /* read_chars / contig_chars / truth_chars are DEVICE pointers */
@@ -97,7 +98,8 @@ typedef struct {
     double *bp_score_norm_by_len;           /* [C] bp_score / sequence_len      (:302-303) */
     int32_t *kmer_breaks;                   /* [C] total_breaks                 (:298)     */
     int32_t *path_prob_dist_startpos;       /* [C] truth.find(contig) if any read hit else 0 */
-    int32_t *lev_dist_vs_true;              /* [C] NOT computed by this library (edlib, off the path): filled with 0 */
+    int32_t *lev_dist_vs_true;              /* [C] with BS_WANT_LEV: smallest edit distance of the contig to any substring of the truth
+                                             *     (edlib EDLIB_MODE_HW semantics); without it: 0 */
     double *ks_stat_prob_dist;              /* [C] KS(path_prob_dist, truth window probabilities) */
     double *ks_stat_path_freq;              /* [C] KS(count/total over table rows, same y); NaN if no breaks */
     double *path_prob_dist;                 /* flat; contig c at path_prob_dist_off[c], max(L_c-kmer+1,0) values */
@@ -120,9 +122,9 @@ BS_API int bs_ctx_synchronize(bs_ctx *ctx);
 BS_API int64_t bs_ctx_launch_count(const bs_ctx *ctx);
 /* per-stage CUDA-event timing (off by default).  bs_ctx_last_timings blocks on the stream and
  * writes up to n stage times (ms, -1 = stage did not run) of the last scoring call, in the order
- * h2d, pack, place, score, truth_spectrum, prob_dist_ks, ks_path_freq, startpos, d2h; returns
+ * h2d, pack, place, score, truth_spectrum, prob_dist_ks, ks_path_freq, startpos, d2h, lev; returns
  * how many it wrote. */
-#define BS_N_STAGES 9
+#define BS_N_STAGES 10
 BS_API int bs_ctx_enable_timing(bs_ctx *ctx, int on);
 BS_API int bs_ctx_last_timings(bs_ctx *ctx, double *ms, int n);
 /* device-event time (ms) of the placement kernel of the last scoring call, -1 if none */

@@ -166,7 +166,7 @@ Rcpp::List calc_breakscore(
     r.path_prob_dist = pd_flat.data();
     r.path_prob_dist_off = pd_off.data();
     check(s, bs_score(s.ctx, ctg_chars, ctg_off.data(), C, read_chars, read_off.data(), (int64_t)sequencing_reads.size(),
-                      truth_chars, (int64_t)true_solution.size(), kmer, BS_DEFAULT_FLAGS, &r));
+                      truth_chars, (int64_t)true_solution.size(), kmer, BS_DEFAULT_FLAGS | BS_WANT_LEV, &r));
 
     std::vector<std::vector<double>> path_prob_dist((size_t)C);
     for (int64_t c = 0; c < C; c++) path_prob_dist[c].assign(pd_flat.begin() + pd_off[c], pd_flat.begin() + pd_off[c + 1]);

@@ -152,6 +152,8 @@ def assert_same_as_oracle(got, want, check_pos=True, check_hist=True):
     for k in ("ks_stat_prob_dist", "ks_stat_path_freq"):
         if k in got and k in want:
             np.testing.assert_allclose(got[k], want[k], rtol=RTOL, atol=KS_ATOL, equal_nan=True, err_msg=k)
+    if "lev_dist_vs_true" in want:  # only when the caller asked the oracle for it
+        assert np.array_equal(got["lev_dist_vs_true"], want["lev_dist_vs_true"]), ("lev_dist_vs_true", got["lev_dist_vs_true"], want["lev_dist_vs_true"])
     if "path_prob_dist" in got and "path_prob_dist" in want:
         for a, b in zip(got["path_prob_dist"], want["path_prob_dist"]):
             assert np.array_equal(a, b), "path_prob_dist"

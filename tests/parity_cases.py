@@ -39,7 +39,8 @@ def check_segment(scorer, oracle, kmers, prob, seg, kmer=8, flags=FULL, truth_pr
     scorer.set_table(kmers, prob, truth_prob)
     got = scorer.score(seg.contigs, reads, seg.truth, kmer=kmer, flags=flags)
     want = oracle.oracle_calc_breakscore(seg.contigs, reads, seg.truth, kmer, kmers, prob, truth_prob=truth_prob,
-                                         want_pos=bool(flags & B.WANT_POS), want_hist=bool(flags & B.WANT_HIST))
+                                         want_pos=bool(flags & B.WANT_POS), want_hist=bool(flags & B.WANT_HIST),
+                                         want_lev=bool(flags & B.WANT_LEV))
     assert_same_as_oracle(got, want, check_pos=bool(flags & B.WANT_POS), check_hist=bool(flags & B.WANT_HIST))
     return got, want
 

@@ -81,3 +81,35 @@ def test_chunked_pipeline_equals_one_chunk(emul_lib, emul_scorer, kmers, prob, m
         many = sc.score_batch(*args, flags=flags)
     for k in one:
         assert np.array_equal(one[k], many[k], equal_nan=True), k
+
+
+# ---- infix edit distance (lev_dist_vs_true) ---------------------------------------------------
+
+@pytest.mark.parametrize("params", P.SMALL[:4], ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL[:4]])
+def test_edit_distance_small_segments(params, emul_scorer, oracle, kmers, prob):
+    seg = P.make(*params, mut=0.6)
+    P.check_segment(emul_scorer, oracle, kmers, prob, seg, flags=P.FULL | B.WANT_LEV)
+
+
+@pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
+def test_edit_distance_edge_inputs(name, contigs, reads, truth, kmer, emul_scorer, oracle, kmers, prob):
+    from genomeassembler_dev_b200.synth import Segment
+    P.check_segment(emul_scorer, oracle, kmers, prob, Segment(truth, None, contigs), kmer=kmer, reads=reads,
+                    flags=B.DEFAULT_FLAGS | B.WANT_LEV)
+
+
+def test_edit_distance_indels_and_long_contigs(emul_scorer, oracle, kmers, prob):
+    """contigs longer than one warp of pattern blocks (2048 bases), with substitutions, insertions,
+    deletions and unrelated sequence"""
+    from genomeassembler_dev_b200 import synth
+    rng = np.random.default_rng(9)
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, 5200)).tobytes()
+    a = bytearray(truth[100:2700]); a[1300] = ord("A") if a[1300] != ord("A") else ord("C")   # 2600 bases, 1 substitution
+    b = truth[300:1500] + truth[1510:2900]                                                    # 10-base deletion
+    c = truth[2000:3000] + b"ACGTTGCA" + truth[3000:4700]                                     # 8-base insertion, 2708 bases
+    d = synth.codes_to_ascii(synth.random_truth_codes(rng, 300)).tobytes()                    # unrelated
+    e = truth[4000:5200] + b"GGGGGGGGGG"                                                      # overhang at the end of the truth
+    seg = synth.Segment(truth, None, [bytes(a), b, c, d, e, truth[50:2500]])
+    reads = [truth[i:i + 40] for i in range(0, 5000, 97)]
+    got, want = P.check_segment(emul_scorer, oracle, kmers, prob, seg, reads=reads, flags=B.DEFAULT_FLAGS | B.WANT_LEV)
+    assert got["lev_dist_vs_true"][0] == 1 and got["lev_dist_vs_true"][5] == 0

@@ -221,3 +221,31 @@ def test_cfg5_shape_scaled(gpu_scorer, oracle, kmers, prob):
     # a read starting inside a contig and ending inside it is placed there exactly once
     expect = np.array([np.count_nonzero((starts >= a) & (starts + r <= a + b)) for a, b in zip(cstart, clen)])
     assert np.all(chk["kmer_breaks"] >= expect)
+
+
+# ---- infix edit distance (lev_dist_vs_true) ---------------------------------------------------
+
+@pytest.mark.parametrize("params", P.SMALL + P.MEDIUM[:2], ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL + P.MEDIUM[:2]])
+def test_edit_distance_vs_oracle(params, gpu_scorer, oracle, kmers, prob):
+    seg = P.make(*params, mut=0.5)
+    P.check_segment(gpu_scorer, oracle, kmers, prob, seg, flags=P.FULL | B.WANT_LEV)
+
+
+@pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
+def test_edit_distance_edge_inputs(name, contigs, reads, truth, kmer, gpu_scorer, oracle, kmers, prob):
+    P.check_segment(gpu_scorer, oracle, kmers, prob, synth.Segment(truth, None, contigs), kmer=kmer, reads=reads,
+                    flags=B.DEFAULT_FLAGS | B.WANT_LEV)
+
+
+def test_edit_distance_indels_and_long_contigs(gpu_scorer, oracle, kmers, prob):
+    rng = np.random.default_rng(9)
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, 20000)).tobytes()
+    a = bytearray(truth[100:9700]); a[4300] = ord("A") if a[4300] != ord("A") else ord("C")
+    b = truth[300:1500] + truth[1510:8900]
+    c = truth[2000:3000] + b"ACGTTGCA" + truth[3000:14700]
+    d = synth.codes_to_ascii(synth.random_truth_codes(rng, 3000)).tobytes()
+    e = truth[14000:20000] + b"GGGGGGGGGG"
+    seg = synth.Segment(truth, None, [bytes(a), b, c, d, e, truth[50:12500]])
+    reads = [truth[i:i + 100] for i in range(0, 19000, 97)]
+    got, want = P.check_segment(gpu_scorer, oracle, kmers, prob, seg, reads=reads, flags=B.DEFAULT_FLAGS | B.WANT_LEV)
+    assert got["lev_dist_vs_true"].tolist()[:3] == [1, 10, 8] and got["lev_dist_vs_true"][5] == 0
