@@ -809,6 +809,8 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             BS_TRY(ensure(ctx, ctx->d_hbuf, (size_t)nblk * warps_per_block * stride));
             la.hbuf = (int8_t *)ctx->d_hbuf.p; la.hbuf_stride = stride;
         }
+        BS_LAUNCH(bs::k_lev_bound, (unsigned)grid_for(C * 32, kLevThreads, grid_cap), kLevThreads, 0, st, la);
+        ctx->launches++;
         BS_LAUNCH(bs::k_lev_infix, (unsigned)nblk, kLevThreads, 0, st, la);
         ctx->launches++;
     }

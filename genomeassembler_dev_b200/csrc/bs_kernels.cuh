@@ -1566,6 +1566,73 @@ __device__ __forceinline__ uint64_t lev_eq(const uint64_t (&peq)[4], uint64_t in
     return m;
 }
 
+// Cheap exact answers before the full scan.  lev[c] = 0 for exact substrings and empty contigs,
+// the contig length against an empty truth, and 1 when the contig lies on some diagonal of the truth
+// with exactly one substituted base (found through its first or last 32 bases as seeds and an
+// XOR/popcount of the packed words): a contig that is not an exact substring cannot do better than
+// 1.  Everything else is left at -1 for k_lev_infix.
+__global__ void __launch_bounds__(128) k_lev_bound(LevArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < a.n_contigs; c += warps) {
+        const int64_t m = a.ctg_off[c + 1] - a.ctg_off[c];
+        const int64_t seg = a.ctg_seg[c];
+        const int64_t n = a.tr_off[seg + 1] - a.tr_off[seg];
+        int32_t res = -1;
+        if (a.exact[c] >= 0 || m == 0) res = 0;
+        else if (n == 0) res = (int32_t)m;
+        if (res >= 0 || m < 32 || m > n) {
+            if (lane == 0) a.lev[c] = res;
+            continue;
+        }
+        const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
+        const uint64_t *tw = a.tr_words + a.tr_woff[seg];
+        const uint32_t *tm = a.tr_mask + a.tr_woff[seg];
+        const int64_t toff = m - 32;  // the last 32 bases of the contig
+        const bool head_ok = cm[0] == 0;
+        const bool tail_ok = window32(cm[toff >> 5], cm[(toff >> 5) + 1], (uint32_t)(toff & 31)) == 0;
+        const uint64_t head = cw[0];
+        const uint64_t tail = window64(cw[toff >> 5], cw[(toff >> 5) + 1], (uint32_t)(toff & 31));
+        const int64_t nw = (m + 31) >> 5;
+        bool found = false;
+        for (int64_t qb = 0; qb < n - 31 && !found; qb += 32) {
+            const int64_t q = qb + lane;
+            int64_t start = -1;  // contig start on the truth suggested by a seed hit at q
+            if (q < n - 31 && window32(tm[q >> 5], tm[(q >> 5) + 1], (uint32_t)(q & 31)) == 0) {
+                const uint64_t sq = window64(tw[q >> 5], tw[(q >> 5) + 1], (uint32_t)(q & 31));
+                if (head_ok && sq == head && q + m <= n) start = q;
+                else if (tail_ok && sq == tail && q - toff >= 0) start = q - toff;
+            }
+            unsigned hits = __ballot_sync(FULL_MASK, start >= 0);
+            while (hits && !found) {
+                const int src = __ffs((int)hits) - 1;
+                hits &= hits - 1;
+                const int64_t st = __shfl_sync(FULL_MASK, start, src);
+                const int64_t idx = st >> 5;
+                const uint32_t o = (uint32_t)(st & 31);
+                int mism = 0;
+                for (int64_t j0 = 0; j0 < nw && mism <= 1; j0 += 32) {
+                    const int64_t j = j0 + lane;
+                    int mine = 0;
+                    if (j < nw) {
+                        const int rem = (m - 32 * j) < 32 ? (int)(m - 32 * j) : 32;
+                        const uint64_t d = (window64(tw[idx + j], tw[idx + j + 1], o) ^ cw[j]) & keep_bases(rem);
+                        mine = __popcll((d | (d >> 1)) & 0x5555555555555555ull);
+                        // a non-ACGT byte on either side: this diagonal is left to the full scan
+                        if ((window32(tm[idx + j], tm[idx + j + 1], o) | cm[j]) & keep_bits(rem)) mine = 2;
+                    }
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) mine += __shfl_xor_sync(FULL_MASK, mine, sft);
+                    mism += mine;
+                }
+                if (mism == 1) found = true;  // (0 cannot happen: the contig is not an exact substring)
+            }
+        }
+        if (lane == 0) a.lev[c] = found ? 1 : -1;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_lev_infix(LevArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t gwarp = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -1579,14 +1646,7 @@ __global__ void __launch_bounds__(128) k_lev_infix(LevArgs a) {
         const int64_t m = a.ctg_off[c + 1] - a.ctg_off[c];
         const int64_t seg = a.ctg_seg[c];
         const int64_t n = a.tr_off[seg + 1] - a.tr_off[seg];
-        if (a.exact[c] >= 0 || m == 0) {  // an exact substring (or the empty contig): distance 0
-            if (lane == 0) a.lev[c] = 0;
-            continue;
-        }
-        if (n == 0) {  // nothing to align against: every base is an insertion
-            if (lane == 0) a.lev[c] = (int32_t)m;
-            continue;
-        }
+        if (a.lev[c] >= 0) continue;  // settled by k_lev_bound
         const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
         const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
         const uint8_t *cc = a.ctg_chars + a.ctg_off[c];

@@ -37,6 +37,21 @@ def main():
     sc = B.BreakageScorer(0)
     sc.set_table(kmers, prob)
     run(sc, "cfg1: 50 kb, r=100 30x, 16 contigs", synth.make_segment(1234, 50000, 100, 30, 16))
+    run(sc, "cfg1 + edit distance (BS_WANT_LEV)", synth.make_segment(1234, 50000, 100, 30, 16), flags=B.DEFAULT_FLAGS | B.WANT_LEV)
+    b = synth.make_batch(200, seed=1234)
+    class _S:  # 200 cfg-2 segments with the edit distance on, through score_batch directly
+        pass
+    sc.enable_timing(True)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off, b.seg_read_start, b.seg_contig_start)
+    for fl, nm in ((B.DEFAULT_FLAGS, "cfg2 x200 segments"), (B.DEFAULT_FLAGS | B.WANT_LEV, "cfg2 x200 segments + edit distance")):
+        sc.score_batch(*args, flags=fl)
+        t0 = time.perf_counter()
+        res = sc.score_batch(*args, flags=fl)
+        wall = time.perf_counter() - t0
+        print(json.dumps({"shape": nm, "contigs": b.n_contigs, "wall_ms": round(wall * 1e3, 2),
+                          "stage_ms": {k: round(v, 3) for k, v in sc.last_timings().items() if v >= 0},
+                          "lev_hist": np.bincount(np.minimum(res["lev_dist_vs_true"], 3)).tolist()}), flush=True)
+    sc.enable_timing(False)
     for r in (50, 300):
         run(sc, f"cfg3: 50 kb, r={r} 30x, 40 contigs", synth.make_segment(1300 + r, 50000, r, 30, 40))
     run(sc, "cfg3: 50 kb, r=12 40x, 60 contigs (script 00 grid)", synth.make_segment(1312, 50000, 12, 40, 60))
