@@ -1,0 +1,20 @@
+import sys, numpy as np
+import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
+from genomeassembler_dev_b200 import breakscore as B, tables, synth
+import parity_cases as P
+from oracle import loader as O
+kmers=tables.all_kmer_strings(); prob=tables.normalised(tables.load_raw())
+sc=B.BreakageScorer(0,'/tmp/asan/libbreakscore_emul.so')
+import conftest
+n=0
+for mode in (0,B.PLACE_TILE,B.PLACE_SCAN):
+    for params in P.SMALL[:3]:
+        P.check_segment(sc,O,kmers,prob,P.make(*params,mut=0.5),flags=P.FULL|mode|B.WANT_LEV); n+=1
+    for name,contigs,reads,truth,kmer in P.edge_inputs():
+        P.check_segment(sc,O,kmers,prob,synth.Segment(truth,None,contigs),kmer=kmer,reads=reads,flags=P.FULL|mode|B.WANT_LEV); n+=1
+rowid=np.arange(1,len(prob)+1,dtype=np.float64)
+P.check_segment(sc,O,kmers,rowid,P.make(*P.SMALL[0]),flags=P.FULL); n+=1
+b=synth.make_batch(5,seed=3,length=1500,read_len=30,coverage=6,contigs_lo=1,contigs_hi=4)
+sc.set_table(kmers,prob)
+sc.score_batch(b.read_chars,None,b.read_len,b.contig_chars,b.contig_off,b.truth_chars,b.truth_off,b.seg_read_start,b.seg_contig_start,flags=B.DEFAULT_FLAGS|B.WANT_HIST|B.WANT_POS|B.WANT_LEV); n+=1
+print('asan run ok', n, 'cases')
