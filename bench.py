@@ -348,12 +348,12 @@ def b200_main(args):
     e0.record()
     for _ in range(args.steps):
         step_device()
-        for k, v in sc.last_timings().items():  # CUDA events on the launching stream, per stage
-            if v > 0:
-                stage_ms[k] += v
     e1.record()
     torch.cuda.synchronize()
     barrier()
+    for k, v in sc.last_timings().items():  # CUDA events on the launching stream, summed over the K steps
+        if v > 0:
+            stage_ms[k] += v
     ms_total = e0.elapsed_time(e1)
     launches = sc.launch_count - launches0
     clocks = sampler.stop()

@@ -963,12 +963,17 @@ int64_t bs_ctx_launch_count(const bs_ctx *ctx) { return ctx ? ctx->launches : 0;
 
 int bs_ctx_enable_timing(bs_ctx *ctx, int on) {
     if (!ctx) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    sync_all(ctx);
     ctx->timing = on != 0;
+    ctx->spans_used = 0;
     return BS_OK;
 }
 
-// per-stage device time (ms) of the last scoring call, summed over its chunks; order: h2d, pack,
-// place, score, spectrum, prob_dist_ks, ks_path_freq, startpos, d2h.  Returns the number written.
+// per-stage device time (ms) summed over the chunks of every scoring call since timing was enabled
+// or last read (reading resets the sums; no synchronisation is forced between calls, so a caller
+// can time K back-to-back calls and divide); order: h2d, pack, place, score, spectrum,
+// prob_dist_ks, ks_path_freq, startpos, d2h, lev.  Returns the number written.
 int bs_ctx_last_timings(bs_ctx *ctx, double *ms, int n) {
     if (!ctx || !ms) return 0;
     cudaSetDevice(ctx->device);
@@ -983,6 +988,7 @@ int bs_ctx_last_timings(bs_ctx *ctx, double *ms, int n) {
     }
     int k = 0;
     for (; k < n && k < ST_COUNT; k++) ms[k] = (ctx->timing && used[k]) ? acc[k] : -1.0;
+    ctx->spans_used = 0;
     return k;
 }
 
@@ -1093,7 +1099,6 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     if (b->contig_off[C] > 0 && !b->contig_chars) return fail(ctx, BS_ERR_INVALID, "contig_chars is NULL");
     if (b->truth_off[S] > 0 && !b->truth_chars) return fail(ctx, BS_ERR_INVALID, "truth_chars is NULL");
     cudaSetDevice(ctx->device);
-    ctx->spans_used = 0;
 
     CallEnv e;
     e.b = b; e.res = res; e.kmer = kmer; e.flags = flags; e.T = ctx->T;

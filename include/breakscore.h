@@ -120,8 +120,9 @@ BS_API int bs_ctx_set_stream(bs_ctx *ctx, void *cuda_stream);
 BS_API int bs_ctx_synchronize(bs_ctx *ctx);
 /* number of kernel launches issued by this context so far */
 BS_API int64_t bs_ctx_launch_count(const bs_ctx *ctx);
-/* per-stage CUDA-event timing (off by default).  bs_ctx_last_timings blocks on the stream and
- * writes up to n stage times (ms, -1 = stage did not run) of the last scoring call, in the order
+/* per-stage CUDA-event timing (off by default).  bs_ctx_last_timings blocks on the streams and
+ * writes up to n stage times (ms, -1 = stage did not run), summed over every scoring call since
+ * timing was enabled or last read (the read resets the sums), in the order
  * h2d, pack, place, score, truth_spectrum, prob_dist_ks, ks_path_freq, startpos, d2h, lev; returns
  * how many it wrote. */
 #define BS_N_STAGES 10
