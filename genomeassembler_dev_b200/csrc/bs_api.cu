@@ -440,18 +440,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         if (place_smem > ctx->smem_optin) return fail(ctx, BS_ERR_INVALID, "placement tile needs %zu bytes of shared memory", place_smem);
     }
 
-    // one 64-byte record per contig in work order (see bs::WorkItem)
-    std::vector<bs::WorkItem> work((size_t)C);
-    for (int64_t i = 0; i < C; i++) {
-        const int32_t c = order[(size_t)i];
-        const int32_t s = ctg_seg[c];
-        bs::WorkItem &w = work[(size_t)i];
-        w.coff = ctg_off[c]; w.woff = ctg_woff[c]; w.r0 = seg_rs[s]; w.tab_off = tab_off[s];
-        w.contig = c; w.seg = s; w.len = (int32_t)(ctg_off[c + 1] - ctg_off[c]);
-        w.n_reads = (int32_t)std::min<int64_t>(seg_rs[s + 1] - seg_rs[s], 0x7fffffff);
-        w.seed_len = seed_len[s]; w.tab_mask = tab_mask[s]; w.pad0 = 0; w.pad1 = 0;
-    }
-
     std::vector<int64_t> pd_off, pos_off;
     if (e.want_pd) {
         pd_off.resize(C + 1);
@@ -479,7 +467,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     const size_t o_tab_off = mb.add(tab_off.data(), (size_t)S);
     const size_t o_tab_mask = mb.add(tab_mask.data(), (size_t)S);
     const size_t o_order = mb.add(order.data(), order.size());
-    const size_t o_work = mb.add(work.data(), work.size());
     const size_t o_items = mb.add(items.data(), items.size());
     const size_t o_pd_off = e.want_pd ? mb.add(pd_off.data(), (size_t)C + 1) : 0;
     const size_t o_pos_off = e.want_pos ? mb.add(pos_off.data(), (size_t)C + 1) : 0;
@@ -539,7 +526,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     const int64_t *d_tab_off = (const int64_t *)(dm + o_tab_off);
     const int32_t *d_tab_mask = (const int32_t *)(dm + o_tab_mask);
     const int32_t *d_order = (const int32_t *)(dm + o_order);
-    const bs::WorkItem *d_work = (const bs::WorkItem *)(dm + o_work);
+    const int32_t *d_order2 = d_order;
     const bs::PlaceItem *d_items = (const bs::PlaceItem *)(dm + o_items);
     const int64_t *d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
     const int64_t *d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
@@ -655,7 +642,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             }
             ctx->best_dirty = true;  // cleared when the call ends without an error
             bs::PlaceIxArgs pa;
-            pa.work = d_work; pa.n_items = (int32_t)C; pa.work_counter = (int32_t *)ctx->d_counters.p;
+            pa.order = d_order; pa.n_items = (int32_t)C; pa.work_counter = (int32_t *)ctx->d_counters.p;
             pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
             pa.ctg_chars = d_cchars; pa.ctg_seg = d_ctg_seg;
             pa.reads = rs; pa.ix = ix;
@@ -721,7 +708,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kScoreThreads, 0));
         bs::ScoreArgs sa;
         std::memset(&sa, 0, sizeof(sa));
-        sa.work = d_work; sa.work_counter = (int32_t *)ctx->d_counters.p + 2;
+        sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + 2;
         sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_seg = d_ctg_seg;
         sa.w = (const int32_t *)ws.w.p; sa.total = (const int32_t *)ws.total.p;
         sa.tab = (const bs::TabEntry *)ctx->d_tab.p;
@@ -746,7 +733,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         StageTimer tm(ctx, ST_PROBDIST, st);
         const KsCache &k = ctx->ks;
         bs::ProbDistArgs pa;
-        pa.work = d_work; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
+        pa.order = d_order2; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
         pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
         pa.ctg_seg = d_ctg_seg;
         pa.win = (kmer >= 1 && kmer <= bs::MAXK) ? (const bs::WinEntry *)k.win.p : nullptr;

@@ -481,49 +481,10 @@ __global__ void k_place(PlaceArgs a) {
 // upstream lib/BreakageScorer.cpp:241.  Work per contig is O(L_c + hits) instead of O(U * L_c).
 // ------------------------------------------------------------------------------------------
 
-// One unit of work of the persistent per-contig kernels, in work order (long contigs first).
-// Everything a block needs to start on a contig sits in one 64-byte record, and the NEXT record is
-// fetched by thread 0 while the block is still busy with the current one: the atomic on the work
-// counter and the dependent metadata loads leave the critical path.
-struct alignas(16) WorkItem {
-    int64_t coff;      // first char of the contig (chunk-local)
-    int64_t woff;      // first packed word of the contig
-    int64_t r0;        // first read of the contig's segment
-    int64_t tab_off;   // the segment's read-index table
-    int32_t contig;
-    int32_t seg;
-    int32_t len;
-    int32_t n_reads;   // reads of the segment
-    int32_t seed_len;
-    int32_t tab_mask;
-    int32_t pad0, pad1;
-};
-
-struct WorkFetch {
-    WorkItem buf[2];
-    int idx[2];
-};
-// call by all threads before the loop; afterwards wf.idx[0] / wf.buf[0] hold the first item
-__device__ __forceinline__ void work_first(WorkFetch &wf, const WorkItem *work, int32_t *counter, int n_items) {
-    if (threadIdx.x == 0) {
-        const int i = atomicAdd(counter, 1);
-        wf.idx[0] = i;
-        if (i < n_items) wf.buf[0] = work[i];
-    }
-    __syncthreads();
-}
-// thread 0 only, right after the block has read item `cur`: start fetching the next one into the
-// other slot.  It becomes visible to the block at the __syncthreads that ends the iteration.
-__device__ __forceinline__ void work_prefetch(WorkFetch &wf, int cur, const WorkItem *work, int32_t *counter, int n_items) {
-    const int i = atomicAdd(counter, 1);
-    wf.idx[cur ^ 1] = i;
-    if (i < n_items) wf.buf[cur ^ 1] = work[i];
-}
-
 constexpr uint32_t POS_INF = 0x7f7f7f7fu;  // memset-able "no position yet"
 
 struct PlaceIxArgs {
-    const WorkItem *work;  // [n_items] contigs in work order
+    const int32_t *order;  // [n_items] contig ids, longest first
     int32_t n_items;
     int32_t *work_counter;  // zero on entry
     const int64_t *ctg_off;
@@ -589,29 +550,27 @@ BS_HD size_t place_index_smem_bytes(int hit_cap) { return (size_t)hit_cap * 4 + 
 __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
     uint32_t *s_hits = (uint32_t *)bs_dyn_smem();
     uint2 *s_cand = (uint2 *)(s_hits + a.hit_cap);  // (read id, contig position) with an equal seed
-    __shared__ int s_nhit, s_placed, s_ncand[2];
-    __shared__ WorkFetch s_wf;
+    __shared__ int s_item, s_nhit, s_placed, s_ncand[2];
     const int tid = threadIdx.x, nthr = blockDim.x;
     uint32_t *best = a.best + (int64_t)blockIdx.x * a.best_stride;
-    work_first(s_wf, a.work, a.work_counter, a.n_items);
-    for (int cur = 0;; cur ^= 1) {
-        if (s_wf.idx[cur] >= a.n_items) break;
-        const WorkItem wi = s_wf.buf[cur];
-        if (tid == 0) { s_nhit = 0; s_placed = 0; s_ncand[0] = 0; s_ncand[1] = 0; }
+    for (;;) {
         __syncthreads();
-        if (tid == 0) work_prefetch(s_wf, cur, a.work, a.work_counter, a.n_items);
-        const int c = wi.contig;
-        const int s = wi.seg;
-        const int64_t coff = wi.coff;
-        const int64_t L = wi.len;
-        const uint64_t *gw = a.ctg_words + wi.woff;
-        const uint32_t *gm = a.ctg_mask + wi.woff;
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; s_ncand[0] = 0; s_ncand[1] = 0; }
+        __syncthreads();
+        const int item = s_item;
+        if (item >= a.n_items) break;
+        const int c = a.order[item];
+        const int s = a.ctg_seg[c];
+        const int64_t coff = a.ctg_off[c];
+        const int64_t L = a.ctg_off[c + 1] - coff;
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
         const uint8_t *cc = a.ctg_chars + coff;
-        const int64_t r0 = wi.r0;
-        const int64_t n_seg_reads = wi.n_reads;
-        const int S = wi.seed_len;
-        const uint32_t *head = a.ix.head + wi.tab_off;
-        const uint32_t hmask = (uint32_t)wi.tab_mask;
+        const int64_t r0 = a.ix.seg_read_start[s];
+        const int64_t n_seg_reads = a.ix.seg_read_start[s + 1] - r0;
+        const int S = a.ix.seed_len[s];
+        const uint32_t *head = a.ix.head + a.ix.tab_off[s];
+        const uint32_t hmask = (uint32_t)a.ix.tab_mask[s];
         const uint64_t keepS = keep_bases(S);
         const uint32_t keepSm = keep_bits(S);
 
@@ -715,7 +674,6 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
         if (placed) atomicAdd(&s_placed, placed);
         __syncthreads();
         if (tid == 0) a.total[c] = s_placed;
-        __syncthreads();  // the next item (prefetched by thread 0) and the reset of the counters
     }
 }
 
@@ -780,7 +738,7 @@ constexpr int CC_DENSE = 4096;  // counts below this are tallied in a dense shar
 constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
 
 struct ScoreArgs {
-    const WorkItem *work;   // [C] contigs in work order
+    const int32_t *order;   // [C] contig ids, longest first
     int32_t *work_counter;  // zero on entry
     const int64_t *ctg_off;
     const int64_t *ctg_woff;
@@ -843,27 +801,23 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
 __global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
     __shared__ double s_w[32];
     __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
-    __shared__ int s_novf, s_maxc, s_nz;
-    __shared__ WorkFetch s_wf;
+    __shared__ int s_item, s_novf, s_maxc, s_nz;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const bool want_ks = a.ks_b != nullptr;
     int32_t *scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
     int32_t *ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     if (want_ks) for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
-    work_first(s_wf, a.work, a.work_counter, (int)a.n_contigs);
-    for (int cur = 0;; cur ^= 1) {
-        __syncthreads();  // previous contig finished: the prefetched item is visible
-        if (s_wf.idx[cur] >= a.n_contigs) break;
-        const WorkItem wi = s_wf.buf[cur];
-        if (tid == 0) { s_novf = 0; s_maxc = 0; s_nz = 0; }
+    for (;;) {
         __syncthreads();
-        if (tid == 0) work_prefetch(s_wf, cur, a.work, a.work_counter, (int)a.n_contigs);
-        const int64_t c = wi.contig;
-        const int64_t coff = wi.coff;
-        const int64_t L = wi.len;
-        const uint64_t *gw = a.ctg_words + wi.woff;
-        const uint32_t *gm = a.ctg_mask + wi.woff;
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; }
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
+        const int64_t coff = a.ctg_off[c];
+        const int64_t L = a.ctg_off[c + 1] - coff;
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
         const int32_t *w = a.w + coff + c;
         const int32_t total = a.total[c];
         const int64_t np = L > 0 ? L : 1;
@@ -951,7 +905,7 @@ __global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
         __syncthreads();
         // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them
         if (tid == 0) {
-            const int32_t *ycum = a.ycum + (int64_t)wi.seg * a.R_y;
+            const int32_t *ycum = a.ycum + (int64_t)a.ctg_seg[c] * a.R_y;
             const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
             const int novf = s_novf < OVF_CAP ? s_novf : OVF_CAP;
             double d = 0.0;
@@ -1168,7 +1122,7 @@ struct alignas(16) WinEntry {
 };
 
 struct ProbDistArgs {
-    const WorkItem *work;     // [C] contigs in work order
+    const int32_t *order;     // [C] contig ids, longest first
     int32_t *work_counter;    // zero on entry
     const int64_t *ctg_off;
     const int64_t *ctg_woff;
@@ -1210,7 +1164,7 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     __shared__ int64_t s_wsum[32];
     __shared__ int64_t s_wmax[32];
-    __shared__ WorkFetch s_wf;
+    __shared__ int s_item;
     // dynamic shared memory (or the global scratch row): histogram words, then the range bitmaps
     uint32_t *s_hist = IN_SMEM ? (uint32_t *)bs_dyn_smem() : a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges);
     uint32_t *s_bm = s_hist + a.hist_words;
@@ -1220,17 +1174,15 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
     if (want_ks) {
         for (int i = tid; i < a.hist_words + a.n_ranges; i += nthr) s_hist[i] = 0;
     }
-    work_first(s_wf, a.work, a.work_counter, (int)a.n_contigs);
-    for (int cur = 0;; cur ^= 1) {
-        __syncthreads();  // previous contig finished: the prefetched item is visible
-        if (s_wf.idx[cur] >= a.n_contigs) break;
-        const WorkItem wi = s_wf.buf[cur];
+    for (;;) {
         __syncthreads();
-        if (tid == 0) work_prefetch(s_wf, cur, a.work, a.work_counter, (int)a.n_contigs);
-        const int64_t c = wi.contig;
-        const int64_t L = wi.len;
-        const uint64_t *gw = a.ctg_words + wi.woff;
-        const uint32_t *gm = a.ctg_mask + wi.woff;
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
+        const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
         int64_t nwin = L - a.kmer + 1;
         if (nwin < 0) nwin = 0;
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
@@ -1273,7 +1225,7 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         __syncthreads();
         // ---- D = sup |F_x - F_y| over the pooled distinct values, evaluated at every x value that
         // is present: just below it (F_x of the previous step vs #{y < v}) and at it ----
-        const int64_t seg = wi.seg;
+        const int64_t seg = a.ctg_seg[c];
         const int32_t *ycum = a.ycum + seg * a.R_y;
         const LeLt *yx = a.yx + seg * a.R_x;
         const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
