@@ -198,6 +198,31 @@ class ClockSampler:
 # the B200 arm
 # ------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank (and so first-touch its pinned staging buffers) on the CPUs NVML reports as
+    local to its GPU: with several ranks per box the H2D copies otherwise cross the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = index
+        if vis:
+            try:
+                idx = int(vis.split(",")[index])
+            except ValueError:
+                pass
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        return None
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -250,6 +275,7 @@ def b200_main(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback for the scorer")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -439,7 +465,8 @@ def b200_main(args):
             "config": {"workload": workload_name(args.segments), "segments_per_gpu": args.segments,
                        "reads_per_gpu": N, "contigs_per_gpu": Cn, "outputs": "scores+kmer_breaks+startpos+path_prob_dist+KS",
                        "l2": "inputs per step (%.0f MB ASCII) exceed the 126 MB L2; no flush" % (h2d / 1e6),
-                       "parallelism": f"segments sharded over {world} GPU(s), NCCL gather of score records"},
+                       "parallelism": f"segments sharded over {world} GPU(s), NCCL gather of score records",
+                       "cpu_affinity": affinity},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "matches_device_resident_run": same,
                     "stage_ms_untimed_extra_step": e2e_stage_ms},
