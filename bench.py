@@ -287,7 +287,11 @@ def b200_main(args):
     prob = tables.normalised(tables.load_raw())
     sc = B.BreakageScorer(local)
     sc.set_table(kmers, prob)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: the library launches on it, torch's events and NCCL calls are
+    # ordered on it too (handle 0, the legacy default stream, would mean "the context's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     sc.set_stream(stream.cuda_stream)
     flags = B.DEFAULT_FLAGS
     Cn, N, S = batch.n_contigs, batch.n_reads, batch.n_segments
