@@ -629,7 +629,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         StageTimer tm(ctx, ST_PLACE, st);
         if (N > 0 && C > 0 && !tile_mode) {
             // per-block scratch row of leftmost positions, all POS_INF between launches
-            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap)));
+            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads)));
             const int64_t stride = (max_seg_reads + 31) / 32 * 32;
             const int64_t budget = (int64_t)8 << 30;
             nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * 4, 1)));
@@ -650,8 +650,8 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
             pa.pos = o_pos; pa.pos_off = d_pos_off;
             pa.hit_cap = kHitCap;
-            BS_CUDA(cudaFuncSetAttribute(bs::k_place_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::place_index_smem_bytes(kHitCap)));
-            BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap), st, pa);
+            BS_CUDA(cudaFuncSetAttribute(bs::k_place_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads)));
+            BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads), st, pa);
             ctx->launches++;
         } else if (N > 0 && !items.empty()) {
             bs::PlaceArgs pa;

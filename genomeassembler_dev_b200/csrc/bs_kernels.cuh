@@ -543,19 +543,21 @@ __device__ __forceinline__ bool verify_at(const PlaceIxArgs &a, const uint64_t *
     return true;
 }
 
-constexpr int PLACE_CAND_CAP = 2048;  // seed hits of one block iteration awaiting verification
+constexpr int PLACE_CAND_CAP = 256;  // seed hits of one WARP iteration (128 positions) awaiting verification
 
-BS_HD size_t place_index_smem_bytes(int hit_cap) { return (size_t)hit_cap * 4 + (size_t)PLACE_CAND_CAP * 8; }
+BS_HD size_t place_index_smem_bytes(int hit_cap, int nthr) { return (size_t)hit_cap * 4 + (size_t)(nthr / 32) * PLACE_CAND_CAP * 8; }
 
 __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
     uint32_t *s_hits = (uint32_t *)bs_dyn_smem();
-    uint2 *s_cand = (uint2 *)(s_hits + a.hit_cap);  // (read id, contig position) with an equal seed
-    __shared__ int s_item, s_nhit, s_placed, s_ncand[2];
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    __shared__ int s_item, s_nhit, s_placed, s_ncand[32];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    // every warp queues and verifies its own candidates: no block barrier inside the position loop
+    uint2 *s_cand = (uint2 *)(s_hits + a.hit_cap) + warp * PLACE_CAND_CAP;  // (read id, contig position) with an equal seed tag
     uint32_t *best = a.best + (int64_t)blockIdx.x * a.best_stride;
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; s_ncand[0] = 0; s_ncand[1] = 0; }
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; }
+        if (lane == 0) s_ncand[warp] = 0;
         __syncthreads();
         const int item = s_item;
         if (item >= a.n_items) break;
@@ -589,10 +591,9 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
 
         if (n_seg_reads > 0) {
             // ---- every contig position against the index.  Phase 1 (sparse, cheap): four positions
-            // per thread in flight, bucket head -> chain -> seed word; equal seeds are queued.
-            // Phase 2 (dense): one queued candidate per thread is verified on the packed words. ----
-            int it = 0;
-            for (int64_t p0 = 0; p0 + S <= L; p0 += 4 * (int64_t)nthr, it ^= 1) {
+            // per thread in flight, bucket head -> chain entry; equal seed tags are queued per warp.
+            // Phase 2 (dense): the warp's lanes verify one queued candidate each on the packed words. ----
+            for (int64_t p0 = 0; p0 + S <= L; p0 += 4 * (int64_t)nthr) {
                 // a thread takes four CONSECUTIVE positions (never straddling a word boundary)
                 const int64_t pb = p0 + 4 * (int64_t)tid;
                 uint32_t q4[4];
@@ -622,19 +623,20 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
                         const uint2 e = a.ix.next[n];
                         q = e.x;
                         if (e.y != tag) continue;
-                        const int slot = atomicAdd(&s_ncand[it], 1);
+                        const int slot = atomicAdd(&s_ncand[warp], 1);
                         if (slot < PLACE_CAND_CAP) s_cand[slot] = make_uint2((uint32_t)n, (uint32_t)p);
                         else verify_and_record(n, p);  // queue full (long chains): verify in place
                     }
                 }
-                __syncthreads();
-                const int nc = s_ncand[it] < PLACE_CAND_CAP ? s_ncand[it] : PLACE_CAND_CAP;
-                if (tid == 0) s_ncand[it ^ 1] = 0;
-                for (int i = tid; i < nc; i += nthr) {
+                __syncwarp();
+                const int nc = s_ncand[warp] < PLACE_CAND_CAP ? s_ncand[warp] : PLACE_CAND_CAP;
+                for (int i = lane; i < nc; i += 32) {
                     const uint2 cd = s_cand[i];
                     verify_and_record((int64_t)cd.x, (int64_t)cd.y);
                 }
-                __syncthreads();
+                __syncwarp();
+                if (lane == 0) s_ncand[warp] = 0;
+                __syncwarp();
             }
             // ---- reads outside the index: text comparison, one read per thread ----
             int i = 0;
@@ -1186,6 +1188,10 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         int64_t nwin = L - a.kmer + 1;
         if (nwin < 0) nwin = 0;
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
+        // truth side of this contig's segment, loaded early so that the latency hides behind the windows
+        const int64_t seg = a.ctg_seg[c];
+        const LeLt *yx = want_ks ? a.yx + seg * a.R_x : nullptr;
+        const int64_t n_y = (want_ks && a.R_y > 0) ? a.ycum[seg * a.R_y + a.R_y - 1] : 0;
         // ---- windows: table value out, rank histogram in.  A thread takes four CONSECUTIVE
         // positions (they never straddle a 32-base word boundary), so the contig words are
         // loaded once per four windows; the four table gathers are in flight together ----
@@ -1225,10 +1231,6 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
         __syncthreads();
         // ---- D = sup |F_x - F_y| over the pooled distinct values, evaluated at every x value that
         // is present: just below it (F_x of the previous step vs #{y < v}) and at it ----
-        const int64_t seg = a.ctg_seg[c];
-        const int32_t *ycum = a.ycum + seg * a.R_y;
-        const LeLt *yx = a.yx + seg * a.R_x;
-        const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
         const bool defined = nwin > 0 && n_y > 0;
         // |F_x - F_y| = |run * n_y - ycount * nwin| / (nwin * n_y): the numerator is maximised in exact
         // 64-bit integers (both factors are below 2^31), one division at the end
@@ -1258,20 +1260,41 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                 if (w < warp) run += s_wsum[w];
                 carry += s_wsum[w];
             }
-            for (uint32_t mm = m; mm; mm &= mm - 1) {
-                const int k = __ffs((int)mm) - 1;
-                const uint32_t w = s_hist[w0 + k];
-                s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
+            // two non-empty words (up to four present ranks) per step: their yx gathers are issued
+            // together, then the statistic is advanced in rank order
+            for (uint32_t mm = m; mm;) {
+                int ii[4];
+                uint32_t cc[4];
+                int ne = 0;
 #pragma unroll
-                for (int h = 0; h < (PACKED ? 2 : 1); h++) {
-                    const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
-                    if (cnt == 0 || !defined) continue;
-                    const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
-                    const LeLt q = yx[i];  // one 8-byte gather
-                    const int64_t lt = q.lt, le = q.le;
-                    int64_t d1 = run * n_y - lt * nwin;
-                    run += cnt;
-                    int64_t d2 = run * n_y - le * nwin;
+                for (int rep = 0; rep < 2; rep++) {
+                    if (!mm) break;
+                    const int k = __ffs((int)mm) - 1;
+                    mm &= mm - 1;
+                    const uint32_t w = s_hist[w0 + k];
+                    s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
+#pragma unroll
+                    for (int h = 0; h < (PACKED ? 2 : 1); h++) {
+                        const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
+                        ii[2 * rep + h] = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
+                        cc[2 * rep + h] = cnt;
+                    }
+                    if (!PACKED) cc[2 * rep + 1] = 0;
+                    ne = 2 * rep + 2;
+                }
+                if (!defined) continue;
+                LeLt q[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    q[e].le = q[e].lt = 0;
+                    if (e < ne && cc[e]) q[e] = yx[ii[e]];  // 8-byte gathers, independent of one another
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (e >= ne || cc[e] == 0) continue;
+                    int64_t d1 = run * n_y - (int64_t)q[e].lt * nwin;
+                    run += cc[e];
+                    int64_t d2 = run * n_y - (int64_t)q[e].le * nwin;
                     if (d1 < 0) d1 = -d1;
                     if (d2 < 0) d2 = -d2;
                     if (d1 > best) best = d1;
