@@ -1260,41 +1260,20 @@ __global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
                 if (w < warp) run += s_wsum[w];
                 carry += s_wsum[w];
             }
-            // two non-empty words (up to four present ranks) per step: their yx gathers are issued
-            // together, then the statistic is advanced in rank order
-            for (uint32_t mm = m; mm;) {
-                int ii[4];
-                uint32_t cc[4];
-                int ne = 0;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const int k = __ffs((int)mm) - 1;
+                const uint32_t w = s_hist[w0 + k];
+                s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
 #pragma unroll
-                for (int rep = 0; rep < 2; rep++) {
-                    if (!mm) break;
-                    const int k = __ffs((int)mm) - 1;
-                    mm &= mm - 1;
-                    const uint32_t w = s_hist[w0 + k];
-                    s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
-#pragma unroll
-                    for (int h = 0; h < (PACKED ? 2 : 1); h++) {
-                        const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
-                        ii[2 * rep + h] = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
-                        cc[2 * rep + h] = cnt;
-                    }
-                    if (!PACKED) cc[2 * rep + 1] = 0;
-                    ne = 2 * rep + 2;
-                }
-                if (!defined) continue;
-                LeLt q[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    q[e].le = q[e].lt = 0;
-                    if (e < ne && cc[e]) q[e] = yx[ii[e]];  // 8-byte gathers, independent of one another
-                }
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    if (e >= ne || cc[e] == 0) continue;
-                    int64_t d1 = run * n_y - (int64_t)q[e].lt * nwin;
-                    run += cc[e];
-                    int64_t d2 = run * n_y - (int64_t)q[e].le * nwin;
+                for (int h = 0; h < (PACKED ? 2 : 1); h++) {
+                    const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
+                    if (cnt == 0 || !defined) continue;
+                    const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
+                    const LeLt q = yx[i];  // one 8-byte gather
+                    const int64_t lt = q.lt, le = q.le;
+                    int64_t d1 = run * n_y - lt * nwin;
+                    run += cnt;
+                    int64_t d2 = run * n_y - le * nwin;
                     if (d1 < 0) d1 = -d1;
                     if (d2 < 0) d2 = -d2;
                     if (d1 > best) best = d1;
