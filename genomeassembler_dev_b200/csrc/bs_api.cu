@@ -34,6 +34,7 @@ constexpr int kScoreThreads = 64;
 constexpr int kStartposThreads = 64;
 constexpr int kLevThreads = 64;
 constexpr int kKsThreads = 64;
+constexpr int kSpectrumThreads = 64;
 constexpr int kPackThreads = 64;
 constexpr int kPlaceIxThreads = 64;
 #else
@@ -41,7 +42,8 @@ constexpr int kPlaceThreads = 256;
 constexpr int kScoreThreads = 256;
 constexpr int kStartposThreads = 256;
 constexpr int kLevThreads = 128;
-constexpr int kKsThreads = 512;
+constexpr int kKsThreads = 768;     // one sweep round covers the 515 ranges of the real table's rank histogram
+constexpr int kSpectrumThreads = 512;
 constexpr int kPackThreads = 256;
 constexpr int kPlaceIxThreads = 256;
 #endif
@@ -684,7 +686,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         if (k.R_y > 0 && kmer <= bs::MAXK && max_tr - kmer + 1 < 65536 && sp_smem + 1024 <= ctx->smem_optin) {
             // one block per segment, histogram and prefix sum in shared memory
             BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
-            BS_LAUNCH(bs::k_truth_spectrum_smem, (unsigned)S, kKsThreads, sp_smem, st, sp);
+            BS_LAUNCH(bs::k_truth_spectrum_smem, (unsigned)S, kSpectrumThreads, sp_smem, st, sp);
             ctx->launches++;
         } else {
             BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, st));

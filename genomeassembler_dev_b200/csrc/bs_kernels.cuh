@@ -1161,7 +1161,7 @@ BS_HD int hist_phys_words(int R_x, bool packed) {
 BS_HD int hist_ranges(int R_x, bool packed) { return (hist_logical_words(R_x, packed) + 31) / 32; }
 
 template <bool PACKED, bool IN_SMEM>
-__global__ void __launch_bounds__(512, 3) k_prob_dist_ks(ProbDistArgs a) {
+__global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     __shared__ int64_t s_wsum[32];
