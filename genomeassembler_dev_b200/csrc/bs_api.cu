@@ -77,7 +77,7 @@ struct Workspace {
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
     DevBuf w, total, ycnt, yx, head, next, odd_head, spbest, exact;
     DevBuf out_i32, out_f64, pd, hist, pos;
-    cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr, ev_seqs = nullptr, ev_spec = nullptr, ev_aux = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
 };
 
@@ -103,8 +103,6 @@ struct bs_ctx {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_stream = nullptr;  // H2D
     cudaStream_t out_stream = nullptr;   // D2H
-    cudaStream_t aux_stream = nullptr;   // truth spectrum + prob_dist/KS-A: independent of the reads, runs beside placement
-    int ks_blocks_per_sm = 0, place_blocks_per_sm = 0;  // 0: what fits; tuning knobs (BS_KS_BLOCKS_PER_SM, BS_PLACE_BLOCKS_PER_SM)
     char err[512] = "";
     int64_t launches = 0;
     int64_t chunk_bytes_host = (int64_t)96 << 20;    // ASCII bytes per chunk when inputs come from the host
@@ -224,7 +222,6 @@ int blocks_per_sm(K kernel, int threads, size_t smem) {
 
 int sync_all(bs_ctx *ctx) {
     BS_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-    BS_CUDA(cudaStreamSynchronize(ctx->aux_stream));
     BS_CUDA(cudaStreamSynchronize(ctx->stream));
     BS_CUDA(cudaStreamSynchronize(ctx->out_stream));
     return BS_OK;
@@ -607,7 +604,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         ix.head = (uint32_t *)ws.head.p; ix.next = (uint2 *)ws.next.p; ix.odd_head = (uint32_t *)ws.odd_head.p;
         ix.tab_off = d_tab_off; ix.tab_mask = d_tab_mask; ix.seed_len = d_seed; ix.seg_read_start = d_seg_rs; ix.n_seg = (int32_t)S;
     }
-    cudaStream_t ax = ctx->aux_stream;
     {
         StageTimer tm(ctx, ST_PACK, st);
         BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
@@ -616,88 +612,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             BS_LAUNCH(bs::k_pack_seqs, grid_for(ts.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, ts);
             ctx->launches++;
         }
-    }
-    // ---- side stream: everything that needs only the packed contigs and truths (truth spectrum,
-    // path_prob_dist, KS-A) runs beside read packing and placement ----
-    BS_CUDA(cudaEventRecord(ws.ev_seqs, st));
-    BS_CUDA(cudaStreamWaitEvent(ax, ws.ev_seqs, 0));
-    if (e.want_ks) {
-        const KsCache &k = ctx->ks;
-        const int R_y = std::max(k.R_y, 1);
-        BS_TRY(ensure(ctx, ws.ycnt, (size_t)S * R_y * 4));
-        if (ks_a) BS_TRY(ensure(ctx, ws.yx, (size_t)S * k.R_x * sizeof(bs::LeLt)));
-        StageTimer tm(ctx, ST_SPECTRUM, ax);
-        const size_t sp_smem = (size_t)((k.R_y + 1) / 2) * 4;
-        bs::SpectrumArgs sp;
-        sp.tr_off = d_tr_off; sp.tr_woff = d_tr_woff; sp.tr_words = ts.words; sp.tr_mask = ts.mask;
-        sp.rank_y = (const int32_t *)k.rank_y.p; sp.ycnt = (int32_t *)ws.ycnt.p;
-        sp.R_y = R_y; sp.kmer = kmer; sp.blocks_per_seg = 1;
-        sp.lelt = ks_a ? (const bs::LeLt *)k.lelt.p : nullptr; sp.yx = ks_a ? (bs::LeLt *)ws.yx.p : nullptr; sp.R_x = k.R_x;
-        if (k.R_y > 0 && kmer <= bs::MAXK && max_tr - kmer + 1 < 65536 && sp_smem + 1024 <= ctx->smem_optin) {
-            // one block per segment, histogram and prefix sum in shared memory
-            BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
-            BS_LAUNCH(bs::k_truth_spectrum_smem, (unsigned)S, kSpectrumThreads, sp_smem, ax, sp);
-            ctx->launches++;
-        } else {
-            BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, ax));
-            if (k.R_y > 0) {
-                sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(64, (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
-                BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, ax, sp);
-                ctx->launches++;
-                BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, ax, (int32_t *)ws.ycnt.p, R_y);
-                ctx->launches++;
-            }
-            if (ks_a) {
-                BS_LAUNCH(bs::k_yx_gather, grid_for(S * (int64_t)k.R_x, kScoreThreads, grid_cap), kScoreThreads, 0, ax, sp, S);
-                ctx->launches++;
-            }
-        }
-    }
-    BS_CUDA(cudaEventRecord(ws.ev_spec, ax));
-    if (e.want_pd || ks_a) {
-        StageTimer tm(ctx, ST_PROBDIST, ax);
-        const KsCache &k = ctx->ks;
-        bs::ProbDistArgs pa;
-        pa.order = d_order2; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
-        pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
-        pa.ctg_seg = d_ctg_seg;
-        pa.win = (kmer >= 1 && kmer <= bs::MAXK) ? (const bs::WinEntry *)k.win.p : nullptr;
-        pa.yx = ks_a ? (const bs::LeLt *)ws.yx.p : nullptr;
-        pa.ycum = ks_a ? (const int32_t *)ws.ycnt.p : nullptr;
-        pa.R_x = k.R_x; pa.R_y = k.R_y; pa.rank_zero = k.rank_zero;
-        pa.kmer = kmer; pa.n_contigs = C;
-        pa.prob_dist = o_pd; pa.pd_off = d_pd_off; pa.ks = ks_a ? o_ksa : nullptr;
-        // rank histogram in shared memory: 16-bit counters (two per word) when no contig has 65 536
-        // windows -- real table: 32 897 ranks = 66 KB, three blocks per SM -- else 32-bit counters,
-        // else (all-distinct tables with long contigs) a per-block global scratch that stays in L2
-        const bool packed = max_ctg - kmer + 1 < 65536;
-        pa.hist_words = ks_a ? bs::hist_phys_words(k.R_x, packed) : 0;
-        pa.n_ranges = ks_a ? bs::hist_ranges(k.R_x, packed) : 0;
-        const size_t hist_bytes = (size_t)(pa.hist_words + pa.n_ranges) * 4;
-        const bool in_smem = hist_bytes + 2048 <= ctx->smem_optin;
-        const size_t smem = in_smem ? hist_bytes : 0;
-        int per_sm = std::max<int>(1, std::min<int>(2048 / kKsThreads, (int)((ctx->smem_optin + 1024) / (smem + 1024))));
-        if (ctx->ks_blocks_per_sm > 0) per_sm = std::min(per_sm, ctx->ks_blocks_per_sm);
-        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm);
-        pa.rank_scratch = nullptr;
-        if (ks_a && !in_smem) {
-            BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * hist_bytes));
-            pa.rank_scratch = (uint32_t *)ctx->d_rank_scratch.p;
-        }
-        auto launch = [&](auto kern) -> int {
-            BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            BS_LAUNCH(kern, (unsigned)nblk, kKsThreads, smem, ax, pa);
-            return BS_OK;
-        };
-        if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true>));
-        else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false>));
-        else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true>));
-        else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
-        ctx->launches++;
-    }
-    BS_CUDA(cudaEventRecord(ws.ev_aux, ax));
-    {
-        StageTimer tm(ctx, ST_PACK, st);
         if (N > 0) {
             if (!tile_mode) {
                 BS_CUDA(cudaMemsetAsync(ws.head.p, 0, (size_t)head_total * 4, st));
@@ -717,9 +631,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         StageTimer tm(ctx, ST_PLACE, st);
         if (N > 0 && C > 0 && !tile_mode) {
             // per-block scratch row of leftmost positions, all POS_INF between launches
-            int place_per_sm = blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads));
-            if (ctx->place_blocks_per_sm > 0) place_per_sm = std::min(place_per_sm, ctx->place_blocks_per_sm);
-            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * place_per_sm);
+            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads)));
             const int64_t stride = (max_seg_reads + 31) / 32 * 32;
             const int64_t budget = (int64_t)8 << 30;
             nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * 4, 1)));
@@ -759,7 +671,38 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             ctx->launches++;
         }
     }
-    BS_CUDA(cudaStreamWaitEvent(st, ws.ev_spec, 0));  // KS-B reads the truth's cumulative counts
+    if (e.want_ks) {
+        const KsCache &k = ctx->ks;
+        const int R_y = std::max(k.R_y, 1);
+        BS_TRY(ensure(ctx, ws.ycnt, (size_t)S * R_y * 4));
+        if (ks_a) BS_TRY(ensure(ctx, ws.yx, (size_t)S * k.R_x * sizeof(bs::LeLt)));
+        StageTimer tm(ctx, ST_SPECTRUM, st);
+        const size_t sp_smem = (size_t)((k.R_y + 1) / 2) * 4;
+        bs::SpectrumArgs sp;
+        sp.tr_off = d_tr_off; sp.tr_woff = d_tr_woff; sp.tr_words = ts.words; sp.tr_mask = ts.mask;
+        sp.rank_y = (const int32_t *)k.rank_y.p; sp.ycnt = (int32_t *)ws.ycnt.p;
+        sp.R_y = R_y; sp.kmer = kmer; sp.blocks_per_seg = 1;
+        sp.lelt = ks_a ? (const bs::LeLt *)k.lelt.p : nullptr; sp.yx = ks_a ? (bs::LeLt *)ws.yx.p : nullptr; sp.R_x = k.R_x;
+        if (k.R_y > 0 && kmer <= bs::MAXK && max_tr - kmer + 1 < 65536 && sp_smem + 1024 <= ctx->smem_optin) {
+            // one block per segment, histogram and prefix sum in shared memory
+            BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+            BS_LAUNCH(bs::k_truth_spectrum_smem, (unsigned)S, kSpectrumThreads, sp_smem, st, sp);
+            ctx->launches++;
+        } else {
+            BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, st));
+            if (k.R_y > 0) {
+                sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(64, (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
+                BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, st, sp);
+                ctx->launches++;
+                BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, st, (int32_t *)ws.ycnt.p, R_y);
+                ctx->launches++;
+            }
+            if (ks_a) {
+                BS_LAUNCH(bs::k_yx_gather, grid_for(S * (int64_t)k.R_x, kScoreThreads, grid_cap), kScoreThreads, 0, st, sp, S);
+                ctx->launches++;
+            }
+        }
+    }
     {
         // scores (+ histogram, + KS of the normalised break histogram); after the truth spectrum
         StageTimer tm(ctx, ST_SCORE, st);
@@ -786,6 +729,46 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             sa.scratch = (int32_t *)ctx->d_scratch.p; sa.ovf_cnt = (int32_t *)ctx->d_ovf.p; sa.status = (int32_t *)ctx->d_status.p;
         }
         BS_LAUNCH(bs::k_break_score, (unsigned)nblk, kScoreThreads, 0, st, sa);
+        ctx->launches++;
+    }
+    if (e.want_pd || ks_a) {
+        StageTimer tm(ctx, ST_PROBDIST, st);
+        const KsCache &k = ctx->ks;
+        bs::ProbDistArgs pa;
+        pa.order = d_order2; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
+        pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
+        pa.ctg_seg = d_ctg_seg;
+        pa.win = (kmer >= 1 && kmer <= bs::MAXK) ? (const bs::WinEntry *)k.win.p : nullptr;
+        pa.yx = ks_a ? (const bs::LeLt *)ws.yx.p : nullptr;
+        pa.ycum = ks_a ? (const int32_t *)ws.ycnt.p : nullptr;
+        pa.R_x = k.R_x; pa.R_y = k.R_y; pa.rank_zero = k.rank_zero;
+        pa.kmer = kmer; pa.n_contigs = C;
+        pa.prob_dist = o_pd; pa.pd_off = d_pd_off; pa.ks = ks_a ? o_ksa : nullptr;
+        // rank histogram in shared memory: 16-bit counters (two per word) when no contig has 65 536
+        // windows -- real table: 32 897 ranks = 66 KB, three blocks per SM -- else 32-bit counters,
+        // else (all-distinct tables with long contigs) a per-block global scratch that stays in L2
+        const bool packed = max_ctg - kmer + 1 < 65536;
+        pa.hist_words = ks_a ? bs::hist_phys_words(k.R_x, packed) : 0;
+        pa.n_ranges = ks_a ? bs::hist_ranges(k.R_x, packed) : 0;
+        const size_t hist_bytes = (size_t)(pa.hist_words + pa.n_ranges) * 4;
+        const bool in_smem = hist_bytes + 2048 <= ctx->smem_optin;
+        const size_t smem = in_smem ? hist_bytes : 0;
+        const int per_sm = std::max<int>(1, std::min<int>(2048 / kKsThreads, (int)((ctx->smem_optin + 1024) / (smem + 1024))));
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm);
+        pa.rank_scratch = nullptr;
+        if (ks_a && !in_smem) {
+            BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * hist_bytes));
+            pa.rank_scratch = (uint32_t *)ctx->d_rank_scratch.p;
+        }
+        auto launch = [&](auto kern) -> int {
+            BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BS_LAUNCH(kern, (unsigned)nblk, kKsThreads, smem, st, pa);
+            return BS_OK;
+        };
+        if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true>));
+        else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false>));
+        else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true>));
+        else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
         ctx->launches++;
     }
     if (e.want_sp || e.want_lev) {
@@ -833,7 +816,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         BS_LAUNCH(bs::k_lev_infix, (unsigned)nblk, kLevThreads, 0, st, la);
         ctx->launches++;
     }
-    BS_CUDA(cudaStreamWaitEvent(st, ws.ev_aux, 0));  // the side stream's results belong to this chunk
     BS_CUDA(cudaGetLastError());
     BS_CUDA(cudaEventRecord(ws.ev_compute, st));
 
@@ -906,23 +888,17 @@ int bs_ctx_create(int device, bs_ctx **out) {
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < kWorkspaces; i++)
         ok = cudaEventCreateWithFlags(&ctx->ws[i].ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ws[i].ev_compute, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ws[i].ev_d2h, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ws[i].ev_seqs, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ws[i].ev_spec, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ws[i].ev_aux, cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ctx->ws[i].ev_d2h, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         fail(nullptr, BS_ERR_CUDA, "stream/event creation failed");
         bs_ctx_destroy(ctx);
         return BS_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
-    if (const char *env = std::getenv("BS_KS_BLOCKS_PER_SM")) ctx->ks_blocks_per_sm = std::atoi(env);
-    if (const char *env = std::getenv("BS_PLACE_BLOCKS_PER_SM")) ctx->place_blocks_per_sm = std::atoi(env);
     if (const char *env = std::getenv("BS_CHUNK_KB")) {  // tuning / tests: ASCII bytes per pipeline chunk
         const long kb = std::atol(env);
         if (kb > 0) ctx->chunk_bytes_host = ctx->chunk_bytes_dev = (int64_t)kb << 10;
@@ -947,9 +923,6 @@ void bs_ctx_destroy(bs_ctx *ctx) {
         if (w.ev_h2d) cudaEventDestroy(w.ev_h2d);
         if (w.ev_compute) cudaEventDestroy(w.ev_compute);
         if (w.ev_d2h) cudaEventDestroy(w.ev_d2h);
-        if (w.ev_seqs) cudaEventDestroy(w.ev_seqs);
-        if (w.ev_spec) cudaEventDestroy(w.ev_spec);
-        if (w.ev_aux) cudaEventDestroy(w.ev_aux);
     }
     for (TimedSpan &t : ctx->spans) {
         if (t.a) cudaEventDestroy(t.a);
@@ -958,7 +931,6 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     delete ctx;
 }
 
