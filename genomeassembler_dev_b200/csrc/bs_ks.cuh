@@ -1,0 +1,337 @@
+// Truth-side distribution and the rolling-window probabilities with their KS statistic.
+#pragma once
+#include "bs_score.cuh"
+
+namespace bs {
+
+// ------------------------------------------------------------------------------------------
+// truth-side distribution for the KS statistics (kmer_from_seq, upstream
+// lib/GenerateReads.R:243-259): per segment, counts of truth windows per distinct table value
+// ------------------------------------------------------------------------------------------
+
+// per x-value rank: index into the truth cumulative counts of the last y value <= / < that x value
+// (table level), or the cumulative counts themselves (segment level, yx below)
+struct LeLt {
+    int32_t le, lt;
+};
+
+struct SpectrumArgs {
+    const int64_t *tr_off;
+    const int64_t *tr_woff;
+    const uint64_t *tr_words;
+    const uint32_t *tr_mask;
+    const int32_t *rank_y;  // [4^kmer] rank of the window's truth-table value, -1 = not in table (NA)
+    int32_t *ycnt;          // [S][R_y]
+    const LeLt *lelt;       // [R_x] table-level indices (NULL: no yx output)
+    LeLt *yx;               // [S][R_x] #{truth windows <= x value}, #{truth windows < x value} per x-value rank
+    int32_t R_x;
+    int32_t R_y;
+    int32_t kmer;
+    int32_t blocks_per_seg;
+};
+
+__global__ void k_truth_spectrum(SpectrumArgs a) {
+    const int64_t s = blockIdx.x / a.blocks_per_seg;
+    const int b = blockIdx.x % a.blocks_per_seg;
+    const int64_t L = a.tr_off[s + 1] - a.tr_off[s];
+    const uint64_t *gw = a.tr_words + a.tr_woff[s];
+    const uint32_t *gm = a.tr_mask + a.tr_woff[s];
+    const int64_t nwin = L - a.kmer + 1;
+    const int doff = dense_offset(a.kmer);
+    for (int64_t p = (int64_t)b * blockDim.x + threadIdx.x; p < nwin; p += (int64_t)a.blocks_per_seg * blockDim.x) {
+        const int di = dense_index_at(gw, gm, p, a.kmer);
+        if (di < 0) continue;
+        const int32_t rk = a.rank_y[di - doff];
+        if (rk >= 0) atomicAdd(&a.ycnt[s * a.R_y + rk], 1);
+    }
+}
+
+// The same for truths of fewer than 65 536 windows, one block per segment: counts in shared
+// memory (two 16-bit counters per word), cumulated in place, written out once, coalesced.
+__global__ void __launch_bounds__(512, 3) k_truth_spectrum_smem(SpectrumArgs a) {
+    uint32_t *s_h = (uint32_t *)bs_dyn_smem();
+    __shared__ uint32_t s_wsum[32];
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t s = blockIdx.x;
+    const int64_t L = a.tr_off[s + 1] - a.tr_off[s];
+    const uint64_t *gw = a.tr_words + a.tr_woff[s];
+    const uint32_t *gm = a.tr_mask + a.tr_woff[s];
+    const int64_t nwin = L - a.kmer + 1;
+    const int kshift = 64 - 2 * a.kmer;
+    const uint32_t kbits = keep_bits(a.kmer);
+    const int nword = (a.R_y + 1) >> 1;
+    for (int i = tid; i < nword; i += nthr) s_h[i] = 0;
+    __syncthreads();
+    // a thread takes four CONSECUTIVE windows (never straddling a 32-base word boundary): the truth
+    // words are loaded once per four windows and the four rank gathers are in flight together
+    for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {
+        const int64_t pb = p0 + 4 * (int64_t)tid;
+        if (pb >= nwin) continue;
+        const int64_t wi = pb >> 5;
+        const uint32_t o = (uint32_t)(pb & 31);
+        const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
+        const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
+        int32_t rk[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            rk[u] = -1;
+            if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) rk[u] = __ldg(&a.rank_y[window64(w0, w1, o + u) >> kshift]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (rk[u] >= 0) atomicAdd(&s_h[rk[u] >> 1], 1u << (16 * (rk[u] & 1)));
+    }
+    __syncthreads();
+    // inclusive prefix over ranks: every thread owns an even number of consecutive ranks
+    int per = (a.R_y + nthr - 1) / nthr;
+    per += per & 1;
+    const int lo = tid * per < a.R_y ? tid * per : a.R_y;
+    const int hi = lo + per < a.R_y ? lo + per : a.R_y;
+    uint32_t sum = 0;
+    for (int i = lo >> 1; i < (hi + 1) >> 1; i++) { const uint32_t w = s_h[i]; sum += (w & 0xffffu) + (w >> 16); }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+    for (int w = 0; w < warp; w++) run += s_wsum[w];
+    for (int i = lo >> 1; i < (hi + 1) >> 1; i++) {
+        const uint32_t w = s_h[i];
+        const uint32_t c0 = run + (w & 0xffffu), c1 = c0 + (w >> 16);
+        s_h[i] = c0 | (c1 << 16);  // totals stay below 65 536
+        run = c1;
+    }
+    __syncthreads();
+    int32_t *out = a.ycnt + s * a.R_y;
+    for (int i = tid; i < a.R_y; i += nthr) out[i] = (int32_t)((s_h[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+    if (a.lelt) {  // the same counts looked up per x-value rank: the KS sweep then needs one gather, not two
+        LeLt *yx = a.yx + s * a.R_x;
+        for (int i = tid; i < a.R_x; i += nthr) {
+            const LeLt q = a.lelt[i];
+            LeLt o;
+            o.le = q.le >= 0 ? (int32_t)((s_h[q.le >> 1] >> (16 * (q.le & 1))) & 0xffffu) : 0;
+            o.lt = q.lt >= 0 ? (int32_t)((s_h[q.lt >> 1] >> (16 * (q.lt & 1))) & 0xffffu) : 0;
+            yx[i] = o;
+        }
+    }
+}
+
+// yx from the cumulative counts in global memory (after k_truth_spectrum + k_row_cumsum)
+__global__ void k_yx_gather(SpectrumArgs a, int64_t n_seg) {
+    const int64_t total = n_seg * a.R_x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = t / a.R_x;
+        const int i = (int)(t - s * a.R_x);
+        const LeLt q = a.lelt[i];
+        const int32_t *ycum = a.ycnt + s * a.R_y;
+        LeLt o;
+        o.le = q.le >= 0 ? ycum[q.le] : 0;
+        o.lt = q.lt >= 0 ? ycum[q.lt] : 0;
+        a.yx[t] = o;
+    }
+}
+
+// in-place inclusive prefix sum of every row of a [rows][R] int32 matrix; one block per row
+__global__ void k_row_cumsum(int32_t *m, int32_t R) {
+    int64_t *s_scan = (int64_t *)bs_dyn_smem();
+    int32_t *row = m + (int64_t)blockIdx.x * R;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int per = (R + nthr - 1) / nthr;
+    const int lo = tid * per, hi = (lo + per < R) ? lo + per : R;
+    int64_t sum = 0;
+    for (int i = lo; i < hi; i++) sum += row[i];
+    int64_t run = block_exclusive_scan(sum, s_scan, nullptr);
+    for (int i = lo; i < hi; i++) { run += row[i]; row[i] = (int32_t)run; }
+}
+
+// ------------------------------------------------------------------------------------------
+// rolling-window probabilities + KS statistic against the truth distribution
+// (upstream lib/BreakageScorer.cpp:200-215 and lib/DeNovoAssembler.R:416-424)
+// ------------------------------------------------------------------------------------------
+
+// one entry per k-mer code of the window length: what a window contributes to path_prob_dist
+// (0.0 when the k-mer is not a table row) and the rank of that value among the distinct x values
+struct alignas(16) WinEntry {
+    double prob;
+    int32_t rank;
+    int32_t pad;
+};
+
+struct ProbDistArgs {
+    const int32_t *order;     // [C] contig ids, longest first
+    int32_t *work_counter;    // zero on entry
+    const int64_t *ctg_off;
+    const int64_t *ctg_woff;
+    const uint64_t *ctg_words;
+    const uint32_t *ctg_mask;
+    const int32_t *ctg_seg;  // [C] segment of a contig
+    const WinEntry *win;     // [4^kmer], NULL when kmer is outside 1..8 (every window is "not in the table")
+    const LeLt *yx;          // [S][R_x] truth windows <= / < every x value
+    const int32_t *ycum;     // [S][R_y] inclusive cumulative counts of the truth distribution
+    int32_t R_x, R_y;
+    int32_t rank_zero;       // rank of the value 0.0 (windows not in the table)
+    int32_t kmer;
+    int64_t n_contigs;
+    double *prob_dist;       // optional
+    const int64_t *pd_off;
+    double *ks;              // optional [C]
+    uint32_t *rank_scratch;  // [gridDim][hist_words + n_ranges] global rank histogram when it does not fit shared memory, else NULL
+    int32_t hist_words;      // 32-bit words of one rank histogram (hist_phys_words)
+    int32_t n_ranges;        // hist_ranges: ranges of 32 histogram words
+};
+
+// Rank histogram layout.  PACKED: two 16-bit counters per 32-bit word (every contig of the launch
+// has < 65536 windows), else one counter per word.  Words are grouped into RANGES of 32 (one
+// thread sweeps one range) with one pad word after every range, which keeps a warp's
+// simultaneous sweeps on different banks.  A bitmap word per range marks the non-empty words, so
+// a sweep touches only those: its cost follows the contig's windows, not the number of ranks.
+template <bool PACKED>
+__device__ __forceinline__ int hist_logical_word(int r) { return PACKED ? r >> 1 : r; }
+BS_HD int hist_logical_words(int R_x, bool packed) { return packed ? (R_x + 1) / 2 : R_x; }
+BS_HD int hist_phys_words(int R_x, bool packed) {
+    const int w = hist_logical_words(R_x, packed);
+    return w + (w >> 5) + 2;
+}
+BS_HD int hist_ranges(int R_x, bool packed) { return (hist_logical_words(R_x, packed) + 31) / 32; }
+
+template <bool PACKED, bool IN_SMEM>
+__global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    __shared__ int64_t s_wsum[32];
+    __shared__ int64_t s_wmax[32];
+    __shared__ int s_item;
+    // dynamic shared memory (or the global scratch row): histogram words, then the range bitmaps
+    uint32_t *s_hist = IN_SMEM ? (uint32_t *)bs_dyn_smem() : a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges);
+    uint32_t *s_bm = s_hist + a.hist_words;
+    const bool want_ks = a.ks != nullptr;
+    const int kshift = 64 - 2 * a.kmer;
+    const uint32_t kbits = keep_bits(a.kmer);
+    if (want_ks) {
+        for (int i = tid; i < a.hist_words + a.n_ranges; i += nthr) s_hist[i] = 0;
+    }
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
+        const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
+        int64_t nwin = L - a.kmer + 1;
+        if (nwin < 0) nwin = 0;
+        double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
+        // truth side of this contig's segment, loaded early so that the latency hides behind the windows
+        const int64_t seg = a.ctg_seg[c];
+        const LeLt *yx = want_ks ? a.yx + seg * a.R_x : nullptr;
+        const int64_t n_y = (want_ks && a.R_y > 0) ? a.ycum[seg * a.R_y + a.R_y - 1] : 0;
+        // ---- windows: table value out, rank histogram in.  A thread takes four CONSECUTIVE
+        // positions (they never straddle a 32-base word boundary), so the contig words are
+        // loaded once per four windows; the four table gathers are in flight together ----
+        for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {
+            const int64_t pb = p0 + 4 * (int64_t)tid;
+            double val[4];
+            int32_t rk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { val[u] = 0.0; rk[u] = a.rank_zero; }
+            if (pb < nwin && a.win) {
+                const int64_t wi = pb >> 5;
+                const uint32_t o = (uint32_t)(pb & 31);  // multiple of 4: o + 3 <= 31
+                const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
+                const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) {
+                        const WinEntry e = a.win[window64(w0, w1, o + u) >> kshift];  // one 16-byte gather
+                        val[u] = e.prob;
+                        rk[u] = e.rank;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (pb + u < nwin) {
+                    if (pd) pd[pb + u] = val[u];
+                    if (want_ks) {
+                        const int lw = hist_logical_word<PACKED>(rk[u]);
+                        atomicAdd(&s_hist[lw + (lw >> 5)], PACKED ? 1u << (16 * (rk[u] & 1)) : 1u);
+                        atomicOr(&s_bm[lw >> 5], 1u << (lw & 31));
+                    }
+                }
+            }
+        }
+        if (!want_ks) continue;
+        __syncthreads();
+        // ---- D = sup |F_x - F_y| over the pooled distinct values, evaluated at every x value that
+        // is present: just below it (F_x of the previous step vs #{y < v}) and at it ----
+        const bool defined = nwin > 0 && n_y > 0;
+        // |F_x - F_y| = |run * n_y - ycount * nwin| / (nwin * n_y): the numerator is maximised in exact
+        // 64-bit integers (both factors are below 2^31), one division at the end
+        int64_t best = 0;
+        int64_t carry = 0;  // windows in the ranges of earlier rounds (same value on every thread)
+        for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {  // one range of 32 words per thread and round
+            const int r = r0 + tid;
+            const uint32_t m = r < a.n_ranges ? s_bm[r] : 0u;
+            if (m) s_bm[r] = 0;
+            const int w0 = 33 * r;  // physical index of the range's first word
+            int64_t cnt_r = 0;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const uint32_t w = s_hist[w0 + __ffs((int)mm) - 1];
+                cnt_r += PACKED ? (w & 0xffffu) + (w >> 16) : w;
+            }
+            // exclusive prefix of the range counts over the block (+ what earlier rounds held)
+            int64_t incl = cnt_r;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int64_t o = __shfl_up_sync(FULL_MASK, incl, dd);
+                if (lane >= dd) incl += o;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int64_t run = carry + incl - cnt_r;
+            for (int w = 0; w < nwarp; w++) {
+                if (w < warp) run += s_wsum[w];
+                carry += s_wsum[w];
+            }
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const int k = __ffs((int)mm) - 1;
+                const uint32_t w = s_hist[w0 + k];
+                s_hist[w0 + k] = 0;  // leave the histogram zeroed for the next contig
+#pragma unroll
+                for (int h = 0; h < (PACKED ? 2 : 1); h++) {
+                    const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
+                    if (cnt == 0 || !defined) continue;
+                    const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
+                    const LeLt q = yx[i];  // one 8-byte gather
+                    const int64_t lt = q.lt, le = q.le;
+                    int64_t d1 = run * n_y - lt * nwin;
+                    run += cnt;
+                    int64_t d2 = run * n_y - le * nwin;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    if (d1 > best) best = d1;
+                    if (d2 > best) best = d2;
+                }
+            }
+            __syncthreads();  // s_wsum is rewritten by the next round
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const int64_t o = __shfl_xor_sync(FULL_MASK, best, m);
+            if (o > best) best = o;
+        }
+        if (lane == 0) s_wmax[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nwarp; w++) if (s_wmax[w] > best) best = s_wmax[w];
+            a.ks[c] = defined ? (double)best / ((double)nwin * (double)n_y) : __longlong_as_double(0x7ff8000000000000ll);
+        }
+    }
+}
+
+}  // namespace bs

@@ -1,0 +1,294 @@
+// Break k-mers -> probability-weighted sums, optional histogram, KS of the normalised break histogram.
+#pragma once
+#include "bs_seq.cuh"
+
+namespace bs {
+
+// ------------------------------------------------------------------------------------------
+// block-level helpers
+// ------------------------------------------------------------------------------------------
+
+// sum of v over the block, fixed tree => bit-reproducible; result valid on every thread
+__device__ __forceinline__ double block_sum(double v, double *s_red) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    __syncthreads();
+    s_red[tid] = v;
+    __syncthreads();
+    for (int s = nthr >> 1; s > 0; s >>= 1) {
+        if (tid < s) s_red[tid] += s_red[tid + s];
+        __syncthreads();
+    }
+    return s_red[0];
+}
+__device__ __forceinline__ double block_max(double v, double *s_red) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    __syncthreads();
+    s_red[tid] = v;
+    __syncthreads();
+    for (int s = nthr >> 1; s > 0; s >>= 1) {
+        if (tid < s) { const double o = s_red[tid + s]; if (o > s_red[tid]) s_red[tid] = o; }
+        __syncthreads();
+    }
+    return s_red[0];
+}
+// exclusive prefix of v over the block (thread order); s_scan holds blockDim ints
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t *s_scan, int64_t *total) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    __syncthreads();
+    s_scan[tid] = v;
+    __syncthreads();
+    for (int d = 1; d < nthr; d <<= 1) {
+        int64_t add = (tid >= d) ? s_scan[tid - d] : 0;
+        __syncthreads();
+        s_scan[tid] += add;
+        __syncthreads();
+    }
+    if (total) *total = s_scan[nthr - 1];
+    return s_scan[tid] - v;
+}
+
+// ------------------------------------------------------------------------------------------
+// break k-mers -> probability-weighted sums (upstream lib/BreakageScorer.cpp:244-303), the
+// optional dense histogram, and the KS statistic of the normalised break histogram (variant
+// lib/DeNovoAssembler.cpp:395-420: x = count_row / total for every table row, y = truth
+// distribution) -- one pass family over the position weights of a contig
+// ------------------------------------------------------------------------------------------
+
+// scoring table over the dense k-mer index space (all lengths 1..8), one 16-byte gather per break
+struct alignas(16) TabEntry {
+    double prob;
+    int32_t row;
+    int32_t pad;
+};
+
+constexpr int CC_DENSE = 4096;  // counts below this are tallied in a dense shared-memory array
+constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
+
+struct ScoreArgs {
+    const int32_t *order;   // [C] contig ids, longest first
+    int32_t *work_counter;  // zero on entry
+    const int64_t *ctg_off;
+    const int64_t *ctg_woff;
+    const uint64_t *ctg_words;
+    const uint32_t *ctg_mask;
+    const int32_t *ctg_seg;
+    const int32_t *w;
+    const int32_t *total;
+    const TabEntry *tab;     // [DENSE_SIZE] probability and table row of a dense k-mer index (row -1 if absent)
+    int32_t kmer;
+    int32_t T;
+    int64_t n_contigs;
+    int32_t *sequence_len;
+    double *bp_score;
+    double *norm_by_break_freqs;
+    double *norm_by_len;
+    int32_t *kmer_breaks;
+    int32_t *hist;  // optional [C][T+1]
+    // KS of the normalised break histogram (all NULL / 0 when not wanted)
+    double *ks_b;          // [C]
+    const double *yv;      // [R_y] sorted distinct truth-table values
+    const int32_t *ycum;   // [S][R_y] inclusive cumulative counts of the truth distribution
+    int32_t R_y;
+    int32_t zero_le, zero_lt;  // indices into ycum of the last y value <= 0.0 / < 0.0 (-1: none)
+    double y_max;          // largest truth-table value
+    int32_t *scratch;      // [gridDim][T+1], all zero on entry and on exit
+    int32_t *ovf_cnt;      // [gridDim][OVF_CAP] counts >= CC_DENSE (unsorted)
+    int32_t *status;       // set to 1 if a block ran out of overflow space
+};
+
+// number of y values <= v (le) and < v (lt), from the cumulative counts
+__device__ __forceinline__ void y_counts_at(const double *yv, const int32_t *ycum, int R_y, double y_max, double v,
+                                            double *le, double *lt) {
+    if (R_y <= 0) { *le = 0.0; *lt = 0.0; return; }
+    if (v > y_max) { *le = *lt = (double)ycum[R_y - 1]; return; }  // the usual case: count/total >> any table value
+    int lo = 0, hi = R_y;  // first index with yv > v
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (yv[mid] <= v) lo = mid + 1; else hi = mid; }
+    const int ule = lo;  // #distinct <= v
+    lo = 0; hi = R_y;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (yv[mid] < v) lo = mid + 1; else hi = mid; }
+    const int ult = lo;  // #distinct < v
+    *le = ule > 0 ? (double)ycum[ule - 1] : 0.0;
+    *lt = ult > 0 ? (double)ycum[ult - 1] : 0.0;
+}
+
+// sum over the block in a fixed order (lane tree, then warps in order): bit-reproducible, the
+// same for every GPU count; valid on thread 0
+__device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL_MASK, v, m);
+    __syncthreads();
+    if (lane == 0) s_w[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) for (int i = 0; i < nwarp; i++) t += s_w[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
+    __shared__ double s_w[32];
+    __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
+    __shared__ int s_item, s_novf, s_maxc, s_nz;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const bool want_ks = a.ks_b != nullptr;
+    int32_t *scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
+    int32_t *ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    if (want_ks) for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; }
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
+        const int64_t coff = a.ctg_off[c];
+        const int64_t L = a.ctg_off[c + 1] - coff;
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
+        const int32_t *w = a.w + coff + c;
+        const int32_t total = a.total[c];
+        const int64_t np = L > 0 ? L : 1;
+        double s1 = 0.0, s2 = 0.0;
+        // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS); four
+        // positions per thread in flight so that the table gathers overlap
+        if (total != 0) {
+            for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
+                int32_t wv[4];
+                TabEntry te[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int64_t p = p0 + (int64_t)u * nthr + tid;
+                    wv[u] = p < np ? w[p] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    te[u].prob = 0.0;
+                    te[u].row = -1;
+                    if (wv[u] != 0) {
+                        const BreakWindow bw = break_window(p0 + (int64_t)u * nthr + tid, a.kmer, L);
+                        const int di = dense_index_at(gw, gm, bw.start, bw.len);
+                        if (di >= 0) te[u] = a.tab[di];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (wv[u] == 0) continue;
+                    const int32_t row = te[u].row;
+                    if (row >= 0) {
+                        s1 += te[u].prob * (double)wv[u];
+                        s2 += te[u].prob * ((double)wv[u] / (double)total);
+                        if (want_ks) atomicAdd(&scratch[row], wv[u]);
+                    }
+                    if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv[u]);
+                }
+            }
+        }
+        s1 = block_sum_fixed(s1, s_w);
+        s2 = block_sum_fixed(s2, s_w);
+        if (tid == 0) {
+            if (a.sequence_len) a.sequence_len[c] = (int32_t)L;
+            if (a.bp_score) a.bp_score[c] = s1;
+            if (a.norm_by_break_freqs) a.norm_by_break_freqs[c] = s2;
+            if (a.norm_by_len) a.norm_by_len[c] = s1 / (double)(int32_t)L;
+            if (a.kmer_breaks) a.kmer_breaks[c] = total;
+        }
+        if (!want_ks) continue;
+        if (total == 0) {  // 0/0 for every row: R drops the NaNs and ks.test stops on empty x
+            if (tid == 0) a.ks_b[c] = qnan;
+            continue;
+        }
+        __threadfence_block();
+        __syncthreads();
+        // pass 2: whoever swaps a row's count out first owns it; tally rows per count value
+        for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
+            int32_t wv[4], row[4], cnt[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t p = p0 + (int64_t)u * nthr + tid;
+                wv[u] = p < np ? w[p] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                row[u] = -1;
+                if (wv[u] != 0) {
+                    const BreakWindow bw = break_window(p0 + (int64_t)u * nthr + tid, a.kmer, L);
+                    const int di = dense_index_at(gw, gm, bw.start, bw.len);
+                    if (di >= 0) row[u] = a.tab[di].row;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) cnt[u] = row[u] >= 0 ? atomicExch(&scratch[row[u]], 0) : 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (cnt[u] == 0) continue;
+                atomicAdd(&s_nz, 1);
+                if (cnt[u] < CC_DENSE) { atomicAdd(&s_cc[cnt[u]], 1); atomicMax(&s_maxc, cnt[u]); }
+                else {
+                    const int slot = atomicAdd(&s_novf, 1);
+                    if (slot < OVF_CAP) ovf[slot] = cnt[u]; else *a.status = 1;
+                }
+            }
+        }
+        __syncthreads();
+        // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them
+        if (tid == 0) {
+            const int32_t *ycum = a.ycum + (int64_t)a.ctg_seg[c] * a.R_y;
+            const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
+            const int novf = s_novf < OVF_CAP ? s_novf : OVF_CAP;
+            double d = 0.0;
+            if (n_y > 0 && a.T > 0) {
+                const double inx = (double)a.T, iny = (double)n_y;
+                int64_t run = (int64_t)a.T - s_nz;  // rows never broken: x value 0
+                if (run > 0) {
+                    const double le = a.zero_le >= 0 ? (double)ycum[a.zero_le] : 0.0;
+                    const double lt = a.zero_lt >= 0 ? (double)ycum[a.zero_lt] : 0.0;
+                    double d1 = lt / iny, d2 = (double)run / inx - le / iny;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    d = d1 > d2 ? d1 : d2;
+                }
+                for (int j = 1; j <= s_maxc; j++) {
+                    const int32_t cnt = s_cc[j];
+                    if (cnt == 0) continue;
+                    s_cc[j] = 0;
+                    double le, lt;
+                    y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)j / (double)total, &le, &lt);
+                    double d1 = (double)run / inx - lt / iny;
+                    run += cnt;
+                    double d2 = (double)run / inx - le / iny;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    if (d1 > d) d = d1;
+                    if (d2 > d) d = d2;
+                }
+                // counts >= CC_DENSE: few; walked in ascending order
+                int32_t last = CC_DENSE - 1;
+                for (int done = 0; done < novf;) {
+                    int32_t cur = 0x7fffffff;
+                    int mult = 0;
+                    for (int i = 0; i < novf; i++) {
+                        const int32_t v = ovf[i];
+                        if (v > last && v < cur) { cur = v; mult = 1; }
+                        else if (v == cur) mult++;
+                    }
+                    double le, lt;
+                    y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)cur / (double)total, &le, &lt);
+                    double d1 = (double)run / inx - lt / iny;
+                    run += mult;
+                    double d2 = (double)run / inx - le / iny;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    if (d1 > d) d = d1;
+                    if (d2 > d) d = d2;
+                    last = cur;
+                    done += mult;
+                }
+            } else {
+                for (int j = 1; j <= s_maxc; j++) s_cc[j] = 0;
+            }
+            a.ks_b[c] = (n_y > 0 && a.T > 0) ? d : qnan;
+        }
+    }
+}
+
+}  // namespace bs

@@ -1,0 +1,294 @@
+// Descriptors of packed sequences and reads, 2-bit packing kernels and the per-segment read index.
+#pragma once
+#include "bs_device.cuh"
+
+namespace bs {
+
+// ------------------------------------------------------------------------------------------
+// descriptors (plain structs passed by value)
+// ------------------------------------------------------------------------------------------
+
+// a set of strings packed AoS: string i owns words [woff[i], woff[i+1]) = ceil(L_i/32) + 2
+// (two pad words: sequence 0, mask all-ones) and the same range of mask words
+struct SeqSet {
+    const uint8_t *chars;  // ASCII
+    const int64_t *off;    // [n+1] char offsets
+    const int64_t *woff;   // [n+1] word offsets
+    uint64_t *words;
+    uint32_t *mask;
+    int64_t n;
+    int64_t total_words;
+};
+
+// reads packed AoS: word j of read i at words[i * W + j] (a placement candidate is verified from
+// one or two 32-byte sectors)
+struct ReadSet {
+    const uint8_t *chars;
+    const int64_t *off;  // NULL => uniform_len, dense
+    int32_t uniform_len;
+    int32_t W;  // words per read
+    int64_t n;
+    uint64_t *words;
+    uint8_t *flags;  // bit0: read holds a byte outside ACGT
+};
+
+BS_HD int64_t read_begin(const ReadSet &r, int64_t i) { return r.off ? r.off[i] : i * (int64_t)r.uniform_len; }
+BS_HD int32_t read_length(const ReadSet &r, int64_t i) { return r.off ? (int32_t)(r.off[i + 1] - r.off[i]) : r.uniform_len; }
+
+// ------------------------------------------------------------------------------------------
+// 2-bit packing
+// ------------------------------------------------------------------------------------------
+
+// one thread per packed word of a SeqSet
+__global__ void k_pack_seqs(SeqSet s) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < s.total_words; wi += stride) {
+        // string owning word wi: largest i with woff[i] <= wi
+        int64_t lo = 0, hi = s.n - 1;
+        while (lo < hi) {
+            int64_t mid = (lo + hi + 1) >> 1;
+            if (s.woff[mid] <= wi) lo = mid; else hi = mid - 1;
+        }
+        const int64_t c0 = s.off[lo];
+        const int64_t L = s.off[lo + 1] - c0;
+        const int64_t b0 = (wi - s.woff[lo]) * 32;
+        uint64_t w = 0;
+        uint32_t m = 0;
+        for (int b = 0; b < 32; b++) {
+            const int64_t p = b0 + b;
+            uint32_t code = 0, bad = 1;
+            if (p < L) {
+                const uint32_t ch = s.chars[c0 + p];
+                if (base_valid(ch)) { code = base_code(ch); bad = 0; }
+            }
+            w = (w << 2) | code;
+            m = (m << 1) | bad;
+        }
+        s.words[wi] = w;
+        s.mask[wi] = m;
+    }
+}
+
+// ---- read index ------------------------------------------------------------------------------
+// Per segment, a chained hash table over the reads' seeds (their first seed_len bases, seed_len =
+// min(32, shortest read of the segment)): head[tab_off[s] + (hash(seed) & tab_mask[s])] -> read id
+// + 1, next[read] -> next read id + 1 of the same bucket (0 ends the chain).  Reads whose seed
+// cannot be packed (a byte outside ACGT in it, or an empty read) hang on odd_head[s] instead and
+// are placed by byte comparison.  Built by the packing kernels, consumed by k_place_index.
+struct ReadIndex {
+    uint32_t *head;
+    uint2 *next;              // [N] x = next read id + 1 of the bucket (0 ends the chain), y = seed tag
+    uint32_t *odd_head;       // [S]
+    const int64_t *tab_off;   // [S]
+    const int32_t *tab_mask;  // [S] table size - 1 (size is a power of two)
+    const int32_t *seed_len;  // [S]
+    const int64_t *seg_read_start;  // [S+1]
+    int32_t n_seg;
+};
+
+// segment owning read n: largest s with seg_read_start[s] <= n (empty segments are skipped)
+__device__ __forceinline__ int segment_of_read(const ReadIndex &ix, int64_t n) {
+    int lo = 0, hi = ix.n_seg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (ix.seg_read_start[mid] <= n) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void index_insert(const ReadIndex &ix, int s, int64_t n, uint64_t word0, int len, bool seed_bad) {
+    const int S = ix.seed_len[s];
+    if (len == 0 || seed_bad) {
+        ix.next[n] = make_uint2(atomicExch(&ix.odd_head[s], (uint32_t)n + 1u), 0u);
+    } else {
+        const uint64_t seed = word0 & keep_bases(S);
+        const uint32_t h = seed_hash(seed) & (uint32_t)ix.tab_mask[s];
+        ix.next[n] = make_uint2(atomicExch(&ix.head[ix.tab_off[s] + h], (uint32_t)n + 1u), seed_tag(seed));
+    }
+}
+
+// general packing (reads of arbitrary lengths): one thread per read, all W words, the
+// "has a byte outside ACGT" flag and the index insertion
+__global__ void k_pack_reads(ReadSet r, ReadIndex ix) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += stride) {
+        const int64_t c0 = read_begin(r, i);
+        const int32_t len = read_length(r, i);
+        uint32_t any_bad = 0, seed_bad = 0;
+        uint64_t w0 = 0;
+        for (int j = 0; j < r.W; j++) {
+            uint64_t w = 0;
+            for (int b = 0; b < 32; b++) {
+                const int p = j * 32 + b;
+                uint32_t code = 0;
+                if (p < len) {
+                    const uint32_t ch = r.chars[c0 + p];
+                    if (base_valid(ch)) code = base_code(ch); else any_bad = 1;
+                }
+                w = (w << 2) | code;
+            }
+            r.words[i * r.W + j] = w;
+            if (j == 0) { w0 = w; seed_bad = any_bad; }
+        }
+        r.flags[i] = (uint8_t)any_bad;
+        if (ix.head) index_insert(ix, segment_of_read(ix, i), i, w0, len, seed_bad != 0);
+    }
+}
+
+// ---- fast packing for reads of one common length (the simulated-read case) -------------------
+// 16 ASCII bytes -> 32 bits of 2-bit codes, four bytes at a time inside a 32-bit register:
+//   code  = ((c >> 1) ^ (c >> 2)) & 3 per byte, gathered into one byte by a multiply;
+//   valid = the byte equals "ACGT"[code] (a byte-permute looks the expected letter up).
+__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t &diff) {
+    const uint32_t t = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+    uint32_t u = (t | (t >> 4)) & 0x00ff00ffu;
+    u = u | (u >> 8);  // code of byte i in nibble i
+    diff |= x ^ __byte_perm(0x54474341u, 0u, u & 0xffffu);
+    return t * 0x40100401u;  // top byte = c0 c1 c2 c3 (first base in the most significant bits)
+}
+__device__ __forceinline__ uint32_t pack16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t &diff) {
+    const uint32_t g0 = pack4(x0, diff), g1 = pack4(x1, diff), g2 = pack4(x2, diff), g3 = pack4(x3, diff);
+    const uint32_t hi = __byte_perm(g0, g1, 0x3700u);  // byte3 = g0.3, byte2 = g1.3
+    const uint32_t lo = __byte_perm(g2, g3, 0x0037u);  // byte1 = g2.3, byte0 = g3.3
+    return __byte_perm(hi, lo, 0x3254u);
+}
+
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_WARP_CELLS = 66;  // 16-byte cells a warp tile (32 words = at most 1024 bytes + alignment) can touch
+
+// One WARP tile = 32 consecutive output words (AoS order: read-major).  Their source bytes are
+// one contiguous span of the dense read buffer: staged by coalesced 16-byte loads, converted
+// once per 16-byte cell into the warp's slice of shared memory, then each lane cuts its 32 bases
+// out of two or three cells with funnel shifts.  Warps never wait for one another (__syncwarp
+// only).  A cell holding any byte outside ACGT flags every read that overlaps it (conservative:
+// flagged reads are verified by byte comparison, still exact).
+__global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, ReadIndex ix) {
+    __shared__ uint32_t s_code_all[PACK_THREADS / 32][PACK_WARP_CELLS];
+    __shared__ uint32_t s_bad_all[PACK_THREADS / 32][PACK_WARP_CELLS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *s_code = s_code_all[warp], *s_bad = s_bad_all[warp];
+    const int64_t n_words = r.n * r.W;
+    const int64_t total_bytes = r.n * (int64_t)r.uniform_len;
+    const uintptr_t base = (uintptr_t)r.chars;
+    const int L = r.uniform_len;
+    const uint32_t W = (uint32_t)r.W;
+    // every warp owns a contiguous run of tiles: consecutive tiles read adjacent bytes and stay in
+    // the same segment, and the next tile's loads can be issued before the current one is finished
+    const int64_t warps_total = (int64_t)gridDim.x * (PACK_THREADS / 32);
+    const int64_t tiles_total = (n_words + 31) / 32;
+    const int64_t per_warp = (tiles_total + warps_total - 1) / warps_total;
+    const int64_t wid = (int64_t)blockIdx.x * (PACK_THREADS / 32) + warp;
+    int64_t k0 = wid * per_warp * 32;
+    int64_t k_end = k0 + per_warp * 32;
+    if (k_end > n_words) k_end = n_words;
+    if (k0 >= k_end) return;
+    // (read, word-in-read) of the tile's first word: one 64-bit division, then 32-bit increments
+    int64_t n0 = k0 / W;
+    uint32_t j0 = (uint32_t)(k0 - n0 * W);
+    const uint32_t adv = 32u % W, adv_n = 32u / W;
+    int seg = ix.head ? segment_of_read(ix, n0) : 0;
+
+    // geometry of a tile and the (up to three) 16-byte cells this lane stages for it
+    struct Tile { int64_t lo16; int n_cells; int ntile; };
+    auto tile_of = [&](int64_t k, int64_t n, uint32_t j) {
+        Tile t;
+        t.ntile = (int)(k_end - k < 32 ? k_end - k : 32);
+        const uint32_t xl = j + (uint32_t)t.ntile - 1;
+        const uint32_t dnl = xl / W;
+        const int64_t lo = n * L + (int64_t)j * 32;                          // first source byte of the tile
+        int64_t hi = (n + dnl) * L + (int64_t)(xl - dnl * W) * 32 + 32;      // one past the last
+        if (hi > total_bytes) hi = total_bytes;
+        t.lo16 = lo - (int64_t)((base + (uintptr_t)lo) & 15);               // 16-byte aligned address, may be < 0
+        t.n_cells = (int)((hi - t.lo16 + 15) >> 4);
+        return t;
+    };
+    auto load_cell = [&](const Tile &t, int ci) {
+        uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+        if (ci < t.n_cells) {
+            const int64_t cb = t.lo16 + 16 * (int64_t)ci;
+            if (cb >= 0 && cb + 16 <= total_bytes) {
+                v = *reinterpret_cast<const uint4 *>(r.chars + cb);
+            } else {  // partly outside the buffer: bytes that do not exist read as 'A'
+                uint32_t xs[4];
+                for (int q = 0; q < 4; q++) {
+                    uint32_t x = 0;
+                    for (int b = 3; b >= 0; b--) {
+                        const int64_t pb = cb + 4 * q + b;
+                        x = (x << 8) | ((pb >= 0 && pb < total_bytes) ? (uint32_t)r.chars[pb] : (uint32_t)'A');
+                    }
+                    xs[q] = x;
+                }
+                v = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+            }
+        }
+        return v;
+    };
+
+    Tile t = tile_of(k0, n0, j0);
+    uint4 c0 = load_cell(t, lane), c1 = load_cell(t, lane + 32), c2 = load_cell(t, lane + 64);
+    for (;;) {
+        // ---- convert this tile's cells into the warp's shared-memory slice ----
+        __syncwarp();
+        {
+            uint32_t diff = 0;
+            s_code[lane] = pack16(c0.x, c0.y, c0.z, c0.w, diff);
+            s_bad[lane] = diff;
+            diff = 0;
+            s_code[lane + 32] = pack16(c1.x, c1.y, c1.z, c1.w, diff);
+            s_bad[lane + 32] = diff;
+            if (lane + 64 < PACK_WARP_CELLS) {
+                diff = 0;
+                s_code[lane + 64] = pack16(c2.x, c2.y, c2.z, c2.w, diff);
+                s_bad[lane + 64] = diff;
+            }
+        }
+        __syncwarp();
+        // ---- issue the next tile's loads before cutting this tile's words ----
+        const Tile cur = t;
+        const int64_t k_cur = k0, n_cur = n0;
+        const uint32_t j_cur = j0;
+        k0 += 32;
+        n0 += adv_n;
+        j0 += adv;
+        if (j0 >= W) { j0 -= W; n0++; }
+        const bool more = k0 < k_end;
+        if (more) {
+            t = tile_of(k0, n0, j0);
+            c0 = load_cell(t, lane);
+            c1 = load_cell(t, lane + 32);
+            c2 = load_cell(t, lane + 64);
+        }
+        if (lane < cur.ntile) {
+            const uint32_t x = j_cur + (uint32_t)lane;
+            const uint32_t dn = x / W;
+            const int64_t n = n_cur + dn;
+            const int j = (int)(x - dn * W);
+            const int a = (int)(n * L + 32 * j - cur.lo16);  // byte offset inside the staged span (< 1100)
+            const int ci = a >> 4;
+            const uint32_t sh = 2u * (uint32_t)(a & 15);
+            const int rem = L - 32 * j;  // bases of this word that belong to the read (may exceed 32)
+            // cells past the staged span are only touched by bases beyond the read: clamp the index
+            const int i1 = ci + 1 < cur.n_cells ? ci + 1 : cur.n_cells - 1, i2 = ci + 2 < cur.n_cells ? ci + 2 : cur.n_cells - 1;
+            const uint32_t w0 = s_code[ci], w1 = s_code[i1], w2 = s_code[i2];
+            const uint32_t o_hi = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
+            const uint32_t o_lo = sh ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;
+            const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(rem);
+            r.words[k_cur + lane] = word;
+            // cells overlapping this word's own bytes [a, a + min(rem, 32))
+            const int last_cell = (a + (rem < 32 ? rem : 32) - 1) >> 4;
+            uint32_t bad = s_bad[ci];
+            if (last_cell >= ci + 1) bad |= s_bad[i1];
+            if (last_cell >= ci + 2) bad |= s_bad[i2];
+            if (bad) atomicOr(reinterpret_cast<unsigned *>(r.flags) + (n >> 2), 1u << (8 * (int)(n & 3)));
+            if (j == 0 && ix.head) {
+                int sg = seg;  // reads of a tile rarely span more than one segment
+                while (sg + 1 < ix.n_seg && n >= ix.seg_read_start[sg + 1]) sg++;
+                index_insert(ix, sg, n, word, L, bad != 0);
+            }
+        }
+        if (!more) break;
+        if (ix.head) while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
+    }
+}
+
+}  // namespace bs
