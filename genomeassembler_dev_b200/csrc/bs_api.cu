@@ -326,15 +326,58 @@ struct CallEnv {
 
 int64_t read_byte_begin(const CallEnv &e, int64_t n) { return e.roff ? e.roff[n] : n * (int64_t)e.rlen; }
 
-// ---- one chunk: metadata, H2D, kernels, D2H --------------------------------------------------
-int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
-    const bs_batch *b = e.b;
-    bs_result *res = e.res;
-    const int64_t S = ch.s1 - ch.s0, N = ch.r1 - ch.r0, C = ch.c1 - ch.c0;
-    const int64_t T = e.T;
-    const int kmer = e.kmer;
-    cudaStream_t st = ctx->stream;
 
+// One chunk on its way through the pipeline: chunk-local metadata, device views and result
+// destinations (prepare), then one method per stage of the compute stream, then the results.
+struct ChunkRun {
+    bs_ctx *ctx;
+    Workspace &ws;
+    const CallEnv &e;
+    const Chunk &ch;
+    const bs_batch *b;
+    bs_result *res;
+    int64_t S, N, C, T;
+    int kmer;
+    cudaStream_t st;
+    int grid_cap = 0;
+
+    // sizes found while building the metadata
+    int W = 1;
+    bool tile_mode = false, ks_a = false, ks_b = false;
+    int64_t max_ctg = 0, max_tr = 0, max_seg_reads = 0, head_total = 0, w_elems = 0, pd_elems = 0, pos_elems = 0;
+    int tile_len = 0, hash_size = 0, found_words = 0;  // tile placement modes
+    size_t place_smem = 0, n_items = 0;
+
+    // device views of the chunk
+    const int64_t *d_ctg_off = nullptr, *d_ctg_woff = nullptr, *d_tr_off = nullptr, *d_tr_woff = nullptr, *d_seg_rs = nullptr,
+                  *d_seg_cs = nullptr, *d_tab_off = nullptr, *d_pd_off = nullptr, *d_pos_off = nullptr, *d_roff = nullptr;
+    const int32_t *d_ctg_seg = nullptr, *d_seed = nullptr, *d_tab_mask = nullptr, *d_order = nullptr;
+    const bs::PlaceItem *d_items = nullptr;
+    const uint8_t *d_rchars = nullptr, *d_cchars = nullptr, *d_tchars = nullptr;
+    bs::SeqSet cs, ts;
+    bs::ReadSet rs;
+    bs::ReadIndex ix;
+
+    // result destinations on the device (user arrays with BS_DEVICE_RESULT, else the workspace)
+    int32_t *o_len = nullptr, *o_breaks = nullptr, *o_startpos = nullptr, *o_lev = nullptr, *o_hist = nullptr, *o_pos = nullptr;
+    double *o_score = nullptr, *o_norm = nullptr, *o_bylen = nullptr, *o_ksa = nullptr, *o_ksb = nullptr, *o_pd = nullptr;
+
+    ChunkRun(bs_ctx *c, Workspace &w, const CallEnv &env, const Chunk &chunk)
+        : ctx(c), ws(w), e(env), ch(chunk), b(env.b), res(env.res), S(chunk.s1 - chunk.s0), N(chunk.r1 - chunk.r0),
+          C(chunk.c1 - chunk.c0), T(env.T), kmer(env.kmer), st(c->stream), grid_cap(c->sm_count * 32) {}
+
+    int prepare();    // metadata, buffers, H2D, result destinations, memsets
+    int pack();       // 2-bit packing of contigs, truths and reads (+ read index)
+    int place();      // leftmost placement of every read in every contig of its segment
+    int spectrum();   // truth-side distribution of the KS statistics
+    int score();      // weighted sums, histogram, KS-B
+    int prob_dist();  // path_prob_dist and KS-A
+    int startpos();   // contig-in-truth offset
+    int lev();        // infix edit distance
+    int results();    // D2H (or the tail of the device-result path)
+};
+
+int ChunkRun::prepare() {
     // the workspace's previous chunk must have left it (its results are on their way or home)
     if (ws.in_flight) {
         BS_CUDA(cudaEventSynchronize(ws.ev_d2h));
@@ -348,7 +391,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
 
     std::vector<int64_t> ctg_off(C + 1), ctg_woff(C + 1), tr_off(S + 1), tr_woff(S + 1), seg_rs(S + 1), seg_cs(S + 1), tab_off(std::max<int64_t>(S, 1));
     std::vector<int32_t> ctg_seg(std::max<int64_t>(C, 1)), seed_len(std::max<int64_t>(S, 1)), tab_mask(std::max<int64_t>(S, 1));
-    int64_t max_ctg = 0, max_tr = 0;
     ctg_woff[0] = 0;
     for (int64_t c = 0; c <= C; c++) ctg_off[c] = b->contig_off[ch.c0 + c] - ctg_b0;
     for (int64_t c = 0; c < C; c++) {
@@ -357,7 +399,6 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         ctg_woff[c + 1] = ctg_woff[c] + (L + 31) / 32 + 2;
     }
     tr_woff[0] = 0;
-    int64_t max_seg_reads = 0, head_total = 0;
     int64_t max_read = 0;
     for (int64_t s = 0; s <= S; s++) {
         tr_off[s] = b->truth_off[ch.s0 + s] - tr_b0;
@@ -390,14 +431,12 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         head_total += hs;
     }
     if (max_read > 0x3fffffff) return fail(ctx, BS_ERR_INVALID, "read longer than 2^30");
-    const int W = (int)std::max<int64_t>(1, (max_read + 31) / 32);
-    const bool tile_mode = (e.flags & (BS_PLACE_SCAN | BS_PLACE_TILE)) != 0;
+    W = (int)std::max<int64_t>(1, (max_read + 31) / 32);
+    tile_mode = (e.flags & (BS_PLACE_SCAN | BS_PLACE_TILE)) != 0;
 
     // placement order of the index kernel: longest contigs first
     std::vector<int32_t> order;
     std::vector<bs::PlaceItem> items;
-    int tile_len = 0, hash_size = 0, found_words = 0;
-    size_t place_smem = 0;
     // work order of the persistent kernels: the long contigs first, longest first (they set the
     // tail), then the rest in input order so that the blocks running at one time share few
     // segments (read index and reads of those segments stay in L2)
@@ -486,9 +525,10 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     std::memcpy(ws.h_meta, mb.bytes.data(), mb.bytes.size());
 
     // ---------------- device buffers ----------------
-    const int64_t w_elems = ctg_bytes + C;
-    const int64_t pd_elems = e.want_pd ? pd_off[C] : 0;
-    const int64_t pos_elems = e.want_pos ? pos_off[C] : 0;
+    w_elems = ctg_bytes + C;
+    pd_elems = e.want_pd ? pd_off[C] : 0;
+    pos_elems = e.want_pos ? pos_off[C] : 0;
+    n_items = items.size();
     BS_TRY(ensure(ctx, ws.meta, mb.bytes.size()));
     if (!e.dev_chars) {
         BS_TRY(ensure(ctx, ws.read_chars, (size_t)read_bytes + 32));
@@ -517,25 +557,23 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     }
 
     unsigned char *dm = (unsigned char *)ws.meta.p;
-    const int64_t *d_ctg_off = (const int64_t *)(dm + o_ctg_off);
-    const int64_t *d_ctg_woff = (const int64_t *)(dm + o_ctg_woff);
-    const int32_t *d_ctg_seg = (const int32_t *)(dm + o_ctg_seg);
-    const int64_t *d_tr_off = (const int64_t *)(dm + o_tr_off);
-    const int64_t *d_tr_woff = (const int64_t *)(dm + o_tr_woff);
-    const int64_t *d_seg_rs = (const int64_t *)(dm + o_seg_rs);
-    const int64_t *d_seg_cs = (const int64_t *)(dm + o_seg_cs);
-    const int32_t *d_seed = (const int32_t *)(dm + o_seed);
-    const int64_t *d_tab_off = (const int64_t *)(dm + o_tab_off);
-    const int32_t *d_tab_mask = (const int32_t *)(dm + o_tab_mask);
-    const int32_t *d_order = (const int32_t *)(dm + o_order);
-    const int32_t *d_order2 = d_order;
-    const bs::PlaceItem *d_items = (const bs::PlaceItem *)(dm + o_items);
-    const int64_t *d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
-    const int64_t *d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
-    const int64_t *d_roff = e.roff ? (const int64_t *)(dm + o_roff) : nullptr;
+    d_ctg_off = (const int64_t *)(dm + o_ctg_off);
+    d_ctg_woff = (const int64_t *)(dm + o_ctg_woff);
+    d_ctg_seg = (const int32_t *)(dm + o_ctg_seg);
+    d_tr_off = (const int64_t *)(dm + o_tr_off);
+    d_tr_woff = (const int64_t *)(dm + o_tr_woff);
+    d_seg_rs = (const int64_t *)(dm + o_seg_rs);
+    d_seg_cs = (const int64_t *)(dm + o_seg_cs);
+    d_seed = (const int32_t *)(dm + o_seed);
+    d_tab_off = (const int64_t *)(dm + o_tab_off);
+    d_tab_mask = (const int32_t *)(dm + o_tab_mask);
+    d_order = (const int32_t *)(dm + o_order);
+    d_items = (const bs::PlaceItem *)(dm + o_items);
+    d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
+    d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
+    d_roff = e.roff ? (const int64_t *)(dm + o_roff) : nullptr;
 
     // ---------------- H2D (copy stream) ----------------
-    const uint8_t *d_rchars, *d_cchars, *d_tchars;
     {
         StageTimer tm(ctx, ST_H2D, ctx->copy_stream);
         cudaStream_t cs = ctx->copy_stream;
@@ -557,9 +595,8 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     BS_CUDA(cudaStreamWaitEvent(st, ws.ev_h2d, 0));
 
     // result destinations on the device
-    int32_t *o_len, *o_breaks, *o_startpos, *o_lev, *o_hist = nullptr, *o_pos = nullptr;
-    double *o_score, *o_norm, *o_bylen, *o_ksa, *o_ksb, *o_pd = nullptr;
-    const bool ks_a = e.want_ks && res->ks_stat_prob_dist, ks_b = e.want_ks && res->ks_stat_path_freq;
+    ks_a = e.want_ks && res->ks_stat_prob_dist;
+    ks_b = e.want_ks && res->ks_stat_path_freq;
     if (e.dev_res) {
         o_len = res->sequence_len ? res->sequence_len + ch.c0 : nullptr;
         o_breaks = res->kmer_breaks ? res->kmer_breaks + ch.c0 : nullptr;
@@ -594,16 +631,18 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     if (o_pos && pos_elems > 0) BS_CUDA(cudaMemsetAsync(o_pos, 0xff, (size_t)pos_elems * 4, st));
 
     // ---------------- kernels (compute stream) ----------------
-    const int grid_cap = ctx->sm_count * 32;
-    bs::SeqSet cs{d_cchars, d_ctg_off, d_ctg_woff, (uint64_t *)ws.cwords.p, (uint32_t *)ws.cmask.p, C, ctg_woff[C]};
-    bs::SeqSet ts{d_tchars, d_tr_off, d_tr_woff, (uint64_t *)ws.twords.p, (uint32_t *)ws.tmask.p, S, tr_woff[S]};
-    bs::ReadSet rs{d_rchars, d_roff, e.rlen, W, N, (uint64_t *)ws.rwords.p, (uint8_t *)ws.rflags.p};
-    bs::ReadIndex ix;
+    cs = bs::SeqSet{d_cchars, d_ctg_off, d_ctg_woff, (uint64_t *)ws.cwords.p, (uint32_t *)ws.cmask.p, C, ctg_woff[C]};
+    ts = bs::SeqSet{d_tchars, d_tr_off, d_tr_woff, (uint64_t *)ws.twords.p, (uint32_t *)ws.tmask.p, S, tr_woff[S]};
+    rs = bs::ReadSet{d_rchars, d_roff, e.rlen, W, N, (uint64_t *)ws.rwords.p, (uint8_t *)ws.rflags.p};
     std::memset(&ix, 0, sizeof(ix));
     if (!tile_mode) {
         ix.head = (uint32_t *)ws.head.p; ix.next = (uint2 *)ws.next.p; ix.odd_head = (uint32_t *)ws.odd_head.p;
         ix.tab_off = d_tab_off; ix.tab_mask = d_tab_mask; ix.seed_len = d_seed; ix.seg_read_start = d_seg_rs; ix.n_seg = (int32_t)S;
     }
+    return BS_OK;
+}
+
+int ChunkRun::pack() {
     {
         StageTimer tm(ctx, ST_PACK, st);
         BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
@@ -627,6 +666,10 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             ctx->launches++;
         }
     }
+    return BS_OK;
+}
+
+int ChunkRun::place() {
     {
         StageTimer tm(ctx, ST_PLACE, st);
         if (N > 0 && C > 0 && !tile_mode) {
@@ -655,7 +698,7 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             BS_CUDA(cudaFuncSetAttribute(bs::k_place_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads)));
             BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads), st, pa);
             ctx->launches++;
-        } else if (N > 0 && !items.empty()) {
+        } else if (N > 0 && n_items > 0) {
             bs::PlaceArgs pa;
             pa.items = d_items;
             pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff;
@@ -667,10 +710,14 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             pa.tile_len = tile_len; pa.hash_size = hash_size; pa.found_words = found_words;
             pa.scan_mode = (e.flags & BS_PLACE_SCAN) ? 1 : 0;
             BS_CUDA(cudaFuncSetAttribute(bs::k_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)place_smem));
-            BS_LAUNCH(bs::k_place, (unsigned)items.size(), kPlaceThreads, place_smem, st, pa);
+            BS_LAUNCH(bs::k_place, (unsigned)n_items, kPlaceThreads, place_smem, st, pa);
             ctx->launches++;
         }
     }
+    return BS_OK;
+}
+
+int ChunkRun::spectrum() {
     if (e.want_ks) {
         const KsCache &k = ctx->ks;
         const int R_y = std::max(k.R_y, 1);
@@ -703,6 +750,10 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
             }
         }
     }
+    return BS_OK;
+}
+
+int ChunkRun::score() {
     {
         // scores (+ histogram, + KS of the normalised break histogram); after the truth spectrum
         StageTimer tm(ctx, ST_SCORE, st);
@@ -731,11 +782,15 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         BS_LAUNCH(bs::k_break_score, (unsigned)nblk, kScoreThreads, 0, st, sa);
         ctx->launches++;
     }
+    return BS_OK;
+}
+
+int ChunkRun::prob_dist() {
     if (e.want_pd || ks_a) {
         StageTimer tm(ctx, ST_PROBDIST, st);
         const KsCache &k = ctx->ks;
         bs::ProbDistArgs pa;
-        pa.order = d_order2; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
+        pa.order = d_order; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
         pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
         pa.ctg_seg = d_ctg_seg;
         pa.win = (kmer >= 1 && kmer <= bs::MAXK) ? (const bs::WinEntry *)k.win.p : nullptr;
@@ -771,6 +826,10 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
         ctx->launches++;
     }
+    return BS_OK;
+}
+
+int ChunkRun::startpos() {
     if (e.want_sp || e.want_lev) {
         StageTimer tm(ctx, ST_STARTPOS, st);
         BS_TRY(ensure(ctx, ws.spbest, (size_t)C * 4));
@@ -792,6 +851,10 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kStartposThreads, 0, st, sa);
         ctx->launches++;
     }
+    return BS_OK;
+}
+
+int ChunkRun::lev() {
     if (e.want_lev) {
         // infix edit distance contig vs truth: one warp per contig, longest first
         StageTimer tm(ctx, ST_LEV, st);
@@ -816,6 +879,10 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
         BS_LAUNCH(bs::k_lev_infix, (unsigned)nblk, kLevThreads, 0, st, la);
         ctx->launches++;
     }
+    return BS_OK;
+}
+
+int ChunkRun::results() {
     BS_CUDA(cudaGetLastError());
     BS_CUDA(cudaEventRecord(ws.ev_compute, st));
 
@@ -852,6 +919,20 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     BS_CUDA(cudaEventRecord(ws.ev_d2h, ctx->out_stream));
     ws.in_flight = true;
     return BS_OK;
+}
+
+// ---- one chunk: metadata, H2D, kernels, D2H --------------------------------------------------
+int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
+    ChunkRun r(ctx, ws, e, ch);
+    BS_TRY(r.prepare());
+    BS_TRY(r.pack());
+    BS_TRY(r.place());
+    BS_TRY(r.spectrum());
+    BS_TRY(r.score());
+    BS_TRY(r.prob_dist());
+    BS_TRY(r.startpos());
+    BS_TRY(r.lev());
+    return r.results();
 }
 
 }  // namespace
