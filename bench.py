@@ -413,6 +413,48 @@ def b200_main(args):
     same = bool(torch.equal(d_f64.cpu().nan_to_num(nan=-1.0), h_f64.nan_to_num(nan=-1.0)) and
                 torch.equal(d_i32[:3].cpu(), h_i32[:3]))
 
+    # ---- the step before the path on the device too: truths and contigs cross PCIe,
+    # the reads are simulated on the device (upstream's sampling law) and scored where they are ----
+    study = None
+    if not args.no_study:
+        cap = int(sc._lib.bs_simulate_capacity(batch.truth_off.ctypes.data, S, READ_LEN, COVERAGE))
+        d_sim = torch.empty(max(cap, 1), dtype=torch.uint8, device=dev)
+        srs = np.zeros(S + 1, np.int64)
+        d_tr2 = torch.empty_like(d_truth)
+        d_ct2 = torch.empty_like(d_ctgs)
+
+        def step_study():
+            d_tr2.copy_(h_truth, non_blocking=True)
+            d_ct2.copy_(h_ctgs, non_blocking=True)
+            sc._check(sc._lib.bs_simulate_reads(sc._ctx, d_tr2.data_ptr(), batch.truth_off.ctypes.data, S, READ_LEN, COVERAGE, 8,
+                                                SEED + rank, B.DEVICE_CHARS | B.DEVICE_RESULT, d_sim.data_ptr(), cap, srs.ctypes.data))
+            sb = B._Batch(S, int(srs[-1]), Cn, d_sim.data_ptr(), None, READ_LEN, d_ct2.data_ptr(), batch.contig_off.ctypes.data,
+                          d_tr2.data_ptr(), batch.truth_off.ctypes.data, srs.ctypes.data, batch.seg_contig_start.ctypes.data)
+            sc.score_batch_raw(sb, hr, 8, flags | B.DEVICE_CHARS)  # results land in the pinned host arrays
+
+        step_study()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_study()
+        torch.cuda.synchronize()
+        st_s = time.perf_counter() - t0
+        n_s = np.diff(srs).astype(np.float64)
+        l_s = np.add.reduceat(np.diff(batch.contig_off), batch.seg_contig_start[:-1]).astype(np.float64) if Cn else np.zeros(S)
+        l_s[np.diff(batch.seg_contig_start) == 0] = 0.0
+        t_st = torch.tensor([st_s, float((n_s * l_s).sum()), float(n_s.sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t_st[:1].clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_st, op=dist.ReduceOp.SUM)
+            t_st[0] = tmax[0]
+        study = {"value": float(t_st[1]) / 1e9 / (float(t_st[0]) / args.steps), "unit": UNIT,
+                 "ms_per_step": 1e3 * float(t_st[0]) / args.steps, "reads_per_step": float(t_st[2]),
+                 "h2d_bytes_per_step": int(h_truth.numel() + h_ctgs.numel()), "d2h_bytes_per_step": d2h,
+                 "what": "bs_simulate_reads (upstream's sampling law, device RNG) + bs_score_batch on the device-resident reads; "
+                         "only truths and contigs are copied in, every result array is copied out"}
+
     # ---- roofline: the placement kernel (north_star's hot kernel), every other stage beside it ----
     peak, peak_src = measured_peak()
     uniq = unique_reads_per_segment(batch)
@@ -476,6 +518,8 @@ def b200_main(args):
                     "stage_ms_untimed_extra_step": e2e_stage_ms},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         }
+        if study:
+            line["study_with_device_simulated_reads"] = study
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
@@ -493,6 +537,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--segments", type=int, default=1000, help="segments per GPU (cfg-2 study size: 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-study", action="store_true", help="skip the extra simulate-on-device measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)

@@ -40,7 +40,7 @@ ABI_SYMBOLS = (
     "bs_ctx_synchronize", "bs_ctx_launch_count", "bs_ctx_enable_timing", "bs_ctx_last_timings",
     "bs_ctx_last_place_ms", "bs_set_table", "bs_set_truth_table", "bs_score_batch", "bs_score",
     "bs_host_alloc", "bs_host_free", "bs_assemble_contigs", "bs_assemble_last_error", "bs_string_list_size",
-    "bs_string_list_bytes", "bs_string_list_copy", "bs_string_list_free",
+    "bs_string_list_bytes", "bs_string_list_copy", "bs_string_list_free", "bs_simulate_capacity", "bs_simulate_reads",
 )
 
 _i64p = C.POINTER(C.c_int64)
@@ -130,6 +130,11 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_string_list_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bs_string_list_free.restype = None
     lib.bs_string_list_free.argtypes = [C.c_void_p]
+    lib.bs_simulate_capacity.restype = C.c_int64
+    lib.bs_simulate_capacity.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double]
+    lib.bs_simulate_reads.restype = C.c_int
+    lib.bs_simulate_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int,
+                                      C.c_uint64, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p]
     if lib.bs_abi_version() != 1:
         raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 1")
     return lib
@@ -232,6 +237,22 @@ class BreakageScorer:
             self._check(self._lib.bs_set_truth_table(self._ctx, _ptr(t), len(t)))
         else:
             self._check(self._lib.bs_set_truth_table(self._ctx, None, 0))
+
+    # -- read simulation ------------------------------------------------------------------
+    def simulate_reads(self, truths, read_len, coverage, seed=1234, kmer=8):
+        """Reads of `read_len` bases sampled from every truth with upstream's law
+        (lib/GenerateReads.R:302-313: starts drawn with replacement proportional to the table probability
+        of the kmer-window, ceil(coverage * L / read_len) draws, overrunning draws dropped).
+        Returns (uint8 [N, read_len], int64 seg_read_start[S+1]).  Uses the scoring table of the context."""
+        tr, tr_off = flatten(truths)
+        S = len(tr_off) - 1
+        cap = int(self._lib.bs_simulate_capacity(_ptr(tr_off), S, int(read_len), float(coverage)))
+        reads = np.zeros(max(cap, 1), np.uint8)
+        srs = np.zeros(S + 1, np.int64)
+        self._check(self._lib.bs_simulate_reads(self._ctx, _ptr(tr), _ptr(tr_off), S, int(read_len), float(coverage), int(kmer),
+                                                int(seed) & 0xFFFFFFFFFFFFFFFF, 0, _ptr(reads), cap, _ptr(srs)))
+        n = int(srs[-1])
+        return reads[:n * read_len].reshape(n, read_len), srs
 
     # -- scoring -------------------------------------------------------------------------
     def score_batch(self, read_chars, read_off, read_len, contig_chars, contig_off, truth_chars,

@@ -33,6 +33,7 @@ constexpr int kPlaceThreads = 64;
 constexpr int kScoreThreads = 64;
 constexpr int kStartposThreads = 64;
 constexpr int kLevThreads = 64;
+constexpr int kSimThreads = 64;
 constexpr int kKsThreads = 64;
 constexpr int kSpectrumThreads = 64;
 constexpr int kPackThreads = 64;
@@ -42,6 +43,7 @@ constexpr int kPlaceThreads = 256;
 constexpr int kScoreThreads = 256;
 constexpr int kStartposThreads = 256;
 constexpr int kLevThreads = 128;
+constexpr int kSimThreads = 256;
 constexpr int kKsThreads = 768;     // one sweep round covers the 515 ranges of the real table's rank histogram
 constexpr int kSpectrumThreads = 512;
 constexpr int kPackThreads = 256;
@@ -122,6 +124,7 @@ struct bs_ctx {
     Workspace ws[kWorkspaces];
     // scratch shared by all chunks (kernels of different chunks never overlap: one compute stream)
     DevBuf d_best, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
+    DevBuf sim_meta, sim_chars, sim_words, sim_mask, sim_cdf, sim_starts, sim_kept, sim_reads;  // bs_simulate_reads
     size_t best_elems = 0;
     bool best_dirty = true;
 
@@ -993,7 +996,8 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf *bufs[] = {&ctx->d_tab, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
-                      &ctx->d_rank_scratch, &ctx->d_counters, &ctx->d_hbuf};
+                      &ctx->d_rank_scratch, &ctx->d_counters, &ctx->d_hbuf, &ctx->sim_meta, &ctx->sim_chars,
+                      &ctx->sim_words, &ctx->sim_mask, &ctx->sim_cdf, &ctx->sim_starts, &ctx->sim_kept, &ctx->sim_reads};
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
@@ -1259,6 +1263,101 @@ int bs_score(bs_ctx *ctx, const char *contig_chars, const int64_t *contig_off, i
     b.seg_read_start = seg_r; b.seg_contig_start = seg_c;
     if (!read_off && n_reads > 0) return fail(ctx, BS_ERR_INVALID, "bs_score: read_off is NULL");
     return bs_score_batch(ctx, &b, kmer, flags, result);
+}
+
+int64_t bs_simulate_capacity(const int64_t *truth_off, int64_t n_segments, int32_t read_len, double coverage) {
+    if (!truth_off || n_segments < 0 || read_len < 1 || !(coverage >= 0.0)) return -1;
+    int64_t draws = 0;
+    for (int64_t s = 0; s < n_segments; s++) {
+        const int64_t L = truth_off[s + 1] - truth_off[s];
+        draws += (int64_t)std::ceil(coverage * (double)L / (double)read_len);  // lib/GenerateReads.R:302
+    }
+    return draws * (int64_t)read_len;
+}
+
+int bs_simulate_reads(bs_ctx *ctx, const char *truth_chars, const int64_t *truth_off, int64_t n_segments, int32_t read_len,
+                      double coverage, int kmer, uint64_t seed, uint32_t flags, char *reads_out, int64_t reads_capacity,
+                      int64_t *seg_read_start) {
+    if (!ctx) return BS_ERR_INVALID;
+    if (!ctx->has_table) return fail(ctx, BS_ERR_STATE, "bs_simulate_reads before bs_set_table");
+    if (!truth_off || !seg_read_start || n_segments < 0) return fail(ctx, BS_ERR_INVALID, "bs_simulate_reads: NULL argument");
+    if (read_len < 1 || !(coverage >= 0.0)) return fail(ctx, BS_ERR_INVALID, "read_len must be >= 1 and coverage >= 0");
+    if (kmer < 1 || kmer > bs::MAXK) return fail(ctx, BS_ERR_INVALID, "kmer must be 1..8 (got %d)", kmer);
+    const int64_t S = n_segments;
+    BS_TRY(check_offsets(ctx, "truth", truth_off, S));
+    seg_read_start[0] = 0;
+    if (S == 0) return BS_OK;
+    const int64_t tr_bytes = truth_off[S] - truth_off[0];
+    if (tr_bytes > 0 && !truth_chars) return fail(ctx, BS_ERR_INVALID, "truth_chars is NULL");
+    std::vector<int64_t> tr_off(S + 1), tr_woff(S + 1), draw_off(S + 1);
+    tr_woff[0] = 0;
+    draw_off[0] = 0;
+    for (int64_t s = 0; s <= S; s++) tr_off[s] = truth_off[s] - truth_off[0];
+    for (int64_t s = 0; s < S; s++) {
+        const int64_t L = tr_off[s + 1] - tr_off[s];
+        if (L > 0x7f000000ll) return fail(ctx, BS_ERR_INVALID, "truth %lld longer than 2^31", (long long)s);
+        tr_woff[s + 1] = tr_woff[s] + (L + 31) / 32 + 2;
+        draw_off[s + 1] = draw_off[s] + (int64_t)std::ceil(coverage * (double)L / (double)read_len);
+    }
+    const int64_t n_draws = draw_off[S];
+    if (n_draws * (int64_t)read_len > reads_capacity)
+        return fail(ctx, BS_ERR_INVALID, "reads_out holds %lld bytes, %lld needed (bs_simulate_capacity)", (long long)reads_capacity,
+                    (long long)(n_draws * (int64_t)read_len));
+    if (n_draws > 0 && !reads_out) return fail(ctx, BS_ERR_INVALID, "reads_out is NULL");
+    cudaSetDevice(ctx->device);
+    BS_TRY(prepare_ks(ctx, kmer));
+    cudaStream_t st = ctx->stream;
+    const bool dev_chars = (flags & BS_DEVICE_CHARS) != 0, dev_out = (flags & BS_DEVICE_RESULT) != 0;
+
+    MetaBuilder mb;
+    const size_t o_tr_off = mb.add(tr_off.data(), (size_t)S + 1);
+    const size_t o_tr_woff = mb.add(tr_woff.data(), (size_t)S + 1);
+    const size_t o_draw_off = mb.add(draw_off.data(), (size_t)S + 1);
+    const size_t o_srs = mb.add(draw_off.data(), (size_t)S + 1);  // placeholder, rewritten below
+    BS_TRY(ensure(ctx, ctx->sim_meta, mb.bytes.size()));
+    if (!dev_chars) BS_TRY(ensure(ctx, ctx->sim_chars, (size_t)tr_bytes + 32));
+    BS_TRY(ensure(ctx, ctx->sim_words, (size_t)tr_woff[S] * 8 + 8));
+    BS_TRY(ensure(ctx, ctx->sim_mask, (size_t)tr_woff[S] * 4 + 8));
+    BS_TRY(ensure(ctx, ctx->sim_cdf, (size_t)std::max<int64_t>(tr_bytes, 1) * 8));
+    BS_TRY(ensure(ctx, ctx->sim_starts, (size_t)std::max<int64_t>(n_draws, 1) * 4));
+    BS_TRY(ensure(ctx, ctx->sim_kept, (size_t)S * 4));
+    if (!dev_out) BS_TRY(ensure(ctx, ctx->sim_reads, (size_t)std::max<int64_t>(n_draws * read_len, 1)));
+    BS_CUDA(cudaMemcpyAsync(ctx->sim_meta.p, mb.bytes.data(), mb.bytes.size(), cudaMemcpyHostToDevice, st));
+    const uint8_t *d_tchars = (const uint8_t *)truth_chars + truth_off[0];
+    if (!dev_chars) {
+        if (tr_bytes) BS_CUDA(cudaMemcpyAsync(ctx->sim_chars.p, truth_chars + truth_off[0], (size_t)tr_bytes, cudaMemcpyHostToDevice, st));
+        d_tchars = (const uint8_t *)ctx->sim_chars.p;
+    }
+    BS_CUDA(cudaStreamSynchronize(st));  // mb.bytes is pageable and reused below
+    unsigned char *dm = (unsigned char *)ctx->sim_meta.p;
+    const int grid_cap = ctx->sm_count * 32;
+    bs::SeqSet ts{d_tchars, (const int64_t *)(dm + o_tr_off), (const int64_t *)(dm + o_tr_woff), (uint64_t *)ctx->sim_words.p,
+                  (uint32_t *)ctx->sim_mask.p, S, tr_woff[S]};
+    bs::SimArgs sa;
+    sa.tr_off = ts.off; sa.tr_woff = ts.woff; sa.tr_words = ts.words; sa.tr_mask = ts.mask; sa.tr_chars = d_tchars;
+    sa.win = (const bs::WinEntry *)ctx->ks.win.p; sa.kmer = kmer; sa.read_len = read_len; sa.n_seg = S; sa.seg_base = 0; sa.seed = seed;
+    sa.draw_off = (const int64_t *)(dm + o_draw_off); sa.cdf = (double *)ctx->sim_cdf.p; sa.starts = (int32_t *)ctx->sim_starts.p;
+    sa.kept = (int32_t *)ctx->sim_kept.p; sa.seg_read_start = (const int64_t *)(dm + o_srs);
+    sa.reads = dev_out ? (uint8_t *)reads_out : (uint8_t *)ctx->sim_reads.p;
+    BS_LAUNCH(bs::k_pack_seqs, grid_for(ts.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, ts);
+    BS_LAUNCH(bs::k_sim_cdf, (unsigned)S, kSimThreads, 0, st, sa);
+    if (n_draws > 0) BS_LAUNCH(bs::k_sim_draw, grid_for(n_draws, kSimThreads, grid_cap), kSimThreads, 0, st, sa);
+    BS_LAUNCH(bs::k_sim_compact, (unsigned)S, kSimThreads, 0, st, sa);
+    ctx->launches += 3 + (n_draws > 0 ? 1 : 0);
+    std::vector<int32_t> kept((size_t)S);
+    BS_CUDA(cudaMemcpyAsync(kept.data(), ctx->sim_kept.p, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+    BS_CUDA(cudaStreamSynchronize(st));
+    for (int64_t s = 0; s < S; s++) seg_read_start[s + 1] = seg_read_start[s] + kept[(size_t)s];
+    const int64_t n_reads = seg_read_start[S];
+    BS_CUDA(cudaMemcpyAsync(dm + o_srs, seg_read_start, (size_t)(S + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_reads > 0) {
+        BS_LAUNCH(bs::k_sim_emit, grid_for(n_reads * 32, kSimThreads, grid_cap), kSimThreads, 0, st, sa);
+        ctx->launches++;
+        if (!dev_out) BS_CUDA(cudaMemcpyAsync(reads_out, ctx->sim_reads.p, (size_t)(n_reads * read_len), cudaMemcpyDeviceToHost, st));
+    }
+    BS_CUDA(cudaGetLastError());
+    BS_CUDA(cudaStreamSynchronize(st));  // seg_read_start is the caller's (pageable) array; results are complete on return
+    return BS_OK;
 }
 
 }  // extern "C"

@@ -12,3 +12,4 @@
 #include "bs_ks.cuh"        // truth spectrum, path_prob_dist, KS-A
 #include "bs_startpos.cuh"  // contig-in-truth offset
 #include "bs_lev.cuh"       // infix edit distance (lev_dist_vs_true)
+#include "bs_simulate.cuh"  // read simulation (the step before the scorer)

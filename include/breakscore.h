@@ -17,6 +17,7 @@
  * ks.test statistic, lib/DeNovoAssembler.R:416-424    | BS_WANT_KS outputs of the same calls
  * Rcpp::stop / R error                                | int status + bs_last_error
  * assemble_contigs, lib/BreakageScorer.cpp:79-174     | bs_assemble_contigs (host; candidate generator)
+ * generate_sequencing_reads, lib/GenerateReads.R:234-379 | bs_simulate_reads (device; the step before the scorer)
  */
 #ifndef BREAKSCORE_H
 #define BREAKSCORE_H
@@ -160,6 +161,22 @@ BS_API int64_t bs_string_list_size(const bs_string_list *l);
 BS_API int64_t bs_string_list_bytes(const bs_string_list *l);
 BS_API void bs_string_list_copy(const bs_string_list *l, char *chars, int64_t *off);
 BS_API void bs_string_list_free(bs_string_list *l);
+
+/*
+ * Read simulation on the device (upstream lib/GenerateReads.R:243-259,302-313,368-379): for every
+ * truth, ceil(coverage * L / read_len) start positions drawn with replacement with probability
+ * proportional to the scoring table's probability of the kmer-window starting there; draws whose
+ * read would overrun the truth are dropped; reads are the substrings (read_len bytes each, dense,
+ * segment after segment).  seg_read_start (HOST, [n_segments+1]) receives the read ranges.
+ * flags: BS_DEVICE_CHARS = truth_chars is a device pointer, BS_DEVICE_RESULT = reads_out is a device
+ * pointer (so the reads can go straight into bs_score_batch without crossing PCIe).  The random
+ * stream is this library's (seeded, reproducible), not R's: the law is upstream's, the sample is not.
+ * bs_simulate_capacity returns the bytes reads_out must hold (the no-drop upper bound).
+ */
+BS_API int64_t bs_simulate_capacity(const int64_t *truth_off, int64_t n_segments, int32_t read_len, double coverage);
+BS_API int bs_simulate_reads(bs_ctx *ctx, const char *truth_chars, const int64_t *truth_off, int64_t n_segments,
+                             int32_t read_len, double coverage, int kmer, uint64_t seed, uint32_t flags,
+                             char *reads_out, int64_t reads_capacity, int64_t *seg_read_start);
 
 /* pinned host memory for staging buffers (cudaHostAlloc / cudaFreeHost) */
 BS_API void *bs_host_alloc(int64_t bytes);
