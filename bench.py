@@ -502,6 +502,29 @@ def b200_main(args):
                 "efficiency (it is L2-latency and issue bound); 'traffic' = ncu DRAM bytes per launch.",
     }
 
+    # ---- for the record: north_star's all-pairs kernel (BS_PLACE_SCAN) on a sample of the workload ----
+    scan = None
+    if rank == 0 and args.scan_segments > 0:
+        ns = min(args.scan_segments, S)
+        r1, c1 = int(batch.seg_read_start[ns]), int(batch.seg_contig_start[ns])
+        sb = B._Batch(ns, r1, c1, d_reads.data_ptr(), None, batch.read_len, d_ctgs.data_ptr(), batch.contig_off.ctypes.data,
+                      d_truth.data_ptr(), batch.truth_off.ctypes.data, batch.seg_read_start.ctypes.data,
+                      batch.seg_contig_start.ctypes.data)
+        scan_ms = {}
+        for name, fl in (("all_pairs_scan", B.PLACE_SCAN), ("contig_tile_index", B.PLACE_TILE), ("read_index", 0)):
+            sc.score_batch_raw(sb, dr, 8, B.DEVICE_CHARS | B.DEVICE_RESULT | fl)
+            sc.enable_timing(True)
+            sc.score_batch_raw(sb, dr, 8, B.DEVICE_CHARS | B.DEVICE_RESULT | fl)
+            scan_ms[name] = sc.last_timings()["place"]
+            sc.enable_timing(False)
+        sample_bytes = float((uniq[:ns] * np.diff(batch.seg_contig_start)[:ns]).sum()) * (8 * W + 4)
+        scan = {"sample_segments": ns, "algorithmic_bytes": sample_bytes,
+                "place_ms": scan_ms,
+                "achieved_GBps": {k: sample_bytes / (v / 1e3) / 1e9 for k, v in scan_ms.items() if v > 0},
+                "frac_of_peak": {k: sample_bytes / (v / 1e3) / 1e9 / peak for k, v in scan_ms.items() if v > 0},
+                "note": "same SURVEY 8(d) algorithmic bytes for the three placement kernels on the first segments of the "
+                        "workload: the all-pairs scan is what north_star describes (every read against every contig position)"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -520,6 +543,8 @@ def b200_main(args):
         }
         if study:
             line["study_with_device_simulated_reads"] = study
+        if scan:
+            line["placement_variants"] = scan
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
@@ -538,6 +563,7 @@ def main():
     ap.add_argument("--segments", type=int, default=1000, help="segments per GPU (cfg-2 study size: 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-study", action="store_true", help="skip the extra simulate-on-device measurement")
+    ap.add_argument("--scan-segments", type=int, default=20, help="segments timed with the all-pairs / tile placement kernels (0: skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
