@@ -399,6 +399,16 @@ def b200_main(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    # the floor of the end-to-end number on this box: the same input bytes through one plain pinned H2D copy
+    d_probe = torch.empty_like(d_reads)
+    d_probe.copy_(h_reads, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d_probe.copy_(h_reads, non_blocking=True)
+    torch.cuda.synchronize()
+    pcie_s = time.perf_counter() - t0
+    pcie_gbps = h_reads.numel() / pcie_s / 1e9
+    del d_probe
     # one more (untimed) host-buffer step with stage events on, to show where the end-to-end time goes
     sc.enable_timing(True)
     step_host()
@@ -538,7 +548,8 @@ def b200_main(args):
                        "cpu_affinity": affinity},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "matches_device_resident_run": same,
-                    "stage_ms_untimed_extra_step": e2e_stage_ms},
+                    "stage_ms_untimed_extra_step": e2e_stage_ms,
+                    "plain_pinned_h2d_GBps": pcie_gbps, "h2d_floor_ms": 1e3 * h2d / (pcie_gbps * 1e9)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         }
         if study:

@@ -249,3 +249,32 @@ def test_edit_distance_indels_and_long_contigs(gpu_scorer, oracle, kmers, prob):
     reads = [truth[i:i + 100] for i in range(0, 19000, 97)]
     got, want = P.check_segment(gpu_scorer, oracle, kmers, prob, seg, reads=reads, flags=B.DEFAULT_FLAGS | B.WANT_LEV)
     assert got["lev_dist_vs_true"].tolist()[:3] == [1, 10, 8] and got["lev_dist_vs_true"][5] == 0
+
+
+def test_cfg2_full_study_properties(gpu_scorer, kmers, prob):
+    """BASELINE.json configs[1] at full size (1000 segments, ~1e7 reads, ~3e4 contigs): the integer
+    checksum table gives integer scores and the same break counts as the real table; scoring the study
+    in one call, in two halves or in many pipeline chunks is bit-identical; lengths and offsets agree
+    with the inputs."""
+    b = synth.make_batch(1000, seed=1234, length=50000, read_len=150, coverage=30)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+            b.seg_read_start, b.seg_contig_start)
+    T = len(prob)
+    gpu_scorer.set_table(kmers, np.arange(1, T + 1, dtype=np.float64))
+    chk = gpu_scorer.score_batch(*args, flags=B.WANT_STARTPOS)
+    assert np.array_equal(chk["bp_score"], np.round(chk["bp_score"])) and chk["bp_score"].max() < 2.0 ** 53
+    assert np.array_equal(chk["sequence_len"], np.diff(b.contig_off))
+    gpu_scorer.set_table(kmers, prob)
+    whole = gpu_scorer.score_batch(*args, flags=B.WANT_KS | B.WANT_STARTPOS)
+    assert np.array_equal(whole["kmer_breaks"], chk["kmer_breaks"])
+    assert np.array_equal(whole["path_prob_dist_startpos"], chk["path_prob_dist_startpos"])
+    assert whole["kmer_breaks"].sum() > 0.8 * b.n_reads   # almost every read lands in exactly one contig of its segment
+    # exact substrings report their cut position, mutated contigs -1 (make_segment's bookkeeping)
+    assert (whole["path_prob_dist_startpos"] >= -1).all()
+    from genomeassembler_dev_b200 import sharding
+    keys = ("bp_score", "bp_score_norm_by_break_freqs", "kmer_breaks", "ks_stat_prob_dist", "ks_stat_path_freq", "path_prob_dist_startpos")
+    for s0, s1 in sharding.shard_segments(b.seg_read_start, b.seg_contig_start, b.contig_off, 2):
+        part = gpu_scorer.score_batch(*sharding.slice_batch(b, s0, s1), flags=B.WANT_KS | B.WANT_STARTPOS)
+        c0, c1 = int(b.seg_contig_start[s0]), int(b.seg_contig_start[s1])
+        for k in keys:
+            assert np.array_equal(part[k], whole[k][c0:c1], equal_nan=True), k
