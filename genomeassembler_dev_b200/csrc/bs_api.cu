@@ -53,7 +53,7 @@ constexpr int kMaxTile = 8192;        // contig positions per shared-memory tile
 constexpr int64_t kMaxChunk = 32768;  // reads per placement work item (tile placement modes)
 constexpr int64_t kMinChunk = 2048;
 constexpr int kHitCap = 4096;         // reads placed per contig kept in shared memory (k_place_index)
-constexpr int kWorkspaces = 2;
+constexpr int kWorkspaces = 3;  // chunks in flight: one copying in, one computing, one copying out
 
 enum Stage { ST_H2D, ST_PACK, ST_PLACE, ST_SCORE, ST_SPECTRUM, ST_PROBDIST, ST_PATHFREQ, ST_STARTPOS, ST_D2H, ST_LEV, ST_COUNT };
 
@@ -122,6 +122,7 @@ struct bs_ctx {
     KsCache ks;
 
     Workspace ws[kWorkspaces];
+    unsigned ws_cursor = 0;  // workspaces rotate across calls too: an asynchronous (device-result) call may still own one
     // scratch shared by all chunks (kernels of different chunks never overlap: one compute stream)
     DevBuf d_best, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
     DevBuf sim_meta, sim_chars, sim_words, sim_mask, sim_cdf, sim_starts, sim_kept, sim_reads;  // bs_simulate_reads
@@ -1205,7 +1206,10 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     }
 
     // ---------------- chunks of whole segments ----------------
-    const int64_t target = e.dev_chars ? ctx->chunk_bytes_dev : ctx->chunk_bytes_host;
+    // inputs on the device but results going home: medium chunks, so that the D2H of one chunk hides
+    // behind the kernels of the next
+    const int64_t target = !e.dev_chars ? ctx->chunk_bytes_host
+                           : (e.dev_res ? ctx->chunk_bytes_dev : std::min<int64_t>(ctx->chunk_bytes_dev, (int64_t)384 << 20));
     std::vector<Chunk> chunks;
     {
         int64_t s0 = 0, bytes = 0;
@@ -1223,16 +1227,14 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
         }
         chunks.push_back({s0, S, b->seg_read_start[s0], b->seg_read_start[S], b->seg_contig_start[s0], b->seg_contig_start[S]});
     }
-    int k = 0;
     for (const Chunk &ch : chunks) {
         if (ch.c1 == ch.c0) continue;  // segments without contigs produce nothing
-        BS_TRY(run_chunk(ctx, ctx->ws[k % kWorkspaces], e, ch));
-        k++;
+        BS_TRY(run_chunk(ctx, ctx->ws[ctx->ws_cursor++ % kWorkspaces], e, ch));
     }
     if (e.dev_res) {
-        // asynchronous: the caller orders later work on the compute stream.  Workspaces are reused
-        // in stream order by the next call, so nothing has to be awaited here.
-        for (Workspace &w : ctx->ws) w.in_flight = false;
+        // asynchronous: the caller orders later work on the compute stream.  The workspaces stay marked
+        // in flight: whoever takes one next (this call's successor included) first waits for the event
+        // recorded behind its last kernel, so staging memory is never rewritten under a running chunk.
         ctx->best_dirty = false;
         return BS_OK;
     }

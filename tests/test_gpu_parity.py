@@ -278,3 +278,42 @@ def test_cfg2_full_study_properties(gpu_scorer, kmers, prob):
         c0, c1 = int(b.seg_contig_start[s0]), int(b.seg_contig_start[s1])
         for k in keys:
             assert np.array_equal(part[k], whole[k][c0:c1], equal_nan=True), k
+
+
+def test_async_device_resident_calls_reuse_workspaces(product_lib, kmers, prob, monkeypatch):
+    """BS_DEVICE_CHARS | BS_DEVICE_RESULT calls return before their kernels finish; back-to-back calls
+    over many small chunks must not rewrite a workspace that a running chunk still reads."""
+    import torch
+    b1 = synth.make_batch(30, seed=300, length=20000, read_len=100, coverage=20, contigs_lo=2, contigs_hi=10)
+    b2 = synth.make_batch(30, seed=900, length=20000, read_len=100, coverage=20, contigs_lo=2, contigs_hi=10)
+    monkeypatch.setenv("BS_CHUNK_KB", "2000")
+    with B.BreakageScorer(0, product_lib) as sc:
+        sc.set_table(kmers, prob)
+        stream = torch.cuda.Stream()
+        sc.set_stream(stream.cuda_stream)
+        outs = []
+        with torch.cuda.stream(stream):
+            for rep in range(3):
+                for b in (b1, b2):
+                    dev = [torch.from_numpy(x).cuda() for x in (b.read_chars, b.contig_chars, b.truth_chars)]
+                    Cn = b.n_contigs
+                    i32 = torch.zeros(4, Cn, dtype=torch.int32, device="cuda")
+                    f64 = torch.zeros(5, Cn, dtype=torch.float64, device="cuda")
+                    bt = B._Batch(b.n_segments, b.n_reads, Cn, dev[0].data_ptr(), None, b.read_len, dev[1].data_ptr(),
+                                  b.contig_off.ctypes.data, dev[2].data_ptr(), b.truth_off.ctypes.data,
+                                  b.seg_read_start.ctypes.data, b.seg_contig_start.ctypes.data)
+                    r = B._Result()
+                    r.sequence_len, r.kmer_breaks, r.path_prob_dist_startpos, r.lev_dist_vs_true = [i32[i].data_ptr() for i in range(4)]
+                    (r.bp_score, r.bp_score_norm_by_break_freqs, r.bp_score_norm_by_len, r.ks_stat_prob_dist,
+                     r.ks_stat_path_freq) = [f64[i].data_ptr() for i in range(5)]
+                    sc.score_batch_raw(bt, r, 8, B.WANT_KS | B.WANT_STARTPOS | B.DEVICE_CHARS | B.DEVICE_RESULT)
+                    outs.append((b, dev, i32, f64))
+        sc.synchronize()
+        torch.cuda.synchronize()
+        for b, dev, i32, f64 in outs:
+            ref = sc.score_batch(b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+                                 b.seg_read_start, b.seg_contig_start, flags=B.WANT_KS | B.WANT_STARTPOS)
+            assert np.array_equal(i32[1].cpu().numpy(), ref["kmer_breaks"])
+            assert np.array_equal(i32[2].cpu().numpy(), ref["path_prob_dist_startpos"])
+            assert np.array_equal(f64[0].cpu().numpy(), ref["bp_score"])
+            assert np.array_equal(f64[3].cpu().numpy(), ref["ks_stat_prob_dist"], equal_nan=True)
