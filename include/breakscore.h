@@ -110,12 +110,16 @@ typedef struct {
     const int64_t *pos_off;                 /* HOST [C+1], required with BS_WANT_POS */
 } bs_result;
 
-/* context: owns the device, a stream, the resident tables and grow-only work buffers */
+/* context: owns the device, its streams, the resident tables and grow-only work buffers.
+ * A context is NOT thread-safe: one host thread at a time (R calls from its single main thread);
+ * use one context per thread / per GPU otherwise. */
 BS_API int bs_ctx_create(int device, bs_ctx **out);
 BS_API void bs_ctx_destroy(bs_ctx *ctx);
 /* last error text of ctx (or of the last failed bs_ctx_create when ctx == NULL) */
 BS_API const char *bs_last_error(const bs_ctx *ctx);
-/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL = the context's own stream */
+/* run the kernels on a caller-owned CUDA stream (cudaStream_t as void*); NULL = the context's own
+ * stream (so the legacy default stream, handle 0, cannot be selected: create a stream).  Copies of
+ * host inputs / results use two internal streams ordered against it by events. */
 BS_API int bs_ctx_set_stream(bs_ctx *ctx, void *cuda_stream);
 /* block until everything queued by this context has finished */
 BS_API int bs_ctx_synchronize(bs_ctx *ctx);
@@ -124,8 +128,9 @@ BS_API int64_t bs_ctx_launch_count(const bs_ctx *ctx);
 /* per-stage CUDA-event timing (off by default).  bs_ctx_last_timings blocks on the streams and
  * writes up to n stage times (ms, -1 = stage did not run), summed over every scoring call since
  * timing was enabled or last read (the read resets the sums), in the order
- * h2d, pack, place, score, truth_spectrum, prob_dist_ks, ks_path_freq, startpos, d2h, lev; returns
- * how many it wrote. */
+ * h2d, pack, place, score (includes the KS of the break histogram), truth_spectrum, prob_dist_ks,
+ * ks_path_freq (unused since it was merged into score: always -1), startpos, d2h, lev; returns how
+ * many it wrote. */
 #define BS_N_STAGES 10
 BS_API int bs_ctx_enable_timing(bs_ctx *ctx, int on);
 BS_API int bs_ctx_last_timings(bs_ctx *ctx, double *ms, int n);
