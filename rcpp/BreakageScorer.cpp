@@ -11,6 +11,7 @@
 // No CPU fallback: without a B200 the call stops with the library's error text.
 #include <Rcpp.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -151,6 +152,12 @@ Rcpp::List calc_breakscore(
         pd_off[c + 1] = pd_off[c] + (n > 0 ? n : 0);
     }
     std::vector<double> pd_flat((size_t)pd_off[C] + 1);
+    // optional (BREAKSCORE_PATH_FREQ=1): the per-row break frequencies that the drifted R driver expects
+    // under the name path_freq (lib/DeNovoAssembler.cpp:352,395-420); 69 904 doubles per contig, so off by default
+    const char *pf_env = std::getenv("BREAKSCORE_PATH_FREQ");
+    const bool want_path_freq = pf_env && pf_env[0] == '1';
+    const int64_t T = (int64_t)bp_prob.size();
+    std::vector<int32_t> hist(want_path_freq ? (size_t)(C * (T + 1)) : 0);
 
     bs_result r;
     std::memset(&r, 0, sizeof(r));
@@ -165,14 +172,26 @@ Rcpp::List calc_breakscore(
     r.ks_stat_path_freq = ks_b.data();
     r.path_prob_dist = pd_flat.data();
     r.path_prob_dist_off = pd_off.data();
+    if (want_path_freq) r.hist = hist.data();
     check(s, bs_score(s.ctx, ctg_chars, ctg_off.data(), C, read_chars, read_off.data(), (int64_t)sequencing_reads.size(),
-                      truth_chars, (int64_t)true_solution.size(), kmer, BS_DEFAULT_FLAGS | BS_WANT_LEV, &r));
+                      truth_chars, (int64_t)true_solution.size(), kmer, BS_DEFAULT_FLAGS | BS_WANT_LEV | (want_path_freq ? BS_WANT_HIST : 0u), &r));
 
     std::vector<std::vector<double>> path_prob_dist((size_t)C);
     for (int64_t c = 0; c < C; c++) path_prob_dist[c].assign(pd_flat.begin() + pd_off[c], pd_flat.begin() + pd_off[c + 1]);
 
+    // always C entries (R turns the list into a data.table: every member needs length C); empty unless asked for
+    std::vector<std::vector<double>> path_freq((size_t)C);
+    if (want_path_freq) {
+        for (int64_t c = 0; c < C; c++) {
+            path_freq[c].resize((size_t)T);
+            for (int64_t t = 0; t < T; t++)  // count / total_breaks; 0/0 = NaN like upstream when nothing was placed
+                path_freq[c][t] = (double)hist[(size_t)(c * (T + 1) + t)] / (double)kmer_breaks[c];
+        }
+    }
+
     // the upstream list (lib/BreakageScorer.cpp:343-353), input order, plus the KS statistics of
-    // lib/DeNovoAssembler.R:416-424 computed on the device
+    // lib/DeNovoAssembler.R:416-424 computed on the device, plus the member names the R driver written
+    // against lib/DeNovoAssembler.cpp looks for (path_freq_startpos; path_freq when asked for)
     return Rcpp::List::create(
         Rcpp::Named("sequence") = path,
         Rcpp::Named("sequence_len") = sequence_len,
@@ -184,5 +203,7 @@ Rcpp::List calc_breakscore(
         Rcpp::Named("path_prob_dist_startpos") = startpos,
         Rcpp::Named("path_prob_dist") = Rcpp::wrap(path_prob_dist),
         Rcpp::Named("ks_stat_prob_dist") = ks_a,
-        Rcpp::Named("ks_stat_path_freq") = ks_b);
+        Rcpp::Named("ks_stat_path_freq") = ks_b,
+        Rcpp::Named("path_freq_startpos") = startpos,
+        Rcpp::Named("path_freq") = Rcpp::wrap(path_freq));
 }
