@@ -1212,15 +1212,29 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
                            : (e.dev_res ? ctx->chunk_bytes_dev : std::min<int64_t>(ctx->chunk_bytes_dev, (int64_t)384 << 20));
     std::vector<Chunk> chunks;
     {
-        int64_t s0 = 0, bytes = 0;
+        auto seg_bytes_of = [&](int64_t s) {
+            return read_byte_begin(e, b->seg_read_start[s + 1]) - read_byte_begin(e, b->seg_read_start[s]) +
+                   (b->contig_off[b->seg_contig_start[s + 1]] - b->contig_off[b->seg_contig_start[s]]) +
+                   (b->truth_off[s + 1] - b->truth_off[s]);
+        };
+        int64_t total_bytes = 0;
+        for (int64_t s = 0; s < S; s++) total_bytes += seg_bytes_of(s);
+        // host inputs: small chunks at both ends of a long call (the first copy and the last kernels and
+        // result copy are the only parts of the pipeline that nothing overlaps), full-size ones between
+        const bool ramp = !e.dev_chars && total_bytes > 4 * target;
+        int64_t s0 = 0, bytes = 0, done = 0;
         for (int64_t s = 0; s < S; s++) {
-            const int64_t rb = read_byte_begin(e, b->seg_read_start[s + 1]) - read_byte_begin(e, b->seg_read_start[s]);
-            const int64_t cb = b->contig_off[b->seg_contig_start[s + 1]] - b->contig_off[b->seg_contig_start[s]];
-            const int64_t tb = b->truth_off[s + 1] - b->truth_off[s];
-            const int64_t seg_bytes = rb + cb + tb;
-            if (s > s0 && bytes + seg_bytes > target) {
+            const int64_t seg_bytes = seg_bytes_of(s);
+            int64_t limit = target;
+            if (ramp) {
+                const int64_t left = total_bytes - done;
+                if (done < target / 4 || left <= target / 2) limit = target / 4;
+                else if (done < target || left <= 3 * target / 2) limit = target / 2;
+            }
+            if (s > s0 && bytes + seg_bytes > limit) {
                 chunks.push_back({s0, s, b->seg_read_start[s0], b->seg_read_start[s], b->seg_contig_start[s0], b->seg_contig_start[s]});
                 s0 = s;
+                done += bytes;
                 bytes = 0;
             }
             bytes += seg_bytes;
