@@ -73,6 +73,8 @@ def edge_inputs():
         ("kmer4", [c, rep], [c[i:i + 8] for i in range(0, 12)], c, 4),
         ("kmer6", [c, rep], [c[i:i + 8] for i in range(0, 12)], c, 6),
         ("kmer2", [c], [c[i:i + 8] for i in range(0, 12)], c, 2),
+        ("kmer10_longer_than_any_row", [c, rep], [c[i:i + 8] for i in range(0, 12)], c, 10),
+        ("kmer40_longer_than_a_word", [c, rep], [c[i:i + 8] for i in range(0, 12)] + [rep[5:60]], c + rep, 40),
         ("kmer3_not_in_table", [c], [c[i:i + 8] for i in range(0, 12)], c, 3),
         ("contig_longer_than_truth", [c + c], [c[4:14]], c, 8),
         ("truth_shorter_than_kmer", [c], [c[4:14]], b"ACG", 8),
