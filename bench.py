@@ -516,6 +516,32 @@ def b200_main(args):
                 "efficiency (it is L2-latency and issue bound); 'traffic' = ncu DRAM bytes per launch.",
     }
 
+    # ---- both table passes of an experiment (real, then uniform) from ONE placement ----
+    two_pass = None
+    if rank == 0 and not args.no_study:
+        sc.set_second_table(tables.uniform(len(prob)))
+        d_f64b = torch.zeros(5, Cn, dtype=torch.float64, device=dev)
+        d_pd2 = torch.zeros_like(d_pd)
+        dr2 = make_result_struct([d_i32[i].data_ptr() for i in range(4)], [d_f64[i].data_ptr() for i in range(5)], d_pd.data_ptr())
+        (dr2.bp_score2, dr2.bp_score_norm_by_break_freqs2, dr2.bp_score_norm_by_len2, dr2.ks_stat_prob_dist2,
+         dr2.ks_stat_path_freq2) = [d_f64b[i].data_ptr() for i in range(5)]
+        dr2.path_prob_dist2 = d_pd2.data_ptr()
+        for _ in range(2):
+            sc.score_batch_raw(db, dr2, 8, dflags | B.WANT_SECOND_TABLE)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            sc.score_batch_raw(db, dr2, 8, dflags | B.WANT_SECOND_TABLE)
+        f1.record()
+        torch.cuda.synchronize()
+        both_ms = f0.elapsed_time(f1) / args.steps
+        two_pass = {"ms_per_step_both_tables_one_call": both_ms, "ms_per_step_one_table": ms_per_step,
+                    "vs_two_separate_calls": both_ms / (2 * ms_per_step),
+                    "what": "real table + uniform table (the R driver's two passes, lib/DeNovoAssembler.R:325-333) scored "
+                            "from one packing/placement/startpos; device-resident, rank 0"}
+        sc.set_second_table(None)
+
     # ---- for the record: north_star's all-pairs kernel (BS_PLACE_SCAN) on a sample of the workload ----
     scan = None
     if rank == 0 and args.scan_segments > 0:
@@ -560,6 +586,8 @@ def b200_main(args):
             line["study_with_device_simulated_reads"] = study
         if scan:
             line["placement_variants"] = scan
+        if two_pass:
+            line["two_table_passes"] = two_pass
         if cpu_base:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))

@@ -26,6 +26,7 @@ WANT_HIST = 0x004
 WANT_POS = 0x008
 WANT_STARTPOS = 0x010
 WANT_LEV = 0x020
+WANT_SECOND_TABLE = 0x040
 PLACE_SCAN = 0x100
 PLACE_TILE = 0x800
 DEVICE_CHARS = 0x200
@@ -38,7 +39,7 @@ STAGES = ("h2d", "pack", "place", "score", "truth_spectrum", "prob_dist_ks", "ks
 ABI_SYMBOLS = (
     "bs_abi_version", "bs_ctx_create", "bs_ctx_destroy", "bs_last_error", "bs_ctx_set_stream",
     "bs_ctx_synchronize", "bs_ctx_launch_count", "bs_ctx_enable_timing", "bs_ctx_last_timings",
-    "bs_ctx_last_place_ms", "bs_set_table", "bs_set_truth_table", "bs_score_batch", "bs_score",
+    "bs_ctx_last_place_ms", "bs_set_table", "bs_set_truth_table", "bs_set_second_table", "bs_score_batch", "bs_score",
     "bs_host_alloc", "bs_host_free", "bs_assemble_contigs", "bs_assemble_last_error", "bs_string_list_size",
     "bs_string_list_bytes", "bs_string_list_copy", "bs_string_list_free", "bs_simulate_capacity", "bs_simulate_reads",
 )
@@ -75,6 +76,8 @@ class _Result(C.Structure):
         ("ks_stat_path_freq", C.c_void_p), ("path_prob_dist", C.c_void_p),
         ("path_prob_dist_off", C.c_void_p), ("hist", C.c_void_p), ("pos", C.c_void_p),
         ("pos_off", C.c_void_p),
+        ("bp_score2", C.c_void_p), ("bp_score_norm_by_break_freqs2", C.c_void_p), ("bp_score_norm_by_len2", C.c_void_p),
+        ("ks_stat_prob_dist2", C.c_void_p), ("ks_stat_path_freq2", C.c_void_p), ("path_prob_dist2", C.c_void_p),
     ]
 
 
@@ -109,6 +112,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_set_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.bs_set_truth_table.restype = C.c_int
     lib.bs_set_truth_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.bs_set_second_table.restype = C.c_int
+    lib.bs_set_second_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     lib.bs_score_batch.restype = C.c_int
     lib.bs_score_batch.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_int, C.c_uint32, C.POINTER(_Result)]
     lib.bs_score.restype = C.c_int
@@ -135,8 +140,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_simulate_reads.restype = C.c_int
     lib.bs_simulate_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int,
                                       C.c_uint64, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p]
-    if lib.bs_abi_version() != 1:
-        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 1")
+    if lib.bs_abi_version() != 2:
+        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 2")
     return lib
 
 
@@ -238,6 +243,16 @@ class BreakageScorer:
         else:
             self._check(self._lib.bs_set_truth_table(self._ctx, None, 0))
 
+    def set_second_table(self, prob2):
+        """A second scoring table over the same rows (e.g. the uniform table of the R driver's "random"
+        pass, lib/DeNovoAssembler.R:325-333); score with flags | WANT_SECOND_TABLE to get the ``*2`` members
+        from the same placement.  None removes it."""
+        if prob2 is None:
+            self._check(self._lib.bs_set_second_table(self._ctx, None, 0))
+            return
+        t = np.ascontiguousarray(prob2, dtype=np.float64)
+        self._check(self._lib.bs_set_second_table(self._ctx, _ptr(t), len(t)))
+
     # -- read simulation ------------------------------------------------------------------
     def simulate_reads(self, truths, read_len, coverage, seed=1234, kmer=8):
         """Reads of `read_len` bases sampled from every truth with upstream's law
@@ -296,6 +311,17 @@ class BreakageScorer:
             out["path_prob_dist_off"] = pd_off
             r.path_prob_dist = out["path_prob_dist_flat"].ctypes.data
             r.path_prob_dist_off = pd_off.ctypes.data
+        if flags & WANT_SECOND_TABLE:
+            for k in ("bp_score2", "bp_score_norm_by_break_freqs2", "bp_score_norm_by_len2"):
+                out[k] = np.zeros(Cn, np.float64)
+                setattr(r, k, out[k].ctypes.data)
+            if flags & WANT_KS:
+                for k in ("ks_stat_prob_dist2", "ks_stat_path_freq2"):
+                    out[k] = np.zeros(Cn, np.float64)
+                    setattr(r, k, out[k].ctypes.data)
+            if flags & WANT_PROB_DIST:
+                out["path_prob_dist2_flat"] = np.zeros(max(int(pd_off[-1]), 1), np.float64)
+                r.path_prob_dist2 = out["path_prob_dist2_flat"].ctypes.data
         if flags & WANT_HIST:
             out["hist"] = np.zeros((Cn, self.n_table + 1), np.int32)
             r.hist = out["hist"].ctypes.data
@@ -331,6 +357,9 @@ class BreakageScorer:
         if flags & WANT_PROB_DIST:
             flat, off = res.pop("path_prob_dist_flat"), res.pop("path_prob_dist_off")
             res["path_prob_dist"] = [flat[off[i]:off[i + 1]] for i in range(len(path))]
+            if flags & WANT_SECOND_TABLE:
+                flat2 = res.pop("path_prob_dist2_flat")
+                res["path_prob_dist2"] = [flat2[off[i]:off[i + 1]] for i in range(len(path))]
         if flags & WANT_POS:
             flat = res.pop("pos_flat")
             res.pop("pos_off")

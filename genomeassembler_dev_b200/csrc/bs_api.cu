@@ -77,8 +77,8 @@ struct Workspace {
     size_t h_meta_cap = 0;
     DevBuf meta, read_chars, read_off, ctg_chars, tr_chars;
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
-    DevBuf w, total, ycnt, yx, head, next, odd_head, spbest, exact;
-    DevBuf out_i32, out_f64, pd, hist, pos;
+    DevBuf w, total, ycnt, yx, yx2, head, next, odd_head, spbest, exact;
+    DevBuf out_i32, out_f64, pd, pd2, hist, pos;
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
 };
@@ -120,6 +120,12 @@ struct bs_ctx {
     bool has_truth_table = false;
     DevBuf d_tab;  // bs::TabEntry[DENSE_SIZE]
     KsCache ks;
+    // optional second scoring table over the same rows (the R driver's "random" pass, lib/DeNovoAssembler.R:325-333):
+    // scored in the same call from the same placement (BS_WANT_SECOND_TABLE)
+    bool has_table2 = false;
+    std::vector<double> prob2_dense;
+    DevBuf d_tab2;
+    KsCache ks2;
 
     Workspace ws[kWorkspaces];
     unsigned ws_cursor = 0;  // workspaces rotate across calls too: an asynchronous (device-result) call may still own one
@@ -231,22 +237,21 @@ int sync_all(bs_ctx *ctx) {
     return BS_OK;
 }
 
-int upload_table(bs_ctx *ctx) {
+int upload_table(bs_ctx *ctx, const std::vector<double> &prob_dense, DevBuf &d_tab) {
     std::vector<bs::TabEntry> tab(bs::DENSE_SIZE);
     for (int i = 0; i < bs::DENSE_SIZE; i++) {
-        tab[i].prob = ctx->prob_dense[i];
+        tab[i].prob = prob_dense[i];
         tab[i].row = ctx->row_dense[i];
         tab[i].pad = 0;
     }
-    BS_TRY(ensure(ctx, ctx->d_tab, tab.size() * sizeof(bs::TabEntry)));
-    BS_CUDA(cudaMemcpyAsync(ctx->d_tab.p, tab.data(), tab.size() * sizeof(bs::TabEntry), cudaMemcpyHostToDevice, ctx->stream));
+    BS_TRY(ensure(ctx, d_tab, tab.size() * sizeof(bs::TabEntry)));
+    BS_CUDA(cudaMemcpyAsync(d_tab.p, tab.data(), tab.size() * sizeof(bs::TabEntry), cudaMemcpyHostToDevice, ctx->stream));
     BS_CUDA(cudaStreamSynchronize(ctx->stream));
     return BS_OK;
 }
 
 // sorted distinct values + rank maps for the KS statistics of window length kmer
-int prepare_ks(bs_ctx *ctx, int kmer) {
-    KsCache &k = ctx->ks;
+int prepare_ks(bs_ctx *ctx, int kmer, KsCache &k, const std::vector<double> &xprob_dense) {
     if (k.kmer == kmer && k.table_version == ctx->table_version) return BS_OK;
     const bool in_range = kmer >= 1 && kmer <= bs::MAXK;
     const int ncode = in_range ? 1 << (2 * kmer) : 1;
@@ -255,7 +260,7 @@ int prepare_ks(bs_ctx *ctx, int kmer) {
     if (in_range) {
         for (int c = 0; c < ncode; c++)
             if (ctx->row_dense[doff + c] >= 0) {
-                xv.push_back(ctx->prob_dense[doff + c]);
+                xv.push_back(xprob_dense[doff + c]);
                 yv.push_back(ctx->tprob_dense[doff + c]);
             }
     }
@@ -268,7 +273,7 @@ int prepare_ks(bs_ctx *ctx, int kmer) {
     if (in_range) {
         for (int c = 0; c < ncode; c++) {
             if (ctx->row_dense[doff + c] < 0) { rank_x[c] = rank_zero; continue; }
-            rank_x[c] = (int32_t)(std::lower_bound(xv.begin(), xv.end(), ctx->prob_dense[doff + c]) - xv.begin());
+            rank_x[c] = (int32_t)(std::lower_bound(xv.begin(), xv.end(), xprob_dense[doff + c]) - xv.begin());
             rank_y[c] = (int32_t)(std::lower_bound(yv.begin(), yv.end(), ctx->tprob_dense[doff + c]) - yv.begin());
         }
     }
@@ -280,7 +285,7 @@ int prepare_ks(bs_ctx *ctx, int kmer) {
     std::vector<bs::WinEntry> win((size_t)ncode);
     for (int c = 0; c < ncode; c++) {
         const bool in_table = in_range && ctx->row_dense[doff + c] >= 0;
-        win[c].prob = in_table ? ctx->prob_dense[doff + c] : 0.0;
+        win[c].prob = in_table ? xprob_dense[doff + c] : 0.0;
         win[c].rank = rank_x[c];
         win[c].pad = 0;
     }
@@ -307,6 +312,8 @@ int prepare_ks(bs_ctx *ctx, int kmer) {
     return BS_OK;
 }
 
+int prepare_ks(bs_ctx *ctx, int kmer) { return prepare_ks(ctx, kmer, ctx->ks, ctx->prob_dense); }
+
 int check_offsets(bs_ctx *ctx, const char *what, const int64_t *off, int64_t n) {
     if (!off) return fail(ctx, BS_ERR_INVALID, "%s offsets are NULL", what);
     if (off[0] < 0) return fail(ctx, BS_ERR_INVALID, "%s offsets start below 0", what);
@@ -321,7 +328,7 @@ struct CallEnv {
     bs_result *res;
     int kmer;
     uint32_t flags;
-    bool dev_chars, dev_res, want_ks, want_pd, want_pos, want_hist, want_sp, want_lev;
+    bool dev_chars, dev_res, want_ks, want_pd, want_pos, want_hist, want_sp, want_lev, second;
     const char *read_chars;  // base of read 0 (shifted when offsets turned out to be uniform)
     const int64_t *roff;     // read offsets or NULL (every read has rlen bytes, dense)
     int32_t rlen;
@@ -365,6 +372,8 @@ struct ChunkRun {
     // result destinations on the device (user arrays with BS_DEVICE_RESULT, else the workspace)
     int32_t *o_len = nullptr, *o_breaks = nullptr, *o_startpos = nullptr, *o_lev = nullptr, *o_hist = nullptr, *o_pos = nullptr;
     double *o_score = nullptr, *o_norm = nullptr, *o_bylen = nullptr, *o_ksa = nullptr, *o_ksb = nullptr, *o_pd = nullptr;
+    // ... for the second table (same order)
+    double *o_score2 = nullptr, *o_norm2 = nullptr, *o_bylen2 = nullptr, *o_ksa2 = nullptr, *o_ksb2 = nullptr, *o_pd2 = nullptr;
 
     ChunkRun(bs_ctx *c, Workspace &w, const CallEnv &env, const Chunk &chunk)
         : ctx(c), ws(w), e(env), ch(chunk), b(env.b), res(env.res), S(chunk.s1 - chunk.s0), N(chunk.r1 - chunk.r0),
@@ -374,8 +383,9 @@ struct ChunkRun {
     int pack();       // 2-bit packing of contigs, truths and reads (+ read index)
     int place();      // leftmost placement of every read in every contig of its segment
     int spectrum();   // truth-side distribution of the KS statistics
-    int score();      // weighted sums, histogram, KS-B
-    int prob_dist();  // path_prob_dist and KS-A
+    int score(int which);      // weighted sums, histogram, KS-B (which: 0 scoring table, 1 second table)
+    int prob_dist(int which);  // path_prob_dist and KS-A
+    int second_table();        // both again for the second table, from the same placement
     int startpos();   // contig-in-truth offset
     int lev();        // infix edit distance
     int results();    // D2H (or the tail of the device-result path)
@@ -554,8 +564,9 @@ int ChunkRun::prepare() {
     }
     if (!e.dev_res) {
         BS_TRY(ensure(ctx, ws.out_i32, (size_t)4 * C * 4));
-        BS_TRY(ensure(ctx, ws.out_f64, (size_t)5 * C * 8));
+        BS_TRY(ensure(ctx, ws.out_f64, (size_t)10 * C * 8));
         if (e.want_pd) BS_TRY(ensure(ctx, ws.pd, (size_t)std::max<int64_t>(pd_elems, 1) * 8));
+        if (e.want_pd && e.second) BS_TRY(ensure(ctx, ws.pd2, (size_t)std::max<int64_t>(pd_elems, 1) * 8));
         if (e.want_hist) BS_TRY(ensure(ctx, ws.hist, (size_t)C * (T + 1) * 4));
         if (e.want_pos) BS_TRY(ensure(ctx, ws.pos, (size_t)std::max<int64_t>(pos_elems, 1) * 4));
     }
@@ -612,6 +623,14 @@ int ChunkRun::prepare() {
         o_ksa = ks_a ? res->ks_stat_prob_dist + ch.c0 : nullptr;
         o_ksb = ks_b ? res->ks_stat_path_freq + ch.c0 : nullptr;
         if (e.want_pd) o_pd = res->path_prob_dist + res->path_prob_dist_off[ch.c0];
+        if (e.second) {
+            o_score2 = res->bp_score2 ? res->bp_score2 + ch.c0 : nullptr;
+            o_norm2 = res->bp_score_norm_by_break_freqs2 ? res->bp_score_norm_by_break_freqs2 + ch.c0 : nullptr;
+            o_bylen2 = res->bp_score_norm_by_len2 ? res->bp_score_norm_by_len2 + ch.c0 : nullptr;
+            o_ksa2 = (e.want_ks && res->ks_stat_prob_dist2) ? res->ks_stat_prob_dist2 + ch.c0 : nullptr;
+            o_ksb2 = (e.want_ks && res->ks_stat_path_freq2) ? res->ks_stat_path_freq2 + ch.c0 : nullptr;
+            if (e.want_pd) o_pd2 = res->path_prob_dist2 + res->path_prob_dist_off[ch.c0];
+        }
         if (e.want_hist) o_hist = res->hist + ch.c0 * (T + 1);
         if (e.want_pos) o_pos = res->pos + res->pos_off[ch.c0];
     } else {
@@ -623,6 +642,12 @@ int ChunkRun::prepare() {
         o_ksa = ks_a ? f64 + 3 * C : nullptr;
         o_ksb = ks_b ? f64 + 4 * C : nullptr;
         if (e.want_pd) o_pd = (double *)ws.pd.p;
+        if (e.second) {
+            o_score2 = f64 + 5 * C; o_norm2 = f64 + 6 * C; o_bylen2 = f64 + 7 * C;
+            o_ksa2 = (e.want_ks && res->ks_stat_prob_dist2) ? f64 + 8 * C : nullptr;
+            o_ksb2 = (e.want_ks && res->ks_stat_path_freq2) ? f64 + 9 * C : nullptr;
+            if (e.want_pd) o_pd2 = (double *)ws.pd2.p;
+        }
         if (e.want_hist) o_hist = (int32_t *)ws.hist.p;
         if (e.want_pos) o_pos = (int32_t *)ws.pos.p;
     }
@@ -757,29 +782,34 @@ int ChunkRun::spectrum() {
     return BS_OK;
 }
 
-int ChunkRun::score() {
+int ChunkRun::score(int which) {
     {
         // scores (+ histogram, + KS of the normalised break histogram); after the truth spectrum
         StageTimer tm(ctx, ST_SCORE, st);
-        const KsCache &k = ctx->ks;
+        const KsCache &k = which ? ctx->ks2 : ctx->ks;
+        const bool ksb = which ? o_ksb2 != nullptr : ks_b;
         const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kScoreThreads, 0));
         bs::ScoreArgs sa;
         std::memset(&sa, 0, sizeof(sa));
-        sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + 2;
+        sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + (which ? 5 : 2);
         sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_seg = d_ctg_seg;
         sa.w = (const int32_t *)ws.w.p; sa.total = (const int32_t *)ws.total.p;
-        sa.tab = (const bs::TabEntry *)ctx->d_tab.p;
+        sa.tab = (const bs::TabEntry *)(which ? ctx->d_tab2.p : ctx->d_tab.p);
         sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
-        sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
-        sa.kmer_breaks = o_breaks; sa.hist = o_hist;
-        if (ks_b) {
+        if (which == 0) {
+            sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
+            sa.kmer_breaks = o_breaks; sa.hist = o_hist;
+        } else {  // lengths, break counts and the histogram do not depend on the table
+            sa.bp_score = o_score2; sa.norm_by_break_freqs = o_norm2; sa.norm_by_len = o_bylen2;
+        }
+        if (ksb) {
             const size_t scratch_bytes = (size_t)nblk * (T + 1) * 4;
             if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
                 BS_TRY(ensure(ctx, ctx->d_scratch, scratch_bytes));
                 BS_CUDA(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, st));
             }
             BS_TRY(ensure(ctx, ctx->d_ovf, (size_t)nblk * bs::OVF_CAP * 4));
-            sa.ks_b = o_ksb; sa.yv = (const double *)k.yv.p; sa.ycum = (const int32_t *)ws.ycnt.p; sa.R_y = k.R_y;
+            sa.ks_b = which ? o_ksb2 : o_ksb; sa.yv = (const double *)k.yv.p; sa.ycum = (const int32_t *)ws.ycnt.p; sa.R_y = k.R_y;
             sa.zero_le = k.zero_le; sa.zero_lt = k.zero_lt; sa.y_max = k.y_max;
             sa.scratch = (int32_t *)ctx->d_scratch.p; sa.ovf_cnt = (int32_t *)ctx->d_ovf.p; sa.status = (int32_t *)ctx->d_status.p;
         }
@@ -789,33 +819,34 @@ int ChunkRun::score() {
     return BS_OK;
 }
 
-int ChunkRun::prob_dist() {
-    if (e.want_pd || ks_a) {
+int ChunkRun::prob_dist(int which) {
+    const bool ksa = which ? o_ksa2 != nullptr : ks_a;
+    if (e.want_pd || ksa) {
         StageTimer tm(ctx, ST_PROBDIST, st);
-        const KsCache &k = ctx->ks;
+        const KsCache &k = which ? ctx->ks2 : ctx->ks;
         bs::ProbDistArgs pa;
-        pa.order = d_order; pa.work_counter = (int32_t *)ctx->d_counters.p + 1;
+        pa.order = d_order; pa.work_counter = (int32_t *)ctx->d_counters.p + (which ? 4 : 1);
         pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
         pa.ctg_seg = d_ctg_seg;
         pa.win = (kmer >= 1 && kmer <= bs::MAXK) ? (const bs::WinEntry *)k.win.p : nullptr;
-        pa.yx = ks_a ? (const bs::LeLt *)ws.yx.p : nullptr;
-        pa.ycum = ks_a ? (const int32_t *)ws.ycnt.p : nullptr;
+        pa.yx = ksa ? (const bs::LeLt *)(which ? ws.yx2.p : ws.yx.p) : nullptr;
+        pa.ycum = ksa ? (const int32_t *)ws.ycnt.p : nullptr;
         pa.R_x = k.R_x; pa.R_y = k.R_y; pa.rank_zero = k.rank_zero;
         pa.kmer = kmer; pa.n_contigs = C;
-        pa.prob_dist = o_pd; pa.pd_off = d_pd_off; pa.ks = ks_a ? o_ksa : nullptr;
+        pa.prob_dist = which ? o_pd2 : o_pd; pa.pd_off = d_pd_off; pa.ks = ksa ? (which ? o_ksa2 : o_ksa) : nullptr;
         // rank histogram in shared memory: 16-bit counters (two per word) when no contig has 65 536
         // windows -- real table: 32 897 ranks = 66 KB, three blocks per SM -- else 32-bit counters,
         // else (all-distinct tables with long contigs) a per-block global scratch that stays in L2
         const bool packed = max_ctg - kmer + 1 < 65536;
-        pa.hist_words = ks_a ? bs::hist_phys_words(k.R_x, packed) : 0;
-        pa.n_ranges = ks_a ? bs::hist_ranges(k.R_x, packed) : 0;
+        pa.hist_words = ksa ? bs::hist_phys_words(k.R_x, packed) : 0;
+        pa.n_ranges = ksa ? bs::hist_ranges(k.R_x, packed) : 0;
         const size_t hist_bytes = (size_t)(pa.hist_words + pa.n_ranges) * 4;
         const bool in_smem = hist_bytes + 2048 <= ctx->smem_optin;
         const size_t smem = in_smem ? hist_bytes : 0;
         const int per_sm = std::max<int>(1, std::min<int>(2048 / kKsThreads, (int)((ctx->smem_optin + 1024) / (smem + 1024))));
         const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * per_sm);
         pa.rank_scratch = nullptr;
-        if (ks_a && !in_smem) {
+        if (ksa && !in_smem) {
             BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * hist_bytes));
             pa.rank_scratch = (uint32_t *)ctx->d_rank_scratch.p;
         }
@@ -831,6 +862,26 @@ int ChunkRun::prob_dist() {
         ctx->launches++;
     }
     return BS_OK;
+}
+
+// The second scoring table over the same rows (the R driver's "random" pass): the placement, the break
+// counts, the contig offsets and the truth's cumulative counts are shared; only the table-dependent
+// stages run again.
+int ChunkRun::second_table() {
+    if (!e.second) return BS_OK;
+    if (o_ksa2) {  // counts <= / < every x value of the SECOND table, from the truth's cumulative counts
+        const KsCache &k2 = ctx->ks2;
+        BS_TRY(ensure(ctx, ws.yx2, (size_t)S * k2.R_x * sizeof(bs::LeLt)));
+        bs::SpectrumArgs sp;
+        std::memset(&sp, 0, sizeof(sp));
+        sp.ycnt = (int32_t *)ws.ycnt.p; sp.R_y = std::max(ctx->ks.R_y, 1);
+        sp.lelt = (const bs::LeLt *)k2.lelt.p; sp.yx = (bs::LeLt *)ws.yx2.p; sp.R_x = k2.R_x;
+        StageTimer tm(ctx, ST_SPECTRUM, st);
+        BS_LAUNCH(bs::k_yx_gather, grid_for(S * (int64_t)k2.R_x, kScoreThreads, grid_cap), kScoreThreads, 0, st, sp, S);
+        ctx->launches++;
+    }
+    BS_TRY(score(1));
+    return prob_dist(1);
 }
 
 int ChunkRun::startpos() {
@@ -917,6 +968,14 @@ int ChunkRun::results() {
         BS_CUDA(d2h(at(res->ks_stat_prob_dist, ch.c0), o_ksa, (size_t)C * 8));
         BS_CUDA(d2h(at(res->ks_stat_path_freq, ch.c0), o_ksb, (size_t)C * 8));
         if (e.want_pd) BS_CUDA(d2h(at(res->path_prob_dist, res->path_prob_dist_off[ch.c0]), o_pd, (size_t)pd_elems * 8));
+        if (e.second) {
+            BS_CUDA(d2h(at(res->bp_score2, ch.c0), o_score2, (size_t)C * 8));
+            BS_CUDA(d2h(at(res->bp_score_norm_by_break_freqs2, ch.c0), o_norm2, (size_t)C * 8));
+            BS_CUDA(d2h(at(res->bp_score_norm_by_len2, ch.c0), o_bylen2, (size_t)C * 8));
+            BS_CUDA(d2h(at(res->ks_stat_prob_dist2, ch.c0), o_ksa2, (size_t)C * 8));
+            BS_CUDA(d2h(at(res->ks_stat_path_freq2, ch.c0), o_ksb2, (size_t)C * 8));
+            if (e.want_pd) BS_CUDA(d2h(at(res->path_prob_dist2, res->path_prob_dist_off[ch.c0]), o_pd2, (size_t)pd_elems * 8));
+        }
         if (e.want_hist) BS_CUDA(d2h(at(res->hist, ch.c0 * (T + 1)), o_hist, (size_t)C * (T + 1) * 4));
         if (e.want_pos) BS_CUDA(d2h(at(res->pos, res->pos_off[ch.c0]), o_pos, (size_t)pos_elems * 4));
     }
@@ -932,8 +991,9 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     BS_TRY(r.pack());
     BS_TRY(r.place());
     BS_TRY(r.spectrum());
-    BS_TRY(r.score());
-    BS_TRY(r.prob_dist());
+    BS_TRY(r.score(0));
+    BS_TRY(r.prob_dist(0));
+    BS_TRY(r.second_table());
     BS_TRY(r.startpos());
     BS_TRY(r.lev());
     return r.results();
@@ -996,14 +1056,14 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->d_tab, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
+    DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_tab2, &ctx->ks2.win, &ctx->ks2.rank_y, &ctx->ks2.lelt, &ctx->ks2.yv, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
                       &ctx->d_rank_scratch, &ctx->d_counters, &ctx->d_hbuf, &ctx->sim_meta, &ctx->sim_chars,
                       &ctx->sim_words, &ctx->sim_mask, &ctx->sim_cdf, &ctx->sim_starts, &ctx->sim_kept, &ctx->sim_reads};
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
-                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact,
-                        &w.out_i32, &w.out_f64, &w.pd, &w.hist, &w.pos};
+                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.yx2, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact,
+                        &w.out_i32, &w.out_f64, &w.pd, &w.pd2, &w.hist, &w.pos};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);
         if (w.ev_h2d) cudaEventDestroy(w.ev_h2d);
@@ -1117,7 +1177,29 @@ int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, c
     ctx->T = n;
     ctx->has_table = true;
     ctx->table_version++;
-    return upload_table(ctx);
+    ctx->has_table2 = false;  // rows may have changed: a second table has to be set again
+    return upload_table(ctx, ctx->prob_dense, ctx->d_tab);
+}
+
+int bs_set_second_table(bs_ctx *ctx, const double *prob, int64_t n) {
+    if (!ctx) return BS_ERR_INVALID;
+    if (!ctx->has_table) return fail(ctx, BS_ERR_STATE, "bs_set_second_table before bs_set_table");
+    if (!prob) { ctx->has_table2 = false; return BS_OK; }
+    if (n != ctx->T) return fail(ctx, BS_ERR_INVALID, "second table has %lld rows, scoring table %lld", (long long)n, (long long)ctx->T);
+    cudaSetDevice(ctx->device);
+    BS_TRY(sync_all(ctx));
+    std::vector<double> t(bs::DENSE_SIZE, 0.0);
+    for (int di = 0; di < bs::DENSE_SIZE; di++) {
+        const int32_t r = ctx->row_dense[di];
+        if (r >= 0) {
+            if (std::isnan(prob[r])) return fail(ctx, BS_ERR_TABLE, "second table row %d is NaN", r);
+            t[di] = prob[r];
+        }
+    }
+    ctx->prob2_dense.swap(t);
+    ctx->has_table2 = true;
+    ctx->ks2.kmer = -1;  // rank maps are rebuilt on the next call
+    return upload_table(ctx, ctx->prob2_dense, ctx->d_tab2);
 }
 
 int bs_set_truth_table(bs_ctx *ctx, const double *prob, int64_t n) {
@@ -1185,6 +1267,9 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     e.want_hist = (flags & BS_WANT_HIST) != 0;
     e.want_sp = (flags & BS_WANT_STARTPOS) && res->path_prob_dist_startpos;
     e.want_lev = (flags & BS_WANT_LEV) && res->lev_dist_vs_true;
+    e.second = (flags & BS_WANT_SECOND_TABLE) != 0;
+    if (e.second && !ctx->has_table2) return fail(ctx, BS_ERR_STATE, "BS_WANT_SECOND_TABLE before bs_set_second_table");
+    if (e.second && e.want_pd && !res->path_prob_dist2) return fail(ctx, BS_ERR_INVALID, "BS_WANT_SECOND_TABLE with BS_WANT_PROB_DIST needs path_prob_dist2");
     e.read_chars = b->read_chars;
     e.roff = b->read_off;
     e.rlen = b->read_len;
@@ -1200,6 +1285,7 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
         }
     }
     if (e.want_ks || e.want_pd) BS_TRY(prepare_ks(ctx, kmer));
+    if (e.second && (e.want_ks || e.want_pd)) BS_TRY(prepare_ks(ctx, kmer, ctx->ks2, ctx->prob2_dense));
     if (e.want_ks && res->ks_stat_path_freq) {
         BS_TRY(ensure(ctx, ctx->d_status, 16));
         BS_CUDA(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));

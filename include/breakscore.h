@@ -15,6 +15,7 @@
  * kmer_from_seq table, lib/GenerateReads.R:243-259    | bs_set_truth_table (KS y-side)
  * calc_breakscore body, lib/BreakageScorer.cpp:200-353| bs_score (one segment) / bs_score_batch
  * ks.test statistic, lib/DeNovoAssembler.R:416-424    | BS_WANT_KS outputs of the same calls
+ * second pass with rep(1/n, n), DeNovoAssembler.R:325-333 | bs_set_second_table + BS_WANT_SECOND_TABLE (one call, one placement)
  * Rcpp::stop / R error                                | int status + bs_last_error
  * assemble_contigs, lib/BreakageScorer.cpp:79-174     | bs_assemble_contigs (host; candidate generator)
  * generate_sequencing_reads, lib/GenerateReads.R:234-379 | bs_simulate_reads (device; the step before the scorer)
@@ -28,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 1
+#define BS_ABI_VERSION 2
 
 /* the library is built with -fvisibility=hidden: only these entry points are exported */
 #if defined(__GNUC__)
@@ -57,6 +58,7 @@ enum {
 #define BS_WANT_POS       0x008u /* fill pos: leftmost match of every read in every contig (parity/debug) */
 #define BS_WANT_STARTPOS  0x010u /* fill path_prob_dist_startpos (lib/BreakageScorer.cpp:273-274) */
 #define BS_WANT_LEV       0x020u /* fill lev_dist_vs_true: infix edit distance contig vs truth (lib/BreakageScorer.cpp:41-55,339) */
+#define BS_WANT_SECOND_TABLE 0x040u /* also fill the *2 members of bs_result from the table of bs_set_second_table */
 #define BS_PLACE_SCAN     0x100u /* placement by exhaustive all-pairs scan of the contig tile in shared memory (same results) */
 #define BS_PLACE_TILE     0x800u /* placement by a seed index over the contig tile, reads streamed past it (same results) */
 #define BS_DEVICE_CHARS   0x200u /* read_chars / contig_chars / truth_chars are DEVICE pointers */
@@ -108,6 +110,15 @@ typedef struct {
     int32_t *hist;                          /* [C][T+1], row-major; bin T = key not in table */
     int32_t *pos;                           /* contig c: n_reads(segment of c) entries at pos_off[c]; -1 = no match */
     const int64_t *pos_off;                 /* HOST [C+1], required with BS_WANT_POS */
+    /* BS_WANT_SECOND_TABLE: the table-dependent members again, for the second scoring table, from the
+     * same placement (the R driver scores every experiment twice, real table then uniform table:
+     * lib/DeNovoAssembler.R:325-333).  Same layout as their namesakes; any may be NULL. */
+    double *bp_score2;
+    double *bp_score_norm_by_break_freqs2;
+    double *bp_score_norm_by_len2;
+    double *ks_stat_prob_dist2;
+    double *ks_stat_path_freq2;
+    double *path_prob_dist2;                /* uses path_prob_dist_off */
 } bs_result;
 
 /* context: owns the device, its streams, the resident tables and grow-only work buffers.
@@ -143,6 +154,9 @@ BS_API int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer
 /* probabilities used for the truth-side distribution of the KS statistics (same keys/rows as the
  * scoring table).  prob == NULL: follow the scoring table. */
 BS_API int bs_set_truth_table(bs_ctx *ctx, const double *prob, int64_t n);
+/* a second scoring table over the SAME rows (prob[i] belongs to row i of bs_set_table); scored in the
+ * same call with BS_WANT_SECOND_TABLE.  prob == NULL removes it; bs_set_table removes it too. */
+BS_API int bs_set_second_table(bs_ctx *ctx, const double *prob, int64_t n);
 
 BS_API int bs_score_batch(bs_ctx *ctx, const bs_batch *batch, int kmer, uint32_t flags, bs_result *result);
 

@@ -113,3 +113,30 @@ def test_edit_distance_indels_and_long_contigs(emul_scorer, oracle, kmers, prob)
     reads = [truth[i:i + 40] for i in range(0, 5000, 97)]
     got, want = P.check_segment(emul_scorer, oracle, kmers, prob, seg, reads=reads, flags=B.DEFAULT_FLAGS | B.WANT_LEV)
     assert got["lev_dist_vs_true"][0] == 1 and got["lev_dist_vs_true"][5] == 0
+
+
+def check_second_table(scorer, kmers, prob, seg):
+    """both table passes of the R driver (real, then uniform with the real table on the truth side) in ONE
+    call == two calls, bit for bit"""
+    uni = tables.uniform(len(prob))
+    flags = B.DEFAULT_FLAGS
+    scorer.set_table(kmers, prob)
+    scorer.set_second_table(uni)
+    both = scorer.score(seg.contigs, seg.read_list, seg.truth, flags=flags | B.WANT_SECOND_TABLE)
+    first = scorer.score(seg.contigs, seg.read_list, seg.truth, flags=flags)
+    scorer.set_table(kmers, uni, truth_prob=prob)
+    second = scorer.score(seg.contigs, seg.read_list, seg.truth, flags=flags)
+    for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len", "ks_stat_prob_dist", "ks_stat_path_freq",
+              "kmer_breaks", "path_prob_dist_startpos"):
+        assert np.array_equal(both[k], first[k], equal_nan=True), k
+    for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len", "ks_stat_prob_dist", "ks_stat_path_freq"):
+        assert np.array_equal(both[k + "2"], second[k], equal_nan=True), k + "2"
+    for a, b in zip(both["path_prob_dist2"], second["path_prob_dist"]):
+        assert np.array_equal(a, b)
+    scorer.set_table(kmers, prob)
+    with pytest.raises(B.BreakscoreError):  # bs_set_table removes the second table
+        scorer.score(seg.contigs, seg.read_list, seg.truth, flags=flags | B.WANT_SECOND_TABLE)
+
+
+def test_second_table_in_one_call(emul_scorer, kmers, prob):
+    check_second_table(emul_scorer, kmers, prob, P.make(43, 2500, 50, 10, 5, 1))

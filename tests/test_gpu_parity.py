@@ -317,3 +317,8 @@ def test_async_device_resident_calls_reuse_workspaces(product_lib, kmers, prob, 
             assert np.array_equal(i32[2].cpu().numpy(), ref["path_prob_dist_startpos"])
             assert np.array_equal(f64[0].cpu().numpy(), ref["bp_score"])
             assert np.array_equal(f64[3].cpu().numpy(), ref["ks_stat_prob_dist"], equal_nan=True)
+
+
+def test_second_table_in_one_call(gpu_scorer, kmers, prob):
+    from test_emul_device_algorithm import check_second_table
+    check_second_table(gpu_scorer, kmers, prob, P.make(44, 50000, 150, 30, 20, 1))
