@@ -276,4 +276,4 @@ template <class K>
 inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 2; return cudaSuccess; }
 
 #define BS_LAUNCH(kern, grid, block, smem, stream, ...) \
-    bs_emul::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+    bs_emul::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { kern(__VA_ARGS__); })  // synchronous: references stay valid

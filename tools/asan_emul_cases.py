@@ -17,4 +17,10 @@ P.check_segment(sc,O,kmers,rowid,P.make(*P.SMALL[0]),flags=P.FULL); n+=1
 b=synth.make_batch(5,seed=3,length=1500,read_len=30,coverage=6,contigs_lo=1,contigs_hi=4)
 sc.set_table(kmers,prob)
 sc.score_batch(b.read_chars,None,b.read_len,b.contig_chars,b.contig_off,b.truth_chars,b.truth_off,b.seg_read_start,b.seg_contig_start,flags=B.DEFAULT_FLAGS|B.WANT_HIST|B.WANT_POS|B.WANT_LEV); n+=1
+from genomeassembler_dev_b200 import tables as T
+sc.set_table(kmers,prob); sc.set_second_table(T.uniform(len(prob)))
+seg=P.make(43, 2500, 50, 10, 5, 1)
+sc.score(seg.contigs, seg.read_list, seg.truth, flags=B.DEFAULT_FLAGS|B.WANT_SECOND_TABLE|B.WANT_LEV|B.WANT_HIST); n+=1
+reads,srs=sc.simulate_reads([seg.truth, b'ACGT', b''], 40, 8, seed=3); n+=1
+print(B.assemble_contigs([b'ACGTACGTAAGGCCTT', b'GGCCTTACGTTTTTTTTT', b'TTTTTTTTTGGA'], 7, 5, n_shuffles=50, lib_path='/tmp/asan/libbreakscore_emul.so')); n+=1
 print('asan run ok', n, 'cases')
