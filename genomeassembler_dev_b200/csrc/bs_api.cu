@@ -363,6 +363,8 @@ struct ChunkRun {
     const int64_t *d_ctg_off = nullptr, *d_ctg_woff = nullptr, *d_tr_off = nullptr, *d_tr_woff = nullptr, *d_seg_rs = nullptr,
                   *d_seg_cs = nullptr, *d_tab_off = nullptr, *d_pd_off = nullptr, *d_pos_off = nullptr, *d_roff = nullptr;
     const int32_t *d_ctg_seg = nullptr, *d_seed = nullptr, *d_tab_mask = nullptr, *d_order = nullptr;
+    const int32_t *d_order_small = nullptr, *d_order_large = nullptr;  // work order split at KS_SMALL_MAX windows
+    int64_t n_small = 0, n_large = 0;
     const bs::PlaceItem *d_items = nullptr;
     const uint8_t *d_rchars = nullptr, *d_cchars = nullptr, *d_tchars = nullptr;
     bs::SeqSet cs, ts;
@@ -462,6 +464,14 @@ int ChunkRun::prepare() {
         auto mid = std::stable_partition(order.begin(), order.end(), [&](int32_t x) { return len_of(x) > long_len; });
         std::stable_sort(order.begin(), mid, [&](int32_t x, int32_t y) { return len_of(x) > len_of(y); });
     }
+    // the KS-A stage runs short contigs (most of a velvet-style set) through its own kernel
+    std::vector<int32_t> order_small, order_large;
+    for (int32_t c : order) {
+        const int64_t nwin = ctg_off[c + 1] - ctg_off[c] - kmer + 1;
+        (nwin <= bs::KS_SMALL_MAX ? order_small : order_large).push_back(c);
+    }
+    n_small = (int64_t)order_small.size();
+    n_large = (int64_t)order_large.size();
     if (tile_mode) {
         // tile placement: one work item per (contig, read chunk)
         tile_len = (int)std::min<int64_t>(kMaxTile, std::max<int64_t>(32, (max_ctg + 31) / 32 * 32));
@@ -522,6 +532,8 @@ int ChunkRun::prepare() {
     const size_t o_tab_off = mb.add(tab_off.data(), (size_t)S);
     const size_t o_tab_mask = mb.add(tab_mask.data(), (size_t)S);
     const size_t o_order = mb.add(order.data(), order.size());
+    const size_t o_order_small = mb.add(order_small.data(), order_small.size());
+    const size_t o_order_large = mb.add(order_large.data(), order_large.size());
     const size_t o_items = mb.add(items.data(), items.size());
     const size_t o_pd_off = e.want_pd ? mb.add(pd_off.data(), (size_t)C + 1) : 0;
     const size_t o_pos_off = e.want_pos ? mb.add(pos_off.data(), (size_t)C + 1) : 0;
@@ -583,6 +595,8 @@ int ChunkRun::prepare() {
     d_tab_off = (const int64_t *)(dm + o_tab_off);
     d_tab_mask = (const int32_t *)(dm + o_tab_mask);
     d_order = (const int32_t *)(dm + o_order);
+    d_order_small = (const int32_t *)(dm + o_order_small);
+    d_order_large = (const int32_t *)(dm + o_order_large);
     d_items = (const bs::PlaceItem *)(dm + o_items);
     d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
     d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
@@ -850,16 +864,32 @@ int ChunkRun::prob_dist(int which) {
             BS_TRY(ensure(ctx, ctx->d_rank_scratch, (size_t)nblk * hist_bytes));
             pa.rank_scratch = (uint32_t *)ctx->d_rank_scratch.p;
         }
+        // short contigs (<= KS_SMALL_MAX windows) sort their ranks by ranges in a small shared-memory
+        // footprint; long ones keep the table-wide rank histogram
+        const size_t small_smem = bs::ks_small_smem_bytes(k.R_x);
+        const bool use_small = ksa && n_small > 0 && small_smem + 1024 <= ctx->smem_optin;
+        if (use_small) {
+            bs::ProbDistArgs ps = pa;
+            ps.order = d_order_small; ps.n_contigs = n_small; ps.work_counter = (int32_t *)ctx->d_counters.p + (which ? 7 : 6);
+            BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+            const int nb = (int)std::min<int64_t>(n_small, (int64_t)ctx->sm_count *
+                                                  blocks_per_sm(bs::k_prob_dist_ks_small, bs::KS_SMALL_THREADS, small_smem));
+            BS_LAUNCH(bs::k_prob_dist_ks_small, (unsigned)nb, bs::KS_SMALL_THREADS, small_smem, st, ps);
+            ctx->launches++;
+            pa.order = d_order_large; pa.n_contigs = n_large;
+        }
         auto launch = [&](auto kern) -> int {
             BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            BS_LAUNCH(kern, (unsigned)nblk, kKsThreads, smem, st, pa);
+            BS_LAUNCH(kern, (unsigned)std::min<int64_t>(nblk, std::max<int64_t>(pa.n_contigs, 1)), kKsThreads, smem, st, pa);
             return BS_OK;
         };
-        if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true>));
-        else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false>));
-        else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true>));
-        else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
-        ctx->launches++;
+        if (pa.n_contigs > 0) {
+            if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true>));
+            else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false>));
+            else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true>));
+            else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
+            ctx->launches++;
+        }
     }
     return BS_OK;
 }

@@ -334,4 +334,150 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same for SHORT contigs (at most KS_SMALL_MAX windows: nine in ten of a velvet-style set).
+// Instead of a rank histogram as wide as the table (66 KB, swept per contig) the block sorts the
+// contig's window ranks by a counting pass over ranges of 64 ranks: per-range counts -> offsets
+// (which are already the number of windows with a smaller rank) -> scatter; a thread then orders
+// the handful of ranks of its range through a 64-bit presence mask.  24 KB of shared memory for
+// the real table, so five blocks of 256 threads are resident per SM and short contigs stop paying
+// for the width of the table.
+// ------------------------------------------------------------------------------------------
+
+constexpr int KS_SMALL_MAX = 4096;  // windows per contig the short-contig kernel takes
+constexpr int KS_SMALL_THREADS = 256;
+
+BS_HD int ks_small_ranges(int R_x) { return (R_x + 63) >> 6; }
+BS_HD size_t ks_small_smem_bytes(int R_x) { return (size_t)KS_SMALL_MAX * 8 + (size_t)(2 * ks_small_ranges(R_x) + 4) * 4; }
+
+__global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDistArgs a) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    __shared__ int64_t s_wmax[32];
+    __shared__ uint32_t s_wsum[32];
+    __shared__ int s_item;
+    uint32_t *s_rank = (uint32_t *)bs_dyn_smem();   // [KS_SMALL_MAX] rank of the window at p
+    uint32_t *s_keys = s_rank + KS_SMALL_MAX;       // [KS_SMALL_MAX] the same ranks grouped by range
+    const int n_rng = ks_small_ranges(a.R_x);
+    uint32_t *s_off = s_keys + KS_SMALL_MAX;        // [n_rng + 1] first slot of a range = windows in smaller ranges
+    uint32_t *s_cur = s_off + n_rng + 2;            // [n_rng] counts, then scatter cursors
+    const int kshift = 64 - 2 * a.kmer;
+    const uint32_t kbits = keep_bits(a.kmer);
+    const int per = (n_rng + nthr - 1) / nthr;      // ranges per thread in the prefix sum
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1);
+        for (int i = tid; i < n_rng; i += nthr) s_cur[i] = 0;
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
+        const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
+        int nwin = (int)(L - a.kmer + 1);
+        if (nwin < 0) nwin = 0;
+        double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
+        const int64_t seg = a.ctg_seg[c];
+        const LeLt *yx = a.yx + seg * a.R_x;
+        const int64_t n_y = a.R_y > 0 ? a.ycum[seg * a.R_y + a.R_y - 1] : 0;
+        // ---- windows: table value out, rank kept, per-range counts ----
+        for (int p0 = 0; p0 < nwin; p0 += 4 * nthr) {
+            const int pb = p0 + 4 * tid;
+            double val[4];
+            int32_t rk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { val[u] = 0.0; rk[u] = a.rank_zero; }
+            if (pb < nwin && a.win) {
+                const int wi = pb >> 5;
+                const uint32_t o = (uint32_t)(pb & 31);
+                const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
+                const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) {
+                        const WinEntry e = a.win[window64(w0, w1, o + u) >> kshift];
+                        val[u] = e.prob;
+                        rk[u] = e.rank;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (pb + u < nwin) {
+                    if (pd) pd[pb + u] = val[u];
+                    s_rank[pb + u] = (uint32_t)rk[u];
+                    atomicAdd(&s_cur[rk[u] >> 6], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- exclusive prefix of the range counts ----
+        const int lo_r = tid * per < n_rng ? tid * per : n_rng, hi_r = lo_r + per < n_rng ? lo_r + per : n_rng;
+        uint32_t sum = 0;
+        for (int i = lo_r; i < hi_r; i++) sum += s_cur[i];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t run0 = incl - sum;
+        for (int w = 0; w < warp; w++) run0 += s_wsum[w];
+        for (int i = lo_r; i < hi_r; i++) {
+            const uint32_t cnt = s_cur[i];
+            s_off[i] = run0;
+            s_cur[i] = run0;  // scatter cursor
+            run0 += cnt;
+        }
+        if (tid == 0) s_off[n_rng] = (uint32_t)nwin;
+        __syncthreads();
+        // ---- scatter the ranks into their ranges ----
+        for (int p = tid; p < nwin; p += nthr) {
+            const uint32_t r = s_rank[p];
+            s_keys[atomicAdd(&s_cur[r >> 6], 1u)] = r;
+        }
+        __syncthreads();
+        // ---- every range in rank order: statistic just below and at each present x value ----
+        int64_t best = 0;
+        const bool defined = nwin > 0 && n_y > 0;
+        if (defined) {
+            for (int r = tid; r < n_rng; r += nthr) {
+                const uint32_t g0 = s_off[r], g1 = s_off[r + 1];
+                if (g1 == g0) continue;
+                uint64_t present = 0;
+                for (uint32_t i = g0; i < g1; i++) present |= 1ull << (s_keys[i] & 63u);
+                int64_t run = g0;  // windows with a smaller rank
+                while (present) {
+                    const int bit = __ffsll((long long)present) - 1;
+                    present &= present - 1;
+                    const uint32_t rank = ((uint32_t)r << 6) + (uint32_t)bit;
+                    uint32_t cnt = 0;
+                    for (uint32_t i = g0; i < g1; i++) cnt += s_keys[i] == rank;
+                    const LeLt q = yx[rank];
+                    int64_t d1 = run * n_y - (int64_t)q.lt * nwin;
+                    run += cnt;
+                    int64_t d2 = run * n_y - (int64_t)q.le * nwin;
+                    if (d1 < 0) d1 = -d1;
+                    if (d2 < 0) d2 = -d2;
+                    if (d1 > best) best = d1;
+                    if (d2 > best) best = d2;
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const int64_t o = __shfl_xor_sync(FULL_MASK, best, m);
+            if (o > best) best = o;
+        }
+        if (lane == 0) s_wmax[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nwarp; w++) if (s_wmax[w] > best) best = s_wmax[w];
+            a.ks[c] = defined ? (double)best / ((double)nwin * (double)n_y) : __longlong_as_double(0x7ff8000000000000ll);
+        }
+    }
+}
+
 }  // namespace bs
