@@ -335,17 +335,23 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// The same for SHORT contigs (at most KS_SMALL_MAX windows: nine in ten of a velvet-style set).
+// The same for SHORT contigs (at most KS_SMALL_MAX windows: three in four of a velvet-style set).
 // Instead of a rank histogram as wide as the table (66 KB, swept per contig) the block sorts the
 // contig's window ranks by a counting pass over ranges of 64 ranks: per-range counts -> offsets
 // (which are already the number of windows with a smaller rank) -> scatter; a thread then orders
-// the handful of ranks of its range through a 64-bit presence mask.  24 KB of shared memory for
-// the real table, so five blocks of 256 threads are resident per SM and short contigs stop paying
+// the handful of ranks of its range through a 64-bit presence mask.  20 KB of shared memory for
+// the real table, so eight blocks of 256 threads are resident per SM and short contigs stop paying
 // for the width of the table.
 // ------------------------------------------------------------------------------------------
 
-constexpr int KS_SMALL_MAX = 4096;  // windows per contig the short-contig kernel takes
-constexpr int KS_SMALL_THREADS = 256;
+#ifndef BS_KS_SMALL_MAX
+#define BS_KS_SMALL_MAX 2048
+#endif
+#ifndef BS_KS_SMALL_THREADS
+#define BS_KS_SMALL_THREADS 256
+#endif
+constexpr int KS_SMALL_MAX = BS_KS_SMALL_MAX;  // windows per contig the short-contig kernel takes
+constexpr int KS_SMALL_THREADS = BS_KS_SMALL_THREADS;
 
 BS_HD int ks_small_ranges(int R_x) { return (R_x + 63) >> 6; }
 BS_HD size_t ks_small_smem_bytes(int R_x) { return (size_t)KS_SMALL_MAX * 8 + (size_t)(2 * ks_small_ranges(R_x) + 4) * 4; }
