@@ -125,7 +125,7 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
     return t;
 }
 
-__global__ void __launch_bounds__(256) k_break_score(ScoreArgs a) {
+__global__ void __launch_bounds__(256, 5) k_break_score(ScoreArgs a) {
     __shared__ double s_w[32];
     __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
     __shared__ int s_item, s_novf, s_maxc, s_nz;
