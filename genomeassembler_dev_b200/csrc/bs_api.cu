@@ -717,7 +717,9 @@ int ChunkRun::place() {
         StageTimer tm(ctx, ST_PLACE, st);
         if (N > 0 && C > 0 && !tile_mode) {
             // per-block scratch row of leftmost positions, all POS_INF between launches
-            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads)));
+            int place_per_sm = blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads));
+            if (const char *env = std::getenv("BS_PLACE_BLOCKS_PER_SM")) place_per_sm = std::max(1, std::min(place_per_sm, std::atoi(env)));  // tuning
+            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * place_per_sm);
             const int64_t stride = (max_seg_reads + 31) / 32 * 32;
             const int64_t budget = (int64_t)8 << 30;
             nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * 4, 1)));
