@@ -162,7 +162,7 @@ constexpr int PACK_WARP_CELLS = 66;  // 16-byte cells a warp tile (32 words = at
 // out of two or three cells with funnel shifts.  Warps never wait for one another (__syncwarp
 // only).  A cell holding any byte outside ACGT flags every read that overlaps it (conservative:
 // flagged reads are verified by byte comparison, still exact).
-__global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_uniform(ReadSet r, ReadIndex ix) {
+__global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet r, ReadIndex ix) {
     __shared__ uint32_t s_code_all[PACK_THREADS / 32][PACK_WARP_CELLS];
     __shared__ uint32_t s_bad_all[PACK_THREADS / 32][PACK_WARP_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

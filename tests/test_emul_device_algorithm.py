@@ -140,3 +140,51 @@ def check_second_table(scorer, kmers, prob, seg):
 
 def test_second_table_in_one_call(emul_scorer, kmers, prob):
     check_second_table(emul_scorer, kmers, prob, P.make(43, 2500, 50, 10, 5, 1))
+
+
+def check_irregular_batch(scorer, oracle, kmers, prob, chunk_env=None):
+    """segments without contigs, without reads, with ragged reads and with very long reads, in one batch"""
+    from genomeassembler_dev_b200 import synth
+    rng = np.random.default_rng(77)
+    segs = []
+    for i, (L, r, nc) in enumerate([(1500, 30, 3), (1200, 25, 0), (1800, 40, 4), (1000, 20, 2), (3000, 1000, 2)]):
+        segs.append(synth.make_segment(500 + i, length=L, read_len=r, coverage=6 if r < 100 else 3, n_contigs=max(nc, 1), mut_frac=0.3))
+    reads, contigs, truths, srs, scs = [], [], [], [0], [0]
+    for i, sg in enumerate(segs):
+        rl = sg.read_list
+        if i == 0:
+            rl = [x[: int(rng.integers(5, 31))] for x in rl]   # ragged
+        if i == 3:
+            rl = []                                            # no reads
+        cs = [] if i == 1 else sg.contigs                      # no contigs
+        reads += rl; contigs += cs; truths.append(sg.truth)
+        srs.append(len(reads)); scs.append(len(contigs))
+    rd, rd_off = B.flatten(reads)
+    ct, ct_off = B.flatten(contigs)
+    tr, tr_off = B.flatten(truths)
+    scorer.set_table(kmers, prob)
+    res = scorer.score_batch(rd, rd_off, 0, ct, ct_off, tr, tr_off, srs, scs, flags=B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_LEV)
+    for s in range(len(segs)):
+        c0, c1 = scs[s], scs[s + 1]
+        if c1 == c0:
+            continue
+        want = oracle.oracle_calc_breakscore(contigs[c0:c1], reads[srs[s]:srs[s + 1]], truths[s], 8, kmers, prob,
+                                             want_hist=True, want_lev=True)
+        for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos", "hist", "lev_dist_vs_true"):
+            assert np.array_equal(res[k][c0:c1], want[k]), (s, k)
+        for k in ("bp_score", "bp_score_norm_by_break_freqs", "ks_stat_prob_dist", "ks_stat_path_freq"):
+            np.testing.assert_allclose(res[k][c0:c1], want[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=f"{s} {k}")
+        off = res["path_prob_dist_off"]
+        for c in range(c0, c1):
+            assert np.array_equal(res["path_prob_dist_flat"][off[c]:off[c + 1]], want["path_prob_dist"][c - c0])
+    return res
+
+
+def test_irregular_batch(emul_scorer, oracle, kmers, prob):
+    check_irregular_batch(emul_scorer, oracle, kmers, prob)
+
+
+def test_irregular_batch_in_small_chunks(emul_lib, oracle, kmers, prob, monkeypatch):
+    monkeypatch.setenv("BS_CHUNK_KB", "3")
+    with B.BreakageScorer(0, emul_lib) as sc:
+        check_irregular_batch(sc, oracle, kmers, prob)

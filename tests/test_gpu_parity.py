@@ -322,3 +322,13 @@ def test_async_device_resident_calls_reuse_workspaces(product_lib, kmers, prob, 
 def test_second_table_in_one_call(gpu_scorer, kmers, prob):
     from test_emul_device_algorithm import check_second_table
     check_second_table(gpu_scorer, kmers, prob, P.make(44, 50000, 150, 30, 20, 1))
+
+
+def test_irregular_batch(product_lib, gpu_scorer, oracle, kmers, prob, monkeypatch):
+    from test_emul_device_algorithm import check_irregular_batch
+    one = check_irregular_batch(gpu_scorer, oracle, kmers, prob)
+    monkeypatch.setenv("BS_CHUNK_KB", "3")
+    with B.BreakageScorer(0, product_lib) as sc:
+        many = check_irregular_batch(sc, oracle, kmers, prob)
+    for k in one:
+        assert np.array_equal(one[k], many[k], equal_nan=True), k
