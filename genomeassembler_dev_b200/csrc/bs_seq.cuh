@@ -166,12 +166,16 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
     __shared__ uint32_t s_code_all[PACK_THREADS / 32][PACK_WARP_CELLS];
     __shared__ uint32_t s_bad_all[PACK_THREADS / 32][PACK_WARP_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *s_code = s_code_all[warp], *s_bad = s_bad_all[warp];
+    __shared__ uint32_t s_seg_all[PACK_THREADS / 32][4];  // the warp's current segment: seed length, table mask, table offset
+    uint32_t *s_code = s_code_all[warp], *s_bad = s_bad_all[warp], *s_seg = s_seg_all[warp];
     const int64_t n_words = r.n * r.W;
     const int64_t total_bytes = r.n * (int64_t)r.uniform_len;
-    const uintptr_t base = (uintptr_t)r.chars;
+    const uint32_t base15 = (uint32_t)((uintptr_t)r.chars & 15);
     const int L = r.uniform_len;
     const uint32_t W = (uint32_t)r.W;
+    // x / W for the small x met below (x * W < 2^32) by one multiply
+    const uint32_t w_magic = W > 1 ? (uint32_t)((0x100000000ull + W - 1) / W) : 0u;
+    auto div_w = [&](uint32_t x) { return W > 1 ? __umulhi(x, w_magic) : x; };
     // every warp owns a contiguous run of tiles: consecutive tiles read adjacent bytes and stay in
     // the same segment, and the next tile's loads can be issued before the current one is finished
     const int64_t warps_total = (int64_t)gridDim.x * (PACK_THREADS / 32);
@@ -182,31 +186,58 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
     int64_t k_end = k0 + per_warp * 32;
     if (k_end > n_words) k_end = n_words;
     if (k0 >= k_end) return;
-    // (read, word-in-read) of the tile's first word: one 64-bit division, then 32-bit increments
-    int64_t n0 = k0 / W;
-    uint32_t j0 = (uint32_t)(k0 - n0 * W);
+    uint64_t *wp = r.words + k0;             // the tile's first output word
+    uint32_t left = (uint32_t)(k_end - k0);  // words this warp still has to write
+    // (read, word-in-read, first source byte) of the tile's first word: one 64-bit division here,
+    // then increments
+    uint32_t n0 = (uint32_t)(k0 / W);  // read ids fit 32 bits (the host refuses more reads per call)
+    uint32_t j0 = (uint32_t)(k0 - (int64_t)n0 * W);
+    int64_t lo0 = (int64_t)n0 * L + (int64_t)j0 * 32;
     const uint32_t adv = 32u % W, adv_n = 32u / W;
-    int seg = ix.head ? segment_of_read(ix, n0) : 0;
+    const int32_t adv_bytes = (int32_t)adv_n * L + (int32_t)adv * 32, wrap_bytes = L - (int32_t)W * 32;
+
+    // the segment of the tile's first read, its end and its index geometry, kept in registers
+    int seg = 0;
+    uint32_t seg_next = 0xffffffffu;  // first read of the next segment
+    auto load_segment = [&]() {
+        seg_next = seg + 1 < ix.n_seg ? (uint32_t)ix.seg_read_start[seg + 1] : 0xffffffffu;
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t off = ix.tab_off[seg];
+            s_seg[0] = (uint32_t)ix.seed_len[seg];
+            s_seg[1] = (uint32_t)ix.tab_mask[seg];
+            s_seg[2] = (uint32_t)off;
+            s_seg[3] = (uint32_t)(off >> 32);
+        }
+        __syncwarp();
+    };
+    if (ix.head) {
+        seg = segment_of_read(ix, n0);
+        load_segment();
+    }
 
     // geometry of a tile and the (up to three) 16-byte cells this lane stages for it
-    struct Tile { int64_t lo16; int n_cells; int ntile; };
-    auto tile_of = [&](int64_t k, int64_t n, uint32_t j) {
+    struct Tile { int64_t lo16; int n_cells; int ntile; int mis; bool inside; };
+    auto tile_of = [&](uint32_t words_left, int64_t lo, uint32_t j) {
         Tile t;
-        t.ntile = (int)(k_end - k < 32 ? k_end - k : 32);
+        t.ntile = (int)(words_left < 32u ? words_left : 32u);
         const uint32_t xl = j + (uint32_t)t.ntile - 1;
-        const uint32_t dnl = xl / W;
-        const int64_t lo = n * L + (int64_t)j * 32;                          // first source byte of the tile
-        int64_t hi = (n + dnl) * L + (int64_t)(xl - dnl * W) * 32 + 32;      // one past the last
+        const uint32_t dnl = div_w(xl);
+        // bytes from the tile's first source byte to one past its last
+        const int32_t span = (int32_t)dnl * L + ((int32_t)(xl - dnl * W) - (int32_t)j) * 32 + 32;
+        int64_t hi = lo + span;
         if (hi > total_bytes) hi = total_bytes;
-        t.lo16 = lo - (int64_t)((base + (uintptr_t)lo) & 15);               // 16-byte aligned address, may be < 0
+        t.mis = (int)((base15 + ((uint32_t)lo & 15u)) & 15u);
+        t.lo16 = lo - t.mis;  // 16-byte aligned address, may be < 0
         t.n_cells = (int)((hi - t.lo16 + 15) >> 4);
+        t.inside = t.lo16 >= 0 && t.lo16 + 16 * (int64_t)t.n_cells <= total_bytes;
         return t;
     };
     auto load_cell = [&](const Tile &t, int ci) {
         uint4 v = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
         if (ci < t.n_cells) {
             const int64_t cb = t.lo16 + 16 * (int64_t)ci;
-            if (cb >= 0 && cb + 16 <= total_bytes) {
+            if (t.inside || (cb >= 0 && cb + 16 <= total_bytes)) {
                 v = *reinterpret_cast<const uint4 *>(r.chars + cb);
             } else {  // partly outside the buffer: bytes that do not exist read as 'A'
                 uint32_t xs[4];
@@ -224,8 +255,9 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
         return v;
     };
 
-    Tile t = tile_of(k0, n0, j0);
-    uint4 c0 = load_cell(t, lane), c1 = load_cell(t, lane + 32), c2 = load_cell(t, lane + 64);
+    Tile t = tile_of(left, lo0, j0);
+    uint4 c0 = load_cell(t, lane), c1 = load_cell(t, lane + 32), c2 = c0;
+    if (t.n_cells > 64) c2 = load_cell(t, lane + 64);
     for (;;) {
         // ---- convert this tile's cells into the warp's shared-memory slice ----
         __syncwarp();
@@ -236,7 +268,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
             diff = 0;
             s_code[lane + 32] = pack16(c1.x, c1.y, c1.z, c1.w, diff);
             s_bad[lane + 32] = diff;
-            if (lane + 64 < PACK_WARP_CELLS) {
+            if (t.n_cells > 64 && lane + 64 < PACK_WARP_CELLS) {  // a tile rarely reaches into a 65th cell
                 diff = 0;
                 s_code[lane + 64] = pack16(c2.x, c2.y, c2.z, c2.w, diff);
                 s_bad[lane + 64] = diff;
@@ -245,25 +277,27 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
         __syncwarp();
         // ---- issue the next tile's loads before cutting this tile's words ----
         const Tile cur = t;
-        const int64_t k_cur = k0, n_cur = n0;
-        const uint32_t j_cur = j0;
-        k0 += 32;
+        uint64_t *const wp_cur = wp;
+        const uint32_t n_cur = n0, j_cur = j0;
+        wp += 32;
+        left = left > 32u ? left - 32u : 0u;
         n0 += adv_n;
         j0 += adv;
-        if (j0 >= W) { j0 -= W; n0++; }
-        const bool more = k0 < k_end;
+        lo0 += adv_bytes;
+        if (j0 >= W) { j0 -= W; n0++; lo0 += wrap_bytes; }
+        const bool more = left != 0u;
         if (more) {
-            t = tile_of(k0, n0, j0);
+            t = tile_of(left, lo0, j0);
             c0 = load_cell(t, lane);
             c1 = load_cell(t, lane + 32);
-            c2 = load_cell(t, lane + 64);
+            if (t.n_cells > 64) c2 = load_cell(t, lane + 64);
         }
         if (lane < cur.ntile) {
             const uint32_t x = j_cur + (uint32_t)lane;
-            const uint32_t dn = x / W;
-            const int64_t n = n_cur + dn;
+            const uint32_t dn = div_w(x);
+            const uint32_t n = n_cur + dn;
             const int j = (int)(x - dn * W);
-            const int a = (int)(n * L + 32 * j - cur.lo16);  // byte offset inside the staged span (< 1100)
+            const int a = cur.mis + (int)dn * L + (j - (int)j_cur) * 32;  // byte offset inside the staged span (< 1100)
             const int ci = a >> 4;
             const uint32_t sh = 2u * (uint32_t)(a & 15);
             const int rem = L - 32 * j;  // bases of this word that belong to the read (may exceed 32)
@@ -273,7 +307,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
             const uint32_t o_hi = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
             const uint32_t o_lo = sh ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;
             const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(rem);
-            r.words[k_cur + lane] = word;
+            wp_cur[lane] = word;
             // cells overlapping this word's own bytes [a, a + min(rem, 32))
             const int last_cell = (a + (rem < 32 ? rem : 32) - 1) >> 4;
             uint32_t bad = s_bad[ci];
@@ -281,13 +315,23 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
             if (last_cell >= ci + 2) bad |= s_bad[i2];
             if (bad) atomicOr(reinterpret_cast<unsigned *>(r.flags) + (n >> 2), 1u << (8 * (int)(n & 3)));
             if (j == 0 && ix.head) {
-                int sg = seg;  // reads of a tile rarely span more than one segment
-                while (sg + 1 < ix.n_seg && n >= ix.seg_read_start[sg + 1]) sg++;
-                index_insert(ix, sg, n, word, L, bad != 0);
+                if (n < seg_next && !bad) {  // the common case: same segment as the tile's first read
+                    const uint64_t seed = word & keep_bases((int)s_seg[0]);
+                    const uint32_t h = seed_hash(seed) & s_seg[1];
+                    const int64_t slot = (int64_t)(((uint64_t)s_seg[3] << 32) | s_seg[2]) + h;
+                    ix.next[n] = make_uint2(atomicExch(&ix.head[slot], n + 1u), seed_tag(seed));
+                } else {
+                    int sg = seg;
+                    while (sg + 1 < ix.n_seg && (int64_t)n >= ix.seg_read_start[sg + 1]) sg++;
+                    index_insert(ix, sg, n, word, L, bad != 0);
+                }
             }
         }
         if (!more) break;
-        if (ix.head) while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
+        if (ix.head && n0 >= seg_next) {
+            while (seg + 1 < ix.n_seg && (int64_t)n0 >= ix.seg_read_start[seg + 1]) seg++;
+            load_segment();
+        }
     }
 }
 

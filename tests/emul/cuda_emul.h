@@ -209,6 +209,7 @@ inline T __shfl_up_sync(unsigned, T v, unsigned d) {
     unsigned l = bs_emul::t_lane;
     return bs_emul_shfl(v, l >= d ? l - d : l);
 }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     const uint64_t v = ((uint64_t)y << 32) | x;
     unsigned r = 0;

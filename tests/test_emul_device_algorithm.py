@@ -188,3 +188,44 @@ def test_irregular_batch_in_small_chunks(emul_lib, oracle, kmers, prob, monkeypa
     monkeypatch.setenv("BS_CHUNK_KB", "3")
     with B.BreakageScorer(0, emul_lib) as sc:
         check_irregular_batch(sc, oracle, kmers, prob)
+
+
+def check_uniform_read_lengths(scorer, oracle, kmers, prob, lengths):
+    """dense reads of one length (the fast packing kernel): word-boundary lengths, tiles of packed words that
+    span several small segments, reads with bytes outside ACGT"""
+    rng = np.random.default_rng(99)
+    scorer.set_table(kmers, prob)
+    for L in lengths:
+        truths, contigs, reads, srs, scs = [], [], [], [0], [0]
+        for s, n_reads in enumerate([3, 1, 0, 9, 2, 14]):
+            t = bytes(rng.choice(list(b"ACGT"), size=L + 60 + 17 * s).astype(np.uint8))
+            cs = [t[5:], t[: L + 20], t[3:L + 3] + b"N" + t[L + 4:L + 30]]
+            rl = []
+            for i in range(n_reads):
+                a = int(rng.integers(0, len(t) - L + 1))
+                x = bytearray(t[a:a + L])
+                if i % 5 == 4:
+                    x[int(rng.integers(0, L))] = ord("N")      # flagged: placed by byte comparison
+                if i % 7 == 6:
+                    x[L - 1] = ord("acgt"[i % 4])               # lowercase never matches
+                rl.append(bytes(x))
+            truths.append(t); contigs += cs; reads += rl
+            srs.append(len(reads)); scs.append(len(contigs))
+        rd, _ = B.flatten(reads)
+        ct, ct_off = B.flatten(contigs)
+        tr, tr_off = B.flatten(truths)
+        res = scorer.score_batch(rd, None, L, ct, ct_off, tr, tr_off, srs, scs, flags=B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS)
+        for s in range(len(truths)):
+            c0, c1 = scs[s], scs[s + 1]
+            want = oracle.oracle_calc_breakscore(contigs[c0:c1], reads[srs[s]:srs[s + 1]], truths[s], 8, kmers, prob,
+                                                 want_hist=True, want_pos=True)
+            for k in ("kmer_breaks", "path_prob_dist_startpos", "hist"):
+                assert np.array_equal(res[k][c0:c1], want[k]), (L, s, k)
+            np.testing.assert_allclose(res["bp_score"][c0:c1], want["bp_score"], rtol=1e-9, err_msg=f"L={L} seg={s}")
+
+
+UNIFORM_LENGTHS = [1, 5, 16, 31, 32, 33, 64, 65, 96, 127, 128, 129, 150, 160, 192, 321]
+
+
+def test_uniform_read_lengths(emul_scorer, oracle, kmers, prob):
+    check_uniform_read_lengths(emul_scorer, oracle, kmers, prob, UNIFORM_LENGTHS)

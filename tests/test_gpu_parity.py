@@ -332,3 +332,8 @@ def test_irregular_batch(product_lib, gpu_scorer, oracle, kmers, prob, monkeypat
         many = check_irregular_batch(sc, oracle, kmers, prob)
     for k in one:
         assert np.array_equal(one[k], many[k], equal_nan=True), k
+
+
+def test_uniform_read_lengths(gpu_scorer, oracle, kmers, prob):
+    from test_emul_device_algorithm import UNIFORM_LENGTHS, check_uniform_read_lengths
+    check_uniform_read_lengths(gpu_scorer, oracle, kmers, prob, UNIFORM_LENGTHS + [250, 1000])
