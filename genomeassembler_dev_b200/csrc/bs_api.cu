@@ -36,6 +36,7 @@ constexpr int kLevThreads = 64;
 constexpr int kSimThreads = 64;
 constexpr int kKsThreads = 64;
 constexpr int kSpectrumThreads = 64;
+constexpr int kSpectrumTabThreads = 64;
 constexpr int kPackThreads = 64;
 constexpr int kPlaceIxThreads = 64;
 #else
@@ -46,6 +47,7 @@ constexpr int kLevThreads = 128;
 constexpr int kSimThreads = 256;
 constexpr int kKsThreads = 768;     // one sweep round covers the 515 ranges of the real table's rank histogram
 constexpr int kSpectrumThreads = 512;
+constexpr int kSpectrumTabThreads = bs::SPECTRUM_TAB_THREADS;
 constexpr int kPackThreads = 256;
 constexpr int kPlaceIxThreads = 256;
 #endif
@@ -776,9 +778,17 @@ int ChunkRun::spectrum() {
         sp.R_y = R_y; sp.kmer = kmer; sp.blocks_per_seg = 1;
         sp.lelt = ks_a ? (const bs::LeLt *)k.lelt.p : nullptr; sp.yx = ks_a ? (bs::LeLt *)ws.yx.p : nullptr; sp.R_x = k.R_x;
         if (k.R_y > 0 && kmer <= bs::MAXK && max_tr - kmer + 1 < 65536 && sp_smem + 1024 <= ctx->smem_optin) {
-            // one block per segment, histogram and prefix sum in shared memory
-            BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
-            BS_LAUNCH(bs::k_truth_spectrum_smem, (unsigned)S, kSpectrumThreads, sp_smem, st, sp);
+            // histogram and prefix sum in shared memory; with the rank table beside them when it fits
+            // (ranks below 65 535, k-mers up to 8): one block per SM walking over the segments
+            const size_t tab_smem = sp_smem + ((size_t)2 << (2 * kmer));
+            const char *tab_env = std::getenv("BS_SPECTRUM_TABLE");  // tests: 0 keeps the rank table in global memory
+            if (kmer <= 8 && k.R_y < 65535 && tab_smem + 1024 <= ctx->smem_optin && !(tab_env && tab_env[0] == '0')) {
+                BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
+                BS_LAUNCH(bs::k_truth_spectrum_smem<true>, (unsigned)std::min<int64_t>(S, ctx->sm_count), kSpectrumTabThreads, tab_smem, st, sp, (int)S);
+            } else {
+                BS_CUDA(cudaFuncSetAttribute(bs::k_truth_spectrum_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp_smem));
+                BS_LAUNCH(bs::k_truth_spectrum_smem<false>, (unsigned)S, kSpectrumThreads, sp_smem, st, sp, (int)S);
+            }
             ctx->launches++;
         } else {
             BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, st));

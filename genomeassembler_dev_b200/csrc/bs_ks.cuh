@@ -11,9 +11,19 @@ namespace bs {
 
 // per x-value rank: index into the truth cumulative counts of the last y value <= / < that x value
 // (table level), or the cumulative counts themselves (segment level, yx below)
-struct LeLt {
+struct alignas(8) LeLt {  // one 8-byte gather
     int32_t le, lt;
 };
+
+// KS numerator at one x value: |F_x - F_y| * nwin * n_y just below the value (n_lt windows, y_lt truth
+// windows smaller) and at it.  Every factor is below 2^31: 32 x 32 -> 64-bit products.
+BS_HD int64_t ks_numerator(uint32_t n_lt, uint32_t n_le, LeLt y, uint32_t n_y, uint32_t nwin) {
+    int64_t d1 = (int64_t)((uint64_t)n_lt * n_y) - (int64_t)((uint64_t)(uint32_t)y.lt * nwin);
+    int64_t d2 = (int64_t)((uint64_t)n_le * n_y) - (int64_t)((uint64_t)(uint32_t)y.le * nwin);
+    if (d1 < 0) d1 = -d1;
+    if (d2 < 0) d2 = -d2;
+    return d1 > d2 ? d1 : d2;
+}
 
 struct SpectrumArgs {
     const int64_t *tr_off;
@@ -46,76 +56,106 @@ __global__ void k_truth_spectrum(SpectrumArgs a) {
     }
 }
 
-// The same for truths of fewer than 65 536 windows, one block per segment: counts in shared
+// The same for truths of fewer than 65 536 windows, a block per segment at a time: counts in shared
 // memory (two 16-bit counters per word), cumulated in place, written out once, coalesced.
-__global__ void __launch_bounds__(512, 3) k_truth_spectrum_smem(SpectrumArgs a) {
+// TAB: the block also keeps the rank table in shared memory (16-bit ranks, 128 KB for 8-mers) and
+// walks over segments: a window's rank is then a shared-memory lookup instead of a divergent
+// global gather (32 L1 wavefronts per warp), which is what bounds the plain variant.
+constexpr int SPECTRUM_TAB_THREADS = 1024;
+constexpr uint32_t SPECTRUM_NO_RANK = 0xffffu;
+
+template <bool TAB>
+__global__ void __launch_bounds__(TAB ? SPECTRUM_TAB_THREADS : 512, TAB ? 1 : 3) k_truth_spectrum_smem(SpectrumArgs a, int n_seg) {
     uint32_t *s_h = (uint32_t *)bs_dyn_smem();
     __shared__ uint32_t s_wsum[32];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t s = blockIdx.x;
-    const int64_t L = a.tr_off[s + 1] - a.tr_off[s];
-    const uint64_t *gw = a.tr_words + a.tr_woff[s];
-    const uint32_t *gm = a.tr_mask + a.tr_woff[s];
-    const int64_t nwin = L - a.kmer + 1;
     const int kshift = 64 - 2 * a.kmer;
     const uint32_t kbits = keep_bits(a.kmer);
     const int nword = (a.R_y + 1) >> 1;
-    for (int i = tid; i < nword; i += nthr) s_h[i] = 0;
-    __syncthreads();
-    // a thread takes four CONSECUTIVE windows (never straddling a 32-base word boundary): the truth
-    // words are loaded once per four windows and the four rank gathers are in flight together
-    for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {
-        const int64_t pb = p0 + 4 * (int64_t)tid;
-        if (pb >= nwin) continue;
-        const int64_t wi = pb >> 5;
-        const uint32_t o = (uint32_t)(pb & 31);
-        const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
-        const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
-        int32_t rk[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            rk[u] = -1;
-            if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) rk[u] = __ldg(&a.rank_y[window64(w0, w1, o + u) >> kshift]);
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_h + nword);  // TAB: [4^kmer]
+    if (TAB) {
+        const int n_codes = 1 << (2 * a.kmer);
+        for (int i = tid; i < n_codes; i += nthr) {
+            const int32_t r = a.rank_y[i];
+            s_tab[i] = (uint16_t)(r < 0 ? SPECTRUM_NO_RANK : (uint32_t)r);
         }
+    }
+    for (int64_t s = blockIdx.x; s < n_seg; s += gridDim.x) {
+        const int64_t L = a.tr_off[s + 1] - a.tr_off[s];
+        const uint64_t *gw = a.tr_words + a.tr_woff[s];
+        const uint32_t *gm = a.tr_mask + a.tr_woff[s];
+        const int64_t nwin = L - a.kmer + 1;
+        __syncthreads();  // the previous segment's counts have been written out (and the table is loaded)
+        for (int i = tid; i < nword; i += nthr) s_h[i] = 0;
+        __syncthreads();
+        // a thread takes eight CONSECUTIVE windows (never straddling a 32-base word boundary): the
+        // truth words are loaded once per eight windows (the next group's while this one is counted)
+        constexpr int PER = 8;
+        const int64_t step = PER * (int64_t)nthr;
+        int64_t pb = PER * (int64_t)tid;
+        uint64_t w0 = 0, w1 = 0;
+        uint32_t m0 = 0, m1 = 0;
+        if (pb < nwin) { w0 = __ldg(&gw[pb >> 5]); w1 = __ldg(&gw[(pb >> 5) + 1]); m0 = __ldg(&gm[pb >> 5]); m1 = __ldg(&gm[(pb >> 5) + 1]); }
+        for (; pb < nwin; pb += step) {
+            const uint64_t c0 = w0, c1 = w1;
+            const uint32_t d0 = m0, d1 = m1;
+            const int64_t nb = pb + step;
+            if (nb < nwin) { w0 = __ldg(&gw[nb >> 5]); w1 = __ldg(&gw[(nb >> 5) + 1]); m0 = __ldg(&gm[nb >> 5]); m1 = __ldg(&gm[(nb >> 5) + 1]); }
+            const uint32_t o = (uint32_t)(pb & 31);
+            int32_t rk[PER];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (rk[u] >= 0) atomicAdd(&s_h[rk[u] >> 1], 1u << (16 * (rk[u] & 1)));
-    }
-    __syncthreads();
-    // inclusive prefix over ranks: every thread owns an even number of consecutive ranks
-    int per = (a.R_y + nthr - 1) / nthr;
-    per += per & 1;
-    const int lo = tid * per < a.R_y ? tid * per : a.R_y;
-    const int hi = lo + per < a.R_y ? lo + per : a.R_y;
-    uint32_t sum = 0;
-    for (int i = lo >> 1; i < (hi + 1) >> 1; i++) { const uint32_t w = s_h[i]; sum += (w & 0xffffu) + (w >> 16); }
-    uint32_t incl = sum;
+            for (int u = 0; u < PER; u++) {
+                rk[u] = -1;
+                if (pb + u < nwin && !(window32(d0, d1, o + u) & kbits)) {
+                    const uint64_t code = window64(c0, c1, o + u) >> kshift;
+                    if (TAB) {
+                        const uint32_t r = s_tab[code];
+                        rk[u] = r == SPECTRUM_NO_RANK ? -1 : (int32_t)r;
+                    } else {
+                        rk[u] = __ldg(&a.rank_y[code]);
+                    }
+                }
+            }
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d);
-        if (lane >= d) incl += o;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    uint32_t run = incl - sum;
-    for (int w = 0; w < warp; w++) run += s_wsum[w];
-    for (int i = lo >> 1; i < (hi + 1) >> 1; i++) {
-        const uint32_t w = s_h[i];
-        const uint32_t c0 = run + (w & 0xffffu), c1 = c0 + (w >> 16);
-        s_h[i] = c0 | (c1 << 16);  // totals stay below 65 536
-        run = c1;
-    }
-    __syncthreads();
-    int32_t *out = a.ycnt + s * a.R_y;
-    for (int i = tid; i < a.R_y; i += nthr) out[i] = (int32_t)((s_h[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-    if (a.lelt) {  // the same counts looked up per x-value rank: the KS sweep then needs one gather, not two
-        LeLt *yx = a.yx + s * a.R_x;
-        for (int i = tid; i < a.R_x; i += nthr) {
-            const LeLt q = a.lelt[i];
-            LeLt o;
-            o.le = q.le >= 0 ? (int32_t)((s_h[q.le >> 1] >> (16 * (q.le & 1))) & 0xffffu) : 0;
-            o.lt = q.lt >= 0 ? (int32_t)((s_h[q.lt >> 1] >> (16 * (q.lt & 1))) & 0xffffu) : 0;
-            yx[i] = o;
+            for (int u = 0; u < PER; u++)
+                if (rk[u] >= 0) atomicAdd(&s_h[rk[u] >> 1], 1u << (16 * (rk[u] & 1)));
+        }
+        __syncthreads();
+        // inclusive prefix over ranks: every thread owns an even number of consecutive ranks
+        int per = (a.R_y + nthr - 1) / nthr;
+        per += per & 1;
+        const int lo = tid * per < a.R_y ? tid * per : a.R_y;
+        const int hi = lo + per < a.R_y ? lo + per : a.R_y;
+        uint32_t sum = 0;
+        for (int i = lo >> 1; i < (hi + 1) >> 1; i++) { const uint32_t w = s_h[i]; sum += (w & 0xffffu) + (w >> 16); }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (int w = 0; w < warp; w++) run += s_wsum[w];
+        for (int i = lo >> 1; i < (hi + 1) >> 1; i++) {
+            const uint32_t w = s_h[i];
+            const uint32_t c0 = run + (w & 0xffffu), c1 = c0 + (w >> 16);
+            s_h[i] = c0 | (c1 << 16);  // totals stay below 65 536
+            run = c1;
+        }
+        __syncthreads();
+        int32_t *out = a.ycnt + s * a.R_y;
+        for (int i = tid; i < a.R_y; i += nthr) out[i] = (int32_t)((s_h[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        if (a.lelt) {  // the same counts looked up per x-value rank: the KS sweep then needs one gather, not two
+            LeLt *yx = a.yx + s * a.R_x;
+            for (int i = tid; i < a.R_x; i += nthr) {
+                const LeLt q = a.lelt[i];
+                LeLt o;
+                o.le = q.le >= 0 ? (int32_t)((s_h[q.le >> 1] >> (16 * (q.le & 1))) & 0xffffu) : 0;
+                o.lt = q.lt >= 0 ? (int32_t)((s_h[q.lt >> 1] >> (16 * (q.lt & 1))) & 0xffffu) : 0;
+                yx[i] = o;
+            }
         }
     }
 }
@@ -273,27 +313,27 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
         // |F_x - F_y| = |run * n_y - ycount * nwin| / (nwin * n_y): the numerator is maximised in exact
         // 64-bit integers (both factors are below 2^31), one division at the end
         int64_t best = 0;
-        int64_t carry = 0;  // windows in the ranges of earlier rounds (same value on every thread)
+        uint32_t carry = 0;  // windows in the ranges of earlier rounds (same value on every thread)
         for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {  // one range of 32 words per thread and round
             const int r = r0 + tid;
             const uint32_t m = r < a.n_ranges ? s_bm[r] : 0u;
             if (m) s_bm[r] = 0;
             const int w0 = 33 * r;  // physical index of the range's first word
-            int64_t cnt_r = 0;
+            uint32_t cnt_r = 0;
             for (uint32_t mm = m; mm; mm &= mm - 1) {
                 const uint32_t w = s_hist[w0 + __ffs((int)mm) - 1];
                 cnt_r += PACKED ? (w & 0xffffu) + (w >> 16) : w;
             }
             // exclusive prefix of the range counts over the block (+ what earlier rounds held)
-            int64_t incl = cnt_r;
+            uint32_t incl = cnt_r;
 #pragma unroll
             for (int dd = 1; dd < 32; dd <<= 1) {
-                const int64_t o = __shfl_up_sync(FULL_MASK, incl, dd);
+                const uint32_t o = __shfl_up_sync(FULL_MASK, incl, dd);
                 if (lane >= dd) incl += o;
             }
             if (lane == 31) s_wsum[warp] = incl;
             __syncthreads();
-            int64_t run = carry + incl - cnt_r;
+            uint32_t run = carry + incl - cnt_r;
             for (int w = 0; w < nwarp; w++) {
                 if (w < warp) run += s_wsum[w];
                 carry += s_wsum[w];
@@ -307,15 +347,9 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
                     const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
                     if (cnt == 0 || !defined) continue;
                     const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
-                    const LeLt q = yx[i];  // one 8-byte gather
-                    const int64_t lt = q.lt, le = q.le;
-                    int64_t d1 = run * n_y - lt * nwin;
+                    const int64_t d = ks_numerator(run, run + cnt, yx[i], (uint32_t)n_y, (uint32_t)nwin);
                     run += cnt;
-                    int64_t d2 = run * n_y - le * nwin;
-                    if (d1 < 0) d1 = -d1;
-                    if (d2 < 0) d2 = -d2;
-                    if (d1 > best) best = d1;
-                    if (d2 > best) best = d2;
+                    if (d > best) best = d;
                 }
             }
             __syncthreads();  // s_wsum is rewritten by the next round
@@ -338,8 +372,8 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
 // The same for SHORT contigs (at most KS_SMALL_MAX windows: three in four of a velvet-style set).
 // Instead of a rank histogram as wide as the table (66 KB, swept per contig) the block sorts the
 // contig's window ranks by a counting pass over ranges of 64 ranks: per-range counts -> offsets
-// (which are already the number of windows with a smaller rank) -> scatter; a thread then orders
-// the handful of ranks of its range through a 64-bit presence mask.  20 KB of shared memory for
+// (which are already the number of windows in smaller ranges) -> scatter; every window then counts
+// the handful of windows that share its range to get its own position.  20 KB of shared memory for
 // the real table, so eight blocks of 256 threads are resident per SM and short contigs stop paying
 // for the width of the table.
 // ------------------------------------------------------------------------------------------
@@ -352,6 +386,7 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
 #endif
 constexpr int KS_SMALL_MAX = BS_KS_SMALL_MAX;  // windows per contig the short-contig kernel takes
 constexpr int KS_SMALL_THREADS = BS_KS_SMALL_THREADS;
+constexpr int KS_SMALL_DIRECT = 24;  // windows sharing a range of 64 ranks up to which every window counts its own neighbours
 
 BS_HD int ks_small_ranges(int R_x) { return (R_x + 63) >> 6; }
 BS_HD size_t ks_small_smem_bytes(int R_x) { return (size_t)KS_SMALL_MAX * 8 + (size_t)(2 * ks_small_ranges(R_x) + 4) * 4; }
@@ -445,30 +480,43 @@ __global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDis
             s_keys[atomicAdd(&s_cur[r >> 6], 1u)] = r;
         }
         __syncthreads();
-        // ---- every range in rank order: statistic just below and at each present x value ----
+        // ---- statistic just below and at every x value that is present ----
         int64_t best = 0;
         const bool defined = nwin > 0 && n_y > 0;
         if (defined) {
+            const uint32_t ny = (uint32_t)n_y, nw = (uint32_t)nwin;
+            // a thread per window: windows of smaller / not larger rank = the range's first slot + those
+            // among the few windows sharing its range
+            for (int i = tid; i < nwin; i += nthr) {
+                const uint32_t key = s_keys[i];
+                const uint32_t g0 = s_off[key >> 6], g1 = s_off[(key >> 6) + 1];
+                if (g1 - g0 > (uint32_t)KS_SMALL_DIRECT) continue;
+                uint32_t n_lt = g0, n_le = g0;
+                for (uint32_t j = g0; j < g1; j++) {
+                    const uint32_t k = s_keys[j];
+                    n_lt += k < key;
+                    n_le += k <= key;
+                }
+                const int64_t d = ks_numerator(n_lt, n_le, yx[key], ny, nw);
+                if (d > best) best = d;
+            }
+            // crowded ranges (low-complexity contigs): a thread per range walks its distinct ranks in
+            // order through a 64-bit presence mask, so the work stays linear in the windows
             for (int r = tid; r < n_rng; r += nthr) {
                 const uint32_t g0 = s_off[r], g1 = s_off[r + 1];
-                if (g1 == g0) continue;
+                if (g1 - g0 <= (uint32_t)KS_SMALL_DIRECT) continue;
                 uint64_t present = 0;
                 for (uint32_t i = g0; i < g1; i++) present |= 1ull << (s_keys[i] & 63u);
-                int64_t run = g0;  // windows with a smaller rank
+                uint32_t run = g0;  // windows with a smaller rank
                 while (present) {
                     const int bit = __ffsll((long long)present) - 1;
                     present &= present - 1;
                     const uint32_t rank = ((uint32_t)r << 6) + (uint32_t)bit;
                     uint32_t cnt = 0;
                     for (uint32_t i = g0; i < g1; i++) cnt += s_keys[i] == rank;
-                    const LeLt q = yx[rank];
-                    int64_t d1 = run * n_y - (int64_t)q.lt * nwin;
+                    const int64_t d = ks_numerator(run, run + cnt, yx[rank], ny, nw);
                     run += cnt;
-                    int64_t d2 = run * n_y - (int64_t)q.le * nwin;
-                    if (d1 < 0) d1 = -d1;
-                    if (d2 < 0) d2 = -d2;
-                    if (d1 > best) best = d1;
-                    if (d2 > best) best = d2;
+                    if (d > best) best = d;
                 }
             }
         }

@@ -229,3 +229,28 @@ UNIFORM_LENGTHS = [1, 5, 16, 31, 32, 33, 64, 65, 96, 127, 128, 129, 150, 160, 19
 
 def test_uniform_read_lengths(emul_scorer, oracle, kmers, prob):
     check_uniform_read_lengths(emul_scorer, oracle, kmers, prob, UNIFORM_LENGTHS)
+
+
+def check_spectrum_variants(scorer, lib, kmers, prob):
+    """truth spectrum with the rank table in shared memory (default) == with the table in global memory"""
+    import os
+    from genomeassembler_dev_b200 import synth
+    b = synth.make_batch(9, seed=91, length=1800, read_len=30, coverage=5, contigs_lo=1, contigs_hi=4)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+            b.seg_read_start, b.seg_contig_start)
+    scorer.set_table(kmers, prob)
+    one = scorer.score_batch(*args, flags=B.DEFAULT_FLAGS)
+    os.environ["BS_SPECTRUM_TABLE"] = "0"
+    try:
+        with B.BreakageScorer(0, lib) as sc:
+            sc.set_table(kmers, prob)
+            two = sc.score_batch(*args, flags=B.DEFAULT_FLAGS)
+    finally:
+        del os.environ["BS_SPECTRUM_TABLE"]
+    assert np.isfinite(one["ks_stat_prob_dist"]).any()
+    for k in one:
+        assert np.array_equal(one[k], two[k], equal_nan=True), k
+
+
+def test_spectrum_variants(emul_scorer, emul_lib, kmers, prob):
+    check_spectrum_variants(emul_scorer, emul_lib, kmers, prob)

@@ -337,3 +337,8 @@ def test_irregular_batch(product_lib, gpu_scorer, oracle, kmers, prob, monkeypat
 def test_uniform_read_lengths(gpu_scorer, oracle, kmers, prob):
     from test_emul_device_algorithm import UNIFORM_LENGTHS, check_uniform_read_lengths
     check_uniform_read_lengths(gpu_scorer, oracle, kmers, prob, UNIFORM_LENGTHS + [250, 1000])
+
+
+def test_spectrum_variants(gpu_scorer, product_lib, kmers, prob):
+    from test_emul_device_algorithm import check_spectrum_variants
+    check_spectrum_variants(gpu_scorer, product_lib, kmers, prob)
