@@ -63,6 +63,11 @@ struct alignas(16) TabEntry {
 
 constexpr int CC_DENSE = 4096;  // counts below this are tallied in a dense shared-memory array
 constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
+#ifdef BS_CPU_EMUL
+constexpr int ROW_CAP = 96;     // (emulation: small, so that the tests run both forms of pass 2)
+#else
+constexpr int ROW_CAP = 2048;   // table rows of a contig's breaks remembered in shared memory between the passes
+#endif
 
 struct ScoreArgs {
     const int32_t *order;   // [C] contig ids, longest first
@@ -128,8 +133,9 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
 __global__ void __launch_bounds__(256, 5) k_break_score(ScoreArgs a) {
     __shared__ double s_w[32];
     __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
-    __shared__ int s_item, s_novf, s_maxc, s_nz;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    __shared__ int32_t s_rows[ROW_CAP];  // rows met in pass 1 (with repeats), for pass 2
+    __shared__ int s_item, s_novf, s_maxc, s_nz, s_nrow;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     const bool want_ks = a.ks_b != nullptr;
     int32_t *scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
     int32_t *ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(256, 5) k_break_score(ScoreArgs a) {
     if (want_ks) for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; }
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; s_nrow = 0; }
         __syncthreads();
         if (s_item >= a.n_contigs) break;
         const int64_t c = a.order[s_item];
@@ -181,6 +187,20 @@ __global__ void __launch_bounds__(256, 5) k_break_score(ScoreArgs a) {
                     }
                     if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv[u]);
                 }
+                if (want_ks) {  // remember the rows (one shared-memory counter bump per warp)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int32_t row = te[u].row;  // -1 where nothing broke
+                        const unsigned m = __ballot_sync(FULL_MASK, row >= 0);
+                        if (m == 0) continue;
+                        const int leader = __ffs((int)m) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(&s_nrow, __popc(m));
+                        base = __shfl_sync(FULL_MASK, base, leader);
+                        const int slot = base + __popc(m & ((1u << lane) - 1u));
+                        if (row >= 0 && slot < ROW_CAP) s_rows[slot] = row;
+                    }
+                }
             }
         }
         s1 = block_sum_fixed(s1, s_w);
@@ -200,6 +220,19 @@ __global__ void __launch_bounds__(256, 5) k_break_score(ScoreArgs a) {
         __threadfence_block();
         __syncthreads();
         // pass 2: whoever swaps a row's count out first owns it; tally rows per count value
+        auto tally = [&](int32_t cnt) {
+            if (cnt == 0) return;
+            atomicAdd(&s_nz, 1);
+            if (cnt < CC_DENSE) { atomicAdd(&s_cc[cnt], 1); atomicMax(&s_maxc, cnt); }
+            else {
+                const int slot = atomicAdd(&s_novf, 1);
+                if (slot < OVF_CAP) ovf[slot] = cnt; else *a.status = 1;
+            }
+        };
+        const int nrow = s_nrow;
+        if (nrow <= ROW_CAP) {  // the usual case: straight from the remembered rows, every lane busy
+            for (int i = tid; i < nrow; i += nthr) tally(atomicExch(&scratch[s_rows[i]], 0));
+        } else
         for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
             int32_t wv[4], row[4], cnt[4];
 #pragma unroll
@@ -219,15 +252,7 @@ __global__ void __launch_bounds__(256, 5) k_break_score(ScoreArgs a) {
 #pragma unroll
             for (int u = 0; u < 4; u++) cnt[u] = row[u] >= 0 ? atomicExch(&scratch[row[u]], 0) : 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (cnt[u] == 0) continue;
-                atomicAdd(&s_nz, 1);
-                if (cnt[u] < CC_DENSE) { atomicAdd(&s_cc[cnt[u]], 1); atomicMax(&s_maxc, cnt[u]); }
-                else {
-                    const int slot = atomicAdd(&s_novf, 1);
-                    if (slot < OVF_CAP) ovf[slot] = cnt[u]; else *a.status = 1;
-                }
-            }
+            for (int u = 0; u < 4; u++) tally(cnt[u]);
         }
         __syncthreads();
         // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them
