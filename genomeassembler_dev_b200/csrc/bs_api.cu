@@ -31,6 +31,7 @@ char g_create_error[512] = "";
 #ifdef BS_CPU_EMUL
 constexpr int kPlaceThreads = 64;
 constexpr int kScoreThreads = 64;
+constexpr int kBreakScoreThreads = 64;
 constexpr int kStartposThreads = 64;
 constexpr int kLevThreads = 64;
 constexpr int kSimThreads = 64;
@@ -39,9 +40,11 @@ constexpr int kSpectrumThreads = 64;
 constexpr int kSpectrumTabThreads = 64;
 constexpr int kPackThreads = 64;
 constexpr int kPlaceIxThreads = 64;
+constexpr int kHitCap = 16;           // (emulation: small, so that the tests reach the global continuation of the hit list)
 #else
 constexpr int kPlaceThreads = 256;
 constexpr int kScoreThreads = 256;
+constexpr int kBreakScoreThreads = bs::SCORE_THREADS;
 constexpr int kStartposThreads = 256;
 constexpr int kLevThreads = 128;
 constexpr int kSimThreads = 256;
@@ -49,12 +52,12 @@ constexpr int kKsThreads = 768;     // one sweep round covers the 515 ranges of 
 constexpr int kSpectrumThreads = 512;
 constexpr int kSpectrumTabThreads = bs::SPECTRUM_TAB_THREADS;
 constexpr int kPackThreads = 256;
-constexpr int kPlaceIxThreads = 256;
+constexpr int kPlaceIxThreads = bs::PLACE_IX_THREADS;
+constexpr int kHitCap = BS_PLACE_HIT_CAP;  // reads placed per contig kept in shared memory (k_place_index); more go to global memory
 #endif
 constexpr int kMaxTile = 8192;        // contig positions per shared-memory tile (tile placement modes)
 constexpr int64_t kMaxChunk = 32768;  // reads per placement work item (tile placement modes)
 constexpr int64_t kMinChunk = 2048;
-constexpr int kHitCap = 4096;         // reads placed per contig kept in shared memory (k_place_index)
 constexpr int kWorkspaces = 3;  // chunks in flight: one copying in, one computing, one copying out
 
 enum Stage { ST_H2D, ST_PACK, ST_PLACE, ST_SCORE, ST_SPECTRUM, ST_PROBDIST, ST_PATHFREQ, ST_STARTPOS, ST_D2H, ST_LEV, ST_COUNT };
@@ -132,7 +135,7 @@ struct bs_ctx {
     Workspace ws[kWorkspaces];
     unsigned ws_cursor = 0;  // workspaces rotate across calls too: an asynchronous (device-result) call may still own one
     // scratch shared by all chunks (kernels of different chunks never overlap: one compute stream)
-    DevBuf d_best, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
+    DevBuf d_best, d_hits_ovf, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
     DevBuf sim_meta, sim_chars, sim_words, sim_mask, sim_cdf, sim_starts, sim_kept, sim_reads;  // bs_simulate_reads
     size_t best_elems = 0;
     bool best_dirty = true;
@@ -732,6 +735,7 @@ int ChunkRun::place() {
                 ctx->best_elems = elems;
                 BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
             }
+            BS_TRY(ensure(ctx, ctx->d_hits_ovf, need * 4));
             ctx->best_dirty = true;  // cleared when the call ends without an error
             bs::PlaceIxArgs pa;
             pa.order = d_order; pa.n_items = (int32_t)C; pa.work_counter = (int32_t *)ctx->d_counters.p;
@@ -741,7 +745,7 @@ int ChunkRun::place() {
             pa.best = (uint32_t *)ctx->d_best.p; pa.best_stride = stride;
             pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
             pa.pos = o_pos; pa.pos_off = d_pos_off;
-            pa.hit_cap = kHitCap;
+            pa.hit_cap = kHitCap; pa.hits_ovf = (uint32_t *)ctx->d_hits_ovf.p;
             BS_CUDA(cudaFuncSetAttribute(bs::k_place_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads)));
             BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads), st, pa);
             ctx->launches++;
@@ -814,7 +818,7 @@ int ChunkRun::score(int which) {
         StageTimer tm(ctx, ST_SCORE, st);
         const KsCache &k = which ? ctx->ks2 : ctx->ks;
         const bool ksb = which ? o_ksb2 != nullptr : ks_b;
-        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kScoreThreads, 0));
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kBreakScoreThreads, 0));
         bs::ScoreArgs sa;
         std::memset(&sa, 0, sizeof(sa));
         sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + (which ? 5 : 2);
@@ -839,7 +843,7 @@ int ChunkRun::score(int which) {
             sa.zero_le = k.zero_le; sa.zero_lt = k.zero_lt; sa.y_max = k.y_max;
             sa.scratch = (int32_t *)ctx->d_scratch.p; sa.ovf_cnt = (int32_t *)ctx->d_ovf.p; sa.status = (int32_t *)ctx->d_status.p;
         }
-        BS_LAUNCH(bs::k_break_score, (unsigned)nblk, kScoreThreads, 0, st, sa);
+        BS_LAUNCH(bs::k_break_score, (unsigned)nblk, kBreakScoreThreads, 0, st, sa);
         ctx->launches++;
     }
     return BS_OK;
@@ -1098,7 +1102,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_tab2, &ctx->ks2.win, &ctx->ks2.rank_y, &ctx->ks2.lelt, &ctx->ks2.yv, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
+    DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_tab2, &ctx->ks2.win, &ctx->ks2.rank_y, &ctx->ks2.lelt, &ctx->ks2.yv, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_hits_ovf, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
                       &ctx->d_rank_scratch, &ctx->d_counters, &ctx->d_hbuf, &ctx->sim_meta, &ctx->sim_chars,
                       &ctx->sim_words, &ctx->sim_mask, &ctx->sim_cdf, &ctx->sim_starts, &ctx->sim_kept, &ctx->sim_reads};
     for (DevBuf *b : bufs) release(*b);

@@ -197,7 +197,8 @@ struct PlaceIxArgs {
     int32_t *total;       // [C] reads placed (kmer_breaks)
     int32_t *pos;         // optional
     const int64_t *pos_off;
-    int32_t hit_cap;      // shared-memory list of reads placed in the current contig
+    int32_t hit_cap;      // shared-memory list of reads placed in the current contig ...
+    uint32_t *hits_ovf;   // [gridDim][best_stride] ... and its continuation in global memory (never full: distinct reads)
 };
 
 // leftmost byte-exact occurrence of read n in contig text, or -1 (reads that cannot be packed)
@@ -239,17 +240,31 @@ __device__ __forceinline__ bool verify_at(const PlaceIxArgs &a, const uint64_t *
     return true;
 }
 
-constexpr int PLACE_CAND_CAP = 256;  // seed hits of one WARP iteration (128 positions) awaiting verification
+#ifndef BS_PLACE_IX_THREADS
+#define BS_PLACE_IX_THREADS 256
+#endif
+#ifndef BS_PLACE_IX_BLOCKS
+#define BS_PLACE_IX_BLOCKS 6
+#endif
+#ifndef BS_PLACE_HIT_CAP
+#define BS_PLACE_HIT_CAP 1024
+#endif
+constexpr int PLACE_IX_THREADS = BS_PLACE_IX_THREADS, PLACE_IX_BLOCKS = BS_PLACE_IX_BLOCKS;  // resident blocks per SM the kernel is built for
+#ifndef BS_PLACE_CAND_CAP
+#define BS_PLACE_CAND_CAP 256
+#endif
+constexpr int PLACE_CAND_CAP = BS_PLACE_CAND_CAP;  // seed hits of one WARP iteration (128 positions) awaiting verification
 
 BS_HD size_t place_index_smem_bytes(int hit_cap, int nthr) { return (size_t)hit_cap * 4 + (size_t)(nthr / 32) * PLACE_CAND_CAP * 8; }
 
-__global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
+__global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_index(PlaceIxArgs a) {
     uint32_t *s_hits = (uint32_t *)bs_dyn_smem();
     __shared__ int s_item, s_nhit, s_placed, s_ncand[32];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     // every warp queues and verifies its own candidates: no block barrier inside the position loop
     uint2 *s_cand = (uint2 *)(s_hits + a.hit_cap) + warp * PLACE_CAND_CAP;  // (read id, contig position) with an equal seed tag
     uint32_t *best = a.best + (int64_t)blockIdx.x * a.best_stride;
+    uint32_t *hits_ovf = a.hits_ovf + (int64_t)blockIdx.x * a.best_stride;
     for (;;) {
         __syncthreads();
         if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; }
@@ -282,6 +297,7 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
             if (old == POS_INF) {  // first time this read is seen in this contig
                 const int slot = atomicAdd(&s_nhit, 1);
                 if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
+                else hits_ovf[slot - a.hit_cap] = (uint32_t)(n - r0);
             }
         };
 
@@ -345,6 +361,7 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
                 best[n - r0] = (uint32_t)p;  // each such read is visited by exactly one thread
                 const int slot = atomicAdd(&s_nhit, 1);
                 if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
+                else hits_ovf[slot - a.hit_cap] = (uint32_t)(n - r0);
             }
         }
         __threadfence_block();
@@ -352,22 +369,12 @@ __global__ void __launch_bounds__(256, 5) k_place_index(PlaceIxArgs a) {
         // ---- leftmost positions -> position weights ----
         const int nh = s_nhit;
         int placed = 0;
-        if (nh <= a.hit_cap) {
-            for (int h = tid; h < nh; h += nthr) {
-                const uint32_t nl = s_hits[h];
-                const uint32_t p = atomicExch(&best[nl], POS_INF);
-                atomicAdd(&a.w[coff + c + p], 1);
-                if (a.pos) a.pos[a.pos_off[c] + nl] = (int32_t)p;
-                placed++;
-            }
-        } else {  // more distinct reads than the list holds: sweep the whole scratch row
-            for (int64_t nl = tid; nl < n_seg_reads; nl += nthr) {
-                const uint32_t p = atomicExch(&best[nl], POS_INF);
-                if (p == POS_INF) continue;
-                atomicAdd(&a.w[coff + c + p], 1);
-                if (a.pos) a.pos[a.pos_off[c] + nl] = (int32_t)p;
-                placed++;
-            }
+        for (int h = tid; h < nh; h += nthr) {
+            const uint32_t nl = h < a.hit_cap ? s_hits[h] : hits_ovf[h - a.hit_cap];
+            const uint32_t p = atomicExch(&best[nl], POS_INF);
+            atomicAdd(&a.w[coff + c + p], 1);
+            if (a.pos) a.pos[a.pos_off[c] + nl] = (int32_t)p;
+            placed++;
         }
         if (placed) atomicAdd(&s_placed, placed);
         __syncthreads();

@@ -61,12 +61,25 @@ struct alignas(16) TabEntry {
     int32_t pad;
 };
 
-constexpr int CC_DENSE = 4096;  // counts below this are tallied in a dense shared-memory array
+#ifndef BS_SCORE_THREADS
+#define BS_SCORE_THREADS 256
+#endif
+#ifndef BS_SCORE_BLOCKS
+#define BS_SCORE_BLOCKS 6
+#endif
+#ifndef BS_SCORE_CC_DENSE
+#define BS_SCORE_CC_DENSE 4096
+#endif
+#ifndef BS_SCORE_ROW_CAP
+#define BS_SCORE_ROW_CAP 2048
+#endif
+constexpr int SCORE_THREADS = BS_SCORE_THREADS, SCORE_BLOCKS = BS_SCORE_BLOCKS;  // block shape k_break_score is built for
+constexpr int CC_DENSE = BS_SCORE_CC_DENSE;  // counts below this are tallied in a dense shared-memory array
 constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
 #ifdef BS_CPU_EMUL
 constexpr int ROW_CAP = 96;     // (emulation: small, so that the tests run both forms of pass 2)
 #else
-constexpr int ROW_CAP = 2048;   // table rows of a contig's breaks remembered in shared memory between the passes
+constexpr int ROW_CAP = BS_SCORE_ROW_CAP;   // table rows of a contig's breaks remembered in shared memory between the passes
 #endif
 
 struct ScoreArgs {
@@ -130,7 +143,7 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
     return t;
 }
 
-__global__ void __launch_bounds__(256, 5) k_break_score(ScoreArgs a) {
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(ScoreArgs a) {
     __shared__ double s_w[32];
     __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
     __shared__ int32_t s_rows[ROW_CAP];  // rows met in pass 1 (with repeats), for pass 2
