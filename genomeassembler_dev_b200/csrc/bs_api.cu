@@ -135,7 +135,7 @@ struct bs_ctx {
     Workspace ws[kWorkspaces];
     unsigned ws_cursor = 0;  // workspaces rotate across calls too: an asynchronous (device-result) call may still own one
     // scratch shared by all chunks (kernels of different chunks never overlap: one compute stream)
-    DevBuf d_best, d_hits_ovf, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
+    DevBuf d_best, d_hits_ovf, d_keys, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
     DevBuf sim_meta, sim_chars, sim_words, sim_mask, sim_cdf, sim_starts, sim_kept, sim_reads;  // bs_simulate_reads
     size_t best_elems = 0;
     bool best_dirty = true;
@@ -722,33 +722,75 @@ int ChunkRun::place() {
         StageTimer tm(ctx, ST_PLACE, st);
         if (N > 0 && C > 0 && !tile_mode) {
             // per-block scratch row of leftmost positions, all POS_INF between launches
-            int place_per_sm = blocks_per_sm(bs::k_place_index, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads));
+            const size_t smem = bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads);
+            int place_per_sm = blocks_per_sm(bs::k_place_index<false>, kPlaceIxThreads, smem);
             if (const char *env = std::getenv("BS_PLACE_BLOCKS_PER_SM")) place_per_sm = std::max(1, std::min(place_per_sm, std::atoi(env)));  // tuning
-            int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * place_per_sm);
-            const int64_t stride = (max_seg_reads + 31) / 32 * 32;
-            const int64_t budget = (int64_t)8 << 30;
-            nblk = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, budget / std::max<int64_t>(stride * 4, 1)));
-            const size_t need = (size_t)nblk * (size_t)stride;
-            if (need > ctx->best_elems || ctx->best_dirty) {
-                const size_t elems = std::max(need, ctx->best_elems);
-                BS_TRY(ensure(ctx, ctx->d_best, elems * 4));
-                ctx->best_elems = elems;
-                BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
-            }
-            BS_TRY(ensure(ctx, ctx->d_hits_ovf, need * 4));
-            ctx->best_dirty = true;  // cleared when the call ends without an error
+            const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * place_per_sm);
+            const int64_t dense_stride = (max_seg_reads + 31) / 32 * 32;
+            int64_t budget = (int64_t)4 << 30;  // bytes of placement scratch a full grid may take as dense rows
+            if (const char *env = std::getenv("BS_PLACE_SCRATCH_MB")) budget = (int64_t)std::atoll(env) << 20;  // tests: 0 forces the hashed scratch
+            const bool hashed = (int64_t)nblk * dense_stride * 8 > budget;
             bs::PlaceIxArgs pa;
             pa.order = d_order; pa.n_items = (int32_t)C; pa.work_counter = (int32_t *)ctx->d_counters.p;
             pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
             pa.ctg_chars = d_cchars; pa.ctg_seg = d_ctg_seg;
             pa.reads = rs; pa.ix = ix;
-            pa.best = (uint32_t *)ctx->d_best.p; pa.best_stride = stride;
             pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
             pa.pos = o_pos; pa.pos_off = d_pos_off;
-            pa.hit_cap = kHitCap; pa.hits_ovf = (uint32_t *)ctx->d_hits_ovf.p;
-            BS_CUDA(cudaFuncSetAttribute(bs::k_place_index, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads)));
-            BS_LAUNCH(bs::k_place_index, (unsigned)nblk, kPlaceIxThreads, bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads), st, pa);
-            ctx->launches++;
+            pa.hit_cap = kHitCap; pa.keys = nullptr; pa.overflow = nullptr;
+            if (!hashed) {
+                const size_t need = (size_t)nblk * (size_t)dense_stride;
+                if (need > ctx->best_elems || ctx->best_dirty) {
+                    const size_t elems = std::max(need, ctx->best_elems);
+                    BS_TRY(ensure(ctx, ctx->d_best, elems * 4));
+                    ctx->best_elems = elems;
+                    BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
+                }
+                BS_TRY(ensure(ctx, ctx->d_hits_ovf, need * 4));
+                ctx->best_dirty = true;  // cleared when the call ends without an error
+                pa.best = (uint32_t *)ctx->d_best.p; pa.best_stride = dense_stride;
+                pa.hits_ovf = (uint32_t *)ctx->d_hits_ovf.p;
+                BS_CUDA(cudaFuncSetAttribute(bs::k_place_index<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                BS_LAUNCH(bs::k_place_index<false>, (unsigned)nblk, kPlaceIxThreads, smem, st, pa);
+                ctx->launches++;
+            } else {
+                // one huge segment (cfg-5: 10^8 reads): a dense row per resident block does not fit, so every
+                // block keeps (read -> leftmost position) in an open-addressed table sized for the reads ONE
+                // contig places: four slots per position of the longest contig to start with.  A contig that
+                // fills half of its table raises `overflow`; the launch is then repeated with twice the table
+                // (ends at the latest when half the table holds every read of the segment).
+                auto pow2_at_least = [](int64_t v) { int64_t c = 1; while (c < v) c <<= 1; return c; };
+                const int64_t cap_min = 4 * (int64_t)kPlaceIxThreads, cap_max = pow2_at_least(2 * max_seg_reads + 4 * (int64_t)kPlaceIxThreads);
+                int64_t cap = pow2_at_least(4 * max_ctg);
+                if (const char *env = std::getenv("BS_PLACE_HASH_CAP")) cap = pow2_at_least(std::atoll(env));  // tests: a small table reaches the repeat
+                cap = std::min(std::max(cap, cap_min), std::max(cap_min, cap_max));
+                int32_t *d_overflow = (int32_t *)ctx->d_counters.p + 15;  // (the persistent kernels' work counters use 0..7)
+                for (;;) {
+                    const size_t elems = (size_t)nblk * (size_t)cap;
+                    BS_TRY(ensure(ctx, ctx->d_best, std::max(elems, ctx->best_elems) * 4));
+                    ctx->best_elems = std::max(elems, ctx->best_elems);
+                    BS_TRY(ensure(ctx, ctx->d_hits_ovf, elems * 4));
+                    BS_TRY(ensure(ctx, ctx->d_keys, elems * 4));
+                    ctx->best_dirty = true;
+                    BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
+                    BS_CUDA(cudaMemsetAsync(ctx->d_keys.p, 0, elems * 4, st));
+                    BS_CUDA(cudaMemsetAsync(d_overflow, 0, 4, st));
+                    pa.best = (uint32_t *)ctx->d_best.p; pa.best_stride = cap;
+                    pa.hits_ovf = (uint32_t *)ctx->d_hits_ovf.p; pa.keys = (uint32_t *)ctx->d_keys.p; pa.overflow = d_overflow;
+                    BS_CUDA(cudaFuncSetAttribute(bs::k_place_index<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    BS_LAUNCH(bs::k_place_index<true>, (unsigned)nblk, kPlaceIxThreads, smem, st, pa);
+                    ctx->launches++;
+                    int32_t overflow = 0;
+                    BS_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
+                    BS_CUDA(cudaStreamSynchronize(st));
+                    if (!overflow) break;
+                    if (cap >= cap_max) return fail(ctx, BS_ERR_STATE, "placement scratch overflow at full capacity");
+                    cap *= 2;
+                    // the abandoned launch added some contigs' weights already: start over
+                    BS_CUDA(cudaMemsetAsync(ws.w.p, 0, (size_t)w_elems * 4, st));
+                    BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 4, st));
+                }
+            }
         } else if (N > 0 && n_items > 0) {
             bs::PlaceArgs pa;
             pa.items = d_items;
@@ -1102,7 +1144,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_tab2, &ctx->ks2.win, &ctx->ks2.rank_y, &ctx->ks2.lelt, &ctx->ks2.yv, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_hits_ovf, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
+    DevBuf *bufs[] = {&ctx->d_tab, &ctx->d_tab2, &ctx->ks2.win, &ctx->ks2.rank_y, &ctx->ks2.lelt, &ctx->ks2.yv, &ctx->ks.win, &ctx->ks.rank_y, &ctx->ks.lelt, &ctx->ks.yv, &ctx->d_best, &ctx->d_hits_ovf, &ctx->d_keys, &ctx->d_scratch, &ctx->d_ovf, &ctx->d_status,
                       &ctx->d_rank_scratch, &ctx->d_counters, &ctx->d_hbuf, &ctx->sim_meta, &ctx->sim_chars,
                       &ctx->sim_words, &ctx->sim_mask, &ctx->sim_cdf, &ctx->sim_starts, &ctx->sim_kept, &ctx->sim_reads};
     for (DevBuf *b : bufs) release(*b);

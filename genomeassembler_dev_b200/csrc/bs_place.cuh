@@ -199,7 +199,15 @@ struct PlaceIxArgs {
     const int64_t *pos_off;
     int32_t hit_cap;      // shared-memory list of reads placed in the current contig ...
     uint32_t *hits_ovf;   // [gridDim][best_stride] ... and its continuation in global memory (never full: distinct reads)
+    // HASHED variant (segments whose read count makes a dense row per resident block too large, cfg-5):
+    // `best` is a per-block open-addressed table instead, best_stride = its capacity (a power of two).
+    uint32_t *keys;       // [gridDim][best_stride] read id + 1, all 0 on entry and on a successful exit
+    int32_t *overflow;    // set when a contig places more than best_stride/2 distinct reads: the host
+                          // repeats the launch with a larger table
 };
+
+// slot of a read in the hashed scratch (Knuth's multiplicative hash of the read's local id)
+__device__ __forceinline__ uint32_t scratch_slot(uint32_t key, uint32_t mask) { return ((key * 2654435761u) >> 7) & mask; }
 
 // leftmost byte-exact occurrence of read n in contig text, or -1 (reads that cannot be packed)
 __device__ __forceinline__ int64_t find_bytes(const uint8_t *cc, int64_t L, const uint8_t *rc, int len) {
@@ -257,17 +265,28 @@ constexpr int PLACE_CAND_CAP = BS_PLACE_CAND_CAP;  // seed hits of one WARP iter
 
 BS_HD size_t place_index_smem_bytes(int hit_cap, int nthr) { return (size_t)hit_cap * 4 + (size_t)(nthr / 32) * PLACE_CAND_CAP * 8; }
 
+template <bool HASHED>
 __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_index(PlaceIxArgs a) {
     uint32_t *s_hits = (uint32_t *)bs_dyn_smem();
     __shared__ int s_item, s_nhit, s_placed, s_ncand[32];
+    __shared__ int s_full;  // HASHED: the current contig does not fit the table
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     // every warp queues and verifies its own candidates: no block barrier inside the position loop
     uint2 *s_cand = (uint2 *)(s_hits + a.hit_cap) + warp * PLACE_CAND_CAP;  // (read id, contig position) with an equal seed tag
     uint32_t *best = a.best + (int64_t)blockIdx.x * a.best_stride;
     uint32_t *hits_ovf = a.hits_ovf + (int64_t)blockIdx.x * a.best_stride;
+    uint32_t *keys = HASHED ? a.keys + (int64_t)blockIdx.x * a.best_stride : nullptr;
+    const uint32_t smask = (uint32_t)a.best_stride - 1u;
+    const int fill_max = (int)(a.best_stride >> 1);
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0; }
+        if (tid == 0) {
+            s_item = atomicAdd(a.work_counter, 1); s_nhit = 0; s_placed = 0;
+            if (HASHED) {
+                s_full = 0;
+                if (*(volatile int32_t *)a.overflow) s_item = a.n_items;  // another block gave up: the launch is repeated
+            }
+        }
         if (lane == 0) s_ncand[warp] = 0;
         __syncthreads();
         const int item = s_item;
@@ -287,18 +306,36 @@ __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_ind
         const uint64_t keepS = keep_bases(S);
         const uint32_t keepSm = keep_bits(S);
 
-        // a read with an equal seed at position p: verify the rest, keep the leftmost position
+        // the list of reads placed in this contig (dense: local read ids; hashed: table slots)
+        auto remember = [&](uint32_t v) {
+            const int slot = atomicAdd(&s_nhit, 1);
+            if (slot < a.hit_cap) s_hits[slot] = v;
+            else hits_ovf[slot - a.hit_cap] = v;
+        };
+        // read nl (local id) occurs at position p: keep the leftmost position
+        auto record = [&](uint32_t nl, uint32_t p) {
+            if constexpr (!HASHED) {
+                const uint32_t old = atomicMin(&best[nl], p);
+                if (old == POS_INF) remember(nl);  // first time this read is seen in this contig
+            } else {
+                // at most fill_max (+ one per thread in flight) of the 2 * fill_max slots are ever taken, so
+                // the probe ends; all table traffic is atomic (L2), nothing stale out of the L1
+                if (*(volatile int *)&s_nhit >= fill_max) { s_full = 1; return; }
+                const uint32_t key = nl + 1u;
+                for (uint32_t slot = scratch_slot(key, smask);; slot = (slot + 1u) & smask) {
+                    const uint32_t old = atomicCAS(&keys[slot], 0u, key);
+                    if (old == 0u) remember(slot);
+                    if (old == 0u || old == key) { atomicMin(&best[slot], p); break; }
+                }
+            }
+        };
+        // a read with an equal seed at position p: verify the rest
         auto verify_and_record = [&](int64_t n, int64_t p) {
             const int len = read_length(a.reads, n);
             if (p + len > L) return;
             const uint64_t w0 = __ldg(&a.reads.words[n * a.reads.W]);
             if (!verify_at(a, gw, gm, cc, p, n, len, w0)) return;
-            const uint32_t old = atomicMin(&best[n - r0], (uint32_t)p);
-            if (old == POS_INF) {  // first time this read is seen in this contig
-                const int slot = atomicAdd(&s_nhit, 1);
-                if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
-                else hits_ovf[slot - a.hit_cap] = (uint32_t)(n - r0);
-            }
+            record((uint32_t)(n - r0), (uint32_t)p);
         };
 
         if (n_seg_reads > 0) {
@@ -358,20 +395,27 @@ __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_ind
                 if (i % nthr != tid) continue;
                 const int64_t p = find_bytes(cc, L, a.reads.chars + read_begin(a.reads, n), read_length(a.reads, n));
                 if (p < 0) continue;
-                best[n - r0] = (uint32_t)p;  // each such read is visited by exactly one thread
-                const int slot = atomicAdd(&s_nhit, 1);
-                if (slot < a.hit_cap) s_hits[slot] = (uint32_t)(n - r0);
-                else hits_ovf[slot - a.hit_cap] = (uint32_t)(n - r0);
+                if constexpr (!HASHED) {
+                    best[n - r0] = (uint32_t)p;  // each such read is visited by exactly one thread
+                    remember((uint32_t)(n - r0));
+                } else {
+                    record((uint32_t)(n - r0), (uint32_t)p);
+                }
             }
         }
         __threadfence_block();
         __syncthreads();
+        if (HASHED && s_full) {  // (block-uniform) leave the table as it is: the host clears it and repeats the launch
+            if (tid == 0) atomicExch(a.overflow, 1);
+            break;
+        }
         // ---- leftmost positions -> position weights ----
         const int nh = s_nhit;
         int placed = 0;
         for (int h = tid; h < nh; h += nthr) {
-            const uint32_t nl = h < a.hit_cap ? s_hits[h] : hits_ovf[h - a.hit_cap];
+            uint32_t nl = h < a.hit_cap ? s_hits[h] : hits_ovf[h - a.hit_cap];
             const uint32_t p = atomicExch(&best[nl], POS_INF);
+            if (HASHED) nl = atomicExch(&keys[nl], 0u) - 1u;  // slot -> the read that owns it
             atomicAdd(&a.w[coff + c + p], 1);
             if (a.pos) a.pos[a.pos_off[c] + nl] = (int32_t)p;
             placed++;

@@ -254,3 +254,64 @@ def check_spectrum_variants(scorer, lib, kmers, prob):
 
 def test_spectrum_variants(emul_scorer, emul_lib, kmers, prob):
     check_spectrum_variants(emul_scorer, emul_lib, kmers, prob)
+
+
+# ---- hashed placement scratch (one huge segment, cfg-5) ---------------------------------------
+
+def check_hashed_scratch(scorer, oracle, kmers, prob, seg, monkeypatch, block_threads):
+    """the open-addressed (read -> leftmost position) table that replaces the dense per-block row when a
+    segment has too many reads for one row per resident block: same results as the oracle and as the
+    dense row, also when a contig overflows the first table and the launch is repeated with a larger one"""
+    dense, _ = P.check_segment(scorer, oracle, kmers, prob, seg)
+    n0 = scorer.launch_count
+    scorer.score(seg.contigs, seg.read_list, seg.truth, flags=P.FULL)
+    dense_launches = scorer.launch_count - n0
+    monkeypatch.setenv("BS_PLACE_SCRATCH_MB", "0")
+    hashed, _ = P.check_segment(scorer, oracle, kmers, prob, seg)
+    monkeypatch.setenv("BS_PLACE_HASH_CAP", "1")   # smallest table: long contigs overflow it
+    n0 = scorer.launch_count
+    small, _ = P.check_segment(scorer, oracle, kmers, prob, seg)
+    small_launches = scorer.launch_count - n0
+    for k in dense:
+        if isinstance(dense[k], np.ndarray):
+            assert np.array_equal(dense[k], hashed[k], equal_nan=True), k
+            assert np.array_equal(dense[k], small[k], equal_nan=True), k
+    # smallest table: 4 slots per thread of a block, given up when half full (a few more reads can slip in)
+    most = int(np.max(dense["kmer_breaks"]))
+    if most >= 3 * block_threads:
+        assert small_launches > dense_launches   # the placement kernel ran more than once
+    elif most < 2 * block_threads:
+        assert small_launches == dense_launches
+
+
+@pytest.mark.parametrize("params", P.SMALL, ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL])
+def test_hashed_scratch_small_segments(params, emul_scorer, oracle, kmers, prob, monkeypatch):
+    seg = P.make(*params)
+    check_hashed_scratch(emul_scorer, oracle, kmers, prob, seg, monkeypatch, block_threads=64)
+
+
+@pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
+def test_hashed_scratch_edge_inputs(name, contigs, reads, truth, kmer, emul_scorer, oracle, kmers, prob, monkeypatch):
+    from genomeassembler_dev_b200.synth import Segment
+    monkeypatch.setenv("BS_PLACE_SCRATCH_MB", "0")
+    monkeypatch.setenv("BS_PLACE_HASH_CAP", "1")
+    P.check_segment(emul_scorer, oracle, kmers, prob, Segment(truth, None, contigs), kmer=kmer, reads=reads)
+
+
+def test_hashed_scratch_duplicate_reads(emul_scorer, oracle, kmers, prob, monkeypatch):
+    """thousands of copies of a few reads: every copy is its own table entry (reads are not deduplicated), so the
+    table grows until it holds them all"""
+    from genomeassembler_dev_b200 import synth
+    rng = np.random.default_rng(5)
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, 900)).tobytes()
+    reads = [truth[100:130]] * 700 + [truth[400:430]] * 500 + [truth[10:40]] * 3 + [b"ACGTNACGTAACCGGTTACGTACGTAAGGT"] * 4
+    seg = synth.Segment(truth, None, [truth[50:600], truth[380:880], truth[100:130] + truth[100:130], truth[5:60]])
+    monkeypatch.setenv("BS_PLACE_SCRATCH_MB", "0")
+    monkeypatch.setenv("BS_PLACE_HASH_CAP", "1")
+    n0 = emul_scorer.launch_count
+    got, want = P.check_segment(emul_scorer, oracle, kmers, prob, seg, reads=reads)
+    assert list(got["kmer_breaks"]) == [1200, 500, 700, 3]
+    monkeypatch.delenv("BS_PLACE_SCRATCH_MB")
+    n1 = emul_scorer.launch_count
+    P.check_segment(emul_scorer, oracle, kmers, prob, seg, reads=reads)
+    assert n1 - n0 >= (emul_scorer.launch_count - n1) + 3   # 256 -> 512 -> 1024 -> 2048 -> 4096 slots

@@ -342,3 +342,50 @@ def test_uniform_read_lengths(gpu_scorer, oracle, kmers, prob):
 def test_spectrum_variants(gpu_scorer, product_lib, kmers, prob):
     from test_emul_device_algorithm import check_spectrum_variants
     check_spectrum_variants(gpu_scorer, product_lib, kmers, prob)
+
+
+# ---- hashed placement scratch (segments with too many reads for a dense row per block, cfg-5) ----
+
+@pytest.mark.parametrize("params", P.SMALL[:3] + [P.MEDIUM[0], P.MEDIUM[1], P.MEDIUM[3]],
+                         ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL[:3] + [P.MEDIUM[0], P.MEDIUM[1], P.MEDIUM[3]]])
+def test_hashed_scratch_vs_oracle(params, gpu_scorer, oracle, kmers, prob, monkeypatch):
+    from test_emul_device_algorithm import check_hashed_scratch
+    check_hashed_scratch(gpu_scorer, oracle, kmers, prob, P.make(*params), monkeypatch, block_threads=256)
+
+
+@pytest.mark.parametrize("name,contigs,reads,truth,kmer", P.edge_inputs(), ids=[e[0] for e in P.edge_inputs()])
+def test_hashed_scratch_edge_inputs(name, contigs, reads, truth, kmer, gpu_scorer, oracle, kmers, prob, monkeypatch):
+    monkeypatch.setenv("BS_PLACE_SCRATCH_MB", "0")
+    monkeypatch.setenv("BS_PLACE_HASH_CAP", "1")
+    P.check_segment(gpu_scorer, oracle, kmers, prob, synth.Segment(truth, None, contigs), kmer=kmer, reads=reads)
+
+
+def test_hashed_scratch_cfg5_shape(gpu_scorer, kmers, prob, monkeypatch):
+    """cfg-5 shape (one 1 Mb truth, 1e5 reads, 1000 contigs) and a batch of segments: the hashed scratch gives
+    the arrays of the dense scratch, bit for bit"""
+    rng = np.random.default_rng(506)
+    L, N, Cn, r = 1_000_000, 100_000, 1000, 150
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, L))
+    starts = rng.integers(0, L - r, size=N)
+    reads = truth[starts[:, None] + np.arange(r)[None, :]]
+    cstart = np.sort(rng.integers(0, L - 3000, size=Cn))
+    contigs = [truth[a:a + b].tobytes() for a, b in zip(cstart, rng.integers(200, 2000, size=Cn))]
+    contigs.append(truth[5000:65000].tobytes())   # one long scaffold: thousands of reads in one table
+    b = synth.make_batch(6, seed=17, length=20000, read_len=100, coverage=20, contigs_lo=3, contigs_hi=9)
+    bargs = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+             b.seg_read_start, b.seg_contig_start)
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS
+    gpu_scorer.set_table(kmers, prob)
+    dense = gpu_scorer.score(contigs, reads, truth.tobytes(), flags=flags)
+    dense_b = gpu_scorer.score_batch(*bargs, flags=flags)
+    monkeypatch.setenv("BS_PLACE_SCRATCH_MB", "0")
+    for cap in (None, "1"):
+        if cap:
+            monkeypatch.setenv("BS_PLACE_HASH_CAP", cap)
+        hashed = gpu_scorer.score(contigs, reads, truth.tobytes(), flags=flags)
+        hashed_b = gpu_scorer.score_batch(*bargs, flags=flags)
+        for one, two in ((dense, hashed), (dense_b, hashed_b)):
+            for k in one:
+                if isinstance(one[k], np.ndarray):
+                    assert np.array_equal(one[k], two[k], equal_nan=True), (cap, k)
+    assert dense["kmer_breaks"][-1] > 4000

@@ -23,4 +23,11 @@ seg=P.make(43, 2500, 50, 10, 5, 1)
 sc.score(seg.contigs, seg.read_list, seg.truth, flags=B.DEFAULT_FLAGS|B.WANT_SECOND_TABLE|B.WANT_LEV|B.WANT_HIST); n+=1
 reads,srs=sc.simulate_reads([seg.truth, b'ACGT', b''], 40, 8, seed=3); n+=1
 print(B.assemble_contigs([b'ACGTACGTAAGGCCTT', b'GGCCTTACGTTTTTTTTT', b'TTTTTTTTTGGA'], 7, 5, n_shuffles=50, lib_path='/tmp/asan/libbreakscore_emul.so')); n+=1
+# hashed placement scratch, smallest table first (launch repeated with larger tables)
+os.environ['BS_PLACE_SCRATCH_MB']='0'; os.environ['BS_PLACE_HASH_CAP']='1'
+for params in P.SMALL[:4]:
+    P.check_segment(sc,O,kmers,prob,P.make(*params,mut=0.5),flags=P.FULL); n+=1
+for name,contigs,reads,truth,kmer in P.edge_inputs():
+    P.check_segment(sc,O,kmers,prob,synth.Segment(truth,None,contigs),kmer=kmer,reads=reads,flags=P.FULL); n+=1
+del os.environ['BS_PLACE_SCRATCH_MB'], os.environ['BS_PLACE_HASH_CAP']
 print('asan run ok', n, 'cases')
