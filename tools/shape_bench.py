@@ -66,7 +66,11 @@ def main():
     cstart = np.sort(rng.integers(0, L - 3000, size=Cn))
     clen = rng.integers(200, 2000, size=Cn)
     seg = synth.Segment(truth.tobytes(), reads, [truth[a:a + b].tobytes() for a, b in zip(cstart, clen)])
-    run(sc, "cfg5 scaled 1/10: 10 Mb truth, 2e6 reads, 1e4 contigs of ~1 kb", seg, reps=2)
+    # 888 resident blocks x 2e6 reads x 8 B of dense rows exceed the 4 GB scratch budget: hashed scratch by default
+    run(sc, "cfg5 scaled 1/10: 10 Mb truth, 2e6 reads, 1e4 contigs of ~1 kb (hashed placement scratch)", seg, reps=2)
+    os.environ["BS_PLACE_SCRATCH_MB"] = "65536"
+    run(sc, "cfg5 scaled 1/10, dense placement scratch (14 GB of rows)", seg, reps=2)
+    del os.environ["BS_PLACE_SCRATCH_MB"]
 
 
 if __name__ == "__main__":
