@@ -17,7 +17,8 @@ def run(sc, name, seg, reps=3, flags=B.DEFAULT_FLAGS):
     rd = np.ascontiguousarray(seg.reads).reshape(-1)
     tr, tr_off = B.flatten([seg.truth])
     args = (rd, None, seg.reads.shape[1], ct, ct_off, tr, tr_off, [0, seg.reads.shape[0]], [0, len(seg.contigs)])
-    sc.score_batch(*args, flags=flags)
+    for _ in range(3):  # every one of the three rotating workspaces grows to this shape before the clock starts
+        sc.score_batch(*args, flags=flags)
     sc.enable_timing(True)
     t0 = time.perf_counter()
     for _ in range(reps):
