@@ -82,7 +82,7 @@ struct Workspace {
     size_t h_meta_cap = 0;
     DevBuf meta, read_chars, read_off, ctg_chars, tr_chars;
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
-    DevBuf w, total, ycnt, yx, yx2, head, next, odd_head, spbest, exact;
+    DevBuf w, total, ycnt, yx, yx2, head, next, odd_head, spbest, exact, sp_key, sp_head, sp_next;
     DevBuf out_i32, out_f64, pd, pd2, hist, pos;
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
@@ -989,6 +989,16 @@ int ChunkRun::startpos() {
         int64_t splits = ((int64_t)ctx->sm_count * 4 + S - 1) / std::max<int64_t>(S, 1);
         splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 2047) / 2048));
         sa.splits = (int32_t)splits;
+        // seed tables of the contig groups, built in their own kernel
+        const size_t tab_slots = (size_t)bs::startpos_group_count(C, S) * (bs::SP_SLOTS + 1);
+        BS_TRY(ensure(ctx, ws.sp_key, tab_slots * 8));
+        BS_TRY(ensure(ctx, ws.sp_head, tab_slots * 4));
+        BS_TRY(ensure(ctx, ws.sp_next, (size_t)C * 4));
+        BS_CUDA(cudaMemsetAsync(ws.sp_key.p, 0xff, tab_slots * 8, st));
+        BS_CUDA(cudaMemsetAsync(ws.sp_head.p, 0, tab_slots * 4, st));
+        sa.tab_key = (unsigned long long *)ws.sp_key.p; sa.tab_head = (int32_t *)ws.sp_head.p; sa.tab_next = (int32_t *)ws.sp_next.p;
+        BS_LAUNCH(bs::k_startpos_build, grid_for(C, kStartposThreads, grid_cap), kStartposThreads, 0, st, sa);
+        ctx->launches++;
         BS_LAUNCH(bs::k_startpos_index, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
         ctx->launches++;
         BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kStartposThreads, 0, st, sa);
@@ -1150,7 +1160,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
-                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.yx2, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact,
+                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.yx2, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact, &w.sp_key, &w.sp_head, &w.sp_next,
                         &w.out_i32, &w.out_f64, &w.pd, &w.pd2, &w.hist, &w.pos};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);

@@ -8,11 +8,18 @@ namespace bs {
 // contig-in-truth offset (upstream lib/BreakageScorer.cpp:273-274): leftmost exact occurrence
 // of the whole contig in its segment's truth, assigned only if at least one read was placed.
 //
-// k_startpos_index: the truth streams past a small shared-memory table of the segment's contig
-// SEEDS (first 32 bases); a seed hit is verified by the whole warp on packed words; the leftmost
+// k_startpos_build: one thread per contig inserts the contig's SEED (first 32 bases) into the
+// seed table of its group (up to SP_GROUP contigs of one segment) in global memory: the slot is
+// claimed by compare-and-swap with linear probing, contigs with equal seeds are chained.
+// k_startpos_index: the truth streams past the group's table, copied into shared memory; the
+// thread that finds a seed hit verifies the whole contig on packed words itself; the leftmost
 // verified position wins through atomicMin.  O(L_truth + sum L_c) per segment instead of
 // O(C * L_truth).  Contigs without a packable seed (shorter than 32, or a non-ACGT byte in it)
 // are left to k_startpos, which also turns the atomicMin scratch into the final values.
+// The table is built and consumed in different kernels, and the scan uses no warp-level
+// primitive: an earlier version (table built with a compare-and-swap loop in shared memory by
+// the scanning block itself, warp-cooperative verification behind ballots and shuffles) missed
+// about 1 % of the hits of a 1000-contig segment on the GPU, depending on how it was compiled.
 // ------------------------------------------------------------------------------------------
 
 struct StartposArgs {
@@ -36,10 +43,19 @@ struct StartposArgs {
     int32_t *startpos;    // optional: truth.find(contig) if a read was placed, else 0 (upstream semantics)
     int32_t *exact;       // optional: truth.find(contig) for EVERY contig (-1: not a substring); feeds the edit distance
     int32_t search_all;   // search also for contigs without a placed read (needed for `exact`)
+    // seed tables, one per group of contigs (startpos_group): all-ones keys and zero heads on entry
+    unsigned long long *tab_key;  // [groups][SP_SLOTS + 1] seed owning the slot
+    int32_t *tab_head;            // [groups][SP_SLOTS + 1] group-local contig index + 1 of the first contig with that seed
+    int32_t *tab_next;            // [C] next contig of the group with the same seed
 };
 
-constexpr int SP_SLOTS = 2048;  // seed table slots per pass
-constexpr int SP_GROUP = 1024;  // contigs per pass
+constexpr int SP_SLOTS = 2048;  // seed table slots per group; slot SP_SLOTS is reserved for the all-ones seed (= the empty marker)
+constexpr int SP_GROUP = 1024;  // contigs per group
+
+// table of the k-th group of a segment whose contigs start at c0: distinct for every (segment, k)
+// without a prefix sum, and below n_contigs / SP_GROUP + n_seg + 1
+BS_HD int64_t startpos_group(int64_t c0, int64_t seg, int64_t k) { return c0 / SP_GROUP + seg + k; }
+BS_HD int64_t startpos_group_count(int64_t n_contigs, int64_t n_seg) { return n_contigs / SP_GROUP + n_seg + 1; }
 
 // a contig the seed index can look for: 32 valid leading bases, fits in the truth, had a read placed
 __device__ __forceinline__ bool startpos_indexable(const StartposArgs &a, int64_t c, int64_t LT) {
@@ -47,12 +63,34 @@ __device__ __forceinline__ bool startpos_indexable(const StartposArgs &a, int64_
     return L >= 32 && L <= LT && (a.search_all || a.total[c] != 0) && a.ctg_mask[a.ctg_woff[c]] == 0;
 }
 
-__global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
-    __shared__ unsigned long long s_key[SP_SLOTS + 1];  // slot SP_SLOTS is reserved for the all-ones seed (= the empty marker)
-    __shared__ int32_t s_head[SP_SLOTS + 1];  // local contig index + 1 of the first contig with that seed
-    __shared__ int32_t s_next[SP_GROUP];  // next contig with the same seed
+__global__ void k_startpos_build(StartposArgs a) {
     const unsigned long long EMPTY = ~0ull;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < a.n_contigs; c += stride) {
+        const int64_t seg = a.ctg_seg[c];
+        if (!startpos_indexable(a, c, a.tr_off[seg + 1] - a.tr_off[seg])) continue;
+        const int64_t c0 = a.seg_contig_start[seg];
+        const int64_t tab = startpos_group(c0, seg, (c - c0) / SP_GROUP) * (SP_SLOTS + 1);
+        const unsigned long long key = a.ctg_words[a.ctg_woff[c]];
+        uint32_t h = SP_SLOTS;
+        if (key != EMPTY) {
+            h = seed_hash(key) & (SP_SLOTS - 1);
+            for (int probe = 0; probe < SP_SLOTS; probe++) {  // at most SP_GROUP of the SP_SLOTS slots are ever taken
+                const unsigned long long prev = atomicCAS(&a.tab_key[tab + h], EMPTY, key);
+                if (prev == EMPTY || prev == key) break;
+                h = (h + 1) & (SP_SLOTS - 1);
+            }
+        }
+        a.tab_next[c] = atomicExch(&a.tab_head[tab + h], (int32_t)((c - c0) % SP_GROUP) + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
+    __shared__ unsigned long long s_key[SP_SLOTS + 1];
+    __shared__ int32_t s_head[SP_SLOTS + 1];
+    __shared__ int32_t s_next[SP_GROUP];
+    const unsigned long long EMPTY = ~0ull;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int seg = blockIdx.x / a.splits, part = blockIdx.x % a.splits;
     const int64_t LT = a.tr_off[seg + 1] - a.tr_off[seg];
     const uint64_t *tw = a.tr_words + a.tr_woff[seg];
@@ -68,93 +106,64 @@ __global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
     const int64_t c0 = a.seg_contig_start[seg], c1 = a.seg_contig_start[seg + 1];
     for (int64_t g0 = c0; g0 < c1; g0 += SP_GROUP) {
         const int gn = (int)(c1 - g0 < SP_GROUP ? c1 - g0 : SP_GROUP);
+        const int64_t tab = startpos_group(c0, seg, (g0 - c0) / SP_GROUP) * (SP_SLOTS + 1);
         __syncthreads();
-        for (int i = tid; i <= SP_SLOTS; i += nthr) { s_head[i] = 0; s_key[i] = EMPTY; }
-        __syncthreads();
-        // parallel build: claim the seed's slot by compare-and-swap (linear probing), then push the
-        // contig on the slot's chain
-        for (int i = tid; i < gn; i += nthr) {
-            const int64_t c = g0 + i;
-            if (!startpos_indexable(a, c, LT)) continue;
-            const unsigned long long key = a.ctg_words[a.ctg_woff[c]];
-            uint32_t h = SP_SLOTS;
-            if (key != EMPTY) {
-                h = seed_hash(key) & (SP_SLOTS - 1);
-                for (;;) {
-                    const unsigned long long prev = atomicCAS(&s_key[h], EMPTY, key);
-                    if (prev == EMPTY || prev == key) break;
+        int any = 0;
+        for (int i = tid; i <= SP_SLOTS; i += nthr) {
+            const int32_t hd = a.tab_head[tab + i];
+            s_head[i] = hd;
+            s_key[i] = a.tab_key[tab + i];
+            any |= hd;
+        }
+        for (int i = tid; i < gn; i += nthr) s_next[i] = a.tab_next[g0 + i];  // (only the entries of chained contigs are ever read)
+        if (!__syncthreads_or(any)) continue;  // no contig of this group is in the index
+        for (int64_t qb = q_begin; qb < q_end; qb += nthr) {
+            const int64_t q = qb + tid;
+            if (q >= q_end) continue;
+            const int64_t idx = q >> 5;
+            const uint32_t o = (uint32_t)(q & 31);
+            if (window32(__ldg(&tm[idx]), __ldg(&tm[idx + 1]), o) != 0) continue;  // a byte outside ACGT in the window
+            const unsigned long long seed = window64(__ldg(&tw[idx]), __ldg(&tw[idx + 1]), o);
+            int cand = 0;
+            if (seed == EMPTY) cand = s_head[SP_SLOTS];
+            else {
+                uint32_t h = seed_hash(seed) & (SP_SLOTS - 1);
+                for (int probe = 0; probe < SP_SLOTS; probe++) {
+                    const unsigned long long k = s_key[h];
+                    if (k == EMPTY) break;
+                    if (k == seed) { cand = s_head[h]; break; }
                     h = (h + 1) & (SP_SLOTS - 1);
                 }
             }
-            s_next[i] = atomicExch(&s_head[h], i + 1);
-        }
-        __syncthreads();
-        for (int64_t qb = q_begin; qb < q_end; qb += nthr) {
-            const int64_t q = qb + tid;
-            int cand = 0;
-            if (q < q_end) {
-                const int64_t idx = q >> 5;
-                const uint32_t o = (uint32_t)(q & 31);
-                if (window32(__ldg(&tm[idx]), __ldg(&tm[idx + 1]), o) == 0) {
-                    const unsigned long long seed = window64(__ldg(&tw[idx]), __ldg(&tw[idx + 1]), o);
-                    if (seed == EMPTY) cand = s_head[SP_SLOTS];
-                    else {
-                        uint32_t h = seed_hash(seed) & (SP_SLOTS - 1);
-                        for (;;) {
-                            const unsigned long long k = s_key[h];
-                            if (k == EMPTY) break;
-                            if (k == seed) { cand = s_head[h]; break; }
-                            h = (h + 1) & (SP_SLOTS - 1);
-                        }
-                    }
+            // seed hits (rare): this thread verifies the whole contig
+            for (int ci = cand; ci != 0; ci = s_next[ci - 1]) {
+                const int64_t c = g0 + ci - 1;
+                const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+                if (q + L > LT) continue;
+                if ((uint32_t)q >= *(volatile uint32_t *)&a.best[c]) continue;  // a position further left is already known
+                const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
+                const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
+                const int64_t nw = (L + 31) >> 5;
+                bool ok = true, any_invalid = false;
+                uint64_t t_lo = tw[idx];
+                uint32_t m_lo = tm[idx];
+                for (int64_t j = 0; ok && j < nw; j++) {
+                    const int rem = (L - 32 * j) < 32 ? (int)(L - 32 * j) : 32;
+                    const uint64_t t_hi = tw[idx + j + 1];
+                    const uint32_t m_hi = tm[idx + j + 1];
+                    const uint32_t mj = cm[j];
+                    // byte equality == equal 2-bit codes AND equal validity AND equal raw bytes where invalid
+                    ok = ((window64(t_lo, t_hi, o) ^ cw[j]) & keep_bases(rem)) == 0 &&
+                         ((window32(m_lo, m_hi, o) ^ mj) & keep_bits(rem)) == 0;
+                    any_invalid |= (mj & keep_bits(rem)) != 0;
+                    t_lo = t_hi;
+                    m_lo = m_hi;
                 }
-            }
-            // seed hits of the warp, one after the other, each verified by all 32 lanes
-            unsigned hits = __ballot_sync(FULL_MASK, cand != 0);
-            while (hits) {
-                const int src = __ffs((int)hits) - 1;
-                hits &= hits - 1;
-                const int64_t qc = __shfl_sync(FULL_MASK, q, src);
-                int ci = __shfl_sync(FULL_MASK, cand, src);
-                for (; ci != 0; ci = s_next[ci - 1]) {
-                    const int64_t c = g0 + ci - 1;
-                    const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
-                    if (qc + L > LT) continue;
-                    // a position further left may already be known; one lane reads so that the whole
-                    // warp takes the same branch (the value can change under us)
-                    uint32_t known = 0;
-                    if (lane == 0) known = *(volatile uint32_t *)&a.best[c];
-                    known = __shfl_sync(FULL_MASK, known, 0);
-                    if ((uint32_t)qc >= known) continue;
-                    const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
-                    const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
-                    const int64_t idx = qc >> 5;
-                    const uint32_t o = (uint32_t)(qc & 31);
-                    const int64_t nw = (L + 31) >> 5;
-                    bool ok = true, any_invalid = false;
-                    for (int64_t j0 = 0; ok && j0 < nw; j0 += 32) {
-                        const int64_t j = j0 + lane;
-                        bool okl = true;
-                        if (j < nw) {
-                            const int rem = (L - 32 * j) < 32 ? (int)(L - 32 * j) : 32;
-                            const uint32_t mj = cm[j];
-                            // byte equality == equal 2-bit codes AND equal validity AND equal raw bytes where invalid
-                            okl = ((window64(tw[idx + j], tw[idx + j + 1], o) ^ cw[j]) & keep_bases(rem)) == 0 &&
-                                  ((window32(tm[idx + j], tm[idx + j + 1], o) ^ mj) & keep_bits(rem)) == 0;
-                            any_invalid |= (mj & keep_bits(rem)) != 0;
-                        }
-                        ok = __ballot_sync(FULL_MASK, !okl) == 0;
-                    }
-                    if (ok && __ballot_sync(FULL_MASK, any_invalid) != 0) {
-                        const uint8_t *cc = a.ctg_chars + a.ctg_off[c];
-                        for (int64_t i0 = 0; ok && i0 < L; i0 += 32) {
-                            const int64_t i = i0 + lane;
-                            const bool okl = i < L ? tc[qc + i] == cc[i] : true;
-                            ok = __ballot_sync(FULL_MASK, !okl) == 0;
-                        }
-                    }
-                    if (ok && lane == 0) atomicMin(&a.best[c], (uint32_t)qc);
+                if (ok && any_invalid) {
+                    const uint8_t *cc = a.ctg_chars + a.ctg_off[c];
+                    for (int64_t i = 0; ok && i < L; i++) ok = tc[q + i] == cc[i];
                 }
+                if (ok) atomicMin(&a.best[c], (uint32_t)q);
             }
         }
     }

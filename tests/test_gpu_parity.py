@@ -223,6 +223,30 @@ def test_cfg5_shape_scaled(gpu_scorer, oracle, kmers, prob):
     assert np.all(chk["kmer_breaks"] >= expect)
 
 
+def test_startpos_of_a_thousand_contigs_in_one_segment(gpu_scorer, kmers, prob):
+    """cfg-5 shape: every contig of a 1001-contig segment is an exact substring of the 1 Mb truth at a known
+    offset (the seed tables of the contig-in-truth search hold 1001 seeds; 489 blocks scan the truth).  Repeated:
+    an earlier kernel lost about 1 % of these offsets at random."""
+    rng = np.random.default_rng(506)
+    L, N, Cn, r = 1_000_000, 100_000, 1000, 150
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, L))
+    starts = rng.integers(0, L - r, size=N)
+    reads = truth[starts[:, None] + np.arange(r)[None, :]]
+    cstart = np.sort(rng.integers(0, L - 3000, size=Cn))
+    contigs = [truth[a:a + b].tobytes() for a, b in zip(cstart, rng.integers(200, 2000, size=Cn))]
+    contigs.append(truth[5000:65000].tobytes())
+    contigs.append(truth[5000:6000].tobytes() + b"A" + truth[6001:7000].tobytes())   # same seed as the one before, not a substring
+    contigs.append(truth[700000:700100].tobytes())                                   # inside other contigs or not: found at its own offset
+    want = np.concatenate([cstart, [5000, -1, 700000]]).astype(np.int32)
+    if truth[6000] == ord("A"):
+        want[-2] = 5000
+    gpu_scorer.set_table(kmers, prob)
+    for it in range(6):
+        res = gpu_scorer.score(contigs, reads, truth.tobytes(), flags=B.WANT_STARTPOS if it % 2 else B.DEFAULT_FLAGS)
+        assert np.array_equal(res["path_prob_dist_startpos"], want * (res["kmer_breaks"] > 0)), it
+        assert np.count_nonzero(res["kmer_breaks"]) >= 1000
+
+
 # ---- infix edit distance (lev_dist_vs_true) ---------------------------------------------------
 
 @pytest.mark.parametrize("params", P.SMALL + P.MEDIUM[:2], ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL + P.MEDIUM[:2]])

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from genomeassembler_dev_b200 import breakscore as B, synth, tables  # noqa: E402
 
 kmers, prob = tables.all_kmer_strings(), tables.normalised(tables.load_raw())
-sc = B.BreakageScorer(0, sys.argv[4] if len(sys.argv) > 4 else None)
+sc = B.BreakageScorer(0, sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None)
 sc.set_table(kmers, prob)
 rng = np.random.default_rng(506)
 L, N, Cn, r = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), 150
@@ -22,13 +22,10 @@ clen = np.append(rng.integers(200, 2000, size=Cn), 60000)
 contigs = [truth[a:a + b].tobytes() for a, b in zip(cstart, clen[:-1])]
 contigs.append(truth[5000:65000].tobytes())
 exp = np.append(cstart, 5000).astype(np.int32)
-for it in range(8):
-    if it == 4:
-        os.environ["BS_PLACE_SCRATCH_MB"] = "0"
-    for flags, nm in ((B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS, "default+hist+pos"), (B.DEFAULT_FLAGS, "default"), (B.WANT_STARTPOS, "startpos only")):
-        res = sc.score(contigs, reads, truth.tobytes(), flags=flags)
-        want = exp * (res["kmer_breaks"] > 0)
-        got = res["path_prob_dist_startpos"]
-        bad = np.nonzero(got != want)[0]
-        print(it, nm, "n_bad", len(bad), "idx", bad[:8].tolist(), "got", got[bad[:8]].tolist(), "want", want[bad[:8]].tolist(),
-              "len", clen[bad[:8]].tolist(), "breaks", res["kmer_breaks"][bad[:8]].tolist(), flush=True)
+for it in range(int(sys.argv[5]) if len(sys.argv) > 5 else 6):
+    res = sc.score(contigs, reads, truth.tobytes(), flags=B.WANT_STARTPOS if it % 2 else B.DEFAULT_FLAGS)
+    want = exp * (res["kmer_breaks"] > 0)
+    got = res["path_prob_dist_startpos"]
+    bad = np.nonzero(got != want)[0]
+    print("call", it, "n_bad", len(bad), "placed_contigs", int((res["kmer_breaks"] > 0).sum()),
+          "idx", bad[:6].tolist(), "got", got[bad[:6]].tolist(), flush=True)
