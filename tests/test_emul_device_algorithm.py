@@ -315,3 +315,42 @@ def test_hashed_scratch_duplicate_reads(emul_scorer, oracle, kmers, prob, monkey
     n1 = emul_scorer.launch_count
     P.check_segment(emul_scorer, oracle, kmers, prob, seg, reads=reads)
     assert n1 - n0 >= (emul_scorer.launch_count - n1) + 3   # 256 -> 512 -> 1024 -> 2048 -> 4096 slots
+
+
+# ---- contig-in-truth offsets with several seed-table groups per segment -------------------------
+
+def check_startpos_many_contigs(scorer, oracle, kmers, prob, n_contigs=2500, L=30000):
+    """more contigs in a segment than one seed table holds (groups of 1024), duplicates, contigs sharing their
+    first 32 bases, mutated copies, contigs shorter than a seed; a second small segment in the same batch"""
+    from genomeassembler_dev_b200 import synth
+    rng = np.random.default_rng(2500)
+    truths, contigs, reads, srs, scs = [], [], [], [0], [0]
+    for s, (Ls, nc) in enumerate([(L, n_contigs), (3000, 7)]):
+        t = synth.codes_to_ascii(synth.random_truth_codes(rng, Ls)).tobytes()
+        cs = []
+        for i in range(nc):
+            a = int(rng.integers(0, Ls - 200))
+            ln = int(rng.integers(20 if i % 50 == 0 else 33, 160))
+            c = bytearray(t[a:a + ln])
+            if i % 9 == 0 and ln > 40:
+                c[int(rng.integers(32, ln))] ^= 6          # substitution after the seed: same seed, not a substring
+            cs.append(bytes(c))
+        cs += [cs[0], cs[1][:40], t[100:164], t[100:150]]   # duplicates and shared seeds
+        rl = [t[a:a + 30] for a in range(0, Ls - 30, 7)]
+        truths.append(t); contigs += cs; reads += rl
+        srs.append(len(reads)); scs.append(len(contigs))
+    rd, _ = B.flatten(reads)
+    ct, ct_off = B.flatten(contigs)
+    tr, tr_off = B.flatten(truths)
+    scorer.set_table(kmers, prob)
+    res = scorer.score_batch(rd, None, 30, ct, ct_off, tr, tr_off, srs, scs, flags=B.WANT_STARTPOS)
+    for s in range(len(truths)):
+        c0, c1 = scs[s], scs[s + 1]
+        want = np.array([truths[s].find(c) for c in contigs[c0:c1]], dtype=np.int32) * (res["kmer_breaks"][c0:c1] > 0)
+        assert np.array_equal(res["path_prob_dist_startpos"][c0:c1], want), s
+    assert np.count_nonzero(res["path_prob_dist_startpos"] == -1) > 100
+    return res
+
+
+def test_startpos_many_contigs(emul_scorer, oracle, kmers, prob):
+    check_startpos_many_contigs(emul_scorer, oracle, kmers, prob)

@@ -247,6 +247,12 @@ def test_startpos_of_a_thousand_contigs_in_one_segment(gpu_scorer, kmers, prob):
         assert np.count_nonzero(res["kmer_breaks"]) >= 1000
 
 
+def test_startpos_many_contigs(gpu_scorer, oracle, kmers, prob):
+    from test_emul_device_algorithm import check_startpos_many_contigs
+    for _ in range(3):
+        check_startpos_many_contigs(gpu_scorer, oracle, kmers, prob, n_contigs=6000, L=200000)
+
+
 # ---- infix edit distance (lev_dist_vs_true) ---------------------------------------------------
 
 @pytest.mark.parametrize("params", P.SMALL + P.MEDIUM[:2], ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL + P.MEDIUM[:2]])
