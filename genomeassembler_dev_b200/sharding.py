@@ -99,3 +99,47 @@ def gather_records(rec: np.ndarray, counts, group=None, dst: int = 0):
     if rank != dst:
         return None
     return np.concatenate([out[r][:int(counts[r])].cpu().numpy() for r in range(world)], axis=0)
+
+
+def score_contigs_sharded(scorer, path, sequencing_reads, true_solution, kmer=8, flags=None, group=None, dst: int = 0):
+    """One segment with many candidate contigs / scaffolds (cfg-4, cfg-5) over the ranks of a process group:
+    contigs are dealt out longest-first (:func:`shard_contigs_lpt`), every rank places the WHOLE read set
+    (replicated input, as BASELINE.json's north_star has it) against its own contigs with `scorer`
+    (a :class:`breakscore.BreakageScorer` whose table is set), the fixed-width score records are gathered
+    and rank `dst` gets them back in INPUT order -- the order of the upstream list
+    (``lib/BreakageScorer.cpp:306-353``; its sort is disabled at ``:311-315``).  Per-contig results do not depend on
+    which rank scored them (fixed reduction order), so the gathered table is bit-identical to an unsharded call.
+
+    Returns on rank `dst` a dict of the record columns (RECORD_F64 + RECORD_I32) plus ``owner`` (rank per contig);
+    ``None`` elsewhere.  Every rank also gets ``local`` -- its own full result dict (``path_prob_dist`` etc. stay on
+    the rank that computed them: the variable-length vectors are not sent through the collective) -- and
+    ``local_index`` via the second return value."""
+    import torch.distributed as dist
+
+    from . import breakscore
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lens = np.fromiter((len(p) for p in path), dtype=np.int64, count=len(path))
+    parts = shard_contigs_lpt(lens, world)
+    mine = parts[rank]
+    counts = [len(p) for p in parts]
+    if flags is None:
+        flags = breakscore.DEFAULT_FLAGS
+    if len(mine):
+        local = scorer.score([path[i] for i in mine], sequencing_reads, true_solution, kmer=kmer, flags=flags)
+    else:  # more ranks than contigs: nothing to score here, but the collective still needs this rank
+        local = {k: np.zeros(0) for k in RECORD_F64 + RECORD_I32}
+    rec = pack_records(local, len(mine))
+    got = gather_records(rec, counts, group=group, dst=dst)
+    local_info = {"local": local, "local_index": mine}
+    if rank != dst:
+        return None, local_info
+    order = np.concatenate(parts) if len(path) else np.zeros(0, np.int64)
+    back = np.empty((len(path), rec.shape[1]), dtype=np.float64)
+    back[order] = got
+    out = unpack_records(back)
+    owner = np.empty(len(path), dtype=np.int32)
+    for r, p in enumerate(parts):
+        owner[p] = r
+    out["owner"] = owner
+    return out, local_info

@@ -81,3 +81,46 @@ def test_lpt_contig_sharding():
     assert max(loads) - min(loads) <= lens.max()
     for p in parts:
         assert np.all(np.diff(p) > 0)
+
+
+def _contig_worker(rank, world, port, q, emul_lib):
+    """cfg-4 shape: one segment, many candidate contigs, reads replicated, contigs LPT-sharded.  Each rank scores
+    with the kernel sources under the CPU emulation (the product library needs a GPU)."""
+    from genomeassembler_dev_b200 import breakscore
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kmers, prob = tables.all_kmer_strings(), tables.normalised(tables.load_raw())
+    b = synth.make_batch(1, seed=11, length=3000, read_len=40, coverage=8, contigs_lo=9, contigs_hi=9)
+    ctgs = [b.contig_chars[b.contig_off[c]:b.contig_off[c + 1]].tobytes() for c in range(b.n_contigs)]
+    reads = b.read_chars.reshape(-1, b.read_len)
+    truth = b.truth_chars.tobytes()
+    sc = breakscore.BreakageScorer(0, emul_lib)
+    sc.set_table(kmers, prob)
+    flags = breakscore.DEFAULT_FLAGS
+    got, info = sharding.score_contigs_sharded(sc, ctgs, reads, truth, kmer=8, flags=flags)
+    ok = len(info["local_index"]) == len(info["local"]["kmer_breaks"])
+    if rank == 0:
+        whole = sc.score(ctgs, reads, truth, kmer=8, flags=flags)
+        for k in sharding.RECORD_F64 + sharding.RECORD_I32:
+            ok = ok and bool(np.array_equal(np.asarray(got[k], dtype=np.float64), np.asarray(whole[k], dtype=np.float64), equal_nan=True))
+        ok = ok and sorted(set(got["owner"].tolist())) == list(range(min(world, len(ctgs))))
+        q.put(ok)
+    else:
+        ok = ok and got is None
+        assert ok
+    sc.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_contig_sharding_reads_replicated(world, emul_lib):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_contig_worker, args=(r, world, port, q, emul_lib)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
