@@ -985,8 +985,8 @@ int ChunkRun::startpos() {
         sa.tr_chars = d_tchars; sa.total = (const int32_t *)ws.total.p; sa.n_contigs = C; sa.n_seg = (int32_t)S;
         sa.best = (uint32_t *)ws.spbest.p; sa.startpos = o_startpos;
         sa.exact = e.want_lev ? (int32_t *)ws.exact.p : nullptr; sa.search_all = e.want_lev ? 1 : 0;
-        // enough blocks to fill the machine even for a single segment; at least 2048 positions each
-        int64_t splits = ((int64_t)ctx->sm_count * 4 + S - 1) / std::max<int64_t>(S, 1);
+        // enough blocks to fill the machine even for a single segment and to keep the last wave short; at least 2048 positions each
+        int64_t splits = ((int64_t)ctx->sm_count * 16 + S - 1) / std::max<int64_t>(S, 1);
         splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 2047) / 2048));
         sa.splits = (int32_t)splits;
         // seed tables of the contig groups, built in their own kernel

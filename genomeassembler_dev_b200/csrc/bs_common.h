@@ -9,6 +9,11 @@
 #else
 #define BS_HD inline
 #endif
+#if defined(__CUDACC__) && !defined(BS_CPU_EMUL)
+#define BS_NOINLINE __noinline__
+#else
+#define BS_NOINLINE
+#endif
 
 namespace bs {
 

@@ -51,6 +51,8 @@ struct StartposArgs {
 
 constexpr int SP_SLOTS = 2048;  // seed table slots per group; slot SP_SLOTS is reserved for the all-ones seed (= the empty marker)
 constexpr int SP_GROUP = 1024;  // contigs per group
+constexpr int SP_RUN = 8;           // consecutive truth positions per thread and scan step of k_startpos_index (divides 32)
+constexpr int SP_VERIFY_BATCH = 4;  // contig words compared per verification step of k_startpos_index
 
 // table of the k-th group of a segment whose contigs start at c0: distinct for every (segment, k)
 // without a prefix sum, and below n_contigs / SP_GROUP + n_seg + 1
@@ -85,11 +87,83 @@ __global__ void k_startpos_build(StartposArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
+// group-local index + 1 of the first contig whose seed is `seed` (0: none) in a group's table in shared memory
+__device__ __forceinline__ int startpos_probe(const unsigned long long *s_key, const int32_t *s_head, unsigned long long seed) {
+    const unsigned long long EMPTY = ~0ull;
+    if (seed == EMPTY) return s_head[SP_SLOTS];
+    uint32_t h = seed_hash(seed) & (SP_SLOTS - 1);
+#pragma unroll 1
+    for (int probe = 0; probe < SP_SLOTS; probe++) {
+        const unsigned long long k = s_key[h];
+        if (k == EMPTY) break;
+        if (k == seed) return s_head[h];
+        h = (h + 1) & (SP_SLOTS - 1);
+    }
+    return 0;
+}
+
+// Seed hit at truth position q for the chain of contigs starting at group-local index ci_head - 1: the calling
+// thread compares every contig of the chain with the truth on packed words (thread-local, no warp primitive)
+// and keeps the leftmost verified position.
+__device__ __forceinline__ void startpos_verify(const StartposArgs &a, int ci_head, const int32_t *s_next, int64_t g0, int64_t q, int64_t LT,
+                                            const uint64_t *tw, const uint32_t *tm, const uint8_t *tc) {
+    const int64_t idx = q >> 5;
+    const uint32_t o = (uint32_t)(q & 31);
+    for (int ci = ci_head; ci != 0; ci = s_next[ci - 1]) {
+        const int64_t c = g0 + ci - 1;
+        const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+        if (q + L > LT) continue;
+        if ((uint32_t)q >= *(volatile uint32_t *)&a.best[c]) continue;  // a position further left is already known
+        const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
+        const int64_t nw = (L + 31) >> 5;
+        bool ok = true, any_invalid = false;
+        uint64_t t_lo = tw[idx];
+        uint32_t m_lo = tm[idx];
+        // SP_VERIFY_BATCH words per step without an early exit in between: the loads of a step are
+        // independent and in flight together (one thread walks a 50 kb contig in ~400 round trips
+        // to L2 instead of ~1600; a batch of 4 keeps the kernel at 64 registers, four blocks per SM)
+        for (int64_t j0 = 0; ok && j0 < nw; j0 += SP_VERIFY_BATCH) {
+            uint64_t t_hi[SP_VERIFY_BATCH], cwj[SP_VERIFY_BATCH];
+            uint32_t m_hi[SP_VERIFY_BATCH], cmj[SP_VERIFY_BATCH];
+#pragma unroll
+            for (int u = 0; u < SP_VERIFY_BATCH; u++) {
+                const bool in = j0 + u < nw;  // (the two pad words of a sequence keep idx + j + 1 inside for j < nw)
+                t_hi[u] = in ? tw[idx + j0 + u + 1] : 0;
+                m_hi[u] = in ? tm[idx + j0 + u + 1] : 0;
+                cwj[u] = in ? cw[j0 + u] : 0;
+                cmj[u] = in ? cm[j0 + u] : 0;
+            }
+            uint64_t diff = 0;
+            uint32_t mdiff = 0, minv = 0;
+#pragma unroll
+            for (int u = 0; u < SP_VERIFY_BATCH; u++) {
+                if (j0 + u < nw) {
+                    const int64_t left = L - 32 * (j0 + u);
+                    const int rem = left < 32 ? (int)left : 32;
+                    // byte equality == equal 2-bit codes AND equal validity AND equal raw bytes where invalid
+                    diff |= (window64(t_lo, t_hi[u], o) ^ cwj[u]) & keep_bases(rem);
+                    mdiff |= (window32(m_lo, m_hi[u], o) ^ cmj[u]) & keep_bits(rem);
+                    minv |= cmj[u] & keep_bits(rem);
+                    t_lo = t_hi[u];
+                    m_lo = m_hi[u];
+                }
+            }
+            ok = diff == 0 && mdiff == 0;
+            any_invalid |= minv != 0;
+        }
+        if (ok && any_invalid) {
+            const uint8_t *cc = a.ctg_chars + a.ctg_off[c];
+            for (int64_t i = 0; ok && i < L; i++) ok = tc[q + i] == cc[i];
+        }
+        if (ok) atomicMin(&a.best[c], (uint32_t)q);
+    }
+}
+
+__global__ void __launch_bounds__(256, 4) k_startpos_index(StartposArgs a) {
     __shared__ unsigned long long s_key[SP_SLOTS + 1];
     __shared__ int32_t s_head[SP_SLOTS + 1];
     __shared__ int32_t s_next[SP_GROUP];
-    const unsigned long long EMPTY = ~0ull;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int seg = blockIdx.x / a.splits, part = blockIdx.x % a.splits;
     const int64_t LT = a.tr_off[seg + 1] - a.tr_off[seg];
@@ -117,53 +191,33 @@ __global__ void __launch_bounds__(256) k_startpos_index(StartposArgs a) {
         }
         for (int i = tid; i < gn; i += nthr) s_next[i] = a.tab_next[g0 + i];  // (only the entries of chained contigs are ever read)
         if (!__syncthreads_or(any)) continue;  // no contig of this group is in the index
-        for (int64_t qb = q_begin; qb < q_end; qb += nthr) {
-            const int64_t q = qb + tid;
-            if (q >= q_end) continue;
-            const int64_t idx = q >> 5;
-            const uint32_t o = (uint32_t)(q & 31);
-            if (window32(__ldg(&tm[idx]), __ldg(&tm[idx + 1]), o) != 0) continue;  // a byte outside ACGT in the window
-            const unsigned long long seed = window64(__ldg(&tw[idx]), __ldg(&tw[idx + 1]), o);
-            int cand = 0;
-            if (seed == EMPTY) cand = s_head[SP_SLOTS];
-            else {
-                uint32_t h = seed_hash(seed) & (SP_SLOTS - 1);
-                for (int probe = 0; probe < SP_SLOTS; probe++) {
-                    const unsigned long long k = s_key[h];
-                    if (k == EMPTY) break;
-                    if (k == seed) { cand = s_head[h]; break; }
-                    h = (h + 1) & (SP_SLOTS - 1);
-                }
+        // SP_RUN consecutive positions per thread: they share one pair of truth words and one pair of mask words
+        // (SP_RUN divides 32 and slices start at multiples of 32), so a position costs two funnel shifts, a hash
+        // and a shared-memory probe -- no global load of its own
+        for (int64_t qb = q_begin; qb < q_end; qb += (int64_t)nthr * SP_RUN) {
+            const int64_t q0 = qb + (int64_t)tid * SP_RUN;
+            if (q0 >= q_end) continue;
+            const int64_t idx = q0 >> 5;
+            const uint32_t o0 = (uint32_t)(q0 & 31);
+            const uint32_t m_a = __ldg(&tm[idx]), m_b = __ldg(&tm[idx + 1]);
+            const uint64_t w_a = __ldg(&tw[idx]), w_b = __ldg(&tw[idx + 1]);
+            uint32_t hits = 0;  // positions of the run whose seed is in the table
+#pragma unroll
+            for (int u = 0; u < SP_RUN; u++) {
+                const uint32_t o = o0 + (uint32_t)u;
+                const unsigned long long seed = window64(w_a, w_b, o);
+                bool hit = startpos_probe(s_key, s_head, seed) != 0;
+                hit = hit && window32(m_a, m_b, o) == 0;  // (no byte outside ACGT in the window)
+                hits |= (uint32_t)hit << u;
             }
-            // seed hits (rare): this thread verifies the whole contig
-            for (int ci = cand; ci != 0; ci = s_next[ci - 1]) {
-                const int64_t c = g0 + ci - 1;
-                const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
-                if (q + L > LT) continue;
-                if ((uint32_t)q >= *(volatile uint32_t *)&a.best[c]) continue;  // a position further left is already known
-                const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
-                const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
-                const int64_t nw = (L + 31) >> 5;
-                bool ok = true, any_invalid = false;
-                uint64_t t_lo = tw[idx];
-                uint32_t m_lo = tm[idx];
-                for (int64_t j = 0; ok && j < nw; j++) {
-                    const int rem = (L - 32 * j) < 32 ? (int)(L - 32 * j) : 32;
-                    const uint64_t t_hi = tw[idx + j + 1];
-                    const uint32_t m_hi = tm[idx + j + 1];
-                    const uint32_t mj = cm[j];
-                    // byte equality == equal 2-bit codes AND equal validity AND equal raw bytes where invalid
-                    ok = ((window64(t_lo, t_hi, o) ^ cw[j]) & keep_bases(rem)) == 0 &&
-                         ((window32(m_lo, m_hi, o) ^ mj) & keep_bits(rem)) == 0;
-                    any_invalid |= (mj & keep_bits(rem)) != 0;
-                    t_lo = t_hi;
-                    m_lo = m_hi;
-                }
-                if (ok && any_invalid) {
-                    const uint8_t *cc = a.ctg_chars + a.ctg_off[c];
-                    for (int64_t i = 0; ok && i < L; i++) ok = tc[q + i] == cc[i];
-                }
-                if (ok) atomicMin(&a.best[c], (uint32_t)q);
+            // seed hits (rare): this thread verifies the whole contig; one copy of that code, outside the unrolled run
+            while (hits) {
+                const int u = __ffs((int)hits) - 1;
+                hits &= hits - 1;
+                const int64_t q = q0 + u;
+                if (q >= q_end) break;
+                const int cand = startpos_probe(s_key, s_head, window64(w_a, w_b, o0 + (uint32_t)u));
+                startpos_verify(a, cand, s_next, g0, q, LT, tw, tm, tc);
             }
         }
     }
