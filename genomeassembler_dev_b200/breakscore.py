@@ -39,10 +39,13 @@ STAGES = ("h2d", "pack", "place", "score", "truth_spectrum", "prob_dist_ks", "ks
 ABI_SYMBOLS = (
     "bs_abi_version", "bs_ctx_create", "bs_ctx_destroy", "bs_last_error", "bs_ctx_set_stream",
     "bs_ctx_synchronize", "bs_ctx_launch_count", "bs_ctx_enable_timing", "bs_ctx_last_timings",
-    "bs_ctx_last_place_ms", "bs_set_table", "bs_set_truth_table", "bs_set_second_table", "bs_score_batch", "bs_score",
+    "bs_ctx_last_place_ms", "bs_ctx_set_poll", "bs_set_table", "bs_set_truth_table", "bs_set_second_table", "bs_score_batch", "bs_score",
     "bs_host_alloc", "bs_host_free", "bs_assemble_contigs", "bs_assemble_last_error", "bs_string_list_size",
     "bs_string_list_bytes", "bs_string_list_copy", "bs_string_list_free", "bs_simulate_capacity", "bs_simulate_reads",
 )
+
+POLL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+ERR_INTERRUPTED = 7
 
 _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
@@ -108,6 +111,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_ctx_last_timings.argtypes = [C.c_void_p, _f64p, C.c_int]
     lib.bs_ctx_last_place_ms.restype = C.c_double
     lib.bs_ctx_last_place_ms.argtypes = [C.c_void_p]
+    lib.bs_ctx_set_poll.restype = C.c_int
+    lib.bs_ctx_set_poll.argtypes = [C.c_void_p, POLL_FN, C.c_void_p]
     lib.bs_set_table.restype = C.c_int
     lib.bs_set_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.bs_set_truth_table.restype = C.c_int
@@ -140,8 +145,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_simulate_reads.restype = C.c_int
     lib.bs_simulate_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int,
                                       C.c_uint64, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p]
-    if lib.bs_abi_version() != 2:
-        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 2")
+    if lib.bs_abi_version() != 3:
+        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 3")
     return lib
 
 
@@ -214,6 +219,13 @@ class BreakageScorer:
     @property
     def launch_count(self) -> int:
         return int(self._lib.bs_ctx_launch_count(self._ctx))
+
+    def set_poll(self, poll=None):
+        """Interrupt poll for long calls: ``poll()`` is called on the calling thread between the pipeline chunks of a
+        scoring call; a true return stops the call with BreakscoreError(code ERR_INTERRUPTED) -- the hook the Rcpp glue
+        uses for ``Rcpp::checkUserInterrupt`` (SURVEY.md 8b).  ``None`` removes it."""
+        self._poll_keepalive = POLL_FN((lambda _user: 1 if poll() else 0)) if poll is not None else C.cast(None, POLL_FN)
+        self._check(self._lib.bs_ctx_set_poll(self._ctx, self._poll_keepalive, None))
 
     def enable_timing(self, on: bool = True):
         self._check(self._lib.bs_ctx_enable_timing(self._ctx, 1 if on else 0))

@@ -140,6 +140,10 @@ struct bs_ctx {
     size_t best_elems = 0;
     bool best_dirty = true;
 
+    // interrupt poll of the calling thread (bs_ctx_set_poll)
+    bs_poll_fn poll = nullptr;
+    void *poll_user = nullptr;
+
     // timing
     bool timing = false;
     std::vector<TimedSpan> spans;
@@ -1194,6 +1198,13 @@ int bs_ctx_synchronize(bs_ctx *ctx) {
 
 int64_t bs_ctx_launch_count(const bs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int bs_ctx_set_poll(bs_ctx *ctx, bs_poll_fn poll, void *user) {
+    if (!ctx) return BS_ERR_INVALID;
+    ctx->poll = poll;
+    ctx->poll_user = poll ? user : nullptr;
+    return BS_OK;
+}
+
 int bs_ctx_enable_timing(bs_ctx *ctx, int on) {
     if (!ctx) return BS_ERR_INVALID;
     cudaSetDevice(ctx->device);
@@ -1425,8 +1436,17 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
         }
         chunks.push_back({s0, S, b->seg_read_start[s0], b->seg_read_start[S], b->seg_contig_start[s0], b->seg_contig_start[S]});
     }
+    bool first_chunk = true;
     for (const Chunk &ch : chunks) {
         if (ch.c1 == ch.c0) continue;  // segments without contigs produce nothing
+        if (!first_chunk && ctx->poll && ctx->poll(ctx->poll_user)) {
+            // the caller wants out (R: user interrupt): nothing new is queued, what is in flight finishes
+            sync_all(ctx);
+            for (Workspace &w : ctx->ws) w.in_flight = false;
+            return fail(ctx, BS_ERR_INTERRUPTED, "interrupted by the caller's poll callback after segment %lld of %lld",
+                        (long long)ch.s0, (long long)S);
+        }
+        first_chunk = false;
         BS_TRY(run_chunk(ctx, ctx->ws[ctx->ws_cursor++ % kWorkspaces], e, ch));
     }
     if (e.dev_res) {

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 2
+#define BS_ABI_VERSION 3
 
 /* the library is built with -fvisibility=hidden: only these entry points are exported */
 #if defined(__GNUC__)
@@ -48,7 +48,8 @@ enum {
     BS_ERR_TABLE = 3,     /* table key outside the supported domain (ACGT, length 1..8) */
     BS_ERR_ALLOC = 4,     /* host or device allocation failed */
     BS_ERR_NO_DEVICE = 5, /* no usable GPU: there is no CPU fallback */
-    BS_ERR_STATE = 6      /* e.g. scoring before bs_set_table */
+    BS_ERR_STATE = 6,     /* e.g. scoring before bs_set_table */
+    BS_ERR_INTERRUPTED = 7 /* the poll callback of bs_ctx_set_poll asked the call to stop */
 };
 
 /* flags of bs_score / bs_score_batch */
@@ -145,6 +146,13 @@ BS_API int64_t bs_ctx_launch_count(const bs_ctx *ctx);
 #define BS_N_STAGES 10
 BS_API int bs_ctx_enable_timing(bs_ctx *ctx, int on);
 BS_API int bs_ctx_last_timings(bs_ctx *ctx, double *ms, int n);
+/* Interrupt poll for long calls (upstream's R driver is interactive: Rcpp::checkUserInterrupt is the idiom,
+ * SURVEY.md 8b).  `poll(user)` is called on the CALLING thread between the pipeline chunks of a scoring call
+ * (never from another thread, never inside a kernel launch sequence); a non-zero return makes the call stop
+ * queueing chunks, wait for the ones in flight and return BS_ERR_INTERRUPTED (result arrays are then partly
+ * filled and must not be used).  The context stays usable.  poll == NULL removes the callback. */
+typedef int (*bs_poll_fn)(void *user);
+BS_API int bs_ctx_set_poll(bs_ctx *ctx, bs_poll_fn poll, void *user);
 /* device-event time (ms) of the placement kernel of the last scoring call, -1 if none */
 BS_API double bs_ctx_last_place_ms(bs_ctx *ctx);
 

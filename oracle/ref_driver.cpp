@@ -73,10 +73,15 @@ int ref_calc_breakscore(const char *contig_chars, const int64_t *contig_off, int
             }
         }
         return 0;
+    } catch (const Rcpp::internal::InterruptedException &) {
+        return 3;  // (only the B200 glue raises it: a user interrupt seen by its poll callback)
     } catch (...) {
         return 1;
     }
 }
+
+// test hook: what Ctrl-C does in an R session -- the next R_CheckUserInterrupt of the stand-in header fires
+void ref_raise_interrupt(void) { shim_pending_interrupt() = 1; }
 
 #ifndef BS_DRIVER_NO_ASSEMBLE
 // Upstream assemble_contigs (lib/BreakageScorer.cpp:79-174): returns the number of scaffolds

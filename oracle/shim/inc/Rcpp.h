@@ -55,4 +55,27 @@ public:
 
 inline void stop(const std::string &msg) { throw std::runtime_error(msg); }
 
+// what Rcpp's END_RCPP turns into an R interrupt condition (used by the B200 glue, rcpp/BreakageScorer.cpp)
+namespace internal {
+struct InterruptedException {};
+}  // namespace internal
+
 }  // namespace Rcpp
+
+// stand-ins for the two entry points of R's C API the B200 glue uses to poll for a user interrupt: the test
+// driver raises the flag through shim_pending_interrupt(); R_CheckUserInterrupt "longjmps" (here: throws) when
+// it is set and R_ToplevelExec reports that as FALSE, as in R.
+typedef int Rboolean;
+#ifndef TRUE
+#define TRUE 1
+#define FALSE 0
+#endif
+inline int &shim_pending_interrupt() { static int flag = 0; return flag; }
+struct ShimLongjmp {};
+inline void R_CheckUserInterrupt(void) {
+    if (shim_pending_interrupt()) { shim_pending_interrupt() = 0; throw ShimLongjmp{}; }
+}
+inline Rboolean R_ToplevelExec(void (*fun)(void *), void *data) {
+    try { fun(data); } catch (const ShimLongjmp &) { return FALSE; }
+    return TRUE;
+}

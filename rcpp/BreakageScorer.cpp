@@ -35,16 +35,25 @@ struct Session {
     }
 };
 
+// User interrupts (Ctrl-C / Esc) during a long call: the library polls this between its pipeline chunks, on R's
+// main thread.  R_CheckUserInterrupt leaves by longjmp, so it runs under R_ToplevelExec and nothing unwinds through
+// the C-ABI; the library then drains its streams and returns BS_ERR_INTERRUPTED, which check() turns into the
+// exception Rcpp reports to R as an interrupt.
+void check_interrupt(void *) { R_CheckUserInterrupt(); }
+int poll_user_interrupt(void *) { return R_ToplevelExec(check_interrupt, nullptr) == FALSE; }
+
 Session &session() {
     static Session s;
     if (!s.ctx) {
         const char *dev = std::getenv("BREAKSCORE_DEVICE");
         if (bs_ctx_create(dev ? std::atoi(dev) : 0, &s.ctx) != BS_OK) Rcpp::stop(bs_last_error(nullptr));
+        bs_ctx_set_poll(s.ctx, poll_user_interrupt, nullptr);
     }
     return s;
 }
 
 void check(Session &s, int rc) {
+    if (rc == BS_ERR_INTERRUPTED) throw Rcpp::internal::InterruptedException();
     if (rc != BS_OK) Rcpp::stop(bs_last_error(s.ctx));
 }
 

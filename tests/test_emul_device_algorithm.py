@@ -83,6 +83,34 @@ def test_chunked_pipeline_equals_one_chunk(emul_lib, emul_scorer, kmers, prob, m
         assert np.array_equal(one[k], many[k], equal_nan=True), k
 
 
+def test_poll_callback_interrupts_between_chunks(emul_lib, kmers, prob, monkeypatch):
+    """bs_ctx_set_poll: called between pipeline chunks on the calling thread; a true return ends the call with
+    BS_ERR_INTERRUPTED, the context stays usable and the next full call is bit-identical to an undisturbed one."""
+    from genomeassembler_dev_b200 import synth
+    b = synth.make_batch(7, seed=91, length=1500, read_len=30, coverage=6, contigs_lo=1, contigs_hi=4)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+            b.seg_read_start, b.seg_contig_start)
+    monkeypatch.setenv("BS_CHUNK_KB", "12")
+    with B.BreakageScorer(0, emul_lib) as sc:
+        sc.set_table(kmers, prob)
+        want = sc.score_batch(*args)
+        calls = []
+        sc.set_poll(lambda: calls.append(1) or False)  # never interrupts: same results, polled once per later chunk
+        got = sc.score_batch(*args)
+        assert len(calls) >= 2
+        for k in want:
+            assert np.array_equal(want[k], got[k], equal_nan=True), k
+        calls.clear()
+        sc.set_poll(lambda: calls.append(1) or len(calls) >= 2)  # interrupt at the second poll
+        with pytest.raises(B.BreakscoreError) as ei:
+            sc.score_batch(*args)
+        assert ei.value.code == B.ERR_INTERRUPTED and len(calls) == 2
+        sc.set_poll(None)
+        again = sc.score_batch(*args)
+        for k in want:
+            assert np.array_equal(want[k], again[k], equal_nan=True), k
+
+
 # ---- infix edit distance (lev_dist_vs_true) ---------------------------------------------------
 
 @pytest.mark.parametrize("params", P.SMALL[:4], ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL[:4]])

@@ -158,6 +158,27 @@ def test_chunked_pipeline_equals_one_chunk(product_lib, gpu_scorer, kmers, prob,
         assert np.array_equal(one[k], again[k], equal_nan=True), k
 
 
+def test_poll_callback_interrupts_between_chunks(product_lib, kmers, prob, monkeypatch):
+    """bs_ctx_set_poll on the GPU pipeline: polled between chunks, a true return ends the call with
+    BS_ERR_INTERRUPTED after the chunks in flight have finished; the context stays usable."""
+    b = synth.make_batch(40, seed=91, length=20000, read_len=100, coverage=20, contigs_lo=2, contigs_hi=10)
+    args = (b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off,
+            b.seg_read_start, b.seg_contig_start)
+    monkeypatch.setenv("BS_CHUNK_KB", "1500")
+    with B.BreakageScorer(0, product_lib) as sc:
+        sc.set_table(kmers, prob)
+        want = sc.score_batch(*args)
+        calls = []
+        sc.set_poll(lambda: calls.append(1) or len(calls) >= 2)
+        with pytest.raises(B.BreakscoreError) as ei:
+            sc.score_batch(*args)
+        assert ei.value.code == B.ERR_INTERRUPTED and len(calls) == 2
+        sc.set_poll(None)
+        again = sc.score_batch(*args)
+    for k in want:
+        assert np.array_equal(want[k], again[k], equal_nan=True), k
+
+
 # ---- cfg-4 / cfg-5 shapes ---------------------------------------------------------------------
 
 def test_cfg4_scaffold_set(gpu_scorer, oracle, kmers, prob):

@@ -66,3 +66,4 @@ def test_glue_returns_the_reference_list(glue_lib, oracle, kmers, table_set, ref
         want = oracle.oracle_calc_breakscore(case["path"], case["reads"], case["truth"], case["kmer"], kmers,
                                              table_set[case["table"]], want_ks=False, want_lev=True, want_prob_dist=False)
         assert np.array_equal(got["lev_dist_vs_true"], want["lev_dist_vs_true"]), case["name"]
+
