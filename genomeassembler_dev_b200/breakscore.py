@@ -39,7 +39,7 @@ STAGES = ("h2d", "pack", "place", "score", "truth_spectrum", "prob_dist_ks", "ks
 ABI_SYMBOLS = (
     "bs_abi_version", "bs_ctx_create", "bs_ctx_destroy", "bs_last_error", "bs_ctx_set_stream",
     "bs_ctx_synchronize", "bs_ctx_launch_count", "bs_ctx_enable_timing", "bs_ctx_last_timings",
-    "bs_ctx_last_place_ms", "bs_ctx_set_poll", "bs_set_table", "bs_set_truth_table", "bs_set_second_table", "bs_score_batch", "bs_score",
+    "bs_ctx_last_place_ms", "bs_ctx_set_poll", "bs_set_table", "bs_set_truth_table", "bs_set_second_table", "bs_score_batch", "bs_score", "bs_score_multi",
     "bs_host_alloc", "bs_host_free", "bs_assemble_contigs", "bs_assemble_last_error", "bs_string_list_size",
     "bs_string_list_bytes", "bs_string_list_copy", "bs_string_list_free", "bs_simulate_capacity", "bs_simulate_reads",
 )
@@ -124,6 +124,9 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_score.restype = C.c_int
     lib.bs_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                              C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.POINTER(_Result)]
+    lib.bs_score_multi.restype = C.c_int
+    lib.bs_score_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.POINTER(_Result)]
     lib.bs_host_alloc.restype = C.c_void_p
     lib.bs_host_alloc.argtypes = [C.c_int64]
     lib.bs_host_free.restype = None
@@ -283,9 +286,11 @@ class BreakageScorer:
 
     # -- scoring -------------------------------------------------------------------------
     def score_batch(self, read_chars, read_off, read_len, contig_chars, contig_off, truth_chars,
-                    truth_off, seg_read_start, seg_contig_start, kmer=8, flags=DEFAULT_FLAGS):
+                    truth_off, seg_read_start, seg_contig_start, kmer=8, flags=DEFAULT_FLAGS, group=None):
         """Many independent segments in one call (one upstream calc_breakscore call each).
-        Host numpy buffers in, dict of numpy arrays out (flat path_prob_dist + offsets)."""
+        Host numpy buffers in, dict of numpy arrays out (flat path_prob_dist + offsets).
+        ``group``: more scorers (one per GPU, same tables) -- ONE segment's contigs are then dealt out over
+        ``[self] + group`` by ``bs_score_multi`` (reads replicated, results in input order)."""
         contig_off = np.ascontiguousarray(contig_off, dtype=np.int64)
         truth_off = np.ascontiguousarray(truth_off, dtype=np.int64)
         srs = np.ascontiguousarray(seg_read_start, dtype=np.int64)
@@ -345,7 +350,17 @@ class BreakageScorer:
             out["pos_off"] = pos_off
             r.pos = out["pos_flat"].ctypes.data
             r.pos_off = pos_off.ctypes.data
-        self._check(self._lib.bs_score_batch(self._ctx, C.byref(b), int(kmer), int(flags), C.byref(r)))
+        if group:
+            if S != 1:
+                raise ValueError("a scorer group shards the contigs of ONE segment (shard whole segments over processes instead)")
+            if read_off is None:
+                read_off = np.arange(N + 1, dtype=np.int64) * int(read_len or 0)
+            ctxs = (C.c_void_p * (1 + len(group)))(self._ctx, *[g._ctx for g in group])
+            self._check(self._lib.bs_score_multi(ctxs, len(ctxs), contig_chars.ctypes.data, contig_off.ctypes.data, Cn,
+                                                 read_chars.ctypes.data, read_off.ctypes.data, N, truth_chars.ctypes.data + int(truth_off[0]),
+                                                 int(truth_off[1] - truth_off[0]), int(kmer), int(flags), C.byref(r)))
+        else:
+            self._check(self._lib.bs_score_batch(self._ctx, C.byref(b), int(kmer), int(flags), C.byref(r)))
         del keep
         return out
 
@@ -353,8 +368,9 @@ class BreakageScorer:
         """Thin call for callers that manage their own (possibly device) buffers: bench.py."""
         self._check(self._lib.bs_score_batch(self._ctx, C.byref(batch), int(kmer), int(flags), C.byref(result)))
 
-    def score(self, path, sequencing_reads, true_solution, kmer=8, flags=DEFAULT_FLAGS):
-        """One segment; returns the upstream list (lib/BreakageScorer.cpp:343-353) as a dict."""
+    def score(self, path, sequencing_reads, true_solution, kmer=8, flags=DEFAULT_FLAGS, group=None):
+        """One segment; returns the upstream list (lib/BreakageScorer.cpp:343-353) as a dict.
+        ``group``: further scorers (one per GPU) to share the contigs with, see :meth:`score_batch`."""
         ct, ct_off = flatten(path)
         if isinstance(sequencing_reads, np.ndarray) and sequencing_reads.ndim == 2:
             rd = np.ascontiguousarray(sequencing_reads, dtype=np.uint8).reshape(-1)
@@ -364,7 +380,7 @@ class BreakageScorer:
             rlen, nr = 0, len(sequencing_reads)
         tr, tr_off = flatten([true_solution])
         res = self.score_batch(rd, rd_off, rlen, ct, ct_off, tr, tr_off, [0, nr], [0, len(path)],
-                               kmer=kmer, flags=flags)
+                               kmer=kmer, flags=flags, group=group)
         res["sequence"] = list(path)
         if flags & WANT_PROB_DIST:
             flat, off = res.pop("path_prob_dist_flat"), res.pop("path_prob_dist_off")

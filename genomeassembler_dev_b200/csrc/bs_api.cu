@@ -20,6 +20,7 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/breakscore.h"
@@ -1483,6 +1484,143 @@ int bs_score(bs_ctx *ctx, const char *contig_chars, const int64_t *contig_off, i
     b.seg_read_start = seg_r; b.seg_contig_start = seg_c;
     if (!read_off && n_reads > 0) return fail(ctx, BS_ERR_INVALID, "bs_score: read_off is NULL");
     return bs_score_batch(ctx, &b, kmer, flags, result);
+}
+
+// ---- one segment over several contexts (GPUs) from one process --------------------------------
+namespace {
+
+// the share of one context: its contigs (ascending input indices), their flattened text and private result arrays
+struct MultiShard {
+    std::vector<int64_t> idx, off, pd_off, pos_off;
+    std::vector<char> chars;
+    std::vector<int32_t> i32[4];      // sequence_len, kmer_breaks, startpos, lev
+    std::vector<double> f64[10];      // score, norm, by_len, ks_a, ks_b and the same for the second table
+    std::vector<double> pd, pd2;
+    std::vector<int32_t> hist, pos;
+    bs_result r;
+    int rc = BS_OK;
+};
+
+}  // namespace
+
+int bs_score_multi(bs_ctx *const *ctxs, int n_ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
+                   const char *read_chars, const int64_t *read_off, int64_t n_reads,
+                   const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *res) {
+    if (!ctxs || n_ctx < 1 || !ctxs[0]) return BS_ERR_INVALID;
+    bs_ctx *ctx = ctxs[0];
+    for (int k = 0; k < n_ctx; k++)
+        if (!ctxs[k]) return fail(ctx, BS_ERR_INVALID, "bs_score_multi: context %d is NULL", k);
+    if (flags & (BS_DEVICE_CHARS | BS_DEVICE_RESULT)) return fail(ctx, BS_ERR_INVALID, "bs_score_multi takes host buffers only");
+    if (!res) return fail(ctx, BS_ERR_INVALID, "bs_score_multi: NULL result");
+    if (n_contigs < 0 || n_reads < 0) return fail(ctx, BS_ERR_INVALID, "negative counts");
+    if (n_ctx == 1 || n_contigs == 0)
+        return bs_score(ctx, contig_chars, contig_off, n_contigs, read_chars, read_off, n_reads, truth, truth_len, kmer, flags, res);
+    BS_TRY(check_offsets(ctx, "contig", contig_off, n_contigs));
+    const bool want_pd = (flags & BS_WANT_PROB_DIST) != 0, want_pos = (flags & BS_WANT_POS) != 0, want_hist = (flags & BS_WANT_HIST) != 0;
+    const bool second = (flags & BS_WANT_SECOND_TABLE) != 0;
+    if (want_pd && (!res->path_prob_dist || !res->path_prob_dist_off)) return fail(ctx, BS_ERR_INVALID, "BS_WANT_PROB_DIST needs path_prob_dist and path_prob_dist_off");
+    if (want_pd && second && !res->path_prob_dist2) return fail(ctx, BS_ERR_INVALID, "BS_WANT_SECOND_TABLE with BS_WANT_PROB_DIST needs path_prob_dist2");
+    if (want_pos && (!res->pos || !res->pos_off)) return fail(ctx, BS_ERR_INVALID, "BS_WANT_POS needs pos and pos_off");
+    if (want_hist && !res->hist) return fail(ctx, BS_ERR_INVALID, "BS_WANT_HIST needs hist");
+    const int64_t T = ctx->T;
+    for (int k = 1; k < n_ctx; k++)
+        if (!ctxs[k]->has_table || ctxs[k]->T != T) return fail(ctx, BS_ERR_STATE, "bs_score_multi: context %d does not hold the same table", k);
+
+    // longest-processing-time-first over contig lengths; a context keeps its contigs in input order
+    std::vector<int64_t> order((size_t)n_contigs);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    auto len_of = [&](int64_t c) { return contig_off[c + 1] - contig_off[c]; };
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return len_of(a) > len_of(b); });
+    std::vector<MultiShard> sh((size_t)n_ctx);
+    {
+        std::vector<int64_t> load((size_t)n_ctx, 0);
+        for (int64_t c : order) {
+            const int k = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            sh[k].idx.push_back(c);
+            load[k] += len_of(c) + 1;
+        }
+    }
+    double *const f64_dst[10] = {res->bp_score, res->bp_score_norm_by_break_freqs, res->bp_score_norm_by_len, res->ks_stat_prob_dist,
+                                 res->ks_stat_path_freq, res->bp_score2, res->bp_score_norm_by_break_freqs2,
+                                 res->bp_score_norm_by_len2, res->ks_stat_prob_dist2, res->ks_stat_path_freq2};
+    int32_t *const i32_dst[4] = {res->sequence_len, res->kmer_breaks, res->path_prob_dist_startpos, res->lev_dist_vs_true};
+    for (MultiShard &m : sh) {
+        std::sort(m.idx.begin(), m.idx.end());
+        const size_t n = m.idx.size();
+        m.off.assign(n + 1, 0);
+        m.pd_off.assign(n + 1, 0);
+        m.pos_off.assign(n + 1, 0);
+        for (size_t i = 0; i < n; i++) {
+            const int64_t L = len_of(m.idx[i]);
+            m.off[i + 1] = m.off[i] + L;
+            m.pd_off[i + 1] = m.pd_off[i] + std::max<int64_t>(L - kmer + 1, 0);
+            m.pos_off[i + 1] = m.pos_off[i] + n_reads;
+        }
+        m.chars.resize((size_t)m.off[n] + 1);
+        for (size_t i = 0; i < n; i++)
+            if (len_of(m.idx[i])) std::memcpy(m.chars.data() + m.off[i], contig_chars + contig_off[m.idx[i]], (size_t)len_of(m.idx[i]));
+        std::memset(&m.r, 0, sizeof(m.r));
+        for (int j = 0; j < 4; j++) if (i32_dst[j]) m.i32[j].assign(n + 1, 0);
+        for (int j = 0; j < 10; j++) if (f64_dst[j]) m.f64[j].assign(n + 1, 0.0);
+        m.r.sequence_len = i32_dst[0] ? m.i32[0].data() : nullptr;
+        m.r.kmer_breaks = i32_dst[1] ? m.i32[1].data() : nullptr;
+        m.r.path_prob_dist_startpos = i32_dst[2] ? m.i32[2].data() : nullptr;
+        m.r.lev_dist_vs_true = i32_dst[3] ? m.i32[3].data() : nullptr;
+        double **f64_src[10] = {&m.r.bp_score, &m.r.bp_score_norm_by_break_freqs, &m.r.bp_score_norm_by_len, &m.r.ks_stat_prob_dist,
+                                &m.r.ks_stat_path_freq, &m.r.bp_score2, &m.r.bp_score_norm_by_break_freqs2,
+                                &m.r.bp_score_norm_by_len2, &m.r.ks_stat_prob_dist2, &m.r.ks_stat_path_freq2};
+        for (int j = 0; j < 10; j++) *f64_src[j] = f64_dst[j] ? m.f64[j].data() : nullptr;
+        if (want_pd) {
+            m.pd.assign((size_t)m.pd_off[n] + 1, 0.0);
+            m.r.path_prob_dist = m.pd.data();
+            m.r.path_prob_dist_off = m.pd_off.data();
+            if (second) { m.pd2.assign((size_t)m.pd_off[n] + 1, 0.0); m.r.path_prob_dist2 = m.pd2.data(); }
+        }
+        if (want_hist) { m.hist.assign(n * (size_t)(T + 1) + 1, 0); m.r.hist = m.hist.data(); }
+        if (want_pos) { m.pos.assign((size_t)m.pos_off[n] + 1, 0); m.r.pos = m.pos.data(); m.r.pos_off = m.pos_off.data(); }
+    }
+
+    // one host thread per context with work (a context is single-threaded, contexts are independent)
+    auto run = [&](int k) {
+        MultiShard &m = sh[k];
+        if (m.idx.empty()) return;
+        m.rc = bs_score(ctxs[k], m.chars.data(), m.off.data(), (int64_t)m.idx.size(), read_chars, read_off, n_reads, truth, truth_len,
+                        kmer, flags, &m.r);
+    };
+#ifdef BS_CPU_EMUL
+    for (int k = 0; k < n_ctx; k++) run(k);  // (the CPU emulation keeps __shared__ arrays in statics: one launch at a time)
+#else
+    {
+        std::vector<std::thread> threads;
+        for (int k = 1; k < n_ctx; k++) threads.emplace_back(run, k);
+        run(0);
+        for (std::thread &t : threads) t.join();
+    }
+#endif
+    for (int k = 0; k < n_ctx; k++)
+        if (sh[k].rc != BS_OK) {
+            if (k != 0) std::snprintf(ctx->err, sizeof(ctx->err), "context %d: %.480s", k, ctxs[k]->err);
+            return sh[k].rc;
+        }
+
+    // back into input order
+    for (const MultiShard &m : sh) {
+        for (size_t i = 0; i < m.idx.size(); i++) {
+            const int64_t c = m.idx[i];
+            for (int j = 0; j < 4; j++) if (i32_dst[j]) i32_dst[j][c] = m.i32[j][i];
+            for (int j = 0; j < 10; j++) if (f64_dst[j] && (j < 5 || second)) f64_dst[j][c] = m.f64[j][i];
+            if (want_pd) {
+                const size_t nb = (size_t)(m.pd_off[i + 1] - m.pd_off[i]) * sizeof(double);
+                if (nb) {
+                    std::memcpy(res->path_prob_dist + res->path_prob_dist_off[c], m.pd.data() + m.pd_off[i], nb);
+                    if (second) std::memcpy(res->path_prob_dist2 + res->path_prob_dist_off[c], m.pd2.data() + m.pd_off[i], nb);
+                }
+            }
+            if (want_hist) std::memcpy(res->hist + (size_t)c * (size_t)(T + 1), m.hist.data() + i * (size_t)(T + 1), (size_t)(T + 1) * 4);
+            if (want_pos && n_reads) std::memcpy(res->pos + res->pos_off[c], m.pos.data() + m.pos_off[i], (size_t)n_reads * 4);
+        }
+    }
+    return BS_OK;
 }
 
 int64_t bs_simulate_capacity(const int64_t *truth_off, int64_t n_segments, int32_t read_len, double coverage) {

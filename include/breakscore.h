@@ -174,6 +174,19 @@ BS_API int bs_score(bs_ctx *ctx, const char *contig_chars, const int64_t *contig
              const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *result);
 
 /*
+ * One segment with many candidate contigs / scaffolds, scored by SEVERAL contexts at once -- one per GPU of the box,
+ * driven from ONE process and one calling thread, which is how upstream's R driver runs.  Contigs
+ * are dealt out to the contexts longest first (LPT), reads and truth go to every context (replicated input), every
+ * context runs bs_score on its share from its own host thread, and the results come back in INPUT order: the same
+ * bytes as one bs_score call on one context (per-contig reductions have a fixed order).  Every context must hold the
+ * same tables (bs_set_table ... on each).  Host buffers only (BS_DEVICE_CHARS / BS_DEVICE_RESULT are refused).
+ * On failure the status of the first failing context is returned and its text is copied to bs_last_error(ctxs[0]).
+ */
+BS_API int bs_score_multi(bs_ctx *const *ctxs, int n_ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
+             const char *read_chars, const int64_t *read_off, int64_t n_reads,
+             const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *result);
+
+/*
  * Scaffold explosion on the host (upstream assemble_contigs, lib/BreakageScorer.cpp:79-174): the
  * generator of the candidate set that bs_score then scores.  n_shuffles: upstream uses 20000;
  * n_threads <= 0: all host cores.  The result is an opaque list of strings (longest first, upstream

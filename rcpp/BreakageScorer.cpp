@@ -23,6 +23,7 @@ namespace {
 // process-lifetime device context: table, work buffers and pinned staging survive across calls
 struct Session {
     bs_ctx *ctx = nullptr;
+    std::vector<bs_ctx *> all;  // ctx first, then one context per further GPU of BREAKSCORE_DEVICES
     std::vector<std::string> table_kmer;
     std::vector<double> table_prob;
     std::vector<double> truth_prob;  // optional: table behind the KS truth side (set_breakscore_truth_prob)
@@ -31,6 +32,7 @@ struct Session {
     int64_t pinned_cap = 0;
     ~Session() {
         if (pinned) bs_host_free(pinned);
+        for (size_t k = 1; k < all.size(); k++) bs_ctx_destroy(all[k]);
         if (ctx) bs_ctx_destroy(ctx);
     }
 };
@@ -45,9 +47,30 @@ int poll_user_interrupt(void *) { return R_ToplevelExec(check_interrupt, nullptr
 Session &session() {
     static Session s;
     if (!s.ctx) {
-        const char *dev = std::getenv("BREAKSCORE_DEVICE");
-        if (bs_ctx_create(dev ? std::atoi(dev) : 0, &s.ctx) != BS_OK) Rcpp::stop(bs_last_error(nullptr));
+        // BREAKSCORE_DEVICES=0,1,...,7: the contigs of every call are shared out over these GPUs (bs_score_multi; R is one
+        // process, so one process drives them all); else BREAKSCORE_DEVICE=<n> (default 0), one GPU
+        std::vector<int> devs;
+        if (const char *list = std::getenv("BREAKSCORE_DEVICES")) {
+            for (const char *p = list; *p;) {
+                char *end = nullptr;
+                const long d = std::strtol(p, &end, 10);
+                if (end == p) break;
+                devs.push_back((int)d);
+                p = *end == ',' ? end + 1 : end;
+            }
+        }
+        if (devs.empty()) {
+            const char *dev = std::getenv("BREAKSCORE_DEVICE");
+            devs.push_back(dev ? std::atoi(dev) : 0);
+        }
+        if (bs_ctx_create(devs[0], &s.ctx) != BS_OK) Rcpp::stop(bs_last_error(nullptr));
         bs_ctx_set_poll(s.ctx, poll_user_interrupt, nullptr);
+        s.all.assign(1, s.ctx);
+        for (size_t k = 1; k < devs.size(); k++) {
+            bs_ctx *more = nullptr;
+            if (bs_ctx_create(devs[k], &more) != BS_OK) Rcpp::stop(bs_last_error(nullptr));
+            s.all.push_back(more);
+        }
     }
     return s;
 }
@@ -127,14 +150,17 @@ Rcpp::List calc_breakscore(
         std::vector<char> chars((size_t)flat_size(bp_kmer) + 1);
         std::vector<int64_t> off;
         flatten(bp_kmer, chars.data(), off);
-        check(s, bs_set_table(s.ctx, chars.data(), off.data(), bp_prob.data(), (int64_t)bp_prob.size()));
+        for (bs_ctx *c : s.all)
+            if (bs_set_table(c, chars.data(), off.data(), bp_prob.data(), (int64_t)bp_prob.size()) != BS_OK) Rcpp::stop(bs_last_error(c));
         s.table_kmer = bp_kmer;
         s.table_prob = bp_prob;
         s.truth_dirty = true;
     }
     if (s.truth_dirty) {
-        if (s.truth_prob.size() == bp_prob.size()) check(s, bs_set_truth_table(s.ctx, s.truth_prob.data(), (int64_t)s.truth_prob.size()));
-        else check(s, bs_set_truth_table(s.ctx, nullptr, 0));
+        const bool own = s.truth_prob.size() == bp_prob.size();
+        for (bs_ctx *c : s.all)
+            if (bs_set_truth_table(c, own ? s.truth_prob.data() : nullptr, own ? (int64_t)s.truth_prob.size() : 0) != BS_OK)
+                Rcpp::stop(bs_last_error(c));
         s.truth_dirty = false;
     }
 
@@ -182,8 +208,9 @@ Rcpp::List calc_breakscore(
     r.path_prob_dist = pd_flat.data();
     r.path_prob_dist_off = pd_off.data();
     if (want_path_freq) r.hist = hist.data();
-    check(s, bs_score(s.ctx, ctg_chars, ctg_off.data(), C, read_chars, read_off.data(), (int64_t)sequencing_reads.size(),
-                      truth_chars, (int64_t)true_solution.size(), kmer, BS_DEFAULT_FLAGS | BS_WANT_LEV | (want_path_freq ? BS_WANT_HIST : 0u), &r));
+    check(s, bs_score_multi(s.all.data(), (int)s.all.size(), ctg_chars, ctg_off.data(), C, read_chars, read_off.data(),
+                            (int64_t)sequencing_reads.size(), truth_chars, (int64_t)true_solution.size(), kmer,
+                            BS_DEFAULT_FLAGS | BS_WANT_LEV | (want_path_freq ? BS_WANT_HIST : 0u), &r));
 
     std::vector<std::vector<double>> path_prob_dist((size_t)C);
     for (int64_t c = 0; c < C; c++) path_prob_dist[c].assign(pd_flat.begin() + pd_off[c], pd_flat.begin() + pd_off[c + 1]);

@@ -111,6 +111,37 @@ def test_poll_callback_interrupts_between_chunks(emul_lib, kmers, prob, monkeypa
             assert np.array_equal(want[k], again[k], equal_nan=True), k
 
 
+def test_one_segment_over_several_contexts(emul_lib, emul_scorer, kmers, prob):
+    """bs_score_multi: the contigs of one segment dealt out over three contexts (one host thread each, reads replicated)
+    == one call on one context, byte for byte, every output including the variable-length ones."""
+    seg = P.make(*P.SMALL[1], mut=0.3)
+    contigs = list(seg.contigs) + [seg.contigs[0][:5], b"", seg.contigs[-1]]  # short, empty and duplicate contigs too
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS | B.WANT_LEV | B.WANT_SECOND_TABLE
+    emul_scorer.set_table(kmers, prob)
+    emul_scorer.set_second_table(tables.uniform(len(prob)))
+    want = emul_scorer.score(contigs, seg.reads, seg.truth, flags=flags)
+    others = [B.BreakageScorer(0, emul_lib) for _ in range(2)]
+    try:
+        for o in others:
+            o.set_table(kmers, prob)
+            o.set_second_table(tables.uniform(len(prob)))
+        got = emul_scorer.score(contigs, seg.reads, seg.truth, flags=flags, group=others)
+        more = emul_scorer.score(contigs[:2], seg.reads, seg.truth, flags=flags, group=others)  # fewer contigs than contexts
+        two = emul_scorer.score(contigs[:2], seg.reads, seg.truth, flags=flags)
+        others[1].set_table(kmers[:16], np.full(16, 1 / 16))  # a context with another table is refused
+        with pytest.raises(B.BreakscoreError):
+            emul_scorer.score(contigs, seg.reads, seg.truth, flags=flags, group=others)
+    finally:
+        for o in others:
+            o.close()
+    for a, b in ((want, got), (two, more)):
+        for k in a:
+            if k in ("path_prob_dist", "path_prob_dist2"):
+                assert all(np.array_equal(x, y) for x, y in zip(a[k], b[k])), k
+            elif k != "sequence":
+                assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
 # ---- infix edit distance (lev_dist_vs_true) ---------------------------------------------------
 
 @pytest.mark.parametrize("params", P.SMALL[:4], ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL[:4]])

@@ -179,6 +179,29 @@ def test_poll_callback_interrupts_between_chunks(product_lib, kmers, prob, monke
         assert np.array_equal(want[k], again[k], equal_nan=True), k
 
 
+def test_one_segment_over_several_contexts(product_lib, gpu_scorer, kmers, prob):
+    """bs_score_multi on the GPU: three contexts (here on the same device; on an 8-GPU box one per GPU), a host
+    thread each, contigs dealt out longest first, reads replicated == one call on one context, byte for byte."""
+    seg = P.make(77, 20000, 64, 20, 25, 1, mut=0.3)
+    contigs = list(seg.contigs) + [seg.contigs[0][:5], b"", seg.contigs[-1]]
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS | B.WANT_LEV
+    gpu_scorer.set_table(kmers, prob)
+    want = gpu_scorer.score(contigs, seg.reads, seg.truth, flags=flags)
+    others = [B.BreakageScorer(0, product_lib) for _ in range(2)]
+    try:
+        for o in others:
+            o.set_table(kmers, prob)
+        got = gpu_scorer.score(contigs, seg.reads, seg.truth, flags=flags, group=others)
+    finally:
+        for o in others:
+            o.close()
+    for k in want:
+        if k == "path_prob_dist":
+            assert all(np.array_equal(x, y) for x, y in zip(want[k], got[k])), k
+        elif k != "sequence":
+            assert np.array_equal(want[k], got[k], equal_nan=True), k
+
+
 # ---- cfg-4 / cfg-5 shapes ---------------------------------------------------------------------
 
 def test_cfg4_scaffold_set(gpu_scorer, oracle, kmers, prob):
