@@ -1004,7 +1004,11 @@ int ChunkRun::startpos() {
         sa.tab_key = (unsigned long long *)ws.sp_key.p; sa.tab_head = (int32_t *)ws.sp_head.p; sa.tab_next = (int32_t *)ws.sp_next.p;
         BS_LAUNCH(bs::k_startpos_build, grid_for(C, kStartposThreads, grid_cap), kStartposThreads, 0, st, sa);
         ctx->launches++;
-        BS_LAUNCH(bs::k_startpos_index, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
+        // BS_STARTPOS_BITMAP=1: prefix-bitmap filter in front of the seed table (fewer instructions per truth position;
+        // same results, CPU-emulation tested, not yet measured on the GPU -- off by default until it is)
+        const char *bm_env = std::getenv("BS_STARTPOS_BITMAP");
+        if (bm_env && bm_env[0] == '1') BS_LAUNCH(bs::k_startpos_index<true>, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
+        else BS_LAUNCH(bs::k_startpos_index<false>, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
         ctx->launches++;
         BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kStartposThreads, 0, st, sa);
         ctx->launches++;

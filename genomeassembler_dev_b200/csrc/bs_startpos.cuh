@@ -51,6 +51,7 @@ struct StartposArgs {
 
 constexpr int SP_SLOTS = 2048;  // seed table slots per group; slot SP_SLOTS is reserved for the all-ones seed (= the empty marker)
 constexpr int SP_GROUP = 1024;  // contigs per group
+constexpr int SP_BITMAP_WORDS = 65536 / 32;  // k_startpos_index<true>: one bit per 8-base prefix of a seed
 constexpr int SP_RUN = 8;           // consecutive truth positions per thread and scan step of k_startpos_index (divides 32)
 constexpr int SP_VERIFY_BATCH = 4;  // contig words compared per verification step of k_startpos_index
 
@@ -160,10 +161,12 @@ __device__ __forceinline__ void startpos_verify(const StartposArgs &a, int ci_he
     }
 }
 
+template <bool BITMAP>
 __global__ void __launch_bounds__(256, 4) k_startpos_index(StartposArgs a) {
     __shared__ unsigned long long s_key[SP_SLOTS + 1];
     __shared__ int32_t s_head[SP_SLOTS + 1];
     __shared__ int32_t s_next[SP_GROUP];
+    __shared__ uint32_t s_bits[BITMAP ? SP_BITMAP_WORDS : 1];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int seg = blockIdx.x / a.splits, part = blockIdx.x % a.splits;
     const int64_t LT = a.tr_off[seg + 1] - a.tr_off[seg];
@@ -191,6 +194,17 @@ __global__ void __launch_bounds__(256, 4) k_startpos_index(StartposArgs a) {
         }
         for (int i = tid; i < gn; i += nthr) s_next[i] = a.tab_next[g0 + i];  // (only the entries of chained contigs are ever read)
         if (!__syncthreads_or(any)) continue;  // no contig of this group is in the index
+        if constexpr (BITMAP) {
+            // one bit per value of a seed's first eight bases: a position whose bit is clear cannot be a seed hit
+            for (int i = tid; i < SP_BITMAP_WORDS; i += nthr) s_bits[i] = 0;
+            __syncthreads();
+            for (int i = tid; i <= SP_SLOTS; i += nthr) {
+                if (s_head[i] == 0) continue;
+                const uint32_t k16 = i == SP_SLOTS ? 0xffffu : (uint32_t)(s_key[i] >> 48);
+                atomicOr(&s_bits[k16 >> 5], 1u << (k16 & 31));
+            }
+            __syncthreads();
+        }
         // SP_RUN consecutive positions per thread: they share one pair of truth words and one pair of mask words
         // (SP_RUN divides 32 and slices start at multiples of 32), so a position costs two funnel shifts, a hash
         // and a shared-memory probe -- no global load of its own
@@ -202,13 +216,31 @@ __global__ void __launch_bounds__(256, 4) k_startpos_index(StartposArgs a) {
             const uint32_t m_a = __ldg(&tm[idx]), m_b = __ldg(&tm[idx + 1]);
             const uint64_t w_a = __ldg(&tw[idx]), w_b = __ldg(&tw[idx + 1]);
             uint32_t hits = 0;  // positions of the run whose seed is in the table
+            if constexpr (BITMAP) {
+                // the first eight bases of the run's eight windows all lie in the top 32 bits of the window at the run's
+                // start: a shift, a shared-memory word and a bit test per position; the table is probed for bitmap hits only
+                const uint32_t r_hi = (uint32_t)(window64(w_a, w_b, o0) >> 32);
+                uint32_t maybe = 0;
 #pragma unroll
-            for (int u = 0; u < SP_RUN; u++) {
-                const uint32_t o = o0 + (uint32_t)u;
-                const unsigned long long seed = window64(w_a, w_b, o);
-                bool hit = startpos_probe(s_key, s_head, seed) != 0;
-                hit = hit && window32(m_a, m_b, o) == 0;  // (no byte outside ACGT in the window)
-                hits |= (uint32_t)hit << u;
+                for (int u = 0; u < SP_RUN; u++) {
+                    const uint32_t k16 = (r_hi >> (16 - 2 * u)) & 0xffffu;
+                    maybe |= ((s_bits[k16 >> 5] >> (k16 & 31)) & 1u) << u;
+                }
+                while (maybe) {
+                    const int u = __ffs((int)maybe) - 1;
+                    maybe &= maybe - 1;
+                    const uint32_t o = o0 + (uint32_t)u;
+                    if (window32(m_a, m_b, o) == 0 && startpos_probe(s_key, s_head, window64(w_a, w_b, o)) != 0) hits |= 1u << u;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < SP_RUN; u++) {
+                    const uint32_t o = o0 + (uint32_t)u;
+                    const unsigned long long seed = window64(w_a, w_b, o);
+                    bool hit = startpos_probe(s_key, s_head, seed) != 0;
+                    hit = hit && window32(m_a, m_b, o) == 0;  // (no byte outside ACGT in the window)
+                    hits |= (uint32_t)hit << u;
+                }
             }
             // seed hits (rare): this thread verifies the whole contig; one copy of that code, outside the unrolled run
             while (hits) {
