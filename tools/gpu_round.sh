@@ -12,6 +12,9 @@ out=gpurun_out
 mkdir -p $out
 timeout 400 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "rc=$?" >> $out/${tag}_pytest.log
 timeout 200 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench.err || exit 1
+# candidates waiting for a GPU measurement ("Open"): same tests and bench with the switch on
+BS_STARTPOS_BITMAP=1 timeout 200 python -m pytest tests -m gpu -x -q -k "startpos or cfg2_shape or cfg4 or cfg5 or edit_distance_edge or reference_vectors" > $out/${tag}_pytest_bitmap.log 2>&1; echo "rc=$?" >> $out/${tag}_pytest_bitmap.log
+BS_STARTPOS_BITMAP=1 timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-study --scan-segments 0 > $out/${tag}_bench_bitmap.json 2>> $out/${tag}_bench.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-study --scan-segments 0 > $out/${tag}_ncu_bench.log 2>&1
 BS_CHUNK_KB=4000000 timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$kernels" -s 2 -c 4 \
