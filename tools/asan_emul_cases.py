@@ -30,4 +30,31 @@ for params in P.SMALL[:4]:
 for name,contigs,reads,truth,kmer in P.edge_inputs():
     P.check_segment(sc,O,kmers,prob,synth.Segment(truth,None,contigs),kmer=kmer,reads=reads,flags=P.FULL); n+=1
 del os.environ['BS_PLACE_SCRATCH_MB'], os.environ['BS_PLACE_HASH_CAP']
+# one segment over several contexts (bs_score_multi: host-side sharding and scatter), every output kind, odd contig sets
+others=[B.BreakageScorer(0,'/tmp/asan/libbreakscore_emul.so') for _ in range(2)]
+for o in others: o.set_table(kmers,prob); o.set_second_table(T.uniform(len(prob)))
+sc.set_table(kmers,prob); sc.set_second_table(T.uniform(len(prob)))
+fl=B.DEFAULT_FLAGS|B.WANT_HIST|B.WANT_POS|B.WANT_LEV|B.WANT_SECOND_TABLE
+for ctgs in (list(seg.contigs)+[b'',seg.contigs[0][:3]], [seg.contigs[0]], [b'',b''], list(seg.contigs)*2):
+    a=sc.score(ctgs, seg.read_list, seg.truth, flags=fl); g=sc.score(ctgs, seg.read_list, seg.truth, flags=fl, group=others)
+    assert all(np.array_equal(a[k],g[k],equal_nan=True) for k in a if k not in ('sequence','path_prob_dist','path_prob_dist2')); n+=1
+sc.score(list(seg.contigs), [], seg.truth, flags=fl, group=others); n+=1   # no reads at all
+for o in others: o.close()
+# prefix-bitmap scan of the contig-in-truth search; interrupt poll between chunks
+os.environ['BS_STARTPOS_BITMAP']='1'
+for params in P.SMALL[:3]:
+    P.check_segment(sc,O,kmers,prob,P.make(*params,mut=0.5),flags=P.FULL|B.WANT_LEV); n+=1
+for name,contigs,reads,truth,kmer in P.edge_inputs():
+    P.check_segment(sc,O,kmers,prob,synth.Segment(truth,None,contigs),kmer=kmer,reads=reads,flags=P.FULL|B.WANT_LEV); n+=1
+del os.environ['BS_STARTPOS_BITMAP']
+os.environ['BS_CHUNK_KB']='12'
+with B.BreakageScorer(0,'/tmp/asan/libbreakscore_emul.so') as sc2:
+    sc2.set_table(kmers,prob); calls=[]
+    sc2.set_poll(lambda: calls.append(1) or len(calls)>=2)
+    try:
+        sc2.score_batch(b.read_chars,None,b.read_len,b.contig_chars,b.contig_off,b.truth_chars,b.truth_off,b.seg_read_start,b.seg_contig_start); raise SystemExit('not interrupted')
+    except B.BreakscoreError as e: assert e.code==B.ERR_INTERRUPTED
+    sc2.set_poll(None)
+    sc2.score_batch(b.read_chars,None,b.read_len,b.contig_chars,b.contig_off,b.truth_chars,b.truth_off,b.seg_read_start,b.seg_contig_start); n+=1
+del os.environ['BS_CHUNK_KB']
 print('asan run ok', n, 'cases')
