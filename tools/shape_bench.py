@@ -57,8 +57,27 @@ def main():
     for r in (50, 300):
         run(sc, f"cfg3: 50 kb, r={r} 30x, 40 contigs", synth.make_segment(1300 + r, 50000, r, 30, 40))
     run(sc, "cfg3: 50 kb, r=12 40x, 60 contigs (script 00 grid)", synth.make_segment(1312, 50000, 12, 40, 60))
-    run(sc, "cfg4: 10000 scaffolds of 10-50 kb, one segment", synth.make_scaffold_set(1400, n_scaffolds=10000), reps=2,
-        flags=B.WANT_KS | B.WANT_STARTPOS)
+    cfg4 = synth.make_scaffold_set(1400, n_scaffolds=10000)
+    run(sc, "cfg4: 10000 scaffolds of 10-50 kb, one segment", cfg4, reps=2, flags=B.WANT_KS | B.WANT_STARTPOS)
+    # SHAPE_MULTI_GPUS=N: the same scaffold set with its contigs dealt out over N GPUs of this process (bs_score_multi)
+    n_gpus = int(os.environ.get("SHAPE_MULTI_GPUS", "1"))
+    if n_gpus > 1:
+        others = [B.BreakageScorer(d) for d in range(1, n_gpus)]
+        for o in others:
+            o.set_table(kmers, prob)
+        fl = B.WANT_KS | B.WANT_STARTPOS
+        one = sc.score(cfg4.contigs, cfg4.reads, cfg4.truth, flags=fl)
+        for _ in range(2):
+            sc.score(cfg4.contigs, cfg4.reads, cfg4.truth, flags=fl, group=others)
+        t0 = time.perf_counter()
+        got = sc.score(cfg4.contigs, cfg4.reads, cfg4.truth, flags=fl, group=others)
+        wall = time.perf_counter() - t0
+        same = all(np.array_equal(one[k], got[k], equal_nan=True) for k in one if k != "sequence")
+        pair = cfg4.reads.shape[0] * float(sum(len(c) for c in cfg4.contigs))
+        print(json.dumps({"shape": f"cfg4 over {n_gpus} GPUs of one process (bs_score_multi)", "wall_ms": round(wall * 1e3, 2),
+                          "pair_Gbp_per_s_wall": round(pair / 1e9 / wall, 1), "identical_to_one_gpu": bool(same)}), flush=True)
+        for o in others:
+            o.close()
     rng = np.random.default_rng(1500)
     L, N, Cn, r = 10_000_000, 2_000_000, 10_000, 150
     truth = synth.codes_to_ascii(synth.random_truth_codes(rng, L))
