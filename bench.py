@@ -376,6 +376,17 @@ def b200_main(args):
     ms_per_step = ms_total / args.steps
     value = all_pair / 1e9 / (ms_per_step / 1e3)
 
+    if args.device_only:  # profiling runs (ncu): the device-resident phase only
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": ms_per_step, "device_only": True,
+                              "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if v > 0},
+                              "gpu_launches": int(launches), "clocks": clocks}))
+        if world > 1:
+            dist.destroy_process_group()
+        sc.close()
+        return 0
+
     # ---- e2e: host buffers through the C-ABI (pinned), H2D + D2H inside the timed region ----
     def pinned_copy(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -605,6 +616,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--segments", type=int, default=1000, help="segments per GPU (cfg-2 study size: 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="device-resident phase only (profiling runs)")
     ap.add_argument("--no-study", action="store_true", help="skip the extra simulate-on-device measurement")
     ap.add_argument("--scan-segments", type=int, default=20, help="segments timed with the all-pairs / tile placement kernels (0: skip)")
     args = ap.parse_args()

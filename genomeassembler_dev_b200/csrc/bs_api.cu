@@ -12,6 +12,7 @@
 #include "bs_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1092,18 +1093,40 @@ int ChunkRun::results() {
 }
 
 // ---- one chunk: metadata, H2D, kernels, D2H --------------------------------------------------
+// BS_TRACE=1: host wall time of every stage's queueing code on stderr (diagnostic; the device times are the
+// CUDA-event stage timers of bs_ctx_last_timings)
+struct HostTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    HostTrace() : on(std::getenv("BS_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[bs trace] %-12s %9.3f ms host\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     ChunkRun r(ctx, ws, e, ch);
+    HostTrace tr;
     BS_TRY(r.prepare());
+    tr.lap("prepare");
     BS_TRY(r.pack());
+    tr.lap("pack");
     BS_TRY(r.place());
+    tr.lap("place");
     BS_TRY(r.spectrum());
     BS_TRY(r.score(0));
     BS_TRY(r.prob_dist(0));
     BS_TRY(r.second_table());
+    tr.lap("score+ks");
     BS_TRY(r.startpos());
     BS_TRY(r.lev());
-    return r.results();
+    tr.lap("startpos+lev");
+    const int rc = r.results();
+    tr.lap("results");
+    return rc;
 }
 
 }  // namespace
