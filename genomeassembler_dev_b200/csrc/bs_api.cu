@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <numeric>
 #include <string>
@@ -141,6 +142,8 @@ struct bs_ctx {
     DevBuf sim_meta, sim_chars, sim_words, sim_mask, sim_cdf, sim_starts, sim_kept, sim_reads;  // bs_simulate_reads
     size_t best_elems = 0;
     bool best_dirty = true;
+
+    bool status_pending = false;  // a device-result call wanted KS-B: d_status has not been read since
 
     // interrupt poll of the calling thread (bs_ctx_set_poll)
     bs_poll_fn poll = nullptr;
@@ -1221,7 +1224,15 @@ int bs_ctx_set_stream(bs_ctx *ctx, void *cuda_stream) {
 int bs_ctx_synchronize(bs_ctx *ctx) {
     if (!ctx) return BS_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    return sync_all(ctx);
+    BS_TRY(sync_all(ctx));
+    if (ctx->status_pending) {  // KS-B tally overflow of an asynchronous (device-result) call: report it here
+        int32_t status = 0;
+        ctx->status_pending = false;
+        BS_CUDA(cudaMemcpyAsync(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        BS_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (status) return fail(ctx, BS_ERR_INVALID, "ks_stat_path_freq of an earlier device-result call: more than %d table rows with a count >= %d in one contig", bs::OVF_CAP, bs::CC_DENSE);
+    }
+    return BS_OK;
 }
 
 int64_t bs_ctx_launch_count(const bs_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -1281,7 +1292,20 @@ void bs_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+static int bs_set_table_impl(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, const double *prob, int64_t n);
+
 int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, const double *prob, int64_t n) {
+    if (!ctx) return BS_ERR_INVALID;
+    try {
+        return bs_set_table_impl(ctx, kmer_chars, kmer_off, prob, n);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, BS_ERR_ALLOC, "bs_set_table: out of host memory");
+    } catch (...) {
+        return fail(ctx, BS_ERR_STATE, "bs_set_table: unexpected exception");
+    }
+}
+
+static int bs_set_table_impl(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, const double *prob, int64_t n) {
     if (!ctx) return BS_ERR_INVALID;
     if (n < 0 || (n > 0 && (!kmer_chars || !kmer_off || !prob))) return fail(ctx, BS_ERR_INVALID, "bs_set_table: NULL argument");
     if (n > 0x7fffffff) return fail(ctx, BS_ERR_INVALID, "bs_set_table: too many rows");
@@ -1307,10 +1331,10 @@ int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, c
     BS_TRY(sync_all(ctx));
     ctx->prob_dense.swap(pd);
     ctx->row_dense.swap(rd);
-    if (!ctx->has_truth_table || (int64_t)ctx->T != n) {
-        ctx->tprob_dense = ctx->prob_dense;
-        ctx->has_truth_table = false;
-    }
+    // a truth-side table is indexed by the PREVIOUS table's key -> row mapping: it goes with the old table
+    // (callers that want one set it again with bs_set_truth_table, as the Python and Rcpp front-ends do)
+    ctx->tprob_dense = ctx->prob_dense;
+    ctx->has_truth_table = false;
     ctx->T = n;
     ctx->has_table = true;
     ctx->table_version++;
@@ -1318,7 +1342,20 @@ int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, c
     return upload_table(ctx, ctx->prob_dense, ctx->d_tab);
 }
 
+static int bs_set_second_table_impl(bs_ctx *ctx, const double *prob, int64_t n);
+
 int bs_set_second_table(bs_ctx *ctx, const double *prob, int64_t n) {
+    if (!ctx) return BS_ERR_INVALID;
+    try {
+        return bs_set_second_table_impl(ctx, prob, n);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, BS_ERR_ALLOC, "bs_set_second_table: out of host memory");
+    } catch (...) {
+        return fail(ctx, BS_ERR_STATE, "bs_set_second_table: unexpected exception");
+    }
+}
+
+static int bs_set_second_table_impl(bs_ctx *ctx, const double *prob, int64_t n) {
     if (!ctx) return BS_ERR_INVALID;
     if (!ctx->has_table) return fail(ctx, BS_ERR_STATE, "bs_set_second_table before bs_set_table");
     if (!prob) { ctx->has_table2 = false; return BS_OK; }
@@ -1339,7 +1376,20 @@ int bs_set_second_table(bs_ctx *ctx, const double *prob, int64_t n) {
     return upload_table(ctx, ctx->prob2_dense, ctx->d_tab2);
 }
 
+static int bs_set_truth_table_impl(bs_ctx *ctx, const double *prob, int64_t n);
+
 int bs_set_truth_table(bs_ctx *ctx, const double *prob, int64_t n) {
+    if (!ctx) return BS_ERR_INVALID;
+    try {
+        return bs_set_truth_table_impl(ctx, prob, n);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, BS_ERR_ALLOC, "bs_set_truth_table: out of host memory");
+    } catch (...) {
+        return fail(ctx, BS_ERR_STATE, "bs_set_truth_table: unexpected exception");
+    }
+}
+
+static int bs_set_truth_table_impl(bs_ctx *ctx, const double *prob, int64_t n) {
     if (!ctx) return BS_ERR_INVALID;
     if (!ctx->has_table) return fail(ctx, BS_ERR_STATE, "bs_set_truth_table before bs_set_table");
     if (!prob) {
@@ -1363,8 +1413,23 @@ int bs_set_truth_table(bs_ctx *ctx, const double *prob, int64_t n) {
     return BS_OK;
 }
 
+static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res);
+
+// nothing throws across the boundary: host allocation failures of the std containers used inside become a status
 int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res) {
     if (!ctx) return BS_ERR_INVALID;
+    try {
+        return score_batch_impl(ctx, b, kmer, flags, res);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, BS_ERR_ALLOC, "bs_score_batch: out of host memory");
+    } catch (const std::exception &ex) {
+        return fail(ctx, BS_ERR_STATE, "bs_score_batch: %s", ex.what());
+    } catch (...) {
+        return fail(ctx, BS_ERR_STATE, "bs_score_batch: unknown exception");
+    }
+}
+
+static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res) {
     if (!b || !res) return fail(ctx, BS_ERR_INVALID, "bs_score_batch: NULL batch or result");
     if (!ctx->has_table) return fail(ctx, BS_ERR_STATE, "bs_score_batch before bs_set_table");
     if (kmer < 1) return fail(ctx, BS_ERR_INVALID, "kmer must be >= 1 (got %d)", kmer);
@@ -1423,9 +1488,12 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     }
     if (e.want_ks || e.want_pd) BS_TRY(prepare_ks(ctx, kmer));
     if (e.second && (e.want_ks || e.want_pd)) BS_TRY(prepare_ks(ctx, kmer, ctx->ks2, ctx->prob2_dense));
-    if (e.want_ks && res->ks_stat_path_freq) {
+    const bool any_ksb = e.want_ks && (res->ks_stat_path_freq || (e.second && res->ks_stat_path_freq2));
+    if (any_ksb) {
         BS_TRY(ensure(ctx, ctx->d_status, 16));
-        BS_CUDA(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
+        // (not cleared between device-result calls: an overflow of an earlier asynchronous call is reported by the
+        // next synchronising call -- bs_ctx_synchronize or a host-result score)
+        if (!ctx->status_pending) BS_CUDA(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
     }
 
     // ---------------- chunks of whole segments ----------------
@@ -1482,10 +1550,12 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
         // in flight: whoever takes one next (this call's successor included) first waits for the event
         // recorded behind its last kernel, so staging memory is never rewritten under a running chunk.
         ctx->best_dirty = false;
+        if (any_ksb) ctx->status_pending = true;  // read by bs_ctx_synchronize / the next host-result call
         return BS_OK;
     }
     int32_t status = 0;
-    if (e.want_ks && res->ks_stat_path_freq) BS_CUDA(cudaMemcpyAsync(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (any_ksb) BS_CUDA(cudaMemcpyAsync(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->status_pending = false;
     BS_TRY(sync_all(ctx));
     for (Workspace &w : ctx->ws) w.in_flight = false;
     ctx->best_dirty = false;
@@ -1530,13 +1600,34 @@ struct MultiShard {
 
 }  // namespace
 
+static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
+                            const char *read_chars, const int64_t *read_off, int64_t n_reads,
+                            const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *res);
+
 int bs_score_multi(bs_ctx *const *ctxs, int n_ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
                    const char *read_chars, const int64_t *read_off, int64_t n_reads,
                    const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *res) {
     if (!ctxs || n_ctx < 1 || !ctxs[0]) return BS_ERR_INVALID;
+    try {
+        return score_multi_impl(ctxs, n_ctx, contig_chars, contig_off, n_contigs, read_chars, read_off, n_reads, truth, truth_len, kmer, flags, res);
+    } catch (const std::bad_alloc &) {
+        return fail(ctxs[0], BS_ERR_ALLOC, "bs_score_multi: out of host memory");
+    } catch (const std::exception &ex) {  // e.g. std::system_error from std::thread
+        return fail(ctxs[0], BS_ERR_STATE, "bs_score_multi: %s", ex.what());
+    } catch (...) {
+        return fail(ctxs[0], BS_ERR_STATE, "bs_score_multi: unknown exception");
+    }
+}
+
+static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,
+                            const char *read_chars, const int64_t *read_off, int64_t n_reads,
+                            const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *res) {
     bs_ctx *ctx = ctxs[0];
-    for (int k = 0; k < n_ctx; k++)
+    for (int k = 0; k < n_ctx; k++) {
         if (!ctxs[k]) return fail(ctx, BS_ERR_INVALID, "bs_score_multi: context %d is NULL", k);
+        for (int j = 0; j < k; j++)  // a context is single-threaded: the same one twice would be driven by two threads
+            if (ctxs[j] == ctxs[k]) return fail(ctx, BS_ERR_INVALID, "bs_score_multi: context %d is the same as context %d", k, j);
+    }
     if (flags & (BS_DEVICE_CHARS | BS_DEVICE_RESULT)) return fail(ctx, BS_ERR_INVALID, "bs_score_multi takes host buffers only");
     if (!res) return fail(ctx, BS_ERR_INVALID, "bs_score_multi: NULL result");
     if (n_contigs < 0 || n_reads < 0) return fail(ctx, BS_ERR_INVALID, "negative counts");
@@ -1608,7 +1699,7 @@ int bs_score_multi(bs_ctx *const *ctxs, int n_ctx, const char *contig_chars, con
     }
 
     // one host thread per context with work (a context is single-threaded, contexts are independent)
-    auto run = [&](int k) {
+    auto run = [&](int k) {  // (bs_score catches everything itself: nothing escapes a worker thread)
         MultiShard &m = sh[k];
         if (m.idx.empty()) return;
         m.rc = bs_score(ctxs[k], m.chars.data(), m.off.data(), (int64_t)m.idx.size(), read_chars, read_off, n_reads, truth, truth_len,
@@ -1619,8 +1710,14 @@ int bs_score_multi(bs_ctx *const *ctxs, int n_ctx, const char *contig_chars, con
 #else
     {
         std::vector<std::thread> threads;
-        for (int k = 1; k < n_ctx; k++) threads.emplace_back(run, k);
+        threads.reserve((size_t)n_ctx);
+        int started = 1;
+        try {
+            for (; started < n_ctx; started++) threads.emplace_back(run, started);
+        } catch (...) {  // could not start a thread: its share (and the rest) runs here
+        }
         run(0);
+        for (int k = started; k < n_ctx; k++) run(k);
         for (std::thread &t : threads) t.join();
     }
 #endif
@@ -1660,7 +1757,24 @@ int64_t bs_simulate_capacity(const int64_t *truth_off, int64_t n_segments, int32
     return draws * (int64_t)read_len;
 }
 
+static int bs_simulate_reads_impl(bs_ctx *ctx, const char *truth_chars, const int64_t *truth_off, int64_t n_segments, int32_t read_len,
+                      double coverage, int kmer, uint64_t seed, uint32_t flags, char *reads_out, int64_t reads_capacity,
+                      int64_t *seg_read_start);
+
 int bs_simulate_reads(bs_ctx *ctx, const char *truth_chars, const int64_t *truth_off, int64_t n_segments, int32_t read_len,
+                      double coverage, int kmer, uint64_t seed, uint32_t flags, char *reads_out, int64_t reads_capacity,
+                      int64_t *seg_read_start) {
+    if (!ctx) return BS_ERR_INVALID;
+    try {
+        return bs_simulate_reads_impl(ctx, truth_chars, truth_off, n_segments, read_len, coverage, kmer, seed, flags, reads_out, reads_capacity, seg_read_start);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, BS_ERR_ALLOC, "bs_simulate_reads: out of host memory");
+    } catch (...) {
+        return fail(ctx, BS_ERR_STATE, "bs_simulate_reads: unexpected exception");
+    }
+}
+
+static int bs_simulate_reads_impl(bs_ctx *ctx, const char *truth_chars, const int64_t *truth_off, int64_t n_segments, int32_t read_len,
                       double coverage, int kmer, uint64_t seed, uint32_t flags, char *reads_out, int64_t reads_capacity,
                       int64_t *seg_read_start) {
     if (!ctx) return BS_ERR_INVALID;

@@ -15,6 +15,8 @@
 // before the final sort.  The final order reproduces upstream's: lexicographic sort, unique, then
 // std::sort by length (the same libstdc++ algorithm on the same sequence gives the same tie order).
 #include <algorithm>
+#include <exception>
+#include <new>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -69,8 +71,28 @@ extern "C" {
 
 const char *bs_assemble_last_error(void) { return g_assemble_error; }
 
+static int assemble_impl(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer, int seed,
+                         int n_shuffles, int n_threads, bs_string_list **out);
+
+// nothing throws across the boundary (bad_alloc of the containers, system_error of std::thread)
 int bs_assemble_contigs(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer, int seed,
                         int n_shuffles, int n_threads, bs_string_list **out) {
+    try {
+        return assemble_impl(contig_chars, contig_off, n_contigs, dbg_kmer, seed, n_shuffles, n_threads, out);
+    } catch (const std::bad_alloc &) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_contigs: out of host memory");
+        return BS_ERR_ALLOC;
+    } catch (const std::exception &ex) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_contigs: %.200s", ex.what());
+        return BS_ERR_STATE;
+    } catch (...) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_contigs: unknown exception");
+        return BS_ERR_STATE;
+    }
+}
+
+static int assemble_impl(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer, int seed,
+                         int n_shuffles, int n_threads, bs_string_list **out) {
     g_assemble_error[0] = 0;
     if (!out || !contig_off || n_contigs < 0 || n_shuffles < 0 || (n_contigs > 0 && !contig_chars)) {
         std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_contigs: bad argument");
@@ -117,24 +139,40 @@ int bs_assemble_contigs(const char *contig_chars, const int64_t *contig_off, int
     std::atomic<size_t> next_perm{0};
     unsigned nt = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::thread::hardware_concurrency());
     nt = (unsigned)std::min<size_t>(nt, std::max<size_t>(perms.size(), 1));
+    std::atomic<bool> failed{false};  // an exception inside a worker (bad_alloc): reported after the join, never escapes a thread
     auto worker = [&]() {
-        std::unordered_set<std::string> local;
-        std::vector<std::string> contigs;
-        for (;;) {
-            const size_t p = next_perm.fetch_add(1);
-            if (p >= perms.size()) break;
-            contigs.clear();
-            for (int32_t id : perms[p]) contigs.push_back(input[(size_t)id]);
-            merge_permutation(contigs, dbg_kmer);
-            for (auto &s : contigs) local.insert(std::move(s));
+        try {
+            std::unordered_set<std::string> local;
+            std::vector<std::string> contigs;
+            for (;;) {
+                const size_t p = next_perm.fetch_add(1);
+                if (p >= perms.size()) break;
+                contigs.clear();
+                for (int32_t id : perms[p]) contigs.push_back(input[(size_t)id]);
+                merge_permutation(contigs, dbg_kmer);
+                for (auto &s : contigs) local.insert(std::move(s));
+            }
+            std::lock_guard<std::mutex> lock(mu);
+            for (auto &s : local) found.insert(s);
+        } catch (...) {
+            failed = true;
+            next_perm = perms.size();  // the other workers stop at their next permutation
         }
-        std::lock_guard<std::mutex> lock(mu);
-        for (auto &s : local) found.insert(s);
     };
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nt; t++) pool.emplace_back(worker);
-    worker();
-    for (auto &t : pool) t.join();
+    {
+        std::vector<std::thread> pool;
+        pool.reserve(nt);
+        try {
+            for (unsigned t = 1; t < nt; t++) pool.emplace_back(worker);
+        } catch (...) {  // fewer threads than asked for: the ones that started share the work
+        }
+        worker();
+        for (auto &t : pool) t.join();
+    }
+    if (failed) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_contigs: out of host memory in a worker");
+        return BS_ERR_ALLOC;
+    }
 
     StringList *res = new (std::nothrow) StringList();
     if (!res) return BS_ERR_ALLOC;

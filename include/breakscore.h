@@ -157,7 +157,9 @@ BS_API int bs_ctx_set_poll(bs_ctx *ctx, bs_poll_fn poll, void *user);
 BS_API double bs_ctx_last_place_ms(bs_ctx *ctx);
 
 /* scoring table: n (k-mer, probability) pairs.  Keys: ACGT strings of length 1..8; a repeated
- * key overrides the earlier row (map assignment, lib/BreakageScorer.cpp:195-197). */
+ * key overrides the earlier row (map assignment, lib/BreakageScorer.cpp:195-197).  Setting a table removes
+ * a truth-side table and a second table set earlier (both are indexed by the rows of the table they were
+ * set against): set them again afterwards. */
 BS_API int bs_set_table(bs_ctx *ctx, const char *kmer_chars, const int64_t *kmer_off, const double *prob, int64_t n);
 /* probabilities used for the truth-side distribution of the KS statistics (same keys/rows as the
  * scoring table).  prob == NULL: follow the scoring table. */

@@ -38,6 +38,28 @@ def test_random_pass_keeps_real_truth_table(emul_scorer, oracle, kmers, prob):
     P.check_segment(emul_scorer, oracle, kmers, tables.uniform(len(prob)), seg, truth_prob=prob)
 
 
+def test_set_table_drops_an_earlier_truth_table(emul_lib, oracle, kmers, prob):
+    """A truth-side table is indexed by the rows of the table it was set against: bs_set_table on its own (direct
+    C-ABI use, no bs_set_truth_table afterwards) must fall back to the new scoring table, whatever the row count."""
+    import ctypes as C
+    seg = P.make(43, 2000, 40, 8, 4, 0)
+    sc = B.BreakageScorer(0, emul_lib)
+    try:
+        sc.set_table(kmers, tables.uniform(len(prob)), truth_prob=prob)  # truth-side table set against these rows
+        perm = np.random.default_rng(5).permutation(len(kmers))           # same n, another key -> row mapping
+        k2, p2 = [kmers[i] for i in perm], prob[perm]
+        chars, off = B.flatten(k2)
+        sc._check(sc._lib.bs_set_table(sc._ctx, C.c_void_p(chars.ctypes.data), C.c_void_p(off.ctypes.data),
+                                       C.c_void_p(p2.ctypes.data), len(p2)))
+        sc.n_table = len(p2)
+        got = sc.score(seg.contigs, seg.reads, seg.truth, flags=B.DEFAULT_FLAGS)
+        want = oracle.oracle_calc_breakscore(seg.contigs, seg.read_list, seg.truth, 8, k2, p2)
+        for k in ("ks_stat_prob_dist", "ks_stat_path_freq"):
+            np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+    finally:
+        sc.close()
+
+
 def test_batch_equals_single_calls(emul_scorer, kmers, prob):
     from genomeassembler_dev_b200 import synth
     emul_scorer.set_table(kmers, prob)
@@ -128,6 +150,8 @@ def test_one_segment_over_several_contexts(emul_lib, emul_scorer, kmers, prob):
         got = emul_scorer.score(contigs, seg.reads, seg.truth, flags=flags, group=others)
         more = emul_scorer.score(contigs[:2], seg.reads, seg.truth, flags=flags, group=others)  # fewer contigs than contexts
         two = emul_scorer.score(contigs[:2], seg.reads, seg.truth, flags=flags)
+        with pytest.raises(B.BreakscoreError, match="same as context"):  # one context twice would be driven by two threads
+            emul_scorer.score(contigs, seg.reads, seg.truth, flags=flags, group=[others[0], others[0]])
         others[1].set_table(kmers[:16], np.full(16, 1 / 16))  # a context with another table is refused
         with pytest.raises(B.BreakscoreError):
             emul_scorer.score(contigs, seg.reads, seg.truth, flags=flags, group=others)
