@@ -27,6 +27,16 @@
 
 #include "../../include/breakscore.h"
 
+// NVTX ranges around the pipeline stages (header-only NVTX3: a no-op unless a tool such as nsys / ncu is attached)
+#ifndef BS_CPU_EMUL
+#include <nvtx3/nvToolsExt.h>
+#define BS_NVTX_PUSH(name) nvtxRangePushA(name)
+#define BS_NVTX_POP() nvtxRangePop()
+#else
+#define BS_NVTX_PUSH(name) ((void)0)
+#define BS_NVTX_POP() ((void)0)
+#endif
+
 namespace {
 
 char g_create_error[512] = "";
@@ -36,6 +46,7 @@ constexpr int kPlaceThreads = 64;
 constexpr int kScoreThreads = 64;
 constexpr int kBreakScoreThreads = 64;
 constexpr int kStartposThreads = 64;
+constexpr int kStartposBigThreads = 64;
 constexpr int kLevThreads = 64;
 constexpr int kSimThreads = 64;
 constexpr int kKsThreads = 64;
@@ -49,6 +60,7 @@ constexpr int kPlaceThreads = 256;
 constexpr int kScoreThreads = 256;
 constexpr int kBreakScoreThreads = bs::SCORE_THREADS;
 constexpr int kStartposThreads = 256;
+constexpr int kStartposBigThreads = 1024;  // one block per SM holds the 128 KB prefix bitmap
 constexpr int kLevThreads = 128;
 constexpr int kSimThreads = 256;
 constexpr int kKsThreads = 768;     // one sweep round covers the 515 ranges of the real table's rank histogram
@@ -85,7 +97,7 @@ struct Workspace {
     size_t h_meta_cap = 0;
     DevBuf meta, read_chars, read_off, ctg_chars, tr_chars;
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
-    DevBuf w, total, ycnt, yx, yx2, head, next, odd_head, spbest, exact, sp_key, sp_head, sp_next;
+    DevBuf w, total, ycnt, yx, yx2, head, next, odd_head, spbest, exact, sp_key, sp_head, sp_next, sp_bitmap, sp_queue;
     DevBuf out_i32, out_f64, pd, pd2, hist, pos;
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
@@ -214,6 +226,9 @@ struct StageTimer {
     cudaStream_t st;
     TimedSpan *span = nullptr;
     StageTimer(bs_ctx *c, Stage s, cudaStream_t stream) : ctx(c), st(stream) {
+        static const char *const names[ST_COUNT] = {"bs:h2d", "bs:pack", "bs:place", "bs:score", "bs:truth_spectrum", "bs:prob_dist_ks",
+                                                    "bs:ks_path_freq", "bs:startpos", "bs:d2h", "bs:lev"};
+        BS_NVTX_PUSH(names[(int)s]);
         if (!ctx->timing) return;
         if (ctx->spans_used == ctx->spans.size()) {
             TimedSpan t{(int)s, nullptr, nullptr};
@@ -226,6 +241,7 @@ struct StageTimer {
     }
     ~StageTimer() {
         if (span) cudaEventRecord(span->b, st);
+        BS_NVTX_POP();
     }
 };
 
@@ -377,6 +393,10 @@ struct ChunkRun {
     const int64_t *d_ctg_off = nullptr, *d_ctg_woff = nullptr, *d_tr_off = nullptr, *d_tr_woff = nullptr, *d_seg_rs = nullptr,
                   *d_seg_cs = nullptr, *d_tab_off = nullptr, *d_pd_off = nullptr, *d_pos_off = nullptr, *d_roff = nullptr;
     const int32_t *d_ctg_seg = nullptr, *d_seed = nullptr, *d_tab_mask = nullptr, *d_order = nullptr;
+    const int64_t *d_sp_tab_off = nullptr;    // contig-in-truth seed tables: first slot per segment
+    const int32_t *d_sp_tab_mask = nullptr;   // ... and slots - 1 (one table per segment geometry)
+    bool sp_big = false;
+    int64_t sp_slots = 0, sp_bitmap_words = 0;
     const int32_t *d_order_small = nullptr, *d_order_large = nullptr;  // work order split at KS_SMALL_MAX windows
     int64_t n_small = 0, n_large = 0;
     const bs::PlaceItem *d_items = nullptr;
@@ -459,6 +479,34 @@ int ChunkRun::prepare() {
         tab_off[s] = head_total;
         tab_mask[s] = (int32_t)(hs - 1);
         head_total += hs;
+    }
+    // contig-in-truth seed tables (bs_startpos.cuh): groups of SP_GROUP contigs with fixed-size tables, or -- when a
+    // segment holds more contigs than one group (cfg-4 / cfg-5) -- ONE table per segment sized for its contigs
+    std::vector<int64_t> sp_tab_off(std::max<int64_t>(S, 1), 0);
+    std::vector<int32_t> sp_tab_mask(std::max<int64_t>(S, 1), bs::SP_SLOTS - 1);
+    {
+        int64_t max_seg_contigs = 0;
+        for (int64_t s = 0; s < S; s++) max_seg_contigs = std::max(max_seg_contigs, seg_cs[s + 1] - seg_cs[s]);
+        sp_big = max_seg_contigs > bs::SP_GROUP;
+        if (const char *env = std::getenv("BS_STARTPOS_BIG")) sp_big = env[0] == '1';  // tests: force a geometry
+        int64_t slots = 0, groups = 0;
+        for (int64_t s = 0; s < S; s++) {
+            const int64_t nc = seg_cs[s + 1] - seg_cs[s];
+            sp_tab_off[s] = slots;
+            if (sp_big) {
+                int64_t sl = 64;
+                while (sl < 2 * nc) sl <<= 1;
+                sp_tab_mask[s] = (int32_t)(sl - 1);
+                slots += sl + 1;
+                groups += 1;
+            } else {
+                const int64_t g = std::max<int64_t>(1, bs::startpos_groups_of(nc));
+                slots += g * (bs::SP_SLOTS + 1);
+                groups += g;
+            }
+        }
+        sp_slots = slots;
+        sp_bitmap_words = sp_big ? S * (int64_t)bs::SP_BITMAP_WORDS_BIG : groups * (int64_t)bs::SP_BITMAP_WORDS;
     }
     if (max_read > 0x3fffffff) return fail(ctx, BS_ERR_INVALID, "read longer than 2^30");
     W = (int)std::max<int64_t>(1, (max_read + 31) / 32);
@@ -545,6 +593,8 @@ int ChunkRun::prepare() {
     const size_t o_seed = mb.add(seed_len.data(), (size_t)S);
     const size_t o_tab_off = mb.add(tab_off.data(), (size_t)S);
     const size_t o_tab_mask = mb.add(tab_mask.data(), (size_t)S);
+    const size_t o_sp_tab_off = mb.add(sp_tab_off.data(), (size_t)S);
+    const size_t o_sp_tab_mask = mb.add(sp_tab_mask.data(), (size_t)S);
     const size_t o_order = mb.add(order.data(), order.size());
     const size_t o_order_small = mb.add(order_small.data(), order_small.size());
     const size_t o_order_large = mb.add(order_large.data(), order_large.size());
@@ -608,6 +658,8 @@ int ChunkRun::prepare() {
     d_seed = (const int32_t *)(dm + o_seed);
     d_tab_off = (const int64_t *)(dm + o_tab_off);
     d_tab_mask = (const int32_t *)(dm + o_tab_mask);
+    d_sp_tab_off = (const int64_t *)(dm + o_sp_tab_off);
+    d_sp_tab_mask = (const int32_t *)(dm + o_sp_tab_mask);
     d_order = (const int32_t *)(dm + o_order);
     d_order_small = (const int32_t *)(dm + o_order_small);
     d_order_large = (const int32_t *)(dm + o_order_large);
@@ -994,25 +1046,43 @@ int ChunkRun::startpos() {
         sa.tr_chars = d_tchars; sa.total = (const int32_t *)ws.total.p; sa.n_contigs = C; sa.n_seg = (int32_t)S;
         sa.best = (uint32_t *)ws.spbest.p; sa.startpos = o_startpos;
         sa.exact = e.want_lev ? (int32_t *)ws.exact.p : nullptr; sa.search_all = e.want_lev ? 1 : 0;
-        // enough blocks to fill the machine even for a single segment and to keep the last wave short; at least 2048 positions each
-        int64_t splits = ((int64_t)ctx->sm_count * 16 + S - 1) / std::max<int64_t>(S, 1);
-        splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 2047) / 2048));
-        sa.splits = (int32_t)splits;
-        // seed tables of the contig groups, built in their own kernel
-        const size_t tab_slots = (size_t)bs::startpos_group_count(C, S) * (bs::SP_SLOTS + 1);
-        BS_TRY(ensure(ctx, ws.sp_key, tab_slots * 8));
-        BS_TRY(ensure(ctx, ws.sp_head, tab_slots * 4));
+        // seed tables + prefix bitmaps of the contig groups, built in their own kernel
+        sa.seg_tab_off = d_sp_tab_off; sa.seg_tab_mask = d_sp_tab_mask; sa.big = sp_big ? 1 : 0;
+        BS_TRY(ensure(ctx, ws.sp_key, (size_t)sp_slots * 8));
+        BS_TRY(ensure(ctx, ws.sp_head, (size_t)sp_slots * 4));
         BS_TRY(ensure(ctx, ws.sp_next, (size_t)C * 4));
-        BS_CUDA(cudaMemsetAsync(ws.sp_key.p, 0xff, tab_slots * 8, st));
-        BS_CUDA(cudaMemsetAsync(ws.sp_head.p, 0, tab_slots * 4, st));
+        BS_TRY(ensure(ctx, ws.sp_bitmap, (size_t)sp_bitmap_words * 4));
+        int64_t q_cap = std::max<int64_t>(4 * C, 1 << 16);
+        if (const char *env = std::getenv("BS_STARTPOS_QCAP")) q_cap = std::max<int64_t>(1, std::atoll(env));  // tests: a tiny queue reaches the in-scan fallback
+        BS_TRY(ensure(ctx, ws.sp_queue, (size_t)q_cap * 8));
+        BS_CUDA(cudaMemsetAsync(ws.sp_key.p, 0xff, (size_t)sp_slots * 8, st));
+        BS_CUDA(cudaMemsetAsync(ws.sp_head.p, 0, (size_t)sp_slots * 4, st));
+        BS_CUDA(cudaMemsetAsync(ws.sp_bitmap.p, 0, (size_t)sp_bitmap_words * 4, st));
         sa.tab_key = (unsigned long long *)ws.sp_key.p; sa.tab_head = (int32_t *)ws.sp_head.p; sa.tab_next = (int32_t *)ws.sp_next.p;
+        sa.bitmap = (uint32_t *)ws.sp_bitmap.p;
+        sa.queue = (uint2 *)ws.sp_queue.p; sa.q_count = (int32_t *)ctx->d_counters.p + 8; sa.q_cap = (int32_t)std::min<int64_t>(q_cap, 0x7fffffff);
         BS_LAUNCH(bs::k_startpos_build, grid_for(C, kStartposThreads, grid_cap), kStartposThreads, 0, st, sa);
         ctx->launches++;
-        // BS_STARTPOS_BITMAP=1: prefix-bitmap filter in front of the seed table (fewer instructions per truth position;
-        // same results, CPU-emulation tested, not yet measured on the GPU -- off by default until it is)
-        const char *bm_env = std::getenv("BS_STARTPOS_BITMAP");
-        if (bm_env && bm_env[0] == '1') BS_LAUNCH(bs::k_startpos_index<true>, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
-        else BS_LAUNCH(bs::k_startpos_index<false>, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
+        // the truth streams past the bitmaps: enough blocks to fill the machine even for a single segment and to keep
+        // the last wave short, at least 2048 positions each (BIG: one fat block per SM and a few waves, every block
+        // copies 128 KB of bitmap first)
+        if (!sp_big) {
+            int64_t splits = ((int64_t)ctx->sm_count * 16 + S - 1) / std::max<int64_t>(S, 1);
+            splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 2047) / 2048));
+            sa.splits = (int32_t)splits;
+            BS_LAUNCH(bs::k_startpos_scan<false>, (unsigned)(S * splits), kStartposThreads, 0, st, sa);
+        } else {
+            int64_t splits = ((int64_t)ctx->sm_count * 4 + S - 1) / std::max<int64_t>(S, 1);
+            splits = std::max<int64_t>(1, std::min<int64_t>(splits, (max_tr + 65535) / 65536));
+            sa.splits = (int32_t)splits;
+            const size_t bm_smem = (size_t)bs::SP_BITMAP_WORDS_BIG * 4;
+            BS_CUDA(cudaFuncSetAttribute(bs::k_startpos_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+            BS_LAUNCH(bs::k_startpos_scan<true>, (unsigned)(S * splits), kStartposBigThreads, bm_smem, st, sa);
+        }
+        ctx->launches++;
+        // queued (contig, position) candidates: one warp each
+        BS_LAUNCH(bs::k_startpos_verify, (unsigned)std::min<int64_t>((q_cap * 32 + kStartposThreads - 1) / kStartposThreads, (int64_t)ctx->sm_count * 8),
+                  kStartposThreads, 0, st, sa);
         ctx->launches++;
         BS_LAUNCH(bs::k_startpos, (unsigned)std::min<int64_t>(C, grid_cap), kStartposThreads, 0, st, sa);
         ctx->launches++;
@@ -1110,7 +1180,13 @@ struct HostTrace {
     }
 };
 
+struct NvtxScope {
+    explicit NvtxScope(const char *name) { BS_NVTX_PUSH(name); }
+    ~NvtxScope() { BS_NVTX_POP(); }
+};
+
 int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
+    NvtxScope range("bs:chunk");
     ChunkRun r(ctx, ws, e, ch);
     HostTrace tr;
     BS_TRY(r.prepare());
@@ -1195,7 +1271,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     for (DevBuf *b : bufs) release(*b);
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
-                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.yx2, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact, &w.sp_key, &w.sp_head, &w.sp_next,
+                        &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.yx2, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact, &w.sp_key, &w.sp_head, &w.sp_next, &w.sp_bitmap, &w.sp_queue,
                         &w.out_i32, &w.out_f64, &w.pd, &w.pd2, &w.hist, &w.pos};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);

@@ -138,6 +138,8 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     if (bs_emul::t_lane == 0) w->ballot[ph].store(0);
     return r;
 }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 template <class T>
 inline T bs_emul_shfl(T v, unsigned src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");

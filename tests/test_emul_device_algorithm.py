@@ -439,15 +439,24 @@ def test_startpos_many_contigs(emul_scorer, oracle, kmers, prob):
     check_startpos_many_contigs(emul_scorer, oracle, kmers, prob)
 
 
-def test_startpos_prefix_bitmap_variant(emul_scorer, oracle, kmers, prob, monkeypatch):
-    """BS_STARTPOS_BITMAP=1 (k_startpos_index<true>: 8-base prefix bitmap in front of the seed table; off by default
-    until it has been timed on the GPU): same offsets on the many-contig case, the edge inputs and a mutated segment."""
-    monkeypatch.setenv("BS_STARTPOS_BITMAP", "1")
-    check_startpos_many_contigs(emul_scorer, oracle, kmers, prob)
-    emul_scorer.set_table(kmers, prob)
-    for name, contigs, reads, truth, kmer in P.edge_inputs():
-        got = emul_scorer.score(contigs, reads, truth, kmer=kmer, flags=B.WANT_STARTPOS | B.WANT_LEV)
-        want = oracle.oracle_calc_breakscore(contigs, reads, truth, kmer, kmers, prob, want_ks=False, want_lev=True, want_prob_dist=False)
-        assert np.array_equal(got["path_prob_dist_startpos"], want["path_prob_dist_startpos"]), name
-        assert np.array_equal(got["lev_dist_vs_true"], want["lev_dist_vs_true"]), name
-    P.check_segment(emul_scorer, oracle, kmers, prob, P.make(*P.SMALL[0], mut=0.5))
+def check_startpos_geometries(scorer, oracle, kmers, prob, monkeypatch, **kw):
+    """Both seed-table geometries of the contig-in-truth search on the same inputs (BS_STARTPOS_BIG forces one:
+    groups of 1024 contigs with the table in shared memory / one table per segment in global memory behind a 10-base
+    prefix bitmap), and a candidate queue of 5 entries (every further candidate is verified inside the scan)."""
+    for env in ({"BS_STARTPOS_BIG": "0"}, {"BS_STARTPOS_BIG": "1"}, {"BS_STARTPOS_QCAP": "5"}, {"BS_STARTPOS_BIG": "0", "BS_STARTPOS_QCAP": "5"}):
+        for k in ("BS_STARTPOS_BIG", "BS_STARTPOS_QCAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        check_startpos_many_contigs(scorer, oracle, kmers, prob, **kw)
+        scorer.set_table(kmers, prob)
+        for name, contigs, reads, truth, kmer in P.edge_inputs():
+            got = scorer.score(contigs, reads, truth, kmer=kmer, flags=B.WANT_STARTPOS | B.WANT_LEV)
+            want = oracle.oracle_calc_breakscore(contigs, reads, truth, kmer, kmers, prob, want_ks=False, want_lev=True, want_prob_dist=False)
+            assert np.array_equal(got["path_prob_dist_startpos"], want["path_prob_dist_startpos"]), (env, name)
+            assert np.array_equal(got["lev_dist_vs_true"], want["lev_dist_vs_true"]), (env, name)
+        P.check_segment(scorer, oracle, kmers, prob, P.make(*P.SMALL[0], mut=0.5))
+
+
+def test_startpos_table_geometries(emul_scorer, oracle, kmers, prob, monkeypatch):
+    check_startpos_geometries(emul_scorer, oracle, kmers, prob, monkeypatch)

@@ -297,6 +297,11 @@ def test_startpos_many_contigs(gpu_scorer, oracle, kmers, prob):
         check_startpos_many_contigs(gpu_scorer, oracle, kmers, prob, n_contigs=6000, L=200000)
 
 
+def test_startpos_table_geometries(gpu_scorer, oracle, kmers, prob, monkeypatch):
+    from test_emul_device_algorithm import check_startpos_geometries
+    check_startpos_geometries(gpu_scorer, oracle, kmers, prob, monkeypatch, n_contigs=6000, L=200000)
+
+
 # ---- infix edit distance (lev_dist_vs_true) ---------------------------------------------------
 
 @pytest.mark.parametrize("params", P.SMALL + P.MEDIUM[:2], ids=[f"L{p[1]}_r{p[2]}" for p in P.SMALL + P.MEDIUM[:2]])

@@ -41,12 +41,12 @@ for ctgs in (list(seg.contigs)+[b'',seg.contigs[0][:3]], [seg.contigs[0]], [b'',
 sc.score(list(seg.contigs), [], seg.truth, flags=fl, group=others); n+=1   # no reads at all
 for o in others: o.close()
 # prefix-bitmap scan of the contig-in-truth search; interrupt poll between chunks
-os.environ['BS_STARTPOS_BITMAP']='1'
+os.environ['BS_STARTPOS_BIG']='1'
 for params in P.SMALL[:3]:
     P.check_segment(sc,O,kmers,prob,P.make(*params,mut=0.5),flags=P.FULL|B.WANT_LEV); n+=1
 for name,contigs,reads,truth,kmer in P.edge_inputs():
     P.check_segment(sc,O,kmers,prob,synth.Segment(truth,None,contigs),kmer=kmer,reads=reads,flags=P.FULL|B.WANT_LEV); n+=1
-del os.environ['BS_STARTPOS_BITMAP']
+del os.environ['BS_STARTPOS_BIG']
 os.environ['BS_CHUNK_KB']='12'
 with B.BreakageScorer(0,'/tmp/asan/libbreakscore_emul.so') as sc2:
     sc2.set_table(kmers,prob); calls=[]

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 evidence in one gpurun call (run ON the GPU box from the repo root):
 #   gpurun --timeout 1500 -- 'bash tools/gpu_round2.sh r02a'
-# GPU suite (default and BS_STARTPOS_BITMAP=1), bench line (both), launch list, one --set full capture of EVERY kernel
+# GPU suite, bench line, launch list, one --set full capture of EVERY kernel
 # of one device-resident 1000-segment step.
 set -u
 tag=${1:-r02x}
@@ -10,10 +10,6 @@ mkdir -p $out
 timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "rc=$?" >> $out/${tag}_pytest.log
 timeout 300 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench.err
 echo "bench rc=$?" >> $out/${tag}_bench.err
-if [ "${SKIP_BITMAP:-0}" != "1" ]; then
-BS_STARTPOS_BITMAP=1 timeout 600 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_bitmap.log 2>&1; echo "rc=$?" >> $out/${tag}_pytest_bitmap.log
-BS_STARTPOS_BITMAP=1 timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-study --scan-segments 0 > $out/${tag}_bench_bitmap.json 2>> $out/${tag}_bench.err
-fi
 if [ -n "${EXTRA_CMD:-}" ]; then bash -c "$EXTRA_CMD" > $out/${tag}_extra.log 2>&1; echo "rc=$?" >> $out/${tag}_extra.log; fi
 timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-study --scan-segments 0 --device-only > $out/${tag}_plain.log 2>&1 &&
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
