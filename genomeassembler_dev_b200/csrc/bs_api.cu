@@ -765,7 +765,16 @@ int ChunkRun::pack() {
                 BS_CUDA(cudaMemsetAsync(ws.head.p, 0, (size_t)head_total * 4, st));
                 BS_CUDA(cudaMemsetAsync(ws.odd_head.p, 0, (size_t)S * 4, st));
             }
-            if (!e.roff && e.rlen >= 1) {
+            const int tile_reads = (!e.roff && e.rlen >= 1) ? bs::packb_tile_reads(e.rlen) : 0;
+            const char *bulk_env = std::getenv("BS_PACK_BULK");  // tests: 0 keeps the register-staged kernel
+            if (tile_reads > 0 && bs::packb_stage_bytes(e.rlen, tile_reads) <= bs::PACKB_MAX_STAGE && !(bulk_env && bulk_env[0] == '0')) {
+                // reads of one length: ASCII staged by bulk asynchronous copies (TMA unit), two stages per block
+                const size_t smem = bs::packb_smem_bytes(e.rlen, tile_reads);
+                BS_CUDA(cudaFuncSetAttribute(bs::k_pack_reads_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const int64_t tiles = (N + tile_reads - 1) / tile_reads;
+                const int per_sm = blocks_per_sm(bs::k_pack_reads_bulk, bs::PACKB_THREADS, smem);
+                BS_LAUNCH(bs::k_pack_reads_bulk, (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * per_sm), bs::PACKB_THREADS, smem, st, rs, ix, tile_reads);
+            } else if (!e.roff && e.rlen >= 1) {
                 BS_CUDA(cudaMemsetAsync(ws.rflags.p, 0, (size_t)N + 8, st));
                 const int64_t tiles = (N * W + bs::PACK_THREADS - 1) / bs::PACK_THREADS;
                 BS_LAUNCH(bs::k_pack_reads_uniform, (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_pack_reads_uniform, bs::PACK_THREADS, 0)), bs::PACK_THREADS, 0, st, rs, ix);

@@ -335,4 +335,242 @@ __global__ void __launch_bounds__(PACK_THREADS, 5) k_pack_reads_uniform(ReadSet 
     }
 }
 
+// ---- the same packing with the ASCII staged by bulk asynchronous copies (sm_90+/sm_100 TMA unit) ------------
+// A block owns a contiguous run of TILES of R whole reads (R * L is a multiple of 16, so every tile starts at
+// the same 16-byte phase `mis` of the buffer).  One thread arms an mbarrier with the tile's byte count and issues
+// ONE cp.async.bulk (global -> shared, SASS UBLKCP) per tile; two stages, so the copy of tile t+1 is in flight
+// while tile t is converted: no load instruction, address arithmetic or register of the SIMD path is spent on the
+// input stream.  Phase A turns 16-byte cells into 32 bits of 2-bit codes + a validity word in shared memory
+// (LDS.128 -> pack16), phase B cuts every output word out of two or three cells with funnel shifts, writes it
+// coalesced, ORs the per-read flag in shared memory (written once per read, no global atomic, no memset) and
+// inserts the read into its segment's index.  The index insertion's atomicExch result is consumed one tile
+// later (the old kernel stalled on it: 54 % of its stall samples, profiles/r02a).  Code / flag buffers are
+// double buffered as well: one block barrier per tile.
+// Cells that are not completely inside the read buffer (the first cell of the buffer when it is not 16-byte
+// aligned, the last one when the buffer does not end on a cell boundary) are never touched by the bulk copy:
+// phase A reads their existing bytes one by one.
+
+#ifndef BS_CPU_EMUL
+__device__ __forceinline__ uint32_t bs_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bs_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bs_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bs_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bs_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(bs_smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BS_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BS_MBAR_DONE;\n"
+        "bra BS_MBAR_WAIT;\n"
+        "BS_MBAR_DONE:\n"
+        "}\n" ::"r"(bs_smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+#else  // CPU emulation (tests): the issuing thread copies at once; the block barrier of the tile loop orders it before its readers
+inline void mbar_init(uint64_t *, uint32_t) {}
+inline void mbar_init_fence() {}
+inline void mbar_arrive_expect_tx(uint64_t *, uint32_t) {}
+inline void mbar_arrive(uint64_t *) {}
+inline void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *) { std::memcpy(dst, src, bytes); }
+inline void mbar_wait(uint64_t *, uint32_t) {}
+#endif
+
+constexpr int PACKB_THREADS = 256;
+constexpr int PACKB_TILE_BYTES = 14 * 1024;  // target ASCII bytes per tile
+constexpr int PACKB_MAX_STAGE = 24 * 1024;   // longest reads the staged kernel takes: 16 of them must fit a stage
+
+// reads per tile for reads of L bytes: a multiple of 4 (flag words) whose byte count is a multiple of 16
+BS_HD int packb_tile_reads(int L) {
+    int g = L & 15;  // gcd(L, 16)
+    g = g == 0 ? 16 : (g & -g);
+    int q = 16 / g;
+    if (q < 4) q = 4;
+    int R = (PACKB_TILE_BYTES / L) / q * q;
+    return R < q ? q : R;
+}
+BS_HD int packb_stage_bytes(int L, int R) { return ((R * L + 15 + 16) / 16 * 16 + 127) / 128 * 128; }
+BS_HD size_t packb_smem_bytes(int L, int R) {
+    const size_t cells = (size_t)packb_stage_bytes(L, R) / 16;
+    return 2 * (size_t)packb_stage_bytes(L, R) + 2 * cells * 8 + 2 * ((size_t)R / 4 + 1) * 4 + 64;
+}
+
+__global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r, ReadIndex ix, int R) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int L = r.uniform_len;
+    const uint32_t W = (uint32_t)r.W;
+    const int SB = packb_stage_bytes(L, R);
+    const int cells_max = SB / 16;
+    const int flag_words = R / 4 + 1;
+    unsigned char *sm = bs_dyn_smem();
+    unsigned char *s_stage = sm;                          sm += 2 * (size_t)SB;
+    uint32_t *s_code = (uint32_t *)sm;                    sm += 2 * (size_t)cells_max * 4;
+    uint32_t *s_bad = (uint32_t *)sm;                     sm += 2 * (size_t)cells_max * 4;
+    uint32_t *s_flagw = (uint32_t *)sm;                   sm += 2 * (size_t)flag_words * 4;
+    uint64_t *s_bar = (uint64_t *)(((uintptr_t)sm + 7) & ~(uintptr_t)7);  // two mbarriers
+    __shared__ int s_tileseg[2];  // segment of the first read of the tile in each stage
+
+    const int64_t N = r.n;
+    const int64_t total_bytes = N * (int64_t)L;
+    const int mis = (int)((uintptr_t)r.chars & 15);
+    const int64_t tiles_total = (N + R - 1) / R;
+    const int64_t per_block = (tiles_total + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * per_block;
+    const int64_t t1 = t0 + per_block < tiles_total ? t0 + per_block : tiles_total;
+    if (t0 >= t1) return;
+    const uint32_t w_magic = W > 1 ? (uint32_t)((0x100000000ull + W - 1) / W) : 0u;  // x / W for x * W < 2^32
+    auto div_w = [&](uint32_t x) { return W > 1 ? __umulhi(x, w_magic) : x; };
+
+    // cells [c_lo, c_hi) of tile t are completely inside the buffer: the bulk copy's share
+    auto tile_geom = [&](int64_t t, int &nr, int &ncell, int &c_lo, int &c_hi) {
+        const int64_t n0 = t * R;
+        nr = (int)(N - n0 < R ? N - n0 : R);
+        ncell = (mis + nr * L + 15) >> 4;
+        const int64_t g0 = n0 * L - mis;  // buffer offset of the tile's cell 0 (may be < 0 for tile 0)
+        c_lo = g0 < 0 ? 1 : 0;
+        c_hi = ncell;
+        if (g0 + 16 * (int64_t)ncell > total_bytes) c_hi = ncell - 1;
+        if (c_hi < c_lo) c_hi = c_lo;
+    };
+    auto issue = [&](int64_t t) {  // thread 0 only
+        int nr, ncell, c_lo, c_hi;
+        tile_geom(t, nr, ncell, c_lo, c_hi);
+        const int st = (int)((t - t0) & 1);
+        const uint32_t bytes = 16u * (uint32_t)(c_hi - c_lo);
+        if (bytes) {
+            mbar_arrive_expect_tx(&s_bar[st], bytes);
+            bulk_copy_g2s(s_stage + (size_t)st * SB + 16 * c_lo, r.chars + (t * R * (int64_t)L - mis + 16 * c_lo), bytes, &s_bar[st]);
+        } else {
+            mbar_arrive(&s_bar[st]);
+        }
+    };
+
+    int seg = 0;  // thread 0: segment of the current tile's first read, advanced tile by tile
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init_fence();
+        issue(t0);
+        if (t0 + 1 < t1) issue(t0 + 1);
+        if (ix.head) seg = segment_of_read(ix, t0 * R);
+    }
+    for (int i = tid; i < 2 * flag_words; i += nthr) s_flagw[i] = 0;
+    __syncthreads();
+
+    // index insertion in flight: the bucket's previous head comes back from the atomic one tile later
+    uint32_t pend_n = 0xffffffffu, pend_old = 0, pend_tag = 0;
+    for (int64_t t = t0; t < t1; t++) {
+        const int st = (int)((t - t0) & 1);
+        const uint32_t parity = (uint32_t)(((t - t0) >> 1) & 1);
+        int nr, ncell, c_lo, c_hi;
+        tile_geom(t, nr, ncell, c_lo, c_hi);
+        const int64_t n0 = t * R;
+        const unsigned char *stage = s_stage + (size_t)st * SB;
+        uint32_t *code = s_code + (size_t)st * cells_max, *bad = s_bad + (size_t)st * cells_max;
+        uint32_t *flagw = s_flagw + (size_t)st * flag_words;
+        mbar_wait(&s_bar[st], parity);
+        // ---- phase A: 16-byte cells -> 2-bit codes + validity ----
+        for (int ci = tid; ci < ncell; ci += nthr) {
+            uint4 v;
+            if (ci >= c_lo && ci < c_hi) {
+                v = *reinterpret_cast<const uint4 *>(stage + 16 * ci);
+            } else {  // a cell that sticks out of the buffer: its existing bytes one by one, 'A' for the rest
+                uint32_t xs[4];
+                const int64_t cb = n0 * L - mis + 16 * (int64_t)ci;
+                for (int q = 0; q < 4; q++) {
+                    uint32_t x = 0;
+                    for (int b = 3; b >= 0; b--) {
+                        const int64_t pb = cb + 4 * q + b;
+                        x = (x << 8) | ((pb >= 0 && pb < total_bytes) ? (uint32_t)r.chars[pb] : (uint32_t)'A');
+                    }
+                    xs[q] = x;
+                }
+                v = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+            }
+            uint32_t diff = 0;
+            code[ci] = pack16(v.x, v.y, v.z, v.w, diff);
+            bad[ci] = diff;
+        }
+        if (tid == 0 && ix.head) {
+            while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
+            s_tileseg[st] = seg;
+        }
+        __syncthreads();  // codes of tile t complete; stage st and everything of tile t-1 are free
+        if (tid == 0 && t + 2 < t1) issue(t + 2);
+        if (t > t0) {  // flags of tile t-1: one word per thread, written once, and the buffer zeroed for tile t+1
+            uint32_t *prev = s_flagw + (size_t)(st ^ 1) * flag_words;
+            const int pnr = R;  // (tile t-1 is never the last one: it is full)
+            if (tid < (pnr + 3) / 4) {
+                reinterpret_cast<uint32_t *>(r.flags)[(n0 - R) / 4 + tid] = prev[tid];
+                prev[tid] = 0;
+            }
+        }
+        // ---- phase B: output words ----
+        const uint32_t nwords = (uint32_t)nr * W;
+        uint64_t *wout = r.words + n0 * (int64_t)W;
+        const int tseg = ix.head ? s_tileseg[st] : 0;
+        for (uint32_t k = tid; k < nwords; k += nthr) {
+            const uint32_t nl = div_w(k);
+            const int j = (int)(k - nl * W);
+            const int a = mis + (int)nl * L + 32 * j;  // byte offset inside the staged span
+            const int ci = a >> 4;
+            const uint32_t sh = 2u * (uint32_t)(a & 15);
+            const int rem = L - 32 * j;  // bases of this word that belong to the read (may exceed 32)
+            // cells past the staged span are only touched by bases beyond the read: clamp the index
+            const int i1 = ci + 1 < ncell ? ci + 1 : ncell - 1, i2 = ci + 2 < ncell ? ci + 2 : ncell - 1;
+            const uint32_t w0 = code[ci], w1 = code[i1], w2 = code[i2];
+            const uint32_t o_hi = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
+            const uint32_t o_lo = sh ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;
+            const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(rem);
+            wout[k] = word;
+            // cells overlapping this word's own bytes [a, a + min(rem, 32)); a cell holding any byte outside ACGT
+            // flags every read that overlaps it (conservative: flagged reads are verified on the text, still exact)
+            const int last_cell = (a + (rem < 32 ? rem : 32) - 1) >> 4;
+            uint32_t b = bad[ci];
+            if (last_cell >= ci + 1) b |= bad[i1];
+            if (last_cell >= ci + 2) b |= bad[i2];
+            if (b) atomicOr(&flagw[nl >> 2], 1u << (8 * (int)(nl & 3)));
+            if (j == 0 && ix.head) {
+                if (pend_n != 0xffffffffu) ix.next[pend_n] = make_uint2(pend_old, pend_tag);
+                const uint32_t n = (uint32_t)n0 + nl;
+                int sg = tseg;
+                while (sg + 1 < ix.n_seg && (int64_t)n >= ix.seg_read_start[sg + 1]) sg++;
+                if (!b) {
+                    const uint64_t seed = word & keep_bases(ix.seed_len[sg]);
+                    const uint32_t h = seed_hash(seed) & (uint32_t)ix.tab_mask[sg];
+                    pend_old = atomicExch(&ix.head[ix.tab_off[sg] + h], n + 1u);
+                    pend_tag = seed_tag(seed);
+                } else {
+                    pend_old = atomicExch(&ix.odd_head[sg], n + 1u);
+                    pend_tag = 0u;
+                }
+                pend_n = n;
+            }
+        }
+    }
+    if (pend_n != 0xffffffffu) ix.next[pend_n] = make_uint2(pend_old, pend_tag);
+    __syncthreads();
+    {  // flags of the block's last tile
+        const int64_t t = t1 - 1;
+        const int st = (int)((t - t0) & 1);
+        const int64_t n0 = t * R;
+        const int nr = (int)(N - n0 < R ? N - n0 : R);
+        const uint32_t *flagw = s_flagw + (size_t)st * flag_words;
+        if (tid < (nr + 3) / 4) reinterpret_cast<uint32_t *>(r.flags)[n0 / 4 + tid] = flagw[tid];
+    }
+}
+
 }  // namespace bs

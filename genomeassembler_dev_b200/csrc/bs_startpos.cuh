@@ -147,11 +147,10 @@ __device__ __forceinline__ int startpos_probe(const unsigned long long *key, con
 }
 
 // does contig c occur at truth position q?  One thread, packed words (the scan's fallback when the queue is full).
-__device__ BS_NOINLINE bool startpos_verify_one(const StartposArgs &a, int64_t c, int64_t q, const uint64_t *tw, const uint32_t *tm,
-                                                const uint8_t *tc) {
-    const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
-    const uint64_t *cw = a.ctg_words + a.ctg_woff[c];
-    const uint32_t *cm = a.ctg_mask + a.ctg_woff[c];
+// (plain pointers, not the argument struct: a reference to kernel parameters in a non-inlined call would make every
+// thread copy the struct to its stack)
+__device__ BS_NOINLINE bool startpos_verify_one(const uint64_t *cw, const uint32_t *cm, const uint8_t *cc, int64_t L, int64_t q,
+                                                const uint64_t *tw, const uint32_t *tm, const uint8_t *tc) {
     const int64_t idx = q >> 5, nw = (L + 31) >> 5;
     const uint32_t o = (uint32_t)(q & 31);
     bool any_invalid = false;
@@ -165,7 +164,6 @@ __device__ BS_NOINLINE bool startpos_verify_one(const StartposArgs &a, int64_t c
         any_invalid |= (mj & keep_bits(rem)) != 0;
     }
     if (any_invalid) {
-        const uint8_t *cc = a.ctg_chars + a.ctg_off[c];
         for (int64_t i = 0; i < L; i++)
             if (tc[q + i] != cc[i]) return false;
     }
@@ -181,7 +179,8 @@ __device__ __forceinline__ void startpos_enqueue(const StartposArgs &a, int ci_h
         if (q + L > LT) continue;
         const int slot = atomicAdd(a.q_count, 1);
         if (slot < a.q_cap) a.queue[slot] = make_uint2((uint32_t)c, (uint32_t)q);
-        else if (startpos_verify_one(a, c, q, tw, tm, tc)) atomicMin(&a.best[c], (uint32_t)q);  // queue full: verify here
+        else if (startpos_verify_one(a.ctg_words + a.ctg_woff[c], a.ctg_mask + a.ctg_woff[c], a.ctg_chars + a.ctg_off[c], L, q, tw, tm, tc))
+            atomicMin(&a.best[c], (uint32_t)q);  // queue full: verify here
     }
 }
 

@@ -314,6 +314,61 @@ def test_uniform_read_lengths(emul_scorer, oracle, kmers, prob):
     check_uniform_read_lengths(emul_scorer, oracle, kmers, prob, UNIFORM_LENGTHS)
 
 
+def check_pack_variants(scorer, kmers, prob, monkeypatch, lengths, to_dev=None, n_reads=(1, 3, 257, 1111)):
+    """Reads of one length through both packing kernels (bulk-copy staged: default; register staged: BS_PACK_BULK=0)
+    from read buffers that start at every 16-byte phase (BS_DEVICE_CHARS: the library packs straight out of the
+    caller's buffer) and end anywhere, with bytes outside ACGT inside, at the ends and next to tile boundaries:
+    positions, flags-dependent placements and break counts identical to the aligned host-buffer call."""
+    import ctypes as C
+    from genomeassembler_dev_b200 import synth
+    rng = np.random.default_rng(77)
+    scorer.set_table(kmers, prob)
+    for L in lengths:
+        for N in n_reads:
+            Lt = max(4 * L, 600)
+            truth = synth.codes_to_ascii(synth.random_truth_codes(rng, Lt))
+            starts = rng.integers(0, Lt - L + 1, size=N)
+            reads = truth[starts[:, None] + np.arange(L)[None, :]].copy()
+            for i in rng.integers(0, N, size=max(1, N // 40)):  # a few reads with a byte outside ACGT (first, last, middle)
+                reads[i, int(rng.choice([0, L - 1, L // 2]))] = ord("N")
+            tr = truth.copy()
+            tr[rng.integers(0, Lt, size=3)] = ord("N")
+            contigs = [tr[:Lt // 2].tobytes(), tr[Lt // 3:].tobytes(), tr.tobytes()]
+            ct, ct_off = B.flatten(contigs)
+            trc, tr_off = B.flatten([tr.tobytes()])
+            flags = B.WANT_POS | B.WANT_STARTPOS
+            want = scorer.score_batch(reads.reshape(-1), None, L, ct, ct_off, trc, tr_off, [0, N], [0, 3], flags=flags)
+            for phase in (0, 1, 7, 15):
+                for bulk in ("1", "0"):
+                    monkeypatch.setenv("BS_PACK_BULK", bulk)
+                    buf = np.full(phase + N * L, ord("T"), np.uint8)  # exact size: nothing behind the last read
+                    buf[phase:] = reads.reshape(-1)
+                    keep = [buf, ct, trc]
+                    if to_dev is not None:
+                        dbuf, dct, dtr = to_dev(buf), to_dev(ct), to_dev(trc)
+                        keep += [dbuf, dct, dtr]
+                        rp, cp, tp = dbuf.data_ptr() + phase, dct.data_ptr(), dtr.data_ptr()
+                    else:
+                        rp, cp, tp = buf.ctypes.data + phase, ct.ctypes.data, trc.ctypes.data
+                    srs, scs = np.array([0, N], np.int64), np.array([0, 3], np.int64)
+                    bt = B._Batch(1, N, 3, rp, None, L, cp, ct_off.ctypes.data, tp, tr_off.ctypes.data, srs.ctypes.data, scs.ctypes.data)
+                    out_i = np.zeros((3, 3), np.int32)
+                    pos = np.zeros(3 * N, np.int32)
+                    pos_off = np.arange(4, dtype=np.int64) * N
+                    r = B._Result()
+                    r.sequence_len, r.kmer_breaks, r.path_prob_dist_startpos = [out_i[i].ctypes.data for i in range(3)]
+                    r.pos, r.pos_off = pos.ctypes.data, pos_off.ctypes.data
+                    scorer.score_batch_raw(bt, r, 8, flags | B.DEVICE_CHARS)
+                    assert np.array_equal(out_i[1], want["kmer_breaks"]), (L, N, phase, bulk)
+                    assert np.array_equal(out_i[2], want["path_prob_dist_startpos"]), (L, N, phase, bulk)
+                    assert np.array_equal(pos, want["pos_flat"][:3 * N]), (L, N, phase, bulk)
+                    del keep
+
+
+def test_pack_variants(emul_scorer, kmers, prob, monkeypatch):
+    check_pack_variants(emul_scorer, kmers, prob, monkeypatch, [1, 12, 31, 33, 100, 150, 151, 1000])
+
+
 def check_spectrum_variants(scorer, lib, kmers, prob):
     """truth spectrum with the rank table in shared memory (default) == with the table in global memory"""
     import os

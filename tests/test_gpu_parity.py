@@ -359,6 +359,15 @@ def test_cfg2_full_study_properties(gpu_scorer, kmers, prob):
             assert np.array_equal(part[k], whole[k][c0:c1], equal_nan=True), k
 
 
+def test_pack_variants(gpu_scorer, kmers, prob, monkeypatch):
+    """bulk-copy staged and register staged packing out of device buffers at every 16-byte phase (exact-size
+    torch tensors: the bulk copy must not touch a byte outside them)"""
+    import torch
+    from test_emul_device_algorithm import check_pack_variants
+    check_pack_variants(gpu_scorer, kmers, prob, monkeypatch, [1, 12, 31, 33, 100, 150, 151, 1000, 3000],
+                        to_dev=lambda a: torch.from_numpy(a).cuda(), n_reads=(1, 3, 257, 1111, 20011))
+
+
 def test_async_device_resident_calls_reuse_workspaces(product_lib, kmers, prob, monkeypatch):
     """BS_DEVICE_CHARS | BS_DEVICE_RESULT calls return before their kernels finish; back-to-back calls
     over many small chunks must not rewrite a workspace that a running chunk still reads."""
