@@ -68,19 +68,26 @@ struct alignas(16) TabEntry {
 #define BS_SCORE_BLOCKS 6
 #endif
 #ifndef BS_SCORE_CC_DENSE
-#define BS_SCORE_CC_DENSE 4096
+#define BS_SCORE_CC_DENSE 1024
 #endif
-#ifndef BS_SCORE_ROW_CAP
-#define BS_SCORE_ROW_CAP 2048
+#ifndef BS_SCORE_HASH_SLOTS
+#define BS_SCORE_HASH_SLOTS 4096
 #endif
 constexpr int SCORE_THREADS = BS_SCORE_THREADS, SCORE_BLOCKS = BS_SCORE_BLOCKS;  // block shape k_break_score is built for
 constexpr int CC_DENSE = BS_SCORE_CC_DENSE;  // counts below this are tallied in a dense shared-memory array
 constexpr int OVF_CAP = 4096;   // per-block capacity for larger counts
+// KS-B needs, per contig, the number of table rows with every count value.  Contigs that placed at most
+// HASH_LIMIT reads (so at most that many distinct break k-mers) count their rows in a shared-memory hash table:
+// one 32-bit slot = (dense k-mer index + 1) << 15 | count.  Larger contigs use the block's row of the global
+// scratch (T+1 counters): rare, so those rows stay out of DRAM (every contig going through them cost 315 MB of
+// write-backs per 1000 segments, profiles/r02a).
 #ifdef BS_CPU_EMUL
-constexpr int ROW_CAP = 96;     // (emulation: small, so that the tests run both forms of pass 2)
+constexpr int HASH_SLOTS = 128;  // (emulation: small, so that the tests run both forms)
 #else
-constexpr int ROW_CAP = BS_SCORE_ROW_CAP;   // table rows of a contig's breaks remembered in shared memory between the passes
+constexpr int HASH_SLOTS = BS_SCORE_HASH_SLOTS;
 #endif
+constexpr int HASH_LIMIT = HASH_SLOTS * 2 / 3;
+static_assert(HASH_LIMIT < (1 << 15) && DENSE_SIZE + 1 < (1 << 17), "slot layout: 17-bit key, 15-bit count");
 
 struct ScoreArgs {
     const int32_t *order;   // [C] contig ids, longest first
@@ -145,18 +152,21 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
 
 __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(ScoreArgs a) {
     __shared__ double s_w[32];
-    __shared__ int32_t s_cc[CC_DENSE];  // rows having count j
-    __shared__ int32_t s_rows[ROW_CAP];  // rows met in pass 1 (with repeats), for pass 2
-    __shared__ int s_item, s_novf, s_maxc, s_nz, s_nrow;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    __shared__ int32_t s_cc[CC_DENSE];      // rows having count j
+    __shared__ uint32_t s_hash[HASH_SLOTS];  // (dense index + 1) << 15 | count, 0 = empty; all empty between contigs
+    __shared__ int s_item, s_novf, s_maxc, s_nz;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const bool want_ks = a.ks_b != nullptr;
     int32_t *scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
     int32_t *ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    if (want_ks) for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
+    if (want_ks) {
+        for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
+        for (int i = tid; i < HASH_SLOTS; i += nthr) s_hash[i] = 0u;
+    }
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; s_nrow = 0; }
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; }
         __syncthreads();
         if (s_item >= a.n_contigs) break;
         const int64_t c = a.order[s_item];
@@ -167,12 +177,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
         const int32_t *w = a.w + coff + c;
         const int32_t total = a.total[c];
         const int64_t np = L > 0 ? L : 1;
+        const bool in_smem = total <= HASH_LIMIT;  // (block-uniform) distinct break k-mers <= placed reads
         double s1 = 0.0, s2 = 0.0;
         // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS); four
         // positions per thread in flight so that the table gathers overlap
         if (total != 0) {
             for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
-                int32_t wv[4];
+                int32_t wv[4], di[4];
                 TabEntry te[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -183,10 +194,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
                 for (int u = 0; u < 4; u++) {
                     te[u].prob = 0.0;
                     te[u].row = -1;
+                    di[u] = -1;
                     if (wv[u] != 0) {
                         const BreakWindow bw = break_window(p0 + (int64_t)u * nthr + tid, a.kmer, L);
-                        const int di = dense_index_at(gw, gm, bw.start, bw.len);
-                        if (di >= 0) te[u] = a.tab[di];
+                        di[u] = dense_index_at(gw, gm, bw.start, bw.len);
+                        if (di[u] >= 0) te[u] = a.tab[di[u]];
                     }
                 }
 #pragma unroll
@@ -196,23 +208,26 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
                     if (row >= 0) {
                         s1 += te[u].prob * (double)wv[u];
                         s2 += te[u].prob * ((double)wv[u] / (double)total);
-                        if (want_ks) atomicAdd(&scratch[row], wv[u]);
+                        if (want_ks) {
+                            if (in_smem) {
+                                // distinct dense indices are distinct table rows: count per k-mer.  At most HASH_LIMIT
+                                // of the HASH_SLOTS slots are ever taken, so the probe ends.
+                                const uint32_t key = (uint32_t)di[u] + 1u;
+                                for (uint32_t h = (key * 2654435761u) >> 16;; h++) {
+                                    h &= (uint32_t)(HASH_SLOTS - 1);
+                                    uint32_t cur = s_hash[h];
+                                    if (cur == 0u) {
+                                        cur = atomicCAS(&s_hash[h], 0u, (key << 15) | (uint32_t)wv[u]);
+                                        if (cur == 0u) break;
+                                    }
+                                    if ((cur >> 15) == key) { atomicAdd(&s_hash[h], (uint32_t)wv[u]); break; }
+                                }
+                            } else {
+                                atomicAdd(&scratch[row], wv[u]);
+                            }
+                        }
                     }
                     if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv[u]);
-                }
-                if (want_ks) {  // remember the rows (one shared-memory counter bump per warp)
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int32_t row = te[u].row;  // -1 where nothing broke
-                        const unsigned m = __ballot_sync(FULL_MASK, row >= 0);
-                        if (m == 0) continue;
-                        const int leader = __ffs((int)m) - 1;
-                        int base = 0;
-                        if (lane == leader) base = atomicAdd(&s_nrow, __popc(m));
-                        base = __shfl_sync(FULL_MASK, base, leader);
-                        const int slot = base + __popc(m & ((1u << lane) - 1u));
-                        if (row >= 0 && slot < ROW_CAP) s_rows[slot] = row;
-                    }
                 }
             }
         }
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
         }
         __threadfence_block();
         __syncthreads();
-        // pass 2: whoever swaps a row's count out first owns it; tally rows per count value
+        // pass 2: tally rows per count value
         auto tally = [&](int32_t cnt) {
             if (cnt == 0) return;
             atomicAdd(&s_nz, 1);
@@ -242,10 +257,13 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
                 if (slot < OVF_CAP) ovf[slot] = cnt; else *a.status = 1;
             }
         };
-        const int nrow = s_nrow;
-        if (nrow <= ROW_CAP) {  // the usual case: straight from the remembered rows, every lane busy
-            for (int i = tid; i < nrow; i += nthr) tally(atomicExch(&scratch[s_rows[i]], 0));
+        if (in_smem) {  // the usual case: the hash table's slots, emptied on the way
+            for (int i = tid; i < HASH_SLOTS; i += nthr) {
+                const uint32_t v = s_hash[i];
+                if (v != 0u) { s_hash[i] = 0u; tally((int32_t)(v & 0x7fffu)); }
+            }
         } else
+        // whoever swaps a row's count out of the scratch first owns it
         for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
             int32_t wv[4], row[4], cnt[4];
 #pragma unroll
