@@ -156,6 +156,10 @@ struct bs_ctx {
     bool best_dirty = true;
 
     bool status_pending = false;  // a device-result call wanted KS-B: d_status has not been read since
+    // pinned staging of this context's share of the contigs in bs_score_multi (grow-only; a pageable std::vector
+    // went up at a fifth of the PCIe rate)
+    char *h_multi = nullptr;
+    size_t h_multi_cap = 0;
 
     // interrupt poll of the calling thread (bs_ctx_set_poll)
     bs_poll_fn poll = nullptr;
@@ -909,7 +913,9 @@ int ChunkRun::spectrum() {
         } else {
             BS_CUDA(cudaMemsetAsync(ws.ycnt.p, 0, (size_t)S * R_y * 4, st));
             if (k.R_y > 0) {
-                sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(64, (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
+                // enough blocks for the whole machine whatever the number of segments (cfg-5: ONE truth of 100 Mb)
+                const int64_t want_blocks = ((int64_t)ctx->sm_count * 8 + S - 1) / std::max<int64_t>(S, 1);
+                sp.blocks_per_seg = (int)std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(64, want_blocks), (max_tr + kScoreThreads * 8 - 1) / (kScoreThreads * 8)));
                 BS_LAUNCH(bs::k_truth_spectrum, (unsigned)(S * sp.blocks_per_seg), kScoreThreads, 0, st, sp);
                 ctx->launches++;
                 BS_LAUNCH(bs::k_row_cumsum, (unsigned)S, kScoreThreads, kScoreThreads * 8 + 16, st, (int32_t *)ws.ycnt.p, R_y);
@@ -1292,6 +1298,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
         if (t.a) cudaEventDestroy(t.a);
         if (t.b) cudaEventDestroy(t.b);
     }
+    if (ctx->h_multi) cudaFreeHost(ctx->h_multi);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
@@ -1674,7 +1681,7 @@ namespace {
 // the share of one context: its contigs (ascending input indices), their flattened text and private result arrays
 struct MultiShard {
     std::vector<int64_t> idx, off, pd_off, pos_off;
-    std::vector<char> chars;
+    char *chars = nullptr;            // the owning context's pinned staging buffer
     std::vector<int32_t> i32[4];      // sequence_len, kmer_breaks, startpos, lev
     std::vector<double> f64[10];      // score, norm, by_len, ks_a, ks_b and the same for the second table
     std::vector<double> pd, pd2;
@@ -1759,9 +1766,23 @@ static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_c
             m.pd_off[i + 1] = m.pd_off[i] + std::max<int64_t>(L - kmer + 1, 0);
             m.pos_off[i + 1] = m.pos_off[i] + n_reads;
         }
-        m.chars.resize((size_t)m.off[n] + 1);
+        {
+            bs_ctx *own = ctxs[&m - sh.data()];
+            const size_t need = (size_t)m.off[n] + 1;
+            if (need > own->h_multi_cap) {
+                cudaSetDevice(own->device);
+                if (own->h_multi) cudaFreeHost(own->h_multi);
+                own->h_multi = nullptr;
+                own->h_multi_cap = 0;
+                const size_t want = need + need / 4 + 4096;
+                if (cudaHostAlloc((void **)&own->h_multi, want, cudaHostAllocPortable) != cudaSuccess)
+                    return fail(ctx, BS_ERR_ALLOC, "bs_score_multi: cudaHostAlloc(%zu) failed", want);
+                own->h_multi_cap = want;
+            }
+            m.chars = own->h_multi;
+        }
         for (size_t i = 0; i < n; i++)
-            if (len_of(m.idx[i])) std::memcpy(m.chars.data() + m.off[i], contig_chars + contig_off[m.idx[i]], (size_t)len_of(m.idx[i]));
+            if (len_of(m.idx[i])) std::memcpy(m.chars + m.off[i], contig_chars + contig_off[m.idx[i]], (size_t)len_of(m.idx[i]));
         std::memset(&m.r, 0, sizeof(m.r));
         for (int j = 0; j < 4; j++) if (i32_dst[j]) m.i32[j].assign(n + 1, 0);
         for (int j = 0; j < 10; j++) if (f64_dst[j]) m.f64[j].assign(n + 1, 0.0);
@@ -1787,7 +1808,7 @@ static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_c
     auto run = [&](int k) {  // (bs_score catches everything itself: nothing escapes a worker thread)
         MultiShard &m = sh[k];
         if (m.idx.empty()) return;
-        m.rc = bs_score(ctxs[k], m.chars.data(), m.off.data(), (int64_t)m.idx.size(), read_chars, read_off, n_reads, truth, truth_len,
+        m.rc = bs_score(ctxs[k], m.chars, m.off.data(), (int64_t)m.idx.size(), read_chars, read_off, n_reads, truth, truth_len,
                         kmer, flags, &m.r);
     };
 #ifdef BS_CPU_EMUL

@@ -240,7 +240,7 @@ typedef void *cudaStream_t;
 typedef struct bs_emul_event { double t; } *cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaEventDisableTiming = 2 };
+enum { cudaHostAllocDefault = 0, cudaHostAllocPortable = 1, cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaEventDisableTiming = 2 };
 struct cudaDeviceProp {
     char name[256];
     int major, minor, multiProcessorCount;

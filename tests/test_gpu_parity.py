@@ -2,6 +2,8 @@
 the oracle (same seeded inputs), the reference vectors, and size-independent properties at
 BASELINE.json's full sizes.  Bit-exact for positions / histograms / integer outputs /
 path_prob_dist; fp64 scores and KS within 1e-9 relative (conftest.RTOL)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -240,6 +242,48 @@ def test_cfg4_scaffold_set(gpu_scorer, oracle, kmers, prob):
                 assert np.array_equal(res[k], whole[k][part], equal_nan=True), (world, k)
 
 
+def test_cfg4_full_size_sampled_oracle(gpu_scorer, kmers, prob):
+    """BASELINE.json configs[3] at its size: 10 000 scaffolds in ONE call.  208 of them -- the longest, the shortest,
+    every member of a few groups of identical scaffolds, the rest at random -- against the CPU oracle with all reads
+    (contigs are independent: lib/BreakageScorer.cpp:231-304), straight out of the 10 000-scaffold call's own output."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import loader as O
+    seg = synth.make_scaffold_set(1400, n_scaffolds=10000)
+    gpu_scorer.set_table(kmers, prob)
+    res = gpu_scorer.score(seg.contigs, seg.reads, seg.truth, flags=B.WANT_KS | B.WANT_STARTPOS)
+    lens = np.array([len(c) for c in seg.contigs])
+    groups = {}
+    for i, c in enumerate(seg.contigs):
+        groups.setdefault(c, []).append(i)
+    dups = [g for g in groups.values() if len(g) > 1][:8]
+    chosen = {int(np.argmax(lens)), int(np.argmin(lens))}
+    for g in dups:
+        chosen.update(g[:4])
+    rng = np.random.default_rng(44)
+    for i in rng.permutation(len(seg.contigs)):
+        if len(chosen) >= 208:
+            break
+        chosen.add(int(i))
+    chosen = sorted(chosen)
+    reads = seg.read_list
+
+    def check(idx):
+        want = O.oracle_calc_breakscore([seg.contigs[i] for i in idx], reads, seg.truth, 8, kmers, prob, want_prob_dist=False)
+        for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos"):
+            assert np.array_equal(res[k][idx], want[k]), k
+        for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len"):
+            np.testing.assert_allclose(res[k][idx], want[k], rtol=1e-9, atol=0, err_msg=k)
+        for k in ("ks_stat_prob_dist", "ks_stat_path_freq"):
+            np.testing.assert_allclose(res[k][idx], want[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+        return len(idx)
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        assert sum(ex.map(check, [chosen[i:i + 4] for i in range(0, len(chosen), 4)])) >= 200
+    for g in dups:  # identical scaffolds score identically
+        for k in ("bp_score", "kmer_breaks", "ks_stat_prob_dist"):
+            assert len({res[k][i].tobytes() for i in g}) == 1, k
+
+
 def test_cfg5_shape_scaled(gpu_scorer, oracle, kmers, prob):
     """cfg-5 shape scaled to test size: one 1 Mb truth, 1e5 uniform-start 150 bp reads, 1000 contigs of
     about 1 kb.  A sample of contigs against the oracle (contigs are independent), the rest through the
@@ -357,6 +401,94 @@ def test_cfg2_full_study_properties(gpu_scorer, kmers, prob):
         c0, c1 = int(b.seg_contig_start[s0]), int(b.seg_contig_start[s1])
         for k in keys:
             assert np.array_equal(part[k], whole[k][c0:c1], equal_nan=True), k
+    # 32 randomly chosen segments of THIS 1000-segment call's own output (default outputs) against the unmodified
+    # reference build where it exists (oracle/_ref travels with the repo), else the C restatement: integer columns and
+    # path_prob_dist bit-exact, scores 1e-9; the KS columns against the restatement (the reference has none)
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import loader as O
+    full = gpu_scorer.score_batch(*args, flags=B.DEFAULT_FLAGS)
+    for k in keys:
+        assert np.array_equal(full[k], whole[k], equal_nan=True), k
+    pick = sorted(np.random.default_rng(20261019).choice(b.n_segments, size=32, replace=False).tolist())
+
+    def check(s):
+        seg = b.segment(s)
+        c0, c1 = int(b.seg_contig_start[s]), int(b.seg_contig_start[s + 1])
+        port = O.oracle_calc_breakscore(seg.contigs, seg.read_list, seg.truth, 8, kmers, prob)
+        want = O.ref_calc_breakscore(seg.contigs, seg.read_list, seg.truth, 8, kmers, prob) if O.have_ref() else port
+        for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos"):
+            assert np.array_equal(full[k][c0:c1], want[k]), (s, k)
+        for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len"):
+            np.testing.assert_allclose(full[k][c0:c1], want[k], rtol=1e-9, atol=0, err_msg=f"{s} {k}")
+        pd0, pd1 = int(full["path_prob_dist_off"][c0]), int(full["path_prob_dist_off"][c1])
+        assert np.array_equal(full["path_prob_dist_flat"][pd0:pd1], np.concatenate(want["path_prob_dist"])), (s, "path_prob_dist")
+        for k in ("ks_stat_prob_dist", "ks_stat_path_freq"):
+            np.testing.assert_allclose(full[k][c0:c1], port[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=f"{s} {k}")
+        return c1 - c0
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:  # (the ctypes calls release the GIL)
+        assert sum(ex.map(check, pick)) > 300
+
+
+@pytest.mark.parametrize("mode", ["default", "tile", "lev", "second_table", "ragged", "big_startpos"])
+def test_hundred_repeats_are_bit_identical(mode, gpu_scorer, oracle, kmers, prob, monkeypatch):
+    """Every kernel that uses warp-level primitives or inter-block atomics (k_place ballot counts, the KS prefix sums and
+    max reductions, block_sum_fixed, k_startpos_verify, k_lev_bound / k_lev_infix, the packing and index kernels),
+    100 calls on the same inputs: every output of every call equals the first call's bit for bit, and the first call's
+    equals the oracle's.  (An earlier contig-in-truth kernel lost offsets at random on the GPU only: DESIGN.md section 5.)"""
+    gpu_scorer.set_table(kmers, prob)
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST
+    if mode == "big_startpos":  # 1500 contigs in one segment: one-table-per-segment geometry, candidate queue, warp verification
+        rng = np.random.default_rng(9)
+        L = 300_000
+        truth = synth.codes_to_ascii(synth.random_truth_codes(rng, L))
+        starts = rng.integers(0, L - 100, size=60_000)
+        reads = truth[starts[:, None] + np.arange(100)[None, :]]
+        cs = np.sort(rng.integers(0, L - 41000, size=1500))
+        cl = rng.integers(100, 1500, size=1500)
+        cl[::300] = 40000  # a few long contigs: many verification steps per candidate
+        contigs = [truth[a:a + b].tobytes() for a, b in zip(cs, cl)]
+        seg = synth.Segment(truth.tobytes(), reads, contigs)
+        flags = B.WANT_STARTPOS | B.WANT_KS
+        call = lambda: gpu_scorer.score(seg.contigs, seg.reads, seg.truth, flags=flags)  # noqa: E731
+        first = call()
+        assert np.array_equal(first["path_prob_dist_startpos"], cs.astype(np.int32) * (first["kmer_breaks"] > 0))
+    else:
+        b = synth.make_batch(12, seed=777, length=20000, read_len=100, coverage=20, contigs_lo=3, contigs_hi=30, n_gap_scaffolds=1)
+        args = [b.read_chars, None, b.read_len, b.contig_chars, b.contig_off, b.truth_chars, b.truth_off, b.seg_read_start, b.seg_contig_start]
+        if mode == "tile":
+            flags |= B.PLACE_TILE
+        elif mode == "lev":
+            flags |= B.WANT_LEV
+        elif mode == "second_table":
+            gpu_scorer.set_second_table(tables.uniform(len(prob)))
+            flags |= B.WANT_SECOND_TABLE
+        elif mode == "ragged":  # offsets given and not uniform: k_pack_reads
+            n = b.n_reads
+            lens = np.full(n, b.read_len, np.int64)
+            lens[::7] = 60
+            off = np.zeros(n + 1, np.int64)
+            np.cumsum(lens, out=off[1:])
+            rows = b.read_chars.reshape(n, b.read_len)
+            args[0] = np.concatenate([rows[i, :lens[i]] for i in range(n)])
+            args[1], args[2] = off, 0
+        call = lambda: gpu_scorer.score_batch(*args, flags=flags)  # noqa: E731
+        first = call()
+        s = 5
+        seg = b.segment(s)
+        rl = seg.read_list if mode != "ragged" else [args[0][args[1][i]:args[1][i + 1]].tobytes() for i in range(int(b.seg_read_start[s]), int(b.seg_read_start[s + 1]))]
+        want = oracle.oracle_calc_breakscore(seg.contigs, rl, seg.truth, 8, kmers, prob, want_hist=True, want_lev=(mode == "lev"))
+        c0, c1 = int(b.seg_contig_start[s]), int(b.seg_contig_start[s + 1])
+        for k in ("kmer_breaks", "path_prob_dist_startpos", "hist") + (("lev_dist_vs_true",) if mode == "lev" else ()):
+            assert np.array_equal(first[k][c0:c1], want[k]), k
+        np.testing.assert_allclose(first["ks_stat_prob_dist"][c0:c1], want["ks_stat_prob_dist"], rtol=1e-9, atol=1e-12)
+    for it in range(int(os.environ.get("BS_TEST_REPS", "100"))):
+        again = call()
+        for k in first:
+            if k != "sequence":
+                assert np.array_equal(first[k], again[k], equal_nan=True), (it, k)
+    if mode == "second_table":
+        gpu_scorer.set_second_table(None)
 
 
 def test_pack_variants(gpu_scorer, kmers, prob, monkeypatch):
