@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_PKG, "libbreakscore.so")
+# (BREAKSCORE_LIB: another build of the same library, e.g. a tuning variant made with `make OUT=... EXTRA_NVFLAGS=-D...`)
+DEFAULT_LIB = os.environ.get("BREAKSCORE_LIB") or os.path.join(_PKG, "libbreakscore.so")
 
 # flags (include/breakscore.h)
 WANT_PROB_DIST = 0x001

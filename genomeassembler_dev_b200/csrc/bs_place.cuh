@@ -261,7 +261,11 @@ constexpr int PLACE_IX_THREADS = BS_PLACE_IX_THREADS, PLACE_IX_BLOCKS = BS_PLACE
 #ifndef BS_PLACE_CAND_CAP
 #define BS_PLACE_CAND_CAP 256
 #endif
-constexpr int PLACE_CAND_CAP = BS_PLACE_CAND_CAP;  // seed hits of one WARP iteration (128 positions) awaiting verification
+constexpr int PLACE_CAND_CAP = BS_PLACE_CAND_CAP;  // seed hits of one WARP iteration (32 * PLACE_POS positions) awaiting verification
+#ifndef BS_PLACE_POS
+#define BS_PLACE_POS 4
+#endif
+constexpr int PLACE_POS = BS_PLACE_POS;  // consecutive contig positions per thread and iteration (divides 32): bucket-head gathers in flight
 
 BS_HD size_t place_index_smem_bytes(int hit_cap, int nthr) { return (size_t)hit_cap * 4 + (size_t)(nthr / 32) * PLACE_CAND_CAP * 8; }
 
@@ -342,39 +346,45 @@ __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_ind
             // ---- every contig position against the index.  Phase 1 (sparse, cheap): four positions
             // per thread in flight, bucket head -> chain entry; equal seed tags are queued per warp.
             // Phase 2 (dense): the warp's lanes verify one queued candidate each on the packed words. ----
-            for (int64_t p0 = 0; p0 + S <= L; p0 += 4 * (int64_t)nthr) {
-                // a thread takes four CONSECUTIVE positions (never straddling a word boundary)
-                const int64_t pb = p0 + 4 * (int64_t)tid;
-                uint32_t q4[4];
-                uint64_t seed4[4];
+            for (int64_t p0 = 0; p0 + S <= L; p0 += PLACE_POS * (int64_t)nthr) {
+                // a thread takes PLACE_POS CONSECUTIVE positions (never straddling a word boundary)
+                const int64_t pb = p0 + PLACE_POS * (int64_t)tid;
+                uint32_t q4[PLACE_POS];
+                uint64_t seed4[PLACE_POS];
 #pragma unroll
-                for (int u = 0; u < 4; u++) { q4[u] = 0; seed4[u] = 0; }
+                for (int u = 0; u < PLACE_POS; u++) { q4[u] = 0; seed4[u] = 0; }
                 if (pb + S <= L) {
                     const int64_t idx = pb >> 5;
                     const uint32_t o = (uint32_t)(pb & 31);
                     const uint64_t cw0 = __ldg(&gw[idx]), cw1 = __ldg(&gw[idx + 1]);
                     const uint32_t cm0 = __ldg(&gm[idx]), cm1 = __ldg(&gm[idx + 1]);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < PLACE_POS; u++) {
                         if (pb + u + S <= L && !(window32(cm0, cm1, o + u) & keepSm)) {  // else: a non-ACGT base in the seed window
                             seed4[u] = window64(cw0, cw1, o + u) & keepS;
                             q4[u] = head[seed_hash(seed4[u]) & hmask];
                         }
                     }
                 }
+                // the first chain entry of every non-empty bucket, all in flight together (the heads were)
+                uint2 e4[PLACE_POS];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < PLACE_POS; u++) e4[u] = q4[u] != 0 ? a.ix.next[q4[u] - 1] : make_uint2(0u, 0u);
+#pragma unroll
+                for (int u = 0; u < PLACE_POS; u++) {
                     const int64_t p = pb + u;
                     uint32_t q = q4[u];
+                    uint2 e = e4[u];
                     const uint32_t tag = seed_tag(seed4[u]);
                     while (q != 0) {  // the chain entry carries a 32-bit tag of the read's seed: the packed
                         const int64_t n = (int64_t)q - 1;  // reads themselves are only touched in phase 2
-                        const uint2 e = a.ix.next[n];
+                        if (e.y == tag) {
+                            const int slot = atomicAdd(&s_ncand[warp], 1);
+                            if (slot < PLACE_CAND_CAP) s_cand[slot] = make_uint2((uint32_t)n, (uint32_t)p);
+                            else verify_and_record(n, p);  // queue full (long chains): verify in place
+                        }
                         q = e.x;
-                        if (e.y != tag) continue;
-                        const int slot = atomicAdd(&s_ncand[warp], 1);
-                        if (slot < PLACE_CAND_CAP) s_cand[slot] = make_uint2((uint32_t)n, (uint32_t)p);
-                        else verify_and_record(n, p);  // queue full (long chains): verify in place
+                        if (q != 0) e = a.ix.next[q - 1];
                     }
                 }
                 __syncwarp();

@@ -390,38 +390,37 @@ inline void mbar_wait(uint64_t *, uint32_t) {}
 #endif
 
 constexpr int PACKB_THREADS = 256;
-constexpr int PACKB_TILE_BYTES = 14 * 1024;  // target ASCII bytes per tile
-constexpr int PACKB_MAX_STAGE = 24 * 1024;   // longest reads the staged kernel takes: 16 of them must fit a stage
+constexpr int PACKB_STAGES = 3;              // bulk copies in flight per block: tiles t+1 and t+2 while tile t is converted
+constexpr int PACKB_TILE_BYTES = 12 * 1024;  // target ASCII bytes per tile
+constexpr int PACKB_MAX_STAGE = 20 * 1024;   // longest reads the staged kernel takes: 16 of them must fit a stage
 
-// reads per tile for reads of L bytes: a multiple of 4 (flag words) whose byte count is a multiple of 16
+// reads per tile for reads of L bytes: a multiple of 4 whose byte count is a multiple of 16, at most one per thread
 BS_HD int packb_tile_reads(int L) {
     int g = L & 15;  // gcd(L, 16)
     g = g == 0 ? 16 : (g & -g);
     int q = 16 / g;
     if (q < 4) q = 4;
     int R = (PACKB_TILE_BYTES / L) / q * q;
+    if (R > PACKB_THREADS) R = PACKB_THREADS / q * q;
     return R < q ? q : R;
 }
 BS_HD int packb_stage_bytes(int L, int R) { return ((R * L + 15 + 16) / 16 * 16 + 127) / 128 * 128; }
 BS_HD size_t packb_smem_bytes(int L, int R) {
     const size_t cells = (size_t)packb_stage_bytes(L, R) / 16;
-    return 2 * (size_t)packb_stage_bytes(L, R) + 2 * cells * 8 + 2 * ((size_t)R / 4 + 1) * 4 + 64;
+    return PACKB_STAGES * (size_t)packb_stage_bytes(L, R) + 2 * cells * 8 + 64;
 }
 
 __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r, ReadIndex ix, int R) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int L = r.uniform_len;
-    const uint32_t W = (uint32_t)r.W;
+    const int W = r.W;
     const int SB = packb_stage_bytes(L, R);
     const int cells_max = SB / 16;
-    const int flag_words = R / 4 + 1;
     unsigned char *sm = bs_dyn_smem();
-    unsigned char *s_stage = sm;                          sm += 2 * (size_t)SB;
-    uint32_t *s_code = (uint32_t *)sm;                    sm += 2 * (size_t)cells_max * 4;
-    uint32_t *s_bad = (uint32_t *)sm;                     sm += 2 * (size_t)cells_max * 4;
-    uint32_t *s_flagw = (uint32_t *)sm;                   sm += 2 * (size_t)flag_words * 4;
-    uint64_t *s_bar = (uint64_t *)(((uintptr_t)sm + 7) & ~(uintptr_t)7);  // two mbarriers
-    __shared__ int s_tileseg[2];  // segment of the first read of the tile in each stage
+    unsigned char *s_stage = sm;                          sm += PACKB_STAGES * (size_t)SB;
+    uint2 *s_cell = (uint2 *)sm;                          sm += 2 * (size_t)cells_max * 8;  // (2-bit codes of 16 bases, validity) per cell, two tiles
+    uint64_t *s_bar = (uint64_t *)(((uintptr_t)sm + 7) & ~(uintptr_t)7);  // one mbarrier per stage
+    __shared__ int s_tileseg[2];  // segment of the first read of the tile being cut
 
     const int64_t N = r.n;
     const int64_t total_bytes = N * (int64_t)L;
@@ -431,8 +430,6 @@ __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r,
     const int64_t t0 = (int64_t)blockIdx.x * per_block;
     const int64_t t1 = t0 + per_block < tiles_total ? t0 + per_block : tiles_total;
     if (t0 >= t1) return;
-    const uint32_t w_magic = W > 1 ? (uint32_t)((0x100000000ull + W - 1) / W) : 0u;  // x / W for x * W < 2^32
-    auto div_w = [&](uint32_t x) { return W > 1 ? __umulhi(x, w_magic) : x; };
 
     // cells [c_lo, c_hi) of tile t are completely inside the buffer: the bulk copy's share
     auto tile_geom = [&](int64_t t, int &nr, int &ncell, int &c_lo, int &c_hi) {
@@ -448,7 +445,7 @@ __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r,
     auto issue = [&](int64_t t) {  // thread 0 only
         int nr, ncell, c_lo, c_hi;
         tile_geom(t, nr, ncell, c_lo, c_hi);
-        const int st = (int)((t - t0) & 1);
+        const int st = (int)((t - t0) % PACKB_STAGES);
         const uint32_t bytes = 16u * (uint32_t)(c_hi - c_lo);
         if (bytes) {
             mbar_arrive_expect_tx(&s_bar[st], bytes);
@@ -460,29 +457,25 @@ __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r,
 
     int seg = 0;  // thread 0: segment of the current tile's first read, advanced tile by tile
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int i = 0; i < PACKB_STAGES; i++) mbar_init(&s_bar[i], 1);
         mbar_init_fence();
-        issue(t0);
-        if (t0 + 1 < t1) issue(t0 + 1);
+        for (int i = 0; i < PACKB_STAGES && t0 + i < t1; i++) issue(t0 + i);
         if (ix.head) seg = segment_of_read(ix, t0 * R);
     }
-    for (int i = tid; i < 2 * flag_words; i += nthr) s_flagw[i] = 0;
     __syncthreads();
 
     // index insertion in flight: the bucket's previous head comes back from the atomic one tile later
     uint32_t pend_n = 0xffffffffu, pend_old = 0, pend_tag = 0;
     for (int64_t t = t0; t < t1; t++) {
-        const int st = (int)((t - t0) & 1);
-        const uint32_t parity = (uint32_t)(((t - t0) >> 1) & 1);
+        const int st = (int)((t - t0) % PACKB_STAGES);
+        const uint32_t parity = (uint32_t)(((t - t0) / PACKB_STAGES) & 1);
         int nr, ncell, c_lo, c_hi;
         tile_geom(t, nr, ncell, c_lo, c_hi);
         const int64_t n0 = t * R;
         const unsigned char *stage = s_stage + (size_t)st * SB;
-        uint32_t *code = s_code + (size_t)st * cells_max, *bad = s_bad + (size_t)st * cells_max;
-        uint32_t *flagw = s_flagw + (size_t)st * flag_words;
+        uint2 *cell = s_cell + (size_t)((t - t0) & 1) * cells_max;
         mbar_wait(&s_bar[st], parity);
-        // ---- phase A: 16-byte cells -> 2-bit codes + validity ----
+        // ---- phase A: 16-byte cells -> 2-bit codes + validity (every thread) ----
         for (int ci = tid; ci < ncell; ci += nthr) {
             uint4 v;
             if (ci >= c_lo && ci < c_hi) {
@@ -501,55 +494,48 @@ __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r,
                 v = make_uint4(xs[0], xs[1], xs[2], xs[3]);
             }
             uint32_t diff = 0;
-            code[ci] = pack16(v.x, v.y, v.z, v.w, diff);
-            bad[ci] = diff;
+            const uint32_t code = pack16(v.x, v.y, v.z, v.w, diff);
+            cell[ci] = make_uint2(code, diff);
         }
         if (tid == 0 && ix.head) {
             while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
-            s_tileseg[st] = seg;
+            s_tileseg[(t - t0) & 1] = seg;
         }
-        __syncthreads();  // codes of tile t complete; stage st and everything of tile t-1 are free
-        if (tid == 0 && t + 2 < t1) issue(t + 2);
-        if (t > t0) {  // flags of tile t-1: one word per thread, written once, and the buffer zeroed for tile t+1
-            uint32_t *prev = s_flagw + (size_t)(st ^ 1) * flag_words;
-            const int pnr = R;  // (tile t-1 is never the last one: it is full)
-            if (tid < (pnr + 3) / 4) {
-                reinterpret_cast<uint32_t *>(r.flags)[(n0 - R) / 4 + tid] = prev[tid];
-                prev[tid] = 0;
+        __syncthreads();  // cells of tile t complete; its stage is free, and so is everything of tile t-1
+        if (tid == 0 && t + PACKB_STAGES < t1) issue(t + PACKB_STAGES);
+        // ---- phase B: a thread cuts all W words of ONE read out of its run of cells (whole warps beyond the
+        // tile's reads skip it: no lane spends issue slots on another lane's index insertion) ----
+        for (int nl = tid; nl < nr; nl += nthr) {
+            const uint32_t n = (uint32_t)n0 + (uint32_t)nl;
+            const int a0 = mis + nl * L;  // byte offset of the read inside the staged span
+            const int ci = a0 >> 4;
+            const uint32_t sh = 2u * (uint32_t)(a0 & 15);
+            const int last_cell = (a0 + L - 1) >> 4;
+            uint64_t *wout = r.words + (int64_t)n * W;
+            uint2 x0 = cell[ci];
+            uint32_t bad = x0.y, seed_bad = 0;
+            uint64_t word0 = 0;
+            for (int j = 0; j < W; j++) {
+                // word j = bases [32 j, 32 j + 32) of the read = cells ci + 2 j .. ci + 2 j + 2 (clamped: cells past the
+                // read's last one are only touched by bases beyond the read)
+                const int i1 = ci + 2 * j + 1 < last_cell ? ci + 2 * j + 1 : last_cell, i2 = ci + 2 * j + 2 < last_cell ? ci + 2 * j + 2 : last_cell;
+                const uint2 x1 = cell[i1], x2 = cell[i2];
+                const uint32_t o_hi = sh ? ((x0.x << sh) | (x1.x >> (32u - sh))) : x0.x;
+                const uint32_t o_lo = sh ? ((x1.x << sh) | (x2.x >> (32u - sh))) : x1.x;
+                const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(L - 32 * j);
+                wout[j] = word;
+                bad |= x1.y | x2.y;  // a cell holding any byte outside ACGT flags every read that overlaps it (conservative:
+                                     // flagged reads are verified on the text, still exact)
+                if (j == 0) { word0 = word; seed_bad = bad; }
+                x0 = x2;
             }
-        }
-        // ---- phase B: output words ----
-        const uint32_t nwords = (uint32_t)nr * W;
-        uint64_t *wout = r.words + n0 * (int64_t)W;
-        const int tseg = ix.head ? s_tileseg[st] : 0;
-        for (uint32_t k = tid; k < nwords; k += nthr) {
-            const uint32_t nl = div_w(k);
-            const int j = (int)(k - nl * W);
-            const int a = mis + (int)nl * L + 32 * j;  // byte offset inside the staged span
-            const int ci = a >> 4;
-            const uint32_t sh = 2u * (uint32_t)(a & 15);
-            const int rem = L - 32 * j;  // bases of this word that belong to the read (may exceed 32)
-            // cells past the staged span are only touched by bases beyond the read: clamp the index
-            const int i1 = ci + 1 < ncell ? ci + 1 : ncell - 1, i2 = ci + 2 < ncell ? ci + 2 : ncell - 1;
-            const uint32_t w0 = code[ci], w1 = code[i1], w2 = code[i2];
-            const uint32_t o_hi = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
-            const uint32_t o_lo = sh ? ((w1 << sh) | (w2 >> (32u - sh))) : w1;
-            const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(rem);
-            wout[k] = word;
-            // cells overlapping this word's own bytes [a, a + min(rem, 32)); a cell holding any byte outside ACGT
-            // flags every read that overlaps it (conservative: flagged reads are verified on the text, still exact)
-            const int last_cell = (a + (rem < 32 ? rem : 32) - 1) >> 4;
-            uint32_t b = bad[ci];
-            if (last_cell >= ci + 1) b |= bad[i1];
-            if (last_cell >= ci + 2) b |= bad[i2];
-            if (b) atomicOr(&flagw[nl >> 2], 1u << (8 * (int)(nl & 3)));
-            if (j == 0 && ix.head) {
+            r.flags[n] = bad ? 1 : 0;
+            if (ix.head) {
                 if (pend_n != 0xffffffffu) ix.next[pend_n] = make_uint2(pend_old, pend_tag);
-                const uint32_t n = (uint32_t)n0 + nl;
-                int sg = tseg;
+                int sg = s_tileseg[(t - t0) & 1];
                 while (sg + 1 < ix.n_seg && (int64_t)n >= ix.seg_read_start[sg + 1]) sg++;
-                if (!b) {
-                    const uint64_t seed = word & keep_bases(ix.seed_len[sg]);
+                if (!seed_bad) {
+                    const uint64_t seed = word0 & keep_bases(ix.seed_len[sg]);
                     const uint32_t h = seed_hash(seed) & (uint32_t)ix.tab_mask[sg];
                     pend_old = atomicExch(&ix.head[ix.tab_off[sg] + h], n + 1u);
                     pend_tag = seed_tag(seed);
@@ -562,15 +548,6 @@ __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r,
         }
     }
     if (pend_n != 0xffffffffu) ix.next[pend_n] = make_uint2(pend_old, pend_tag);
-    __syncthreads();
-    {  // flags of the block's last tile
-        const int64_t t = t1 - 1;
-        const int st = (int)((t - t0) & 1);
-        const int64_t n0 = t * R;
-        const int nr = (int)(N - n0 < R ? N - n0 : R);
-        const uint32_t *flagw = s_flagw + (size_t)st * flag_words;
-        if (tid < (nr + 3) / 4) reinterpret_cast<uint32_t *>(r.flags)[n0 / 4 + tid] = flagw[tid];
-    }
 }
 
 }  // namespace bs
