@@ -32,6 +32,8 @@ PLACE_SCAN = 0x100
 PLACE_TILE = 0x800
 DEVICE_CHARS = 0x200
 DEVICE_RESULT = 0x400
+WEIGHTS_OUT = 0x1000   # two-phase scoring (reads sharded over GPUs): stop after the placement, weights out
+WEIGHTS_IN = 0x2000    # ... score from (summed) weights, no reads
 DEFAULT_FLAGS = WANT_PROB_DIST | WANT_KS | WANT_STARTPOS
 
 STAGES = ("h2d", "pack", "place", "score", "truth_spectrum", "prob_dist_ks", "ks_path_freq",
@@ -82,6 +84,7 @@ class _Result(C.Structure):
         ("pos_off", C.c_void_p),
         ("bp_score2", C.c_void_p), ("bp_score_norm_by_break_freqs2", C.c_void_p), ("bp_score_norm_by_len2", C.c_void_p),
         ("ks_stat_prob_dist2", C.c_void_p), ("ks_stat_path_freq2", C.c_void_p), ("path_prob_dist2", C.c_void_p),
+        ("weights", C.c_void_p), ("weights_total", C.c_void_p),
     ]
 
 
@@ -149,8 +152,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_simulate_reads.restype = C.c_int
     lib.bs_simulate_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int,
                                       C.c_uint64, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p]
-    if lib.bs_abi_version() != 3:
-        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 3")
+    if lib.bs_abi_version() != 4:
+        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 4")
     return lib
 
 
@@ -239,6 +242,25 @@ class BreakageScorer:
         n = self._lib.bs_ctx_last_timings(self._ctx, ms.ctypes.data_as(_f64p), len(STAGES))
         return {STAGES[i]: float(ms[i]) for i in range(n)}
 
+    def pinned_empty(self, shape, dtype=np.uint8):
+        """A numpy array in page-locked host memory (bs_host_alloc).  Inputs built in such arrays go to the device at the
+        PCIe rate (~55 GB/s); pageable numpy memory is staged by the driver at about a fifth of that.  The memory is
+        released when the array (and every view of it) is garbage collected."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = self._lib.bs_host_alloc(max(n, 1))
+        if not ptr:
+            raise MemoryError(f"bs_host_alloc({n}) failed")
+        lib = self._lib
+
+        class _Owner:  # frees the block when the last view goes away
+            def __del__(self, p=ptr):
+                lib.bs_host_free(p)
+
+        buf = (C.c_ubyte * max(n, 1)).from_address(ptr)
+        buf._owner = _Owner()
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     # -- table ---------------------------------------------------------------------------
     def set_table(self, bp_kmer, bp_prob, truth_prob=None):
         """bp_kmer / bp_prob of the upstream call (lib/BreakageScorer.cpp:194-197); truth_prob is
@@ -287,7 +309,7 @@ class BreakageScorer:
 
     # -- scoring -------------------------------------------------------------------------
     def score_batch(self, read_chars, read_off, read_len, contig_chars, contig_off, truth_chars,
-                    truth_off, seg_read_start, seg_contig_start, kmer=8, flags=DEFAULT_FLAGS, group=None):
+                    truth_off, seg_read_start, seg_contig_start, kmer=8, flags=DEFAULT_FLAGS, group=None, weights=None):
         """Many independent segments in one call (one upstream calc_breakscore call each).
         Host numpy buffers in, dict of numpy arrays out (flat path_prob_dist + offsets).
         ``group``: more scorers (one per GPU, same tables) -- ONE segment's contigs are then dealt out over
@@ -351,6 +373,8 @@ class BreakageScorer:
             out["pos_off"] = pos_off
             r.pos = out["pos_flat"].ctypes.data
             r.pos_off = pos_off.ctypes.data
+        if weights is not None:
+            r.weights, r.weights_total = weights
         if group:
             if S != 1:
                 raise ValueError("a scorer group shards the contigs of ONE segment (shard whole segments over processes instead)")
@@ -364,6 +388,43 @@ class BreakageScorer:
             self._check(self._lib.bs_score_batch(self._ctx, C.byref(b), int(kmer), int(flags), C.byref(r)))
         del keep
         return out
+
+    # -- two-phase scoring: the READS of one segment sharded over several GPUs (sharding.score_reads_sharded) --------
+    def place_weights(self, path, sequencing_reads, weights_ptr: int, weights_total_ptr: int, flags=0):
+        """Phase 1: place THIS rank's reads (uint8 [n, L] or a list of strings) in ALL contigs and leave the position
+        weights in the caller's DEVICE arrays (int32: sum(L_c) + C entries / C entries; see include/breakscore.h).
+        The weights of disjoint read sets add: sum them over the ranks, then call :meth:`score_from_weights`."""
+        ct, ct_off = flatten(path)
+        if isinstance(sequencing_reads, np.ndarray) and sequencing_reads.ndim == 2:
+            rd = np.ascontiguousarray(sequencing_reads, dtype=np.uint8).reshape(-1)
+            rd_off, rlen, nr = None, sequencing_reads.shape[1], sequencing_reads.shape[0]
+        else:
+            rd, rd_off = flatten(sequencing_reads)
+            rlen, nr = 0, len(sequencing_reads)
+        tr_off = np.zeros(2, np.int64)
+        srs, scs = np.array([0, nr], np.int64), np.array([0, len(path)], np.int64)
+        tr = np.zeros(1, np.uint8)
+        b = _Batch(1, nr, len(path), rd.ctypes.data, None if rd_off is None else rd_off.ctypes.data, int(rlen), ct.ctypes.data,
+                   ct_off.ctypes.data, tr.ctypes.data, tr_off.ctypes.data, srs.ctypes.data, scs.ctypes.data)
+        r = _Result()
+        r.weights, r.weights_total = weights_ptr, weights_total_ptr
+        self._check(self._lib.bs_score_batch(self._ctx, C.byref(b), 8, int(flags) | WEIGHTS_OUT, C.byref(r)))
+
+    def score_from_weights(self, path, true_solution, weights_ptr: int, weights_total_ptr: int, kmer=8, flags=DEFAULT_FLAGS):
+        """Phase 2: score the contigs `path` from (summed) position weights; same dict as :meth:`score`."""
+        ct, ct_off = flatten(path)
+        tr, tr_off = flatten([true_solution])
+        empty = np.zeros(1, np.uint8)
+        return self._score_prepared(empty, None, 1, ct, ct_off, tr, tr_off, [0, 0], [0, len(path)], kmer, int(flags) | WEIGHTS_IN, path,
+                                    weights=(weights_ptr, weights_total_ptr))
+
+    def _score_prepared(self, rd, rd_off, rlen, ct, ct_off, tr, tr_off, srs, scs, kmer, flags, path, weights=None):
+        res = self.score_batch(rd, rd_off, rlen, ct, ct_off, tr, tr_off, srs, scs, kmer=kmer, flags=flags, weights=weights)
+        res["sequence"] = list(path)
+        if flags & WANT_PROB_DIST:
+            flat, off = res.pop("path_prob_dist_flat"), res.pop("path_prob_dist_off")
+            res["path_prob_dist"] = [flat[off[i]:off[i + 1]] for i in range(len(path))]
+        return res
 
     def score_batch_raw(self, batch: _Batch, result: _Result, kmer: int, flags: int):
         """Thin call for callers that manage their own (possibly device) buffers: bench.py."""

@@ -363,6 +363,7 @@ struct CallEnv {
     int kmer;
     uint32_t flags;
     bool dev_chars, dev_res, want_ks, want_pd, want_pos, want_hist, want_sp, want_lev, second;
+    bool w_out, w_in;  // two-phase scoring: stop after the placement / start from given position weights
     const char *read_chars;  // base of read 0 (shifted when offsets turned out to be uniform)
     const int64_t *roff;     // read offsets or NULL (every read has rlen bytes, dense)
     int32_t rlen;
@@ -408,6 +409,7 @@ struct ChunkRun {
     bs::SeqSet cs, ts;
     bs::ReadSet rs;
     bs::ReadIndex ix;
+    int32_t *w_ptr = nullptr, *total_ptr = nullptr;  // position weights and reads placed per contig (workspace, or the caller's with BS_WEIGHTS_*)
 
     // result destinations on the device (user arrays with BS_DEVICE_RESULT, else the workspace)
     int32_t *o_len = nullptr, *o_breaks = nullptr, *o_startpos = nullptr, *o_lev = nullptr, *o_hist = nullptr, *o_pos = nullptr;
@@ -635,8 +637,15 @@ int ChunkRun::prepare() {
     BS_TRY(ensure(ctx, ws.cmask, (size_t)ctg_woff[C] * 4 + 8));
     BS_TRY(ensure(ctx, ws.twords, (size_t)tr_woff[S] * 8 + 8));
     BS_TRY(ensure(ctx, ws.tmask, (size_t)tr_woff[S] * 4 + 8));
-    BS_TRY(ensure(ctx, ws.w, (size_t)w_elems * 4));
-    BS_TRY(ensure(ctx, ws.total, (size_t)C * 4));
+    if (e.w_out || e.w_in) {
+        w_ptr = res->weights + (b->contig_off[ch.c0] - b->contig_off[0]) + ch.c0;
+        total_ptr = res->weights_total + ch.c0;
+    } else {
+        BS_TRY(ensure(ctx, ws.w, (size_t)w_elems * 4));
+        BS_TRY(ensure(ctx, ws.total, (size_t)C * 4));
+        w_ptr = (int32_t *)ws.w.p;
+        total_ptr = (int32_t *)ws.total.p;
+    }
     if (!tile_mode) {
         BS_TRY(ensure(ctx, ws.head, (size_t)std::max<int64_t>(head_total, 1) * 4));
         BS_TRY(ensure(ctx, ws.next, (size_t)std::max<int64_t>(N, 1) * 8));
@@ -736,8 +745,10 @@ int ChunkRun::prepare() {
         if (e.want_pos) o_pos = (int32_t *)ws.pos.p;
     }
 
-    BS_CUDA(cudaMemsetAsync(ws.w.p, 0, (size_t)w_elems * 4, st));
-    BS_CUDA(cudaMemsetAsync(ws.total.p, 0, (size_t)C * 4, st));
+    if (!e.w_in) {
+        BS_CUDA(cudaMemsetAsync(w_ptr, 0, (size_t)w_elems * 4, st));
+        BS_CUDA(cudaMemsetAsync(total_ptr, 0, (size_t)C * 4, st));
+    }
     BS_TRY(ensure(ctx, ctx->d_counters, 64));
     BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));  // work counters of the persistent kernels
     if (o_hist) BS_CUDA(cudaMemsetAsync(o_hist, 0, (size_t)C * (T + 1) * 4, st));
@@ -760,11 +771,11 @@ int ChunkRun::pack() {
         StageTimer tm(ctx, ST_PACK, st);
         BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
         ctx->launches++;
-        if (e.want_ks || e.want_sp || e.want_lev) {
+        if ((e.want_ks || e.want_sp || e.want_lev) && !e.w_out) {
             BS_LAUNCH(bs::k_pack_seqs, grid_for(ts.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, ts);
             ctx->launches++;
         }
-        if (N > 0) {
+        if (N > 0 && !e.w_in) {
             if (!tile_mode) {
                 BS_CUDA(cudaMemsetAsync(ws.head.p, 0, (size_t)head_total * 4, st));
                 BS_CUDA(cudaMemsetAsync(ws.odd_head.p, 0, (size_t)S * 4, st));
@@ -809,7 +820,7 @@ int ChunkRun::place() {
             pa.ctg_off = d_ctg_off; pa.ctg_woff = d_ctg_woff; pa.ctg_words = cs.words; pa.ctg_mask = cs.mask;
             pa.ctg_chars = d_cchars; pa.ctg_seg = d_ctg_seg;
             pa.reads = rs; pa.ix = ix;
-            pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
+            pa.w = w_ptr; pa.total = total_ptr;
             pa.pos = o_pos; pa.pos_off = d_pos_off;
             pa.hit_cap = kHitCap; pa.keys = nullptr; pa.overflow = nullptr;
             if (!hashed) {
@@ -861,7 +872,7 @@ int ChunkRun::place() {
                     if (cap >= cap_max) return fail(ctx, BS_ERR_STATE, "placement scratch overflow at full capacity");
                     cap *= 2;
                     // the abandoned launch added some contigs' weights already: start over
-                    BS_CUDA(cudaMemsetAsync(ws.w.p, 0, (size_t)w_elems * 4, st));
+                    BS_CUDA(cudaMemsetAsync(w_ptr, 0, (size_t)w_elems * 4, st));
                     BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 4, st));
                 }
             }
@@ -872,7 +883,7 @@ int ChunkRun::place() {
             pa.ctg_words = cs.words; pa.ctg_mask = cs.mask; pa.ctg_chars = d_cchars;
             pa.reads = rs;
             pa.seg_seed_len = d_seed; pa.seg_read_start = d_seg_rs;
-            pa.w = (int32_t *)ws.w.p; pa.total = (int32_t *)ws.total.p;
+            pa.w = w_ptr; pa.total = total_ptr;
             pa.pos = o_pos; pa.pos_off = d_pos_off;
             pa.tile_len = tile_len; pa.hash_size = hash_size; pa.found_words = found_words;
             pa.scan_mode = (e.flags & BS_PLACE_SCAN) ? 1 : 0;
@@ -941,7 +952,7 @@ int ChunkRun::score(int which) {
         std::memset(&sa, 0, sizeof(sa));
         sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + (which ? 5 : 2);
         sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_seg = d_ctg_seg;
-        sa.w = (const int32_t *)ws.w.p; sa.total = (const int32_t *)ws.total.p;
+        sa.w = w_ptr; sa.total = total_ptr;
         sa.tab = (const bs::TabEntry *)(which ? ctx->d_tab2.p : ctx->d_tab.p);
         sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
         if (which == 0) {
@@ -1058,7 +1069,7 @@ int ChunkRun::startpos() {
         sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_chars = d_cchars;
         sa.ctg_seg = d_ctg_seg; sa.seg_contig_start = d_seg_cs;
         sa.tr_off = d_tr_off; sa.tr_woff = d_tr_woff; sa.tr_words = ts.words; sa.tr_mask = ts.mask;
-        sa.tr_chars = d_tchars; sa.total = (const int32_t *)ws.total.p; sa.n_contigs = C; sa.n_seg = (int32_t)S;
+        sa.tr_chars = d_tchars; sa.total = total_ptr; sa.n_contigs = C; sa.n_seg = (int32_t)S;
         sa.best = (uint32_t *)ws.spbest.p; sa.startpos = o_startpos;
         sa.exact = e.want_lev ? (int32_t *)ws.exact.p : nullptr; sa.search_all = e.want_lev ? 1 : 0;
         // seed tables + prefix bitmaps of the contig groups, built in their own kernel
@@ -1138,6 +1149,11 @@ int ChunkRun::results() {
     BS_CUDA(cudaEventRecord(ws.ev_compute, st));
 
     // ---------------- results ----------------
+    if (e.w_out) {  // phase 1 of a two-phase call: the weights already sit in the caller's device arrays
+        BS_CUDA(cudaEventRecord(ws.ev_d2h, st));
+        ws.in_flight = true;
+        return BS_OK;
+    }
     if (e.dev_res) {
         if (res->lev_dist_vs_true && !e.want_lev) BS_CUDA(cudaMemsetAsync(res->lev_dist_vs_true + ch.c0, 0, (size_t)C * 4, st));
         if (!e.want_sp && res->path_prob_dist_startpos) BS_CUDA(cudaMemsetAsync(res->path_prob_dist_startpos + ch.c0, 0, (size_t)C * 4, st));
@@ -1208,8 +1224,9 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     tr.lap("prepare");
     BS_TRY(r.pack());
     tr.lap("pack");
-    BS_TRY(r.place());
+    if (!e.w_in) BS_TRY(r.place());
     tr.lap("place");
+    if (e.w_out) return r.results();  // phase 1 of a two-phase call: the weights are the result
     BS_TRY(r.spectrum());
     BS_TRY(r.score(0));
     BS_TRY(r.prob_dist(0));
@@ -1562,6 +1579,15 @@ static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t f
     e.want_sp = (flags & BS_WANT_STARTPOS) && res->path_prob_dist_startpos;
     e.want_lev = (flags & BS_WANT_LEV) && res->lev_dist_vs_true;
     e.second = (flags & BS_WANT_SECOND_TABLE) != 0;
+    e.w_out = (flags & BS_WEIGHTS_OUT) != 0;
+    e.w_in = (flags & BS_WEIGHTS_IN) != 0;
+    if (e.w_out && e.w_in) return fail(ctx, BS_ERR_INVALID, "BS_WEIGHTS_OUT and BS_WEIGHTS_IN exclude each other");
+    if ((e.w_out || e.w_in) && (!res->weights || !res->weights_total))
+        return fail(ctx, BS_ERR_INVALID, "BS_WEIGHTS_OUT / BS_WEIGHTS_IN need result->weights and result->weights_total (device pointers)");
+    if (e.w_in && (flags & BS_WANT_POS)) return fail(ctx, BS_ERR_INVALID, "BS_WANT_POS needs the placement: not with BS_WEIGHTS_IN");
+    if (e.w_out) {  // nothing but the placement runs
+        e.want_ks = e.want_pd = e.want_hist = e.want_sp = e.want_lev = e.second = false;
+    }
     if (e.second && !ctx->has_table2) return fail(ctx, BS_ERR_STATE, "BS_WANT_SECOND_TABLE before bs_set_second_table");
     if (e.second && e.want_pd && !res->path_prob_dist2) return fail(ctx, BS_ERR_INVALID, "BS_WANT_SECOND_TABLE with BS_WANT_PROB_DIST needs path_prob_dist2");
     e.read_chars = b->read_chars;

@@ -366,25 +366,19 @@ __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_ind
                         }
                     }
                 }
-                // the first chain entry of every non-empty bucket, all in flight together (the heads were)
-                uint2 e4[PLACE_POS];
-#pragma unroll
-                for (int u = 0; u < PLACE_POS; u++) e4[u] = q4[u] != 0 ? a.ix.next[q4[u] - 1] : make_uint2(0u, 0u);
 #pragma unroll
                 for (int u = 0; u < PLACE_POS; u++) {
                     const int64_t p = pb + u;
                     uint32_t q = q4[u];
-                    uint2 e = e4[u];
                     const uint32_t tag = seed_tag(seed4[u]);
                     while (q != 0) {  // the chain entry carries a 32-bit tag of the read's seed: the packed
                         const int64_t n = (int64_t)q - 1;  // reads themselves are only touched in phase 2
-                        if (e.y == tag) {
-                            const int slot = atomicAdd(&s_ncand[warp], 1);
-                            if (slot < PLACE_CAND_CAP) s_cand[slot] = make_uint2((uint32_t)n, (uint32_t)p);
-                            else verify_and_record(n, p);  // queue full (long chains): verify in place
-                        }
+                        const uint2 e = a.ix.next[n];
                         q = e.x;
-                        if (q != 0) e = a.ix.next[q - 1];
+                        if (e.y != tag) continue;
+                        const int slot = atomicAdd(&s_ncand[warp], 1);
+                        if (slot < PLACE_CAND_CAP) s_cand[slot] = make_uint2((uint32_t)n, (uint32_t)p);
+                        else verify_and_record(n, p);  // queue full (long chains): verify in place
                     }
                 }
                 __syncwarp();

@@ -39,9 +39,13 @@ BS_HD int32_t read_length(const ReadSet &r, int64_t i) { return r.off ? (int32_t
 // 2-bit packing
 // ------------------------------------------------------------------------------------------
 
-// one thread per packed word of a SeqSet
+// one thread per packed word of a SeqSet: the word's 32 bytes come in as nine aligned 32-bit loads realigned with
+// byte funnel shifts, four bytes are converted per step inside a register (pack4 below); the pad words and the
+// positions past the end of a string pack as code 0 with their mask bits set
+__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t &diff);
 __global__ void k_pack_seqs(SeqSet s) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total_chars = s.n > 0 ? s.off[s.n] : 0;
     for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < s.total_words; wi += stride) {
         // string owning word wi: largest i with woff[i] <= wi
         int64_t lo = 0, hi = s.n - 1;
@@ -52,17 +56,52 @@ __global__ void k_pack_seqs(SeqSet s) {
         const int64_t c0 = s.off[lo];
         const int64_t L = s.off[lo + 1] - c0;
         const int64_t b0 = (wi - s.woff[lo]) * 32;
+        const int nvalid = L - b0 >= 32 ? 32 : (L - b0 > 0 ? (int)(L - b0) : 0);  // bytes of the string in this word
         uint64_t w = 0;
-        uint32_t m = 0;
-        for (int b = 0; b < 32; b++) {
-            const int64_t p = b0 + b;
-            uint32_t code = 0, bad = 1;
-            if (p < L) {
-                const uint32_t ch = s.chars[c0 + p];
-                if (base_valid(ch)) { code = base_code(ch); bad = 0; }
+        uint32_t m = ~0u;
+        if (nvalid > 0) {
+            const uint8_t *p = s.chars + c0 + b0;
+            const uint32_t sh = (uint32_t)((uintptr_t)p & 3);
+            const uint8_t *q = p - sh;                       // 4-byte aligned
+            const int64_t q_off = (c0 + b0) - (int64_t)sh;   // its offset in the char buffer (may be < 0 for the first word)
+            uint32_t a[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const int64_t o = q_off + 4 * k;
+                a[k] = 0x41414141u;
+                if (4 * k - (int)sh < nvalid && 4 * k + 4 - (int)sh > 0) {  // the aligned word overlaps the string's bytes
+                    if (o >= 0 && o + 4 <= total_chars) {
+                        a[k] = *reinterpret_cast<const uint32_t *>(q + 4 * k);
+                    } else {  // sticks out of the buffer: the bytes that exist, one by one
+                        uint32_t x = 0;
+                        for (int b = 3; b >= 0; b--) x = (x << 8) | ((o + b >= 0 && o + b < total_chars) ? (uint32_t)q[4 * k + b] : 0x41u);
+                        a[k] = x;
+                    }
+                }
             }
-            w = (w << 2) | code;
-            m = (m << 1) | bad;
+            uint32_t bad = 0;  // bit i: byte i of the word is outside ACGT
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t x = __funnelshift_r(a[k], a[k + 1], 8 * sh);  // bytes 4k .. 4k+3 of the word
+                uint32_t diff = 0;
+                const uint32_t code = pack4(x, diff) >> 24;  // c0 c1 c2 c3, first base in the most significant bits
+                w = (w << 8) | code;
+                // diff holds a non-zero BYTE per invalid base: one bit per base, first base highest
+                const uint32_t nz = (diff | (diff >> 4)) & 0x0f0f0f0fu;
+                const uint32_t nz2 = (nz | (nz >> 2)) & 0x03030303u;
+                const uint32_t nz1 = (nz2 | (nz2 >> 1)) & 0x01010101u;  // bit 0 of byte i = base 4k+i invalid
+                const uint32_t four = ((nz1 & 1u) << 3) | (((nz1 >> 8) & 1u) << 2) | (((nz1 >> 16) & 1u) << 1) | ((nz1 >> 24) & 1u);
+                bad = (bad << 4) | four;
+            }
+            m = bad | ~keep_bits(nvalid);
+            // code 0 wherever the mask is set: every mask bit spread to its base's two bits
+            uint64_t mm = m;
+            mm = (mm | (mm << 16)) & 0x0000ffff0000ffffull;
+            mm = (mm | (mm << 8)) & 0x00ff00ff00ff00ffull;
+            mm = (mm | (mm << 4)) & 0x0f0f0f0f0f0f0f0full;
+            mm = (mm | (mm << 2)) & 0x3333333333333333ull;
+            mm = (mm | (mm << 1)) & 0x5555555555555555ull;
+            w &= ~(mm | (mm << 1));
         }
         s.words[wi] = w;
         s.mask[wi] = m;
@@ -401,13 +440,50 @@ BS_HD int packb_tile_reads(int L) {
     int q = 16 / g;
     if (q < 4) q = 4;
     int R = (PACKB_TILE_BYTES / L) / q * q;
-    if (R > PACKB_THREADS) R = PACKB_THREADS / q * q;
+    if (R > PACKB_THREADS / 2) R = PACKB_THREADS / 2 / q * q;  // a cutting thread per read; at least as many converting threads
     return R < q ? q : R;
 }
 BS_HD int packb_stage_bytes(int L, int R) { return ((R * L + 15 + 16) / 16 * 16 + 127) / 128 * 128; }
 BS_HD size_t packb_smem_bytes(int L, int R) {
     const size_t cells = (size_t)packb_stage_bytes(L, R) / 16;
     return PACKB_STAGES * (size_t)packb_stage_bytes(L, R) + 2 * cells * 8 + 64;
+}
+
+// all NW words of one read out of its run of cells (cell = 2-bit codes of 16 bases + validity word): the cells are
+// loaded first, all in flight together, then cut with funnel shifts.  `bad` = any byte outside ACGT in a cell the read
+// overlaps (conservative: flagged reads are verified on the text, still exact); seed_bad = the same for the first word.
+template <int NW>
+__device__ __forceinline__ void packb_cut(const uint2 *cell, int ci, uint32_t sh, int last_cell, int L, uint64_t *wout, uint32_t &bad,
+                                          uint32_t &seed_bad, uint64_t &word0) {
+    uint2 x[2 * NW + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * NW; k++) x[k] = cell[ci + k < last_cell ? ci + k : last_cell];  // (cells past the read's last one are only touched by bases beyond the read)
+    bad = 0;
+#pragma unroll
+    for (int k = 0; k <= 2 * NW; k++) bad |= x[k].y;
+    seed_bad = x[0].y | x[1].y | x[2].y;
+#pragma unroll
+    for (int j = 0; j < NW; j++) {
+        const uint32_t o_hi = __funnelshift_l(x[2 * j + 1].x, x[2 * j].x, sh), o_lo = __funnelshift_l(x[2 * j + 2].x, x[2 * j + 1].x, sh);
+        const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(L - 32 * j);
+        wout[j] = word;
+        if (j == 0) word0 = word;
+    }
+}
+__device__ __forceinline__ void packb_cut_any(const uint2 *cell, int ci, uint32_t sh, int last_cell, int L, int W, uint64_t *wout, uint32_t &bad,
+                                              uint32_t &seed_bad, uint64_t &word0) {
+    uint2 x0 = cell[ci];
+    bad = x0.y;
+    for (int j = 0; j < W; j++) {
+        const int i1 = ci + 2 * j + 1 < last_cell ? ci + 2 * j + 1 : last_cell, i2 = ci + 2 * j + 2 < last_cell ? ci + 2 * j + 2 : last_cell;
+        const uint2 x1 = cell[i1], x2 = cell[i2];
+        const uint32_t o_hi = __funnelshift_l(x1.x, x0.x, sh), o_lo = __funnelshift_l(x2.x, x1.x, sh);
+        const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(L - 32 * j);
+        wout[j] = word;
+        bad |= x1.y | x2.y;
+        if (j == 0) { word0 = word; seed_bad = bad; }
+        x0 = x2;
+    }
 }
 
 __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r, ReadIndex ix, int R) {
@@ -455,6 +531,11 @@ __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r,
         }
     };
 
+    // warp roles: the last ceil(R / 32) warps CUT (a thread per read of the tile converted one iteration earlier), the
+    // others CONVERT the current tile's cells: the two phases of consecutive tiles overlap, one block barrier per tile
+    const int n_cut_threads = (R + 31) / 32 * 32;
+    const int n_conv = nthr - n_cut_threads;  // (the host launches with enough threads: n_conv >= 32)
+    const bool converter = tid < n_conv;
     int seg = 0;  // thread 0: segment of the current tile's first read, advanced tile by tile
     if (tid == 0) {
         for (int i = 0; i < PACKB_STAGES; i++) mbar_init(&s_bar[i], 1);
@@ -466,86 +547,89 @@ __global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r,
 
     // index insertion in flight: the bucket's previous head comes back from the atomic one tile later
     uint32_t pend_n = 0xffffffffu, pend_old = 0, pend_tag = 0;
-    for (int64_t t = t0; t < t1; t++) {
-        const int st = (int)((t - t0) % PACKB_STAGES);
-        const uint32_t parity = (uint32_t)(((t - t0) / PACKB_STAGES) & 1);
-        int nr, ncell, c_lo, c_hi;
-        tile_geom(t, nr, ncell, c_lo, c_hi);
-        const int64_t n0 = t * R;
-        const unsigned char *stage = s_stage + (size_t)st * SB;
-        uint2 *cell = s_cell + (size_t)((t - t0) & 1) * cells_max;
-        mbar_wait(&s_bar[st], parity);
-        // ---- phase A: 16-byte cells -> 2-bit codes + validity (every thread) ----
-        for (int ci = tid; ci < ncell; ci += nthr) {
-            uint4 v;
-            if (ci >= c_lo && ci < c_hi) {
-                v = *reinterpret_cast<const uint4 *>(stage + 16 * ci);
-            } else {  // a cell that sticks out of the buffer: its existing bytes one by one, 'A' for the rest
-                uint32_t xs[4];
-                const int64_t cb = n0 * L - mis + 16 * (int64_t)ci;
-                for (int q = 0; q < 4; q++) {
-                    uint32_t x = 0;
-                    for (int b = 3; b >= 0; b--) {
-                        const int64_t pb = cb + 4 * q + b;
-                        x = (x << 8) | ((pb >= 0 && pb < total_bytes) ? (uint32_t)r.chars[pb] : (uint32_t)'A');
+    for (int64_t t = t0; t <= t1; t++) {
+        if (converter && t < t1) {
+            const int st = (int)((t - t0) % PACKB_STAGES);
+            const uint32_t parity = (uint32_t)(((t - t0) / PACKB_STAGES) & 1);
+            int nr, ncell, c_lo, c_hi;
+            tile_geom(t, nr, ncell, c_lo, c_hi);
+            const int64_t n0 = t * R;
+            const unsigned char *stage = s_stage + (size_t)st * SB;
+            uint2 *cell = s_cell + (size_t)((t - t0) & 1) * cells_max;
+            mbar_wait(&s_bar[st], parity);
+            // ---- 16-byte cells -> 2-bit codes + validity ----
+            for (int ci = tid; ci < ncell; ci += n_conv) {
+                uint4 v;
+                if (ci >= c_lo && ci < c_hi) {
+                    v = *reinterpret_cast<const uint4 *>(stage + 16 * ci);
+                } else {  // a cell that sticks out of the buffer: its existing bytes one by one, 'A' for the rest
+                    uint32_t xs[4];
+                    const int64_t cb = n0 * L - mis + 16 * (int64_t)ci;
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t x = 0;
+                        for (int b = 3; b >= 0; b--) {
+                            const int64_t pb = cb + 4 * q + b;
+                            x = (x << 8) | ((pb >= 0 && pb < total_bytes) ? (uint32_t)r.chars[pb] : (uint32_t)'A');
+                        }
+                        xs[q] = x;
                     }
-                    xs[q] = x;
+                    v = make_uint4(xs[0], xs[1], xs[2], xs[3]);
                 }
-                v = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+                uint32_t diff = 0;
+                const uint32_t code = pack16(v.x, v.y, v.z, v.w, diff);
+                cell[ci] = make_uint2(code, diff);
             }
-            uint32_t diff = 0;
-            const uint32_t code = pack16(v.x, v.y, v.z, v.w, diff);
-            cell[ci] = make_uint2(code, diff);
+            if (tid == 0 && ix.head) {
+                while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
+                s_tileseg[(t - t0) & 1] = seg;
+            }
+        } else if (!converter && t > t0) {
+            // ---- the previous tile: a thread cuts all W words of ONE read out of its run of cells ----
+            const int64_t tp = t - 1;
+            const int64_t n0 = tp * R;
+            const int nr = (int)(N - n0 < R ? N - n0 : R);
+            const uint2 *cell = s_cell + (size_t)((tp - t0) & 1) * cells_max;
+            const int nl = tid - n_conv;
+            if (nl < nr) {
+                const uint32_t n = (uint32_t)n0 + (uint32_t)nl;
+                const int a0 = mis + nl * L;  // byte offset of the read inside the staged span
+                const int ci = a0 >> 4;
+                const uint32_t sh = 2u * (uint32_t)(a0 & 15);
+                const int last_cell = (a0 + L - 1) >> 4;
+                uint64_t *wout = r.words + (int64_t)n * W;
+                uint32_t bad = 0, seed_bad = 0;
+                uint64_t word0 = 0;
+                switch (W) {
+                    case 1: packb_cut<1>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    case 2: packb_cut<2>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    case 3: packb_cut<3>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    case 4: packb_cut<4>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    case 5: packb_cut<5>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    case 6: packb_cut<6>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    case 7: packb_cut<7>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    case 8: packb_cut<8>(cell, ci, sh, last_cell, L, wout, bad, seed_bad, word0); break;
+                    default: packb_cut_any(cell, ci, sh, last_cell, L, W, wout, bad, seed_bad, word0); break;
+                }
+                r.flags[n] = bad ? 1 : 0;
+                if (ix.head) {
+                    if (pend_n != 0xffffffffu) ix.next[pend_n] = make_uint2(pend_old, pend_tag);
+                    int sg = s_tileseg[(tp - t0) & 1];
+                    while (sg + 1 < ix.n_seg && (int64_t)n >= ix.seg_read_start[sg + 1]) sg++;
+                    if (!seed_bad) {
+                        const uint64_t seed = word0 & keep_bases(ix.seed_len[sg]);
+                        const uint32_t h = seed_hash(seed) & (uint32_t)ix.tab_mask[sg];
+                        pend_old = atomicExch(&ix.head[ix.tab_off[sg] + h], n + 1u);
+                        pend_tag = seed_tag(seed);
+                    } else {
+                        pend_old = atomicExch(&ix.odd_head[sg], n + 1u);
+                        pend_tag = 0u;
+                    }
+                    pend_n = n;
+                }
+            }
         }
-        if (tid == 0 && ix.head) {
-            while (seg + 1 < ix.n_seg && n0 >= ix.seg_read_start[seg + 1]) seg++;
-            s_tileseg[(t - t0) & 1] = seg;
-        }
-        __syncthreads();  // cells of tile t complete; its stage is free, and so is everything of tile t-1
+        __syncthreads();  // cells of tile t complete (its stage is free); tile t-1 is cut (its cells are free)
         if (tid == 0 && t + PACKB_STAGES < t1) issue(t + PACKB_STAGES);
-        // ---- phase B: a thread cuts all W words of ONE read out of its run of cells (whole warps beyond the
-        // tile's reads skip it: no lane spends issue slots on another lane's index insertion) ----
-        for (int nl = tid; nl < nr; nl += nthr) {
-            const uint32_t n = (uint32_t)n0 + (uint32_t)nl;
-            const int a0 = mis + nl * L;  // byte offset of the read inside the staged span
-            const int ci = a0 >> 4;
-            const uint32_t sh = 2u * (uint32_t)(a0 & 15);
-            const int last_cell = (a0 + L - 1) >> 4;
-            uint64_t *wout = r.words + (int64_t)n * W;
-            uint2 x0 = cell[ci];
-            uint32_t bad = x0.y, seed_bad = 0;
-            uint64_t word0 = 0;
-            for (int j = 0; j < W; j++) {
-                // word j = bases [32 j, 32 j + 32) of the read = cells ci + 2 j .. ci + 2 j + 2 (clamped: cells past the
-                // read's last one are only touched by bases beyond the read)
-                const int i1 = ci + 2 * j + 1 < last_cell ? ci + 2 * j + 1 : last_cell, i2 = ci + 2 * j + 2 < last_cell ? ci + 2 * j + 2 : last_cell;
-                const uint2 x1 = cell[i1], x2 = cell[i2];
-                const uint32_t o_hi = sh ? ((x0.x << sh) | (x1.x >> (32u - sh))) : x0.x;
-                const uint32_t o_lo = sh ? ((x1.x << sh) | (x2.x >> (32u - sh))) : x1.x;
-                const uint64_t word = (((uint64_t)o_hi << 32) | o_lo) & keep_bases(L - 32 * j);
-                wout[j] = word;
-                bad |= x1.y | x2.y;  // a cell holding any byte outside ACGT flags every read that overlaps it (conservative:
-                                     // flagged reads are verified on the text, still exact)
-                if (j == 0) { word0 = word; seed_bad = bad; }
-                x0 = x2;
-            }
-            r.flags[n] = bad ? 1 : 0;
-            if (ix.head) {
-                if (pend_n != 0xffffffffu) ix.next[pend_n] = make_uint2(pend_old, pend_tag);
-                int sg = s_tileseg[(t - t0) & 1];
-                while (sg + 1 < ix.n_seg && (int64_t)n >= ix.seg_read_start[sg + 1]) sg++;
-                if (!seed_bad) {
-                    const uint64_t seed = word0 & keep_bases(ix.seed_len[sg]);
-                    const uint32_t h = seed_hash(seed) & (uint32_t)ix.tab_mask[sg];
-                    pend_old = atomicExch(&ix.head[ix.tab_off[sg] + h], n + 1u);
-                    pend_tag = seed_tag(seed);
-                } else {
-                    pend_old = atomicExch(&ix.odd_head[sg], n + 1u);
-                    pend_tag = 0u;
-                }
-                pend_n = n;
-            }
-        }
     }
     if (pend_n != 0xffffffffu) ix.next[pend_n] = make_uint2(pend_old, pend_tag);
 }

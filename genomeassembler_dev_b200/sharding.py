@@ -143,3 +143,59 @@ def score_contigs_sharded(scorer, path, sequencing_reads, true_solution, kmer=8,
         owner[p] = r
     out["owner"] = owner
     return out, local_info
+
+
+def balanced_ranges(contig_lens, world: int):
+    """[0, C) cut into `world` contiguous ranges of about equal total length; returns world + 1 bounds"""
+    lens = np.asarray(contig_lens, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(lens + 1)])
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(cum, cum[-1] * r / world, side="left")))
+    bounds.append(len(lens))
+    return [int(x) for x in np.maximum.accumulate(np.minimum(bounds, len(lens)))]
+
+
+def score_reads_sharded(scorer, path, reads_shard, true_solution, kmer=8, flags=None, group=None, dst: int = 0):
+    """One segment whose READS are sharded over the ranks (cfg-5: the read set is the big input, and packing +
+    indexing it is most of the work, so replicating it does not scale).  Upstream places every read on its own
+    (``lib/BreakageScorer.cpp:235-243``), so the per-position break counts of disjoint read sets ADD:
+
+      phase 1  every rank places ITS reads in ALL contigs            -> position weights on its device
+      exchange all-reduce of the weights over the group (NCCL on GPUs; the path's one real data exchange)
+      phase 2  every rank scores a contiguous range of the contigs from the summed weights; records gathered
+
+    Returns on rank `dst` the record columns in input order (bit-identical to one unsharded call), None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    from . import breakscore
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    if flags is None:
+        flags = breakscore.DEFAULT_FLAGS
+    lens = np.fromiter((len(p) for p in path), dtype=np.int64, count=len(path))
+    off = np.concatenate([[0], np.cumsum(lens)])
+    C = len(path)
+    w = torch.zeros(int(off[-1]) + C + 1, dtype=torch.int32, device=dev)
+    tot = torch.zeros(C + 1, dtype=torch.int32, device=dev)
+    scorer.place_weights(path, reads_shard, w.data_ptr(), tot.data_ptr())
+    scorer.synchronize()
+    dist.all_reduce(w, group=group)
+    dist.all_reduce(tot, group=group)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    bounds = balanced_ranges(lens, world)
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    counts = [bounds[r + 1] - bounds[r] for r in range(world)]
+    if c1 > c0:
+        w_ptr = w.data_ptr() + 4 * (int(off[c0]) + c0)
+        local = scorer.score_from_weights(path[c0:c1], true_solution, w_ptr, tot.data_ptr() + 4 * c0, kmer=kmer, flags=flags)
+    else:
+        local = {k: np.zeros(0) for k in RECORD_F64 + RECORD_I32}
+    got = gather_records(pack_records(local, c1 - c0), counts, group=group, dst=dst)
+    if rank != dst:
+        return None
+    return unpack_records(got)

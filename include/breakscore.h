@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 3
+#define BS_ABI_VERSION 4
 
 /* the library is built with -fvisibility=hidden: only these entry points are exported */
 #if defined(__GNUC__)
@@ -64,6 +64,15 @@ enum {
 #define BS_PLACE_TILE     0x800u /* placement by a seed index over the contig tile, reads streamed past it (same results) */
 #define BS_DEVICE_CHARS   0x200u /* read_chars / contig_chars / truth_chars are DEVICE pointers */
 #define BS_DEVICE_RESULT  0x400u /* every non-NULL pointer in bs_result is a DEVICE pointer */
+/* Two-phase scoring, for ONE job whose READS are sharded over several GPUs (cfg-5: the read set is the big input).
+ * The leftmost placement of a read in a contig does not depend on any other read (lib/BreakageScorer.cpp:235-243),
+ * so the per-position break counts of disjoint read sets ADD.  Phase 1, every GPU with its own reads and ALL contigs:
+ * BS_WEIGHTS_OUT stops after the placement and leaves the position weights in result->weights / weights_total.
+ * The caller sums both arrays over the GPUs (NCCL all-reduce).  Phase 2, any split of the contigs: BS_WEIGHTS_IN skips
+ * read packing and placement and scores from the given weights (reads of the batch are ignored; n_reads may be 0).
+ * Same results as one call with all the reads, bit for bit. */
+#define BS_WEIGHTS_OUT    0x1000u
+#define BS_WEIGHTS_IN     0x2000u
 #define BS_DEFAULT_FLAGS (BS_WANT_PROB_DIST | BS_WANT_KS | BS_WANT_STARTPOS)
 
 /*
@@ -120,6 +129,11 @@ typedef struct {
     double *ks_stat_prob_dist2;
     double *ks_stat_path_freq2;
     double *path_prob_dist2;                /* uses path_prob_dist_off */
+    /* BS_WEIGHTS_OUT / BS_WEIGHTS_IN: always DEVICE pointers.  weights: int32, contig c (index within this call) owns
+     * L_c + 1 entries starting at (contig_off[c] - contig_off[0]) + c; entry p = number of reads whose leftmost match
+     * in the contig is at position p.  weights_total: int32 [C], reads placed per contig (kmer_breaks). */
+    int32_t *weights;
+    int32_t *weights_total;
 } bs_result;
 
 /* context: owns the device, its streams, the resident tables and grow-only work buffers.

@@ -211,6 +211,14 @@ inline T __shfl_up_sync(unsigned, T v, unsigned d) {
     unsigned l = bs_emul::t_lane;
     return bs_emul_shfl(v, l >= d ? l - d : l);
 }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
+    shift &= 31u;
+    return shift ? (hi << shift) | (lo >> (32u - shift)) : hi;
+}
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    shift &= 31u;
+    return shift ? (lo >> shift) | (hi << (32u - shift)) : lo;
+}
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     const uint64_t v = ((uint64_t)y << 32) | x;

@@ -314,6 +314,48 @@ def test_uniform_read_lengths(emul_scorer, oracle, kmers, prob):
     check_uniform_read_lengths(emul_scorer, oracle, kmers, prob, UNIFORM_LENGTHS)
 
 
+def check_two_phase(scorer, oracle, kmers, prob, seg, n_shards=3):
+    """BS_WEIGHTS_OUT / BS_WEIGHTS_IN: the reads of one segment in n disjoint shards placed one shard at a time, the
+    position weights summed (what the all-reduce of sharding.score_reads_sharded does), the contigs scored from the sum
+    in two separate ranges == one call with all the reads, every output bit for bit; and == the oracle."""
+    scorer.set_table(kmers, prob)
+    flags = B.DEFAULT_FLAGS | B.WANT_HIST
+    want = scorer.score(seg.contigs, seg.reads, seg.truth, flags=flags)
+    lens = np.array([len(c) for c in seg.contigs])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    C = len(seg.contigs)
+    w_sum, t_sum = np.zeros(int(off[-1]) + C + 1, np.int32), np.zeros(C + 1, np.int32)
+    for k in range(n_shards):
+        w, t = np.full_like(w_sum, -7), np.full_like(t_sum, -7)  # (the library must overwrite, not accumulate)
+        scorer.place_weights(seg.contigs, seg.reads[k::n_shards], w.ctypes.data, t.ctypes.data)
+        scorer.synchronize()
+        w_sum[:-1] += w[:-1]
+        t_sum[:-1] += t[:-1]
+    assert np.array_equal(t_sum[:C], want["kmer_breaks"])
+    cut = C // 2
+    parts = []
+    for c0, c1 in ((0, cut), (cut, C)):
+        parts.append(scorer.score_from_weights(seg.contigs[c0:c1], seg.truth, w_sum.ctypes.data + 4 * (int(off[c0]) + c0),
+                                               t_sum.ctypes.data + 4 * c0, flags=flags))
+    for k in want:
+        if k == "sequence":
+            continue
+        if k == "path_prob_dist":
+            got = parts[0][k] + parts[1][k]
+            assert all(np.array_equal(a, b) for a, b in zip(got, want[k])), k
+        else:
+            assert np.array_equal(np.concatenate([parts[0][k], parts[1][k]]), want[k], equal_nan=True), k
+    ref = oracle.oracle_calc_breakscore(seg.contigs, seg.read_list, seg.truth, 8, kmers, prob, want_hist=True)
+    assert np.array_equal(want["hist"], ref["hist"])
+    with pytest.raises(B.BreakscoreError):  # the two flags exclude each other; weights pointers are required
+        scorer.score_batch(np.zeros(1, np.uint8), None, 1, *B.flatten(seg.contigs), *B.flatten([seg.truth]), [0, 0], [0, C], flags=B.WEIGHTS_IN)
+
+
+def test_two_phase_scoring(emul_scorer, oracle, kmers, prob):
+    check_two_phase(emul_scorer, oracle, kmers, prob, P.make(*P.SMALL[0], mut=0.3))
+    check_two_phase(emul_scorer, oracle, kmers, prob, P.make(*P.SMALL[2], mut=0.3), n_shards=2)
+
+
 def check_pack_variants(scorer, kmers, prob, monkeypatch, lengths, to_dev=None, n_reads=(1, 3, 257, 1111)):
     """Reads of one length through both packing kernels (bulk-copy staged: default; register staged: BS_PACK_BULK=0)
     from read buffers that start at every 16-byte phase (BS_DEVICE_CHARS: the library packs straight out of the
@@ -366,7 +408,7 @@ def check_pack_variants(scorer, kmers, prob, monkeypatch, lengths, to_dev=None, 
 
 
 def test_pack_variants(emul_scorer, kmers, prob, monkeypatch):
-    check_pack_variants(emul_scorer, kmers, prob, monkeypatch, [1, 12, 31, 33, 100, 150, 151, 1000])
+    check_pack_variants(emul_scorer, kmers, prob, monkeypatch, [1, 12, 150, 151, 1000], n_reads=(1, 3, 300))
 
 
 def check_spectrum_variants(scorer, lib, kmers, prob):
@@ -505,7 +547,7 @@ def check_startpos_geometries(scorer, oracle, kmers, prob, monkeypatch, **kw):
             monkeypatch.setenv(k, v)
         check_startpos_many_contigs(scorer, oracle, kmers, prob, **kw)
         scorer.set_table(kmers, prob)
-        for name, contigs, reads, truth, kmer in P.edge_inputs():
+        for name, contigs, reads, truth, kmer in (P.edge_inputs() if "BS_STARTPOS_BIG" in env else []):
             got = scorer.score(contigs, reads, truth, kmer=kmer, flags=B.WANT_STARTPOS | B.WANT_LEV)
             want = oracle.oracle_calc_breakscore(contigs, reads, truth, kmer, kmers, prob, want_ks=False, want_lev=True, want_prob_dist=False)
             assert np.array_equal(got["path_prob_dist_startpos"], want["path_prob_dist_startpos"]), (env, name)
@@ -514,4 +556,4 @@ def check_startpos_geometries(scorer, oracle, kmers, prob, monkeypatch, **kw):
 
 
 def test_startpos_table_geometries(emul_scorer, oracle, kmers, prob, monkeypatch):
-    check_startpos_geometries(emul_scorer, oracle, kmers, prob, monkeypatch)
+    check_startpos_geometries(emul_scorer, oracle, kmers, prob, monkeypatch, n_contigs=1200, L=6000)

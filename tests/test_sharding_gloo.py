@@ -124,3 +124,44 @@ def test_contig_sharding_reads_replicated(world, emul_lib):
         p.join(timeout=180)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _read_shard_worker(rank, world, port, q, emul_lib):
+    """cfg-5 shape: the READS sharded, position weights all-reduced (gloo here, NCCL on the GPUs), contig ranges scored
+    from the sum.  Kernels under the CPU emulation."""
+    from genomeassembler_dev_b200 import breakscore
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kmers, prob = tables.all_kmer_strings(), tables.normalised(tables.load_raw())
+    b = synth.make_batch(1, seed=12, length=3000, read_len=40, coverage=8, contigs_lo=7, contigs_hi=7)
+    ctgs = [b.contig_chars[b.contig_off[c]:b.contig_off[c + 1]].tobytes() for c in range(b.n_contigs)]
+    reads = b.read_chars.reshape(-1, b.read_len)
+    truth = b.truth_chars.tobytes()
+    sc = breakscore.BreakageScorer(0, emul_lib)
+    sc.set_table(kmers, prob)
+    n = len(reads)
+    mine = reads[n * rank // world:n * (rank + 1) // world]
+    got = sharding.score_reads_sharded(sc, ctgs, mine, truth, kmer=8, flags=breakscore.DEFAULT_FLAGS)
+    if rank == 0:
+        whole = sc.score(ctgs, reads, truth, kmer=8, flags=breakscore.DEFAULT_FLAGS)
+        ok = all(np.array_equal(np.asarray(got[k], dtype=np.float64), np.asarray(whole[k], dtype=np.float64), equal_nan=True)
+                 for k in sharding.RECORD_F64 + sharding.RECORD_I32)
+        q.put(bool(ok))
+    else:
+        assert got is None
+    sc.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_read_sharding_weights_all_reduced(world, emul_lib):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_read_shard_worker, args=(r, world, port, q, emul_lib)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

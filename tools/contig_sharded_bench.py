@@ -307,6 +307,81 @@ def measure(bench, rig, sh, steps, warmup, sample=None, expected=None, host_read
     return out
 
 
+def measure_read_sharded(bench, rig, sh, steps, warmup, timing=True):
+    """The other split of the same segment (sharding.score_reads_sharded on device-resident inputs): every rank packs,
+    indexes and places 1/N of the READS against ALL contigs, the position weights are all-reduced over NCCL (the path's
+    one real data exchange: int32, sum(L_c) + C entries), every rank scores a contiguous range of the contigs from the
+    sum, the records are all-gathered.  Bit-identical to the contig-sharded table (additivity of the break counts)."""
+    torch, dist, B, sc = rig.torch, rig.dist, rig.B, rig.sc
+    world, rank, dev = rig.world, rig.rank, rig.dev
+    lens = np.fromiter((len(c) for c in sh.contigs), dtype=np.int64, count=len(sh.contigs))
+    ct, ct_off = B.flatten(sh.contigs)
+    d_ct = torch.from_numpy(ct).to(dev)
+    C = len(sh.contigs)
+    bounds = sharding.balanced_ranges(lens, world)
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    counts = [bounds[r + 1] - bounds[r] for r in range(world)]
+    pad = max(max(counts), 1)
+    n0, n1 = sh.n_reads * rank // world, sh.n_reads * (rank + 1) // world
+    w = torch.zeros(int(ct_off[-1]) + C + 1, dtype=torch.int32, device=dev)
+    tot = torch.zeros(C + 1, dtype=torch.int32, device=dev)
+    f64 = torch.zeros(5, pad, dtype=torch.float64, device=dev)
+    i32 = torch.zeros(3, pad, dtype=torch.int32, device=dev)
+    g_f64 = torch.zeros(world, 5, pad, dtype=torch.float64, device=dev)
+    g_i32 = torch.zeros(world, 3, pad, dtype=torch.int32, device=dev)
+    tr_off = sh.tr_off
+    srs1, scs1 = np.array([0, n1 - n0], np.int64), np.array([0, C], np.int64)
+    srs2, scs2 = np.array([0, 0], np.int64), np.array([0, c1 - c0], np.int64)
+    off2 = np.ascontiguousarray(ct_off[c0:c1 + 1] - ct_off[c0])
+    b1 = B._Batch(1, n1 - n0, C, sh.d_reads.data_ptr() + n0 * READ_LEN, None, READ_LEN, d_ct.data_ptr(), ct_off.ctypes.data,
+                  sh.d_truth.data_ptr(), tr_off.ctypes.data, srs1.ctypes.data, scs1.ctypes.data)
+    r1 = B._Result()
+    r1.weights, r1.weights_total = w.data_ptr(), tot.data_ptr()
+    b2 = B._Batch(1, 0, c1 - c0, None, None, READ_LEN, d_ct.data_ptr() + int(ct_off[c0]), off2.ctypes.data,
+                  sh.d_truth.data_ptr(), tr_off.ctypes.data, srs2.ctypes.data, scs2.ctypes.data)
+    r2 = sh.result_struct(f64, i32)
+    r2.weights, r2.weights_total = w.data_ptr() + 4 * (int(ct_off[c0]) + c0), tot.data_ptr() + 4 * c0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step():
+        ev[0].record()
+        sc.score_batch_raw(b1, r1, 8, B.DEVICE_CHARS | B.WEIGHTS_OUT)
+        ev[1].record()
+        if world > 1:
+            dist.all_reduce(w)
+            dist.all_reduce(tot)
+        ev[2].record()
+        if c1 > c0:
+            sc.score_batch_raw(b2, r2, 8, sh.flags | B.DEVICE_CHARS | B.DEVICE_RESULT | B.WEIGHTS_IN)
+        if world > 1:
+            dist.all_gather_into_tensor(g_f64.view(-1), f64.view(-1))
+            dist.all_gather_into_tensor(g_i32.view(-1), i32.view(-1))
+        else:
+            g_f64[0].copy_(f64)
+            g_i32[0].copy_(i32)
+        ev[3].record()
+
+    ms = rig.time_device(step, steps if timing else 1, warmup if timing else 1)
+    rig.sync()
+    phases = [rig.max_over_ranks(ev[i].elapsed_time(ev[i + 1])) for i in range(3)]
+    tf = torch.cat([g_f64[r, :, :counts[r]] for r in range(world)], dim=1).t().contiguous()
+    ti = torch.cat([g_i32[r, :, :counts[r]] for r in range(world)], dim=1).t().contiguous()
+    rf, ri = sh.table_in_input_order()
+    out = {"same_table_as_contig_sharded": bool(torch.equal(tf.nan_to_num(nan=-1.0), rf.nan_to_num(nan=-1.0)) and torch.equal(ti, ri)),
+           "reads_per_rank": int(n1 - n0), "contigs_scored_per_rank": counts,
+           "all_reduce_bytes": int(w.numel() * 4 + tot.numel() * 4),
+           "what": "reads sharded: phase 1 = pack + index + place this rank's reads in ALL contigs (BS_WEIGHTS_OUT); all-reduce of the "
+                   "int32 position weights over NCCL; phase 2 = score a contiguous contig range from the sum (BS_WEIGHTS_IN); records "
+                   "all-gathered"}
+    if timing:
+        pair = float(sh.n_reads) * sh.bases
+        out.update({"ms_per_step": ms, "value": pair / 1e9 / (ms / 1e3), "unit": bench.UNIT,
+                    "last_step_ms_max_over_ranks": {"phase1_pack_index_place": phases[0], "all_reduce_weights": phases[1],
+                                                    "phase2_score_and_gather": phases[2]}})
+    del w, tot, d_ct
+    return out
+
+
 def cfg5_device(rig, p, seed=1500):
     """cfg-5 on the device: truth, reads (uniform starts), contigs (substrings, a fraction with one substitution) and the
     generator's ground truth for kmer_breaks / startpos of every contig"""
@@ -380,6 +455,7 @@ def run_gpu_side(bench, rig, plan):
                 res["cpu_baseline"] = plan["cpu_cfg4"]
         else:
             res["workload"] = "cfg5 shape at 1 Mb truth / 3e5 reads / 1000 contigs (5 % mutated): parity only, the CPU oracle sees every read"
+            res["read_sharded"] = measure_read_sharded(bench, rig, sh, steps, warmup, timing=False)
         out[key] = res
         del sh, d_reads, d_truth
         torch.cuda.empty_cache()
@@ -414,6 +490,7 @@ def run_gpu_side(bench, rig, plan):
         h_truth = torch.empty(g["d_truth"].numel(), dtype=torch.uint8, pin_memory=True)
         h_truth.copy_(g["d_truth"])
     res = measure(bench, rig, sh, steps, warmup, host_reads=h_reads, host_truth=h_truth, timing=True)
+    res["read_sharded"] = measure_read_sharded(bench, rig, sh, steps, warmup)
     if not enough:
         res["e2e"] = {"skipped": f"host MemAvailable {avail / 1e9:.0f} GB < {need / 1e9:.0f} GB needed to pin the reads on {world} rank(s)"}
     # ground truth of the generator for ALL contigs (kmer_breaks, startpos), on the gathered table
