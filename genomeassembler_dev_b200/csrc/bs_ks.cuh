@@ -274,29 +274,38 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
         // positions (they never straddle a 32-base word boundary), so the contig words are
         // loaded once per four windows; the four table gathers are in flight together ----
         for (int64_t p0 = 0; p0 < nwin; p0 += 4 * (int64_t)nthr) {
-            const int64_t pb = p0 + 4 * (int64_t)tid;
+            // a WARP takes 128 consecutive positions, lane l the positions 32 u + l of them (u = 0..3): the contig
+            // words of a step are the same for every lane (one broadcast load), the four table gathers of a thread
+            // are in flight together and the 8-byte results of a step go out as one coalesced 256-byte store
+            const int64_t base = p0 + 128 * (int64_t)warp;
             double val[4];
             int32_t rk[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) { val[u] = 0.0; rk[u] = a.rank_zero; }
-            if (pb < nwin && a.win) {
-                const int64_t wi = pb >> 5;
-                const uint32_t o = (uint32_t)(pb & 31);  // multiple of 4: o + 3 <= 31
-                const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
-                const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
+            if (base < nwin && a.win) {
+                const int64_t wi = base >> 5;
+                uint64_t w0 = __ldg(&gw[wi]);
+                uint32_t m0 = __ldg(&gm[wi]);
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) {
-                        const WinEntry e = a.win[window64(w0, w1, o + u) >> kshift];  // one 16-byte gather
-                        val[u] = e.prob;
-                        rk[u] = e.rank;
+                    if (base + 32 * u < nwin) {  // (warp-uniform: the next word exists, strings carry two pad words)
+                        const uint64_t w1 = __ldg(&gw[wi + u + 1]);
+                        const uint32_t m1 = __ldg(&gm[wi + u + 1]);
+                        if (base + 32 * u + lane < nwin && !(window32(m0, m1, (uint32_t)lane) & kbits)) {
+                            const WinEntry e = a.win[window64(w0, w1, (uint32_t)lane) >> kshift];  // one 16-byte gather
+                            val[u] = e.prob;
+                            rk[u] = e.rank;
+                        }
+                        w0 = w1;
+                        m0 = m1;
                     }
                 }
             }
+            const int64_t pb = base + lane;  // this thread's positions: pb + 32 u
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (pb + u < nwin) {
-                    if (pd) pd[pb + u] = val[u];
+                if (pb + 32 * u < nwin) {
+                    if (pd) pd[pb + 32 * u] = val[u];
                     if (want_ks) {
                         const int lw = hist_logical_word<PACKED>(rk[u]);
                         atomicAdd(&s_hist[lw + (lw >> 5)], PACKED ? 1u << (16 * (rk[u] & 1)) : 1u);
@@ -423,30 +432,37 @@ __global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDis
         const int64_t n_y = a.R_y > 0 ? a.ycum[seg * a.R_y + a.R_y - 1] : 0;
         // ---- windows: table value out, rank kept, per-range counts ----
         for (int p0 = 0; p0 < nwin; p0 += 4 * nthr) {
-            const int pb = p0 + 4 * tid;
+            // (same mapping as k_prob_dist_ks: a warp takes 128 consecutive positions, lane l the positions 32 u + l)
+            const int base = p0 + 128 * warp;
             double val[4];
             int32_t rk[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) { val[u] = 0.0; rk[u] = a.rank_zero; }
-            if (pb < nwin && a.win) {
-                const int wi = pb >> 5;
-                const uint32_t o = (uint32_t)(pb & 31);
-                const uint64_t w0 = __ldg(&gw[wi]), w1 = __ldg(&gw[wi + 1]);
-                const uint32_t m0 = __ldg(&gm[wi]), m1 = __ldg(&gm[wi + 1]);
+            if (base < nwin && a.win) {
+                const int wi = base >> 5;
+                uint64_t w0 = __ldg(&gw[wi]);
+                uint32_t m0 = __ldg(&gm[wi]);
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (pb + u < nwin && !(window32(m0, m1, o + u) & kbits)) {
-                        const WinEntry e = a.win[window64(w0, w1, o + u) >> kshift];
-                        val[u] = e.prob;
-                        rk[u] = e.rank;
+                    if (base + 32 * u < nwin) {
+                        const uint64_t w1 = __ldg(&gw[wi + u + 1]);
+                        const uint32_t m1 = __ldg(&gm[wi + u + 1]);
+                        if (base + 32 * u + lane < nwin && !(window32(m0, m1, (uint32_t)lane) & kbits)) {
+                            const WinEntry e = a.win[window64(w0, w1, (uint32_t)lane) >> kshift];
+                            val[u] = e.prob;
+                            rk[u] = e.rank;
+                        }
+                        w0 = w1;
+                        m0 = m1;
                     }
                 }
             }
+            const int pb = base + lane;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (pb + u < nwin) {
-                    if (pd) pd[pb + u] = val[u];
-                    s_rank[pb + u] = (uint32_t)rk[u];
+                if (pb + 32 * u < nwin) {
+                    if (pd) pd[pb + 32 * u] = val[u];
+                    s_rank[pb + 32 * u] = (uint32_t)rk[u];
                     atomicAdd(&s_cur[rk[u] >> 6], 1u);
                 }
             }
