@@ -152,9 +152,8 @@ struct bs_ctx {
     // scratch shared by all chunks (kernels of different chunks never overlap: one compute stream)
     DevBuf d_best, d_hits_ovf, d_keys, d_scratch, d_ovf, d_status, d_rank_scratch, d_counters, d_hbuf;
     DevBuf sim_meta, sim_chars, sim_words, sim_mask, sim_cdf, sim_starts, sim_kept, sim_reads;  // bs_simulate_reads
-    size_t best_elems = 0;       // 4-byte elements of d_best
-    int best_mode = 0;           // what d_best holds: 0 nothing, 1 dense (generation, position) rows, 2 the hashed scratch
-    uint32_t place_gen = 0;      // dense rows: generation of the next launch's first work item (decreasing)
+    size_t best_elems = 0;
+    bool best_dirty = true;
 
     bool status_pending = false;  // a device-result call wanted KS-B: d_status has not been read since
     // pinned staging of this context's share of the contigs in bs_score_multi (grow-only; a pageable std::vector
@@ -825,25 +824,19 @@ int ChunkRun::place() {
             pa.pos = o_pos; pa.pos_off = d_pos_off;
             pa.hit_cap = kHitCap; pa.keys = nullptr; pa.overflow = nullptr;
             if (!hashed) {
-                // one 8-byte (generation, leftmost position) entry per read of the largest segment and resident block;
-                // generations only ever decrease, so the rows are cleared when they are (re)allocated, after the hashed
-                // variant used the buffer, or when the 32-bit generation space runs out -- not per launch
                 const size_t need = (size_t)nblk * (size_t)dense_stride;
-                const size_t dense_smem = bs::place_index_smem_bytes(0, kPlaceIxThreads);
-                if (need * 2 > ctx->best_elems || ctx->best_mode != 1 || ctx->place_gen < (uint32_t)C + 2u) {
-                    const size_t elems = std::max(need * 2, ctx->best_elems);  // (best_elems counts 4-byte elements)
+                if (need > ctx->best_elems || ctx->best_dirty) {
+                    const size_t elems = std::max(need, ctx->best_elems);
                     BS_TRY(ensure(ctx, ctx->d_best, elems * 4));
                     ctx->best_elems = elems;
-                    BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0xff, elems * 4, st));
-                    ctx->best_mode = 1;
-                    ctx->place_gen = 0xfffffffeu;
+                    BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
                 }
-                pa.best = nullptr; pa.best64 = (unsigned long long *)ctx->d_best.p; pa.best_stride = dense_stride;
-                pa.gen_base = ctx->place_gen;
-                ctx->place_gen -= (uint32_t)C;
-                pa.hits_ovf = nullptr; pa.hit_cap = 0;
-                BS_CUDA(cudaFuncSetAttribute(bs::k_place_index<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem));
-                BS_LAUNCH(bs::k_place_index<false>, (unsigned)nblk, kPlaceIxThreads, dense_smem, st, pa);
+                BS_TRY(ensure(ctx, ctx->d_hits_ovf, need * 4));
+                ctx->best_dirty = true;  // cleared when the call ends without an error
+                pa.best = (uint32_t *)ctx->d_best.p; pa.best_stride = dense_stride;
+                pa.hits_ovf = (uint32_t *)ctx->d_hits_ovf.p;
+                BS_CUDA(cudaFuncSetAttribute(bs::k_place_index<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                BS_LAUNCH(bs::k_place_index<false>, (unsigned)nblk, kPlaceIxThreads, smem, st, pa);
                 ctx->launches++;
             } else {
                 // one huge segment (cfg-5: 10^8 reads): a dense row per resident block does not fit, so every
@@ -863,7 +856,7 @@ int ChunkRun::place() {
                     ctx->best_elems = std::max(elems, ctx->best_elems);
                     BS_TRY(ensure(ctx, ctx->d_hits_ovf, elems * 4));
                     BS_TRY(ensure(ctx, ctx->d_keys, elems * 4));
-                    ctx->best_mode = 2;
+                    ctx->best_dirty = true;
                     BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
                     BS_CUDA(cudaMemsetAsync(ctx->d_keys.p, 0, elems * 4, st));
                     BS_CUDA(cudaMemsetAsync(d_overflow, 0, 4, st));
@@ -1674,6 +1667,7 @@ static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t f
         // asynchronous: the caller orders later work on the compute stream.  The workspaces stay marked
         // in flight: whoever takes one next (this call's successor included) first waits for the event
         // recorded behind its last kernel, so staging memory is never rewritten under a running chunk.
+        ctx->best_dirty = false;
         if (any_ksb) ctx->status_pending = true;  // read by bs_ctx_synchronize / the next host-result call
         return BS_OK;
     }
@@ -1682,6 +1676,7 @@ static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t f
     ctx->status_pending = false;
     BS_TRY(sync_all(ctx));
     for (Workspace &w : ctx->ws) w.in_flight = false;
+    ctx->best_dirty = false;
     if (res->lev_dist_vs_true && !e.want_lev) std::memset(res->lev_dist_vs_true, 0, (size_t)C * 4);
     if (!e.want_sp && res->path_prob_dist_startpos) std::memset(res->path_prob_dist_startpos, 0, (size_t)C * 4);
     if (status) return fail(ctx, BS_ERR_INVALID, "ks_stat_path_freq: more than %d table rows with a count >= %d in one contig", bs::OVF_CAP, bs::CC_DENSE);

@@ -191,11 +191,7 @@ struct PlaceIxArgs {
     const int32_t *ctg_seg;
     ReadSet reads;
     ReadIndex ix;
-    uint32_t *best;       // HASHED: [gridDim][best_stride] open-addressed positions, all POS_INF on entry and on exit
-    unsigned long long *best64;  // dense: [gridDim][best_stride] (generation << 32 | leftmost position) per read of the segment;
-                          // a block's contigs carry DEcreasing generations (gen_base - item), so an entry of an earlier contig
-                          // (or launch) compares larger than anything the current contig writes: no clean-up between contigs
-    uint32_t gen_base;    // dense: generation of work item 0 of this launch (the host lowers it by n_items per launch)
+    uint32_t *best;       // [gridDim][best_stride], all POS_INF on entry and on exit
     int64_t best_stride;  // >= reads of the largest segment
     int32_t *w;           // position weights: contig c, position p at ctg_off[c] + c + p
     int32_t *total;       // [C] reads placed (kmer_breaks)
@@ -281,9 +277,8 @@ __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_ind
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     // every warp queues and verifies its own candidates: no block barrier inside the position loop
     uint2 *s_cand = (uint2 *)(s_hits + a.hit_cap) + warp * PLACE_CAND_CAP;  // (read id, contig position) with an equal seed tag
-    uint32_t *best = HASHED ? a.best + (int64_t)blockIdx.x * a.best_stride : nullptr;
-    unsigned long long *best64 = HASHED ? nullptr : a.best64 + (int64_t)blockIdx.x * a.best_stride;
-    uint32_t *hits_ovf = HASHED ? a.hits_ovf + (int64_t)blockIdx.x * a.best_stride : nullptr;
+    uint32_t *best = a.best + (int64_t)blockIdx.x * a.best_stride;
+    uint32_t *hits_ovf = a.hits_ovf + (int64_t)blockIdx.x * a.best_stride;
     uint32_t *keys = HASHED ? a.keys + (int64_t)blockIdx.x * a.best_stride : nullptr;
     const uint32_t smask = (uint32_t)a.best_stride - 1u;
     const int fill_max = (int)(a.best_stride >> 1);
@@ -315,33 +310,17 @@ __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_ind
         const uint64_t keepS = keep_bases(S);
         const uint32_t keepSm = keep_bits(S);
 
-        // the list of reads placed in this contig (hashed scratch only: table slots)
+        // the list of reads placed in this contig (dense: local read ids; hashed: table slots)
         auto remember = [&](uint32_t v) {
             const int slot = atomicAdd(&s_nhit, 1);
             if (slot < a.hit_cap) s_hits[slot] = v;
             else hits_ovf[slot - a.hit_cap] = v;
         };
-        const uint32_t gen = a.gen_base - (uint32_t)item;
-        int placed_here = 0;  // dense: reads this thread saw first in this contig
-        int32_t *wc = a.w + coff + c;
         // read nl (local id) occurs at position p: keep the leftmost position
         auto record = [&](uint32_t nl, uint32_t p) {
             if constexpr (!HASHED) {
-                // the weight moves with the minimum: whoever lowers a read's entry takes the count from the position it
-                // replaces (atomicMin returns it), so w holds exactly one count per placed read at its leftmost position
-                // whatever the order of the occurrences -- no pass over the placed reads afterwards
-                const unsigned long long key = ((unsigned long long)gen << 32) | p;
-                const unsigned long long old = atomicMin(&best64[nl], key);
-                if ((uint32_t)(old >> 32) != gen) {  // first time this read is seen in this contig
-                    atomicAdd(&wc[p], 1);
-                    placed_here++;
-                } else if (p < (uint32_t)old) {
-                    atomicAdd(&wc[(uint32_t)old], -1);
-                    atomicAdd(&wc[p], 1);
-                } else {
-                    return;
-                }
-                if (a.pos) atomicMin(reinterpret_cast<unsigned *>(a.pos + a.pos_off[c]) + nl, p);  // (-1 = all ones = no match yet)
+                const uint32_t old = atomicMin(&best[nl], p);
+                if (old == POS_INF) remember(nl);  // first time this read is seen in this contig
             } else {
                 // at most fill_max (+ one per thread in flight) of the 2 * fill_max slots are ever taken, so
                 // the probe ends; all table traffic is atomic (L2), nothing stale out of the L1
@@ -420,18 +399,13 @@ __global__ void __launch_bounds__(PLACE_IX_THREADS, PLACE_IX_BLOCKS) k_place_ind
                 if (i % nthr != tid) continue;
                 const int64_t p = find_bytes(cc, L, a.reads.chars + read_begin(a.reads, n), read_length(a.reads, n));
                 if (p < 0) continue;
-                if constexpr (!HASHED) {  // each such read is visited by exactly one thread, find_bytes gave its leftmost position
-                    atomicAdd(&wc[p], 1);
-                    placed_here++;
-                    if (a.pos) a.pos[a.pos_off[c] + (n - r0)] = (int32_t)p;
+                if constexpr (!HASHED) {
+                    best[n - r0] = (uint32_t)p;  // each such read is visited by exactly one thread
+                    remember((uint32_t)(n - r0));
                 } else {
                     record((uint32_t)(n - r0), (uint32_t)p);
                 }
             }
-        }
-        if constexpr (!HASHED) {  // nothing to clean up, nothing to wait for: the next item's barrier is the only one
-            if (placed_here) atomicAdd(&a.total[c], placed_here);
-            continue;
         }
         __threadfence_block();
         __syncthreads();

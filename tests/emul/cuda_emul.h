@@ -183,11 +183,6 @@ inline unsigned atomicMin(unsigned *p, unsigned v) {
     while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return old;
 }
-inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
-    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
-    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
-    return old;
-}
 inline int atomicMax(int *p, int v) {
     int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
     while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
