@@ -46,13 +46,24 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t &diff);
 __global__ void k_pack_seqs(SeqSet s) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t total_chars = s.n > 0 ? s.off[s.n] : 0;
-    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < s.total_words; wi += stride) {
-        // string owning word wi: largest i with woff[i] <= wi
-        int64_t lo = 0, hi = s.n - 1;
-        while (lo < hi) {
-            int64_t mid = (lo + hi + 1) >> 1;
-            if (s.woff[mid] <= wi) lo = mid; else hi = mid - 1;
+    __shared__ int64_t s_first;  // string owning the block's first word of the current round
+    for (int64_t wb = (int64_t)blockIdx.x * blockDim.x; wb < s.total_words; wb += stride) {
+        // string owning word wi: largest i with woff[i] <= wi.  One binary search per block and round (its first word),
+        // then every thread walks forward from there: a block's 256 words span a handful of strings
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t lo = 0, hi = s.n - 1;
+            while (lo < hi) {
+                int64_t mid = (lo + hi + 1) >> 1;
+                if (s.woff[mid] <= wb) lo = mid; else hi = mid - 1;
+            }
+            s_first = lo;
         }
+        __syncthreads();
+        const int64_t wi = wb + threadIdx.x;
+        if (wi >= s.total_words) continue;
+        int64_t lo = s_first;
+        while (lo + 1 < s.n && s.woff[lo + 1] <= wi) lo++;
         const int64_t c0 = s.off[lo];
         const int64_t L = s.off[lo + 1] - c0;
         const int64_t b0 = (wi - s.woff[lo]) * 32;
@@ -430,7 +441,13 @@ inline void mbar_wait(uint64_t *, uint32_t) {}
 
 constexpr int PACKB_THREADS = 256;
 constexpr int PACKB_STAGES = 3;              // bulk copies in flight per block: tiles t+1 and t+2 while tile t is converted
-constexpr int PACKB_TILE_BYTES = 12 * 1024;  // target ASCII bytes per tile
+#ifndef BS_PACKB_TILE_KB
+#define BS_PACKB_TILE_KB 16
+#endif
+#ifndef BS_PACKB_BLOCKS
+#define BS_PACKB_BLOCKS 3
+#endif
+constexpr int PACKB_TILE_BYTES = BS_PACKB_TILE_KB * 1024;  // target ASCII bytes per tile
 constexpr int PACKB_MAX_STAGE = 20 * 1024;   // longest reads the staged kernel takes: 16 of them must fit a stage
 
 // reads per tile for reads of L bytes: a multiple of 4 whose byte count is a multiple of 16, at most one per thread
@@ -486,7 +503,7 @@ __device__ __forceinline__ void packb_cut_any(const uint2 *cell, int ci, uint32_
     }
 }
 
-__global__ void __launch_bounds__(PACKB_THREADS, 4) k_pack_reads_bulk(ReadSet r, ReadIndex ix, int R) {
+__global__ void __launch_bounds__(PACKB_THREADS, BS_PACKB_BLOCKS) k_pack_reads_bulk(ReadSet r, ReadIndex ix, int R) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int L = r.uniform_len;
     const int W = r.W;
