@@ -178,6 +178,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
         const int32_t total = a.total[c];
         const int64_t np = L > 0 ? L : 1;
         const bool in_smem = total <= HASH_LIMIT;  // (block-uniform) distinct break k-mers <= placed reads
+        // slots of the table this contig uses: a power of two >= 2 * total (so pass 2 sweeps what a small contig can
+        // have touched, not all HASH_SLOTS), all HASH_SLOTS for the largest contigs that still fit
+        int hs = 64;
+        while (hs < 2 * total && hs < HASH_SLOTS) hs <<= 1;
+        const uint32_t hmask = (uint32_t)hs - 1u;
         double s1 = 0.0, s2 = 0.0;
         // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS); four
         // positions per thread in flight so that the table gathers overlap
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
                                 // of the HASH_SLOTS slots are ever taken, so the probe ends.
                                 const uint32_t key = (uint32_t)di[u] + 1u;
                                 for (uint32_t h = (key * 2654435761u) >> 16;; h++) {
-                                    h &= (uint32_t)(HASH_SLOTS - 1);
+                                    h &= hmask;
                                     uint32_t cur = s_hash[h];
                                     if (cur == 0u) {
                                         cur = atomicCAS(&s_hash[h], 0u, (key << 15) | (uint32_t)wv[u]);
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
             }
         };
         if (in_smem) {  // the usual case: the hash table's slots, emptied on the way
-            for (int i = tid; i < HASH_SLOTS; i += nthr) {
+            for (int i = tid; i < hs; i += nthr) {
                 const uint32_t v = s_hash[i];
                 if (v != 0u) { s_hash[i] = 0u; tally((int32_t)(v & 0x7fffu)); }
             }
