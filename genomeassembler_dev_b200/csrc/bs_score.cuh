@@ -150,23 +150,215 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
     return t;
 }
 
-__global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(ScoreArgs a) {
-    __shared__ double s_w[32];
-    __shared__ int32_t s_cc[CC_DENSE];      // rows having count j
-    __shared__ uint32_t s_hash[HASH_SLOTS];  // (dense index + 1) << 15 | count, 0 = empty; all empty between contigs
-    __shared__ int s_item, s_novf, s_maxc, s_nz;
+// ---- the per-contig scoring state, shared by k_break_score and by the KS-A kernels when they score on the way
+// (bs_ks.cuh: with kmer == 8 the break k-mer of position p IS the rolling window p - 4, already gathered there) ----
+
+struct ScoreShared {
+    double w[32];
+    int32_t cc[CC_DENSE];        // rows having count j
+    uint32_t hash[HASH_SLOTS];   // (dense index + 1) << 15 | count, 0 = empty; all empty between contigs
+    int novf, maxc, nz;          // reset by thread 0 where the block fetches its next contig
+};
+
+struct ScoreState {
+    int32_t total;
+    bool in_smem;     // (block-uniform) distinct break k-mers <= placed reads <= HASH_LIMIT
+    int hs;           // slots of the table this contig uses: a power of two >= 2 * total (pass 2 sweeps what a small contig
+    uint32_t hmask;   // can have touched, not all HASH_SLOTS), all HASH_SLOTS for the largest contigs that still fit
+    double s1, s2;
+    int32_t *scratch, *ovf;
+};
+
+__device__ __forceinline__ void score_shared_init(const ScoreArgs &a, ScoreShared &sh) {  // once per kernel, before the first barrier
+    if (a.ks_b == nullptr) return;
+    for (int i = threadIdx.x; i < CC_DENSE; i += blockDim.x) sh.cc[i] = 0;
+    for (int i = threadIdx.x; i < HASH_SLOTS; i += blockDim.x) sh.hash[i] = 0u;
+}
+
+__device__ __forceinline__ void score_begin(const ScoreArgs &a, int64_t c, ScoreState &st) {
+    const bool want_ks = a.ks_b != nullptr;
+    st.total = a.total[c];
+    st.in_smem = st.total <= HASH_LIMIT;
+    st.hs = 64;
+    while (st.hs < 2 * st.total && st.hs < HASH_SLOTS) st.hs <<= 1;
+    st.hmask = (uint32_t)st.hs - 1u;
+    st.s1 = st.s2 = 0.0;
+    st.scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
+    st.ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
+}
+
+// wv reads broke the k-mer with dense index di (table entry te) in contig c
+__device__ __forceinline__ void score_add(const ScoreArgs &a, ScoreShared &sh, ScoreState &st, int64_t c, int di, double prob, int32_t row,
+                                          int32_t wv) {
+    if (row >= 0) {
+        st.s1 += prob * (double)wv;
+        st.s2 += prob * ((double)wv / (double)st.total);
+        if (a.ks_b != nullptr) {
+            if (st.in_smem) {
+                // distinct dense indices are distinct table rows: count per k-mer.  At most HASH_LIMIT
+                // of the HASH_SLOTS slots are ever taken, so the probe ends.
+                const uint32_t key = (uint32_t)di + 1u;
+                for (uint32_t h = (key * 2654435761u) >> 16;; h++) {
+                    h &= st.hmask;
+                    uint32_t cur = sh.hash[h];
+                    if (cur == 0u) {
+                        cur = atomicCAS(&sh.hash[h], 0u, (key << 15) | (uint32_t)wv);
+                        if (cur == 0u) break;
+                    }
+                    if ((cur >> 15) == key) { atomicAdd(&sh.hash[h], (uint32_t)wv); break; }
+                }
+            } else {
+                atomicAdd(&st.scratch[row], wv);
+            }
+        }
+    }
+    if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv);
+}
+
+// the generic form: position p of a contig of length L (any kmer, any position)
+__device__ __forceinline__ void score_add_position(const ScoreArgs &a, ScoreShared &sh, ScoreState &st, int64_t c, const uint64_t *gw,
+                                                   const uint32_t *gm, int64_t p, int64_t L, int32_t wv) {
+    const BreakWindow bw = break_window(p, a.kmer, L);
+    const int di = dense_index_at(gw, gm, bw.start, bw.len);
+    TabEntry te;
+    te.prob = 0.0;
+    te.row = -1;
+    if (di >= 0) te = a.tab[di];
+    score_add(a, sh, st, c, di, te.prob, te.row, wv);
+}
+
+// sums, outputs and the KS of the break histogram; every thread of the block calls it (barriers inside)
+__device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreShared &sh, ScoreState &st, int64_t c, int64_t L, const uint64_t *gw,
+                                             const uint32_t *gm, const int32_t *w) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const bool want_ks = a.ks_b != nullptr;
-    int32_t *scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
-    int32_t *ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    if (want_ks) {
-        for (int i = tid; i < CC_DENSE; i += nthr) s_cc[i] = 0;
-        for (int i = tid; i < HASH_SLOTS; i += nthr) s_hash[i] = 0u;
+    const int32_t total = st.total;
+    const int64_t np = L > 0 ? L : 1;
+    const double s1 = block_sum_fixed(st.s1, sh.w);
+    const double s2 = block_sum_fixed(st.s2, sh.w);
+    if (tid == 0) {
+        if (a.sequence_len) a.sequence_len[c] = (int32_t)L;
+        if (a.bp_score) a.bp_score[c] = s1;
+        if (a.norm_by_break_freqs) a.norm_by_break_freqs[c] = s2;
+        if (a.norm_by_len) a.norm_by_len[c] = s1 / (double)(int32_t)L;
+        if (a.kmer_breaks) a.kmer_breaks[c] = total;
     }
+    if (!want_ks) return;
+    if (total == 0) {  // 0/0 for every row: R drops the NaNs and ks.test stops on empty x
+        if (tid == 0) a.ks_b[c] = qnan;
+        return;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // pass 2: tally rows per count value
+    auto tally = [&](int32_t cnt) {
+        if (cnt == 0) return;
+        atomicAdd(&sh.nz, 1);
+        if (cnt < CC_DENSE) { atomicAdd(&sh.cc[cnt], 1); atomicMax(&sh.maxc, cnt); }
+        else {
+            const int slot = atomicAdd(&sh.novf, 1);
+            if (slot < OVF_CAP) st.ovf[slot] = cnt; else *a.status = 1;
+        }
+    };
+    if (st.in_smem) {  // the usual case: the hash table's slots, emptied on the way
+        for (int i = tid; i < st.hs; i += nthr) {
+            const uint32_t v = sh.hash[i];
+            if (v != 0u) { sh.hash[i] = 0u; tally((int32_t)(v & 0x7fffu)); }
+        }
+    } else
+    // whoever swaps a row's count out of the scratch first owns it
+    for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
+        int32_t wv[4], row[4], cnt[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t p = p0 + (int64_t)u * nthr + tid;
+            wv[u] = p < np ? w[p] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            row[u] = -1;
+            if (wv[u] != 0) {
+                const BreakWindow bw = break_window(p0 + (int64_t)u * nthr + tid, a.kmer, L);
+                const int di = dense_index_at(gw, gm, bw.start, bw.len);
+                if (di >= 0) row[u] = a.tab[di].row;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) cnt[u] = row[u] >= 0 ? atomicExch(&st.scratch[row[u]], 0) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) tally(cnt[u]);
+    }
+    __syncthreads();
+    // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them
+    if (tid == 0) {
+        const int32_t *ycum = a.ycum + (int64_t)a.ctg_seg[c] * a.R_y;
+        const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
+        const int novf = sh.novf < OVF_CAP ? sh.novf : OVF_CAP;
+        const int32_t *ovf = st.ovf;
+        double d = 0.0;
+        if (n_y > 0 && a.T > 0) {
+            const double inx = (double)a.T, iny = (double)n_y;
+            int64_t run = (int64_t)a.T - sh.nz;  // rows never broken: x value 0
+            if (run > 0) {
+                const double le = a.zero_le >= 0 ? (double)ycum[a.zero_le] : 0.0;
+                const double lt = a.zero_lt >= 0 ? (double)ycum[a.zero_lt] : 0.0;
+                double d1 = lt / iny, d2 = (double)run / inx - le / iny;
+                if (d1 < 0) d1 = -d1;
+                if (d2 < 0) d2 = -d2;
+                d = d1 > d2 ? d1 : d2;
+            }
+            for (int j = 1; j <= sh.maxc; j++) {
+                const int32_t cnt = sh.cc[j];
+                if (cnt == 0) continue;
+                sh.cc[j] = 0;
+                double le, lt;
+                y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)j / (double)total, &le, &lt);
+                double d1 = (double)run / inx - lt / iny;
+                run += cnt;
+                double d2 = (double)run / inx - le / iny;
+                if (d1 < 0) d1 = -d1;
+                if (d2 < 0) d2 = -d2;
+                if (d1 > d) d = d1;
+                if (d2 > d) d = d2;
+            }
+            // counts >= CC_DENSE: few; walked in ascending order
+            int32_t last = CC_DENSE - 1;
+            for (int done = 0; done < novf;) {
+                int32_t cur = 0x7fffffff;
+                int mult = 0;
+                for (int i = 0; i < novf; i++) {
+                    const int32_t v = ovf[i];
+                    if (v > last && v < cur) { cur = v; mult = 1; }
+                    else if (v == cur) mult++;
+                }
+                double le, lt;
+                y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)cur / (double)total, &le, &lt);
+                double d1 = (double)run / inx - lt / iny;
+                run += mult;
+                double d2 = (double)run / inx - le / iny;
+                if (d1 < 0) d1 = -d1;
+                if (d2 < 0) d2 = -d2;
+                if (d1 > d) d = d1;
+                if (d2 > d) d = d2;
+                last = cur;
+                done += mult;
+            }
+        } else {
+            for (int j = 1; j <= sh.maxc; j++) sh.cc[j] = 0;
+        }
+        a.ks_b[c] = (n_y > 0 && a.T > 0) ? d : qnan;
+    }
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(ScoreArgs a) {
+    __shared__ ScoreShared sh;
+    __shared__ int s_item;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    score_shared_init(a, sh);
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_novf = 0; s_maxc = 0; s_nz = 0; }
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); sh.novf = 0; sh.maxc = 0; sh.nz = 0; }
         __syncthreads();
         if (s_item >= a.n_contigs) break;
         const int64_t c = a.order[s_item];
@@ -175,18 +367,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
         const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
         const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
         const int32_t *w = a.w + coff + c;
-        const int32_t total = a.total[c];
         const int64_t np = L > 0 ? L : 1;
-        const bool in_smem = total <= HASH_LIMIT;  // (block-uniform) distinct break k-mers <= placed reads
-        // slots of the table this contig uses: a power of two >= 2 * total (so pass 2 sweeps what a small contig can
-        // have touched, not all HASH_SLOTS), all HASH_SLOTS for the largest contigs that still fit
-        int hs = 64;
-        while (hs < 2 * total && hs < HASH_SLOTS) hs <<= 1;
-        const uint32_t hmask = (uint32_t)hs - 1u;
-        double s1 = 0.0, s2 = 0.0;
+        ScoreState st;
+        score_begin(a, c, st);
         // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS); four
         // positions per thread in flight so that the table gathers overlap
-        if (total != 0) {
+        if (st.total != 0) {
             for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
                 int32_t wv[4], di[4];
                 TabEntry te[4];
@@ -207,148 +393,11 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (wv[u] == 0) continue;
-                    const int32_t row = te[u].row;
-                    if (row >= 0) {
-                        s1 += te[u].prob * (double)wv[u];
-                        s2 += te[u].prob * ((double)wv[u] / (double)total);
-                        if (want_ks) {
-                            if (in_smem) {
-                                // distinct dense indices are distinct table rows: count per k-mer.  At most HASH_LIMIT
-                                // of the HASH_SLOTS slots are ever taken, so the probe ends.
-                                const uint32_t key = (uint32_t)di[u] + 1u;
-                                for (uint32_t h = (key * 2654435761u) >> 16;; h++) {
-                                    h &= hmask;
-                                    uint32_t cur = s_hash[h];
-                                    if (cur == 0u) {
-                                        cur = atomicCAS(&s_hash[h], 0u, (key << 15) | (uint32_t)wv[u]);
-                                        if (cur == 0u) break;
-                                    }
-                                    if ((cur >> 15) == key) { atomicAdd(&s_hash[h], (uint32_t)wv[u]); break; }
-                                }
-                            } else {
-                                atomicAdd(&scratch[row], wv[u]);
-                            }
-                        }
-                    }
-                    if (a.hist) atomicAdd(&a.hist[c * (int64_t)(a.T + 1) + (row >= 0 ? row : a.T)], wv[u]);
-                }
+                for (int u = 0; u < 4; u++)
+                    if (wv[u] != 0) score_add(a, sh, st, c, di[u], te[u].prob, te[u].row, wv[u]);
             }
         }
-        s1 = block_sum_fixed(s1, s_w);
-        s2 = block_sum_fixed(s2, s_w);
-        if (tid == 0) {
-            if (a.sequence_len) a.sequence_len[c] = (int32_t)L;
-            if (a.bp_score) a.bp_score[c] = s1;
-            if (a.norm_by_break_freqs) a.norm_by_break_freqs[c] = s2;
-            if (a.norm_by_len) a.norm_by_len[c] = s1 / (double)(int32_t)L;
-            if (a.kmer_breaks) a.kmer_breaks[c] = total;
-        }
-        if (!want_ks) continue;
-        if (total == 0) {  // 0/0 for every row: R drops the NaNs and ks.test stops on empty x
-            if (tid == 0) a.ks_b[c] = qnan;
-            continue;
-        }
-        __threadfence_block();
-        __syncthreads();
-        // pass 2: tally rows per count value
-        auto tally = [&](int32_t cnt) {
-            if (cnt == 0) return;
-            atomicAdd(&s_nz, 1);
-            if (cnt < CC_DENSE) { atomicAdd(&s_cc[cnt], 1); atomicMax(&s_maxc, cnt); }
-            else {
-                const int slot = atomicAdd(&s_novf, 1);
-                if (slot < OVF_CAP) ovf[slot] = cnt; else *a.status = 1;
-            }
-        };
-        if (in_smem) {  // the usual case: the hash table's slots, emptied on the way
-            for (int i = tid; i < hs; i += nthr) {
-                const uint32_t v = s_hash[i];
-                if (v != 0u) { s_hash[i] = 0u; tally((int32_t)(v & 0x7fffu)); }
-            }
-        } else
-        // whoever swaps a row's count out of the scratch first owns it
-        for (int64_t p0 = 0; p0 < np; p0 += 4 * (int64_t)nthr) {
-            int32_t wv[4], row[4], cnt[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int64_t p = p0 + (int64_t)u * nthr + tid;
-                wv[u] = p < np ? w[p] : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                row[u] = -1;
-                if (wv[u] != 0) {
-                    const BreakWindow bw = break_window(p0 + (int64_t)u * nthr + tid, a.kmer, L);
-                    const int di = dense_index_at(gw, gm, bw.start, bw.len);
-                    if (di >= 0) row[u] = a.tab[di].row;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) cnt[u] = row[u] >= 0 ? atomicExch(&scratch[row[u]], 0) : 0;
-#pragma unroll
-            for (int u = 0; u < 4; u++) tally(cnt[u]);
-        }
-        __syncthreads();
-        // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them
-        if (tid == 0) {
-            const int32_t *ycum = a.ycum + (int64_t)a.ctg_seg[c] * a.R_y;
-            const int64_t n_y = a.R_y > 0 ? ycum[a.R_y - 1] : 0;
-            const int novf = s_novf < OVF_CAP ? s_novf : OVF_CAP;
-            double d = 0.0;
-            if (n_y > 0 && a.T > 0) {
-                const double inx = (double)a.T, iny = (double)n_y;
-                int64_t run = (int64_t)a.T - s_nz;  // rows never broken: x value 0
-                if (run > 0) {
-                    const double le = a.zero_le >= 0 ? (double)ycum[a.zero_le] : 0.0;
-                    const double lt = a.zero_lt >= 0 ? (double)ycum[a.zero_lt] : 0.0;
-                    double d1 = lt / iny, d2 = (double)run / inx - le / iny;
-                    if (d1 < 0) d1 = -d1;
-                    if (d2 < 0) d2 = -d2;
-                    d = d1 > d2 ? d1 : d2;
-                }
-                for (int j = 1; j <= s_maxc; j++) {
-                    const int32_t cnt = s_cc[j];
-                    if (cnt == 0) continue;
-                    s_cc[j] = 0;
-                    double le, lt;
-                    y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)j / (double)total, &le, &lt);
-                    double d1 = (double)run / inx - lt / iny;
-                    run += cnt;
-                    double d2 = (double)run / inx - le / iny;
-                    if (d1 < 0) d1 = -d1;
-                    if (d2 < 0) d2 = -d2;
-                    if (d1 > d) d = d1;
-                    if (d2 > d) d = d2;
-                }
-                // counts >= CC_DENSE: few; walked in ascending order
-                int32_t last = CC_DENSE - 1;
-                for (int done = 0; done < novf;) {
-                    int32_t cur = 0x7fffffff;
-                    int mult = 0;
-                    for (int i = 0; i < novf; i++) {
-                        const int32_t v = ovf[i];
-                        if (v > last && v < cur) { cur = v; mult = 1; }
-                        else if (v == cur) mult++;
-                    }
-                    double le, lt;
-                    y_counts_at(a.yv, ycum, a.R_y, a.y_max, (double)cur / (double)total, &le, &lt);
-                    double d1 = (double)run / inx - lt / iny;
-                    run += mult;
-                    double d2 = (double)run / inx - le / iny;
-                    if (d1 < 0) d1 = -d1;
-                    if (d2 < 0) d2 = -d2;
-                    if (d1 > d) d = d1;
-                    if (d2 > d) d = d2;
-                    last = cur;
-                    done += mult;
-                }
-            } else {
-                for (int j = 1; j <= s_maxc; j++) s_cc[j] = 0;
-            }
-            a.ks_b[c] = (n_y > 0 && a.T > 0) ? d : qnan;
-        }
+        score_finish(a, sh, st, c, L, gw, gm, w);
     }
 }
 
