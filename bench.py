@@ -68,7 +68,7 @@ STAGE_LIMITER = {
     "place": "divergent gathers (L1 wavefronts) + dependent L2 round trips: bucket head -> chain entry -> packed read",
     "score": "divergent table gathers + shared-memory atomics",
     "truth_spectrum": "shared-memory atomics, output writes",
-    "prob_dist_ks": "divergent gathers (window table entry, truth counts)",
+    "prob_dist_ks": "divergent gathers (window table entry, truth counts); with kmer == 8 also the break scoring (position weights, KS-B hash)",
     "startpos": "shared-memory bitmap probes per truth position (issue)",
 }
 
@@ -420,6 +420,10 @@ def build_roofline(batch, ms, h2d_bytes, n_segments, all_pairs):
     peak, peak_src = measured_peak()
     comp = compulsory_stage_bytes(batch, h2d_bytes)
     traffic, traffic_src = load_traffic(n_segments)
+    if ms.get("score", 0.0) <= 0:  # kmer == 8: the KS-A kernels score on their way over the windows (no k_break_score launch)
+        comp["prob_dist_ks"] += comp.pop("score")
+        if traffic and traffic.get("score") and traffic.get("prob_dist_ks"):
+            traffic["prob_dist_ks"] += traffic.pop("score")
     stages = {}
     for k, b in comp.items():
         t = ms.get(k, 0.0)

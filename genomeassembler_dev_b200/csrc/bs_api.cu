@@ -321,7 +321,7 @@ int prepare_ks(bs_ctx *ctx, int kmer, KsCache &k, const std::vector<double> &xpr
         const bool in_table = in_range && ctx->row_dense[doff + c] >= 0;
         win[c].prob = in_table ? xprob_dense[doff + c] : 0.0;
         win[c].rank = rank_x[c];
-        win[c].pad = 0;
+        win[c].row = in_table ? ctx->row_dense[doff + c] : -1;
     }
     k.y_max = yv.empty() ? 0.0 : yv.back();
     k.zero_le = (int)(std::upper_bound(yv.begin(), yv.end(), 0.0) - yv.begin()) - 1;
@@ -425,6 +425,8 @@ struct ChunkRun {
     int pack();       // 2-bit packing of contigs, truths and reads (+ read index)
     int place();      // leftmost placement of every read in every contig of its segment
     int spectrum();   // truth-side distribution of the KS statistics
+    bool fused(int which) const;  // scores computed inside the KS-A kernels (kmer == 8, no dense histogram, those kernels run)
+    int score_args(int which, int64_t rows, bs::ScoreArgs &sa);  // k_break_score's arguments (rows: blocks that may use a scratch row)
     int score(int which);      // weighted sums, histogram, KS-B (which: 0 scoring table, 1 second table)
     int prob_dist(int which);  // path_prob_dist and KS-A
     int second_table();        // both again for the second table, from the same placement
@@ -941,37 +943,49 @@ int ChunkRun::spectrum() {
     return BS_OK;
 }
 
+bool ChunkRun::fused(int which) const {
+    const bool ksa = which ? o_ksa2 != nullptr : ks_a;
+    const char *env = std::getenv("BS_FUSE_SCORE");  // tests / tuning: 0 keeps k_break_score
+    return kmer == 8 && !e.want_hist && (e.want_pd || ksa) && !(env && env[0] == '0');
+}
+
+int ChunkRun::score_args(int which, int64_t rows, bs::ScoreArgs &sa) {
+    const KsCache &k = which ? ctx->ks2 : ctx->ks;
+    const bool ksb = which ? o_ksb2 != nullptr : ks_b;
+    std::memset(&sa, 0, sizeof(sa));
+    sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + (which ? 5 : 2);
+    sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_seg = d_ctg_seg;
+    sa.w = w_ptr; sa.total = total_ptr;
+    sa.tab = (const bs::TabEntry *)(which ? ctx->d_tab2.p : ctx->d_tab.p);
+    sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
+    if (which == 0) {
+        sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
+        sa.kmer_breaks = o_breaks; sa.hist = o_hist;
+    } else {  // lengths, break counts and the histogram do not depend on the table
+        sa.bp_score = o_score2; sa.norm_by_break_freqs = o_norm2; sa.norm_by_len = o_bylen2;
+    }
+    if (ksb) {
+        const size_t scratch_bytes = (size_t)rows * (T + 1) * 4;
+        if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
+            BS_TRY(ensure(ctx, ctx->d_scratch, scratch_bytes));
+            BS_CUDA(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, st));
+        }
+        BS_TRY(ensure(ctx, ctx->d_ovf, (size_t)rows * bs::OVF_CAP * 4));
+        sa.ks_b = which ? o_ksb2 : o_ksb; sa.yv = (const double *)k.yv.p; sa.ycum = (const int32_t *)ws.ycnt.p; sa.R_y = k.R_y;
+        sa.zero_le = k.zero_le; sa.zero_lt = k.zero_lt; sa.y_max = k.y_max;
+        sa.scratch = (int32_t *)ctx->d_scratch.p; sa.ovf_cnt = (int32_t *)ctx->d_ovf.p; sa.status = (int32_t *)ctx->d_status.p;
+    }
+    return BS_OK;
+}
+
 int ChunkRun::score(int which) {
+    if (fused(which)) return BS_OK;  // the KS-A kernels do it on their way over the windows
     {
         // scores (+ histogram, + KS of the normalised break histogram); after the truth spectrum
         StageTimer tm(ctx, ST_SCORE, st);
-        const KsCache &k = which ? ctx->ks2 : ctx->ks;
-        const bool ksb = which ? o_ksb2 != nullptr : ks_b;
         const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kBreakScoreThreads, 0));
         bs::ScoreArgs sa;
-        std::memset(&sa, 0, sizeof(sa));
-        sa.order = d_order; sa.work_counter = (int32_t *)ctx->d_counters.p + (which ? 5 : 2);
-        sa.ctg_off = d_ctg_off; sa.ctg_woff = d_ctg_woff; sa.ctg_words = cs.words; sa.ctg_mask = cs.mask; sa.ctg_seg = d_ctg_seg;
-        sa.w = w_ptr; sa.total = total_ptr;
-        sa.tab = (const bs::TabEntry *)(which ? ctx->d_tab2.p : ctx->d_tab.p);
-        sa.kmer = kmer; sa.T = (int32_t)T; sa.n_contigs = C;
-        if (which == 0) {
-            sa.sequence_len = o_len; sa.bp_score = o_score; sa.norm_by_break_freqs = o_norm; sa.norm_by_len = o_bylen;
-            sa.kmer_breaks = o_breaks; sa.hist = o_hist;
-        } else {  // lengths, break counts and the histogram do not depend on the table
-            sa.bp_score = o_score2; sa.norm_by_break_freqs = o_norm2; sa.norm_by_len = o_bylen2;
-        }
-        if (ksb) {
-            const size_t scratch_bytes = (size_t)nblk * (T + 1) * 4;
-            if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
-                BS_TRY(ensure(ctx, ctx->d_scratch, scratch_bytes));
-                BS_CUDA(cudaMemsetAsync(ctx->d_scratch.p, 0, ctx->d_scratch.cap, st));
-            }
-            BS_TRY(ensure(ctx, ctx->d_ovf, (size_t)nblk * bs::OVF_CAP * 4));
-            sa.ks_b = which ? o_ksb2 : o_ksb; sa.yv = (const double *)k.yv.p; sa.ycum = (const int32_t *)ws.ycnt.p; sa.R_y = k.R_y;
-            sa.zero_le = k.zero_le; sa.zero_lt = k.zero_lt; sa.y_max = k.y_max;
-            sa.scratch = (int32_t *)ctx->d_scratch.p; sa.ovf_cnt = (int32_t *)ctx->d_ovf.p; sa.status = (int32_t *)ctx->d_status.p;
-        }
+        BS_TRY(score_args(which, nblk, sa));
         BS_LAUNCH(bs::k_break_score, (unsigned)nblk, kBreakScoreThreads, 0, st, sa);
         ctx->launches++;
     }
@@ -1013,13 +1027,19 @@ int ChunkRun::prob_dist(int which) {
         // footprint; long ones keep the table-wide rank histogram
         const size_t small_smem = bs::ks_small_smem_bytes(k.R_x);
         const bool use_small = ksa && n_small > 0 && small_smem + 1024 <= ctx->smem_optin;
+        const bool fuse = fused(which);
+        auto small_kernel = fuse ? bs::k_prob_dist_ks_small<true> : bs::k_prob_dist_ks_small<false>;
+        int nb_small = 0;
+        if (use_small) {
+            BS_CUDA(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
+            nb_small = (int)std::min<int64_t>(n_small, (int64_t)ctx->sm_count * blocks_per_sm(small_kernel, bs::KS_SMALL_THREADS, small_smem));
+        }
+        std::memset(&pa.sc, 0, sizeof(pa.sc));
+        if (fuse) BS_TRY(score_args(which, std::max(nb_small, nblk), pa.sc));  // (a scratch row per block of the wider launch)
         if (use_small) {
             bs::ProbDistArgs ps = pa;
             ps.order = d_order_small; ps.n_contigs = n_small; ps.work_counter = (int32_t *)ctx->d_counters.p + (which ? 7 : 6);
-            BS_CUDA(cudaFuncSetAttribute(bs::k_prob_dist_ks_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
-            const int nb = (int)std::min<int64_t>(n_small, (int64_t)ctx->sm_count *
-                                                  blocks_per_sm(bs::k_prob_dist_ks_small, bs::KS_SMALL_THREADS, small_smem));
-            BS_LAUNCH(bs::k_prob_dist_ks_small, (unsigned)nb, bs::KS_SMALL_THREADS, small_smem, st, ps);
+            BS_LAUNCH(small_kernel, (unsigned)nb_small, bs::KS_SMALL_THREADS, small_smem, st, ps);
             ctx->launches++;
             pa.order = d_order_large; pa.n_contigs = n_large;
         }
@@ -1029,10 +1049,17 @@ int ChunkRun::prob_dist(int which) {
             return BS_OK;
         };
         if (pa.n_contigs > 0) {
-            if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true>));
-            else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false>));
-            else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true>));
-            else BS_TRY(launch(bs::k_prob_dist_ks<false, false>));
+            if (fuse) {
+                if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true, true>));
+                else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false, true>));
+                else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true, true>));
+                else BS_TRY(launch(bs::k_prob_dist_ks<false, false, true>));
+            } else {
+                if (packed && in_smem) BS_TRY(launch(bs::k_prob_dist_ks<true, true, false>));
+                else if (packed) BS_TRY(launch(bs::k_prob_dist_ks<true, false, false>));
+                else if (in_smem) BS_TRY(launch(bs::k_prob_dist_ks<false, true, false>));
+                else BS_TRY(launch(bs::k_prob_dist_ks<false, false, false>));
+            }
             ctx->launches++;
         }
     }

@@ -198,7 +198,7 @@ __global__ void k_row_cumsum(int32_t *m, int32_t R) {
 struct alignas(16) WinEntry {
     double prob;
     int32_t rank;
-    int32_t pad;
+    int32_t row;  // table row of the k-mer, -1 when it is not a row (what TabEntry holds for the same k-mer)
 };
 
 struct ProbDistArgs {
@@ -222,7 +222,44 @@ struct ProbDistArgs {
     uint32_t *rank_scratch;  // [gridDim][hist_words + n_ranges] global rank histogram when it does not fit shared memory, else NULL
     int32_t hist_words;      // 32-bit words of one rank histogram (hist_phys_words)
     int32_t n_ranges;        // hist_ranges: ranges of 32 histogram words
+    // FUSE instantiations also do k_break_score's work (kmer == 8 only): the break k-mer of contig position p is the
+    // rolling window p - 4 (upstream lib/BreakageScorer.cpp:244-267 with kmer/2 == 4 and the fixed expanded size 8), whose
+    // table entry this kernel has just gathered -- so the position weights are read beside the windows and the second
+    // scan of the contig, its table gathers and its launch disappear.  Positions 0..3 and L-3..L-1 (the start rules and
+    // the clamped end) take the generic path.
+    ScoreArgs sc;
 };
+
+// the part of the fused scoring that sits in the window loop: window pw (valid: all bases ACGT) with table entry e
+template <bool FUSE>
+__device__ __forceinline__ void fused_score_window(const ProbDistArgs &a, ScoreShared *sh, ScoreState &st, int64_t c, const int32_t *wsc,
+                                                   int64_t pw, bool valid, uint32_t code, const WinEntry &e) {
+    if constexpr (FUSE) {
+        if (st.total != 0) {
+            const int32_t wv = wsc[pw + 4];
+            if (wv != 0 && valid) score_add(a.sc, *sh, st, c, dense_offset(8) + (int)code, e.prob, e.row, wv);
+        }
+    }
+}
+// ... and after it: the irregular positions, then sums / outputs / KS of the break histogram (barriers inside)
+template <bool FUSE>
+__device__ __forceinline__ void fused_score_tail(const ProbDistArgs &a, ScoreShared *sh, ScoreState &st, int64_t c, int64_t L, const uint64_t *gw,
+                                                 const uint32_t *gm, const int32_t *wsc) {
+    if constexpr (FUSE) {
+        const int tid = threadIdx.x;
+        const int64_t np = L > 0 ? L : 1;
+        if (st.total != 0 && tid < 7) {
+            const int64_t p = tid < 4 ? tid : L - 3 + (tid - 4);
+            const bool mine = tid < 4 ? p < np : (p >= 4 && p < np);
+            if (mine) {
+                const int32_t wv = wsc[p];
+                if (wv != 0) score_add_position(a.sc, *sh, st, c, gw, gm, p, L, wv);
+            }
+        }
+        score_finish(a.sc, *sh, st, c, L, gw, gm, wsc);
+    }
+}
+
 
 // Rank histogram layout.  PACKED: two 16-bit counters per 32-bit word (every contig of the launch
 // has < 65536 windows), else one counter per word.  Words are grouped into RANGES of 32 (one
@@ -238,13 +275,19 @@ BS_HD int hist_phys_words(int R_x, bool packed) {
 }
 BS_HD int hist_ranges(int R_x, bool packed) { return (hist_logical_words(R_x, packed) + 31) / 32; }
 
-template <bool PACKED, bool IN_SMEM>
+template <bool PACKED, bool IN_SMEM, bool FUSE>
 __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     __shared__ int64_t s_wsum[32];
     __shared__ int64_t s_wmax[32];
     __shared__ int s_item;
+    ScoreShared *sh = nullptr;
+    if constexpr (FUSE) {
+        __shared__ ScoreShared s_score;
+        sh = &s_score;
+        score_shared_init(a.sc, *sh);
+    }
     // dynamic shared memory (or the global scratch row): histogram words, then the range bitmaps
     uint32_t *s_hist = IN_SMEM ? (uint32_t *)bs_dyn_smem() : a.rank_scratch + (int64_t)blockIdx.x * (a.hist_words + a.n_ranges);
     uint32_t *s_bm = s_hist + a.hist_words;
@@ -256,7 +299,10 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
     }
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(a.work_counter, 1);
+        if (tid == 0) {
+            s_item = atomicAdd(a.work_counter, 1);
+            if constexpr (FUSE) { sh->novf = 0; sh->maxc = 0; sh->nz = 0; }
+        }
         __syncthreads();
         if (s_item >= a.n_contigs) break;
         const int64_t c = a.order[s_item];
@@ -266,6 +312,12 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
         int64_t nwin = L - a.kmer + 1;
         if (nwin < 0) nwin = 0;
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
+        ScoreState st;
+        const int32_t *wsc = nullptr;
+        if constexpr (FUSE) {
+            score_begin(a.sc, c, st);
+            wsc = a.sc.w + a.ctg_off[c] + c;
+        }
         // truth side of this contig's segment, loaded early so that the latency hides behind the windows
         const int64_t seg = a.ctg_seg[c];
         const LeLt *yx = want_ks ? a.yx + seg * a.R_x : nullptr;
@@ -291,10 +343,15 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
                     if (base + 32 * u < nwin) {  // (warp-uniform: the next word exists, strings carry two pad words)
                         const uint64_t w1 = __ldg(&gw[wi + u + 1]);
                         const uint32_t m1 = __ldg(&gm[wi + u + 1]);
-                        if (base + 32 * u + lane < nwin && !(window32(m0, m1, (uint32_t)lane) & kbits)) {
-                            const WinEntry e = a.win[window64(w0, w1, (uint32_t)lane) >> kshift];  // one 16-byte gather
+                        if (base + 32 * u + lane < nwin) {
+                            const bool valid = !(window32(m0, m1, (uint32_t)lane) & kbits);
+                            const uint32_t code = (uint32_t)(window64(w0, w1, (uint32_t)lane) >> kshift);
+                            WinEntry e;
+                            e.prob = 0.0; e.rank = a.rank_zero; e.row = -1;
+                            if (valid) e = a.win[code];  // one 16-byte gather
                             val[u] = e.prob;
                             rk[u] = e.rank;
+                            fused_score_window<FUSE>(a, sh, st, c, wsc, base + 32 * u + lane, valid, code, e);
                         }
                         w0 = w1;
                         m0 = m1;
@@ -314,6 +371,7 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
                 }
             }
         }
+        fused_score_tail<FUSE>(a, sh, st, c, L, gw, gm, wsc);
         if (!want_ks) continue;
         __syncthreads();
         // ---- D = sup |F_x - F_y| over the pooled distinct values, evaluated at every x value that
@@ -400,12 +458,19 @@ constexpr int KS_SMALL_DIRECT = 24;  // windows sharing a range of 64 ranks up t
 BS_HD int ks_small_ranges(int R_x) { return (R_x + 63) >> 6; }
 BS_HD size_t ks_small_smem_bytes(int R_x) { return (size_t)KS_SMALL_MAX * 8 + (size_t)(2 * ks_small_ranges(R_x) + 4) * 4; }
 
-__global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDistArgs a) {
+template <bool FUSE>
+__global__ void __launch_bounds__(KS_SMALL_THREADS, FUSE ? 5 : 6) k_prob_dist_ks_small(ProbDistArgs a) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     __shared__ int64_t s_wmax[32];
     __shared__ uint32_t s_wsum[32];
     __shared__ int s_item;
+    ScoreShared *sh = nullptr;
+    if constexpr (FUSE) {
+        __shared__ ScoreShared s_score;
+        sh = &s_score;
+        score_shared_init(a.sc, *sh);
+    }
     uint32_t *s_rank = (uint32_t *)bs_dyn_smem();   // [KS_SMALL_MAX] rank of the window at p
     uint32_t *s_keys = s_rank + KS_SMALL_MAX;       // [KS_SMALL_MAX] the same ranks grouped by range
     const int n_rng = ks_small_ranges(a.R_x);
@@ -416,7 +481,10 @@ __global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDis
     const int per = (n_rng + nthr - 1) / nthr;      // ranges per thread in the prefix sum
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(a.work_counter, 1);
+        if (tid == 0) {
+            s_item = atomicAdd(a.work_counter, 1);
+            if constexpr (FUSE) { sh->novf = 0; sh->maxc = 0; sh->nz = 0; }
+        }
         for (int i = tid; i < n_rng; i += nthr) s_cur[i] = 0;
         __syncthreads();
         if (s_item >= a.n_contigs) break;
@@ -427,6 +495,12 @@ __global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDis
         int nwin = (int)(L - a.kmer + 1);
         if (nwin < 0) nwin = 0;
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
+        ScoreState st;
+        const int32_t *wsc = nullptr;
+        if constexpr (FUSE) {
+            score_begin(a.sc, c, st);
+            wsc = a.sc.w + a.ctg_off[c] + c;
+        }
         const int64_t seg = a.ctg_seg[c];
         const LeLt *yx = a.yx + seg * a.R_x;
         const int64_t n_y = a.R_y > 0 ? a.ycum[seg * a.R_y + a.R_y - 1] : 0;
@@ -447,10 +521,15 @@ __global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDis
                     if (base + 32 * u < nwin) {
                         const uint64_t w1 = __ldg(&gw[wi + u + 1]);
                         const uint32_t m1 = __ldg(&gm[wi + u + 1]);
-                        if (base + 32 * u + lane < nwin && !(window32(m0, m1, (uint32_t)lane) & kbits)) {
-                            const WinEntry e = a.win[window64(w0, w1, (uint32_t)lane) >> kshift];
+                        if (base + 32 * u + lane < nwin) {
+                            const bool valid = !(window32(m0, m1, (uint32_t)lane) & kbits);
+                            const uint32_t code = (uint32_t)(window64(w0, w1, (uint32_t)lane) >> kshift);
+                            WinEntry e;
+                            e.prob = 0.0; e.rank = a.rank_zero; e.row = -1;
+                            if (valid) e = a.win[code];
                             val[u] = e.prob;
                             rk[u] = e.rank;
+                            fused_score_window<FUSE>(a, sh, st, c, wsc, (int64_t)base + 32 * u + lane, valid, code, e);
                         }
                         w0 = w1;
                         m0 = m1;
@@ -467,6 +546,7 @@ __global__ void __launch_bounds__(KS_SMALL_THREADS) k_prob_dist_ks_small(ProbDis
                 }
             }
         }
+        fused_score_tail<FUSE>(a, sh, st, c, L, gw, gm, wsc);
         __syncthreads();
         // ---- exclusive prefix of the range counts ----
         const int lo_r = tid * per < n_rng ? tid * per : n_rng, hi_r = lo_r + per < n_rng ? lo_r + per : n_rng;

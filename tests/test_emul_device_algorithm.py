@@ -356,6 +356,54 @@ def test_two_phase_scoring(emul_scorer, oracle, kmers, prob):
     check_two_phase(emul_scorer, oracle, kmers, prob, P.make(*P.SMALL[2], mut=0.3), n_shards=2)
 
 
+def check_fused_scoring(scorer, oracle, kmers, prob, monkeypatch, segs):
+    """kmer == 8 without the dense histogram: the KS-A kernels score on their way over the windows (position p <-> window
+    p - 4; positions 0..3 and L-3..L-1 by the generic rule).  Against the oracle, and against k_break_score
+    (BS_FUSE_SCORE=0): integer outputs and KS-B bit-exact, the sums to 1e-12 (another summation order)."""
+    scorer.set_table(kmers, prob)
+    scorer.set_second_table(tables.uniform(len(prob)))
+    flags = B.DEFAULT_FLAGS | B.WANT_SECOND_TABLE
+    for seg, reads in segs:
+        monkeypatch.delenv("BS_FUSE_SCORE", raising=False)
+        n0 = scorer.launch_count
+        got = scorer.score(seg.contigs, reads, seg.truth, flags=flags)
+        n_fused = scorer.launch_count - n0
+        monkeypatch.setenv("BS_FUSE_SCORE", "0")
+        n0 = scorer.launch_count
+        ref = scorer.score(seg.contigs, reads, seg.truth, flags=flags)
+        assert scorer.launch_count - n0 == n_fused + 2  # k_break_score for both tables
+        monkeypatch.delenv("BS_FUSE_SCORE")
+        want = oracle.oracle_calc_breakscore(seg.contigs, reads, seg.truth, 8, kmers, prob)
+        for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos"):
+            assert np.array_equal(got[k], ref[k]) and np.array_equal(got[k], want[k]), k
+        for k in ("ks_stat_path_freq", "ks_stat_path_freq2", "ks_stat_prob_dist", "ks_stat_prob_dist2"):
+            assert np.array_equal(got[k], ref[k], equal_nan=True), k
+        for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len", "bp_score2", "bp_score_norm_by_break_freqs2"):
+            np.testing.assert_allclose(got[k], ref[k], rtol=1e-12, atol=0, err_msg=k)
+        for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len"):
+            np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=0, err_msg=k)
+        for k in ("ks_stat_prob_dist", "ks_stat_path_freq"):
+            np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+    scorer.set_second_table(None)
+
+
+def fused_cases():
+    from genomeassembler_dev_b200.synth import Segment
+    segs = [(P.make(*p, mut=0.3), None) for p in P.SMALL[:4]]
+    segs = [(s, s.read_list) for s, _ in segs]
+    for name, contigs, reads, truth, kmer in P.edge_inputs():
+        if kmer == 8:
+            segs.append((Segment(truth, None, contigs), reads))
+    # reads shorter than four bases reach the clamped end of a contig (positions L-3 .. L-1), reads of every start rule
+    c = b"ACGTTGCAAGGCTTACCGATAGGATTCAGC"
+    segs.append((Segment(c + b"GG", None, [c, c[:9], c[:7], c[:3], c[3:]]), [c[-1:], c[-2:], c[-3:], c[-4:], c[:2], c[1:3], c[2:5], c[3:6], c[4:9], c[-9:]] * 3))
+    return segs
+
+
+def test_fused_scoring(emul_scorer, oracle, kmers, prob, monkeypatch):
+    check_fused_scoring(emul_scorer, oracle, kmers, prob, monkeypatch, fused_cases())
+
+
 def check_pack_variants(scorer, kmers, prob, monkeypatch, lengths, to_dev=None, n_reads=(1, 3, 257, 1111)):
     """Reads of one length through both packing kernels (bulk-copy staged: default; register staged: BS_PACK_BULK=0)
     from read buffers that start at every 16-byte phase (BS_DEVICE_CHARS: the library packs straight out of the

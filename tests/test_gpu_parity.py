@@ -491,6 +491,12 @@ def test_hundred_repeats_are_bit_identical(mode, gpu_scorer, oracle, kmers, prob
         gpu_scorer.set_second_table(None)
 
 
+def test_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch):
+    from test_emul_device_algorithm import check_fused_scoring, fused_cases
+    segs = fused_cases() + [(s, s.read_list) for s in (P.make(*p, mut=0.3) for p in P.MEDIUM[:3])]
+    check_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch, segs)
+
+
 def test_pack_variants(gpu_scorer, kmers, prob, monkeypatch):
     """bulk-copy staged and register staged packing out of device buffers at every 16-byte phase (exact-size
     torch tensors: the bulk copy must not touch a byte outside them)"""
