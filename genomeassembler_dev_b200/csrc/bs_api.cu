@@ -945,8 +945,13 @@ int ChunkRun::spectrum() {
 
 bool ChunkRun::fused(int which) const {
     const bool ksa = which ? o_ksa2 != nullptr : ks_a;
-    const char *env = std::getenv("BS_FUSE_SCORE");  // tests / tuning: 0 keeps k_break_score
-    return kmer == 8 && !e.want_hist && (e.want_pd || ksa) && !(env && env[0] == '0');
+    if (!(kmer == 8 && !e.want_hist && (e.want_pd || ksa))) return false;
+    // Measured (profiles/r02o): one scan instead of two pays for LONG contigs (cfg-4's 32 kb scaffolds: 7.3 -> 5.5 ms) and
+    // costs for sets of short ones (cfg-2: 1.44 -> 1.63 ms; the KS-A kernels lose occupancy to the scoring state and the
+    // per-contig epilogues add up), so it follows the mean contig length of the chunk.  BS_FUSE_SCORE=0/1 forces it.
+    const char *env = std::getenv("BS_FUSE_SCORE");
+    if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
+    return C > 0 && (b->contig_off[ch.c1] - b->contig_off[ch.c0]) / C >= 8192;
 }
 
 int ChunkRun::score_args(int which, int64_t rows, bs::ScoreArgs &sa) {

@@ -357,14 +357,14 @@ def test_two_phase_scoring(emul_scorer, oracle, kmers, prob):
 
 
 def check_fused_scoring(scorer, oracle, kmers, prob, monkeypatch, segs):
-    """kmer == 8 without the dense histogram: the KS-A kernels score on their way over the windows (position p <-> window
-    p - 4; positions 0..3 and L-3..L-1 by the generic rule).  Against the oracle, and against k_break_score
+    """kmer == 8 without the dense histogram, BS_FUSE_SCORE=1 (default for sets of long contigs): the KS-A kernels score on
+    their way over the windows (position p <-> window p - 4; positions 0..3 and L-3..L-1 by the generic rule).  Against the oracle, and against k_break_score
     (BS_FUSE_SCORE=0): integer outputs and KS-B bit-exact, the sums to 1e-12 (another summation order)."""
     scorer.set_table(kmers, prob)
     scorer.set_second_table(tables.uniform(len(prob)))
     flags = B.DEFAULT_FLAGS | B.WANT_SECOND_TABLE
     for seg, reads in segs:
-        monkeypatch.delenv("BS_FUSE_SCORE", raising=False)
+        monkeypatch.setenv("BS_FUSE_SCORE", "1")  # (by default only sets of long contigs take the fused path)
         n0 = scorer.launch_count
         got = scorer.score(seg.contigs, reads, seg.truth, flags=flags)
         n_fused = scorer.launch_count - n0
