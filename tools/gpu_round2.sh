@@ -18,6 +18,6 @@ timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-study --
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-study --scan-segments 0 --device-only > $out/${tag}_ncu_bench.log 2>&1
 timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-study --scan-segments 0 --device-only > $out/${tag}_plain2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^k_|bs::k_" -s ${FULL_SKIP:-33} -c ${FULL_COUNT:-11} \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:^k_|bs::k_" -s ${FULL_SKIP:-36} -c ${FULL_COUNT:-12} \
     -o $out/${tag}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-study --scan-segments 0 --device-only > $out/${tag}_ncu_full.log 2>&1
 ls -la $out | grep $tag
