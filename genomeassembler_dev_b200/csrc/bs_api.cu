@@ -160,6 +160,10 @@ struct bs_ctx {
     // went up at a fifth of the PCIe rate)
     char *h_multi = nullptr;
     size_t h_multi_cap = 0;
+    // bs_score_multi with a large read set: the reads cross PCIe ONCE (context 0) and reach the other GPUs by peer
+    // copies over NVLink; contigs and truth of this context's share go up beside them
+    DevBuf m_reads, m_ctgs, m_truth;
+    cudaEvent_t ev_share = nullptr;
 
     // interrupt poll of the calling thread (bs_ctx_set_poll)
     bs_poll_fn poll = nullptr;
@@ -403,7 +407,8 @@ struct ChunkRun {
     bool sp_big = false;
     int64_t sp_slots = 0, sp_bitmap_words = 0;
     const int32_t *d_order_small = nullptr, *d_order_large = nullptr;  // work order split at KS_SMALL_MAX windows
-    int64_t n_small = 0, n_large = 0;
+    const int32_t *d_order_score = nullptr;                            // contigs below FUSE_MIN_LEN
+    int64_t n_small = 0, n_large = 0, n_score = 0;
     const bs::PlaceItem *d_items = nullptr;
     const uint8_t *d_rchars = nullptr, *d_cchars = nullptr, *d_tchars = nullptr;
     bs::SeqSet cs, ts;
@@ -542,6 +547,11 @@ int ChunkRun::prepare() {
     }
     n_small = (int64_t)order_small.size();
     n_large = (int64_t)order_large.size();
+    // k_break_score's share when the long-contig KS-A kernel scores on its way (fused()): contigs below FUSE_MIN_LEN
+    std::vector<int32_t> order_score;
+    for (int32_t c : order)
+        if (ctg_off[c + 1] - ctg_off[c] < bs::FUSE_MIN_LEN) order_score.push_back(c);
+    n_score = (int64_t)order_score.size();
     if (tile_mode) {
         // tile placement: one work item per (contig, read chunk)
         tile_len = (int)std::min<int64_t>(kMaxTile, std::max<int64_t>(32, (max_ctg + 31) / 32 * 32));
@@ -606,6 +616,7 @@ int ChunkRun::prepare() {
     const size_t o_order = mb.add(order.data(), order.size());
     const size_t o_order_small = mb.add(order_small.data(), order_small.size());
     const size_t o_order_large = mb.add(order_large.data(), order_large.size());
+    const size_t o_order_score = mb.add(order_score.data(), order_score.size());
     const size_t o_items = mb.add(items.data(), items.size());
     const size_t o_pd_off = e.want_pd ? mb.add(pd_off.data(), (size_t)C + 1) : 0;
     const size_t o_pos_off = e.want_pos ? mb.add(pos_off.data(), (size_t)C + 1) : 0;
@@ -678,6 +689,7 @@ int ChunkRun::prepare() {
     d_order = (const int32_t *)(dm + o_order);
     d_order_small = (const int32_t *)(dm + o_order_small);
     d_order_large = (const int32_t *)(dm + o_order_large);
+    d_order_score = (const int32_t *)(dm + o_order_score);
     d_items = (const bs::PlaceItem *)(dm + o_items);
     d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
     d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
@@ -945,13 +957,9 @@ int ChunkRun::spectrum() {
 
 bool ChunkRun::fused(int which) const {
     const bool ksa = which ? o_ksa2 != nullptr : ks_a;
-    if (!(kmer == 8 && !e.want_hist && (e.want_pd || ksa))) return false;
-    // Measured (profiles/r02o): one scan instead of two pays for LONG contigs (cfg-4's 32 kb scaffolds: 7.3 -> 5.5 ms) and
-    // costs for sets of short ones (cfg-2: 1.44 -> 1.63 ms; the KS-A kernels lose occupancy to the scoring state and the
-    // per-contig epilogues add up), so it follows the mean contig length of the chunk.  BS_FUSE_SCORE=0/1 forces it.
-    const char *env = std::getenv("BS_FUSE_SCORE");
-    if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
-    return C > 0 && (b->contig_off[ch.c1] - b->contig_off[ch.c0]) / C >= 8192;
+    // contigs of at least bs::FUSE_MIN_LEN bases are then scored by the long-contig KS-A kernel, the others by k_break_score
+    const char *env = std::getenv("BS_FUSE_SCORE");  // tests / tuning: 0 keeps k_break_score for every contig
+    return kmer == 8 && !e.want_hist && (e.want_pd || ksa) && !(env && env[0] == '0');
 }
 
 int ChunkRun::score_args(int which, int64_t rows, bs::ScoreArgs &sa) {
@@ -970,6 +978,7 @@ int ChunkRun::score_args(int which, int64_t rows, bs::ScoreArgs &sa) {
         sa.bp_score = o_score2; sa.norm_by_break_freqs = o_norm2; sa.norm_by_len = o_bylen2;
     }
     if (ksb) {
+        rows = std::max<int64_t>(rows, (int64_t)ctx->sm_count * 8);  // (k_break_score and the fused KS-A kernel take turns on the same rows)
         const size_t scratch_bytes = (size_t)rows * (T + 1) * 4;
         if (ctx->d_scratch.cap < scratch_bytes || !ctx->d_scratch.p) {
             BS_TRY(ensure(ctx, ctx->d_scratch, scratch_bytes));
@@ -984,13 +993,15 @@ int ChunkRun::score_args(int which, int64_t rows, bs::ScoreArgs &sa) {
 }
 
 int ChunkRun::score(int which) {
-    if (fused(which)) return BS_OK;  // the KS-A kernels do it on their way over the windows
-    {
+    const bool fz = fused(which);  // the long-contig KS-A kernel scores contigs of FUSE_MIN_LEN bases and more on its way
+    const int64_t n = fz ? n_score : C;
+    if (n > 0) {
         // scores (+ histogram, + KS of the normalised break histogram); after the truth spectrum
         StageTimer tm(ctx, ST_SCORE, st);
-        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kBreakScoreThreads, 0));
+        const int nblk = (int)std::min<int64_t>(n, (int64_t)ctx->sm_count * blocks_per_sm(bs::k_break_score, kBreakScoreThreads, 0));
         bs::ScoreArgs sa;
         BS_TRY(score_args(which, nblk, sa));
+        if (fz) { sa.order = d_order_score; sa.n_contigs = n_score; }
         BS_LAUNCH(bs::k_break_score, (unsigned)nblk, kBreakScoreThreads, 0, st, sa);
         ctx->launches++;
     }
@@ -1033,7 +1044,7 @@ int ChunkRun::prob_dist(int which) {
         const size_t small_smem = bs::ks_small_smem_bytes(k.R_x);
         const bool use_small = ksa && n_small > 0 && small_smem + 1024 <= ctx->smem_optin;
         const bool fuse = fused(which);
-        auto small_kernel = fuse ? bs::k_prob_dist_ks_small<true> : bs::k_prob_dist_ks_small<false>;
+        auto small_kernel = bs::k_prob_dist_ks_small;
         int nb_small = 0;
         if (use_small) {
             BS_CUDA(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem));
@@ -1348,6 +1359,10 @@ void bs_ctx_destroy(bs_ctx *ctx) {
         if (t.b) cudaEventDestroy(t.b);
     }
     if (ctx->h_multi) cudaFreeHost(ctx->h_multi);
+    release(ctx->m_reads);
+    release(ctx->m_ctgs);
+    release(ctx->m_truth);
+    if (ctx->ev_share) cudaEventDestroy(ctx->ev_share);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
@@ -1862,10 +1877,69 @@ static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_c
         if (want_pos) { m.pos.assign((size_t)m.pos_off[n] + 1, 0); m.r.pos = m.pos.data(); m.r.pos_off = m.pos_off.data(); }
     }
 
+    // A large read set is replicated over NVLink instead of PCIe: context 0 copies it in once, the others get it by peer
+    // copies along a binary tree (round r: the 2^r contexts that hold it each feed one that does not), everything
+    // queued here on the contexts' copy streams and ordered by events.  BS_MULTI_P2P_MB: smallest read set (MB) that
+    // takes this way (default 64; a negative value switches it off).
+    bool share = false;
+    std::vector<int64_t> read_off0;
+#ifndef BS_CPU_EMUL
+    {
+        const int64_t read_bytes = n_reads > 0 ? read_off[n_reads] - read_off[0] : 0;
+        int64_t thresh_mb = 64;
+        if (const char *env = std::getenv("BS_MULTI_P2P_MB")) thresh_mb = std::atoll(env);
+        share = n_reads > 0 && thresh_mb >= 0 && read_bytes >= (thresh_mb << 20);
+        if (share) {
+            read_off0.resize((size_t)n_reads + 1);
+            for (int64_t n = 0; n <= n_reads; n++) read_off0[(size_t)n] = read_off[n] - read_off[0];
+            for (int k = 0; k < n_ctx; k++) {
+                bs_ctx *c = ctxs[k];
+                cudaSetDevice(c->device);
+                BS_TRY(ensure(c, c->m_reads, (size_t)read_bytes + 32));
+                if (!c->ev_share && cudaEventCreateWithFlags(&c->ev_share, cudaEventDisableTiming) != cudaSuccess)
+                    return fail(ctx, BS_ERR_CUDA, "bs_score_multi: event creation failed on context %d", k);
+            }
+            cudaSetDevice(ctx->device);
+            BS_CUDA(cudaMemcpyAsync(ctx->m_reads.p, read_chars + read_off[0], (size_t)read_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            BS_CUDA(cudaEventRecord(ctx->ev_share, ctx->copy_stream));
+            for (int have = 1; have < n_ctx; have *= 2) {
+                for (int src = 0; src < have && src + have < n_ctx; src++) {
+                    bs_ctx *from = ctxs[src], *to = ctxs[src + have];
+                    cudaSetDevice(to->device);
+                    if (to->device != from->device) {
+                        const cudaError_t pe = cudaDeviceEnablePeerAccess(from->device, 0);  // (already enabled / unsupported: the copy is staged)
+                        if (pe != cudaSuccess) cudaGetLastError();
+                    }
+                    BS_CUDA(cudaStreamWaitEvent(to->copy_stream, from->ev_share, 0));
+                    BS_CUDA(cudaMemcpyPeerAsync(to->m_reads.p, to->device, from->m_reads.p, from->device, (size_t)read_bytes, to->copy_stream));
+                    BS_CUDA(cudaEventRecord(to->ev_share, to->copy_stream));
+                }
+            }
+        }
+    }
+#endif
     // one host thread per context with work (a context is single-threaded, contexts are independent)
     auto run = [&](int k) {  // (bs_score catches everything itself: nothing escapes a worker thread)
         MultiShard &m = sh[k];
         if (m.idx.empty()) return;
+#ifndef BS_CPU_EMUL
+        if (share) {  // this context's contigs and the truth go up beside the reads; the call then takes device pointers
+            bs_ctx *c = ctxs[k];
+            cudaSetDevice(c->device);
+            const size_t cb = (size_t)m.off[m.idx.size()], tb = (size_t)truth_len;
+            m.rc = ensure(c, c->m_ctgs, cb + 32);
+            if (m.rc == BS_OK) m.rc = ensure(c, c->m_truth, tb + 32);
+            if (m.rc != BS_OK) return;
+            cudaError_t ce = cudaSuccess;
+            if (cb) ce = cudaMemcpyAsync(c->m_ctgs.p, m.chars, cb, cudaMemcpyHostToDevice, c->copy_stream);
+            if (ce == cudaSuccess && tb) ce = cudaMemcpyAsync(c->m_truth.p, truth, tb, cudaMemcpyHostToDevice, c->copy_stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->copy_stream);  // (the reads arrive on the same stream)
+            if (ce != cudaSuccess) { m.rc = fail(c, BS_ERR_CUDA, "bs_score_multi: staging failed: %s", cudaGetErrorString(ce)); return; }
+            m.rc = bs_score(c, (const char *)c->m_ctgs.p, m.off.data(), (int64_t)m.idx.size(), (const char *)c->m_reads.p, read_off0.data(), n_reads,
+                            (const char *)c->m_truth.p, truth_len, kmer, flags | BS_DEVICE_CHARS, &m.r);
+            return;
+        }
+#endif
         m.rc = bs_score(ctxs[k], m.chars, m.off.data(), (int64_t)m.idx.size(), read_chars, read_off, n_reads, truth, truth_len,
                         kmer, flags, &m.r);
     };

@@ -230,6 +230,16 @@ struct ProbDistArgs {
     ScoreArgs sc;
 };
 
+// Which contigs are scored on the way: those of at least FUSE_MIN_LEN bases.  Measured (profiles/r02o): one scan instead of
+// two pays for long contigs (cfg-4's 32 kb scaffolds: 7.3 -> 5.5 ms) and costs for short ones (cfg-2's set: 1.44 -> 1.63 ms;
+// the KS-A kernels lose occupancy to the scoring state and the per-contig epilogues add up).  The rule looks at the contig
+// alone, so a contig's sums do not depend on what else is in the call, the chunk or the shard.
+#ifdef BS_CPU_EMUL
+constexpr int64_t FUSE_MIN_LEN = 2560;  // (emulation: the tests' contigs are short)
+#else
+constexpr int64_t FUSE_MIN_LEN = 8192;
+#endif
+
 // the part of the fused scoring that sits in the window loop: window pw (valid: all bases ACGT) with table entry e
 template <bool FUSE>
 __device__ __forceinline__ void fused_score_window(const ProbDistArgs &a, ScoreShared *sh, ScoreState &st, int64_t c, const int32_t *wsc,
@@ -314,8 +324,10 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
         ScoreState st;
         const int32_t *wsc = nullptr;
+        const bool fz = FUSE && L >= FUSE_MIN_LEN;  // (block-uniform) a property of the contig alone: see FUSE_MIN_LEN
         if constexpr (FUSE) {
             score_begin(a.sc, c, st);
+            if (!fz) st.total = 0;  // scored by k_break_score: nothing is accumulated here
             wsc = a.sc.w + a.ctg_off[c] + c;
         }
         // truth side of this contig's segment, loaded early so that the latency hides behind the windows
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
                 }
             }
         }
-        fused_score_tail<FUSE>(a, sh, st, c, L, gw, gm, wsc);
+        if (fz) fused_score_tail<FUSE>(a, sh, st, c, L, gw, gm, wsc);
         if (!want_ks) continue;
         __syncthreads();
         // ---- D = sup |F_x - F_y| over the pooled distinct values, evaluated at every x value that
@@ -453,13 +465,14 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
 #endif
 constexpr int KS_SMALL_MAX = BS_KS_SMALL_MAX;  // windows per contig the short-contig kernel takes
 constexpr int KS_SMALL_THREADS = BS_KS_SMALL_THREADS;
+static_assert(FUSE_MIN_LEN > KS_SMALL_MAX + MAXK, "a contig scored on the way must be one the long-contig kernel takes");
 constexpr int KS_SMALL_DIRECT = 24;  // windows sharing a range of 64 ranks up to which every window counts its own neighbours
 
 BS_HD int ks_small_ranges(int R_x) { return (R_x + 63) >> 6; }
 BS_HD size_t ks_small_smem_bytes(int R_x) { return (size_t)KS_SMALL_MAX * 8 + (size_t)(2 * ks_small_ranges(R_x) + 4) * 4; }
 
-template <bool FUSE>
-__global__ void __launch_bounds__(KS_SMALL_THREADS, FUSE ? 5 : 6) k_prob_dist_ks_small(ProbDistArgs a) {
+__global__ void __launch_bounds__(KS_SMALL_THREADS, 6) k_prob_dist_ks_small(ProbDistArgs a) {
+    constexpr bool FUSE = false;  // short contigs are scored by k_break_score (see FUSE_MIN_LEN)
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     __shared__ int64_t s_wmax[32];

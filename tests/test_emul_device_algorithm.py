@@ -356,24 +356,38 @@ def test_two_phase_scoring(emul_scorer, oracle, kmers, prob):
     check_two_phase(emul_scorer, oracle, kmers, prob, P.make(*P.SMALL[2], mut=0.3), n_shards=2)
 
 
-def check_fused_scoring(scorer, oracle, kmers, prob, monkeypatch, segs):
-    """kmer == 8 without the dense histogram, BS_FUSE_SCORE=1 (default for sets of long contigs): the KS-A kernels score on
-    their way over the windows (position p <-> window p - 4; positions 0..3 and L-3..L-1 by the generic rule).  Against the oracle, and against k_break_score
-    (BS_FUSE_SCORE=0): integer outputs and KS-B bit-exact, the sums to 1e-12 (another summation order)."""
+def check_fused_scoring(scorer, oracle, kmers, prob, monkeypatch, long_len):
+    """kmer == 8 without the dense histogram: contigs of at least FUSE_MIN_LEN bases (8192; 2560 under the emulation) are
+    scored by the long-contig KS-A kernel on its way over the windows (position p <-> window p - 4; positions 0..3 and
+    L-3..L-1 by the generic rule), the others by k_break_score.  Against the oracle, and against k_break_score for every
+    contig (BS_FUSE_SCORE=0): integer outputs and KS bit-exact, the sums to 1e-12 (another summation order).  A contig's
+    results do not depend on what else is in the call."""
+    from genomeassembler_dev_b200 import synth
+    rng = np.random.default_rng(808)
+    Lt = 3 * long_len
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, Lt))
+    starts = rng.integers(0, Lt - 60, size=Lt // 4)
+    reads = [truth[a:a + 60].tobytes() for a in starts] + [truth[:3].tobytes(), truth[long_len - 2:long_len].tobytes(), truth[1:3].tobytes()]
+    long_a, long_b = truth[:long_len].tobytes(), truth[long_len // 2:long_len // 2 + long_len + 77].tobytes()
+    mutated = bytearray(truth[Lt - long_len - 5:Lt]); mutated[long_len // 3] ^= 6
+    with_n = bytearray(truth[100:100 + long_len]); with_n[4000 % long_len] = ord("N"); with_n[5] = ord("N")
+    shorts = [truth[50:50 + long_len - 1].tobytes(), truth[7:900].tobytes(), truth[300:309].tobytes(), b"ACGT"]
     scorer.set_table(kmers, prob)
     scorer.set_second_table(tables.uniform(len(prob)))
     flags = B.DEFAULT_FLAGS | B.WANT_SECOND_TABLE
-    for seg, reads in segs:
-        monkeypatch.setenv("BS_FUSE_SCORE", "1")  # (by default only sets of long contigs take the fused path)
+    tr = truth.tobytes()
+    for contigs, all_long in (([long_a, long_b, bytes(mutated), bytes(with_n)], True), ([long_a] + shorts + [long_b, bytes(with_n)], False)):
+        monkeypatch.delenv("BS_FUSE_SCORE", raising=False)
         n0 = scorer.launch_count
-        got = scorer.score(seg.contigs, reads, seg.truth, flags=flags)
+        got = scorer.score(contigs, reads, tr, flags=flags)
         n_fused = scorer.launch_count - n0
         monkeypatch.setenv("BS_FUSE_SCORE", "0")
         n0 = scorer.launch_count
-        ref = scorer.score(seg.contigs, reads, seg.truth, flags=flags)
-        assert scorer.launch_count - n0 == n_fused + 2  # k_break_score for both tables
+        ref = scorer.score(contigs, reads, tr, flags=flags)
+        assert scorer.launch_count - n0 == n_fused + (2 if all_long else 0)  # no k_break_score launch when every contig is long
         monkeypatch.delenv("BS_FUSE_SCORE")
-        want = oracle.oracle_calc_breakscore(seg.contigs, reads, seg.truth, 8, kmers, prob)
+        want = oracle.oracle_calc_breakscore(contigs, reads, tr, 8, kmers, prob)
+        assert want["kmer_breaks"].sum() > Lt // 8
         for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos"):
             assert np.array_equal(got[k], ref[k]) and np.array_equal(got[k], want[k]), k
         for k in ("ks_stat_path_freq", "ks_stat_path_freq2", "ks_stat_prob_dist", "ks_stat_prob_dist2"):
@@ -384,24 +398,18 @@ def check_fused_scoring(scorer, oracle, kmers, prob, monkeypatch, segs):
             np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=0, err_msg=k)
         for k in ("ks_stat_prob_dist", "ks_stat_path_freq"):
             np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+        for a, b in zip(got["path_prob_dist"], want["path_prob_dist"]):
+            assert np.array_equal(a, b)
+        if all_long:
+            first = got
+        else:  # the same contig in another call: the same bits
+            for k in ("bp_score", "bp_score_norm_by_break_freqs", "ks_stat_path_freq", "ks_stat_prob_dist", "bp_score2"):
+                assert got[k][0] == first[k][0] and got[k][-2] == first[k][1] and (got[k][-1] == first[k][3] or np.isnan(got[k][-1])), k
     scorer.set_second_table(None)
 
 
-def fused_cases():
-    from genomeassembler_dev_b200.synth import Segment
-    segs = [(P.make(*p, mut=0.3), None) for p in P.SMALL[:4]]
-    segs = [(s, s.read_list) for s, _ in segs]
-    for name, contigs, reads, truth, kmer in P.edge_inputs():
-        if kmer == 8:
-            segs.append((Segment(truth, None, contigs), reads))
-    # reads shorter than four bases reach the clamped end of a contig (positions L-3 .. L-1), reads of every start rule
-    c = b"ACGTTGCAAGGCTTACCGATAGGATTCAGC"
-    segs.append((Segment(c + b"GG", None, [c, c[:9], c[:7], c[:3], c[3:]]), [c[-1:], c[-2:], c[-3:], c[-4:], c[:2], c[1:3], c[2:5], c[3:6], c[4:9], c[-9:]] * 3))
-    return segs
-
-
 def test_fused_scoring(emul_scorer, oracle, kmers, prob, monkeypatch):
-    check_fused_scoring(emul_scorer, oracle, kmers, prob, monkeypatch, fused_cases())
+    check_fused_scoring(emul_scorer, oracle, kmers, prob, monkeypatch, long_len=2600)
 
 
 def check_pack_variants(scorer, kmers, prob, monkeypatch, lengths, to_dev=None, n_reads=(1, 3, 257, 1111)):

@@ -181,9 +181,13 @@ def test_poll_callback_interrupts_between_chunks(product_lib, kmers, prob, monke
         assert np.array_equal(want[k], again[k], equal_nan=True), k
 
 
-def test_one_segment_over_several_contexts(product_lib, gpu_scorer, kmers, prob):
+@pytest.mark.parametrize("p2p_mb", [None, "0"], ids=["reads_over_pcie", "reads_by_peer_copies"])
+def test_one_segment_over_several_contexts(p2p_mb, product_lib, gpu_scorer, kmers, prob, monkeypatch):
     """bs_score_multi on the GPU: three contexts (here on the same device; on an 8-GPU box one per GPU), a host
-    thread each, contigs dealt out longest first, reads replicated == one call on one context, byte for byte."""
+    thread each, contigs dealt out longest first, reads replicated == one call on one context, byte for byte.
+    BS_MULTI_P2P_MB=0: the reads go to context 0 once and reach the others by peer copies (what a large read set does)."""
+    if p2p_mb is not None:
+        monkeypatch.setenv("BS_MULTI_P2P_MB", p2p_mb)
     seg = P.make(77, 20000, 64, 20, 25, 1, mut=0.3)
     contigs = list(seg.contigs) + [seg.contigs[0][:5], b"", seg.contigs[-1]]
     flags = B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS | B.WANT_LEV
@@ -492,9 +496,9 @@ def test_hundred_repeats_are_bit_identical(mode, gpu_scorer, oracle, kmers, prob
 
 
 def test_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch):
-    from test_emul_device_algorithm import check_fused_scoring, fused_cases
-    segs = fused_cases() + [(s, s.read_list) for s in (P.make(*p, mut=0.3) for p in P.MEDIUM[:3])]
-    check_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch, segs)
+    from test_emul_device_algorithm import check_fused_scoring
+    check_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch, long_len=8200)
+    check_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch, long_len=40000)
 
 
 def test_pack_variants(gpu_scorer, kmers, prob, monkeypatch):

@@ -275,36 +275,56 @@ def measure(bench, rig, sh, steps, warmup, sample=None, expected=None, host_read
             "what": "host ASCII -> records on rank 0's host, contigs sharded either way; the reads reach every GPU over PCIe (xN) or "
                     "once over PCIe + NVLink"}
         del d_full, d_ct2, d_tr2
-    # ---- ONE process driving all GPUs (upstream's R driver is one process): bs_score_multi, rank 0 only ----
     if multi_ctx and world > 1 and host_reads is not None:
-        rig.sync()
-        rig.barrier()
-        if rank == 0:
-            others = [B.BreakageScorer(d) for d in range(1, world)]
-            try:
-                for o in others:
-                    o.set_table(rig.kmers, rig.prob)
-                ct, ct_off = B.flatten(sh.contigs)
-                rd = host_reads.numpy()
-                tr = host_truth.numpy()
-                call = lambda: sc.score_batch(rd, None, READ_LEN, ct, ct_off, tr, sh.tr_off, sh.srs, [0, len(sh.contigs)],  # noqa: E731
-                                              flags=sh.flags, group=others)
-                call()
-                t0 = time.perf_counter()
-                for _ in range(2):
-                    got = call()
-                multi_ms = 1e3 * (time.perf_counter() - t0) / 2
-                same = bool(np.array_equal(got["kmer_breaks"], ti[:, 1].cpu().numpy()) and
-                            np.array_equal(got["bp_score"], tf[:, 0].cpu().numpy()))
-                out["one_process_bs_score_multi"] = {"ms_per_call": multi_ms, "value": pair / 1e9 / (multi_ms / 1e3), "unit": bench.UNIT,
-                                                     "contexts": world, "same_records": same,
-                                                     "what": "ONE process, one context per GPU, a host thread each (bs_score_multi): host buffers in, "
-                                                             "host arrays out in input order, no collective"}
-            finally:
-                for o in others:
-                    o.close()
-        rig.barrier()
+        one = measure_one_process(bench, rig, sh.contigs, sh.tr_off, sh.srs, sh.flags, host_reads, host_truth, tf, ti, pair)
+        if one is not None:
+            out["one_process_bs_score_multi"] = one
     return out
+
+
+def measure_one_process(bench, rig, contigs, tr_off, srs, flags, host_reads, host_truth, tf, ti, pair):
+    """ONE process driving all GPUs (upstream's R driver is one process): bs_score_multi from rank 0 while the other ranks
+    wait; host buffers in, host arrays out in input order, no collective.  A read set of 64 MB or more crosses PCIe once
+    and is replicated by peer copies over NVLink (BS_MULTI_P2P_MB); timed both ways when the set is that large."""
+    B, sc, world, rank = rig.B, rig.sc, rig.world, rig.rank
+    rig.sync()
+    rig.barrier()
+    res1 = None
+    if rank == 0:
+        others = []
+        try:
+            others = [B.BreakageScorer(d) for d in range(1, world)]
+            for o in others:
+                o.set_table(rig.kmers, rig.prob)
+            ct, ct_off = B.flatten(contigs)
+            rd = host_reads.numpy()
+            tr = host_truth.numpy()
+            call = lambda: sc.score_batch(rd, None, READ_LEN, ct, ct_off, tr, tr_off, srs, [0, len(contigs)], flags=flags, group=others)  # noqa: E731
+            res1 = {"contexts": world,
+                    "what": "ONE process, one context per GPU, a host thread each (bs_score_multi): host buffers in, host arrays out in "
+                            "input order, no collective; a read set of 64 MB or more crosses PCIe once and is replicated by peer copies"}
+            big = rd.nbytes >= (64 << 20)
+            for name, env in ((("reads_by_peer_copies", None), ("reads_over_pcie_per_gpu", "-1")) if big else (("reads_over_pcie_per_gpu", None),)):
+                if env is None:
+                    os.environ.pop("BS_MULTI_P2P_MB", None)
+                else:
+                    os.environ["BS_MULTI_P2P_MB"] = env
+                try:
+                    call()
+                    t0 = time.perf_counter()
+                    got = call()
+                    ms = 1e3 * (time.perf_counter() - t0)
+                    same = bool(np.array_equal(got["kmer_breaks"], ti[:, 1].cpu().numpy()) and
+                                np.array_equal(got["bp_score"], tf[:, 0].cpu().numpy()))
+                    res1[name] = {"ms_per_call": ms, "value": pair / 1e9 / (ms / 1e3), "unit": bench.UNIT, "same_records": same}
+                except B.BreakscoreError as e:  # e.g. device memory: the other ranks' buffers share these GPUs
+                    res1[name] = {"failed": str(e)[:200]}
+            os.environ.pop("BS_MULTI_P2P_MB", None)
+        finally:
+            for o in others:
+                o.close()
+    rig.barrier()
+    return res1
 
 
 def measure_read_sharded(bench, rig, sh, steps, warmup, timing=True):
@@ -508,6 +528,14 @@ def run_gpu_side(bench, rig, plan):
     if "cpu_cfg5" in plan:
         res["cpu_baseline"] = plan["cpu_cfg5"]
     out["cfg5"] = res
-    del sh, g, h_reads, h_truth
+    # the one-process path last, with this rank's device tensors gone (rank 0's extra contexts need room on every GPU)
+    contigs, tr_off, srs, flags, pair = sh.contigs, sh.tr_off, sh.srs, sh.flags, float(sh.n_reads) * sh.bases
+    tf, ti = tf.clone(), ti.clone()
+    del sh, g
     torch.cuda.empty_cache()
+    if world > 1 and h_reads is not None:
+        one = measure_one_process(bench, rig, contigs, tr_off, srs, flags, h_reads, h_truth, tf, ti, pair)
+        if one is not None:
+            res["one_process_bs_score_multi"] = one
+    del h_reads, h_truth
     return out
