@@ -1890,8 +1890,10 @@ static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_c
         if (const char *env = std::getenv("BS_MULTI_P2P_MB")) thresh_mb = std::atoll(env);
         share = n_reads > 0 && thresh_mb >= 0 && read_bytes >= (thresh_mb << 20);
         if (share) {
-            read_off0.resize((size_t)n_reads + 1);
-            for (int64_t n = 0; n <= n_reads; n++) read_off0[(size_t)n] = read_off[n] - read_off[0];
+            if (read_off[0] != 0) {  // offsets relative to the staged copy
+                read_off0.resize((size_t)n_reads + 1);
+                for (int64_t n = 0; n <= n_reads; n++) read_off0[(size_t)n] = read_off[n] - read_off[0];
+            }
             for (int k = 0; k < n_ctx; k++) {
                 bs_ctx *c = ctxs[k];
                 cudaSetDevice(c->device);
@@ -1915,6 +1917,12 @@ static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_c
                     BS_CUDA(cudaEventRecord(to->ev_share, to->copy_stream));
                 }
             }
+            if (std::getenv("BS_TRACE")) {  // diagnostic: when the last GPU holds the reads
+                const auto t0 = std::chrono::steady_clock::now();
+                for (int k = 0; k < n_ctx; k++) cudaEventSynchronize(ctxs[k]->ev_share);
+                std::fprintf(stderr, "[bs trace] reads on %d GPUs   %9.3f ms after queueing (%lld bytes)\n", n_ctx,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), (long long)read_bytes);
+            }
         }
     }
 #endif
@@ -1935,7 +1943,8 @@ static int score_multi_impl(bs_ctx *const *ctxs, int n_ctx, const char *contig_c
             if (ce == cudaSuccess && tb) ce = cudaMemcpyAsync(c->m_truth.p, truth, tb, cudaMemcpyHostToDevice, c->copy_stream);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->copy_stream);  // (the reads arrive on the same stream)
             if (ce != cudaSuccess) { m.rc = fail(c, BS_ERR_CUDA, "bs_score_multi: staging failed: %s", cudaGetErrorString(ce)); return; }
-            m.rc = bs_score(c, (const char *)c->m_ctgs.p, m.off.data(), (int64_t)m.idx.size(), (const char *)c->m_reads.p, read_off0.data(), n_reads,
+            m.rc = bs_score(c, (const char *)c->m_ctgs.p, m.off.data(), (int64_t)m.idx.size(), (const char *)c->m_reads.p,
+                            read_off0.empty() ? read_off : read_off0.data(), n_reads,
                             (const char *)c->m_truth.p, truth_len, kmer, flags | BS_DEVICE_CHARS, &m.r);
             return;
         }
