@@ -230,14 +230,14 @@ struct ProbDistArgs {
     ScoreArgs sc;
 };
 
-// Which contigs are scored on the way: those of at least FUSE_MIN_LEN bases.  Measured (profiles/r02o): one scan instead of
+// Which contigs are scored on the way: those of at least FUSE_MIN_LEN bases (16 kb).  Measured (profiles/r02o): one scan instead of
 // two pays for long contigs (cfg-4's 32 kb scaffolds: 7.3 -> 5.5 ms) and costs for short ones (cfg-2's set: 1.44 -> 1.63 ms;
 // the KS-A kernels lose occupancy to the scoring state and the per-contig epilogues add up).  The rule looks at the contig
 // alone, so a contig's sums do not depend on what else is in the call, the chunk or the shard.
 #ifdef BS_CPU_EMUL
 constexpr int64_t FUSE_MIN_LEN = 2560;  // (emulation: the tests' contigs are short)
 #else
-constexpr int64_t FUSE_MIN_LEN = 8192;
+constexpr int64_t FUSE_MIN_LEN = 16384;
 #endif
 
 // the part of the fused scoring that sits in the window loop: window pw (valid: all bases ACGT) with table entry e

@@ -357,7 +357,7 @@ def test_two_phase_scoring(emul_scorer, oracle, kmers, prob):
 
 
 def check_fused_scoring(scorer, oracle, kmers, prob, monkeypatch, long_len):
-    """kmer == 8 without the dense histogram: contigs of at least FUSE_MIN_LEN bases (8192; 2560 under the emulation) are
+    """kmer == 8 without the dense histogram: contigs of at least FUSE_MIN_LEN bases (16384; 2560 under the emulation) are
     scored by the long-contig KS-A kernel on its way over the windows (position p <-> window p - 4; positions 0..3 and
     L-3..L-1 by the generic rule), the others by k_break_score.  Against the oracle, and against k_break_score for every
     contig (BS_FUSE_SCORE=0): integer outputs and KS bit-exact, the sums to 1e-12 (another summation order).  A contig's

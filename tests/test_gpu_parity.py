@@ -497,7 +497,7 @@ def test_hundred_repeats_are_bit_identical(mode, gpu_scorer, oracle, kmers, prob
 
 def test_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch):
     from test_emul_device_algorithm import check_fused_scoring
-    check_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch, long_len=8200)
+    check_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch, long_len=16400)
     check_fused_scoring(gpu_scorer, oracle, kmers, prob, monkeypatch, long_len=40000)
 
 
