@@ -45,6 +45,8 @@ ABI_SYMBOLS = (
     "bs_ctx_last_place_ms", "bs_ctx_set_poll", "bs_set_table", "bs_set_truth_table", "bs_set_second_table", "bs_score_batch", "bs_score", "bs_score_multi",
     "bs_host_alloc", "bs_host_free", "bs_assemble_contigs", "bs_assemble_last_error", "bs_string_list_size",
     "bs_string_list_bytes", "bs_string_list_copy", "bs_string_list_free", "bs_simulate_capacity", "bs_simulate_reads",
+    "bs_score_scaffolds", "bs_scaffold_lengths", "bs_scaffold_texts", "bs_assemble_scaffolds", "bs_scaffold_list_size",
+    "bs_scaffold_list_parts", "bs_scaffold_list_copy", "bs_scaffold_list_free",
 )
 
 POLL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -85,6 +87,14 @@ class _Result(C.Structure):
         ("bp_score2", C.c_void_p), ("bp_score_norm_by_break_freqs2", C.c_void_p), ("bp_score_norm_by_len2", C.c_void_p),
         ("ks_stat_prob_dist2", C.c_void_p), ("ks_stat_path_freq2", C.c_void_p), ("path_prob_dist2", C.c_void_p),
         ("weights", C.c_void_p), ("weights_total", C.c_void_p),
+    ]
+
+
+class _ScaffoldSet(C.Structure):
+    _fields_ = [
+        ("n_base", C.c_int64), ("base_chars", C.c_void_p), ("base_off", C.c_void_p),
+        ("n_scaffolds", C.c_int64), ("scaffold_part_start", C.c_void_p), ("part_base", C.c_void_p),
+        ("part_overlap", C.c_void_p),
     ]
 
 
@@ -152,8 +162,26 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.bs_simulate_reads.restype = C.c_int
     lib.bs_simulate_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int,
                                       C.c_uint64, C.c_uint32, C.c_void_p, C.c_int64, C.c_void_p]
-    if lib.bs_abi_version() != 4:
-        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 4")
+    lib.bs_score_scaffolds.restype = C.c_int
+    lib.bs_score_scaffolds.argtypes = [C.c_void_p, C.POINTER(_ScaffoldSet), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                       C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.POINTER(_Result)]
+    lib.bs_scaffold_lengths.restype = C.c_int
+    lib.bs_scaffold_lengths.argtypes = [C.POINTER(_ScaffoldSet), C.c_void_p]
+    lib.bs_scaffold_texts.restype = C.c_int
+    lib.bs_scaffold_texts.argtypes = [C.POINTER(_ScaffoldSet), C.c_void_p, C.c_void_p]
+    lib.bs_assemble_scaffolds.restype = C.c_int
+    lib.bs_assemble_scaffolds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.bs_scaffold_list_size.restype = C.c_int64
+    lib.bs_scaffold_list_size.argtypes = [C.c_void_p]
+    lib.bs_scaffold_list_parts.restype = C.c_int64
+    lib.bs_scaffold_list_parts.argtypes = [C.c_void_p]
+    lib.bs_scaffold_list_copy.restype = None
+    lib.bs_scaffold_list_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bs_scaffold_list_free.restype = None
+    lib.bs_scaffold_list_free.argtypes = [C.c_void_p]
+    if lib.bs_abi_version() != 5:
+        raise RuntimeError(f"{path}: ABI version {lib.bs_abi_version()} != 5")
     return lib
 
 
@@ -177,6 +205,49 @@ def prob_dist_offsets(contig_off, kmer):
 
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class ScaffoldSet:
+    """Candidate scaffolds as PARTS of base contigs (include/breakscore.h: bs_scaffold_set): scaffold s is
+    ``base[part_base[i]][part_overlap[i]:]`` joined over ``i in part_start[s]:part_start[s+1]``.  What upstream's
+    ``assemble_contigs`` (lib/BreakageScorer.cpp:105-171) builds, before it is flattened into strings."""
+
+    def __init__(self, base_contigs, part_start, part_base, part_overlap, lib_path: str | None = None):
+        self.base_contigs = [c.encode("ascii") if isinstance(c, str) else bytes(c) for c in base_contigs]
+        self.base_chars, self.base_off = flatten(self.base_contigs)
+        self.part_start = np.ascontiguousarray(part_start, dtype=np.int64)
+        self.part_base = np.ascontiguousarray(part_base, dtype=np.int32)
+        self.part_overlap = np.ascontiguousarray(part_overlap, dtype=np.int32)
+        self._lib_path = lib_path
+
+    def __len__(self):
+        return len(self.part_start) - 1
+
+    def c_struct(self) -> _ScaffoldSet:
+        return _ScaffoldSet(len(self.base_contigs), self.base_chars.ctypes.data, self.base_off.ctypes.data, len(self),
+                            self.part_start.ctypes.data, self.part_base.ctypes.data, self.part_overlap.ctypes.data)
+
+    def lengths(self) -> np.ndarray:
+        lib = load_library(self._lib_path)
+        out = np.zeros(max(len(self), 1), np.int64)
+        rc = lib.bs_scaffold_lengths(C.byref(self.c_struct()), _ptr(out))
+        if rc != 0:
+            raise BreakscoreError(rc, lib.bs_assemble_last_error().decode())
+        return out[:len(self)]
+
+    def texts(self) -> list:
+        """the scaffold strings (host; what upstream's assemble_contigs returns)"""
+        lib = load_library(self._lib_path)
+        off = np.zeros(len(self) + 1, np.int64)
+        st = self.c_struct()
+        rc = lib.bs_scaffold_texts(C.byref(st), None, _ptr(off))
+        if rc != 0:
+            raise BreakscoreError(rc, lib.bs_assemble_last_error().decode())
+        chars = np.zeros(max(int(off[-1]), 1), np.uint8)
+        rc = lib.bs_scaffold_texts(C.byref(st), _ptr(chars), _ptr(off))
+        if rc != 0:
+            raise BreakscoreError(rc, lib.bs_assemble_last_error().decode())
+        return [chars[off[i]:off[i + 1]].tobytes() for i in range(len(self))]
 
 
 class BreakageScorer:
@@ -309,7 +380,8 @@ class BreakageScorer:
 
     # -- scoring -------------------------------------------------------------------------
     def score_batch(self, read_chars, read_off, read_len, contig_chars, contig_off, truth_chars,
-                    truth_off, seg_read_start, seg_contig_start, kmer=8, flags=DEFAULT_FLAGS, group=None, weights=None):
+                    truth_off, seg_read_start, seg_contig_start, kmer=8, flags=DEFAULT_FLAGS, group=None, weights=None,
+                    scaffolds: "ScaffoldSet | None" = None):
         """Many independent segments in one call (one upstream calc_breakscore call each).
         Host numpy buffers in, dict of numpy arrays out (flat path_prob_dist + offsets).
         ``group``: more scorers (one per GPU, same tables) -- ONE segment's contigs are then dealt out over
@@ -375,7 +447,16 @@ class BreakageScorer:
             r.pos_off = pos_off.ctypes.data
         if weights is not None:
             r.weights, r.weights_total = weights
-        if group:
+        if scaffolds is not None:
+            # the contigs are a scaffold set given as parts: contig_chars is not used, contig_off = its text offsets
+            if S != 1 or group:
+                raise ValueError("a scaffold set is scored for ONE segment on one scorer")
+            st = scaffolds.c_struct()
+            self._check(self._lib.bs_score_scaffolds(self._ctx, C.byref(st), read_chars.ctypes.data,
+                                                     None if read_off is None else read_off.ctypes.data, N, int(read_len or 0),
+                                                     truth_chars.ctypes.data + int(truth_off[0]), int(truth_off[1] - truth_off[0]),
+                                                     int(kmer), int(flags), C.byref(r)))
+        elif group:
             if S != 1:
                 raise ValueError("a scorer group shards the contigs of ONE segment (shard whole segments over processes instead)")
             if read_off is None:
@@ -424,6 +505,36 @@ class BreakageScorer:
         if flags & WANT_PROB_DIST:
             flat, off = res.pop("path_prob_dist_flat"), res.pop("path_prob_dist_off")
             res["path_prob_dist"] = [flat[off[i]:off[i + 1]] for i in range(len(path))]
+        return res
+
+    def score_scaffolds(self, scaffolds: ScaffoldSet, sequencing_reads, true_solution, kmer=8, flags=DEFAULT_FLAGS):
+        """:meth:`score` for a candidate set given as parts of base contigs (``assemble_scaffolds``): the same dict, but the
+        reads are placed once per BASE contig and every scaffold is scored from its parts and junction windows
+        (``bs_score_scaffolds``); the scaffold texts never leave the device.  ``res["sequence"]`` holds the texts."""
+        lens = scaffolds.lengths()
+        ct_off = np.zeros(len(scaffolds) + 1, np.int64)
+        np.cumsum(lens, out=ct_off[1:])
+        if isinstance(sequencing_reads, np.ndarray) and sequencing_reads.ndim == 2:
+            rd = np.ascontiguousarray(sequencing_reads, dtype=np.uint8).reshape(-1)
+            rd_off, rlen, nr = None, sequencing_reads.shape[1], sequencing_reads.shape[0]
+        else:
+            rd, rd_off = flatten(sequencing_reads)
+            rlen, nr = 0, len(sequencing_reads)
+        tr, tr_off = flatten([true_solution])
+        n = len(scaffolds)
+        res = self.score_batch(rd, rd_off, rlen, np.zeros(1, np.uint8), ct_off, tr, tr_off, [0, nr], [0, n], kmer=kmer, flags=flags,
+                               scaffolds=scaffolds)
+        res["sequence"] = scaffolds.texts()
+        if flags & WANT_PROB_DIST:
+            flat, off = res.pop("path_prob_dist_flat"), res.pop("path_prob_dist_off")
+            res["path_prob_dist"] = [flat[off[i]:off[i + 1]] for i in range(n)]
+            if flags & WANT_SECOND_TABLE:
+                flat2 = res.pop("path_prob_dist2_flat")
+                res["path_prob_dist2"] = [flat2[off[i]:off[i + 1]] for i in range(n)]
+        if flags & WANT_POS:
+            flat = res.pop("pos_flat")
+            res.pop("pos_off")
+            res["pos"] = flat[:n * nr].reshape(n, nr)
         return res
 
     def score_batch_raw(self, batch: _Batch, result: _Result, kmer: int, flags: int):
@@ -510,3 +621,30 @@ def assemble_contigs(velvet_contigs, dbg_kmer, seed, *, n_shuffles=20000, n_thre
     finally:
         lib.bs_string_list_free(h)
     return [out_chars[out_off[i]:out_off[i + 1]].tobytes() for i in range(n)]
+
+
+def assemble_scaffolds(velvet_contigs, dbg_kmer, seed, *, n_shuffles=20000, n_threads=0, lib_path=None):
+    """:func:`assemble_contigs` that keeps HOW every scaffold was glued together: returns ``(strings, ScaffoldSet)`` -- the
+    same strings in the same (upstream) order, and their parts for :meth:`BreakageScorer.score_scaffolds`."""
+    lib = load_library(lib_path)
+    chars, off = flatten(velvet_contigs)
+    h, hp = C.c_void_p(), C.c_void_p()
+    rc = lib.bs_assemble_scaffolds(_ptr(chars), _ptr(off), len(velvet_contigs), int(dbg_kmer), int(seed), int(n_shuffles),
+                                   int(n_threads), C.byref(h), C.byref(hp))
+    if rc != 0:
+        raise BreakscoreError(rc, lib.bs_assemble_last_error().decode())
+    try:
+        n = lib.bs_string_list_size(h)
+        out_chars = np.zeros(max(int(lib.bs_string_list_bytes(h)), 1), np.uint8)
+        out_off = np.zeros(n + 1, np.int64)
+        lib.bs_string_list_copy(h, _ptr(out_chars), _ptr(out_off))
+        n_parts = int(lib.bs_scaffold_list_parts(hp))
+        part_start = np.zeros(n + 1, np.int64)
+        part_base = np.zeros(max(n_parts, 1), np.int32)
+        part_overlap = np.zeros(max(n_parts, 1), np.int32)
+        lib.bs_scaffold_list_copy(hp, _ptr(part_start), _ptr(part_base), _ptr(part_overlap))
+    finally:
+        lib.bs_string_list_free(h)
+        lib.bs_scaffold_list_free(hp)
+    strings = [out_chars[out_off[i]:out_off[i + 1]].tobytes() for i in range(n)]
+    return strings, ScaffoldSet(velvet_contigs, part_start, part_base[:n_parts], part_overlap[:n_parts], lib_path)

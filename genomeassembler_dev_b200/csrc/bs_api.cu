@@ -54,6 +54,7 @@ constexpr int kSpectrumThreads = 64;
 constexpr int kSpectrumTabThreads = 64;
 constexpr int kPackThreads = 64;
 constexpr int kPlaceIxThreads = 64;
+constexpr int kComposeThreads = 64;
 constexpr int kHitCap = 16;           // (emulation: small, so that the tests reach the global continuation of the hit list)
 #else
 constexpr int kPlaceThreads = 256;
@@ -68,6 +69,7 @@ constexpr int kSpectrumThreads = 512;
 constexpr int kSpectrumTabThreads = bs::SPECTRUM_TAB_THREADS;
 constexpr int kPackThreads = 256;
 constexpr int kPlaceIxThreads = bs::PLACE_IX_THREADS;
+constexpr int kComposeThreads = bs::COMPOSE_THREADS;
 constexpr int kHitCap = BS_PLACE_HIT_CAP;  // reads placed per contig kept in shared memory (k_place_index); more go to global memory
 #endif
 constexpr int kMaxTile = 8192;        // contig positions per shared-memory tile (tile placement modes)
@@ -99,6 +101,7 @@ struct Workspace {
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
     DevBuf w, total, ycnt, yx, yx2, head, next, odd_head, spbest, exact, sp_key, sp_head, sp_next, sp_bitmap, sp_queue;
     DevBuf out_i32, out_f64, pd, pd2, hist, pos;
+    DevBuf base_chars, base_words, base_mask, base_pos, base_w, base_total, base_hits, base_cnt, base_di;  // compositional scoring: the base contigs of a scaffold set
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
 };
@@ -372,6 +375,10 @@ struct CallEnv {
     const int64_t *roff;     // read offsets or NULL (every read has rlen bytes, dense)
     int32_t rlen;
     int64_t T;
+    // compositional scoring (bs_score_scaffolds): the contigs of the call are scaffolds given as parts of base contigs
+    const bs_scaffold_set *comp = nullptr;
+    const int32_t *part_dst = nullptr;  // [parts] scaffold position of the first base a part adds
+    bool comp_score = false;            // the break k-mers are scored inside the compositional placement kernel
 };
 
 int64_t read_byte_begin(const CallEnv &e, int64_t n) { return e.roff ? e.roff[n] : n * (int64_t)e.rlen; }
@@ -409,11 +416,18 @@ struct ChunkRun {
     const int32_t *d_order_small = nullptr, *d_order_large = nullptr;  // work order split at KS_SMALL_MAX windows
     const int32_t *d_order_score = nullptr;                            // contigs below FUSE_MIN_LEN
     int64_t n_small = 0, n_large = 0, n_score = 0;
+    int64_t fuse_min_len = bs::FUSE_MIN_LEN;  // (BS_FUSE_MIN_LEN: tuning runs)
     const bs::PlaceItem *d_items = nullptr;
     const uint8_t *d_rchars = nullptr, *d_cchars = nullptr, *d_tchars = nullptr;
     bs::SeqSet cs, ts;
     bs::ReadSet rs;
     bs::ReadIndex ix;
+    // compositional scoring: the base contigs as their own small contig set, the parts of the scaffolds
+    bs::SeqSet bset;
+    bs::ScaffoldParts sparts;
+    const int64_t *d_base_off = nullptr, *d_base_woff = nullptr, *d_base_pos_off = nullptr;
+    const int32_t *d_base_seg = nullptr, *d_base_order = nullptr;
+    int64_t n_base = 0, base_bytes = 0, base_w_elems = 0, max_read_len = 0;
     int32_t *w_ptr = nullptr, *total_ptr = nullptr;  // position weights and reads placed per contig (workspace, or the caller's with BS_WEIGHTS_*)
 
     // result destinations on the device (user arrays with BS_DEVICE_RESULT, else the workspace)
@@ -429,6 +443,7 @@ struct ChunkRun {
     int prepare();    // metadata, buffers, H2D, result destinations, memsets
     int pack();       // 2-bit packing of contigs, truths and reads (+ read index)
     int place();      // leftmost placement of every read in every contig of its segment
+    int place_composed();  // ... of a scaffold set: reads placed in the base contigs, scaffolds from their parts
     int spectrum();   // truth-side distribution of the KS statistics
     bool fused(int which) const;  // scores computed inside the KS-A kernels (kmer == 8, no dense histogram, those kernels run)
     int score_args(int which, int64_t rows, bs::ScoreArgs &sa);  // k_break_score's arguments (rows: blocks that may use a scratch row)
@@ -448,6 +463,7 @@ int ChunkRun::prepare() {
     }
 
     // ---------------- chunk-local metadata ----------------
+    const bool comp = e.comp != nullptr;  // the contigs are scaffolds given as parts: their text is composed on the device
     const int64_t ctg_b0 = b->contig_off[ch.c0], ctg_bytes = b->contig_off[ch.c1] - ctg_b0;
     const int64_t tr_b0 = b->truth_off[ch.s0], tr_bytes = b->truth_off[ch.s1] - tr_b0;
     const int64_t rd_b0 = read_byte_begin(e, ch.r0), read_bytes = read_byte_begin(e, ch.r1) - rd_b0;
@@ -523,6 +539,7 @@ int ChunkRun::prepare() {
     }
     if (max_read > 0x3fffffff) return fail(ctx, BS_ERR_INVALID, "read longer than 2^30");
     W = (int)std::max<int64_t>(1, (max_read + 31) / 32);
+    max_read_len = max_read;
     tile_mode = (e.flags & (BS_PLACE_SCAN | BS_PLACE_TILE)) != 0;
 
     // placement order of the index kernel: longest contigs first
@@ -549,8 +566,9 @@ int ChunkRun::prepare() {
     n_large = (int64_t)order_large.size();
     // k_break_score's share when the long-contig KS-A kernel scores on its way (fused()): contigs below FUSE_MIN_LEN
     std::vector<int32_t> order_score;
+    if (const char *env = std::getenv("BS_FUSE_MIN_LEN")) fuse_min_len = std::max<int64_t>(std::atoll(env), bs::KS_SMALL_MAX + bs::MAXK + 1);
     for (int32_t c : order)
-        if (ctg_off[c + 1] - ctg_off[c] < bs::FUSE_MIN_LEN) order_score.push_back(c);
+        if (ctg_off[c + 1] - ctg_off[c] < fuse_min_len) order_score.push_back(c);
     n_score = (int64_t)order_score.size();
     if (tile_mode) {
         // tile placement: one work item per (contig, read chunk)
@@ -621,6 +639,34 @@ int ChunkRun::prepare() {
     const size_t o_pd_off = e.want_pd ? mb.add(pd_off.data(), (size_t)C + 1) : 0;
     const size_t o_pos_off = e.want_pos ? mb.add(pos_off.data(), (size_t)C + 1) : 0;
     const size_t o_roff = e.roff ? mb.add(roff_local.data(), (size_t)N + 1) : 0;
+    // compositional scoring: the base contigs as a contig set of their own (one segment) and the parts of the scaffolds
+    size_t o_base_off = 0, o_base_woff = 0, o_base_seg = 0, o_base_order = 0, o_base_pos_off = 0, o_part_start = 0, o_part_base = 0,
+           o_part_ov = 0, o_part_dst = 0;
+    int64_t base_words = 0;
+    if (comp) {
+        const bs_scaffold_set *cp = e.comp;
+        n_base = cp->n_base;
+        std::vector<int64_t> base_off((size_t)n_base + 1), base_woff((size_t)n_base + 1), base_pos_off((size_t)n_base + 1);
+        std::vector<int32_t> base_seg((size_t)std::max<int64_t>(n_base, 1), 0), base_order((size_t)n_base);
+        base_woff[0] = 0;
+        for (int64_t i = 0; i <= n_base; i++) { base_off[i] = cp->base_off[i] - cp->base_off[0]; base_pos_off[i] = i * N; }
+        for (int64_t i = 0; i < n_base; i++) base_woff[i + 1] = base_woff[i] + (base_off[i + 1] - base_off[i] + 31) / 32 + 2;
+        std::iota(base_order.begin(), base_order.end(), 0);
+        std::stable_sort(base_order.begin(), base_order.end(), [&](int32_t x, int32_t y) { return base_off[x + 1] - base_off[x] > base_off[y + 1] - base_off[y]; });
+        base_bytes = base_off[n_base];
+        base_words = base_woff[n_base];
+        base_w_elems = base_bytes + n_base;
+        const int64_t n_parts = cp->scaffold_part_start[cp->n_scaffolds];
+        o_base_off = mb.add(base_off.data(), base_off.size());
+        o_base_woff = mb.add(base_woff.data(), base_woff.size());
+        o_base_seg = mb.add(base_seg.data(), base_seg.size());
+        o_base_order = mb.add(base_order.data(), base_order.size());
+        o_base_pos_off = mb.add(base_pos_off.data(), base_pos_off.size());
+        o_part_start = mb.add(cp->scaffold_part_start, (size_t)cp->n_scaffolds + 1);
+        o_part_base = mb.add(cp->part_base, (size_t)n_parts);
+        o_part_ov = mb.add(cp->part_overlap, (size_t)n_parts);
+        o_part_dst = mb.add(e.part_dst, (size_t)n_parts);
+    }
 
     if (mb.bytes.size() > ws.h_meta_cap) {
         if (ws.h_meta) cudaFreeHost(ws.h_meta);
@@ -641,8 +687,19 @@ int ChunkRun::prepare() {
     BS_TRY(ensure(ctx, ws.meta, mb.bytes.size()));
     if (!e.dev_chars) {
         BS_TRY(ensure(ctx, ws.read_chars, (size_t)read_bytes + 32));
-        BS_TRY(ensure(ctx, ws.ctg_chars, (size_t)ctg_bytes + 32));
         BS_TRY(ensure(ctx, ws.tr_chars, (size_t)tr_bytes + 32));
+    }
+    if (!e.dev_chars || comp) BS_TRY(ensure(ctx, ws.ctg_chars, (size_t)ctg_bytes + 32));
+    if (comp) {
+        BS_TRY(ensure(ctx, ws.base_chars, (size_t)base_bytes + 32));
+        BS_TRY(ensure(ctx, ws.base_words, (size_t)base_words * 8 + 8));
+        BS_TRY(ensure(ctx, ws.base_mask, (size_t)base_words * 4 + 8));
+        BS_TRY(ensure(ctx, ws.base_pos, (size_t)std::max<int64_t>(n_base * N, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_w, (size_t)std::max<int64_t>(base_w_elems, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_total, (size_t)std::max<int64_t>(n_base, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_hits, (size_t)std::max<int64_t>(n_base * N, 1) * 8));
+        BS_TRY(ensure(ctx, ws.base_cnt, (size_t)std::max<int64_t>(n_base, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_di, (size_t)std::max<int64_t>(n_base * N, 1) * 4));
     }
     BS_TRY(ensure(ctx, ws.rwords, (size_t)std::max<int64_t>(N, 1) * W * 8));
     BS_TRY(ensure(ctx, ws.rflags, (size_t)std::max<int64_t>(N, 1) + 8));
@@ -654,9 +711,9 @@ int ChunkRun::prepare() {
         w_ptr = res->weights + (b->contig_off[ch.c0] - b->contig_off[0]) + ch.c0;
         total_ptr = res->weights_total + ch.c0;
     } else {
-        BS_TRY(ensure(ctx, ws.w, (size_t)w_elems * 4));
+        if (!e.comp_score) BS_TRY(ensure(ctx, ws.w, (size_t)w_elems * 4));  // (scored inside the compositional placement: no position weights)
         BS_TRY(ensure(ctx, ws.total, (size_t)C * 4));
-        w_ptr = (int32_t *)ws.w.p;
+        w_ptr = e.comp_score ? nullptr : (int32_t *)ws.w.p;
         total_ptr = (int32_t *)ws.total.p;
     }
     if (!tile_mode) {
@@ -694,6 +751,14 @@ int ChunkRun::prepare() {
     d_pd_off = e.want_pd ? (const int64_t *)(dm + o_pd_off) : nullptr;
     d_pos_off = e.want_pos ? (const int64_t *)(dm + o_pos_off) : nullptr;
     d_roff = e.roff ? (const int64_t *)(dm + o_roff) : nullptr;
+    if (comp) {
+        d_base_off = (const int64_t *)(dm + o_base_off); d_base_woff = (const int64_t *)(dm + o_base_woff);
+        d_base_seg = (const int32_t *)(dm + o_base_seg); d_base_order = (const int32_t *)(dm + o_base_order);
+        d_base_pos_off = (const int64_t *)(dm + o_base_pos_off);
+        sparts.part_start = (const int64_t *)(dm + o_part_start); sparts.part_base = (const int32_t *)(dm + o_part_base);
+        sparts.part_ov = (const int32_t *)(dm + o_part_ov); sparts.part_dst = (const int32_t *)(dm + o_part_dst);
+        bset = bs::SeqSet{(const uint8_t *)ws.base_chars.p, d_base_off, d_base_woff, (uint64_t *)ws.base_words.p, (uint32_t *)ws.base_mask.p, n_base, base_words};
+    }
 
     // ---------------- H2D (copy stream) ----------------
     {
@@ -706,11 +771,15 @@ int ChunkRun::prepare() {
             d_tchars = (const uint8_t *)b->truth_chars + tr_b0;
         } else {
             if (read_bytes) BS_CUDA(cudaMemcpyAsync(ws.read_chars.p, e.read_chars + rd_b0, (size_t)read_bytes, cudaMemcpyHostToDevice, cs));
-            if (ctg_bytes) BS_CUDA(cudaMemcpyAsync(ws.ctg_chars.p, b->contig_chars + ctg_b0, (size_t)ctg_bytes, cudaMemcpyHostToDevice, cs));
+            if (ctg_bytes && !comp) BS_CUDA(cudaMemcpyAsync(ws.ctg_chars.p, b->contig_chars + ctg_b0, (size_t)ctg_bytes, cudaMemcpyHostToDevice, cs));
             if (tr_bytes) BS_CUDA(cudaMemcpyAsync(ws.tr_chars.p, b->truth_chars + tr_b0, (size_t)tr_bytes, cudaMemcpyHostToDevice, cs));
             d_rchars = (const uint8_t *)ws.read_chars.p;
             d_cchars = (const uint8_t *)ws.ctg_chars.p;
             d_tchars = (const uint8_t *)ws.tr_chars.p;
+        }
+        if (comp) {  // only the base contigs cross PCIe; k_compose_text writes the scaffold texts into the workspace
+            if (base_bytes) BS_CUDA(cudaMemcpyAsync(ws.base_chars.p, e.comp->base_chars + e.comp->base_off[0], (size_t)base_bytes, cudaMemcpyHostToDevice, cs));
+            d_cchars = (const uint8_t *)ws.ctg_chars.p;
         }
     }
     BS_CUDA(cudaEventRecord(ws.ev_h2d, ctx->copy_stream));
@@ -760,8 +829,14 @@ int ChunkRun::prepare() {
     }
 
     if (!e.w_in) {
-        BS_CUDA(cudaMemsetAsync(w_ptr, 0, (size_t)w_elems * 4, st));
+        if (w_ptr) BS_CUDA(cudaMemsetAsync(w_ptr, 0, (size_t)w_elems * 4, st));
         BS_CUDA(cudaMemsetAsync(total_ptr, 0, (size_t)C * 4, st));
+    }
+    if (comp) {
+        BS_CUDA(cudaMemsetAsync(ws.base_w.p, 0, (size_t)std::max<int64_t>(base_w_elems, 1) * 4, st));
+        BS_CUDA(cudaMemsetAsync(ws.base_total.p, 0, (size_t)std::max<int64_t>(n_base, 1) * 4, st));
+        BS_CUDA(cudaMemsetAsync(ws.base_cnt.p, 0, (size_t)std::max<int64_t>(n_base, 1) * 4, st));
+        BS_CUDA(cudaMemsetAsync(ws.base_pos.p, 0xff, (size_t)std::max<int64_t>(n_base * N, 1) * 4, st));
     }
     BS_TRY(ensure(ctx, ctx->d_counters, 64));
     BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));  // work counters of the persistent kernels
@@ -783,6 +858,17 @@ int ChunkRun::prepare() {
 int ChunkRun::pack() {
     {
         StageTimer tm(ctx, ST_PACK, st);
+        if (e.comp) {  // base contigs packed as their own set; scaffold texts written from them, then packed like any contig
+            if (n_base > 0) {
+                BS_LAUNCH(bs::k_pack_seqs, grid_for(bset.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, bset);
+                ctx->launches++;
+            }
+            bs::ComposeTextArgs ca;
+            ca.sp = sparts; ca.base_chars = bset.chars; ca.base_off = d_base_off; ca.ctg_off = d_ctg_off; ca.ctg_chars = (uint8_t *)ws.ctg_chars.p;
+            ca.n_scaffolds = C;
+            BS_LAUNCH(bs::k_compose_text, (unsigned)std::min<int64_t>(C, (int64_t)ctx->sm_count * 8), kPackThreads, 0, st, ca);
+            ctx->launches++;
+        }
         BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
         ctx->launches++;
         if ((e.want_ks || e.want_sp || e.want_lev) && !e.w_out) {
@@ -909,6 +995,100 @@ int ChunkRun::place() {
     return BS_OK;
 }
 
+// Scaffold sets (bs_score_scaffolds): the reads are placed in the BASE contigs (k_place_index with the dense leftmost
+// positions out), then every scaffold takes the minimum over its parts and probes its junction windows (k_place_compose),
+// which also scores the break k-mers unless position weights are needed (second table).
+int ChunkRun::place_composed() {
+    StageTimer tm(ctx, ST_PLACE, st);
+    if (C <= 0) return BS_OK;
+    if (N > 0 && n_base > 0) {
+        const size_t smem = bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads);
+        const int per_sm = blocks_per_sm(bs::k_place_index<false>, kPlaceIxThreads, smem);
+        const int nblk = (int)std::min<int64_t>(n_base, (int64_t)ctx->sm_count * per_sm);
+        const int64_t dense_stride = (max_seg_reads + 31) / 32 * 32;
+        bs::PlaceIxArgs pa;
+        pa.order = d_base_order; pa.n_items = (int32_t)n_base; pa.work_counter = (int32_t *)ctx->d_counters.p + 11;
+        pa.ctg_off = d_base_off; pa.ctg_woff = d_base_woff; pa.ctg_words = bset.words; pa.ctg_mask = bset.mask;
+        pa.ctg_chars = bset.chars; pa.ctg_seg = d_base_seg;
+        pa.reads = rs; pa.ix = ix;
+        pa.w = (int32_t *)ws.base_w.p; pa.total = (int32_t *)ws.base_total.p;
+        pa.pos = (int32_t *)ws.base_pos.p; pa.pos_off = d_base_pos_off;
+        pa.hit_cap = kHitCap; pa.keys = nullptr; pa.overflow = nullptr;
+        const size_t need = (size_t)nblk * (size_t)dense_stride;
+        if (need > ctx->best_elems || ctx->best_dirty) {
+            const size_t elems = std::max(need, ctx->best_elems);
+            BS_TRY(ensure(ctx, ctx->d_best, elems * 4));
+            ctx->best_elems = elems;
+            BS_CUDA(cudaMemsetAsync(ctx->d_best.p, 0x7f, elems * 4, st));
+        }
+        BS_TRY(ensure(ctx, ctx->d_hits_ovf, need * 4));
+        ctx->best_dirty = true;  // cleared when the call ends without an error
+        pa.best = (uint32_t *)ctx->d_best.p; pa.best_stride = dense_stride;
+        pa.hits_ovf = (uint32_t *)ctx->d_hits_ovf.p;
+        BS_CUDA(cudaFuncSetAttribute(bs::k_place_index<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BS_LAUNCH(bs::k_place_index<false>, (unsigned)nblk, kPlaceIxThreads, smem, st, pa);
+        ctx->launches++;
+    }
+    if (n_base > 0) {  // per base contig, once: the list of reads placed in it and the break 8-mer of its interior positions
+        bs::BaseSideArgs ba;
+        ba.base_pos = (const int32_t *)ws.base_pos.p; ba.n_base = n_base; ba.n_reads = N;
+        ba.hits = (uint2 *)ws.base_hits.p; ba.hit_di = (int32_t *)ws.base_di.p; ba.cnt = (int32_t *)ws.base_cnt.p;
+        ba.base_off = d_base_off; ba.base_woff = d_base_woff; ba.base_words = bset.words; ba.base_mask = bset.mask;
+        ba.kmer = kmer;
+        BS_LAUNCH(bs::k_base_side, (unsigned)n_base, kScoreThreads, kScoreThreads * 8 + 16, st, ba);
+        ctx->launches++;
+    }
+    bs::PlaceComposeArgs ca;
+    std::memset(&ca, 0, sizeof(ca));
+    ca.p.order = d_order; ca.p.n_items = (int32_t)C; ca.p.work_counter = (int32_t *)ctx->d_counters.p + 12;
+    ca.p.ctg_off = d_ctg_off; ca.p.ctg_woff = d_ctg_woff; ca.p.ctg_words = cs.words; ca.p.ctg_mask = cs.mask;
+    ca.p.ctg_chars = d_cchars; ca.p.ctg_seg = d_ctg_seg;
+    ca.p.reads = rs; ca.p.ix = ix;
+    ca.p.w = w_ptr; ca.p.total = total_ptr; ca.p.pos = o_pos; ca.p.pos_off = d_pos_off;
+    ca.sp = sparts; ca.n_reads = N; ca.max_read_len = (int32_t)max_read_len;
+    ca.base_hits = (const uint2 *)ws.base_hits.p; ca.base_cnt = (const int32_t *)ws.base_cnt.p; ca.base_hit_di = (const int32_t *)ws.base_di.p;
+    // dynamic shared memory of a block: (scored here) the hash table of the break k-mers, sized for the reads one scaffold can
+    // place so that KS-B never needs the global scratch rows; then the block's row of leftmost positions per read, while two
+    // blocks per SM fit -- else the row lives in global memory (L2)
+    // (an SM holds 228 KB of shared memory, 1 KB of it reserved per resident block; the kernel's static part goes off as well)
+    const size_t static_smem = sizeof(bs::ScoreSharedCore) + 4 * (size_t)(bs::COMPOSE_PART_CHUNK + 1) * 4 + 256;
+    const size_t budget = ((size_t)228 * 1024) / 2 - 1024 - static_smem;
+    int hash_slots = 0;
+    if (e.comp_score) {
+        hash_slots = bs::HASH_SLOTS;
+        while (hash_slots < 32768 && (int64_t)hash_slots * 2 / 3 < std::min<int64_t>(N, 32767)) hash_slots <<= 1;
+        while (hash_slots > bs::HASH_SLOTS && (size_t)hash_slots * 4 > budget) hash_slots >>= 1;
+        if (const char *env = std::getenv("BS_COMPOSE_HASH_SLOTS")) {  // tests: a small table sends scaffolds through the global scratch rows
+            hash_slots = 64;
+            while (hash_slots < std::atoi(env) && hash_slots < 32768) hash_slots <<= 1;
+        }
+    }
+    ca.hash_slots = hash_slots;
+    const size_t hash_bytes = (size_t)hash_slots * 4;
+    const size_t row_bytes = (size_t)std::max<int64_t>(N, 1) * 4;
+    const char *rows_env = std::getenv("BS_COMPOSE_ROWS");  // tests: "global" keeps the rows out of shared memory
+    const bool row_smem = hash_bytes + row_bytes <= budget && !(rows_env && rows_env[0] == 'g');
+    const size_t smem = hash_bytes + (row_smem ? row_bytes : 0);
+    auto launch = [&](auto kern) -> int {
+        BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int nblk = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(kern, kComposeThreads, smem));
+        if (!row_smem) {
+            ca.row_stride = (N + 31) / 32 * 32;
+            BS_TRY(ensure(ctx, ctx->d_hits_ovf, (size_t)nblk * (size_t)ca.row_stride * 4));  // (free again: the base placement is ahead on the same stream)
+            ca.rows = (uint32_t *)ctx->d_hits_ovf.p;
+        }
+        if (e.comp_score) BS_TRY(score_args(0, nblk, ca.sc));
+        BS_LAUNCH(kern, (unsigned)nblk, kComposeThreads, smem, st, ca);
+        ctx->launches++;
+        return BS_OK;
+    };
+    if (e.comp_score && row_smem) BS_TRY(launch(bs::k_place_compose<true, true>));
+    else if (e.comp_score) BS_TRY(launch(bs::k_place_compose<true, false>));
+    else if (row_smem) BS_TRY(launch(bs::k_place_compose<false, true>));
+    else BS_TRY(launch(bs::k_place_compose<false, false>));
+    return BS_OK;
+}
+
 int ChunkRun::spectrum() {
     if (e.want_ks) {
         const KsCache &k = ctx->ks;
@@ -959,7 +1139,7 @@ bool ChunkRun::fused(int which) const {
     const bool ksa = which ? o_ksa2 != nullptr : ks_a;
     // contigs of at least bs::FUSE_MIN_LEN bases are then scored by the long-contig KS-A kernel, the others by k_break_score
     const char *env = std::getenv("BS_FUSE_SCORE");  // tests / tuning: 0 keeps k_break_score for every contig
-    return kmer == 8 && !e.want_hist && (e.want_pd || ksa) && !(env && env[0] == '0');
+    return kmer == 8 && !e.want_hist && !e.comp_score && (e.want_pd || ksa) && !(env && env[0] == '0');
 }
 
 int ChunkRun::score_args(int which, int64_t rows, bs::ScoreArgs &sa) {
@@ -993,6 +1173,7 @@ int ChunkRun::score_args(int which, int64_t rows, bs::ScoreArgs &sa) {
 }
 
 int ChunkRun::score(int which) {
+    if (e.comp_score) return BS_OK;  // done inside k_place_compose
     const bool fz = fused(which);  // the long-contig KS-A kernel scores contigs of FUSE_MIN_LEN bases and more on its way
     const int64_t n = fz ? n_score : C;
     if (n > 0) {
@@ -1051,6 +1232,7 @@ int ChunkRun::prob_dist(int which) {
             nb_small = (int)std::min<int64_t>(n_small, (int64_t)ctx->sm_count * blocks_per_sm(small_kernel, bs::KS_SMALL_THREADS, small_smem));
         }
         std::memset(&pa.sc, 0, sizeof(pa.sc));
+        pa.fuse_min_len = fuse_min_len;
         if (fuse) BS_TRY(score_args(which, std::max(nb_small, nblk), pa.sc));  // (a scratch row per block of the wider launch)
         if (use_small) {
             bs::ProbDistArgs ps = pa;
@@ -1267,10 +1449,11 @@ int run_chunk(bs_ctx *ctx, Workspace &ws, const CallEnv &e, const Chunk &ch) {
     tr.lap("prepare");
     BS_TRY(r.pack());
     tr.lap("pack");
-    if (!e.w_in) BS_TRY(r.place());
+    if (e.comp_score) BS_TRY(r.spectrum());  // (the compositional placement scores on its way: KS-B needs the truth side first)
+    if (!e.w_in) BS_TRY(e.comp ? r.place_composed() : r.place());
     tr.lap("place");
     if (e.w_out) return r.results();  // phase 1 of a two-phase call: the weights are the result
-    BS_TRY(r.spectrum());
+    if (!e.comp_score) BS_TRY(r.spectrum());
     BS_TRY(r.score(0));
     BS_TRY(r.prob_dist(0));
     BS_TRY(r.second_table());
@@ -1347,7 +1530,8 @@ void bs_ctx_destroy(bs_ctx *ctx) {
     for (Workspace &w : ctx->ws) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
                         &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.yx2, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact, &w.sp_key, &w.sp_head, &w.sp_next, &w.sp_bitmap, &w.sp_queue,
-                        &w.out_i32, &w.out_f64, &w.pd, &w.pd2, &w.hist, &w.pos};
+                        &w.out_i32, &w.out_f64, &w.pd, &w.pd2, &w.hist, &w.pos,
+                        &w.base_chars, &w.base_words, &w.base_mask, &w.base_pos, &w.base_w, &w.base_total, &w.base_hits, &w.base_cnt, &w.base_di};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);
         if (w.ev_h2d) cudaEventDestroy(w.ev_h2d);
@@ -1569,7 +1753,8 @@ static int bs_set_truth_table_impl(bs_ctx *ctx, const double *prob, int64_t n) {
     return BS_OK;
 }
 
-static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res);
+static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res,
+                            const bs_scaffold_set *comp = nullptr, const int32_t *part_dst = nullptr);
 
 // nothing throws across the boundary: host allocation failures of the std containers used inside become a status
 int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res) {
@@ -1585,7 +1770,8 @@ int bs_score_batch(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_
     }
 }
 
-static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res) {
+static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t flags, bs_result *res,
+                            const bs_scaffold_set *comp, const int32_t *part_dst) {
     if (!b || !res) return fail(ctx, BS_ERR_INVALID, "bs_score_batch: NULL batch or result");
     if (!ctx->has_table) return fail(ctx, BS_ERR_STATE, "bs_score_batch before bs_set_table");
     if (kmer < 1) return fail(ctx, BS_ERR_INVALID, "kmer must be >= 1 (got %d)", kmer);
@@ -1611,7 +1797,7 @@ static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t f
     if (C == 0) return BS_OK;
     const int64_t read_total = b->read_off ? b->read_off[N] : N * (int64_t)b->read_len;
     if (N > 0 && !b->read_chars && read_total > 0) return fail(ctx, BS_ERR_INVALID, "read_chars is NULL");
-    if (b->contig_off[C] > 0 && !b->contig_chars) return fail(ctx, BS_ERR_INVALID, "contig_chars is NULL");
+    if (b->contig_off[C] > 0 && !b->contig_chars && !comp) return fail(ctx, BS_ERR_INVALID, "contig_chars is NULL");
     if (b->truth_off[S] > 0 && !b->truth_chars) return fail(ctx, BS_ERR_INVALID, "truth_chars is NULL");
     cudaSetDevice(ctx->device);
 
@@ -1636,6 +1822,18 @@ static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t f
         e.want_ks = e.want_pd = e.want_hist = e.want_sp = e.want_lev = e.second = false;
     }
     if (e.second && !ctx->has_table2) return fail(ctx, BS_ERR_STATE, "BS_WANT_SECOND_TABLE before bs_set_second_table");
+    if (comp) {
+        if (e.w_out || e.w_in || (flags & (BS_PLACE_SCAN | BS_PLACE_TILE)))
+            return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: BS_WEIGHTS_* and BS_PLACE_SCAN / BS_PLACE_TILE do not apply to a scaffold set");
+        if (S != 1) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: one segment per call");
+        if (comp->n_base * N > ((int64_t)1 << 31)) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: base contigs x reads = %lld exceeds 2^31 (score the texts with bs_score)", (long long)(comp->n_base * N));
+        e.comp = comp;
+        e.part_dst = part_dst;
+        // the second table needs the position weights (its scores come from k_break_score): then the compositional kernel
+        // writes them and the scoring stages run as for any contig set
+        const char *env = std::getenv("BS_COMPOSE_SCORE");  // tests: 0 keeps the weights path
+        e.comp_score = !e.second && !(env && env[0] == '0');
+    }
     if (e.second && e.want_pd && !res->path_prob_dist2) return fail(ctx, BS_ERR_INVALID, "BS_WANT_SECOND_TABLE with BS_WANT_PROB_DIST needs path_prob_dist2");
     e.read_chars = b->read_chars;
     e.roff = b->read_off;
@@ -1728,6 +1926,51 @@ static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t f
     if (!e.want_sp && res->path_prob_dist_startpos) std::memset(res->path_prob_dist_startpos, 0, (size_t)C * 4);
     if (status) return fail(ctx, BS_ERR_INVALID, "ks_stat_path_freq: more than %d table rows with a count >= %d in one contig", bs::OVF_CAP, bs::CC_DENSE);
     return BS_OK;
+}
+
+// full validation of a scaffold set (bs_assemble.cpp)
+int bs_scaffold_validate(const bs_scaffold_set *set, int64_t *lengths, int32_t *part_dst, char *err, size_t errn);
+
+static int score_scaffolds_impl(bs_ctx *ctx, const bs_scaffold_set *set, const char *read_chars, const int64_t *read_off, int64_t n_reads,
+                                int32_t read_len, const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *result) {
+    if (!set || !result) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: NULL set or result");
+    if (truth_len < 0 || n_reads < 0) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: negative size");
+    const int64_t C = set->n_scaffolds;
+    if (C < 0) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: negative scaffold count");
+    if (C == 0) return BS_OK;
+    const int64_t n_parts = set->scaffold_part_start ? set->scaffold_part_start[C] : 0;
+    std::vector<int64_t> off((size_t)C + 1, 0);
+    std::vector<int32_t> part_dst((size_t)std::max<int64_t>(n_parts, 1));
+    {
+        std::vector<int64_t> len((size_t)C);
+        char msg[256] = "";
+        if (bs_scaffold_validate(set, len.data(), part_dst.data(), msg, sizeof msg) != BS_OK) return fail(ctx, BS_ERR_INVALID, "%s", msg);
+        for (int64_t c = 0; c < C; c++) off[(size_t)c + 1] = off[(size_t)c] + len[(size_t)c];
+    }
+    const int64_t truth_off[2] = {0, truth_len};
+    const int64_t seg_r[2] = {0, n_reads}, seg_c[2] = {0, C};
+    bs_batch b;
+    std::memset(&b, 0, sizeof(b));
+    b.n_segments = 1; b.n_reads = n_reads; b.n_contigs = C;
+    b.read_chars = read_chars; b.read_off = read_off; b.read_len = read_len;
+    b.contig_chars = nullptr; b.contig_off = off.data();
+    b.truth_chars = truth; b.truth_off = truth_off;
+    b.seg_read_start = seg_r; b.seg_contig_start = seg_c;
+    return score_batch_impl(ctx, &b, kmer, flags, result, set, part_dst.data());
+}
+
+int bs_score_scaffolds(bs_ctx *ctx, const bs_scaffold_set *set, const char *read_chars, const int64_t *read_off, int64_t n_reads,
+                       int32_t read_len, const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *result) {
+    if (!ctx) return BS_ERR_INVALID;
+    try {
+        return score_scaffolds_impl(ctx, set, read_chars, read_off, n_reads, read_len, truth, truth_len, kmer, flags, result);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, BS_ERR_ALLOC, "bs_score_scaffolds: out of host memory");
+    } catch (const std::exception &ex) {
+        return fail(ctx, BS_ERR_STATE, "bs_score_scaffolds: %s", ex.what());
+    } catch (...) {
+        return fail(ctx, BS_ERR_STATE, "bs_score_scaffolds: unknown exception");
+    }
 }
 
 int bs_score(bs_ctx *ctx, const char *contig_chars, const int64_t *contig_off, int64_t n_contigs,

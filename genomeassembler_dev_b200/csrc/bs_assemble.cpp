@@ -26,6 +26,7 @@
 #include <random>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -37,10 +38,21 @@ struct StringList {
     std::vector<std::string> items;
 };
 
+// how a scaffold was glued together: (base contig, overlap with the scaffold so far) per part
+struct Part {
+    int32_t base, overlap;
+};
+typedef std::vector<Part> Composition;
+struct ScaffoldList {
+    std::vector<int64_t> part_start;
+    std::vector<int32_t> part_base, part_overlap;
+};
+
 thread_local char g_assemble_error[256] = "";
 
 // one permutation: greedy suffix/prefix merging, exactly the sweep order of upstream :105-143
-void merge_permutation(std::vector<std::string> &contigs, int dbg_kmer) {
+// comps (optional): the parts of every string of `contigs`, kept in step with it
+void merge_permutation(std::vector<std::string> &contigs, int dbg_kmer, std::vector<Composition> *comps = nullptr) {
     for (int k = dbg_kmer - 1; k > 0; k--) {
         bool len_changed = true;
         while (len_changed) {
@@ -56,7 +68,20 @@ void merge_permutation(std::vector<std::string> &contigs, int dbg_kmer) {
                     if (std::memcmp(a.data() + a.size() - k, b.data(), (size_t)k) != 0) continue;
                     a.append(b, (size_t)k, std::string::npos);
                     contigs[jj].clear();
+                    if (comps) {  // j's parts follow i's; its first part now overlaps the end of i by k
+                        Composition &ci = (*comps)[i], &cj = (*comps)[jj];
+                        const size_t at = ci.size();
+                        ci.insert(ci.end(), cj.begin(), cj.end());
+                        ci[at].overlap = k;
+                        cj.clear();
+                    }
                 }
+            }
+            if (comps) {  // (an input contig that is empty to begin with has parts but no text: it goes with its string)
+                size_t o = 0;
+                for (size_t i = 0; i < contigs.size(); i++)
+                    if (!contigs[i].empty()) { if (o != i) (*comps)[o] = std::move((*comps)[i]); o++; }
+                comps->resize(o);
             }
             contigs.erase(std::remove_if(contigs.begin(), contigs.end(), [](const std::string &s) { return s.empty(); }),
                           contigs.end());
@@ -72,7 +97,7 @@ extern "C" {
 const char *bs_assemble_last_error(void) { return g_assemble_error; }
 
 static int assemble_impl(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer, int seed,
-                         int n_shuffles, int n_threads, bs_string_list **out);
+                         int n_shuffles, int n_threads, bs_string_list **out, bs_scaffold_list **parts = nullptr);
 
 // nothing throws across the boundary (bad_alloc of the containers, system_error of std::thread)
 int bs_assemble_contigs(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer, int seed,
@@ -91,9 +116,30 @@ int bs_assemble_contigs(const char *contig_chars, const int64_t *contig_off, int
     }
 }
 
+int bs_assemble_scaffolds(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer, int seed,
+                          int n_shuffles, int n_threads, bs_string_list **out, bs_scaffold_list **parts) {
+    if (!parts) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_scaffolds: parts is NULL");
+        return BS_ERR_INVALID;
+    }
+    try {
+        return assemble_impl(contig_chars, contig_off, n_contigs, dbg_kmer, seed, n_shuffles, n_threads, out, parts);
+    } catch (const std::bad_alloc &) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_scaffolds: out of host memory");
+        return BS_ERR_ALLOC;
+    } catch (const std::exception &ex) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_scaffolds: %.200s", ex.what());
+        return BS_ERR_STATE;
+    } catch (...) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_scaffolds: unknown exception");
+        return BS_ERR_STATE;
+    }
+}
+
 static int assemble_impl(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer, int seed,
-                         int n_shuffles, int n_threads, bs_string_list **out) {
+                         int n_shuffles, int n_threads, bs_string_list **out, bs_scaffold_list **parts) {
     g_assemble_error[0] = 0;
+    if (parts) *parts = nullptr;
     if (!out || !contig_off || n_contigs < 0 || n_shuffles < 0 || (n_contigs > 0 && !contig_chars)) {
         std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_assemble_contigs: bad argument");
         return BS_ERR_INVALID;
@@ -135,25 +181,49 @@ static int assemble_impl(const char *contig_chars, const int64_t *contig_off, in
     perms.erase(std::unique(perms.begin(), perms.end()), perms.end());
 
     std::unordered_set<std::string> found;
+    std::unordered_map<std::string, Composition> found_comp;  // (with parts) one composition per distinct scaffold: the first one seen
     std::mutex mu;
     std::atomic<size_t> next_perm{0};
     unsigned nt = n_threads > 0 ? (unsigned)n_threads : std::max(1u, std::thread::hardware_concurrency());
     nt = (unsigned)std::min<size_t>(nt, std::max<size_t>(perms.size(), 1));
     std::atomic<bool> failed{false};  // an exception inside a worker (bad_alloc): reported after the join, never escapes a thread
+    // which of several equal-text compositions is kept must not depend on threads or timing: the smallest one
+    auto keep_smallest = [](std::unordered_map<std::string, Composition> &m, const std::string &text, Composition &&comp) {
+        auto less = [](const Composition &x, const Composition &y) {
+            return std::lexicographical_compare(x.begin(), x.end(), y.begin(), y.end(), [](const Part &a, const Part &b) {
+                return a.base != b.base ? a.base < b.base : a.overlap < b.overlap; });
+        };
+        auto it = m.find(text);
+        if (it == m.end()) m.emplace(text, std::move(comp));
+        else if (less(comp, it->second)) it->second = std::move(comp);
+    };
     auto worker = [&]() {
         try {
             std::unordered_set<std::string> local;
+            std::unordered_map<std::string, Composition> local_comp;
             std::vector<std::string> contigs;
+            std::vector<Composition> comps;
             for (;;) {
                 const size_t p = next_perm.fetch_add(1);
                 if (p >= perms.size()) break;
                 contigs.clear();
                 for (int32_t id : perms[p]) contigs.push_back(input[(size_t)id]);
-                merge_permutation(contigs, dbg_kmer);
-                for (auto &s : contigs) local.insert(std::move(s));
+                if (parts) {
+                    comps.clear();
+                    for (int32_t id : perms[p]) comps.push_back(Composition{Part{id, 0}});
+                    merge_permutation(contigs, dbg_kmer, &comps);
+                    for (size_t i = 0; i < contigs.size(); i++) keep_smallest(local_comp, contigs[i], std::move(comps[i]));
+                } else {
+                    merge_permutation(contigs, dbg_kmer);
+                    for (auto &s : contigs) local.insert(std::move(s));
+                }
             }
             std::lock_guard<std::mutex> lock(mu);
             for (auto &s : local) found.insert(s);
+            for (auto &kv : local_comp) {
+                found.insert(kv.first);
+                keep_smallest(found_comp, kv.first, std::move(kv.second));
+            }
         } catch (...) {
             failed = true;
             next_perm = perms.size();  // the other workers stop at their next permutation
@@ -181,8 +251,113 @@ static int assemble_impl(const char *contig_chars, const int64_t *contig_off, in
     res->items.erase(std::unique(res->items.begin(), res->items.end()), res->items.end());
     std::sort(res->items.begin(), res->items.end(),
               [](const std::string &a, const std::string &b) -> bool { return a.length() > b.length(); });
+    if (parts) {
+        ScaffoldList *sl = new (std::nothrow) ScaffoldList();
+        if (!sl) { delete res; return BS_ERR_ALLOC; }
+        sl->part_start.push_back(0);
+        for (const std::string &s : res->items) {
+            for (const Part &pt : found_comp.at(s)) { sl->part_base.push_back(pt.base); sl->part_overlap.push_back(pt.overlap); }
+            sl->part_start.push_back((int64_t)sl->part_base.size());
+        }
+        *parts = reinterpret_cast<bs_scaffold_list *>(sl);
+    }
     *out = reinterpret_cast<bs_string_list *>(res);
     return BS_OK;
+}
+
+int64_t bs_scaffold_list_size(const bs_scaffold_list *l) { return l ? (int64_t)reinterpret_cast<const ScaffoldList *>(l)->part_start.size() - 1 : 0; }
+int64_t bs_scaffold_list_parts(const bs_scaffold_list *l) { return l ? (int64_t)reinterpret_cast<const ScaffoldList *>(l)->part_base.size() : 0; }
+void bs_scaffold_list_copy(const bs_scaffold_list *l, int64_t *part_start, int32_t *part_base, int32_t *part_overlap) {
+    if (!l) return;
+    const ScaffoldList *sl = reinterpret_cast<const ScaffoldList *>(l);
+    if (part_start) std::memcpy(part_start, sl->part_start.data(), sl->part_start.size() * sizeof(int64_t));
+    if (part_base && !sl->part_base.empty()) std::memcpy(part_base, sl->part_base.data(), sl->part_base.size() * sizeof(int32_t));
+    if (part_overlap && !sl->part_overlap.empty()) std::memcpy(part_overlap, sl->part_overlap.data(), sl->part_overlap.size() * sizeof(int32_t));
+}
+void bs_scaffold_list_free(bs_scaffold_list *l) { delete reinterpret_cast<ScaffoldList *>(l); }
+
+// ---- scaffold sets given as parts (include/breakscore.h: bs_scaffold_set) ----
+
+}  // extern "C"
+
+// Full validation of a scaffold set (shared with bs_score_scaffolds in bs_api.cu; not exported): counts, indices, overlaps
+// in range, starts of the parts ascending, and every overlap a true suffix/prefix match of the text built so far.
+// lengths [n_scaffolds] and part_dst [parts] (scaffold position of the first base a part adds) are optional outputs.
+extern "C" int bs_scaffold_validate(const bs_scaffold_set *set, int64_t *lengths, int32_t *part_dst, char *err, size_t errn) {
+    auto bad = [&](const char *what, long long a, long long b) {
+        std::snprintf(err, errn, "scaffold set: %s (%lld, %lld)", what, a, b);
+        return (int)BS_ERR_INVALID;
+    };
+    if (!set) return bad("NULL set", 0, 0);
+    if (set->n_base < 0 || set->n_scaffolds < 0 || set->n_base > 0x7fffffff || set->n_scaffolds > 0x7fffffff) return bad("bad counts", set->n_base, set->n_scaffolds);
+    if (set->n_scaffolds == 0) return BS_OK;
+    if (!set->base_off || !set->scaffold_part_start || !set->part_base || !set->part_overlap) return bad("NULL array", 0, 0);
+    for (int64_t b = 0; b < set->n_base; b++)
+        if (set->base_off[b + 1] < set->base_off[b]) return bad("base offsets are not monotone at", b, 0);
+    if (set->n_base > 0 && set->base_off[set->n_base] > set->base_off[0] && !set->base_chars) return bad("base_chars is NULL", 0, 0);
+    if (set->scaffold_part_start[0] != 0) return bad("scaffold_part_start[0] != 0", set->scaffold_part_start[0], 0);
+    for (int64_t c = 0; c < set->n_scaffolds; c++) {
+        const int64_t p0 = set->scaffold_part_start[c], p1 = set->scaffold_part_start[c + 1];
+        if (p1 <= p0) return bad("scaffold without parts", c, p1 - p0);
+        int64_t len = 0, prev_start = 0;
+        for (int64_t i = p0; i < p1; i++) {
+            const int64_t b = set->part_base[i], ov = set->part_overlap[i];
+            if (b < 0 || b >= set->n_base) return bad("part names a base contig out of range", i, b);
+            const int64_t Lb = set->base_off[b + 1] - set->base_off[b];
+            if (ov < 0 || ov >= Lb || (i == p0 && ov != 0)) return bad("overlap out of range (0 for a first part, below the part's length)", i, ov);
+            if (ov > len) return bad("overlap longer than the scaffold built so far", i, ov);
+            if (i > p0 && len - ov < prev_start) return bad("a part starts before its predecessor", i, ov);
+            // the last ov bases of the text so far == the first ov bases of the part: walk back over the parts
+            const char *pc = set->base_chars + set->base_off[b];
+            int64_t rem = ov;
+            for (int64_t k = i - 1; rem > 0 && k >= p0; k--) {
+                const int64_t bk = set->part_base[k], ovk = set->part_overlap[k];
+                const char *kc = set->base_chars + set->base_off[bk];
+                const int64_t Lk = set->base_off[bk + 1] - set->base_off[bk];
+                const int64_t take = std::min(rem, Lk - ovk);  // bases that part k added
+                if (std::memcmp(kc + Lk - take, pc + rem - take, (size_t)take) != 0) return bad("overlap is not a suffix/prefix match", i, ov);
+                rem -= take;
+            }
+            prev_start = len - ov;
+            if (part_dst) part_dst[i] = (int32_t)len;
+            len += Lb - ov;
+            if (len > 0x7f000000ll) return bad("scaffold longer than 2^31", c, len);
+        }
+        if (lengths) lengths[c] = len;
+    }
+    return BS_OK;
+}
+
+extern "C" {
+
+int bs_scaffold_lengths(const bs_scaffold_set *set, int64_t *lengths) {
+    if (!lengths) return BS_ERR_INVALID;
+    return bs_scaffold_validate(set, lengths, nullptr, g_assemble_error, sizeof g_assemble_error);
+}
+
+int bs_scaffold_texts(const bs_scaffold_set *set, char *chars, int64_t *off) {
+    if (!set || !off) return BS_ERR_INVALID;
+    try {
+        std::vector<int64_t> len((size_t)std::max<int64_t>(set->n_scaffolds, 1));
+        const int rc = bs_scaffold_validate(set, len.data(), nullptr, g_assemble_error, sizeof g_assemble_error);
+        if (rc != BS_OK) return rc;
+        off[0] = 0;
+        for (int64_t c = 0; c < set->n_scaffolds; c++) off[c + 1] = off[c] + len[(size_t)c];
+        if (!chars) return BS_OK;
+        for (int64_t c = 0; c < set->n_scaffolds; c++) {
+            char *o = chars + off[c];
+            for (int64_t i = set->scaffold_part_start[c]; i < set->scaffold_part_start[c + 1]; i++) {
+                const int64_t b = set->part_base[i], ov = set->part_overlap[i];
+                const int64_t n = set->base_off[b + 1] - set->base_off[b] - ov;
+                std::memcpy(o, set->base_chars + set->base_off[b] + ov, (size_t)n);
+                o += n;
+            }
+        }
+        return BS_OK;
+    } catch (...) {
+        std::snprintf(g_assemble_error, sizeof g_assemble_error, "bs_scaffold_texts: out of host memory");
+        return BS_ERR_ALLOC;
+    }
 }
 
 int64_t bs_string_list_size(const bs_string_list *l) { return l ? (int64_t)reinterpret_cast<const StringList *>(l)->items.size() : 0; }

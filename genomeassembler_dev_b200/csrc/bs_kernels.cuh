@@ -10,6 +10,7 @@
 #include "bs_place.cuh"     // placement (read index; contig-tile index; all-pairs scan)
 #include "bs_score.cuh"     // break k-mers -> sums, histogram, KS-B
 #include "bs_ks.cuh"        // truth spectrum, path_prob_dist, KS-A
+#include "bs_compose.cuh"   // scaffold sets scored from their parts (base contigs + junction windows)
 #include "bs_startpos.cuh"  // contig-in-truth offset
 #include "bs_lev.cuh"       // infix edit distance (lev_dist_vs_true)
 #include "bs_simulate.cuh"  // read simulation (the step before the scorer)

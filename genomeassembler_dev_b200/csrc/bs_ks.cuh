@@ -228,6 +228,7 @@ struct ProbDistArgs {
     // scan of the contig, its table gathers and its launch disappear.  Positions 0..3 and L-3..L-1 (the start rules and
     // the clamped end) take the generic path.
     ScoreArgs sc;
+    int64_t fuse_min_len;    // contigs of at least this many bases are scored on the way (FUSE_MIN_LEN unless tuned)
 };
 
 // Which contigs are scored on the way: those of at least FUSE_MIN_LEN bases (16 kb).  Measured (profiles/r02o): one scan instead of
@@ -324,9 +325,9 @@ __global__ void __launch_bounds__(768, 2) k_prob_dist_ks(ProbDistArgs a) {
         double *pd = a.prob_dist ? a.prob_dist + a.pd_off[c] : nullptr;
         ScoreState st;
         const int32_t *wsc = nullptr;
-        const bool fz = FUSE && L >= FUSE_MIN_LEN;  // (block-uniform) a property of the contig alone: see FUSE_MIN_LEN
+        const bool fz = FUSE && L >= a.fuse_min_len;  // (block-uniform) a property of the contig alone: see FUSE_MIN_LEN
         if constexpr (FUSE) {
-            score_begin(a.sc, c, st);
+            score_begin(a.sc, *sh, c, st);
             if (!fz) st.total = 0;  // scored by k_break_score: nothing is accumulated here
             wsc = a.sc.w + a.ctg_off[c] + c;
         }
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(KS_SMALL_THREADS, 6) k_prob_dist_ks_small(Prob
         ScoreState st;
         const int32_t *wsc = nullptr;
         if constexpr (FUSE) {
-            score_begin(a.sc, c, st);
+            score_begin(a.sc, *sh, c, st);
             wsc = a.sc.w + a.ctg_off[c] + c;
         }
         const int64_t seg = a.ctg_seg[c];

@@ -153,46 +153,56 @@ __device__ __forceinline__ double block_sum_fixed(double v, double *s_w) {
 // ---- the per-contig scoring state, shared by k_break_score and by the KS-A kernels when they score on the way
 // (bs_ks.cuh: with kmer == 8 the break k-mer of position p IS the rolling window p - 4, already gathered there) ----
 
-struct ScoreShared {
+struct ScoreSharedCore {
     double w[32];
     int32_t cc[CC_DENSE];        // rows having count j
-    uint32_t hash[HASH_SLOTS];   // (dense index + 1) << 15 | count, 0 = empty; all empty between contigs
     int novf, maxc, nz;          // reset by thread 0 where the block fetches its next contig
+};
+struct ScoreShared : ScoreSharedCore {
+    uint32_t hash[HASH_SLOTS];   // (dense index + 1) << 15 | count, 0 = empty; all empty between contigs
 };
 
 struct ScoreState {
     int32_t total;
-    bool in_smem;     // (block-uniform) distinct break k-mers <= placed reads <= HASH_LIMIT
+    bool in_smem;     // (block-uniform) distinct break k-mers <= placed reads <= two thirds of the hash table (and < 2^15)
+    uint32_t *hash;   // the block's shared-memory hash table: ScoreShared::hash, or a larger one in dynamic shared memory (bs_compose.cuh)
     int hs;           // slots of the table this contig uses: a power of two >= 2 * total (pass 2 sweeps what a small contig
     uint32_t hmask;   // can have touched, not all HASH_SLOTS), all HASH_SLOTS for the largest contigs that still fit
     double s1, s2;
+    double inv_total;  // 1.0 / total: what (double)wv / (double)total is for wv == 1, the usual weight (one division per contig, not per break)
     int32_t *scratch, *ovf;
 };
 
-__device__ __forceinline__ void score_shared_init(const ScoreArgs &a, ScoreShared &sh) {  // once per kernel, before the first barrier
+__device__ __forceinline__ void score_shared_init(const ScoreArgs &a, ScoreSharedCore &sh, uint32_t *hash, int slots) {  // once per kernel, before the first barrier
     if (a.ks_b == nullptr) return;
     for (int i = threadIdx.x; i < CC_DENSE; i += blockDim.x) sh.cc[i] = 0;
-    for (int i = threadIdx.x; i < HASH_SLOTS; i += blockDim.x) sh.hash[i] = 0u;
+    for (int i = threadIdx.x; i < slots; i += blockDim.x) hash[i] = 0u;
 }
+__device__ __forceinline__ void score_shared_init(const ScoreArgs &a, ScoreShared &sh) { score_shared_init(a, sh, sh.hash, HASH_SLOTS); }
 
-__device__ __forceinline__ void score_begin(const ScoreArgs &a, int64_t c, ScoreState &st) {
+// (total: reads placed in the contig; given by the caller where it has just been counted, bs_compose.cuh)
+// hash / slots: the shared-memory table (slots a power of two)
+__device__ __forceinline__ void score_begin_total(const ScoreArgs &a, int32_t total, ScoreState &st, uint32_t *hash, int slots) {
     const bool want_ks = a.ks_b != nullptr;
-    st.total = a.total[c];
-    st.in_smem = st.total <= HASH_LIMIT;
-    st.hs = 64;
-    while (st.hs < 2 * st.total && st.hs < HASH_SLOTS) st.hs <<= 1;
+    st.total = total;
+    st.hash = hash;
+    st.in_smem = st.total <= slots * 2 / 3 && st.total < (1 << 15);
+    st.hs = 64 < slots ? 64 : slots;
+    while (st.hs < 2 * st.total && st.hs < slots) st.hs <<= 1;
     st.hmask = (uint32_t)st.hs - 1u;
     st.s1 = st.s2 = 0.0;
+    st.inv_total = 1.0 / (double)total;
     st.scratch = want_ks ? a.scratch + (int64_t)blockIdx.x * (a.T + 1) : nullptr;
     st.ovf = want_ks ? a.ovf_cnt + (int64_t)blockIdx.x * OVF_CAP : nullptr;
 }
+__device__ __forceinline__ void score_begin(const ScoreArgs &a, ScoreShared &sh, int64_t c, ScoreState &st) { score_begin_total(a, a.total[c], st, sh.hash, HASH_SLOTS); }
 
 // wv reads broke the k-mer with dense index di (table entry te) in contig c
-__device__ __forceinline__ void score_add(const ScoreArgs &a, ScoreShared &sh, ScoreState &st, int64_t c, int di, double prob, int32_t row,
+__device__ __forceinline__ void score_add(const ScoreArgs &a, ScoreSharedCore &sh, ScoreState &st, int64_t c, int di, double prob, int32_t row,
                                           int32_t wv) {
     if (row >= 0) {
         st.s1 += prob * (double)wv;
-        st.s2 += prob * ((double)wv / (double)st.total);
+        st.s2 += prob * (wv == 1 ? st.inv_total : (double)wv / (double)st.total);
         if (a.ks_b != nullptr) {
             if (st.in_smem) {
                 // distinct dense indices are distinct table rows: count per k-mer.  At most HASH_LIMIT
@@ -200,12 +210,12 @@ __device__ __forceinline__ void score_add(const ScoreArgs &a, ScoreShared &sh, S
                 const uint32_t key = (uint32_t)di + 1u;
                 for (uint32_t h = (key * 2654435761u) >> 16;; h++) {
                     h &= st.hmask;
-                    uint32_t cur = sh.hash[h];
+                    uint32_t cur = st.hash[h];
                     if (cur == 0u) {
-                        cur = atomicCAS(&sh.hash[h], 0u, (key << 15) | (uint32_t)wv);
+                        cur = atomicCAS(&st.hash[h], 0u, (key << 15) | (uint32_t)wv);
                         if (cur == 0u) break;
                     }
-                    if ((cur >> 15) == key) { atomicAdd(&sh.hash[h], (uint32_t)wv); break; }
+                    if ((cur >> 15) == key) { atomicAdd(&st.hash[h], (uint32_t)wv); break; }
                 }
             } else {
                 atomicAdd(&st.scratch[row], wv);
@@ -216,7 +226,7 @@ __device__ __forceinline__ void score_add(const ScoreArgs &a, ScoreShared &sh, S
 }
 
 // the generic form: position p of a contig of length L (any kmer, any position)
-__device__ __forceinline__ void score_add_position(const ScoreArgs &a, ScoreShared &sh, ScoreState &st, int64_t c, const uint64_t *gw,
+__device__ __forceinline__ void score_add_position(const ScoreArgs &a, ScoreSharedCore &sh, ScoreState &st, int64_t c, const uint64_t *gw,
                                                    const uint32_t *gm, int64_t p, int64_t L, int32_t wv) {
     const BreakWindow bw = break_window(p, a.kmer, L);
     const int di = dense_index_at(gw, gm, bw.start, bw.len);
@@ -227,9 +237,13 @@ __device__ __forceinline__ void score_add_position(const ScoreArgs &a, ScoreShar
     score_add(a, sh, st, c, di, te.prob, te.row, wv);
 }
 
-// sums, outputs and the KS of the break histogram; every thread of the block calls it (barriers inside)
-__device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreShared &sh, ScoreState &st, int64_t c, int64_t L, const uint64_t *gw,
-                                             const uint32_t *gm, const int32_t *w) {
+// sums, outputs and the KS of the break histogram; every thread of the block calls it (barriers inside).
+// The broken positions of a contig that counted its rows in the global scratch are found again through the position
+// weights w, or -- rows != NULL, the compositional path, which has no weights -- through the block's row of leftmost
+// positions per read (POS_INF_ROW: read not placed).
+constexpr uint32_t POS_INF_ROW = 0x7f7f7f7fu;
+__device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreSharedCore &sh, ScoreState &st, int64_t c, int64_t L, const uint64_t *gw,
+                                             const uint32_t *gm, const int32_t *w, const uint32_t *rows = nullptr, int64_t n_rows = 0) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const bool want_ks = a.ks_b != nullptr;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
@@ -252,10 +266,14 @@ __device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreShared &sh
     __threadfence_block();
     __syncthreads();
     // pass 2: tally rows per count value
+    // (a thread keeps its own tallies of the rows it saw, of those with count 1 -- nearly all -- and of the largest
+    // count; they reach the shared counters once, behind the sweep: no same-address atomic per row)
+    int t_nz = 0, t_c1 = 0, t_max = 0;
     auto tally = [&](int32_t cnt) {
         if (cnt == 0) return;
-        atomicAdd(&sh.nz, 1);
-        if (cnt < CC_DENSE) { atomicAdd(&sh.cc[cnt], 1); atomicMax(&sh.maxc, cnt); }
+        t_nz++;
+        if (cnt == 1) { t_c1++; if (t_max < 1) t_max = 1; }
+        else if (cnt < CC_DENSE) { atomicAdd(&sh.cc[cnt], 1); if (t_max < cnt) t_max = cnt; }
         else {
             const int slot = atomicAdd(&sh.novf, 1);
             if (slot < OVF_CAP) st.ovf[slot] = cnt; else *a.status = 1;
@@ -263,8 +281,17 @@ __device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreShared &sh
     };
     if (st.in_smem) {  // the usual case: the hash table's slots, emptied on the way
         for (int i = tid; i < st.hs; i += nthr) {
-            const uint32_t v = sh.hash[i];
-            if (v != 0u) { sh.hash[i] = 0u; tally((int32_t)(v & 0x7fffu)); }
+            const uint32_t v = st.hash[i];
+            if (v != 0u) { st.hash[i] = 0u; tally((int32_t)(v & 0x7fffu)); }
+        }
+    } else if (rows != nullptr) {
+        for (int64_t r = tid; r < n_rows; r += nthr) {
+            const uint32_t p = rows[r];
+            if (p == POS_INF_ROW) continue;
+            const BreakWindow bw = break_window((int64_t)p, a.kmer, L);
+            const int di = dense_index_at(gw, gm, bw.start, bw.len);
+            const int32_t trow = di >= 0 ? a.tab[di].row : -1;
+            tally(trow >= 0 ? atomicExch(&st.scratch[trow], 0) : 0);
         }
     } else
     // whoever swaps a row's count out of the scratch first owns it
@@ -289,6 +316,9 @@ __device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreShared &sh
 #pragma unroll
         for (int u = 0; u < 4; u++) tally(cnt[u]);
     }
+    if (t_nz) atomicAdd(&sh.nz, t_nz);
+    if (t_c1) atomicAdd(&sh.cc[1], t_c1);
+    if (t_max) atomicMax(&sh.maxc, t_max);
     __syncthreads();
     // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them
     if (tid == 0) {
@@ -369,7 +399,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, SCORE_BLOCKS) k_break_score(Sco
         const int32_t *w = a.w + coff + c;
         const int64_t np = L > 0 ? L : 1;
         ScoreState st;
-        score_begin(a, c, st);
+        score_begin(a, sh, c, st);
         // pass 1: weighted sums in position order (+ histogram, + per-row counts for the KS); four
         // positions per thread in flight so that the table gathers overlap
         if (st.total != 0) {

@@ -191,15 +191,22 @@ def make_scaffold_set(seed, length=50_000, read_len=150, coverage=30.0, n_base=1
     rng = np.random.default_rng(seed)
     seg = make_segment(seed, length, read_len, coverage, n_base, prob8, mut_frac=0.0)
     base = [np.frombuffer(c, dtype=np.uint8) for c in seg.contigs]
-    scaffolds = []
+    scaffolds, part_start, part_base = [], [0], []
     for _ in range(n_scaffolds):
         target = int(rng.integers(lo, hi + 1))
         order = rng.permutation(len(base))
         parts, tot = [], 0
         for j in order:
             parts.append(base[j])
+            part_base.append(int(j))
             tot += len(base[j])
             if tot >= target:
                 break
+        part_start.append(len(part_base))
         scaffolds.append(np.concatenate(parts).tobytes())
-    return Segment(seg.truth, seg.reads, scaffolds)
+    out = Segment(seg.truth, seg.reads, scaffolds)
+    # how the candidates were put together (plain concatenations: every overlap 0), for bs_score_scaffolds
+    out.base_contigs = list(seg.contigs)
+    out.part_start = np.asarray(part_start, np.int64)
+    out.part_base = np.asarray(part_base, np.int32)
+    return out

@@ -18,6 +18,8 @@
  * second pass with rep(1/n, n), DeNovoAssembler.R:325-333 | bs_set_second_table + BS_WANT_SECOND_TABLE (one call, one placement)
  * Rcpp::stop / R error                                | int status + bs_last_error
  * assemble_contigs, lib/BreakageScorer.cpp:79-174     | bs_assemble_contigs (host; candidate generator)
+ * assemble_contigs + calc_breakscore on its output    | bs_assemble_scaffolds + bs_score_scaffolds: the candidates stay a list of
+ *   (lib/DeNovoAssembler.R:343-355)                   |   (base contig, overlap) parts and are scored from their parts
  * generate_sequencing_reads, lib/GenerateReads.R:234-379 | bs_simulate_reads (device; the step before the scorer)
  */
 #ifndef BREAKSCORE_H
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BS_ABI_VERSION 4
+#define BS_ABI_VERSION 5
 
 /* the library is built with -fvisibility=hidden: only these entry points are exported */
 #if defined(__GNUC__)
@@ -217,6 +219,51 @@ BS_API int64_t bs_string_list_size(const bs_string_list *l);
 BS_API int64_t bs_string_list_bytes(const bs_string_list *l);
 BS_API void bs_string_list_copy(const bs_string_list *l, char *chars, int64_t *off);
 BS_API void bs_string_list_free(bs_string_list *l);
+
+/*
+ * COMPOSITIONAL scoring of a scaffold set.  The candidates upstream scores after assemble_contigs
+ * (lib/BreakageScorer.cpp:105-171) are chains of the same few base contigs, each glued to the scaffold built so far over
+ * a suffix/prefix overlap (:118-131).  A scaffold is given here as its PARTS instead of its text:
+ *     text(scaffold) = base[part 0] + base[part 1][overlap 1 ..] + base[part 2][overlap 2 ..] + ...
+ * where the first overlap_i bases of part i must equal the last overlap_i bases of the text built so far (checked; it is
+ * what makes every base contig a whole substring of the scaffold).  bs_score_scaffolds returns exactly what bs_score
+ * returns for the materialised texts (integers bit for bit, fp64 sums to 1e-9: another summation order), but the reads
+ * are placed ONCE per base contig; a scaffold's leftmost positions are then the minimum over its parts plus a probe of
+ * the read index at the few positions whose match would cross a junction -- O(reads x parts + junction windows) per
+ * scaffold instead of O(scaffold length) index probes -- and the break k-mers are scored from those positions directly.
+ * The scaffold texts never cross PCIe (cfg-4: 50 kb of base contigs instead of 324 MB).
+ * All arrays of bs_scaffold_set are HOST memory.  One segment per call.  flags: as bs_score; BS_DEVICE_CHARS applies to
+ * read_chars / truth only; BS_PLACE_SCAN / BS_PLACE_TILE / BS_WEIGHTS_* are refused.  read_off == NULL: every read has
+ * read_len bytes.  path_prob_dist_off / pos_off refer to the scaffold lengths (bs_scaffold_lengths).
+ */
+typedef struct {
+    int64_t n_base;
+    const char *base_chars;
+    const int64_t *base_off;             /* [n_base+1] */
+    int64_t n_scaffolds;
+    const int64_t *scaffold_part_start;  /* [n_scaffolds+1]; scaffold s = parts [start[s], start[s+1]), at least one */
+    const int32_t *part_base;            /* base contig of a part */
+    const int32_t *part_overlap;         /* bases of the part already present at the end of the scaffold so far; 0 for a first part, < length of the part */
+} bs_scaffold_set;
+
+BS_API int bs_score_scaffolds(bs_ctx *ctx, const bs_scaffold_set *set, const char *read_chars, const int64_t *read_off, int64_t n_reads,
+                              int32_t read_len, const char *truth, int64_t truth_len, int kmer, uint32_t flags, bs_result *result);
+/* lengths[n_scaffolds] of the scaffold texts; returns BS_ERR_INVALID for a malformed set (needs no GPU, no context) */
+BS_API int bs_scaffold_lengths(const bs_scaffold_set *set, int64_t *lengths);
+/* the texts themselves: off[n_scaffolds+1], chars (may be NULL: offsets only) -- for callers that want the strings upstream returns */
+BS_API int bs_scaffold_texts(const bs_scaffold_set *set, char *chars, int64_t *off);
+/*
+ * bs_assemble_contigs that also reports HOW every scaffold was glued together: the same strings in the same (upstream)
+ * order in *out, and their parts in *parts (one composition per string: the first one found).  Read the composition
+ * with bs_scaffold_list_parts (n_parts total) / _copy (part_start[n+1], part_base[n_parts], part_overlap[n_parts]).
+ */
+typedef struct bs_scaffold_list bs_scaffold_list;
+BS_API int bs_assemble_scaffolds(const char *contig_chars, const int64_t *contig_off, int64_t n_contigs, int dbg_kmer,
+                                 int seed, int n_shuffles, int n_threads, bs_string_list **out, bs_scaffold_list **parts);
+BS_API int64_t bs_scaffold_list_size(const bs_scaffold_list *l);
+BS_API int64_t bs_scaffold_list_parts(const bs_scaffold_list *l);
+BS_API void bs_scaffold_list_copy(const bs_scaffold_list *l, int64_t *part_start, int32_t *part_base, int32_t *part_overlap);
+BS_API void bs_scaffold_list_free(bs_scaffold_list *l);
 
 /*
  * Read simulation on the device (upstream lib/GenerateReads.R:243-259,302-313,368-379): for every

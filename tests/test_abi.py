@@ -42,7 +42,7 @@ def test_library_holds_sm100a_code(product_lib):
 
 def test_loads_and_fails_loudly_without_gpu(product_lib):
     lib = B.load_library(product_lib)
-    assert lib.bs_abi_version() == 4
+    assert lib.bs_abi_version() == 5
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")

@@ -619,3 +619,91 @@ def test_hashed_scratch_cfg5_shape(gpu_scorer, kmers, prob, monkeypatch):
                 if isinstance(one[k], np.ndarray):
                     assert np.array_equal(one[k], two[k], equal_nan=True), (cap, k)
     assert dense["kmer_breaks"][-1] > 4000
+
+
+# ---- scaffold sets scored from their parts (bs_score_scaffolds) --------------------------------------
+
+import scaffold_cases as SC  # noqa: E402
+from test_scaffold_sets import SETS as SCAFFOLD_SETS  # noqa: E402
+
+
+@pytest.mark.parametrize("kw", SCAFFOLD_SETS + [dict(seed=66, length=50000, read_len=150, coverage=30, n_base=16, n_scaffolds=60, overlap=30),
+                                                dict(seed=67, length=50000, read_len=100, coverage=30, n_base=24, n_scaffolds=60, overlap=0, ragged=True)],
+                         ids=lambda k: f"seed{k['seed']}")
+@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash"])
+def test_scaffold_sets_vs_rescan_and_oracle(kw, mode, gpu_scorer, oracle, kmers, prob, monkeypatch):
+    if mode == "weights":
+        monkeypatch.setenv("BS_COMPOSE_SCORE", "0")
+    if mode == "small_hash":
+        monkeypatch.setenv("BS_COMPOSE_HASH_SLOTS", "64")
+    if mode == "global_rows":
+        monkeypatch.setenv("BS_COMPOSE_ROWS", "global")
+    truth, reads, sset = SC.make_set(**kw)
+    before = gpu_scorer.launch_count
+    SC.check_scaffolds(gpu_scorer, oracle, kmers, prob, truth, reads, sset)
+    assert gpu_scorer.launch_count > before
+
+
+@pytest.mark.parametrize("name,base,chains,reads,truth,kmer", SC.hand_sets(), ids=[h[0] for h in SC.hand_sets()])
+@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash"])
+def test_scaffold_hand_built_sets(name, base, chains, reads, truth, kmer, mode, gpu_scorer, oracle, kmers, prob, monkeypatch):
+    if mode == "weights":
+        monkeypatch.setenv("BS_COMPOSE_SCORE", "0")
+    if mode == "small_hash":
+        monkeypatch.setenv("BS_COMPOSE_HASH_SLOTS", "64")
+    if mode == "global_rows":
+        monkeypatch.setenv("BS_COMPOSE_ROWS", "global")
+    SC.check_scaffolds(gpu_scorer, oracle, kmers, prob, truth, reads, SC.hand_scaffold_set(base, chains), kmer=kmer)
+
+
+def test_scaffold_second_table_and_assembled_set(gpu_scorer, oracle, kmers, prob):
+    truth, reads, sset = SC.make_set(65, length=20000, read_len=50, coverage=20, n_base=10, n_scaffolds=40, overlap=11)
+    SC.check_scaffolds(gpu_scorer, oracle, kmers, prob, truth, reads, sset, second=tables.uniform(len(prob)))
+    gpu_scorer.set_second_table(None)
+    # the upstream sequence of calls: assemble_contigs -> calc_breakscore, here assemble_scaffolds -> score_scaffolds
+    seg = synth.make_segment(77, length=20000, read_len=100, coverage=20, n_contigs=9, mut_frac=0.0)
+    contigs = [seg.truth[s:s + len(c) + 60] for s, c in zip(seg.contig_truth_start, seg.contigs)]
+    strings, aset = B.assemble_scaffolds(contigs, 13, 1234, n_shuffles=2000)
+    got = SC.check_scaffolds(gpu_scorer, oracle, kmers, prob, seg.truth, seg.read_list, aset, oracle_sample=range(0, len(strings), max(1, len(strings) // 24)))
+    assert got["sequence"] == strings and len(strings) >= 2
+
+
+def test_cfg4_full_size_from_parts(gpu_scorer, kmers, prob):
+    """BASELINE.json configs[3] at its size: the 10 000 scaffolds scored from their parts == the same 10 000 texts re-scanned
+    (integer columns and KS-A bit for bit, fp64 sums to 1e-9), 64 of them against the CPU oracle with all reads, and 20
+    repeats of the call bit-identical (shared-memory atomicMin rows, per-block scratch)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import loader as O
+    seg = synth.make_scaffold_set(1400, n_scaffolds=10000)
+    sset = B.ScaffoldSet(seg.base_contigs, seg.part_start, seg.part_base, np.zeros(len(seg.part_base), np.int32))
+    gpu_scorer.set_table(kmers, prob)
+    flags = B.WANT_KS | B.WANT_STARTPOS
+    got = gpu_scorer.score_scaffolds(sset, seg.reads, seg.truth, flags=flags)
+    ref = gpu_scorer.score(seg.contigs, seg.reads, seg.truth, flags=flags)
+    assert got["sequence"] == seg.contigs
+    for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos", "ks_stat_prob_dist"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len"):
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-9, atol=0, err_msg=k)
+    np.testing.assert_allclose(got["ks_stat_path_freq"], ref["ks_stat_path_freq"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    lens = np.array([len(c) for c in seg.contigs])
+    chosen = sorted({int(np.argmax(lens)), int(np.argmin(lens))} | {int(i) for i in np.random.default_rng(45).permutation(len(lens))[:62]})
+    reads = seg.read_list
+
+    def check(idx):
+        want = O.oracle_calc_breakscore([seg.contigs[i] for i in idx], reads, seg.truth, 8, kmers, prob, want_prob_dist=False)
+        for k in ("sequence_len", "kmer_breaks", "path_prob_dist_startpos"):
+            assert np.array_equal(got[k][idx], want[k]), k
+        for k in ("bp_score", "bp_score_norm_by_break_freqs", "bp_score_norm_by_len"):
+            np.testing.assert_allclose(got[k][idx], want[k], rtol=1e-9, atol=0, err_msg=k)
+        for k in ("ks_stat_prob_dist", "ks_stat_path_freq"):
+            np.testing.assert_allclose(got[k][idx], want[k], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg=k)
+        return len(idx)
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        assert sum(ex.map(check, [chosen[i:i + 4] for i in range(0, len(chosen), 4)])) >= 62
+    for it in range(20):
+        again = gpu_scorer.score_scaffolds(sset, seg.reads, seg.truth, flags=flags)
+        for k in got:
+            if k != "sequence":
+                assert np.array_equal(got[k], again[k], equal_nan=True), (it, k)

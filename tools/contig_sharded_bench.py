@@ -18,6 +18,7 @@ prepare_cpu_side runs before CUDA is initialised (forked oracle workers); run_gp
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import time
 
@@ -65,7 +66,7 @@ def prepare_cpu_side(bench, args, rank, world, procs):
         bench._POOL[key] = {"contigs": contigs, "read_list": [r.tobytes() for r in reads], "truth": truth}
         expected = bench.oracle_sample(key, sample, procs)
         plan[key] = {"contigs": contigs, "reads": np.ascontiguousarray(reads), "truth": truth, "parts": parts,
-                     "sample": sample, "expected": expected}
+                     "sample": sample, "expected": expected, "seg": cfg4 if key == "cfg4" else None}
         if world == 1 and rank == 0 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             if key == "cfg4":
@@ -282,6 +283,72 @@ def measure(bench, rig, sh, steps, warmup, sample=None, expected=None, host_read
     return out
 
 
+def measure_compositional(bench, rig, sh, seg, steps, warmup, sample, expected, host_reads, host_truth):
+    """cfg-4 scored from the PARTS of its scaffolds (bs_score_scaffolds): the reads are placed once per base
+    contig, every scaffold takes the minimum over its parts + junction-window probes and is scored from those positions.
+    Same sharding as the rescan above (this rank's scaffolds, all base contigs), same record buffers, same gather; the
+    gathered table is compared with the rescan's."""
+    torch, B, sc = rig.torch, rig.B, rig.sc
+    world, rank = rig.world, rig.rank
+    tf0, ti0 = sh.table_in_input_order()
+    tf0, ti0 = tf0.clone(), ti0.clone()
+    # this rank's share of the scaffolds as a set of its own
+    ps = seg.part_start
+    counts = np.diff(ps)[sh.mine]
+    my_start = np.zeros(len(sh.mine) + 1, np.int64)
+    np.cumsum(counts, out=my_start[1:])
+    my_base = np.concatenate([seg.part_base[ps[i]:ps[i + 1]] for i in sh.mine]) if len(sh.mine) else np.zeros(0, np.int32)
+    sset = B.ScaffoldSet(seg.base_contigs, my_start, my_base, np.zeros(len(my_base), np.int32))
+    st = sset.c_struct()
+    lib, ctx = sc._lib, sc._ctx
+
+    def call(rc, tc, flags):
+        if len(sh.mine):
+            sc._check(lib.bs_score_scaffolds(ctx, C.byref(st), rc, None, sh.n_reads, READ_LEN, tc, sh.truth_len, 8, flags, C.byref(sh.res)))
+
+    def step_device():
+        call(sh.d_reads.data_ptr(), sh.d_truth.data_ptr(), sh.flags | B.DEVICE_CHARS | B.DEVICE_RESULT)
+        sh.gather()
+
+    dev_ms = rig.time_device(step_device, steps, warmup)
+    pair = float(sh.n_reads) * sh.bases
+    out = {"ms_per_step": dev_ms, "value": pair / 1e9 / (dev_ms / 1e3), "unit": bench.UNIT, "scaffolds_per_rank": sh.counts,
+           "base_contigs": len(seg.base_contigs), "parts": int(ps[-1]),
+           "what": "bs_score_scaffolds: reads placed once per base contig (k_place_index), scaffolds from their parts + junction-window "
+                   "probes and scored from those positions (k_place_compose); scaffold texts composed on the device (KS-A, startpos "
+                   "still scan them); value = the same read x scaffold-base pairs as the rescan, per second"}
+    sc.enable_timing(True)
+    step_device()
+    rig.sync()
+    out["stage_ms_rank0_extra_step"] = {k: v for k, v in sc.last_timings().items() if v > 0}
+    sc.enable_timing(False)
+    ok, n = sh.check_sample(sample, expected)
+    tot = rig.sum_over_ranks([0.0 if ok else 1.0, float(n)])
+    out["oracle_sample"] = {"contigs_checked": int(tot[1]), "all_match": tot[0] == 0.0}
+    tf, ti = sh.table_in_input_order()
+    f0, f1 = tf0.nan_to_num(nan=-1.0), tf.nan_to_num(nan=-1.0)
+    rel = ((f1 - f0).abs() / f0.abs().clamp_min(1e-300)).max().item() if f0.numel() else 0.0
+    out["vs_rescan"] = {"integer_columns_identical": bool(torch.equal(ti, ti0)), "ks_prob_dist_identical": bool(torch.equal(f1[:, 3], f0[:, 3])),
+                        "max_rel_diff_fp64_columns": rel, "within_1e-9": rel <= 1e-9}
+    if host_reads is not None:
+        h_out_f = torch.zeros_like(sh.g_f64, device="cpu").pin_memory()
+        h_out_i = torch.zeros_like(sh.g_i32, device="cpu").pin_memory()
+
+        def step_host():
+            call(host_reads.data_ptr(), host_truth.data_ptr(), sh.flags | B.DEVICE_RESULT)
+            sh.gather()
+            if rank == 0:
+                h_out_f.copy_(sh.g_f64, non_blocking=True)
+                h_out_i.copy_(sh.g_i32, non_blocking=True)
+
+        ms = rig.time_wall(step_host, max(2, min(steps, 3)), 1)
+        out["e2e"] = {"ms_per_step": ms, "value": pair / 1e9 / (ms / 1e3), "unit": bench.UNIT,
+                      "h2d_bytes_per_step": int(host_reads.numel() + host_truth.numel() + sset.base_chars.nbytes + 12 * len(my_base)),
+                      "d2h_bytes_per_step": int(h_out_f.numel() * 8 + h_out_i.numel() * 4),
+                      "same_records_as_device_resident": bool(torch.equal(h_out_i, sh.g_i32.cpu())) if rank == 0 else True}
+    return out
+
+
 def measure_one_process(bench, rig, contigs, tr_off, srs, flags, host_reads, host_truth, tf, ti, pair):
     """ONE process driving all GPUs (upstream's R driver is one process): bs_score_multi from rank 0 while the other ranks
     wait; host buffers in, host arrays out in input order, no collective.  A read set of 64 MB or more crosses PCIe once
@@ -468,6 +535,9 @@ def run_gpu_side(bench, rig, plan):
                       host_reads=rig.pinned(reads) if timing else None,
                       host_truth=rig.pinned(np.frombuffer(d["truth"], np.uint8)) if timing else None,
                       timing=timing, multi_ctx=timing)
+        if key == "cfg4" and d.get("seg") is not None:
+            res["compositional"] = measure_compositional(bench, rig, sh, d["seg"], steps, warmup, d["sample"], d["expected"],
+                                                         rig.pinned(reads), rig.pinned(np.frombuffer(d["truth"], np.uint8)))
         if key == "cfg4":
             res["workload"] = (f"cfg4: {len(d['contigs'])} candidate scaffolds of 10-50 kb (concatenations of 16 base contigs) of one 50 kb "
                                f"segment, {len(d['reads'])} reads of 150 bp (30x), outputs scores+kmer_breaks+startpos+KS")
