@@ -101,7 +101,7 @@ struct Workspace {
     DevBuf rwords, rflags, cwords, cmask, twords, tmask;
     DevBuf w, total, ycnt, yx, yx2, head, next, odd_head, spbest, exact, sp_key, sp_head, sp_next, sp_bitmap, sp_queue;
     DevBuf out_i32, out_f64, pd, pd2, hist, pos;
-    DevBuf base_chars, base_words, base_mask, base_pos, base_w, base_total, base_hits, base_cnt, base_di;  // compositional scoring: the base contigs of a scaffold set
+    DevBuf base_chars, base_words, base_mask, base_pos, base_w, base_total, base_hits, base_cnt, base_di, base_rank;  // compositional scoring: the base contigs of a scaffold set
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     bool in_flight = false;
 };
@@ -444,6 +444,7 @@ struct ChunkRun {
     int pack();       // 2-bit packing of contigs, truths and reads (+ read index)
     int place();      // leftmost placement of every read in every contig of its segment
     int place_composed();  // ... of a scaffold set: reads placed in the base contigs, scaffolds from their parts
+    bool ks_compose() const;  // KS-A of a scaffold set from the window ranks of its base contigs (k_ks_compose)
     int spectrum();   // truth-side distribution of the KS statistics
     bool fused(int which) const;  // scores computed inside the KS-A kernels (kmer == 8, no dense histogram, those kernels run)
     int score_args(int which, int64_t rows, bs::ScoreArgs &sa);  // k_break_score's arguments (rows: blocks that may use a scratch row)
@@ -700,6 +701,7 @@ int ChunkRun::prepare() {
         BS_TRY(ensure(ctx, ws.base_hits, (size_t)std::max<int64_t>(n_base * N, 1) * 8));
         BS_TRY(ensure(ctx, ws.base_cnt, (size_t)std::max<int64_t>(n_base, 1) * 4));
         BS_TRY(ensure(ctx, ws.base_di, (size_t)std::max<int64_t>(n_base * N, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_rank, (size_t)std::max<int64_t>(base_bytes, 1) * 2 + 16));
     }
     BS_TRY(ensure(ctx, ws.rwords, (size_t)std::max<int64_t>(N, 1) * W * 8));
     BS_TRY(ensure(ctx, ws.rflags, (size_t)std::max<int64_t>(N, 1) + 8));
@@ -998,6 +1000,17 @@ int ChunkRun::place() {
 // Scaffold sets (bs_score_scaffolds): the reads are placed in the BASE contigs (k_place_index with the dense leftmost
 // positions out), then every scaffold takes the minimum over its parts and probes its junction windows (k_place_compose),
 // which also scores the break k-mers unless position weights are needed (second table).
+bool ChunkRun::ks_compose() const {
+    // scaffold set, first table, no path_prob_dist out, ranks fit 16 bits, the rank histogram fits shared memory
+    const KsCache &k = ctx->ks;
+    if (!e.comp || !ks_a || e.want_pd || kmer < 1 || kmer > bs::MAXK || k.R_x > 65535 || N <= 0 || n_base <= 0) return false;
+    const char *env = std::getenv("BS_COMPOSE_KS");  // tests: 0 keeps k_prob_dist_ks on the composed texts
+    if (env && env[0] == '0') return false;
+    const bool packed = max_ctg - kmer + 1 < 65536;
+    const size_t hist_bytes = (size_t)(bs::hist_phys_words(k.R_x, packed) + bs::hist_ranges(k.R_x, packed)) * 4;
+    return hist_bytes + 8192 <= ctx->smem_optin;
+}
+
 int ChunkRun::place_composed() {
     StageTimer tm(ctx, ST_PLACE, st);
     if (C <= 0) return BS_OK;
@@ -1035,6 +1048,9 @@ int ChunkRun::place_composed() {
         ba.hits = (uint2 *)ws.base_hits.p; ba.hit_di = (int32_t *)ws.base_di.p; ba.cnt = (int32_t *)ws.base_cnt.p;
         ba.base_off = d_base_off; ba.base_woff = d_base_woff; ba.base_words = bset.words; ba.base_mask = bset.mask;
         ba.kmer = kmer;
+        const bool ranks = ks_compose();
+        ba.win = ranks ? (const bs::WinEntry *)ctx->ks.win.p : nullptr; ba.rank_zero = ctx->ks.rank_zero;
+        ba.base_rank = ranks ? (uint16_t *)ws.base_rank.p : nullptr;
         BS_LAUNCH(bs::k_base_side, (unsigned)n_base, kScoreThreads, kScoreThreads * 8 + 16, st, ba);
         ctx->launches++;
     }
@@ -1137,6 +1153,7 @@ int ChunkRun::spectrum() {
 
 bool ChunkRun::fused(int which) const {
     const bool ksa = which ? o_ksa2 != nullptr : ks_a;
+    if (which == 0 && ks_compose()) return false;  // (k_ks_compose takes the stage: nothing scores on the way)
     // contigs of at least bs::FUSE_MIN_LEN bases are then scored by the long-contig KS-A kernel, the others by k_break_score
     const char *env = std::getenv("BS_FUSE_SCORE");  // tests / tuning: 0 keeps k_break_score for every contig
     return kmer == 8 && !e.want_hist && !e.comp_score && (e.want_pd || ksa) && !(env && env[0] == '0');
@@ -1233,6 +1250,19 @@ int ChunkRun::prob_dist(int which) {
         }
         std::memset(&pa.sc, 0, sizeof(pa.sc));
         pa.fuse_min_len = fuse_min_len;
+        if (which == 0 && ks_compose()) {
+            bs::KsComposeArgs ka;
+            ka.pd = pa; ka.pd.prob_dist = nullptr;
+            ka.sp = sparts; ka.base_rank = (const uint16_t *)ws.base_rank.p; ka.base_off = d_base_off;
+            auto launch_kc = [&](auto kern) -> int {
+                BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+                const int nb = (int)std::min<int64_t>(C, (int64_t)ctx->sm_count * blocks_per_sm(kern, kKsThreads, hist_bytes));
+                BS_LAUNCH(kern, (unsigned)nb, kKsThreads, hist_bytes, st, ka);
+                ctx->launches++;
+                return BS_OK;
+            };
+            return packed ? launch_kc(bs::k_ks_compose<true>) : launch_kc(bs::k_ks_compose<false>);
+        }
         if (fuse) BS_TRY(score_args(which, std::max(nb_small, nblk), pa.sc));  // (a scratch row per block of the wider launch)
         if (use_small) {
             bs::ProbDistArgs ps = pa;
@@ -1531,7 +1561,7 @@ void bs_ctx_destroy(bs_ctx *ctx) {
         DevBuf *wb[] = {&w.meta, &w.read_chars, &w.read_off, &w.ctg_chars, &w.tr_chars, &w.rwords, &w.rflags, &w.cwords,
                         &w.cmask, &w.twords, &w.tmask, &w.w, &w.total, &w.ycnt, &w.yx, &w.yx2, &w.head, &w.next, &w.odd_head, &w.spbest, &w.exact, &w.sp_key, &w.sp_head, &w.sp_next, &w.sp_bitmap, &w.sp_queue,
                         &w.out_i32, &w.out_f64, &w.pd, &w.pd2, &w.hist, &w.pos,
-                        &w.base_chars, &w.base_words, &w.base_mask, &w.base_pos, &w.base_w, &w.base_total, &w.base_hits, &w.base_cnt, &w.base_di};
+                        &w.base_chars, &w.base_words, &w.base_mask, &w.base_pos, &w.base_w, &w.base_total, &w.base_hits, &w.base_cnt, &w.base_di, &w.base_rank};
         for (DevBuf *b : wb) release(*b);
         if (w.h_meta) cudaFreeHost(w.h_meta);
         if (w.ev_h2d) cudaEventDestroy(w.ev_h2d);

@@ -14,6 +14,7 @@
 #pragma once
 #include "bs_place.cuh"
 #include "bs_score.cuh"
+#include "bs_ks.cuh"
 
 namespace bs {
 
@@ -76,6 +77,10 @@ struct BaseSideArgs {
     const uint64_t *base_words;
     const uint32_t *base_mask;
     int32_t kmer;
+    // for the KS statistic of the rolling-window probabilities (k_ks_compose), all NULL / 0 when it is not wanted:
+    const WinEntry *win;       // [4^kmer]
+    int32_t rank_zero;
+    uint16_t *base_rank;       // [sum L_b] out: rank of the window that starts at a base contig position (rank_zero: a base outside ACGT)
 };
 
 // one block per base contig: ordered compaction of its row of leftmost positions (block scan per chunk of reads), so
@@ -107,6 +112,18 @@ __global__ void k_base_side(BaseSideArgs a) {
     }
     __syncthreads();
     if (tid == 0) a.cnt[b] = (int32_t)s_base;
+    if (a.base_rank) {
+        const int kshift = 64 - 2 * a.kmer;
+        const uint32_t kbits = keep_bits(a.kmer);
+        uint16_t *out = a.base_rank + a.base_off[b];
+        for (int64_t q = tid; q + a.kmer <= Lb; q += nthr) {
+            const int64_t wi = q >> 5;
+            const uint32_t o = (uint32_t)(q & 31);
+            int32_t rk = a.rank_zero;
+            if (!(window32(bm[wi], bm[wi + 1], o) & kbits)) rk = a.win[(uint32_t)(window64(bw[wi], bw[wi + 1], o) >> kshift)].rank;
+            out[q] = (uint16_t)rk;
+        }
+    }
 }
 
 // ---- placement (and scoring) of a scaffold from its parts ----
@@ -345,6 +362,153 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                 }
             }
             score_finish(a.sc, s_score, st, c, L, gw, gm, nullptr, row, N);
+        }
+    }
+}
+
+// ---- KS statistic of a scaffold's rolling-window probabilities from its parts ----
+// The windows of a scaffold are the windows of its parts (their ranks were computed once per base contig: a coalesced
+// 2-byte load instead of a 16-byte table gather per window) plus the few windows that start before a part and end in it.
+// A running "first window not yet counted" walks over the parts, so every window start 0 .. L - kmer is counted once
+// whatever the overlaps and however short a part is.  Histogram layout and sweep are k_prob_dist_ks's.
+struct KsComposeArgs {
+    ProbDistArgs pd;  // scaffolds as the contig set, table, truth side, histogram geometry, ks out (prob_dist must be NULL)
+    ScaffoldParts sp;
+    const uint16_t *base_rank;
+    const int64_t *base_off;
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(768, 2) k_ks_compose(KsComposeArgs b) {
+    const ProbDistArgs &a = b.pd;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    __shared__ int64_t s_wsum[32];
+    __shared__ int64_t s_wmax[32];
+    __shared__ int s_item;
+    __shared__ int64_t s_cov;
+    __shared__ int32_t s_rlo[COMPOSE_PART_CHUNK], s_rn[COMPOSE_PART_CHUNK], s_glo[COMPOSE_PART_CHUNK + 1], s_gn[COMPOSE_PART_CHUNK + 1];
+    __shared__ int64_t s_src[COMPOSE_PART_CHUNK];
+    uint32_t *s_hist = (uint32_t *)bs_dyn_smem();
+    uint32_t *s_bm = s_hist + a.hist_words;
+    const int kshift = 64 - 2 * a.kmer;
+    const uint32_t kbits = keep_bits(a.kmer);
+    for (int i = tid; i < a.hist_words + a.n_ranges; i += nthr) s_hist[i] = 0;
+    auto count = [&](int32_t rk) {
+        const int lw = hist_logical_word<PACKED>(rk);
+        atomicAdd(&s_hist[lw + (lw >> 5)], PACKED ? 1u << (16 * (rk & 1)) : 1u);
+        atomicOr(&s_bm[lw >> 5], 1u << (lw & 31));
+    };
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_cov = 0; }
+        __syncthreads();
+        if (s_item >= a.n_contigs) break;
+        const int64_t c = a.order[s_item];
+        const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+        const uint64_t *gw = a.ctg_words + a.ctg_woff[c];
+        const uint32_t *gm = a.ctg_mask + a.ctg_woff[c];
+        int64_t nwin = L - a.kmer + 1;
+        if (nwin < 0) nwin = 0;
+        const int64_t seg = a.ctg_seg[c];
+        const LeLt *yx = a.yx + seg * a.R_x;
+        const int64_t n_y = a.R_y > 0 ? a.ycum[seg * a.R_y + a.R_y - 1] : 0;
+        auto count_generic = [&](int64_t p) {  // a window read off the scaffold's own words
+            const int64_t wi = p >> 5;
+            const uint32_t o = (uint32_t)(p & 31);
+            int32_t rk = a.rank_zero;
+            if (!(window32(__ldg(&gm[wi]), __ldg(&gm[wi + 1]), o) & kbits))
+                rk = a.win[(uint32_t)(window64(__ldg(&gw[wi]), __ldg(&gw[wi + 1]), o) >> kshift)].rank;
+            count(rk);
+        };
+        const int64_t ps = b.sp.part_start[c], pe = b.sp.part_start[c + 1];
+        for (int64_t pc = ps; pc < pe; pc += COMPOSE_PART_CHUNK) {
+            const int np = (int)(pe - pc < COMPOSE_PART_CHUNK ? pe - pc : COMPOSE_PART_CHUNK);
+            __syncthreads();
+            if (tid == 0) {  // window ranges of the chunk's parts, in order (a handful of parts: serial)
+                int64_t cov = s_cov;
+                for (int i = 0; i < np; i++) {
+                    const int64_t g = pc + i;
+                    const int32_t bb = b.sp.part_base[g];
+                    const int64_t si = (int64_t)b.sp.part_dst[g] - b.sp.part_ov[g], b0 = b.base_off[bb], ei = si + (b.base_off[bb + 1] - b0);
+                    const int64_t gend = si < nwin ? si : nwin;  // windows that start before the part: off the scaffold
+                    s_glo[i] = (int32_t)cov;
+                    s_gn[i] = (int32_t)(gend > cov ? gend - cov : 0);
+                    if (si > cov) cov = si;
+                    int64_t last = ei - a.kmer;  // last window that lies inside the part
+                    if (last > nwin - 1) last = nwin - 1;
+                    s_rlo[i] = (int32_t)cov;
+                    s_rn[i] = (int32_t)(last >= cov ? last - cov + 1 : 0);
+                    s_src[i] = b0 + (cov - si);
+                    if (last + 1 > cov) cov = last + 1;
+                }
+                s_cov = cov;
+                s_glo[np] = (int32_t)cov;  // after the last part of the scaffold: what is left (nothing, for a well-formed set)
+                s_gn[np] = (int32_t)((pc + np >= pe && nwin > cov) ? nwin - cov : 0);
+            }
+            __syncthreads();
+            for (int i = 0; i < np; i++) {
+                const uint16_t *src = b.base_rank + s_src[i];
+                const int n = s_rn[i];
+                for (int k = tid; k < n; k += nthr) count((int32_t)__ldg(&src[k]));
+                for (int k = tid; k < s_gn[i]; k += nthr) count_generic((int64_t)s_glo[i] + k);
+            }
+            for (int k = tid; k < s_gn[np]; k += nthr) count_generic((int64_t)s_glo[np] + k);
+        }
+        __syncthreads();
+        // ---- the sweep of k_prob_dist_ks: D = sup |F_x - F_y| at every x value that is present, exact 64-bit numerators ----
+        const bool defined = nwin > 0 && n_y > 0;
+        int64_t best = 0;
+        uint32_t carry = 0;
+        for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {
+            const int r = r0 + tid;
+            const uint32_t m = r < a.n_ranges ? s_bm[r] : 0u;
+            if (m) s_bm[r] = 0;
+            const int w0 = 33 * r;
+            uint32_t cnt_r = 0;
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const uint32_t w = s_hist[w0 + __ffs((int)mm) - 1];
+                cnt_r += PACKED ? (w & 0xffffu) + (w >> 16) : w;
+            }
+            uint32_t incl = cnt_r;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL_MASK, incl, dd);
+                if (lane >= dd) incl += o;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t run = carry + incl - cnt_r;
+            for (int w = 0; w < nwarp; w++) {
+                if (w < warp) run += s_wsum[w];
+                carry += s_wsum[w];
+            }
+            for (uint32_t mm = m; mm; mm &= mm - 1) {
+                const int k = __ffs((int)mm) - 1;
+                const uint32_t w = s_hist[w0 + k];
+                s_hist[w0 + k] = 0;
+#pragma unroll
+                for (int h = 0; h < (PACKED ? 2 : 1); h++) {
+                    const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
+                    if (cnt == 0 || !defined) continue;
+                    const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
+                    const int64_t d = ks_numerator(run, run + cnt, yx[i], (uint32_t)n_y, (uint32_t)nwin);
+                    run += cnt;
+                    if (d > best) best = d;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            const int64_t o = __shfl_xor_sync(FULL_MASK, best, m);
+            if (o > best) best = o;
+        }
+        if (lane == 0) s_wmax[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nwarp; w++) if (s_wmax[w] > best) best = s_wmax[w];
+            a.ks[c] = defined ? (double)best / ((double)nwin * (double)n_y) : __longlong_as_double(0x7ff8000000000000ll);
         }
     }
 }

@@ -10,6 +10,11 @@ from genomeassembler_dev_b200 import synth, tables
 FULL = B.DEFAULT_FLAGS | B.WANT_HIST | B.WANT_POS
 
 
+def mode_flags(mode):
+    """without path_prob_dist out, the KS statistic of the window probabilities comes from the parts too (k_ks_compose)"""
+    return FULL & ~B.WANT_PROB_DIST if mode.startswith("ks_from_parts") else FULL
+
+
 def make_set(seed, length=3000, read_len=40, coverage=10, n_base=8, n_scaffolds=40, overlap=9, max_parts=None, ragged=False,
              mutate=0.0, lib_path=None):
     """truth, reads and a scaffold set: base contigs = consecutive truth intervals, each extended by `overlap` bases of
