@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
         if (tid == 0) {
             s_item = atomicAdd(a.p.work_counter, 1);
             s_placed = 0;
-            if constexpr (SCORE) { s_score.novf = 0; s_score.maxc = 0; s_score.nz = 0; }
+            if constexpr (SCORE) { s_score.novf = 0; s_score.maxc = 0; s_score.nz = 0; s_score.fallback = 0; }
         }
         __syncthreads();
         const int item = s_item;
@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
         if (tid == 0) a.p.total[c] = total;
         if constexpr (SCORE) {
             ScoreState st;
+            IncrTally tl{0, 0, 0};
             score_begin_total(a.sc, total, st, hash, hash_slots);
             if (total != 0) {
                 // (1) the reads a part placed: the parts' lists once more.  A list entry is THE placement of its read iff it
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                             te.prob = 0.0;
                             te.row = -1;
                             if (di >= 0) te = a.sc.tab[di];
-                            score_add(a.sc, s_score, st, c, di, te.prob, te.row, 1);
+                            score_add<true>(a.sc, s_score, st, c, di, te.prob, te.row, 1, &tl);
                         }
                     }
                 }
@@ -358,10 +359,16 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                     const uint32_t v = row[r];
                     if (v == POS_INF) continue;
                     if (v & ROW_SCORED) { row[r] = v & ~ROW_SCORED; continue; }
-                    score_add_position(a.sc, s_score, st, c, gw, gm, (int64_t)v, L, 1);
+                    const BreakWindow bw = break_window((int64_t)v, a.sc.kmer, L);
+                    const int di = dense_index_at(gw, gm, bw.start, bw.len);
+                    TabEntry te;
+                    te.prob = 0.0;
+                    te.row = -1;
+                    if (di >= 0) te = a.sc.tab[di];
+                    score_add<true>(a.sc, s_score, st, c, di, te.prob, te.row, 1, &tl);
                 }
             }
-            score_finish(a.sc, s_score, st, c, L, gw, gm, nullptr, row, N);
+            score_finish<true>(a.sc, s_score, st, c, L, gw, gm, nullptr, row, N, &tl);
         }
     }
 }

@@ -157,6 +157,14 @@ struct ScoreSharedCore {
     double w[32];
     int32_t cc[CC_DENSE];        // rows having count j
     int novf, maxc, nz;          // reset by thread 0 where the block fetches its next contig
+    int fallback;                // INCR (below): a count reached CC_DENSE, the rows are tallied by the sweep after all
+};
+// INCR instantiations of score_add / score_finish (bs_compose.cuh: every call adds ONE read) keep the number of rows per
+// count value up to date while the hash table fills -- a new key is a row of count 1, an increment moves a row from its
+// old count to the next -- so that no sweep over the table is needed afterwards, only its reset.  A thread's share of the
+// rows of count 1 and of all rows stays in registers until score_finish.
+struct IncrTally {
+    int nz, c1, mx;
 };
 struct ScoreShared : ScoreSharedCore {
     uint32_t hash[HASH_SLOTS];   // (dense index + 1) << 15 | count, 0 = empty; all empty between contigs
@@ -198,8 +206,9 @@ __device__ __forceinline__ void score_begin_total(const ScoreArgs &a, int32_t to
 __device__ __forceinline__ void score_begin(const ScoreArgs &a, ScoreShared &sh, int64_t c, ScoreState &st) { score_begin_total(a, a.total[c], st, sh.hash, HASH_SLOTS); }
 
 // wv reads broke the k-mer with dense index di (table entry te) in contig c
+template <bool INCR = false>
 __device__ __forceinline__ void score_add(const ScoreArgs &a, ScoreSharedCore &sh, ScoreState &st, int64_t c, int di, double prob, int32_t row,
-                                          int32_t wv) {
+                                          int32_t wv, IncrTally *t = nullptr) {
     if (row >= 0) {
         st.s1 += prob * (double)wv;
         st.s2 += prob * (wv == 1 ? st.inv_total : (double)wv / (double)st.total);
@@ -213,9 +222,24 @@ __device__ __forceinline__ void score_add(const ScoreArgs &a, ScoreSharedCore &s
                     uint32_t cur = st.hash[h];
                     if (cur == 0u) {
                         cur = atomicCAS(&st.hash[h], 0u, (key << 15) | (uint32_t)wv);
-                        if (cur == 0u) break;
+                        if (cur == 0u) {
+                            if constexpr (INCR) { t->nz++; t->c1++; if (t->mx < 1) t->mx = 1; }  // (wv == 1)
+                            break;
+                        }
                     }
-                    if ((cur >> 15) == key) { atomicAdd(&st.hash[h], (uint32_t)wv); break; }
+                    if ((cur >> 15) == key) {
+                        const uint32_t old = atomicAdd(&st.hash[h], (uint32_t)wv);
+                        if constexpr (INCR) {  // the row moves from count `was` to was + 1
+                            const int was = (int)(old & 0x7fffu);
+                            if (was + 1 >= CC_DENSE) sh.fallback = 1;
+                            else {
+                                if (was == 1) t->c1--; else atomicAdd(&sh.cc[was], -1);
+                                atomicAdd(&sh.cc[was + 1], 1);
+                                if (t->mx < was + 1) t->mx = was + 1;
+                            }
+                        }
+                        break;
+                    }
                 }
             } else {
                 atomicAdd(&st.scratch[row], wv);
@@ -242,8 +266,10 @@ __device__ __forceinline__ void score_add_position(const ScoreArgs &a, ScoreShar
 // weights w, or -- rows != NULL, the compositional path, which has no weights -- through the block's row of leftmost
 // positions per read (POS_INF_ROW: read not placed).
 constexpr uint32_t POS_INF_ROW = 0x7f7f7f7fu;
+template <bool INCR = false>
 __device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreSharedCore &sh, ScoreState &st, int64_t c, int64_t L, const uint64_t *gw,
-                                             const uint32_t *gm, const int32_t *w, const uint32_t *rows = nullptr, int64_t n_rows = 0) {
+                                             const uint32_t *gm, const int32_t *w, const uint32_t *rows = nullptr, int64_t n_rows = 0,
+                                             IncrTally *t = nullptr) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const bool want_ks = a.ks_b != nullptr;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
@@ -279,7 +305,23 @@ __device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreSharedCore
             if (slot < OVF_CAP) st.ovf[slot] = cnt; else *a.status = 1;
         }
     };
-    if (st.in_smem) {  // the usual case: the hash table's slots, emptied on the way
+    bool swept = false;
+    if constexpr (INCR) {
+        if (st.in_smem) {
+            if (!sh.fallback) {  // (block-uniform: read behind the barrier) the rows are tallied already: reset the table
+                for (int i = tid; i < st.hs; i += nthr) st.hash[i] = 0u;
+                t_nz = t->nz; t_c1 = t->c1; t_max = t->mx;
+                swept = true;
+            } else {  // a count reached CC_DENSE: forget the running tallies, sweep as usual
+                for (int i = tid; i < CC_DENSE; i += nthr) sh.cc[i] = 0;
+                __syncthreads();
+                if (tid == 0) { sh.nz = 0; sh.maxc = 0; }
+                __syncthreads();
+            }
+        }
+    }
+    if (swept) {
+    } else if (st.in_smem) {  // the usual case: the hash table's slots, emptied on the way
         for (int i = tid; i < st.hs; i += nthr) {
             const uint32_t v = st.hash[i];
             if (v != 0u) { st.hash[i] = 0u; tally((int32_t)(v & 0x7fffu)); }
@@ -317,7 +359,7 @@ __device__ __forceinline__ void score_finish(const ScoreArgs &a, ScoreSharedCore
         for (int u = 0; u < 4; u++) tally(cnt[u]);
     }
     if (t_nz) atomicAdd(&sh.nz, t_nz);
-    if (t_c1) atomicAdd(&sh.cc[1], t_c1);
+    if (t_c1) atomicAdd(&sh.cc[1], t_c1);  // (INCR: a thread's share can be negative)
     if (t_max) atomicMax(&sh.maxc, t_max);
     __syncthreads();
     // the distinct x values are 0 and count/total for the few distinct counts: thread 0 walks them

@@ -126,6 +126,9 @@ def hand_sets():
     # ragged reads, the shortest one shorter than a word: seed length < 32, junction windows as wide as the longest read
     out.append(("ragged_reads", [t[0:40], t[32:96]], [[(0, 0), (1, 8)], [(1, 0), (0, 0)]],
                 [t[i:i + 3 + (i % 37)] for i in range(0, 60)] + [t[1:70]], t, 8))
+    # one break k-mer more than CC_DENSE (1024) times in a scaffold: the running tallies of KS-B give way to the sweep
+    out.append(("one_kmer_a_thousand_times", [b"A" * 300, b"ACGT" * 10 + b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"],
+                [[(0, 0), (1, 0)], [(1, 0), (0, 0)], [(1, 0)]], [b"A" * 20] * 1100 + [b"AAAC", b"CGTA", b"GTAAAAAA"], b"A" * 300 + b"ACGT" * 10, 8))
     return out
 
 
