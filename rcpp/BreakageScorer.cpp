@@ -3,7 +3,9 @@
 // Rcpp-exported entry point, argument list and returned list (upstream :185-191, :343-353), with
 // the bodies replaced by calls into libbreakscore.so (include/breakscore.h).  Both exports of the
 // upstream file are here: assemble_contigs (:79-174, the scaffold explosion, native host code in the
-// library) and calc_breakscore (the scorer, CUDA).
+// library) and calc_breakscore (the scorer, CUDA) -- plus assemble_and_score, the two in one call for the place
+// where the R driver runs them back to back (lib/DeNovoAssembler.R:343-355): the candidates then stay a list of
+// (base contig, overlap) parts and are scored from their parts (bs_score_scaffolds).
 //
 // Build from R:
 //   Sys.setenv(PKG_CXXFLAGS = "-I<repo>/include", PKG_LIBS = "-L<repo>/genomeassembler_dev_b200 -lbreakscore -Wl,-rpath,<repo>/genomeassembler_dev_b200")
@@ -134,14 +136,16 @@ void set_breakscore_truth_prob(const std::vector<double> &prob) {
     s.truth_dirty = true;
 }
 
-// [[Rcpp::export]]
-Rcpp::List calc_breakscore(
+namespace {
+// calc_breakscore's body; `set` != NULL: `path` holds the texts of a scaffold set given as parts, scored from the parts
+Rcpp::List score_impl(
     const std::vector<std::string> &path,
     const std::vector<std::string> &sequencing_reads,
     const std::string &true_solution,
     const int &kmer,
     const std::vector<std::string> &bp_kmer,
-    const std::vector<double> &bp_prob) {
+    const std::vector<double> &bp_prob,
+    const bs_scaffold_set *set) {
     Session &s = session();
     if (bp_kmer.size() != bp_prob.size()) Rcpp::stop("bp_kmer and bp_prob differ in length");
 
@@ -165,7 +169,7 @@ Rcpp::List calc_breakscore(
     }
 
     // inputs: flattened straight into pinned memory (the copy Rcpp's conversion forces anyway)
-    const int64_t need = flat_size(path) + flat_size(sequencing_reads) + (int64_t)true_solution.size() + 64;
+    const int64_t need = (set ? 0 : flat_size(path)) + flat_size(sequencing_reads) + (int64_t)true_solution.size() + 64;
     if (need > s.pinned_cap) {
         if (s.pinned) bs_host_free(s.pinned);
         s.pinned = (char *)bs_host_alloc(need + need / 4);
@@ -174,7 +178,7 @@ Rcpp::List calc_breakscore(
     }
     std::vector<int64_t> ctg_off, read_off;
     char *ctg_chars = s.pinned;
-    char *read_chars = flatten(path, ctg_chars, ctg_off);
+    char *read_chars = set ? ctg_chars : flatten(path, ctg_chars, ctg_off);
     char *truth_chars = flatten(sequencing_reads, read_chars, read_off);
     std::memcpy(truth_chars, true_solution.data(), true_solution.size());
 
@@ -208,9 +212,13 @@ Rcpp::List calc_breakscore(
     r.path_prob_dist = pd_flat.data();
     r.path_prob_dist_off = pd_off.data();
     if (want_path_freq) r.hist = hist.data();
-    check(s, bs_score_multi(s.all.data(), (int)s.all.size(), ctg_chars, ctg_off.data(), C, read_chars, read_off.data(),
-                            (int64_t)sequencing_reads.size(), truth_chars, (int64_t)true_solution.size(), kmer,
-                            BS_DEFAULT_FLAGS | BS_WANT_LEV | (want_path_freq ? BS_WANT_HIST : 0u), &r));
+    const uint32_t flags = BS_DEFAULT_FLAGS | BS_WANT_LEV | (want_path_freq ? BS_WANT_HIST : 0u);
+    if (set)  // (one GPU: the first context)
+        check(s, bs_score_scaffolds(s.ctx, set, read_chars, read_off.data(), (int64_t)sequencing_reads.size(), 0, truth_chars,
+                                    (int64_t)true_solution.size(), kmer, flags, &r));
+    else
+        check(s, bs_score_multi(s.all.data(), (int)s.all.size(), ctg_chars, ctg_off.data(), C, read_chars, read_off.data(),
+                                (int64_t)sequencing_reads.size(), truth_chars, (int64_t)true_solution.size(), kmer, flags, &r));
 
     std::vector<std::vector<double>> path_prob_dist((size_t)C);
     for (int64_t c = 0; c < C; c++) path_prob_dist[c].assign(pd_flat.begin() + pd_off[c], pd_flat.begin() + pd_off[c + 1]);
@@ -242,4 +250,52 @@ Rcpp::List calc_breakscore(
         Rcpp::Named("ks_stat_path_freq") = ks_b,
         Rcpp::Named("path_freq_startpos") = startpos,
         Rcpp::Named("path_freq") = Rcpp::wrap(path_freq));
+}
+}  // namespace
+
+// [[Rcpp::export]]
+Rcpp::List calc_breakscore(
+    const std::vector<std::string> &path,
+    const std::vector<std::string> &sequencing_reads,
+    const std::string &true_solution,
+    const int &kmer,
+    const std::vector<std::string> &bp_kmer,
+    const std::vector<double> &bp_prob) {
+    return score_impl(path, sequencing_reads, true_solution, kmer, bp_kmer, bp_prob, nullptr);
+}
+
+// assemble_contigs(velvet_contigs, dbg_kmer, seed) followed by calc_breakscore(<its result>, ...) in one call: the same
+// list (its "sequence" member is what assemble_contigs returns, same strings in the same order), but the candidates are
+// scored from their parts -- reads placed once per velvet contig, scaffold texts never copied to the device.
+// [[Rcpp::export]]
+Rcpp::List assemble_and_score(
+    const std::vector<std::string> &velvet_contigs,
+    const int &dbg_kmer,
+    const int &seed,
+    const std::vector<std::string> &sequencing_reads,
+    const std::string &true_solution,
+    const int &kmer,
+    const std::vector<std::string> &bp_kmer,
+    const std::vector<double> &bp_prob) {
+    std::vector<char> chars((size_t)flat_size(velvet_contigs) + 1);
+    std::vector<int64_t> off;
+    flatten(velvet_contigs, chars.data(), off);
+    bs_string_list *list = nullptr;
+    bs_scaffold_list *parts = nullptr;
+    if (bs_assemble_scaffolds(chars.data(), off.data(), (int64_t)velvet_contigs.size(), dbg_kmer, seed, 20000, 0, &list, &parts) != BS_OK)
+        Rcpp::stop(bs_assemble_last_error());
+    const int64_t n = bs_string_list_size(list);
+    std::vector<char> out_chars((size_t)bs_string_list_bytes(list) + 1);
+    std::vector<int64_t> out_off((size_t)n + 1), part_start((size_t)n + 1);
+    std::vector<int32_t> part_base((size_t)bs_scaffold_list_parts(parts) + 1), part_overlap(part_base.size());
+    bs_string_list_copy(list, out_chars.data(), out_off.data());
+    bs_scaffold_list_copy(parts, part_start.data(), part_base.data(), part_overlap.data());
+    bs_string_list_free(list);
+    bs_scaffold_list_free(parts);
+    std::vector<std::string> path((size_t)n);
+    for (int64_t i = 0; i < n; i++) path[(size_t)i].assign(out_chars.data() + out_off[i], (size_t)(out_off[i + 1] - out_off[i]));
+    bs_scaffold_set set;
+    set.n_base = (int64_t)velvet_contigs.size(); set.base_chars = chars.data(); set.base_off = off.data();
+    set.n_scaffolds = n; set.scaffold_part_start = part_start.data(); set.part_base = part_base.data(); set.part_overlap = part_overlap.data();
+    return score_impl(path, sequencing_reads, true_solution, kmer, bp_kmer, bp_prob, &set);
 }
