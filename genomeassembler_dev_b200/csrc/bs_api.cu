@@ -428,6 +428,7 @@ struct ChunkRun {
     const int64_t *d_base_off = nullptr, *d_base_woff = nullptr, *d_base_pos_off = nullptr;
     const int32_t *d_base_seg = nullptr, *d_base_order = nullptr;
     int64_t n_base = 0, base_bytes = 0, base_w_elems = 0, max_read_len = 0;
+    bool comp_text = true;  // the scaffold texts are composed on the device (else only their packed words: base contigs of ACGT only)
     int32_t *w_ptr = nullptr, *total_ptr = nullptr;  // position weights and reads placed per contig (workspace, or the caller's with BS_WEIGHTS_*)
 
     // result destinations on the device (user arrays with BS_DEVICE_RESULT, else the workspace)
@@ -656,6 +657,14 @@ int ChunkRun::prepare() {
         std::stable_sort(base_order.begin(), base_order.end(), [&](int32_t x, int32_t y) { return base_off[x + 1] - base_off[x] > base_off[y + 1] - base_off[y]; });
         base_bytes = base_off[n_base];
         base_words = base_woff[n_base];
+        {   // no kernel looks at the text of a contig made of ACGT only (every byte-comparison path starts from a byte outside
+            // ACGT in the contig, the read or the truth, which then cannot match): such a set is kept as packed words alone
+            const char *bc = cp->base_chars + cp->base_off[0];
+            bool pure = true;
+            for (int64_t i = 0; pure && i < base_bytes; i++) pure = bc[i] == 'A' || bc[i] == 'C' || bc[i] == 'G' || bc[i] == 'T';
+            const char *env = std::getenv("BS_COMPOSE_TEXT");  // tests: 1 composes the text anyway
+            comp_text = !pure || e.want_lev || (env && env[0] == '1');
+        }
         base_w_elems = base_bytes + n_base;
         const int64_t n_parts = cp->scaffold_part_start[cp->n_scaffolds];
         o_base_off = mb.add(base_off.data(), base_off.size());
@@ -690,7 +699,7 @@ int ChunkRun::prepare() {
         BS_TRY(ensure(ctx, ws.read_chars, (size_t)read_bytes + 32));
         BS_TRY(ensure(ctx, ws.tr_chars, (size_t)tr_bytes + 32));
     }
-    if (!e.dev_chars || comp) BS_TRY(ensure(ctx, ws.ctg_chars, (size_t)ctg_bytes + 32));
+    if (!e.dev_chars || (comp && comp_text)) BS_TRY(ensure(ctx, ws.ctg_chars, (size_t)ctg_bytes + 32));
     if (comp) {
         BS_TRY(ensure(ctx, ws.base_chars, (size_t)base_bytes + 32));
         BS_TRY(ensure(ctx, ws.base_words, (size_t)base_words * 8 + 8));
@@ -781,7 +790,7 @@ int ChunkRun::prepare() {
         }
         if (comp) {  // only the base contigs cross PCIe; k_compose_text writes the scaffold texts into the workspace
             if (base_bytes) BS_CUDA(cudaMemcpyAsync(ws.base_chars.p, e.comp->base_chars + e.comp->base_off[0], (size_t)base_bytes, cudaMemcpyHostToDevice, cs));
-            d_cchars = (const uint8_t *)ws.ctg_chars.p;
+            d_cchars = comp_text ? (const uint8_t *)ws.ctg_chars.p : nullptr;
         }
     }
     BS_CUDA(cudaEventRecord(ws.ev_h2d, ctx->copy_stream));
@@ -865,14 +874,23 @@ int ChunkRun::pack() {
                 BS_LAUNCH(bs::k_pack_seqs, grid_for(bset.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, bset);
                 ctx->launches++;
             }
-            bs::ComposeTextArgs ca;
-            ca.sp = sparts; ca.base_chars = bset.chars; ca.base_off = d_base_off; ca.ctg_off = d_ctg_off; ca.ctg_chars = (uint8_t *)ws.ctg_chars.p;
-            ca.n_scaffolds = C;
-            BS_LAUNCH(bs::k_compose_text, (unsigned)std::min<int64_t>(C, (int64_t)ctx->sm_count * 8), kPackThreads, 0, st, ca);
+            if (comp_text) {
+                bs::ComposeTextArgs ca;
+                ca.sp = sparts; ca.base_chars = bset.chars; ca.base_off = d_base_off; ca.ctg_off = d_ctg_off; ca.ctg_chars = (uint8_t *)ws.ctg_chars.p;
+                ca.n_scaffolds = C;
+                BS_LAUNCH(bs::k_compose_text, (unsigned)std::min<int64_t>(C, (int64_t)ctx->sm_count * 8), kPackThreads, 0, st, ca);
+            } else {
+                bs::ComposeWordsArgs cw;
+                cw.sp = sparts; cw.base_woff = d_base_woff; cw.base_words = bset.words; cw.base_mask = bset.mask;
+                cw.ctg_off = d_ctg_off; cw.ctg_woff = d_ctg_woff; cw.ctg_words = cs.words; cw.ctg_mask = cs.mask; cw.n_scaffolds = C;
+                BS_LAUNCH(bs::k_compose_words, (unsigned)std::min<int64_t>(C, (int64_t)ctx->sm_count * 8), kPackThreads, 0, st, cw);
+            }
             ctx->launches++;
         }
-        BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
-        ctx->launches++;
+        if (!e.comp || comp_text) {
+            BS_LAUNCH(bs::k_pack_seqs, grid_for(cs.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, cs);
+            ctx->launches++;
+        }
         if ((e.want_ks || e.want_sp || e.want_lev) && !e.w_out) {
             BS_LAUNCH(bs::k_pack_seqs, grid_for(ts.total_words, kPackThreads, grid_cap), kPackThreads, 0, st, ts);
             ctx->launches++;

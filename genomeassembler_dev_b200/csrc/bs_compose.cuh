@@ -64,6 +64,66 @@ __global__ void k_compose_text(ComposeTextArgs a) {
     }
 }
 
+// ---- ... or, when no kernel will look at the text (base contigs of ACGT only: a read or truth with another byte cannot
+// match them, so the byte-comparison paths are never taken), the packed words and masks straight from the base contigs'
+// packed words: a thread per output word, funnel shifts over the parts the word spans ----
+struct ComposeWordsArgs {
+    ScaffoldParts sp;
+    const int64_t *base_woff;
+    const uint64_t *base_words;
+    const uint32_t *base_mask;
+    const int64_t *ctg_off;   // [n_scaffolds + 1] text offsets (lengths)
+    const int64_t *ctg_woff;  // [n_scaffolds + 1] word offsets
+    uint64_t *ctg_words;
+    uint32_t *ctg_mask;
+    int64_t n_scaffolds;
+};
+
+__global__ void k_compose_words(ComposeWordsArgs a) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int64_t c = blockIdx.x; c < a.n_scaffolds; c += gridDim.x) {
+        const int64_t L = a.ctg_off[c + 1] - a.ctg_off[c];
+        const int64_t nwords = a.ctg_woff[c + 1] - a.ctg_woff[c];
+        uint64_t *ow = a.ctg_words + a.ctg_woff[c];
+        uint32_t *om = a.ctg_mask + a.ctg_woff[c];
+        const int64_t ps = a.sp.part_start[c], pe = a.sp.part_start[c + 1];
+        for (int64_t w = tid; w < nwords; w += nthr) {
+            int64_t pos = 32 * w;
+            uint64_t word = 0;
+            uint32_t mask = 0;
+            if (pos >= L) mask = ~0u;  // past the end and the two pad words: code 0, mask set
+            else {
+                int64_t lo = ps, hi = pe - 1;  // last part whose new bases start at or before pos
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi + 1) >> 1;
+                    if ((int64_t)__ldg(&a.sp.part_dst[mid]) <= pos) lo = mid; else hi = mid - 1;
+                }
+                int64_t i = lo;
+                int filled = 0;
+                while (filled < 32) {
+                    if (pos >= L) { mask |= keep_bits(32 - filled) >> filled; break; }
+                    const int64_t dst = __ldg(&a.sp.part_dst[i]);
+                    const int64_t end = i + 1 < pe ? (int64_t)__ldg(&a.sp.part_dst[i + 1]) : L;
+                    int n = 32 - filled;
+                    if (end - pos < n) n = (int)(end - pos);
+                    if (n > 0) {
+                        const int64_t q = (int64_t)__ldg(&a.sp.part_ov[i]) + (pos - dst);
+                        const int64_t bo = __ldg(&a.base_woff[__ldg(&a.sp.part_base[i])]) + (q >> 5);
+                        const uint32_t o = (uint32_t)(q & 31);
+                        word |= (window64(__ldg(&a.base_words[bo]), __ldg(&a.base_words[bo + 1]), o) & keep_bases(n)) >> (2 * filled);
+                        mask |= (window32(__ldg(&a.base_mask[bo]), __ldg(&a.base_mask[bo + 1]), o) & keep_bits(n)) >> filled;
+                        filled += n;
+                        pos += n;
+                    }
+                    if (pos >= end) i++;
+                }
+            }
+            ow[w] = word;
+            om[w] = mask;
+        }
+    }
+}
+
 // ---- what a base contig contributes to every scaffold it is part of, computed once ----
 struct BaseSideArgs {
     const int32_t *base_pos;   // [n_base][n_reads] leftmost positions out of k_place_index, -1: none
@@ -187,7 +247,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
         const int64_t L = a.p.ctg_off[c + 1] - coff;
         const uint64_t *gw = a.p.ctg_words + a.p.ctg_woff[c];
         const uint32_t *gm = a.p.ctg_mask + a.p.ctg_woff[c];
-        const uint8_t *cc = a.p.ctg_chars + coff;
+        const uint8_t *cc = a.p.ctg_chars ? a.p.ctg_chars + coff : nullptr;  // (NULL: no text was composed -- nothing but ACGT anywhere in it)
         const int64_t ps = a.sp.part_start[c], pe = a.sp.part_start[c + 1];
         const int64_t r0 = a.p.ix.seg_read_start[s];
 
@@ -254,7 +314,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
             }
             // reads outside the index (a byte outside ACGT in the seed): text comparison in every junction window
             int64_t k = 0;
-            for (uint32_t q = a.p.ix.odd_head[s]; q != 0;) {
+            for (uint32_t q = cc ? a.p.ix.odd_head[s] : 0u; q != 0;) {  // (without a text: such a read matches nowhere)
                 const int64_t n = (int64_t)q - 1;
                 q = a.p.ix.next[n].x;
                 const int len = read_length(a.p.reads, n);

@@ -224,6 +224,7 @@ __device__ __forceinline__ int64_t find_bytes(const uint8_t *cc, int64_t L, cons
 __device__ __forceinline__ bool verify_at(const PlaceIxArgs &a, const uint64_t *gw, const uint32_t *gm, const uint8_t *cc,
                                           int64_t p, int64_t n, int len, uint64_t w0) {
     if (a.reads.flags[n] & 1) {  // bytes outside ACGT somewhere in (or next to) the read: compare the text
+        if (cc == nullptr) return false;  // (bs_compose.cuh: a contig of ACGT only, kept without its text)
         const uint8_t *rc = a.reads.chars + read_begin(a.reads, n);
         for (int i = 0; i < len; i++)
             if (cc[p + i] != rc[i]) return false;
