@@ -23,6 +23,7 @@
 #include <numeric>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/breakscore.h"
@@ -428,6 +429,11 @@ struct ChunkRun {
     const int64_t *d_base_off = nullptr, *d_base_woff = nullptr, *d_base_pos_off = nullptr;
     const int32_t *d_base_seg = nullptr, *d_base_order = nullptr;
     int64_t n_base = 0, base_bytes = 0, base_w_elems = 0, max_read_len = 0;
+    // ... extended by the texts around the distinct junctions (previous base contig's tail + next one's head): placed like base
+    // contigs, once, so that a scaffold takes its junction-crossing reads from a list as well (reads of one length only)
+    int64_t n_ext = 0, ext_bytes = 0;
+    std::vector<char> junc_chars;
+    const int32_t *d_part_jid = nullptr;
     bool comp_text = true;  // the scaffold texts are composed on the device (else only their packed words: base contigs of ACGT only)
     int32_t *w_ptr = nullptr, *total_ptr = nullptr;  // position weights and reads placed per contig (workspace, or the caller's with BS_WEIGHTS_*)
 
@@ -643,20 +649,69 @@ int ChunkRun::prepare() {
     const size_t o_roff = e.roff ? mb.add(roff_local.data(), (size_t)N + 1) : 0;
     // compositional scoring: the base contigs as a contig set of their own (one segment) and the parts of the scaffolds
     size_t o_base_off = 0, o_base_woff = 0, o_base_seg = 0, o_base_order = 0, o_base_pos_off = 0, o_part_start = 0, o_part_base = 0,
-           o_part_ov = 0, o_part_dst = 0;
+           o_part_ov = 0, o_part_dst = 0, o_part_jid = 0;
     int64_t base_words = 0;
     if (comp) {
         const bs_scaffold_set *cp = e.comp;
         n_base = cp->n_base;
-        std::vector<int64_t> base_off((size_t)n_base + 1), base_woff((size_t)n_base + 1), base_pos_off((size_t)n_base + 1);
-        std::vector<int32_t> base_seg((size_t)std::max<int64_t>(n_base, 1), 0), base_order((size_t)n_base);
+        const int64_t n_parts = cp->scaffold_part_start[cp->n_scaffolds];
+        // distinct junctions (previous base contig, next base contig, overlap) whose crossing reads can be found once, in the
+        // text  previous[L - span ..] + next[overlap .. overlap + span)  (span = read length - 1): both contigs at least span
+        // long, reads of ONE length (then every occurrence in that text crosses the junction, and the leftmost one the read
+        // index placement reports is the leftmost crossing one).  Other junctions are probed per scaffold (k_place_compose).
+        std::vector<int32_t> part_jid((size_t)std::max<int64_t>(n_parts, 1), -1);
+        std::vector<int64_t> junc_len;
+        junc_chars.clear();
+        {
+            const int64_t span = max_read_len - 1;
+            const char *jenv = std::getenv("BS_COMPOSE_JUNCTIONS");  // tests: 0 probes every junction per scaffold
+            if (!e.roff && span >= 1 && N > 0 && !(jenv && jenv[0] == '0')) {
+                // (base contig pair -> junction: a direct table for the usual handful of base contigs -- one overlap per pair is
+                // the rule, further ones go to the map -- so that the 10^5 parts of a cfg-4 set cost a table look-up each)
+                std::unordered_map<uint64_t, int32_t> seen;
+                const bool direct = n_base <= 2048;
+                std::vector<int32_t> pair_jid(direct ? (size_t)(n_base * n_base) : 0, -1), pair_ov(direct ? (size_t)(n_base * n_base) : 0, 0);
+                const int64_t max_junc = std::max<int64_t>(0, std::min<int64_t>(n_parts, ((int64_t)1 << 28) / std::max<int64_t>(N, 1)) - n_base);
+                for (int64_t c = 0; c < cp->n_scaffolds; c++)
+                    for (int64_t g = cp->scaffold_part_start[c] + 1; g < cp->scaffold_part_start[c + 1]; g++) {
+                        const int64_t bp = cp->part_base[g - 1], bn = cp->part_base[g], ov = cp->part_overlap[g];
+                        const int64_t Lp = cp->base_off[bp + 1] - cp->base_off[bp], Ln = cp->base_off[bn + 1] - cp->base_off[bn];
+                        if (Lp < span || Ln < span || ov >= 65536 || bp >= (1 << 24) || bn >= (1 << 24)) continue;
+                        int32_t jid = -1;
+                        const size_t slot = direct ? (size_t)(bp * n_base + bn) : 0;
+                        const uint64_t key = ((uint64_t)bp << 40) | ((uint64_t)bn << 16) | (uint64_t)ov;
+                        if (direct && pair_jid[slot] >= 0 && pair_ov[slot] == (int32_t)ov) jid = pair_jid[slot];
+                        else if (!direct || pair_jid[slot] >= 0) {
+                            auto it = seen.find(key);
+                            if (it != seen.end()) jid = it->second;
+                        }
+                        if (jid < 0) {
+                            if ((int64_t)junc_len.size() >= max_junc) continue;  // (the lists are [contig][read] arrays: bounded)
+                            jid = (int32_t)junc_len.size();
+                            if (direct && pair_jid[slot] < 0) { pair_jid[slot] = jid; pair_ov[slot] = (int32_t)ov; }
+                            else seen.emplace(key, jid);
+                            const int64_t head = std::min<int64_t>(Ln - ov, span);
+                            junc_chars.insert(junc_chars.end(), cp->base_chars + cp->base_off[bp + 1] - span, cp->base_chars + cp->base_off[bp + 1]);
+                            junc_chars.insert(junc_chars.end(), cp->base_chars + cp->base_off[bn] + ov, cp->base_chars + cp->base_off[bn] + ov + head);
+                            junc_len.push_back(span + head);
+                        }
+                        part_jid[(size_t)g] = (int32_t)n_base + jid;
+                    }
+            }
+        }
+        n_ext = n_base + (int64_t)junc_len.size();
+        std::vector<int64_t> base_off((size_t)n_ext + 1), base_woff((size_t)n_ext + 1), base_pos_off((size_t)n_ext + 1);
+        std::vector<int32_t> base_seg((size_t)std::max<int64_t>(n_ext, 1), 0), base_order((size_t)n_ext);
         base_woff[0] = 0;
-        for (int64_t i = 0; i <= n_base; i++) { base_off[i] = cp->base_off[i] - cp->base_off[0]; base_pos_off[i] = i * N; }
-        for (int64_t i = 0; i < n_base; i++) base_woff[i + 1] = base_woff[i] + (base_off[i + 1] - base_off[i] + 31) / 32 + 2;
+        for (int64_t i = 0; i <= n_base; i++) base_off[i] = cp->base_off[i] - cp->base_off[0];
+        for (int64_t i = n_base; i < n_ext; i++) base_off[i + 1] = base_off[i] + junc_len[(size_t)(i - n_base)];
+        for (int64_t i = 0; i <= n_ext; i++) base_pos_off[i] = i * N;
+        for (int64_t i = 0; i < n_ext; i++) base_woff[i + 1] = base_woff[i] + (base_off[i + 1] - base_off[i] + 31) / 32 + 2;
         std::iota(base_order.begin(), base_order.end(), 0);
         std::stable_sort(base_order.begin(), base_order.end(), [&](int32_t x, int32_t y) { return base_off[x + 1] - base_off[x] > base_off[y + 1] - base_off[y]; });
+        ext_bytes = base_off[n_ext];
         base_bytes = base_off[n_base];
-        base_words = base_woff[n_base];
+        base_words = base_woff[n_ext];
         {   // no kernel looks at the text of a contig made of ACGT only (every byte-comparison path starts from a byte outside
             // ACGT in the contig, the read or the truth, which then cannot match): such a set is kept as packed words alone
             const char *bc = cp->base_chars + cp->base_off[0];
@@ -665,8 +720,7 @@ int ChunkRun::prepare() {
             const char *env = std::getenv("BS_COMPOSE_TEXT");  // tests: 1 composes the text anyway
             comp_text = !pure || e.want_lev || (env && env[0] == '1');
         }
-        base_w_elems = base_bytes + n_base;
-        const int64_t n_parts = cp->scaffold_part_start[cp->n_scaffolds];
+        base_w_elems = ext_bytes + n_ext;
         o_base_off = mb.add(base_off.data(), base_off.size());
         o_base_woff = mb.add(base_woff.data(), base_woff.size());
         o_base_seg = mb.add(base_seg.data(), base_seg.size());
@@ -676,6 +730,7 @@ int ChunkRun::prepare() {
         o_part_base = mb.add(cp->part_base, (size_t)n_parts);
         o_part_ov = mb.add(cp->part_overlap, (size_t)n_parts);
         o_part_dst = mb.add(e.part_dst, (size_t)n_parts);
+        o_part_jid = mb.add(part_jid.data(), (size_t)n_parts);
     }
 
     if (mb.bytes.size() > ws.h_meta_cap) {
@@ -701,16 +756,16 @@ int ChunkRun::prepare() {
     }
     if (!e.dev_chars || (comp && comp_text)) BS_TRY(ensure(ctx, ws.ctg_chars, (size_t)ctg_bytes + 32));
     if (comp) {
-        BS_TRY(ensure(ctx, ws.base_chars, (size_t)base_bytes + 32));
+        BS_TRY(ensure(ctx, ws.base_chars, (size_t)ext_bytes + 32));
         BS_TRY(ensure(ctx, ws.base_words, (size_t)base_words * 8 + 8));
         BS_TRY(ensure(ctx, ws.base_mask, (size_t)base_words * 4 + 8));
-        BS_TRY(ensure(ctx, ws.base_pos, (size_t)std::max<int64_t>(n_base * N, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_pos, (size_t)std::max<int64_t>(n_ext * N, 1) * 4));
         BS_TRY(ensure(ctx, ws.base_w, (size_t)std::max<int64_t>(base_w_elems, 1) * 4));
-        BS_TRY(ensure(ctx, ws.base_total, (size_t)std::max<int64_t>(n_base, 1) * 4));
-        BS_TRY(ensure(ctx, ws.base_hits, (size_t)std::max<int64_t>(n_base * N, 1) * 8));
-        BS_TRY(ensure(ctx, ws.base_cnt, (size_t)std::max<int64_t>(n_base, 1) * 4));
-        BS_TRY(ensure(ctx, ws.base_di, (size_t)std::max<int64_t>(n_base * N, 1) * 4));
-        BS_TRY(ensure(ctx, ws.base_rank, (size_t)std::max<int64_t>(base_bytes, 1) * 2 + 16));
+        BS_TRY(ensure(ctx, ws.base_total, (size_t)std::max<int64_t>(n_ext, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_hits, (size_t)std::max<int64_t>(n_ext * N, 1) * 8));
+        BS_TRY(ensure(ctx, ws.base_cnt, (size_t)std::max<int64_t>(n_ext, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_di, (size_t)std::max<int64_t>(n_ext * N, 1) * 4));
+        BS_TRY(ensure(ctx, ws.base_rank, (size_t)std::max<int64_t>(ext_bytes, 1) * 2 + 16));
     }
     BS_TRY(ensure(ctx, ws.rwords, (size_t)std::max<int64_t>(N, 1) * W * 8));
     BS_TRY(ensure(ctx, ws.rflags, (size_t)std::max<int64_t>(N, 1) + 8));
@@ -768,7 +823,8 @@ int ChunkRun::prepare() {
         d_base_pos_off = (const int64_t *)(dm + o_base_pos_off);
         sparts.part_start = (const int64_t *)(dm + o_part_start); sparts.part_base = (const int32_t *)(dm + o_part_base);
         sparts.part_ov = (const int32_t *)(dm + o_part_ov); sparts.part_dst = (const int32_t *)(dm + o_part_dst);
-        bset = bs::SeqSet{(const uint8_t *)ws.base_chars.p, d_base_off, d_base_woff, (uint64_t *)ws.base_words.p, (uint32_t *)ws.base_mask.p, n_base, base_words};
+        d_part_jid = (const int32_t *)(dm + o_part_jid);
+        bset = bs::SeqSet{(const uint8_t *)ws.base_chars.p, d_base_off, d_base_woff, (uint64_t *)ws.base_words.p, (uint32_t *)ws.base_mask.p, n_ext, base_words};
     }
 
     // ---------------- H2D (copy stream) ----------------
@@ -790,6 +846,8 @@ int ChunkRun::prepare() {
         }
         if (comp) {  // only the base contigs cross PCIe; k_compose_text writes the scaffold texts into the workspace
             if (base_bytes) BS_CUDA(cudaMemcpyAsync(ws.base_chars.p, e.comp->base_chars + e.comp->base_off[0], (size_t)base_bytes, cudaMemcpyHostToDevice, cs));
+            if (!junc_chars.empty())  // (pageable source: staged before the call returns)
+                BS_CUDA(cudaMemcpyAsync((char *)ws.base_chars.p + base_bytes, junc_chars.data(), junc_chars.size(), cudaMemcpyHostToDevice, cs));
             d_cchars = comp_text ? (const uint8_t *)ws.ctg_chars.p : nullptr;
         }
     }
@@ -845,9 +903,9 @@ int ChunkRun::prepare() {
     }
     if (comp) {
         BS_CUDA(cudaMemsetAsync(ws.base_w.p, 0, (size_t)std::max<int64_t>(base_w_elems, 1) * 4, st));
-        BS_CUDA(cudaMemsetAsync(ws.base_total.p, 0, (size_t)std::max<int64_t>(n_base, 1) * 4, st));
-        BS_CUDA(cudaMemsetAsync(ws.base_cnt.p, 0, (size_t)std::max<int64_t>(n_base, 1) * 4, st));
-        BS_CUDA(cudaMemsetAsync(ws.base_pos.p, 0xff, (size_t)std::max<int64_t>(n_base * N, 1) * 4, st));
+        BS_CUDA(cudaMemsetAsync(ws.base_total.p, 0, (size_t)std::max<int64_t>(n_ext, 1) * 4, st));
+        BS_CUDA(cudaMemsetAsync(ws.base_cnt.p, 0, (size_t)std::max<int64_t>(n_ext, 1) * 4, st));
+        BS_CUDA(cudaMemsetAsync(ws.base_pos.p, 0xff, (size_t)std::max<int64_t>(n_ext * N, 1) * 4, st));
     }
     BS_TRY(ensure(ctx, ctx->d_counters, 64));
     BS_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, st));  // work counters of the persistent kernels
@@ -1035,10 +1093,10 @@ int ChunkRun::place_composed() {
     if (N > 0 && n_base > 0) {
         const size_t smem = bs::place_index_smem_bytes(kHitCap, kPlaceIxThreads);
         const int per_sm = blocks_per_sm(bs::k_place_index<false>, kPlaceIxThreads, smem);
-        const int nblk = (int)std::min<int64_t>(n_base, (int64_t)ctx->sm_count * per_sm);
+        const int nblk = (int)std::min<int64_t>(n_ext, (int64_t)ctx->sm_count * per_sm);
         const int64_t dense_stride = (max_seg_reads + 31) / 32 * 32;
         bs::PlaceIxArgs pa;
-        pa.order = d_base_order; pa.n_items = (int32_t)n_base; pa.work_counter = (int32_t *)ctx->d_counters.p + 11;
+        pa.order = d_base_order; pa.n_items = (int32_t)n_ext; pa.work_counter = (int32_t *)ctx->d_counters.p + 11;
         pa.ctg_off = d_base_off; pa.ctg_woff = d_base_woff; pa.ctg_words = bset.words; pa.ctg_mask = bset.mask;
         pa.ctg_chars = bset.chars; pa.ctg_seg = d_base_seg;
         pa.reads = rs; pa.ix = ix;
@@ -1062,14 +1120,14 @@ int ChunkRun::place_composed() {
     }
     if (n_base > 0) {  // per base contig, once: the list of reads placed in it and the break 8-mer of its interior positions
         bs::BaseSideArgs ba;
-        ba.base_pos = (const int32_t *)ws.base_pos.p; ba.n_base = n_base; ba.n_reads = N;
+        ba.base_pos = (const int32_t *)ws.base_pos.p; ba.n_base = n_ext; ba.n_reads = N;
         ba.hits = (uint2 *)ws.base_hits.p; ba.hit_di = (int32_t *)ws.base_di.p; ba.cnt = (int32_t *)ws.base_cnt.p;
         ba.base_off = d_base_off; ba.base_woff = d_base_woff; ba.base_words = bset.words; ba.base_mask = bset.mask;
         ba.kmer = kmer;
         const bool ranks = ks_compose();
         ba.win = ranks ? (const bs::WinEntry *)ctx->ks.win.p : nullptr; ba.rank_zero = ctx->ks.rank_zero;
         ba.base_rank = ranks ? (uint16_t *)ws.base_rank.p : nullptr;
-        BS_LAUNCH(bs::k_base_side, (unsigned)n_base, kScoreThreads, kScoreThreads * 8 + 16, st, ba);
+        BS_LAUNCH(bs::k_base_side, (unsigned)n_ext, kScoreThreads, kScoreThreads * 8 + 16, st, ba);
         ctx->launches++;
     }
     bs::PlaceComposeArgs ca;
@@ -1079,13 +1137,13 @@ int ChunkRun::place_composed() {
     ca.p.ctg_chars = d_cchars; ca.p.ctg_seg = d_ctg_seg;
     ca.p.reads = rs; ca.p.ix = ix;
     ca.p.w = w_ptr; ca.p.total = total_ptr; ca.p.pos = o_pos; ca.p.pos_off = d_pos_off;
-    ca.sp = sparts; ca.n_reads = N; ca.max_read_len = (int32_t)max_read_len;
+    ca.sp = sparts; ca.part_jid = d_part_jid; ca.n_reads = N; ca.max_read_len = (int32_t)max_read_len;
     ca.base_hits = (const uint2 *)ws.base_hits.p; ca.base_cnt = (const int32_t *)ws.base_cnt.p; ca.base_hit_di = (const int32_t *)ws.base_di.p;
     // dynamic shared memory of a block: (scored here) the hash table of the break k-mers, sized for the reads one scaffold can
     // place so that KS-B never needs the global scratch rows; then the block's row of leftmost positions per read, while two
     // blocks per SM fit -- else the row lives in global memory (L2)
     // (an SM holds 228 KB of shared memory, 1 KB of it reserved per resident block; the kernel's static part goes off as well)
-    const size_t static_smem = sizeof(bs::ScoreSharedCore) + 4 * (size_t)(bs::COMPOSE_PART_CHUNK + 1) * 4 + 256;
+    const size_t static_smem = sizeof(bs::ScoreSharedCore) + 6 * (size_t)(2 * bs::COMPOSE_PART_CHUNK + 1) * 4 + 256;
     const size_t budget = ((size_t)228 * 1024) / 2 - 1024 - static_smem;
     int hash_slots = 0;
     if (e.comp_score) {

@@ -190,6 +190,8 @@ __global__ void k_base_side(BaseSideArgs a) {
 struct PlaceComposeArgs {
     PlaceIxArgs p;            // scaffolds as the contig set (order, counter, words, mask, text), reads, read index; w / total / pos
     ScaffoldParts sp;
+    const int32_t *part_jid;  // [P] list of the reads that cross the junction in front of a part (an entry of the extended base
+                              // set: the text around the junction, placed once), or -1: first part / probed here
     const uint2 *base_hits;   // [n_base][n_reads] (read, leftmost position) of the reads placed in a base contig (k_base_side)
     const int32_t *base_hit_di;  // [n_base][n_reads] their break 8-mers where the base contig alone decides them
     const int32_t *base_cnt;  // [n_base] how many
@@ -208,7 +210,7 @@ constexpr int COMPOSE_THREADS = BS_COMPOSE_THREADS;
 #ifdef BS_CPU_EMUL
 constexpr int COMPOSE_PART_CHUNK = 4;    // (emulation: small, so that the tests reach the chunked form)
 #else
-constexpr int COMPOSE_PART_CHUNK = 256;  // parts of a scaffold staged in shared memory at a time
+constexpr int COMPOSE_PART_CHUNK = 64;   // parts of a scaffold staged in shared memory at a time
 #endif
 constexpr uint32_t ROW_SCORED = 0x80000000u;  // flag on a row entry: the read's break has been added by the part that owns it
 
@@ -217,8 +219,12 @@ constexpr uint32_t ROW_SCORED = 0x80000000u;  // flag on a row entry: the read's
 template <bool SCORE, bool ROWS_SMEM>
 __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceComposeArgs a) {
     __shared__ int s_item, s_placed;
-    __shared__ int32_t s_pstart[COMPOSE_PART_CHUNK + 1], s_pbase[COMPOSE_PART_CHUNK], s_pcnt[COMPOSE_PART_CHUNK];
-    __shared__ int32_t s_pstep[COMPOSE_PART_CHUNK + 1];  // warp steps (32 list entries each) before part i of the staged chunk
+    // the lists a scaffold draws its placements from, two slots per staged part: [2i] the reads crossing the junction in
+    // front of part i (if that junction has a list), [2i + 1] the reads placed in part i's base contig
+    constexpr int NSRC = 2 * COMPOSE_PART_CHUNK;
+    __shared__ int32_t s_pstart[NSRC], s_pbase[NSRC], s_pcnt[NSRC];  // scaffold position of the list's position 0, list, entries
+    __shared__ int32_t s_qmax[NSRC], s_own[NSRC];  // entries at or beyond qmax are not placements here; an entry owns its read below own
+    __shared__ int32_t s_pstep[NSRC + 1];          // warp steps (32 list entries each) before a source of the staged chunk
     __shared__ ScoreSharedCore s_score;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -255,21 +261,27 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
         // (the lists of the staged parts are walked as ONE sequence of warp steps, dealt out to the warps round-robin: no
         // part leaves a block-wide loop with a mostly idle tail)
         auto stage_parts = [&](int64_t pc, int np) {
-            for (int i = tid; i <= np; i += nthr) {
+            for (int i = tid; i < np; i += nthr) {
                 const int64_t g = pc + i;
-                s_pstart[i] = g < pe ? a.sp.part_dst[g] - a.sp.part_ov[g] : 0x7fffffff;
-                if (i < np) {
-                    const int32_t b = a.sp.part_base[g];
-                    s_pbase[i] = b;
-                    s_pcnt[i] = a.base_cnt[b];
-                }
+                const int32_t b = a.sp.part_base[g], dst = a.sp.part_dst[g], ov = a.sp.part_ov[g];
+                const int32_t jid = g > ps ? a.part_jid[g] : -1;
+                s_pstart[2 * i] = dst - span;  // the junction's text starts span bases before the end of the scaffold so far
+                s_pbase[2 * i] = jid >= 0 ? jid : 0;
+                s_pcnt[2 * i] = jid >= 0 ? a.base_cnt[jid] : 0;
+                s_qmax[2 * i] = span - ov;     // ... and a crossing read starts before part i does
+                s_own[2 * i] = 0x7fffffff;
+                s_pstart[2 * i + 1] = dst - ov;
+                s_pbase[2 * i + 1] = b;
+                s_pcnt[2 * i + 1] = a.base_cnt[b];
+                s_qmax[2 * i + 1] = 0x7fffffff;
+                s_own[2 * i + 1] = g + 1 < pe ? a.sp.part_dst[g + 1] - a.sp.part_ov[g + 1] : 0x7fffffff;  // the next part's start
             }
         };
         auto stage_steps = [&](int np) {  // (after a barrier behind stage_parts; followed by one)
             if (tid == 0) {
                 int acc = 0;
-                for (int i = 0; i < np; i++) { s_pstep[i] = acc; acc += (s_pcnt[i] + 31) >> 5; }
-                s_pstep[np] = acc;
+                for (int i = 0; i < 2 * np; i++) { s_pstep[i] = acc; acc += (s_pcnt[i] + 31) >> 5; }
+                s_pstep[2 * np] = acc;
             }
         };
         const int np0 = (int)(pe - ps < COMPOSE_PART_CHUNK ? pe - ps : COMPOSE_PART_CHUNK);
@@ -292,6 +304,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
             for (int it = warp; it < nstep; it += nwarp) {
                 const int jj = it / ngroup, off = (it - jj * ngroup) * 32 + lane;
                 const int64_t j = ps + 1 + jj;
+                if (__ldg(&a.part_jid[j]) >= 0) continue;  // (warp-uniform) this junction's crossing reads come from a list
                 const int64_t e = __ldg(&a.sp.part_dst[j]);        // end of the scaffold before part j
                 const int64_t sj = e - __ldg(&a.sp.part_ov[j]);    // where part j starts as a whole
                 const int64_t p = e - span + off;
@@ -323,6 +336,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                 for (int64_t jj = 0; jj < nj; jj++, k++) {
                     if (k % nthr != tid) continue;
                     const int64_t j = ps + 1 + jj;
+                    if (a.part_jid[j] >= 0) continue;
                     const int64_t e = a.sp.part_dst[j], sj = e - a.sp.part_ov[j];
                     int64_t lo = e - (len - 1);
                     if (lo < 0) lo = 0;
@@ -346,13 +360,13 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                 stage_steps(np);
                 __syncthreads();
             }
-            const int nstep = s_pstep[np];
+            const int nstep = s_pstep[2 * np];
             for (int it = warp, i = 0; it < nstep; it += nwarp) {
                 while (it >= s_pstep[i + 1]) i++;
                 const int k = (it - s_pstep[i]) * 32 + lane;
                 if (k < s_pcnt[i]) {
                     const uint2 e = __ldg(&a.base_hits[(int64_t)s_pbase[i] * N + k]);
-                    atomicMin(&row[e.x], (uint32_t)s_pstart[i] + e.y);
+                    if (e.y < (uint32_t)s_qmax[i]) atomicMin(&row[e.x], (uint32_t)(s_pstart[i] + (int32_t)e.y));
                 }
             }
         }
@@ -390,15 +404,15 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                         stage_steps(np);
                         __syncthreads();
                     }
-                    const int nstep = s_pstep[np];
+                    const int nstep = s_pstep[2 * np];
                     for (int it = warp, i = 0; it < nstep; it += nwarp) {
                         while (it >= s_pstep[i + 1]) i++;
                         const int k = (it - s_pstep[i]) * 32 + lane;
                         if (k < s_pcnt[i]) {
                             const int64_t hb = (int64_t)s_pbase[i] * N;
                             const uint2 e = __ldg(&a.base_hits[hb + k]);
-                            const uint32_t p = (uint32_t)s_pstart[i] + e.y;
-                            if (p >= (uint32_t)s_pstart[i + 1] || row[e.x] != p) continue;
+                            const uint32_t p = (uint32_t)(s_pstart[i] + (int32_t)e.y);
+                            if (e.y >= (uint32_t)s_qmax[i] || p >= (uint32_t)s_own[i] || row[e.x] != p) continue;
                             row[e.x] = p | ROW_SCORED;
                             int32_t di = a.sc.kmer == 8 ? __ldg(&a.base_hit_di[hb + k]) : -2;
                             if (di == -2) {

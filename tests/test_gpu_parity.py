@@ -630,12 +630,14 @@ from test_scaffold_sets import SETS as SCAFFOLD_SETS  # noqa: E402
 @pytest.mark.parametrize("kw", SCAFFOLD_SETS + [dict(seed=66, length=50000, read_len=150, coverage=30, n_base=16, n_scaffolds=60, overlap=30),
                                                 dict(seed=67, length=50000, read_len=100, coverage=30, n_base=24, n_scaffolds=60, overlap=0, ragged=True)],
                          ids=lambda k: f"seed{k['seed']}")
-@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text"])
+@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text", "junctions_probed"])
 def test_scaffold_sets_vs_rescan_and_oracle(kw, mode, gpu_scorer, oracle, kmers, prob, monkeypatch):
     if mode in ("weights", "ks_from_parts_weights"):
         monkeypatch.setenv("BS_COMPOSE_SCORE", "0")
     if mode == "small_hash":
         monkeypatch.setenv("BS_COMPOSE_HASH_SLOTS", "64")
+    if mode == "junctions_probed":  # (with reads of one length the junctions are otherwise placed once per distinct pair)
+        monkeypatch.setenv("BS_COMPOSE_JUNCTIONS", "0")
     if mode == "with_text":  # (sets of ACGT only are otherwise kept as packed words alone: k_compose_words)
         monkeypatch.setenv("BS_COMPOSE_TEXT", "1")
     if mode == "global_rows":
@@ -647,12 +649,14 @@ def test_scaffold_sets_vs_rescan_and_oracle(kw, mode, gpu_scorer, oracle, kmers,
 
 
 @pytest.mark.parametrize("name,base,chains,reads,truth,kmer", SC.hand_sets(), ids=[h[0] for h in SC.hand_sets()])
-@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text"])
+@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text", "junctions_probed"])
 def test_scaffold_hand_built_sets(name, base, chains, reads, truth, kmer, mode, gpu_scorer, oracle, kmers, prob, monkeypatch):
     if mode in ("weights", "ks_from_parts_weights"):
         monkeypatch.setenv("BS_COMPOSE_SCORE", "0")
     if mode == "small_hash":
         monkeypatch.setenv("BS_COMPOSE_HASH_SLOTS", "64")
+    if mode == "junctions_probed":  # (with reads of one length the junctions are otherwise placed once per distinct pair)
+        monkeypatch.setenv("BS_COMPOSE_JUNCTIONS", "0")
     if mode == "with_text":  # (sets of ACGT only are otherwise kept as packed words alone: k_compose_words)
         monkeypatch.setenv("BS_COMPOSE_TEXT", "1")
     if mode == "global_rows":

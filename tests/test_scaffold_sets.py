@@ -72,12 +72,14 @@ SETS = [
 
 
 @pytest.mark.parametrize("kw", SETS, ids=[f"seed{k['seed']}" for k in SETS])
-@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text"])
+@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text", "junctions_probed"])
 def test_random_sets_vs_rescan_and_oracle(kw, mode, emul_scorer, emul_lib, oracle, kmers, prob, monkeypatch):
     if mode in ("weights", "ks_from_parts_weights"):
         monkeypatch.setenv("BS_COMPOSE_SCORE", "0")
     if mode == "small_hash":
         monkeypatch.setenv("BS_COMPOSE_HASH_SLOTS", "64")
+    if mode == "junctions_probed":  # (with reads of one length the junctions are otherwise placed once per distinct pair)
+        monkeypatch.setenv("BS_COMPOSE_JUNCTIONS", "0")
     if mode == "with_text":  # (sets of ACGT only are otherwise kept as packed words alone: k_compose_words)
         monkeypatch.setenv("BS_COMPOSE_TEXT", "1")
     truth, reads, sset = SC.make_set(lib_path=emul_lib, **kw)
@@ -85,12 +87,14 @@ def test_random_sets_vs_rescan_and_oracle(kw, mode, emul_scorer, emul_lib, oracl
 
 
 @pytest.mark.parametrize("name,base,chains,reads,truth,kmer", SC.hand_sets(), ids=[h[0] for h in SC.hand_sets()])
-@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text"])
+@pytest.mark.parametrize("mode", ["scored_in_place", "weights", "global_rows", "small_hash", "ks_from_parts", "ks_from_parts_weights", "with_text", "junctions_probed"])
 def test_hand_built_sets(name, base, chains, reads, truth, kmer, mode, emul_scorer, emul_lib, oracle, kmers, prob, monkeypatch):
     if mode in ("weights", "ks_from_parts_weights"):
         monkeypatch.setenv("BS_COMPOSE_SCORE", "0")
     if mode == "small_hash":
         monkeypatch.setenv("BS_COMPOSE_HASH_SLOTS", "64")
+    if mode == "junctions_probed":  # (with reads of one length the junctions are otherwise placed once per distinct pair)
+        monkeypatch.setenv("BS_COMPOSE_JUNCTIONS", "0")
     if mode == "with_text":  # (sets of ACGT only are otherwise kept as packed words alone: k_compose_words)
         monkeypatch.setenv("BS_COMPOSE_TEXT", "1")
     if mode == "global_rows":
