@@ -467,7 +467,6 @@ __global__ void __launch_bounds__(768, 2) k_ks_compose(KsComposeArgs b) {
     __shared__ int64_t s_wsum[32];
     __shared__ int64_t s_wmax[32];
     __shared__ int s_item;
-    __shared__ int64_t s_cov;
     __shared__ int32_t s_rlo[COMPOSE_PART_CHUNK], s_rn[COMPOSE_PART_CHUNK], s_glo[COMPOSE_PART_CHUNK + 1], s_gn[COMPOSE_PART_CHUNK + 1];
     __shared__ int64_t s_src[COMPOSE_PART_CHUNK];
     uint32_t *s_hist = (uint32_t *)bs_dyn_smem();
@@ -482,7 +481,7 @@ __global__ void __launch_bounds__(768, 2) k_ks_compose(KsComposeArgs b) {
     };
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_item = atomicAdd(a.work_counter, 1); s_cov = 0; }
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1);
         __syncthreads();
         if (s_item >= a.n_contigs) break;
         const int64_t c = a.order[s_item];
@@ -506,27 +505,36 @@ __global__ void __launch_bounds__(768, 2) k_ks_compose(KsComposeArgs b) {
         for (int64_t pc = ps; pc < pe; pc += COMPOSE_PART_CHUNK) {
             const int np = (int)(pe - pc < COMPOSE_PART_CHUNK ? pe - pc : COMPOSE_PART_CHUNK);
             __syncthreads();
-            if (tid == 0) {  // window ranges of the chunk's parts, in order (a handful of parts: serial)
-                int64_t cov = s_cov;
-                for (int i = 0; i < np; i++) {
-                    const int64_t g = pc + i;
-                    const int32_t bb = b.sp.part_base[g];
-                    const int64_t si = (int64_t)b.sp.part_dst[g] - b.sp.part_ov[g], b0 = b.base_off[bb], ei = si + (b.base_off[bb + 1] - b0);
-                    const int64_t gend = si < nwin ? si : nwin;  // windows that start before the part: off the scaffold
-                    s_glo[i] = (int32_t)cov;
-                    s_gn[i] = (int32_t)(gend > cov ? gend - cov : 0);
-                    if (si > cov) cov = si;
-                    int64_t last = ei - a.kmer;  // last window that lies inside the part
-                    if (last > nwin - 1) last = nwin - 1;
-                    s_rlo[i] = (int32_t)cov;
-                    s_rn[i] = (int32_t)(last >= cov ? last - cov + 1 : 0);
-                    s_src[i] = b0 + (cov - si);
-                    if (last + 1 > cov) cov = last + 1;
+            // window ranges of the chunk's parts, a thread per part: starts and ends of the parts ascend (checked at the entry
+            // point), so the first window not yet counted when part g comes up is fixed by part g - 1 alone
+            for (int i = tid; i < np; i += nthr) {
+                const int64_t g = pc + i;
+                const int32_t bb = b.sp.part_base[g];
+                const int64_t si = (int64_t)b.sp.part_dst[g] - b.sp.part_ov[g], b0 = b.base_off[bb], ei = si + (b.base_off[bb + 1] - b0);
+                int64_t cov = 0;
+                if (g > ps) {
+                    const int32_t bq = b.sp.part_base[g - 1];
+                    const int64_t sq = (int64_t)b.sp.part_dst[g - 1] - b.sp.part_ov[g - 1], eq = sq + (b.base_off[bq + 1] - b.base_off[bq]);
+                    cov = eq - a.kmer + 1 > sq ? eq - a.kmer + 1 : sq;
+                    if (cov < 0) cov = 0;
+                    if (cov > nwin) cov = nwin;
                 }
-                s_cov = cov;
-                s_glo[np] = (int32_t)cov;  // after the last part of the scaffold: what is left (nothing, for a well-formed set)
-                s_gn[np] = (int32_t)((pc + np >= pe && nwin > cov) ? nwin - cov : 0);
+                const int64_t gend = si < nwin ? si : nwin;  // windows that start before the part: off the scaffold
+                s_glo[i] = (int32_t)cov;
+                s_gn[i] = (int32_t)(gend > cov ? gend - cov : 0);
+                if (si > cov) cov = si;
+                int64_t last = ei - a.kmer;  // last window that lies inside the part
+                if (last > nwin - 1) last = nwin - 1;
+                s_rlo[i] = (int32_t)cov;
+                s_rn[i] = (int32_t)(last >= cov ? last - cov + 1 : 0);
+                s_src[i] = b0 + (cov - si);
+                if (g + 1 == pe) {  // after the last part of the scaffold: what is left (nothing, for a well-formed set)
+                    if (last + 1 > cov) cov = last + 1;
+                    s_glo[np] = (int32_t)cov;
+                    s_gn[np] = (int32_t)(nwin > cov ? nwin - cov : 0);
+                }
             }
+            if (tid == 0 && pc + np < pe) s_gn[np] = 0;
             __syncthreads();
             for (int i = 0; i < np; i++) {
                 const uint16_t *src = b.base_rank + s_src[i];
