@@ -470,14 +470,12 @@ __global__ void __launch_bounds__(768, 2) k_ks_compose(KsComposeArgs b) {
     __shared__ int32_t s_rlo[COMPOSE_PART_CHUNK], s_rn[COMPOSE_PART_CHUNK], s_glo[COMPOSE_PART_CHUNK + 1], s_gn[COMPOSE_PART_CHUNK + 1];
     __shared__ int64_t s_src[COMPOSE_PART_CHUNK];
     uint32_t *s_hist = (uint32_t *)bs_dyn_smem();
-    uint32_t *s_bm = s_hist + a.hist_words;
     const int kshift = 64 - 2 * a.kmer;
     const uint32_t kbits = keep_bits(a.kmer);
-    for (int i = tid; i < a.hist_words + a.n_ranges; i += nthr) s_hist[i] = 0;
+    for (int i = tid; i < a.hist_words; i += nthr) s_hist[i] = 0;
     auto count = [&](int32_t rk) {
         const int lw = hist_logical_word<PACKED>(rk);
         atomicAdd(&s_hist[lw + (lw >> 5)], PACKED ? 1u << (16 * (rk & 1)) : 1u);
-        atomicOr(&s_bm[lw >> 5], 1u << (lw & 31));
     };
     for (;;) {
         __syncthreads();
@@ -545,48 +543,44 @@ __global__ void __launch_bounds__(768, 2) k_ks_compose(KsComposeArgs b) {
             for (int k = tid; k < s_gn[np]; k += nthr) count_generic((int64_t)s_glo[np] + k);
         }
         __syncthreads();
-        // ---- the sweep of k_prob_dist_ks: D = sup |F_x - F_y| at every x value that is present, exact 64-bit numerators ----
+        // ---- D = sup |F_x - F_y| at every x value that is present, exact 64-bit numerators (k_prob_dist_ks's).  A scaffold
+        // fills most of the histogram, so the sweep is dense: a thread owns a run of consecutive words (an odd number of
+        // them: its neighbours' runs start in other banks), sums it, the block scans the sums, the thread walks its run
+        // again with the running count in hand and leaves it zeroed.  No bitmap of touched words is kept. ----
         const bool defined = nwin > 0 && n_y > 0;
         int64_t best = 0;
-        uint32_t carry = 0;
-        for (int r0 = 0; r0 < a.n_ranges; r0 += nthr) {
-            const int r = r0 + tid;
-            const uint32_t m = r < a.n_ranges ? s_bm[r] : 0u;
-            if (m) s_bm[r] = 0;
-            const int w0 = 33 * r;
-            uint32_t cnt_r = 0;
-            for (uint32_t mm = m; mm; mm &= mm - 1) {
-                const uint32_t w = s_hist[w0 + __ffs((int)mm) - 1];
-                cnt_r += PACKED ? (w & 0xffffu) + (w >> 16) : w;
-            }
-            uint32_t incl = cnt_r;
+        const int nwords = hist_logical_words(a.R_x, PACKED);
+        const int per = ((nwords + nthr - 1) / nthr) | 1;
+        const int w_lo = tid * per < nwords ? tid * per : nwords, w_hi = w_lo + per < nwords ? w_lo + per : nwords;
+        uint32_t cnt_t = 0;
+        for (int w = w_lo; w < w_hi; w++) {
+            const uint32_t v = s_hist[w + (w >> 5)];
+            cnt_t += PACKED ? (v & 0xffffu) + (v >> 16) : v;
+        }
+        uint32_t incl = cnt_t;
 #pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const uint32_t o = __shfl_up_sync(FULL_MASK, incl, dd);
-                if (lane >= dd) incl += o;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
-            __syncthreads();
-            uint32_t run = carry + incl - cnt_r;
-            for (int w = 0; w < nwarp; w++) {
-                if (w < warp) run += s_wsum[w];
-                carry += s_wsum[w];
-            }
-            for (uint32_t mm = m; mm; mm &= mm - 1) {
-                const int k = __ffs((int)mm) - 1;
-                const uint32_t w = s_hist[w0 + k];
-                s_hist[w0 + k] = 0;
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL_MASK, incl, dd);
+            if (lane >= dd) incl += o;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - cnt_t;
+        for (int w = 0; w < warp; w++) run += (uint32_t)s_wsum[w];
+        for (int w = w_lo; w < w_hi; w++) {
+            const int pw = w + (w >> 5);
+            const uint32_t v = s_hist[pw];
+            if (v == 0u) continue;
+            s_hist[pw] = 0;
 #pragma unroll
-                for (int h = 0; h < (PACKED ? 2 : 1); h++) {
-                    const uint32_t cnt = PACKED ? (w >> (16 * h)) & 0xffffu : w;
-                    if (cnt == 0 || !defined) continue;
-                    const int i = PACKED ? 64 * r + 2 * k + h : 32 * r + k;
-                    const int64_t d = ks_numerator(run, run + cnt, yx[i], (uint32_t)n_y, (uint32_t)nwin);
-                    run += cnt;
-                    if (d > best) best = d;
-                }
+            for (int h = 0; h < (PACKED ? 2 : 1); h++) {
+                const uint32_t cnt = PACKED ? (v >> (16 * h)) & 0xffffu : v;
+                if (cnt == 0 || !defined) continue;
+                const int i = PACKED ? 2 * w + h : w;
+                const int64_t d = ks_numerator(run, run + cnt, yx[i], (uint32_t)n_y, (uint32_t)nwin);
+                run += cnt;
+                if (d > best) best = d;
             }
-            __syncthreads();
         }
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) {
