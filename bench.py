@@ -25,7 +25,9 @@ Extra keys of the same line (measured in the same run, after the headline):
                    cfg4 (10 000 scaffolds) and cfg5 (100 Mb truth, 1e8 reads, 1e5 contigs, generated on the device);
                    each with device-resident and host-to-host timings, the cost of replicating the reads two ways,
                    a sampled oracle diff per rank and the gathered table compared with one GPU scoring everything
-                   (tools/contig_sharded_bench.py).
+                   (tools/contig_sharded_bench.py).  cfg4 also carries `compositional`: the same scaffolds given as parts
+                   of their 16 base contigs and scored from the parts (bs_score_scaffolds), sharded the same way, with
+                   its own oracle sample and every column compared with the rescan of the texts.
 """
 from __future__ import annotations
 

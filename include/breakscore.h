@@ -228,9 +228,9 @@ BS_API void bs_string_list_free(bs_string_list *l);
  * where the first overlap_i bases of part i must equal the last overlap_i bases of the text built so far (checked; it is
  * what makes every base contig a whole substring of the scaffold).  bs_score_scaffolds returns exactly what bs_score
  * returns for the materialised texts (integers bit for bit, fp64 sums to 1e-9: another summation order), but the reads
- * are placed ONCE per base contig; a scaffold's leftmost positions are then the minimum over its parts plus a probe of
- * the read index at the few positions whose match would cross a junction -- O(reads x parts + junction windows) per
- * scaffold instead of O(scaffold length) index probes -- and the break k-mers are scored from those positions directly.
+ * are placed ONCE per base contig (and once per distinct junction: the text around it); a scaffold's leftmost positions
+ * are then the minimum over the lists of its parts and junctions -- O(reads placed in its parts) per scaffold instead of
+ * O(scaffold length) index probes -- and the break k-mers and both KS statistics come from the parts as well.
  * The scaffold texts never cross PCIe (cfg-4: 50 kb of base contigs instead of 324 MB).
  * All arrays of bs_scaffold_set are HOST memory.  One segment per call.  flags: as bs_score; BS_DEVICE_CHARS applies to
  * read_chars / truth only; BS_PLACE_SCAN / BS_PLACE_TILE / BS_WEIGHTS_* are refused.  read_off == NULL: every read has
