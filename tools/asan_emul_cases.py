@@ -57,4 +57,21 @@ with B.BreakageScorer(0,'/tmp/asan/libbreakscore_emul.so') as sc2:
     sc2.set_poll(None)
     sc2.score_batch(b.read_chars,None,b.read_len,b.contig_chars,b.contig_off,b.truth_chars,b.truth_off,b.seg_read_start,b.seg_contig_start); n+=1
 del os.environ['BS_CHUNK_KB']
+# scaffold sets scored from their parts (bs_score_scaffolds): every mode of the compositional path, hand-built and random sets
+import scaffold_cases as SC
+L='/tmp/asan/libbreakscore_emul.so'
+modes=[{}, {'BS_COMPOSE_SCORE':'0'}, {'BS_COMPOSE_ROWS':'global'}, {'BS_COMPOSE_HASH_SLOTS':'64'}, {'BS_COMPOSE_TEXT':'1'}, {'BS_COMPOSE_JUNCTIONS':'0'}]
+for env in modes:
+    os.environ.update(env)
+    for flags in (SC.FULL, SC.FULL & ~B.WANT_PROB_DIST, SC.FULL | B.WANT_LEV):
+        for name,base,chains,reads,truth,kmer in SC.hand_sets():
+            SC.check_scaffolds(sc,O,kmers,prob,truth,reads,SC.hand_scaffold_set(base,chains,L),kmer=kmer,flags=flags); n+=1
+        for kw in (dict(seed=61,length=1500,read_len=40,coverage=8,n_base=6,n_scaffolds=12,overlap=9), dict(seed=63,length=1200,read_len=33,coverage=8,n_base=8,n_scaffolds=10,overlap=15,ragged=True)):
+            truth,reads,sset=SC.make_set(lib_path=L,**kw)
+            SC.check_scaffolds(sc,O,kmers,prob,truth,reads,sset,flags=flags); n+=1
+    for k in env: del os.environ[k]
+truth,reads,sset=SC.make_set(65,length=1200,read_len=50,coverage=6,n_base=5,n_scaffolds=8,overlap=11,lib_path=L)
+SC.check_scaffolds(sc,O,kmers,prob,truth,reads,sset,second=T.uniform(len(prob))); n+=1
+strings,aset=B.assemble_scaffolds([b'ACGTACGTAAGGCCTT', b'GGCCTTACGTTTTTTTTT', b'TTTTTTTTTGGA'], 7, 5, n_shuffles=50, lib_path=L)
+assert aset.texts()==strings; n+=1
 print('asan run ok', n, 'cases')
