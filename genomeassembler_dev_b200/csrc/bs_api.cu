@@ -1932,7 +1932,6 @@ static int score_batch_impl(bs_ctx *ctx, const bs_batch *b, int kmer, uint32_t f
         if (e.w_out || e.w_in || (flags & (BS_PLACE_SCAN | BS_PLACE_TILE)))
             return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: BS_WEIGHTS_* and BS_PLACE_SCAN / BS_PLACE_TILE do not apply to a scaffold set");
         if (S != 1) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: one segment per call");
-        if (comp->n_base * N > ((int64_t)1 << 31)) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: base contigs x reads = %lld exceeds 2^31 (score the texts with bs_score)", (long long)(comp->n_base * N));
         e.comp = comp;
         e.part_dst = part_dst;
         // the second table needs the position weights (its scores come from k_break_score): then the compositional kernel
@@ -2062,6 +2061,26 @@ static int score_scaffolds_impl(bs_ctx *ctx, const bs_scaffold_set *set, const c
     b.contig_chars = nullptr; b.contig_off = off.data();
     b.truth_chars = truth; b.truth_off = truth_off;
     b.seg_read_start = seg_r; b.seg_contig_start = seg_c;
+    // The lists of the from-the-parts path are [base contig][read] arrays: past 2^31 cells (a cfg-5 sized read set against
+    // hundreds of base contigs) the texts are materialised instead and scored the ordinary way -- same results.
+    int64_t max_cells = (int64_t)1 << 31;
+    if (const char *env = std::getenv("BS_COMPOSE_MAX_CELLS")) max_cells = std::atoll(env);  // tests
+    if (set->n_base * n_reads > max_cells) {
+        if (flags & (BS_WEIGHTS_OUT | BS_WEIGHTS_IN)) return fail(ctx, BS_ERR_INVALID, "bs_score_scaffolds: BS_WEIGHTS_* do not apply to a scaffold set");
+        std::vector<char> chars((size_t)off[(size_t)C] + 1);
+        std::vector<int64_t> off2((size_t)C + 1);
+        if (bs_scaffold_texts(set, chars.data(), off2.data()) != BS_OK) return fail(ctx, BS_ERR_INVALID, "%s", bs_assemble_last_error());
+        b.contig_chars = chars.data();
+        if (flags & BS_DEVICE_CHARS) {  // reads and truth are on the device: the texts go there too
+            cudaSetDevice(ctx->device);
+            BS_TRY(sync_all(ctx));  // (m_ctgs may still be read by an earlier asynchronous call)
+            BS_TRY(ensure(ctx, ctx->m_ctgs, chars.size() + 32));
+            BS_CUDA(cudaMemcpyAsync(ctx->m_ctgs.p, chars.data(), (size_t)off[(size_t)C], cudaMemcpyHostToDevice, ctx->stream));
+            BS_CUDA(cudaStreamSynchronize(ctx->stream));
+            b.contig_chars = (const char *)ctx->m_ctgs.p;
+        }
+        return score_batch_impl(ctx, &b, kmer, flags, result);
+    }
     return score_batch_impl(ctx, &b, kmer, flags, result, set, part_dst.data());
 }
 

@@ -234,7 +234,8 @@ BS_API void bs_string_list_free(bs_string_list *l);
  * The scaffold texts never cross PCIe (cfg-4: 50 kb of base contigs instead of 324 MB).
  * All arrays of bs_scaffold_set are HOST memory.  One segment per call.  flags: as bs_score; BS_DEVICE_CHARS applies to
  * read_chars / truth only; BS_PLACE_SCAN / BS_PLACE_TILE / BS_WEIGHTS_* are refused.  read_off == NULL: every read has
- * read_len bytes.  path_prob_dist_off / pos_off refer to the scaffold lengths (bs_scaffold_lengths).
+ * read_len bytes.  path_prob_dist_off / pos_off refer to the scaffold lengths (bs_scaffold_lengths).  The lists are
+ * [base contig][read] arrays: with more than 2^31 such cells the texts are materialised and scored like any contig set.
  */
 typedef struct {
     int64_t n_base;

@@ -129,3 +129,12 @@ def test_refused_flags(emul_scorer, emul_lib, kmers, prob):
     bad = SC.hand_scaffold_set([b"ACGTACGTAA", b"GTAACCGGTT"], [[(0, 0), (1, 3)]], emul_lib)
     with pytest.raises(B.BreakscoreError):
         emul_scorer.score_scaffolds(bad, [b"ACGT"], b"ACGTACGT")
+
+
+def test_large_sets_fall_back_to_the_texts(emul_scorer, emul_lib, oracle, kmers, prob, monkeypatch):
+    """more (base contig, read) cells than the lists may take: the texts are materialised and scored the ordinary way"""
+    monkeypatch.setenv("BS_COMPOSE_MAX_CELLS", "100")
+    truth, reads, sset = SC.make_set(66, length=1500, read_len=40, coverage=8, n_base=6, n_scaffolds=10, overlap=9, lib_path=emul_lib)
+    before = emul_scorer.launch_count
+    SC.check_scaffolds(emul_scorer, oracle, kmers, prob, truth, reads, sset)
+    assert emul_scorer.launch_count > before
