@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                 s_pstart[2 * i] = dst - span;  // the junction's text starts span bases before the end of the scaffold so far
                 s_pbase[2 * i] = jid >= 0 ? jid : 0;
                 s_pcnt[2 * i] = jid >= 0 ? a.base_cnt[jid] : 0;
-                s_qmax[2 * i] = span - ov;     // ... and a crossing read starts before part i does
+                s_qmax[2 * i] = span > ov ? span - ov : 0;  // ... and a crossing read starts before part i does (never, if the overlap is that long)
                 s_own[2 * i] = 0x7fffffff;
                 s_pstart[2 * i + 1] = dst - ov;
                 s_pbase[2 * i + 1] = b;

@@ -65,6 +65,7 @@ def test_scaffold_set_validation(product_lib):
 
 SETS = [
     dict(seed=61, length=3000, read_len=40, coverage=10, n_base=8, n_scaffolds=30, overlap=9),
+    dict(seed=68, length=1500, read_len=8, coverage=6, n_base=6, n_scaffolds=20, overlap=9),    # overlaps longer than the reads: nothing can cross a junction
     dict(seed=62, length=2500, read_len=100, coverage=8, n_base=6, n_scaffolds=20, overlap=0),       # cfg-4 shape: plain concatenations
     dict(seed=63, length=2000, read_len=33, coverage=10, n_base=12, n_scaffolds=25, overlap=15, ragged=True),
     dict(seed=64, length=2600, read_len=150, coverage=10, n_base=10, n_scaffolds=20, overlap=20, mutate=0.5),
