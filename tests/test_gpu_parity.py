@@ -715,3 +715,10 @@ def test_cfg4_full_size_from_parts(gpu_scorer, kmers, prob):
         for k in got:
             if k != "sequence":
                 assert np.array_equal(got[k], again[k], equal_nan=True), (it, k)
+
+
+@pytest.mark.parametrize("mode", ["scored_in_place", "ks_from_parts"])
+def test_scaffold_longer_than_65535_windows(mode, gpu_scorer, oracle, kmers, prob):
+    from test_scaffold_sets import long_scaffold_case
+    truth, reads, sset = long_scaffold_case()
+    SC.check_scaffolds(gpu_scorer, oracle, kmers, prob, truth, reads, sset, flags=SC.mode_flags(mode) & ~B.WANT_POS & ~B.WANT_HIST)

@@ -139,3 +139,21 @@ def test_large_sets_fall_back_to_the_texts(emul_scorer, emul_lib, oracle, kmers,
     before = emul_scorer.launch_count
     SC.check_scaffolds(emul_scorer, oracle, kmers, prob, truth, reads, sset)
     assert emul_scorer.launch_count > before
+
+
+def long_scaffold_case(lib_path=None):
+    """one scaffold of more than 65 536 windows (the rank histogram then keeps 32-bit counters) beside short ones"""
+    from genomeassembler_dev_b200 import synth
+    rng = np.random.default_rng(70)
+    truth = synth.codes_to_ascii(synth.random_truth_codes(rng, 75_000))
+    base = [truth[0:26_000].tobytes(), truth[26_000:50_000].tobytes(), truth[50_000:75_000].tobytes(), truth[100:400].tobytes()]
+    starts = rng.integers(0, 75_000 - 60, size=300)
+    reads = [truth[s:s + 60].tobytes() for s in starts] + [truth[25_990:26_050].tobytes(), truth[49_960:50_020].tobytes()]
+    sset = SC.hand_scaffold_set(base, [[(0, 0), (1, 0), (2, 0)], [(3, 0), (1, 0)], [(2, 0)]], lib_path)
+    return truth.tobytes(), reads, sset
+
+
+@pytest.mark.parametrize("mode", ["scored_in_place", "ks_from_parts"])
+def test_scaffold_longer_than_65535_windows(mode, emul_scorer, emul_lib, oracle, kmers, prob):
+    truth, reads, sset = long_scaffold_case(emul_lib)
+    SC.check_scaffolds(emul_scorer, oracle, kmers, prob, truth, reads, sset, flags=SC.mode_flags(mode) & ~B.WANT_POS & ~B.WANT_HIST)
