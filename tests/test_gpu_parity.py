@@ -722,3 +722,37 @@ def test_scaffold_longer_than_65535_windows(mode, gpu_scorer, oracle, kmers, pro
     from test_scaffold_sets import long_scaffold_case
     truth, reads, sset = long_scaffold_case()
     SC.check_scaffolds(gpu_scorer, oracle, kmers, prob, truth, reads, sset, flags=SC.mode_flags(mode) & ~B.WANT_POS & ~B.WANT_HIST)
+
+
+@pytest.mark.parametrize("fallback", [False, True], ids=["from_parts", "texts_materialised"])
+def test_scaffolds_device_resident(fallback, gpu_scorer, kmers, prob, monkeypatch):
+    """bs_score_scaffolds with reads, truth and results on the device (what bench.py times), also through the fall-back for
+    sets with too many (base contig, read) cells, against the host-buffer call of the same set"""
+    import ctypes as C
+    import torch
+    if fallback:
+        monkeypatch.setenv("BS_COMPOSE_MAX_CELLS", "1000")
+    truth, reads, sset = SC.make_set(69, length=20000, read_len=100, coverage=20, n_base=10, n_scaffolds=50, overlap=12)
+    gpu_scorer.set_table(kmers, prob)
+    flags = B.WANT_KS | B.WANT_STARTPOS
+    want = gpu_scorer.score_scaffolds(sset, reads, truth, flags=flags)
+    n = len(sset)
+    rd = torch.from_numpy(np.frombuffer(b"".join(reads), np.uint8).copy()).cuda()
+    tr = torch.from_numpy(np.frombuffer(truth, np.uint8).copy()).cuda()
+    i32 = torch.zeros(4, n, dtype=torch.int32, device="cuda")
+    f64 = torch.zeros(5, n, dtype=torch.float64, device="cuda")
+    r = B._Result()
+    r.sequence_len, r.kmer_breaks, r.path_prob_dist_startpos, r.lev_dist_vs_true = [i32[i].data_ptr() for i in range(4)]
+    (r.bp_score, r.bp_score_norm_by_break_freqs, r.bp_score_norm_by_len, r.ks_stat_prob_dist,
+     r.ks_stat_path_freq) = [f64[i].data_ptr() for i in range(5)]
+    st = sset.c_struct()
+    for _ in range(2):
+        gpu_scorer._check(gpu_scorer._lib.bs_score_scaffolds(gpu_scorer._ctx, C.byref(st), rd.data_ptr(), None, len(reads), 100, tr.data_ptr(),
+                                                             len(truth), 8, flags | B.DEVICE_CHARS | B.DEVICE_RESULT, C.byref(r)))
+    gpu_scorer.synchronize()
+    torch.cuda.synchronize()
+    for j, k in enumerate(("sequence_len", "kmer_breaks", "path_prob_dist_startpos")):
+        assert np.array_equal(i32[j].cpu().numpy(), want[k]), k
+    assert np.array_equal(f64[0].cpu().numpy(), want["bp_score"])
+    assert np.array_equal(f64[3].cpu().numpy(), want["ks_stat_prob_dist"], equal_nan=True)
+    assert np.array_equal(f64[4].cpu().numpy(), want["ks_stat_path_freq"], equal_nan=True)
