@@ -1127,7 +1127,7 @@ int ChunkRun::place_composed() {
         const bool ranks = ks_compose();
         ba.win = ranks ? (const bs::WinEntry *)ctx->ks.win.p : nullptr; ba.rank_zero = ctx->ks.rank_zero;
         ba.base_rank = ranks ? (uint16_t *)ws.base_rank.p : nullptr;
-        BS_LAUNCH(bs::k_base_side, (unsigned)n_ext, kScoreThreads, kScoreThreads * 8 + 16, st, ba);
+        BS_LAUNCH(bs::k_base_side, (unsigned)n_ext, kScoreThreads, 0, st, ba);
         ctx->launches++;
     }
     bs::PlaceComposeArgs ca;

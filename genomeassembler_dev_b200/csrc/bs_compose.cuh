@@ -143,25 +143,34 @@ struct BaseSideArgs {
     uint16_t *base_rank;       // [sum L_b] out: rank of the window that starts at a base contig position (rank_zero: a base outside ACGT)
 };
 
-// one block per base contig: ordered compaction of its row of leftmost positions (block scan per chunk of reads), so
+// one block per base contig: ordered compaction of its row of leftmost positions (warp ballots per round of reads), so
 // that the list -- and with it which thread of k_place_compose adds which read's probability -- is the same in every run
 __global__ void k_base_side(BaseSideArgs a) {
-    int64_t *s_scan = (int64_t *)bs_dyn_smem();
+    __shared__ int s_wcnt[32];
     __shared__ int64_t s_base;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     const int64_t b = blockIdx.x, N = a.n_reads;
     const int32_t *row = a.base_pos + b * N;
     const int64_t Lb = a.base_off[b + 1] - a.base_off[b];
     const uint64_t *bw = a.base_words + a.base_woff[b];
     const uint32_t *bm = a.base_mask + a.base_woff[b];
     if (tid == 0) s_base = 0;
+    __syncthreads();
+    // blockDim reads per round: a ballot per warp gives the lane's place among its warp's placed reads, the warps'
+    // counts (shared memory) the warp's place in the round (the loop bounds are block-uniform: every lane votes)
     for (int64_t r0 = 0; r0 < N; r0 += nthr) {
         const int64_t r = r0 + tid;
         const int32_t q = r < N ? row[r] : -1;
-        int64_t total;
-        const int64_t at = block_exclusive_scan(q >= 0 ? 1 : 0, s_scan, &total);  // (barriers inside: s_base is visible)
+        const unsigned m = __ballot_sync(FULL_MASK, q >= 0);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < nwarp; w++) {
+            if (w < warp) before += s_wcnt[w];
+            total += s_wcnt[w];
+        }
         if (q >= 0) {
-            const int64_t o = b * N + s_base + at;
+            const int64_t o = b * N + s_base + before + __popc(m & ((1u << lane) - 1u));
             a.hits[o] = make_uint2((uint32_t)r, (uint32_t)q);
             int32_t di = -2;
             if (a.kmer == 8 && q >= 4 && (int64_t)q + 4 <= Lb) di = dense_index_at(bw, bm, (int64_t)q - 4, 8);
