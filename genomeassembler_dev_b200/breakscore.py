@@ -223,6 +223,16 @@ class ScaffoldSet:
     def __len__(self):
         return len(self.part_start) - 1
 
+    def subset(self, index) -> "ScaffoldSet":
+        """the scaffolds `index` (ascending input indices) as a set of their own over the same base contigs: what one
+        rank scores when a set is sharded over GPUs (sharding.score_scaffolds_sharded)"""
+        index = np.asarray(index, dtype=np.int64)
+        counts = (self.part_start[1:] - self.part_start[:-1])[index]
+        start = np.zeros(len(index) + 1, np.int64)
+        np.cumsum(counts, out=start[1:])
+        pick = np.concatenate([np.arange(self.part_start[i], self.part_start[i + 1]) for i in index]) if len(index) else np.zeros(0, np.int64)
+        return ScaffoldSet(self.base_contigs, start, self.part_base[pick], self.part_overlap[pick], self._lib_path)
+
     def c_struct(self) -> _ScaffoldSet:
         return _ScaffoldSet(len(self.base_contigs), self.base_chars.ctypes.data, self.base_off.ctypes.data, len(self),
                             self.part_start.ctypes.data, self.part_base.ctypes.data, self.part_overlap.ctypes.data)

@@ -671,7 +671,9 @@ int ChunkRun::prepare() {
                 std::unordered_map<uint64_t, int32_t> seen;
                 const bool direct = n_base <= 2048;
                 std::vector<int32_t> pair_jid(direct ? (size_t)(n_base * n_base) : 0, -1), pair_ov(direct ? (size_t)(n_base * n_base) : 0, 0);
-                const int64_t max_junc = std::max<int64_t>(0, std::min<int64_t>(n_parts, ((int64_t)1 << 28) / std::max<int64_t>(N, 1)) - n_base);
+                // (bounded by memory alone -- the lists are [contig][read] arrays -- so that which junctions have a list does not
+                // depend on how many scaffolds travel in the call)
+                const int64_t max_junc = std::max<int64_t>(0, ((int64_t)1 << 28) / std::max<int64_t>(N, 1) - n_base);
                 for (int64_t c = 0; c < cp->n_scaffolds; c++)
                     for (int64_t g = cp->scaffold_part_start[c] + 1; g < cp->scaffold_part_start[c + 1]; g++) {
                         const int64_t bp = cp->part_base[g - 1], bn = cp->part_base[g], ov = cp->part_overlap[g];
@@ -1143,7 +1145,7 @@ int ChunkRun::place_composed() {
     // place so that KS-B never needs the global scratch rows; then the block's row of leftmost positions per read, while two
     // blocks per SM fit -- else the row lives in global memory (L2)
     // (an SM holds 228 KB of shared memory, 1 KB of it reserved per resident block; the kernel's static part goes off as well)
-    const size_t static_smem = sizeof(bs::ScoreSharedCore) + 6 * (size_t)(2 * bs::COMPOSE_PART_CHUNK + 1) * 4 + 256;
+    const size_t static_smem = sizeof(bs::ScoreSharedCore) + 7 * (size_t)(2 * bs::COMPOSE_PART_CHUNK + 1) * 4 + 256;
     const size_t budget = ((size_t)228 * 1024) / 2 - 1024 - static_smem;
     int hash_slots = 0;
     if (e.comp_score) {

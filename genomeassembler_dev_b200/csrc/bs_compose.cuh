@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
     __shared__ int32_t s_pstart[NSRC], s_pbase[NSRC], s_pcnt[NSRC];  // scaffold position of the list's position 0, list, entries
     __shared__ int32_t s_qmax[NSRC], s_own[NSRC];  // entries at or beyond qmax are not placements here; an entry owns its read below own
     __shared__ int32_t s_pstep[NSRC + 1];          // warp steps (32 list entries each) before a source of the staged chunk
+    __shared__ int32_t s_qstep[COMPOSE_PART_CHUNK + 1];  // ... counting the parts' lists alone (the scoring walk)
     __shared__ ScoreSharedCore s_score;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
@@ -288,9 +289,11 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
         };
         auto stage_steps = [&](int np) {  // (after a barrier behind stage_parts; followed by one)
             if (tid == 0) {
-                int acc = 0;
+                int acc = 0, accp = 0;
                 for (int i = 0; i < 2 * np; i++) { s_pstep[i] = acc; acc += (s_pcnt[i] + 31) >> 5; }
                 s_pstep[2 * np] = acc;
+                for (int i = 0; i < np; i++) { s_qstep[i] = accp; accp += (s_pcnt[2 * i + 1] + 31) >> 5; }
+                s_qstep[np] = accp;
             }
         };
         const int np0 = (int)(pe - ps < COMPOSE_PART_CHUNK ? pe - ps : COMPOSE_PART_CHUNK);
@@ -404,6 +407,9 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                 // can only give the same position inside their overlap, where the later part's list holds the read as
                 // well): every read is added by exactly one thread, always the same one, whatever the timing.  The break
                 // 8-mer of a placement inside its base contig came with the list; the others are read off the scaffold.
+                // Which thread adds which read depends on the scaffold's parts alone -- not on the other scaffolds of the
+                // call, nor on which junctions have lists (those reads are added in (2), by read id): a scaffold's sums are
+                // the same bits in any subset of the set, on any number of GPUs.
                 for (int64_t pc = ps; pc < pe; pc += COMPOSE_PART_CHUNK) {
                     const int np = (int)(pe - pc < COMPOSE_PART_CHUNK ? pe - pc : COMPOSE_PART_CHUNK);
                     if (pe - ps > COMPOSE_PART_CHUNK) {  // (else the only chunk is still staged)
@@ -413,15 +419,16 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                         stage_steps(np);
                         __syncthreads();
                     }
-                    const int nstep = s_pstep[2 * np];
-                    for (int it = warp, i = 0; it < nstep; it += nwarp) {
-                        while (it >= s_pstep[i + 1]) i++;
-                        const int k = (it - s_pstep[i]) * 32 + lane;
+                    const int nstep = s_qstep[np];
+                    for (int it = warp, ip = 0; it < nstep; it += nwarp) {
+                        while (it >= s_qstep[ip + 1]) ip++;
+                        const int i = 2 * ip + 1;  // the part's slot
+                        const int k = (it - s_qstep[ip]) * 32 + lane;
                         if (k < s_pcnt[i]) {
                             const int64_t hb = (int64_t)s_pbase[i] * N;
                             const uint2 e = __ldg(&a.base_hits[hb + k]);
                             const uint32_t p = (uint32_t)(s_pstart[i] + (int32_t)e.y);
-                            if (e.y >= (uint32_t)s_qmax[i] || p >= (uint32_t)s_own[i] || row[e.x] != p) continue;
+                            if (p >= (uint32_t)s_own[i] || row[e.x] != p) continue;
                             row[e.x] = p | ROW_SCORED;
                             int32_t di = a.sc.kmer == 8 ? __ldg(&a.base_hit_di[hb + k]) : -2;
                             if (di == -2) {

@@ -6,7 +6,8 @@ fixed-width per-contig records are gathered afterwards.
 
 * many segments (cfg-2 study): contiguous runs of whole segments balanced by read x contig work;
 * one segment, many contigs (cfg-4 scaffold sets, cfg-5): contigs dealt out longest-first (LPT) with
-  the segment's reads replicated to every rank.
+  the segment's reads replicated to every rank; a scaffold set given as parts of base contigs the same way, every rank
+  scoring its share from the parts.
 """
 from __future__ import annotations
 
@@ -139,6 +140,43 @@ def score_contigs_sharded(scorer, path, sequencing_reads, true_solution, kmer=8,
     back[order] = got
     out = unpack_records(back)
     owner = np.empty(len(path), dtype=np.int32)
+    for r, p in enumerate(parts):
+        owner[p] = r
+    out["owner"] = owner
+    return out, local_info
+
+
+def score_scaffolds_sharded(scorer, scaffolds, sequencing_reads, true_solution, kmer=8, flags=None, group=None, dst: int = 0):
+    """:func:`score_contigs_sharded` for a candidate set given as PARTS of base contigs (``breakscore.ScaffoldSet``, what
+    ``assemble_scaffolds`` returns): the scaffolds are dealt out longest-first, every rank gets all base contigs and the
+    whole read set and scores its share from the parts (``bs_score_scaffolds``: reads placed once per base contig on
+    every rank -- that part is replicated, it is the small one), records gathered into input order on rank `dst`.
+    Bit-identical to one rank scoring the whole set (the per-scaffold reductions have a fixed order)."""
+    import torch.distributed as dist
+
+    from . import breakscore
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lens = scaffolds.lengths()
+    parts = shard_contigs_lpt(lens, world)
+    mine = parts[rank]
+    counts = [len(p) for p in parts]
+    if flags is None:
+        flags = breakscore.WANT_KS | breakscore.WANT_STARTPOS
+    if len(mine):
+        local = scorer.score_scaffolds(scaffolds.subset(mine), sequencing_reads, true_solution, kmer=kmer, flags=flags)
+    else:
+        local = {k: np.zeros(0) for k in RECORD_F64 + RECORD_I32}
+    rec = pack_records(local, len(mine))
+    got = gather_records(rec, counts, group=group, dst=dst)
+    local_info = {"local": local, "local_index": mine}
+    if rank != dst:
+        return None, local_info
+    order = np.concatenate(parts) if len(lens) else np.zeros(0, np.int64)
+    back = np.empty((len(lens), rec.shape[1]), dtype=np.float64)
+    back[order] = got
+    out = unpack_records(back)
+    owner = np.empty(len(lens), dtype=np.int32)
     for r, p in enumerate(parts):
         owner[p] = r
     out["owner"] = owner

@@ -140,3 +140,24 @@ def hand_scaffold_set(base, chains, lib_path=None):
             part_ov.append(ov)
         part_start.append(len(part_base))
     return B.ScaffoldSet(base, part_start, part_base, part_ov, lib_path)
+
+
+def check_set_independence(scorer, kmers, prob, monkeypatch, lib_path=None, **kw):
+    """a scaffold's record is the same bits whatever else travels in the call (any subset of the set: what a rank of a
+    sharded job scores) and whether or not its junctions have lists"""
+    from genomeassembler_dev_b200 import sharding
+    truth, reads, sset = make_set(lib_path=lib_path, **kw)
+    scorer.set_table(kmers, prob)
+    flags = B.WANT_KS | B.WANT_STARTPOS
+    whole = scorer.score_scaffolds(sset, reads, truth, flags=flags)
+    keys = sharding.RECORD_F64 + sharding.RECORD_I32
+    for world in (2, 3, 5):
+        for part in sharding.shard_contigs_lpt(sset.lengths(), world):
+            if len(part):
+                loc = scorer.score_scaffolds(sset.subset(part), reads, truth, flags=flags)
+                for k in keys:
+                    assert np.array_equal(loc[k], whole[k][part], equal_nan=True), (world, k)
+    monkeypatch.setenv("BS_COMPOSE_JUNCTIONS", "0")
+    probed = scorer.score_scaffolds(sset, reads, truth, flags=flags)
+    for k in keys:
+        assert np.array_equal(probed[k], whole[k], equal_nan=True), ("junctions probed", k)

@@ -756,3 +756,8 @@ def test_scaffolds_device_resident(fallback, gpu_scorer, kmers, prob, monkeypatc
     assert np.array_equal(f64[0].cpu().numpy(), want["bp_score"])
     assert np.array_equal(f64[3].cpu().numpy(), want["ks_stat_prob_dist"], equal_nan=True)
     assert np.array_equal(f64[4].cpu().numpy(), want["ks_stat_path_freq"], equal_nan=True)
+
+
+def test_a_scaffolds_record_does_not_depend_on_the_rest_of_the_set(gpu_scorer, kmers, prob, monkeypatch):
+    SC.check_set_independence(gpu_scorer, kmers, prob, monkeypatch, seed=72, length=50000, read_len=150, coverage=30, n_base=16,
+                              n_scaffolds=80, overlap=20)

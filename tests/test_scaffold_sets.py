@@ -161,3 +161,8 @@ def long_scaffold_case(lib_path=None):
 def test_scaffold_longer_than_65535_windows(mode, emul_scorer, emul_lib, oracle, kmers, prob):
     truth, reads, sset = long_scaffold_case(emul_lib)
     SC.check_scaffolds(emul_scorer, oracle, kmers, prob, truth, reads, sset, flags=SC.mode_flags(mode) & ~B.WANT_POS & ~B.WANT_HIST)
+
+
+def test_a_scaffolds_record_does_not_depend_on_the_rest_of_the_set(emul_scorer, emul_lib, kmers, prob, monkeypatch):
+    SC.check_set_independence(emul_scorer, kmers, prob, monkeypatch, lib_path=emul_lib, seed=71, length=2500, read_len=40, coverage=8,
+                              n_base=7, n_scaffolds=11, overlap=9)

@@ -165,3 +165,49 @@ def test_read_sharding_weights_all_reduced(world, emul_lib):
         p.join(timeout=180)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _scaffold_worker(rank, world, port, q, emul_lib):
+    """a scaffold set given as parts, sharded like contigs: every rank scores its scaffolds from the parts (kernels under
+    the CPU emulation); the gathered table equals one rank scoring the whole set, bit for bit"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import scaffold_cases as SC
+    from genomeassembler_dev_b200 import breakscore
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kmers, prob = tables.all_kmer_strings(), tables.normalised(tables.load_raw())
+    truth, reads, sset = SC.make_set(71, length=2500, read_len=40, coverage=8, n_base=7, n_scaffolds=11, overlap=9, lib_path=emul_lib)
+    sc = breakscore.BreakageScorer(0, emul_lib)
+    sc.set_table(kmers, prob)
+    flags = breakscore.WANT_KS | breakscore.WANT_STARTPOS
+    got, info = sharding.score_scaffolds_sharded(sc, sset, reads, truth, kmer=8, flags=flags)
+    ok = len(info["local_index"]) == len(info["local"]["kmer_breaks"])
+    if rank == 0:
+        whole = sc.score_scaffolds(sset, reads, truth, kmer=8, flags=flags)
+        texts = sc.score(sset.texts(), reads, truth, kmer=8, flags=flags)
+        for k in sharding.RECORD_F64 + sharding.RECORD_I32:
+            ok = ok and bool(np.array_equal(np.asarray(got[k], dtype=np.float64), np.asarray(whole[k], dtype=np.float64), equal_nan=True))
+        for k in sharding.RECORD_I32 + ("ks_stat_prob_dist",):
+            ok = ok and bool(np.array_equal(np.asarray(got[k], dtype=np.float64), np.asarray(texts[k], dtype=np.float64), equal_nan=True))
+        ok = ok and sorted(set(got["owner"].tolist())) == list(range(min(world, len(sset))))
+        q.put(ok)
+    else:
+        ok = ok and got is None
+        assert ok
+    sc.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_scaffold_set_sharding(world, emul_lib):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_scaffold_worker, args=(r, world, port, q, emul_lib)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
