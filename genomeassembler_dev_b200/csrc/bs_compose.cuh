@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
             }
             // reads outside the index (a byte outside ACGT in the seed): text comparison in every junction window
             int64_t k = 0;
-            for (uint32_t q = cc ? a.p.ix.odd_head[s] : 0u; q != 0;) {  // (without a text: such a read matches nowhere)
+            for (uint32_t q = a.p.ix.odd_head[s]; q != 0;) {
                 const int64_t n = (int64_t)q - 1;
                 q = a.p.ix.next[n].x;
                 const int len = read_length(a.p.reads, n);
@@ -355,7 +355,11 @@ __global__ void __launch_bounds__(COMPOSE_THREADS, 2) k_place_compose(PlaceCompo
                     int64_t hi = sj - 1 + len;  // one past the last byte a match starting before sj can cover
                     if (hi > L) hi = L;
                     if (hi - lo < len) continue;
-                    const int64_t f = find_bytes(cc + lo, hi - lo, rc, len);
+                    int64_t f = -1;
+                    if (cc) f = find_bytes(cc + lo, hi - lo, rc, len);
+                    else  // (no text: the scaffold is ACGT only; the read's bytes against the bases decoded from the words)
+                        for (int64_t t = 0; t + len <= hi - lo && f < 0; t++)
+                            if (match_text_packed(gw, gm, lo + t, rc, len)) f = t;
                     if (f >= 0) atomicMin(&row[n - r0], (uint32_t)(lo + f));
                 }
             }

@@ -220,12 +220,26 @@ __device__ __forceinline__ int64_t find_bytes(const uint8_t *cc, int64_t L, cons
     return -1;
 }
 
+// A contig of ACGT only that is kept as packed words alone (bs_compose.cuh): the bytes of a read against the bases decoded
+// from the words.  For reads whose flag is set -- the flag is conservative: it also marks a read that sits next to a byte
+// outside ACGT in the read buffer, and such a read can match.
+__device__ __forceinline__ bool match_text_packed(const uint64_t *gw, const uint32_t *gm, int64_t p, const uint8_t *rc, int len) {
+    for (int i = 0; i < len; i++) {
+        const int64_t q = p + i;
+        const int o = (int)(q & 31);
+        if ((__ldg(&gm[q >> 5]) >> (31 - o)) & 1u) return false;  // (a masked position: past the end)
+        const uint32_t code = (uint32_t)(__ldg(&gw[q >> 5]) >> (62 - 2 * o)) & 3u;
+        if (rc[i] != (uint8_t)("ACGT"[code])) return false;
+    }
+    return true;
+}
+
 // does read n (length len, packed words rw) equal the contig at position p?
 __device__ __forceinline__ bool verify_at(const PlaceIxArgs &a, const uint64_t *gw, const uint32_t *gm, const uint8_t *cc,
                                           int64_t p, int64_t n, int len, uint64_t w0) {
     if (a.reads.flags[n] & 1) {  // bytes outside ACGT somewhere in (or next to) the read: compare the text
-        if (cc == nullptr) return false;  // (bs_compose.cuh: a contig of ACGT only, kept without its text)
         const uint8_t *rc = a.reads.chars + read_begin(a.reads, n);
+        if (cc == nullptr) return match_text_packed(gw, gm, p, rc, len);  // (bs_compose.cuh: a contig of ACGT only, kept without its text)
         for (int i = 0; i < len; i++)
             if (cc[p + i] != rc[i]) return false;
         return true;

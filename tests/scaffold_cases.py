@@ -129,6 +129,11 @@ def hand_sets():
     # one break k-mer more than CC_DENSE (1024) times in a scaffold: the running tallies of KS-B give way to the sweep
     out.append(("one_kmer_a_thousand_times", [b"A" * 300, b"ACGT" * 10 + b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"],
                 [[(0, 0), (1, 0)], [(1, 0), (0, 0)], [(1, 0)]], [b"A" * 20] * 1100 + [b"AAAC", b"CGTA", b"GTAAAAAA"], b"A" * 300 + b"ACGT" * 10, 8))
+    # a read of ACGT only between reads with Ns (the packers flag it as well: "next to a byte outside ACGT"), crossing several
+    # junctions of a set that is kept as packed words alone
+    out.append(("flagged_pure_read_crossing_short_parts", [b"CTGGGCG"], [[(0, 0)], [(0, 0)] * 5, [(0, 0)] * 4],
+                [b"AATTNTGGTGCGCCNATANANNGNCGAGC", b"GCGCTGGGCGCTGGGCGCTGGGCGCTGGG", b"NCTNTTACATGCCGGCGTTTGNTTNAANN"],
+                b"GANNACGATTATCTGGGCGTGANNNT", 8))
     return out
 
 
